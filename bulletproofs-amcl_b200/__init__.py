@@ -1,0 +1,12 @@
+"""bulletproofs-amcl_b200 — B200-native G1 MSM / inner-product-argument hot path.
+
+Host-side Python binding (ctypes) over the C ABI in include/bpgpu.h.  The compute lives in
+`libbpgpu.so` (hand-written sm_100a CUDA, csrc/); this package only marshals bytes.
+There is no CPU fallback: importing works anywhere (so the ABI can be inspected), but creating
+a context without the built library or without a CUDA device raises.
+"""
+from .binding import (BLS12_381, BN254, BpgpuError, Context, DevicePoints, DeviceScalars, build_library, lib,
+                      library_path)
+
+__all__ = ["BLS12_381", "BN254", "BpgpuError", "Context", "DevicePoints", "DeviceScalars", "build_library", "lib",
+           "library_path"]

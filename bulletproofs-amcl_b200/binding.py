@@ -1,0 +1,210 @@
+"""ctypes binding of include/bpgpu.h.  Byte conventions are the ABI's: scalars are
+FieldElement::to_bytes() (MODBYTES big endian), points are G1::to_bytes()[1:] (X||Y)."""
+import ctypes
+import os
+import subprocess
+
+BLS12_381 = 0
+BN254 = 1
+
+_HERE = os.path.dirname(os.path.abspath(__file__))
+_LIB = None
+
+# (name, restype, argtypes) for every symbol include/bpgpu.h declares
+_c = ctypes
+_VP, _SZ, _U8P, _INT = _c.c_void_p, _c.c_size_t, _c.c_char_p, _c.c_int
+SYMBOLS = [
+    ("bpgpu_strerror", _c.c_char_p, [_INT]),
+    ("bpgpu_modbytes", _INT, [_INT]),
+    ("bpgpu_device_count", _INT, []),
+    ("bpgpu_ctx_create", _INT, [_INT, _INT, _c.POINTER(_VP)]),
+    ("bpgpu_ctx_destroy", None, [_VP]),
+    ("bpgpu_ctx_stream", _VP, [_VP]),
+    ("bpgpu_ctx_sync", _INT, [_VP]),
+    ("bpgpu_ctx_curve", _INT, [_VP]),
+    ("bpgpu_ctx_launches", _c.c_uint64, [_VP]),
+    ("bpgpu_host_alloc", _VP, [_SZ]),
+    ("bpgpu_host_free", None, [_VP]),
+    ("bpgpu_points_upload", _INT, [_VP, _VP, _SZ, _c.POINTER(_VP)]),
+    ("bpgpu_points_download", _INT, [_VP, _VP, _SZ, _SZ, _VP]),
+    ("bpgpu_points_len", _SZ, [_VP]),
+    ("bpgpu_points_free", None, [_VP]),
+    ("bpgpu_scalars_upload", _INT, [_VP, _VP, _SZ, _c.POINTER(_VP)]),
+    ("bpgpu_scalars_download", _INT, [_VP, _VP, _SZ, _SZ, _VP]),
+    ("bpgpu_scalars_len", _SZ, [_VP]),
+    ("bpgpu_scalars_free", None, [_VP]),
+    ("bpgpu_msm", _INT, [_VP, _VP, _SZ, _SZ, _VP, _VP]),
+    ("bpgpu_msm_device", _INT, [_VP, _VP, _SZ, _SZ, _VP, _SZ, _VP]),
+    ("bpgpu_msm_refs", _INT, [_VP, _VP, _VP, _SZ, _VP]),
+    ("bpgpu_msm_window_bits", _INT, [_SZ]),
+    ("bpgpu_selftest_field", _INT, [_VP, _INT, _INT, _VP, _VP, _SZ, _VP]),
+    ("bpgpu_selftest_group", _INT, [_VP, _INT, _VP, _VP, _VP, _SZ, _VP]),
+    ("bpgpu_int_pipe_bench", _INT, [_VP, _INT, _INT, _c.POINTER(_c.c_double), _c.POINTER(_c.c_double)]),
+]
+
+
+class BpgpuError(RuntimeError):
+    def __init__(self, code, what=""):
+        self.code = code
+        msg = lib().bpgpu_strerror(code).decode() if _LIB is not None else str(code)
+        super().__init__(f"{what}: {msg} ({code})")
+
+
+def library_path():
+    return os.path.join(_HERE, "libbpgpu.so")
+
+
+def build_library(verbose=False):
+    """Compile csrc/ into libbpgpu.so for sm_100a (nvcc cross-compiles without a GPU)."""
+    r = subprocess.run(["make", "-C", os.path.join(_HERE, "csrc"), "-j4"], capture_output=True, text=True)
+    if verbose or r.returncode:
+        print(r.stdout[-4000:], r.stderr[-4000:])
+    if r.returncode:
+        raise RuntimeError("building libbpgpu.so failed")
+    return library_path()
+
+
+def lib():
+    """Load libbpgpu.so; raises loudly if it has not been built (no fallback path exists)."""
+    global _LIB
+    if _LIB is None:
+        path = library_path()
+        if not os.path.exists(path):
+            raise RuntimeError(f"{path} is missing: run __graft_entry__.build() (there is no CPU fallback)")
+        L = ctypes.CDLL(path)
+        for name, res, args in SYMBOLS:
+            fn = getattr(L, name)
+            fn.restype = res
+            fn.argtypes = args
+        _LIB = L
+    return _LIB
+
+
+def _buf(b):
+    """bytes/bytearray/memoryview/int address -> something ctypes accepts as void*."""
+    if isinstance(b, int):
+        return ctypes.c_void_p(b)
+    if isinstance(b, (bytes, bytearray)):
+        return ctypes.cast(ctypes.c_char_p(bytes(b)) if isinstance(b, bytearray) else ctypes.c_char_p(b), ctypes.c_void_p)
+    return ctypes.cast(ctypes.c_char_p(bytes(b)), ctypes.c_void_p)
+
+
+class DevicePoints:
+    def __init__(self, ctx, handle):
+        self.ctx, self.handle = ctx, handle
+
+    def __len__(self):
+        return lib().bpgpu_points_len(self.handle)
+
+    def download(self, off=0, n=None):
+        n = len(self) - off if n is None else n
+        out = ctypes.create_string_buffer(max(1, n * 2 * self.ctx.modbytes))
+        self.ctx._check(lib().bpgpu_points_download(self.ctx.handle, self.handle, off, n, out), "points_download")
+        return out.raw[:n * 2 * self.ctx.modbytes]
+
+    def free(self):
+        if self.handle:
+            lib().bpgpu_points_free(self.handle)
+            self.handle = None
+
+
+class DeviceScalars:
+    def __init__(self, ctx, handle):
+        self.ctx, self.handle = ctx, handle
+
+    def __len__(self):
+        return lib().bpgpu_scalars_len(self.handle)
+
+    def download(self, off=0, n=None):
+        n = len(self) - off if n is None else n
+        out = ctypes.create_string_buffer(max(1, n * self.ctx.modbytes))
+        self.ctx._check(lib().bpgpu_scalars_download(self.ctx.handle, self.handle, off, n, out), "scalars_download")
+        return out.raw[:n * self.ctx.modbytes]
+
+    def free(self):
+        if self.handle:
+            lib().bpgpu_scalars_free(self.handle)
+            self.handle = None
+
+
+class Context:
+    """One CUDA stream + scratch on one device, for one curve (bpgpu_ctx)."""
+
+    def __init__(self, curve=BLS12_381, device=0):
+        h = ctypes.c_void_p()
+        rc = lib().bpgpu_ctx_create(curve, device, ctypes.byref(h))
+        if rc:
+            raise BpgpuError(rc, "bpgpu_ctx_create")
+        self.handle, self.curve, self.device = h, curve, device
+        self.modbytes = lib().bpgpu_modbytes(curve)
+
+    def _check(self, rc, what):
+        if rc:
+            raise BpgpuError(rc, what)
+
+    def close(self):
+        if self.handle:
+            lib().bpgpu_ctx_destroy(self.handle)
+            self.handle = None
+
+    @property
+    def stream(self):
+        return lib().bpgpu_ctx_stream(self.handle)
+
+    @property
+    def launches(self):
+        return lib().bpgpu_ctx_launches(self.handle)
+
+    def sync(self):
+        self._check(lib().bpgpu_ctx_sync(self.handle), "sync")
+
+    # ---- residency
+    def upload_points(self, xy, n=None):
+        n = len(xy) // (2 * self.modbytes) if n is None else n
+        h = ctypes.c_void_p()
+        self._check(lib().bpgpu_points_upload(self.handle, _buf(xy), n, ctypes.byref(h)), "points_upload")
+        return DevicePoints(self, h)
+
+    def upload_scalars(self, be, n=None):
+        n = len(be) // self.modbytes if n is None else n
+        h = ctypes.c_void_p()
+        self._check(lib().bpgpu_scalars_upload(self.handle, _buf(be), n, ctypes.byref(h)), "scalars_upload")
+        return DeviceScalars(self, h)
+
+    # ---- MSM (G1Vector::multi_scalar_mul_var_time & friends)
+    def msm(self, points, scalars_be, off=0, n=None):
+        n = len(scalars_be) // self.modbytes if n is None else n
+        out = ctypes.create_string_buffer(2 * self.modbytes)
+        self._check(lib().bpgpu_msm(self.handle, points.handle, off, n, _buf(scalars_be), out), "msm")
+        return out.raw
+
+    def msm_device(self, points, scalars, poff=0, soff=0, n=None):
+        n = len(scalars) - soff if n is None else n
+        out = ctypes.create_string_buffer(2 * self.modbytes)
+        self._check(lib().bpgpu_msm_device(self.handle, points.handle, poff, n, scalars.handle, soff, out), "msm_device")
+        return out.raw
+
+    def msm_refs(self, points_xy, scalars_be, n=None):
+        n = len(scalars_be) // self.modbytes if n is None else n
+        out = ctypes.create_string_buffer(2 * self.modbytes)
+        self._check(lib().bpgpu_msm_refs(self.handle, _buf(points_xy), _buf(scalars_be), n, out), "msm_refs")
+        return out.raw
+
+    # ---- self-test hooks
+    def selftest_field(self, field, op, a, b):
+        n = len(a) // self.modbytes
+        out = ctypes.create_string_buffer(max(1, len(a)))
+        self._check(lib().bpgpu_selftest_field(self.handle, field, op, _buf(a), _buf(b), n, out), "selftest_field")
+        return out.raw[:len(a)]
+
+    def selftest_group(self, op, p_xy, q_xy, scalars_be):
+        n = len(p_xy) // (2 * self.modbytes)
+        out = ctypes.create_string_buffer(max(1, len(p_xy)))
+        self._check(lib().bpgpu_selftest_group(self.handle, op, _buf(p_xy), _buf(q_xy), _buf(scalars_be), n, out),
+                    "selftest_group")
+        return out.raw[:len(p_xy)]
+
+    def int_pipe_bench(self, kind, iters):
+        ops, ms = ctypes.c_double(), ctypes.c_double()
+        self._check(lib().bpgpu_int_pipe_bench(self.handle, kind, iters, ctypes.byref(ops), ctypes.byref(ms)), "int_pipe_bench")
+        return ops.value, ms.value

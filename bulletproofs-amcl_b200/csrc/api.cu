@@ -1,0 +1,531 @@
+// C ABI of libbpgpu (include/bpgpu.h): context, residency, byte<->Montgomery conversion kernels,
+// the MSM entry points, and the self-test / microbenchmark hooks.
+#include <string.h>
+
+#include <new>
+
+#include "common.cuh"
+#include "host_fp.h"
+
+namespace bp {
+
+int msm_window_bits(size_t n);
+
+int launch_check(bpgpu_ctx* ctx, const char* what) {
+  cudaError_t e = cudaGetLastError();
+  if (e != cudaSuccess) {
+    fprintf(stderr, "bpgpu: launch of %s failed: %s\n", what, cudaGetErrorString(e));
+    return BPGPU_E_CUDA;
+  }
+  (void)ctx;
+  return BPGPU_OK;
+}
+
+// ------------------------------------------------------------------ conversion kernels
+template <class Curve>
+__global__ void k_points_from_be(const uint8_t* __restrict__ xy, size_t n, Affine<typename Curve::Fq>* __restrict__ out) {
+  using Fq = typename Curve::Fq;
+  size_t i = (size_t)blockIdx.x * blockDim.x + threadIdx.x;
+  if (i >= n) return;
+  const uint8_t* p = xy + i * 2 * Curve::MODBYTES;
+  Affine<Fq> a;
+  be_to_limbs<Fq::N>(p, Curve::MODBYTES, a.x.v);
+  be_to_limbs<Fq::N>(p + Curve::MODBYTES, Curve::MODBYTES, a.y.v);
+  bool y_one = a.y.v[0] == 1;
+  for (int k = 1; k < Fq::N; k++) y_one = y_one && a.y.v[k] == 0;
+  if (a.x.is_zero() && y_one) {
+    a = Affine<Fq>::inf();                 // AMCL's identity (0, 1)
+  } else {
+    canonicalise(a.x); canonicalise(a.y);
+    a.x = a.x.to_mont(); a.y = a.y.to_mont();
+  }
+  store_vec(out + i, a);
+}
+
+template <class Fq>
+__device__ __forceinline__ void affine_to_be2(const Affine<Fq>& a, int modbytes, uint8_t* out) {
+  if (a.is_inf()) {
+    for (int i = 0; i < 2 * modbytes; i++) out[i] = 0;
+    out[2 * modbytes - 1] = 1;
+    return;
+  }
+  Fq x = a.x.from_mont(), y = a.y.from_mont();
+  limbs_to_be<Fq::N>(x.v, modbytes, out);
+  limbs_to_be<Fq::N>(y.v, modbytes, out + modbytes);
+}
+
+template <class Curve>
+__global__ void k_points_to_be(const Affine<typename Curve::Fq>* __restrict__ in, size_t n, uint8_t* __restrict__ xy) {
+  size_t i = (size_t)blockIdx.x * blockDim.x + threadIdx.x;
+  if (i >= n) return;
+  Affine<typename Curve::Fq> a = load_vec(in + i);
+  affine_to_be2(a, Curve::MODBYTES, xy + i * 2 * Curve::MODBYTES);
+}
+
+// big-endian MODBYTES -> Fr; mont = 0 leaves the canonical integer (MSM digit source)
+template <class Curve>
+__global__ void k_scalars_from_be(const uint8_t* __restrict__ be, size_t n, int mont, typename Curve::Fr* __restrict__ out) {
+  using Fr = typename Curve::Fr;
+  size_t i = (size_t)blockIdx.x * blockDim.x + threadIdx.x;
+  if (i >= n) return;
+  Fr s;
+  be_to_limbs<8>(be + i * Curve::MODBYTES, Curve::MODBYTES, s.v);
+  canonicalise(s);
+  if (mont) s = s.to_mont();
+  store_vec(out + i, s);
+}
+
+template <class Curve>
+__global__ void k_scalars_to_be(const typename Curve::Fr* __restrict__ in, size_t n, uint8_t* __restrict__ be) {
+  using Fr = typename Curve::Fr;
+  size_t i = (size_t)blockIdx.x * blockDim.x + threadIdx.x;
+  if (i >= n) return;
+  Fr s = load_vec(in + i).from_mont();
+  limbs_to_be<8>(s.v, Curve::MODBYTES, be + i * Curve::MODBYTES);
+}
+
+// ------------------------------------------------------------------ self-test kernels
+template <class F>
+__global__ void k_field_op(int op, const uint8_t* a, const uint8_t* b, size_t n, int modbytes, uint8_t* out) {
+  size_t i = (size_t)blockIdx.x * blockDim.x + threadIdx.x;
+  if (i >= n) return;
+  F x, y, r;
+  be_to_limbs<F::N>(a + i * modbytes, modbytes, x.v);
+  be_to_limbs<F::N>(b + i * modbytes, modbytes, y.v);
+  canonicalise(x); canonicalise(y);
+  x = x.to_mont(); y = y.to_mont();
+  switch (op) {
+    case 0: r = x * y; break;
+    case 1: r = x + y; break;
+    case 2: r = x - y; break;
+    case 3: r = x.inv(); break;
+    default: r = x.sqr(); break;
+  }
+  r = r.from_mont();
+  limbs_to_be<F::N>(r.v, modbytes, out + i * modbytes);
+}
+
+template <class Curve>
+__global__ void k_group_op(int op, const Affine<typename Curve::Fq>* p, const Affine<typename Curve::Fq>* q,
+                           const typename Curve::Fr* k, size_t n, Affine<typename Curve::Fq>* out) {
+  using Fq = typename Curve::Fq;
+  size_t i = (size_t)blockIdx.x * blockDim.x + threadIdx.x;
+  if (i >= n) return;
+  XYZZ<Fq> P = XYZZ<Fq>::from_affine(load_vec(p + i));
+  if (op == 0) {
+    P.madd(load_vec(q + i));
+  } else if (op == 1) {
+    P.dbl();
+  } else if (op == 2) {
+    typename Curve::Fr s = load_vec(k + i);
+    P = mul_limbs(P, s.v, 8);
+  } else {
+    XYZZ<Fq> Q = XYZZ<Fq>::from_affine(load_vec(q + i));
+    Q.dbl(); Q.add(P);                       // exercises the full add: 2Q + P
+    P = Q;
+  }
+  store_vec(out + i, P.to_affine());
+}
+
+// ------------------------------------------------------------------ integer-pipe microbenchmarks
+// kind 0: independent IMAD.WIDE.U32 accumulate chains, 8 per thread, no memory traffic
+__global__ void __launch_bounds__(256) k_imad_wide(int iters, uint32_t seed, uint64_t* sink) {
+  uint32_t a = seed + threadIdx.x, b = seed * 3 + blockIdx.x;
+  uint64_t acc[8];
+#pragma unroll
+  for (int k = 0; k < 8; k++) acc[k] = seed + k;
+  for (int it = 0; it < iters; it++) {
+#pragma unroll
+    for (int u = 0; u < 8; u++) {
+#pragma unroll
+      for (int k = 0; k < 8; k++) acc[k] = (uint64_t)a * (b + k) + acc[k];   // IMAD.WIDE.U32
+      a += (uint32_t)acc[0];
+    }
+  }
+  uint64_t x = 0;
+#pragma unroll
+  for (int k = 0; k < 8; k++) x ^= acc[k];
+  if (x == 0x123456789abcdefull) sink[0] = x;
+}
+// kind 1: dependent chain of Fq Montgomery products per thread (2 interleaved chains)
+template <class F>
+__global__ void __launch_bounds__(256) k_fq_mul_chain(int iters, const F* in, F* out) {
+  size_t i = (size_t)blockIdx.x * blockDim.x + threadIdx.x;
+  F x = load_vec(in + (i & 255)), y = load_vec(in + ((i + 7) & 255));
+  for (int it = 0; it < iters; it++) { x = x * y; y = y * x; }
+  if (x.is_zero() && y.is_zero()) store_vec(out, x);
+}
+
+template <class Curve>
+static int points_upload_t(bpgpu_ctx* ctx, const uint8_t* xy, size_t n, void* dst) {
+  if (n == 0) return BPGPU_OK;
+  size_t bytes = n * 2 * Curve::MODBYTES;
+  int rc = ctx->io_dev.reserve(bytes);
+  if (rc) return rc;
+  BP_CUDA_OK(cudaMemcpyAsync(ctx->io_dev.p, xy, bytes, cudaMemcpyHostToDevice, ctx->stream));
+  k_points_from_be<Curve><<<(unsigned)((n + 127) / 128), 128, 0, ctx->stream>>>((const uint8_t*)ctx->io_dev.p, n,
+                                                                              (Affine<typename Curve::Fq>*)dst);
+  ctx->launches++;
+  return launch_check(ctx, "k_points_from_be");
+}
+
+template <class Curve>
+static int scalars_upload_t(bpgpu_ctx* ctx, const uint8_t* be, size_t n, int mont, void* dst, Scratch& stage) {
+  if (n == 0) return BPGPU_OK;
+  size_t bytes = n * Curve::MODBYTES;
+  int rc = stage.reserve(bytes);
+  if (rc) return rc;
+  BP_CUDA_OK(cudaMemcpyAsync(stage.p, be, bytes, cudaMemcpyHostToDevice, ctx->stream));
+  k_scalars_from_be<Curve><<<(unsigned)((n + 255) / 256), 256, 0, ctx->stream>>>((const uint8_t*)stage.p, n, mont,
+                                                                               (typename Curve::Fr*)dst);
+  ctx->launches++;
+  return launch_check(ctx, "k_scalars_from_be");
+}
+
+static int fetch_result(bpgpu_ctx* ctx, const void* d_src, size_t bytes, uint8_t* host_out) {
+  BP_CUDA_OK(cudaMemcpyAsync(ctx->pinned, d_src, bytes, cudaMemcpyDeviceToHost, ctx->stream));
+  BP_CUDA_OK(cudaStreamSynchronize(ctx->stream));
+  memcpy(host_out, ctx->pinned, bytes);
+  return BPGPU_OK;
+}
+
+// Horner over the per-window sums + affine normalisation, on the host (see host_fp.h for why)
+template <class FqParams>
+static void msm_finish_host(const uint8_t* winsum_bytes, int W, int c, int modbytes, uint8_t* out_xy) {
+  using HP = host::HXYZZ<FqParams>;
+  HP acc = HP::inf();
+  const HP* ws = reinterpret_cast<const HP*>(winsum_bytes);
+  for (int w = W - 1; w >= 0; w--) {
+    if (w != W - 1) for (int k = 0; k < c; k++) acc.dbl();
+    acc.add(ws[w]);
+  }
+  acc.to_xy_be(modbytes, out_xy);
+}
+
+}  // namespace bp
+
+using namespace bp;
+
+#define DISPATCH(ctx, CALL)                          \
+  ((ctx)->curve == BPGPU_BLS12_381 ? CALL(Bls) : CALL(Bn))
+
+extern "C" {
+
+const char* bpgpu_strerror(int code) {
+  switch (code) {
+    case BPGPU_OK: return "ok";
+    case BPGPU_E_LEN: return "unequal vector lengths (ValueError::UnequalSizeVectors)";
+    case BPGPU_E_NOT_POW2: return "vector length is not a power of two";
+    case BPGPU_E_GENS_LEN: return "not enough generators (R1CSError::InvalidGeneratorsLength)";
+    case BPGPU_E_VERIFY: return "verification failed (R1CSError::VerificationError)";
+    case BPGPU_E_FORMAT: return "malformed input (R1CSError::FormatError)";
+    case BPGPU_E_CUDA: return "CUDA failure or no usable device";
+    case BPGPU_E_ARG: return "bad argument";
+    default: return "unknown error";
+  }
+}
+
+int bpgpu_modbytes(int curve) { return curve == BPGPU_BLS12_381 ? 48 : (curve == BPGPU_BN254 ? 32 : BPGPU_E_ARG); }
+
+int bpgpu_device_count(void) {
+  int n = 0;
+  if (cudaGetDeviceCount(&n) != cudaSuccess) return 0;
+  return n;
+}
+
+int bpgpu_ctx_create(int curve, int device, bpgpu_ctx** out) {
+  if (!out || (curve != BPGPU_BLS12_381 && curve != BPGPU_BN254)) return BPGPU_E_ARG;
+  *out = nullptr;
+  int n = 0;
+  if (cudaGetDeviceCount(&n) != cudaSuccess || n == 0) {
+    fprintf(stderr, "bpgpu: no CUDA device (this library has no CPU fallback)\n");
+    return BPGPU_E_CUDA;
+  }
+  if (device < 0 || device >= n) return BPGPU_E_ARG;
+  BP_CUDA_OK(cudaSetDevice(device));
+  bpgpu_ctx* c = new (std::nothrow) bpgpu_ctx();
+  if (!c) return BPGPU_E_CUDA;
+  c->curve = curve;
+  c->device = device;
+  cudaDeviceProp prop;
+  BP_CUDA_OK(cudaGetDeviceProperties(&prop, device));
+  c->sm_count = prop.multiProcessorCount;
+  BP_CUDA_OK(cudaStreamCreateWithFlags(&c->stream, cudaStreamNonBlocking));
+  c->pinned_cap = 1 << 16;
+  BP_CUDA_OK(cudaHostAlloc((void**)&c->pinned, c->pinned_cap, cudaHostAllocDefault));
+  *out = c;
+  return BPGPU_OK;
+}
+
+void bpgpu_ctx_destroy(bpgpu_ctx* c) {
+  if (!c) return;
+  cudaSetDevice(c->device);
+  cudaStreamSynchronize(c->stream);
+  c->msm_a.release(); c->msm_b.release(); c->msm_c.release(); c->msm_d.release(); c->msm_e.release();
+  c->io_dev.release(); c->io_dev2.release();
+  if (c->pinned) cudaFreeHost(c->pinned);
+  cudaStreamDestroy(c->stream);
+  delete c;
+}
+
+void* bpgpu_ctx_stream(bpgpu_ctx* c) { return c ? (void*)c->stream : nullptr; }
+int bpgpu_ctx_sync(bpgpu_ctx* c) {
+  if (!c) return BPGPU_E_ARG;
+  BP_CUDA_OK(cudaStreamSynchronize(c->stream));
+  return BPGPU_OK;
+}
+int bpgpu_ctx_curve(const bpgpu_ctx* c) { return c ? c->curve : BPGPU_E_ARG; }
+uint64_t bpgpu_ctx_launches(const bpgpu_ctx* c) { return c ? c->launches : 0; }
+
+void* bpgpu_host_alloc(size_t bytes) {
+  void* p = nullptr;
+  if (cudaHostAlloc(&p, bytes ? bytes : 1, cudaHostAllocDefault) != cudaSuccess) return nullptr;
+  return p;
+}
+void bpgpu_host_free(void* p) { if (p) cudaFreeHost(p); }
+
+// ------------------------------------------------------------------ residency
+int bpgpu_points_upload(bpgpu_ctx* ctx, const uint8_t* xy, size_t n, bpgpu_points** out) {
+  if (!ctx || !out || (!xy && n)) return BPGPU_E_ARG;
+  *out = nullptr;
+  BP_CUDA_OK(cudaSetDevice(ctx->device));
+  bpgpu_points* p = new (std::nothrow) bpgpu_points();
+  if (!p) return BPGPU_E_CUDA;
+  p->ctx = ctx; p->n = n; p->d = nullptr;
+  size_t psz = (ctx->curve == BPGPU_BLS12_381) ? sizeof(Affine<Bls::Fq>) : sizeof(Affine<Bn::Fq>);
+  if (cudaMalloc(&p->d, n ? n * psz : 16) != cudaSuccess) { delete p; return BPGPU_E_CUDA; }
+#define CALL(C) points_upload_t<C>(ctx, xy, n, p->d)
+  int rc = DISPATCH(ctx, CALL);
+#undef CALL
+  if (rc == BPGPU_OK && cudaStreamSynchronize(ctx->stream) != cudaSuccess) rc = BPGPU_E_CUDA;
+  if (rc) { cudaFree(p->d); delete p; return rc; }
+  *out = p;
+  return BPGPU_OK;
+}
+
+int bpgpu_points_download(bpgpu_ctx* ctx, const bpgpu_points* p, size_t off, size_t n, uint8_t* xy) {
+  if (!ctx || !p || (!xy && n)) return BPGPU_E_ARG;
+  if (off > p->n || n > p->n - off) return BPGPU_E_ARG;
+  if (n == 0) return BPGPU_OK;
+  BP_CUDA_OK(cudaSetDevice(ctx->device));
+  size_t bytes = n * 2 * bpgpu_modbytes(ctx->curve);
+  int rc = ctx->io_dev.reserve(bytes);
+  if (rc) return rc;
+  if (ctx->curve == BPGPU_BLS12_381)
+    k_points_to_be<Bls><<<(unsigned)((n + 127) / 128), 128, 0, ctx->stream>>>((const Affine<Bls::Fq>*)p->d + off, n, (uint8_t*)ctx->io_dev.p);
+  else
+    k_points_to_be<Bn><<<(unsigned)((n + 127) / 128), 128, 0, ctx->stream>>>((const Affine<Bn::Fq>*)p->d + off, n, (uint8_t*)ctx->io_dev.p);
+  ctx->launches++;
+  if ((rc = launch_check(ctx, "k_points_to_be"))) return rc;
+  BP_CUDA_OK(cudaMemcpyAsync(xy, ctx->io_dev.p, bytes, cudaMemcpyDeviceToHost, ctx->stream));
+  BP_CUDA_OK(cudaStreamSynchronize(ctx->stream));
+  return BPGPU_OK;
+}
+
+size_t bpgpu_points_len(const bpgpu_points* p) { return p ? p->n : 0; }
+void bpgpu_points_free(bpgpu_points* p) {
+  if (!p) return;
+  cudaSetDevice(p->ctx->device);
+  cudaFree(p->d);
+  delete p;
+}
+
+int bpgpu_scalars_upload(bpgpu_ctx* ctx, const uint8_t* be, size_t n, bpgpu_scalars** out) {
+  if (!ctx || !out || (!be && n)) return BPGPU_E_ARG;
+  *out = nullptr;
+  BP_CUDA_OK(cudaSetDevice(ctx->device));
+  bpgpu_scalars* s = new (std::nothrow) bpgpu_scalars();
+  if (!s) return BPGPU_E_CUDA;
+  s->ctx = ctx; s->n = n; s->d = nullptr;
+  if (cudaMalloc(&s->d, n ? n * 32 : 16) != cudaSuccess) { delete s; return BPGPU_E_CUDA; }
+#define CALL(C) scalars_upload_t<C>(ctx, be, n, 1, s->d, ctx->io_dev)
+  int rc = DISPATCH(ctx, CALL);
+#undef CALL
+  if (rc == BPGPU_OK && cudaStreamSynchronize(ctx->stream) != cudaSuccess) rc = BPGPU_E_CUDA;
+  if (rc) { cudaFree(s->d); delete s; return rc; }
+  *out = s;
+  return BPGPU_OK;
+}
+
+int bpgpu_scalars_download(bpgpu_ctx* ctx, const bpgpu_scalars* s, size_t off, size_t n, uint8_t* be) {
+  if (!ctx || !s || (!be && n)) return BPGPU_E_ARG;
+  if (off > s->n || n > s->n - off) return BPGPU_E_ARG;
+  if (n == 0) return BPGPU_OK;
+  BP_CUDA_OK(cudaSetDevice(ctx->device));
+  size_t bytes = n * bpgpu_modbytes(ctx->curve);
+  int rc = ctx->io_dev.reserve(bytes);
+  if (rc) return rc;
+  if (ctx->curve == BPGPU_BLS12_381)
+    k_scalars_to_be<Bls><<<(unsigned)((n + 255) / 256), 256, 0, ctx->stream>>>((const Bls::Fr*)s->d + off, n, (uint8_t*)ctx->io_dev.p);
+  else
+    k_scalars_to_be<Bn><<<(unsigned)((n + 255) / 256), 256, 0, ctx->stream>>>((const Bn::Fr*)s->d + off, n, (uint8_t*)ctx->io_dev.p);
+  ctx->launches++;
+  if ((rc = launch_check(ctx, "k_scalars_to_be"))) return rc;
+  BP_CUDA_OK(cudaMemcpyAsync(be, ctx->io_dev.p, bytes, cudaMemcpyDeviceToHost, ctx->stream));
+  BP_CUDA_OK(cudaStreamSynchronize(ctx->stream));
+  return BPGPU_OK;
+}
+
+size_t bpgpu_scalars_len(const bpgpu_scalars* s) { return s ? s->n : 0; }
+void bpgpu_scalars_free(bpgpu_scalars* s) {
+  if (!s) return;
+  cudaSetDevice(s->ctx->device);
+  cudaFree(s->d);
+  delete s;
+}
+
+// ------------------------------------------------------------------ MSM
+int bpgpu_msm_window_bits(size_t n) { return msm_window_bits(n); }
+
+static int msm_dispatch(bpgpu_ctx* ctx, const void* d_pts, const void* d_scal, bool mont, size_t n, uint8_t* out_xy) {
+  int mb = bpgpu_modbytes(ctx->curve);
+  MsmResult res;
+  int rc;
+  if (ctx->curve == BPGPU_BLS12_381) rc = msm_run<Bls>(ctx, (const Affine<Bls::Fq>*)d_pts, d_scal, mont, n, &res);
+  else rc = msm_run<Bn>(ctx, (const Affine<Bn::Fq>*)d_pts, d_scal, mont, n, &res);
+  if (rc) return rc;
+  size_t psz = (ctx->curve == BPGPU_BLS12_381) ? sizeof(XYZZ<Bls::Fq>) : sizeof(XYZZ<Bn::Fq>);
+  if (res.W) {
+    BP_CUDA_OK(cudaMemcpyAsync(ctx->pinned, res.d_winsum, res.W * psz, cudaMemcpyDeviceToHost, ctx->stream));
+    BP_CUDA_OK(cudaStreamSynchronize(ctx->stream));
+  }
+  if (ctx->curve == BPGPU_BLS12_381) msm_finish_host<BlsFq>(ctx->pinned, res.W, res.c, mb, out_xy);
+  else msm_finish_host<BnFq>(ctx->pinned, res.W, res.c, mb, out_xy);
+  return BPGPU_OK;
+}
+
+int bpgpu_msm(bpgpu_ctx* ctx, const bpgpu_points* p, size_t off, size_t n, const uint8_t* scalars_be, uint8_t* out_xy) {
+  if (!ctx || !p || !out_xy || (!scalars_be && n)) return BPGPU_E_ARG;
+  if (off > p->n || n > p->n - off) return BPGPU_E_LEN;
+  BP_CUDA_OK(cudaSetDevice(ctx->device));
+  int rc = ctx->msm_c.reserve(n * 32 + 32);
+  if (rc) return rc;
+#define CALL(C) scalars_upload_t<C>(ctx, scalars_be, n, 0, ctx->msm_c.p, ctx->io_dev2)
+  rc = DISPATCH(ctx, CALL);
+#undef CALL
+  if (rc) return rc;
+  size_t psz = (ctx->curve == BPGPU_BLS12_381) ? sizeof(Affine<Bls::Fq>) : sizeof(Affine<Bn::Fq>);
+  return msm_dispatch(ctx, (const uint8_t*)p->d + off * psz, ctx->msm_c.p, false, n, out_xy);
+}
+
+int bpgpu_msm_device(bpgpu_ctx* ctx, const bpgpu_points* p, size_t poff, size_t n, const bpgpu_scalars* s, size_t soff,
+                     uint8_t* out_xy) {
+  if (!ctx || !p || !s || !out_xy) return BPGPU_E_ARG;
+  if (poff > p->n || n > p->n - poff || soff > s->n || n > s->n - soff) return BPGPU_E_LEN;
+  BP_CUDA_OK(cudaSetDevice(ctx->device));
+  size_t psz = (ctx->curve == BPGPU_BLS12_381) ? sizeof(Affine<Bls::Fq>) : sizeof(Affine<Bn::Fq>);
+  return msm_dispatch(ctx, (const uint8_t*)p->d + poff * psz, (const uint8_t*)s->d + soff * 32, true, n, out_xy);
+}
+
+int bpgpu_msm_refs(bpgpu_ctx* ctx, const uint8_t* points_xy, const uint8_t* scalars_be, size_t n, uint8_t* out_xy) {
+  if (!ctx || !out_xy || ((!points_xy || !scalars_be) && n)) return BPGPU_E_ARG;
+  BP_CUDA_OK(cudaSetDevice(ctx->device));
+  size_t psz = (ctx->curve == BPGPU_BLS12_381) ? sizeof(Affine<Bls::Fq>) : sizeof(Affine<Bn::Fq>);
+  int rc = ctx->msm_d.reserve(n * psz + 32);
+  if (rc) return rc;
+  if ((rc = ctx->msm_c.reserve(n * 32 + 32))) return rc;
+#define CALL(C) points_upload_t<C>(ctx, points_xy, n, ctx->msm_d.p)
+  rc = DISPATCH(ctx, CALL);
+#undef CALL
+  if (rc) return rc;
+#define CALL(C) scalars_upload_t<C>(ctx, scalars_be, n, 0, ctx->msm_c.p, ctx->io_dev2)
+  rc = DISPATCH(ctx, CALL);
+#undef CALL
+  if (rc) return rc;
+  return msm_dispatch(ctx, ctx->msm_d.p, ctx->msm_c.p, false, n, out_xy);
+}
+
+// ------------------------------------------------------------------ self tests
+int bpgpu_selftest_field(bpgpu_ctx* ctx, int field, int op, const uint8_t* a, const uint8_t* b, size_t n, uint8_t* out) {
+  if (!ctx || !a || !b || !out) return BPGPU_E_ARG;
+  BP_CUDA_OK(cudaSetDevice(ctx->device));
+  int mb = bpgpu_modbytes(ctx->curve);
+  size_t bytes = n * mb;
+  int rc = ctx->io_dev.reserve(bytes * 3);
+  if (rc) return rc;
+  uint8_t* da = (uint8_t*)ctx->io_dev.p; uint8_t* db = da + bytes; uint8_t* dout = db + bytes;
+  BP_CUDA_OK(cudaMemcpyAsync(da, a, bytes, cudaMemcpyHostToDevice, ctx->stream));
+  BP_CUDA_OK(cudaMemcpyAsync(db, b, bytes, cudaMemcpyHostToDevice, ctx->stream));
+  unsigned blocks = (unsigned)((n + 63) / 64);
+  if (ctx->curve == BPGPU_BLS12_381) {
+    if (field == 0) k_field_op<Bls::Fq><<<blocks, 64, 0, ctx->stream>>>(op, da, db, n, mb, dout);
+    else k_field_op<Bls::Fr><<<blocks, 64, 0, ctx->stream>>>(op, da, db, n, mb, dout);
+  } else {
+    if (field == 0) k_field_op<Bn::Fq><<<blocks, 64, 0, ctx->stream>>>(op, da, db, n, mb, dout);
+    else k_field_op<Bn::Fr><<<blocks, 64, 0, ctx->stream>>>(op, da, db, n, mb, dout);
+  }
+  ctx->launches++;
+  if ((rc = launch_check(ctx, "k_field_op"))) return rc;
+  BP_CUDA_OK(cudaMemcpyAsync(out, dout, bytes, cudaMemcpyDeviceToHost, ctx->stream));
+  BP_CUDA_OK(cudaStreamSynchronize(ctx->stream));
+  return BPGPU_OK;
+}
+
+int bpgpu_selftest_group(bpgpu_ctx* ctx, int op, const uint8_t* p_xy, const uint8_t* q_xy, const uint8_t* scalars_be, size_t n,
+                         uint8_t* out_xy) {
+  if (!ctx || !p_xy || !q_xy || !scalars_be || !out_xy) return BPGPU_E_ARG;
+  bpgpu_points *P = nullptr, *Q = nullptr, *O = nullptr;
+  int rc = bpgpu_points_upload(ctx, p_xy, n, &P);
+  if (!rc) rc = bpgpu_points_upload(ctx, q_xy, n, &Q);
+  if (!rc) rc = bpgpu_points_upload(ctx, p_xy, n, &O);
+  if (!rc) rc = ctx->msm_c.reserve(n * 32 + 32);
+  if (!rc) {
+#define CALL(C) scalars_upload_t<C>(ctx, scalars_be, n, 0, ctx->msm_c.p, ctx->io_dev2)
+    rc = DISPATCH(ctx, CALL);
+#undef CALL
+  }
+  if (!rc) {
+    unsigned blocks = (unsigned)((n + 63) / 64);
+    if (ctx->curve == BPGPU_BLS12_381)
+      k_group_op<Bls><<<blocks, 64, 0, ctx->stream>>>(op, (const Affine<Bls::Fq>*)P->d, (const Affine<Bls::Fq>*)Q->d,
+                                                      (const Bls::Fr*)ctx->msm_c.p, n, (Affine<Bls::Fq>*)O->d);
+    else
+      k_group_op<Bn><<<blocks, 64, 0, ctx->stream>>>(op, (const Affine<Bn::Fq>*)P->d, (const Affine<Bn::Fq>*)Q->d,
+                                                     (const Bn::Fr*)ctx->msm_c.p, n, (Affine<Bn::Fq>*)O->d);
+    ctx->launches++;
+    rc = launch_check(ctx, "k_group_op");
+  }
+  if (!rc) rc = bpgpu_points_download(ctx, O, 0, n, out_xy);
+  bpgpu_points_free(P); bpgpu_points_free(Q); bpgpu_points_free(O);
+  return rc;
+}
+
+int bpgpu_int_pipe_bench(bpgpu_ctx* ctx, int kind, int iters, double* ops_per_s, double* ms_out) {
+  if (!ctx || !ops_per_s) return BPGPU_E_ARG;
+  BP_CUDA_OK(cudaSetDevice(ctx->device));
+  int rc = ctx->io_dev.reserve(1 << 16);
+  if (rc) return rc;
+  cudaEvent_t e0, e1;
+  BP_CUDA_OK(cudaEventCreate(&e0));
+  BP_CUDA_OK(cudaEventCreate(&e1));
+  const int blocks = ctx->sm_count * 8, threads = 256;
+  double ops = 0;
+  float best = 1e30f;
+  for (int rep = 0; rep < 5; rep++) {
+    BP_CUDA_OK(cudaEventRecord(e0, ctx->stream));
+    if (kind == 0) {
+      k_imad_wide<<<blocks, threads, 0, ctx->stream>>>(iters, 12345u + rep, (uint64_t*)ctx->io_dev.p);
+      ops = (double)blocks * threads * (double)iters * 64.0;
+    } else {
+      BP_CUDA_OK(cudaMemsetAsync(ctx->io_dev.p, 0x5a, 1 << 16, ctx->stream));
+      if (ctx->curve == BPGPU_BLS12_381)
+        k_fq_mul_chain<Bls::Fq><<<blocks, threads, 0, ctx->stream>>>(iters, (const Bls::Fq*)ctx->io_dev.p, (Bls::Fq*)ctx->io_dev.p);
+      else
+        k_fq_mul_chain<Bn::Fq><<<blocks, threads, 0, ctx->stream>>>(iters, (const Bn::Fq*)ctx->io_dev.p, (Bn::Fq*)ctx->io_dev.p);
+      ops = (double)blocks * threads * (double)iters * 2.0;
+    }
+    ctx->launches++;
+    BP_CUDA_OK(cudaEventRecord(e1, ctx->stream));
+    BP_CUDA_OK(cudaEventSynchronize(e1));
+    float ms = 0;
+    BP_CUDA_OK(cudaEventElapsedTime(&ms, e0, e1));
+    if (rep > 0 && ms < best) best = ms;
+  }
+  cudaEventDestroy(e0); cudaEventDestroy(e1);
+  if ((rc = launch_check(ctx, "int_pipe_bench"))) return rc;
+  *ops_per_s = ops / (best * 1e-3);
+  if (ms_out) *ms_out = best;
+  return BPGPU_OK;
+}
+
+}  // extern "C"

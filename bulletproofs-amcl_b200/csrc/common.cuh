@@ -1,0 +1,147 @@
+// Shared internals of libbpgpu: curve traits, the context object, scratch arenas, vector I/O.
+#pragma once
+#include <cuda_runtime.h>
+#include <stdint.h>
+#include <stdio.h>
+#include <vector>
+
+#include "../../include/bpgpu.h"
+#include "ec.cuh"
+
+namespace bp {
+
+struct Bls {
+  using Fq = Fp<BlsFq>;
+  using Fr = Fp<BlsFr>;
+  static constexpr int ID = BPGPU_BLS12_381;
+  static constexpr int MODBYTES = 48;
+  static constexpr int SCALAR_BITS = 255;
+};
+struct Bn {
+  using Fq = Fp<BnFq>;
+  using Fr = Fp<BnFr>;
+  static constexpr int ID = BPGPU_BN254;
+  static constexpr int MODBYTES = 32;
+  static constexpr int SCALAR_BITS = 254;
+};
+
+// A scalar as the MSM consumes it: canonical integer, 8 little-endian 32-bit limbs.
+struct ScalarInt { uint32_t v[8]; };
+
+#define BP_CUDA_OK(expr)                                                                   \
+  do {                                                                                     \
+    cudaError_t _e = (expr);                                                               \
+    if (_e != cudaSuccess) {                                                               \
+      fprintf(stderr, "bpgpu: CUDA error %s at %s:%d\n", cudaGetErrorString(_e), __FILE__, __LINE__); \
+      return BPGPU_E_CUDA;                                                                 \
+    }                                                                                      \
+  } while (0)
+
+// Growable device scratch buffer owned by a context.
+struct Scratch {
+  void* p = nullptr;
+  size_t cap = 0;
+  int reserve(size_t bytes) {
+    if (bytes <= cap) return BPGPU_OK;
+    if (p) cudaFree(p);
+    p = nullptr; cap = 0;
+    size_t want = bytes + bytes / 8 + 256;
+    BP_CUDA_OK(cudaMalloc(&p, want));
+    cap = want;
+    return BPGPU_OK;
+  }
+  void release() { if (p) cudaFree(p); p = nullptr; cap = 0; }
+};
+
+}  // namespace bp
+
+struct bpgpu_ctx {
+  int curve = 0;
+  int device = 0;
+  int sm_count = 148;
+  cudaStream_t stream = nullptr;
+  uint64_t launches = 0;
+  // MSM scratch
+  bp::Scratch msm_a, msm_b, msm_c, msm_d, msm_e, io_dev, io_dev2;
+  uint8_t* pinned = nullptr;      // small pinned staging (results, challenges)
+  size_t pinned_cap = 0;
+};
+
+struct bpgpu_points {
+  bpgpu_ctx* ctx;
+  void* d;        // Affine<Fq>[n]
+  size_t n;
+};
+struct bpgpu_scalars {
+  bpgpu_ctx* ctx;
+  void* d;        // Fr[n] Montgomery
+  size_t n;
+};
+
+namespace bp {
+
+// ------------------------------------------------------------------ 128-bit vector I/O
+template <class T>
+__device__ __forceinline__ T load_vec(const T* src) {
+  static_assert(sizeof(T) % 16 == 0, "16-byte multiple");
+  T out;
+  const uint4* s = reinterpret_cast<const uint4*>(src);
+  uint4* d = reinterpret_cast<uint4*>(&out);
+#pragma unroll
+  for (int i = 0; i < (int)(sizeof(T) / 16); i++) d[i] = s[i];
+  return out;
+}
+template <class T>
+__device__ __forceinline__ T load_vec_ro(const T* src) {   // read-only path (LDG.NC)
+  T out;
+  const uint4* s = reinterpret_cast<const uint4*>(src);
+  uint4* d = reinterpret_cast<uint4*>(&out);
+#pragma unroll
+  for (int i = 0; i < (int)(sizeof(T) / 16); i++) d[i] = __ldg(s + i);
+  return out;
+}
+template <class T>
+__device__ __forceinline__ void store_vec(T* dst, const T& v) {
+  static_assert(sizeof(T) % 16 == 0, "16-byte multiple");
+  uint4* d = reinterpret_cast<uint4*>(dst);
+  const uint4* s = reinterpret_cast<const uint4*>(&v);
+#pragma unroll
+  for (int i = 0; i < (int)(sizeof(T) / 16); i++) d[i] = s[i];
+}
+
+// ------------------------------------------------------------------ byte <-> limb conversion
+// big-endian MODBYTES -> N little-endian limbs (canonical integer); bytes beyond 4N are ignored
+template <int N>
+__device__ __forceinline__ void be_to_limbs(const uint8_t* be, int nbytes, uint32_t* out) {
+#pragma unroll
+  for (int i = 0; i < N; i++) {
+    const uint8_t* p = be + nbytes - 4 * (i + 1);
+    out[i] = ((uint32_t)p[0] << 24) | ((uint32_t)p[1] << 16) | ((uint32_t)p[2] << 8) | (uint32_t)p[3];
+  }
+}
+template <int N>
+__device__ __forceinline__ void limbs_to_be(const uint32_t* in, int nbytes, uint8_t* be) {
+  for (int i = 0; i < nbytes - 4 * N; i++) be[i] = 0;
+#pragma unroll
+  for (int i = 0; i < N; i++) {
+    uint8_t* p = be + nbytes - 4 * (i + 1);
+    p[0] = (uint8_t)(in[i] >> 24); p[1] = (uint8_t)(in[i] >> 16); p[2] = (uint8_t)(in[i] >> 8); p[3] = (uint8_t)in[i];
+  }
+}
+
+// x mod p for an arbitrary N-limb integer x < 2^(32N) (p has at least 32N-3 bits: at most 7 subtractions)
+template <class F>
+__device__ __forceinline__ void canonicalise(F& x) {
+#pragma unroll 1
+  for (int k = 0; k < 8; k++) F::reduce_once(x.v);
+}
+
+int launch_check(bpgpu_ctx* ctx, const char* what);
+
+// per-window sums an MSM leaves on the device: result = sum_w 2^(c*w) * winsum[w]
+struct MsmResult { int W; int c; const void* d_winsum; };
+
+template <class Curve> int msm_run(bpgpu_ctx* ctx, const Affine<typename Curve::Fq>* d_points, const void* d_scalars,
+                                   bool scalars_mont, size_t n, MsmResult* res);
+
+}  // namespace bp

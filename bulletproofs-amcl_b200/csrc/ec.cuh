@@ -1,0 +1,157 @@
+// G1 group law for short-Weierstrass curves with a = 0 (BLS12-381: b = 4, AMCL BN254: b = 2).
+//
+// Device replacement for the AMCL ECP operations the reference reaches through amcl_wrapper's
+// G1 (`+`, `binary_scalar_mul`, `*`; /root/reference/src/ipp.rs:119-129,185-187,
+// src/r1cs/prover.rs:123,358,550).  All coordinates are Fp<...> in Montgomery form.
+//
+//  * Affine  : (x, y); the identity is stored as (0, 0), which is on neither curve.
+//  * XYZZ    : (X, Y, ZZ, ZZZ) with x = X/ZZ, y = Y/ZZZ, ZZ^3 = ZZZ^2; identity: ZZ = 0.
+//    Mixed add 8M+2S, full add 12M+2S, double 6M+3S (EFD "xyzz" formulas for a = 0).
+// The add routines are COMPLETE: equal inputs fall through to doubling and opposite inputs
+// to the identity, because bucket sums do meet P+P and P+(-P) (repeated generators, 0/1 witnesses).
+#pragma once
+#include "fp.cuh"
+
+namespace bp {
+
+template <class F>
+struct Affine {
+  F x, y;
+  BP_HD bool is_inf() const { return x.is_zero() && y.is_zero(); }
+  BP_HD static Affine inf() { Affine a; a.x = F::zero(); a.y = F::zero(); return a; }
+  BP_HD Affine neg() const { Affine a; a.x = x; a.y = is_inf() ? y : y.neg(); return a; }
+};
+
+template <class F>
+struct XYZZ {
+  F x, y, zz, zzz;
+  BP_HD bool is_inf() const { return zz.is_zero(); }
+  BP_HD static XYZZ inf() { XYZZ p; p.x = F::zero(); p.y = F::zero(); p.zz = F::zero(); p.zzz = F::zero(); return p; }
+  BP_HD static XYZZ from_affine(const Affine<F>& a) {
+    XYZZ p;
+    if (a.is_inf()) return inf();
+    p.x = a.x; p.y = a.y; p.zz = F::one(); p.zzz = F::one();
+    return p;
+  }
+  BP_HD XYZZ neg() const { XYZZ p = *this; p.y = y.neg(); return p; }
+
+  // dbl-2008-s-1 with a = 0
+  BP_HD_COLD void dbl() {
+    if (is_inf()) return;
+    if (y.is_zero()) { *this = inf(); return; }
+    F U = y.dbl();
+    F V = U.sqr();
+    F W = U * V;
+    F S = x * V;
+    F X2 = x.sqr();
+    F M = X2.dbl() + X2;
+    F X3 = M.sqr() - S.dbl();
+    F Y3 = M * (S - X3) - W * y;
+    zz = V * zz;
+    zzz = W * zzz;
+    x = X3; y = Y3;
+  }
+
+  // mdbl-2008-s-1: 2 * affine
+  BP_HD_COLD static XYZZ dbl_affine(const Affine<F>& a) {
+    if (a.is_inf() || a.y.is_zero()) return inf();
+    XYZZ p;
+    F U = a.y.dbl();
+    F V = U.sqr();
+    F W = U * V;
+    F S = a.x * V;
+    F X2 = a.x.sqr();
+    F M = X2.dbl() + X2;
+    p.x = M.sqr() - S.dbl();
+    p.y = M * (S - p.x) - W * a.y;
+    p.zz = V; p.zzz = W;
+    return p;
+  }
+
+  // madd-2008-s: this += affine
+  BP_HD void madd(const Affine<F>& a) {
+    if (a.is_inf()) return;
+    if (is_inf()) { *this = from_affine(a); return; }
+    F U2 = a.x * zz;
+    F S2 = a.y * zzz;
+    F Pd = U2 - x;
+    F R = S2 - y;
+    if (Pd.is_zero()) {
+      if (R.is_zero()) *this = dbl_affine(a); else *this = inf();
+      return;
+    }
+    F PP = Pd.sqr();
+    F PPP = Pd * PP;
+    F Q = x * PP;
+    F X3 = R.sqr() - PPP - Q.dbl();
+    F Y3 = R * (Q - X3) - y * PPP;
+    zz = zz * PP;
+    zzz = zzz * PPP;
+    x = X3; y = Y3;
+  }
+
+  // add-2008-s: this += q
+  BP_HD_COLD void add(const XYZZ& q) {
+    if (q.is_inf()) return;
+    if (is_inf()) { *this = q; return; }
+    F U1 = x * q.zz;
+    F U2 = q.x * zz;
+    F S1 = y * q.zzz;
+    F S2 = q.y * zzz;
+    F Pd = U2 - U1;
+    F R = S2 - S1;
+    if (Pd.is_zero()) {
+      if (R.is_zero()) dbl(); else *this = inf();
+      return;
+    }
+    F PP = Pd.sqr();
+    F PPP = Pd * PP;
+    F Q = U1 * PP;
+    F X3 = R.sqr() - PPP - Q.dbl();
+    F Y3 = R * (Q - X3) - S1 * PPP;
+    zz = zz * q.zz * PP;
+    zzz = zzz * q.zzz * PPP;
+    x = X3; y = Y3;
+  }
+
+  // normalise; one field inversion
+  BP_HD_COLD Affine<F> to_affine() const {
+    if (is_inf()) return Affine<F>::inf();
+    F i3 = zzz.inv();          // 1/Z^3
+    F i1 = i3 * zz;            // 1/Z
+    Affine<F> a;
+    a.x = x * i1.sqr();
+    a.y = y * i3;
+    return a;
+  }
+};
+
+// k * P for a small unsigned integer k (bucket-chunk offsets), double-and-add MSB first
+template <class F>
+BP_HD XYZZ<F> mul_small(const XYZZ<F>& p, uint32_t k) {
+  XYZZ<F> r = XYZZ<F>::inf();
+  if (k == 0 || p.is_inf()) return r;
+  int top = 31;
+  while (!((k >> top) & 1)) top--;
+  r = p;
+  for (int b = top - 1; b >= 0; b--) {
+    r.dbl();
+    if ((k >> b) & 1) r.add(p);
+  }
+  return r;
+}
+
+// k * P for a multi-limb little-endian integer scalar (NOT Montgomery form)
+template <class F>
+BP_HD XYZZ<F> mul_limbs(const XYZZ<F>& p, const uint32_t* k, int nlimbs) {
+  XYZZ<F> r = XYZZ<F>::inf();
+  for (int i = nlimbs - 1; i >= 0; i--) {
+    for (int b = 31; b >= 0; b--) {
+      r.dbl();
+      if ((k[i] >> b) & 1) r.add(p);
+    }
+  }
+  return r;
+}
+
+}  // namespace bp

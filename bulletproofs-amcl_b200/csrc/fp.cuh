@@ -1,0 +1,234 @@
+// Montgomery prime-field arithmetic on 32-bit limbs for sm_100a (and a bit-identical host
+// emulation used by the CPU unit tests of the limb schedule).
+//
+// Replaces, on the device, the field arithmetic the reference gets from amcl_wrapper's
+// FieldElement / AMCL FP (call sites /root/reference/src/ipp.rs:115-130,181-188;
+// src/r1cs/prover.rs:469-486).  Values are kept in Montgomery form (x*2^(32N) mod p),
+// fully reduced to [0, p) after every operation, so equality is limb equality.
+//
+// Multiplier schedule: two accumulators, one holding the products that start on even limb
+// positions and one those on odd positions.  Every 32x32->64 product is issued as a
+// mad.lo.cc / madc.hi.cc pair on adjacent limbs of ONE accumulator, so ptxas fuses each pair
+// into a single IMAD.WIDE.U32(.X) with the carry riding the chain: 2*N*N wide multiply-adds
+// per Montgomery product (288 for the 12-limb BLS12-381 Fq, 128 for 8 limbs) plus N IMADs for
+// the quotient digits.  After each reduction row the accumulators swap roles, which performs
+// the one-limb right shift by register renaming.
+#pragma once
+#include <stdint.h>
+
+#if defined(__CUDACC__)
+#define BP_HD __host__ __device__ __forceinline__
+#define BP_D __device__ __forceinline__
+// cold-path group operations are real calls on the device: keeps code size and ptxas time bounded
+#define BP_HD_COLD __host__ __device__ __noinline__
+#else
+#define BP_HD inline
+#define BP_D inline
+#define BP_HD_COLD inline
+#endif
+
+#include "field_params.h"
+
+namespace bp {
+
+// ---------------------------------------------------------------------------------------------
+// Carry-flag primitives.  Device: PTX with the .cc flag.  Host: emulation with an explicit flag
+// (lets tests/host_fp_check.cpp run the exact same limb schedule on the CPU).
+// ---------------------------------------------------------------------------------------------
+#if defined(__CUDA_ARCH__)
+struct CarryChain {
+  BP_D uint32_t add_cc(uint32_t a, uint32_t b) { uint32_t r; asm volatile("add.cc.u32 %0, %1, %2;" : "=r"(r) : "r"(a), "r"(b)); return r; }
+  BP_D uint32_t addc_cc(uint32_t a, uint32_t b) { uint32_t r; asm volatile("addc.cc.u32 %0, %1, %2;" : "=r"(r) : "r"(a), "r"(b)); return r; }
+  BP_D uint32_t addc(uint32_t a, uint32_t b) { uint32_t r; asm volatile("addc.u32 %0, %1, %2;" : "=r"(r) : "r"(a), "r"(b)); return r; }
+  BP_D uint32_t sub_cc(uint32_t a, uint32_t b) { uint32_t r; asm volatile("sub.cc.u32 %0, %1, %2;" : "=r"(r) : "r"(a), "r"(b)); return r; }
+  BP_D uint32_t subc_cc(uint32_t a, uint32_t b) { uint32_t r; asm volatile("subc.cc.u32 %0, %1, %2;" : "=r"(r) : "r"(a), "r"(b)); return r; }
+  BP_D uint32_t subc(uint32_t a, uint32_t b) { uint32_t r; asm volatile("subc.u32 %0, %1, %2;" : "=r"(r) : "r"(a), "r"(b)); return r; }
+  BP_D uint32_t mad_lo_cc(uint32_t a, uint32_t b, uint32_t c) { uint32_t r; asm volatile("mad.lo.cc.u32 %0, %1, %2, %3;" : "=r"(r) : "r"(a), "r"(b), "r"(c)); return r; }
+  BP_D uint32_t madc_lo_cc(uint32_t a, uint32_t b, uint32_t c) { uint32_t r; asm volatile("madc.lo.cc.u32 %0, %1, %2, %3;" : "=r"(r) : "r"(a), "r"(b), "r"(c)); return r; }
+  BP_D uint32_t mad_hi_cc(uint32_t a, uint32_t b, uint32_t c) { uint32_t r; asm volatile("mad.hi.cc.u32 %0, %1, %2, %3;" : "=r"(r) : "r"(a), "r"(b), "r"(c)); return r; }
+  BP_D uint32_t madc_hi_cc(uint32_t a, uint32_t b, uint32_t c) { uint32_t r; asm volatile("madc.hi.cc.u32 %0, %1, %2, %3;" : "=r"(r) : "r"(a), "r"(b), "r"(c)); return r; }
+  BP_D uint32_t madc_hi(uint32_t a, uint32_t b, uint32_t c) { uint32_t r; asm volatile("madc.hi.u32 %0, %1, %2, %3;" : "=r"(r) : "r"(a), "r"(b), "r"(c)); return r; }
+};
+#else
+struct CarryChain {
+  uint32_t cf = 0;
+  uint32_t add_cc(uint32_t a, uint32_t b) { uint64_t t = (uint64_t)a + b; cf = (uint32_t)(t >> 32); return (uint32_t)t; }
+  uint32_t addc_cc(uint32_t a, uint32_t b) { uint64_t t = (uint64_t)a + b + cf; cf = (uint32_t)(t >> 32); return (uint32_t)t; }
+  uint32_t addc(uint32_t a, uint32_t b) { uint64_t t = (uint64_t)a + b + cf; return (uint32_t)t; }
+  uint32_t sub_cc(uint32_t a, uint32_t b) { uint64_t t = (uint64_t)a - b; cf = (uint32_t)(t >> 63); return (uint32_t)t; }
+  uint32_t subc_cc(uint32_t a, uint32_t b) { uint64_t t = (uint64_t)a - b - cf; cf = (uint32_t)(t >> 63); return (uint32_t)t; }
+  uint32_t subc(uint32_t a, uint32_t b) { uint64_t t = (uint64_t)a - b - cf; return (uint32_t)t; }
+  uint32_t mad_lo_cc(uint32_t a, uint32_t b, uint32_t c) { return add_cc((uint32_t)((uint64_t)a * b), c); }
+  uint32_t madc_lo_cc(uint32_t a, uint32_t b, uint32_t c) { return addc_cc((uint32_t)((uint64_t)a * b), c); }
+  uint32_t mad_hi_cc(uint32_t a, uint32_t b, uint32_t c) { return add_cc((uint32_t)(((uint64_t)a * b) >> 32), c); }
+  uint32_t madc_hi_cc(uint32_t a, uint32_t b, uint32_t c) { return addc_cc((uint32_t)(((uint64_t)a * b) >> 32), c); }
+  uint32_t madc_hi(uint32_t a, uint32_t b, uint32_t c) { return addc((uint32_t)(((uint64_t)a * b) >> 32), c); }
+};
+#endif
+
+template <class P>
+struct Fp {
+  static constexpr int N = P::N;
+  uint32_t v[N];
+
+  BP_HD static Fp zero() { Fp r; for (int i = 0; i < N; i++) r.v[i] = 0; return r; }
+  BP_HD static Fp one() { Fp r; for (int i = 0; i < N; i++) r.v[i] = P::R1(i); return r; }   // Montgomery 1
+  BP_HD static Fp r2() { Fp r; for (int i = 0; i < N; i++) r.v[i] = P::R2(i); return r; }
+  BP_HD static Fp modulus() { Fp r; for (int i = 0; i < N; i++) r.v[i] = P::P(i); return r; }
+
+  BP_HD bool is_zero() const { uint32_t o = 0; for (int i = 0; i < N; i++) o |= v[i]; return o == 0; }
+  BP_HD bool operator==(const Fp& b) const { uint32_t o = 0; for (int i = 0; i < N; i++) o |= v[i] ^ b.v[i]; return o == 0; }
+  BP_HD bool operator!=(const Fp& b) const { return !(*this == b); }
+
+  // r = a - p if a >= p (a < 2p, possibly with an extra top carry bit `hi`)
+  BP_HD static void reduce_once(uint32_t* a, uint32_t hi = 0) {
+    CarryChain c;
+    uint32_t t[N];
+    t[0] = c.sub_cc(a[0], P::P(0));
+#pragma unroll
+    for (int i = 1; i < N; i++) t[i] = c.subc_cc(a[i], P::P(i));
+    uint32_t borrow = c.subc(hi, 0);          // 0 if a >= p, 0xffffffff otherwise
+#pragma unroll
+    for (int i = 0; i < N; i++) a[i] = borrow ? a[i] : t[i];
+  }
+
+  BP_HD friend Fp operator+(const Fp& a, const Fp& b) {
+    Fp r;
+    CarryChain c;
+    r.v[0] = c.add_cc(a.v[0], b.v[0]);
+#pragma unroll
+    for (int i = 1; i < N; i++) r.v[i] = c.addc_cc(a.v[i], b.v[i]);
+    uint32_t hi = c.addc(0, 0);
+    reduce_once(r.v, hi);
+    return r;
+  }
+
+  BP_HD friend Fp operator-(const Fp& a, const Fp& b) {
+    Fp r;
+    CarryChain c;
+    r.v[0] = c.sub_cc(a.v[0], b.v[0]);
+#pragma unroll
+    for (int i = 1; i < N; i++) r.v[i] = c.subc_cc(a.v[i], b.v[i]);
+    uint32_t borrow = c.subc(0, 0);           // 0xffffffff when a < b
+    CarryChain d;
+    r.v[0] = d.add_cc(r.v[0], P::P(0) & borrow);
+#pragma unroll
+    for (int i = 1; i < N; i++) r.v[i] = d.addc_cc(r.v[i], P::P(i) & borrow);
+    return r;
+  }
+
+  BP_HD Fp neg() const { return zero() - *this; }
+  BP_HD Fp dbl() const { return *this + *this; }
+
+  // ---- Montgomery product, even/odd accumulator schedule (see file header)
+  BP_HD friend Fp operator*(const Fp& a, const Fp& b) {
+    static_assert(N % 2 == 0, "even limb count");
+    uint32_t ev[N], od[N];
+    // row 0: plain products, no accumulation
+    {
+      const uint32_t bi = b.v[0];
+#pragma unroll
+      for (int j = 0; j < N; j += 2) {
+        uint64_t pe = (uint64_t)a.v[j] * bi;       // IMAD.WIDE.U32
+        ev[j] = (uint32_t)pe; ev[j + 1] = (uint32_t)(pe >> 32);
+        uint64_t po = (uint64_t)a.v[j + 1] * bi;
+        od[j] = (uint32_t)po; od[j + 1] = (uint32_t)(po >> 32);
+      }
+      reduce_row(ev, od);
+    }
+#pragma unroll
+    for (int i = 1; i < N; i++) {
+      // roles alternate: after a reduction row the accumulator whose limb 0 was cleared is,
+      // shifted right by one limb, the odd accumulator of the next row.
+      if (i & 1) { mul_row(od, ev, a.v, b.v[i]); reduce_row(od, ev); }
+      else       { mul_row(ev, od, a.v, b.v[i]); reduce_row(ev, od); }
+    }
+    // after N rows (N even) the cleared accumulator is `od`... the last reduce_row call had
+    // (even=od, odd=ev) when N-1 is odd.
+    Fp r;
+    {
+      uint32_t* e = ((N - 1) & 1) ? od : ev;   // accumulator with limb 0 == 0
+      uint32_t* o = ((N - 1) & 1) ? ev : od;
+      CarryChain c;
+      r.v[0] = c.add_cc(o[0], e[1]);
+#pragma unroll
+      for (int k = 1; k < N - 1; k++) r.v[k] = c.addc_cc(o[k], e[k + 1]);
+      r.v[N - 1] = c.addc(o[N - 1], 0);
+    }
+    reduce_once(r.v);
+    return r;
+  }
+
+  BP_HD Fp sqr() const { return (*this) * (*this); }
+
+  // out-of-Montgomery: multiply by 1
+  BP_HD Fp from_mont() const { Fp o; for (int i = 0; i < N; i++) o.v[i] = (i == 0); return (*this) * o; }
+  BP_HD Fp to_mont() const { return (*this) * r2(); }
+
+  // x^e for a public N-limb exponent given by a getter (MSB first square-and-multiply; variable time)
+  template <class E>
+  BP_HD Fp pow_limbs(E exp_limb, int nlimbs) const {
+    Fp acc = one();
+    bool started = false;
+    for (int i = nlimbs - 1; i >= 0; i--) {
+      uint32_t w = exp_limb(i);
+      for (int b = 31; b >= 0; b--) {
+        if (started) acc = acc.sqr();
+        if ((w >> b) & 1) { acc = started ? acc * (*this) : *this; started = true; }
+      }
+    }
+    return acc;
+  }
+  // Fermat inverse; 0 -> 0 (FieldElement::inverse of 0 is 0 in AMCL)
+  BP_HD_COLD Fp inv() const { return pow_limbs([](int i) { return P::PM2(i); }, N); }
+
+ private:
+  // even := od_prev (already at even positions) ; odd := ev_prev >> 64 (register renaming);
+  // then even += a_even*bi, odd += a_odd*bi.
+  //   `even` enters holding the previous odd accumulator, `odd` enters holding the previous even
+  //   accumulator whose limb 0 is zero and whose limb 1 still has to be added at position 0.
+  BP_HD static void mul_row(uint32_t* even, uint32_t* odd, const uint32_t* a, uint32_t bi) {
+    CarryChain c;
+    even[0] = c.add_cc(even[0], odd[1]);                 // carry -> position 1 = first limb of the odd chain
+#pragma unroll
+    for (int j = 0; j < N - 2; j += 2) {                 // odd[k] <- odd[k+2] + a[j+1]*bi  (shifted accumulate)
+      odd[j] = c.madc_lo_cc(a[j + 1], bi, odd[j + 2]);
+      odd[j + 1] = c.madc_hi_cc(a[j + 1], bi, odd[j + 3]);
+    }
+    odd[N - 2] = c.madc_lo_cc(a[N - 1], bi, 0);
+    odd[N - 1] = c.madc_hi(a[N - 1], bi, 0);            // no carry out: value bound < 2^(32(N+1))
+    CarryChain d;
+    even[0] = d.mad_lo_cc(a[0], bi, even[0]);
+    even[1] = d.madc_hi_cc(a[0], bi, even[1]);
+#pragma unroll
+    for (int j = 2; j < N; j += 2) {
+      even[j] = d.madc_lo_cc(a[j], bi, even[j]);
+      even[j + 1] = d.madc_hi_cc(a[j], bi, even[j + 1]);
+    }
+    odd[N - 1] = d.addc(odd[N - 1], 0);                  // position N lives in odd[N-1]
+  }
+
+  // m = even[0] * (-p^-1); even += p_even*m (clears even[0]); odd += p_odd*m
+  BP_HD static void reduce_row(uint32_t* even, uint32_t* odd) {
+    const uint32_t m = even[0] * P::INV;
+    CarryChain c;
+    odd[0] = c.mad_lo_cc(P::PC(1), m, odd[0]);
+    odd[1] = c.madc_hi_cc(P::PC(1), m, odd[1]);
+#pragma unroll
+    for (int j = 2; j < N; j += 2) {
+      odd[j] = c.madc_lo_cc(P::PC(j + 1), m, odd[j]);
+      odd[j + 1] = c.madc_hi_cc(P::PC(j + 1), m, odd[j + 1]);
+    }
+    CarryChain d;
+    even[0] = d.mad_lo_cc(P::PC(0), m, even[0]);
+    even[1] = d.madc_hi_cc(P::PC(0), m, even[1]);
+#pragma unroll
+    for (int j = 2; j < N; j += 2) {
+      even[j] = d.madc_lo_cc(P::PC(j), m, even[j]);
+      even[j + 1] = d.madc_hi_cc(P::PC(j), m, even[j + 1]);
+    }
+    odd[N - 1] = d.addc(odd[N - 1], 0);
+  }
+};
+
+}  // namespace bp

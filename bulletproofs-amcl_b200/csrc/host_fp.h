@@ -1,0 +1,150 @@
+// Host-side (CPU) Montgomery arithmetic on 64-bit limbs, same Montgomery radix as the device
+// (2^(32*N32) = 2^(64*NL)), so device values can be consumed without conversion.
+//
+// Used by the host layer for the parts of the path that are serial by nature and tiny:
+//   * the Horner combination of the <= 64 per-window sums an MSM leaves on the device and the
+//     final affine normalisation (one field inversion) -- a dependent chain of ~256 point
+//     doublings that one GPU thread needs milliseconds for and one CPU core ~0.1 ms;
+//   * Fr arithmetic on challenges (u^-1, y^-1, x^k ...) in the transcript-driven orchestration
+//     (/root/reference/src/ipp.rs:112-113, src/r1cs/prover.rs:438-463,508-546).
+// This is product code, not the oracle: the oracle (oracle/c) has its own independent field code.
+#pragma once
+#include <stdint.h>
+#include <string.h>
+
+#include "field_params.h"
+
+namespace bp {
+namespace host {
+
+template <class P>
+struct HFp {
+  static constexpr int NL = P::N / 2;
+  uint64_t v[NL];
+
+  static uint64_t limb(uint32_t (*f)(int), int i) { return (uint64_t)f(2 * i) | ((uint64_t)f(2 * i + 1) << 32); }
+  static uint64_t pl(int i) { return (uint64_t)P::P(2 * i) | ((uint64_t)P::P(2 * i + 1) << 32); }
+  static uint64_t inv64() {
+    // -p^-1 mod 2^64 by Newton iteration from the 32-bit constant
+    uint64_t p0 = pl(0), x = (uint64_t)(0u - P::INV);  // x = p^-1 mod 2^32
+    x *= 2 - p0 * x;                                    // mod 2^64
+    return 0 - x;
+  }
+  static HFp zero() { HFp r; memset(r.v, 0, sizeof r.v); return r; }
+  static HFp one() { HFp r; for (int i = 0; i < NL; i++) r.v[i] = (uint64_t)P::R1(2 * i) | ((uint64_t)P::R1(2 * i + 1) << 32); return r; }
+  static HFp r2() { HFp r; for (int i = 0; i < NL; i++) r.v[i] = (uint64_t)P::R2(2 * i) | ((uint64_t)P::R2(2 * i + 1) << 32); return r; }
+  static HFp from_u64(uint64_t x) { HFp r = zero(); r.v[0] = x; return r.to_mont(); }
+
+  bool is_zero() const { uint64_t o = 0; for (int i = 0; i < NL; i++) o |= v[i]; return o == 0; }
+  bool operator==(const HFp& b) const { uint64_t o = 0; for (int i = 0; i < NL; i++) o |= v[i] ^ b.v[i]; return o == 0; }
+  bool operator!=(const HFp& b) const { return !(*this == b); }
+
+  static bool geq_p(const uint64_t* a) {
+    for (int i = NL - 1; i >= 0; i--) { uint64_t p = pl(i); if (a[i] > p) return true; if (a[i] < p) return false; }
+    return true;
+  }
+  static void sub_p(uint64_t* a) {
+    unsigned __int128 br = 0;
+    for (int i = 0; i < NL; i++) { unsigned __int128 t = (unsigned __int128)a[i] - pl(i) - (uint64_t)br; a[i] = (uint64_t)t; br = (t >> 64) & 1; }
+  }
+  friend HFp operator+(const HFp& a, const HFp& b) {
+    HFp r; unsigned __int128 c = 0;
+    for (int i = 0; i < NL; i++) { c += (unsigned __int128)a.v[i] + b.v[i]; r.v[i] = (uint64_t)c; c >>= 64; }
+    if (c || geq_p(r.v)) sub_p(r.v);
+    return r;
+  }
+  friend HFp operator-(const HFp& a, const HFp& b) {
+    HFp r; unsigned __int128 br = 0;
+    for (int i = 0; i < NL; i++) { unsigned __int128 t = (unsigned __int128)a.v[i] - b.v[i] - (uint64_t)br; r.v[i] = (uint64_t)t; br = (t >> 64) & 1; }
+    if (br) { unsigned __int128 c = 0; for (int i = 0; i < NL; i++) { c += (unsigned __int128)r.v[i] + pl(i); r.v[i] = (uint64_t)c; c >>= 64; } }
+    return r;
+  }
+  HFp neg() const { return zero() - *this; }
+  HFp dbl() const { return *this + *this; }
+  friend HFp operator*(const HFp& a, const HFp& b) {
+    static const uint64_t INV = inv64();
+    uint64_t p[NL];
+    for (int i = 0; i < NL; i++) p[i] = pl(i);
+    uint64_t t[NL + 2];
+    memset(t, 0, sizeof t);
+    for (int i = 0; i < NL; i++) {
+      unsigned __int128 c = 0;
+      for (int j = 0; j < NL; j++) { c += (unsigned __int128)a.v[j] * b.v[i] + t[j]; t[j] = (uint64_t)c; c >>= 64; }
+      c += t[NL]; t[NL] = (uint64_t)c; t[NL + 1] = (uint64_t)(c >> 64);
+      uint64_t m = t[0] * INV;
+      c = (unsigned __int128)m * p[0] + t[0]; c >>= 64;
+      for (int j = 1; j < NL; j++) { c += (unsigned __int128)m * p[j] + t[j]; t[j - 1] = (uint64_t)c; c >>= 64; }
+      c += t[NL]; t[NL - 1] = (uint64_t)c; t[NL] = t[NL + 1] + (uint64_t)(c >> 64);
+    }
+    if (t[NL] || geq_p(t)) sub_p(t);
+    HFp r; memcpy(r.v, t, sizeof r.v);
+    return r;
+  }
+  HFp sqr() const { return (*this) * (*this); }
+  HFp to_mont() const { return (*this) * r2(); }
+  HFp from_mont() const { HFp o = zero(); o.v[0] = 1; return (*this) * o; }
+  // Fermat inverse, 0 -> 0 (FieldElement::inverse of zero is zero in AMCL)
+  HFp inv() const {
+    uint64_t e[NL];
+    for (int i = 0; i < NL; i++) e[i] = pl(i);
+    e[0] -= 2;
+    HFp acc = one();
+    for (int i = NL - 1; i >= 0; i--)
+      for (int b = 63; b >= 0; b--) { acc = acc.sqr(); if ((e[i] >> b) & 1) acc = acc * (*this); }
+    return acc;
+  }
+  // canonical big-endian bytes <-> Montgomery
+  static HFp from_be(const uint8_t* be, int nbytes) {
+    HFp t;
+    for (int i = 0; i < NL; i++) {
+      uint64_t w = 0; const uint8_t* p = be + nbytes - 8 * (i + 1);
+      for (int k = 0; k < 8; k++) w = (w << 8) | p[k];
+      t.v[i] = w;
+    }
+    while (geq_p(t.v)) sub_p(t.v);
+    return t.to_mont();
+  }
+  void to_be(uint8_t* be, int nbytes) const {
+    HFp t = from_mont();
+    memset(be, 0, nbytes);
+    for (int i = 0; i < NL; i++) { uint8_t* p = be + nbytes - 8 * (i + 1); for (int k = 0; k < 8; k++) p[k] = (uint8_t)(t.v[i] >> (56 - 8 * k)); }
+  }
+};
+
+// XYZZ point on the host; layout-compatible with the device's XYZZ<Fp<P>> (little-endian limbs)
+template <class P>
+struct HXYZZ {
+  using F = HFp<P>;
+  F x, y, zz, zzz;
+  bool is_inf() const { return zz.is_zero(); }
+  static HXYZZ inf() { HXYZZ p; p.x = p.y = p.zz = p.zzz = F::zero(); return p; }
+  void dbl() {
+    if (is_inf()) return;
+    if (y.is_zero()) { *this = inf(); return; }
+    F U = y.dbl(), V = U.sqr(), W = U * V, S = x * V, X2 = x.sqr(), M = X2.dbl() + X2;
+    F X3 = M.sqr() - S.dbl();
+    F Y3 = M * (S - X3) - W * y;
+    zz = V * zz; zzz = W * zzz; x = X3; y = Y3;
+  }
+  void add(const HXYZZ& q) {
+    if (q.is_inf()) return;
+    if (is_inf()) { *this = q; return; }
+    F U1 = x * q.zz, U2 = q.x * zz, S1 = y * q.zzz, S2 = q.y * zzz;
+    F Pd = U2 - U1, R = S2 - S1;
+    if (Pd.is_zero()) { if (R.is_zero()) dbl(); else *this = inf(); return; }
+    F PP = Pd.sqr(), PPP = Pd * PP, Q = U1 * PP;
+    F X3 = R.sqr() - PPP - Q.dbl();
+    F Y3 = R * (Q - X3) - S1 * PPP;
+    zz = zz * q.zz * PP; zzz = zzz * q.zzz * PPP; x = X3; y = Y3;
+  }
+  // X||Y big endian, identity = AMCL's (0, 1)
+  void to_xy_be(int modbytes, uint8_t* out) const {
+    if (is_inf()) { memset(out, 0, 2 * modbytes); out[2 * modbytes - 1] = 1; return; }
+    F i3 = zzz.inv(), i1 = i3 * zz;
+    F ax = x * i1.sqr(), ay = y * i3;
+    ax.to_be(out, modbytes); ay.to_be(out + modbytes, modbytes);
+  }
+};
+
+}  // namespace host
+}  // namespace bp

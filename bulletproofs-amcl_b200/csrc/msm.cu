@@ -1,0 +1,418 @@
+// G1 multi-scalar multiplication for sm_100a: signed-digit Pippenger with a balanced,
+// sort-based bucket accumulation.
+//
+// Replaces amcl_wrapper's Straus/wNAF `multi_scalar_mul_var_time`,
+// `inner_product_var_time_with_ref_vecs` and the fixed-window `inner_product_const_time`
+// (call sites /root/reference/src/ipp.rs:91,104,158,170,251-253; src/r1cs/verifier.rs:451;
+// src/r1cs/prover.rs:347-362).  Output is the normalised affine point, which is unique, so the
+// different summation order changes no observable byte.
+//
+// Pipeline (all on one stream, inputs and every intermediate resident in HBM):
+//   k_digits        scalars -> W signed c-bit digits each, histogram per (window, bucket)
+//   k_scan          per window: bucket start offsets + offsets of the per-chunk partial sums
+//   k_scatter       counting-sort scatter of (point index | sign) by bucket
+//   k_chunk_acc     ONE THREAD PER FIXED-SIZE CHUNK of the sorted list: S mixed XYZZ additions
+//                   each, whatever the bucket sizes are -> no divergence between lanes and no
+//                   serialisation on a hot bucket (0/1 witness scalars put half of all points
+//                   in one bucket: helper_constraints/positive_no.rs:18-24)
+//   k_bucket_finish per bucket: add the few chunk partials; buckets spanning > T chunks go to
+//   k_giant         a block-wide tree reduction
+//   k_reduce_chunks running-sum of L consecutive buckets + small multiple for the chunk offset
+//   k_window_sum    tree over a window's chunk results
+//   (host)          Horner over the W window sums + affine normalisation: a ~256-doubling
+//                   dependent chain, ~0.1 ms on one CPU core vs milliseconds on one GPU thread
+#include <stdlib.h>
+
+#include "common.cuh"
+
+namespace bp {
+
+struct MsmGeom {
+  uint32_t n;       // number of terms
+  int c;            // window bits
+  int W;            // windows
+  uint32_t nbp;     // bucket slots per window = 2^(c-1) + 1 (slot 0 unused)
+  uint32_t S;       // sorted entries per chunk thread
+  uint32_t nchunk;  // chunk threads per window = ceil(n / S)
+  uint32_t pcap;    // partial-sum slots per window = nchunk + nbp
+  uint32_t L;       // buckets per reduce thread
+  uint32_t nrch;    // reduce threads per window = ceil((nbp - 1) / L)
+};
+
+static const int GIANT_T = 8;          // buckets with more partials than this use k_giant
+static const int GIANT_BLOCK = 128;
+
+int msm_window_bits(size_t n) {
+  if (n == 0) return 4;
+  double best = 1e300;
+  int bc = 4;
+  for (int c = 3; c <= 18; c++) {
+    int W = (256 + c - 1) / c;
+    double cost = (double)W * ((double)n * 10.0 + (double)(1u << (c - 1)) * 60.0);
+    if (cost < best) { best = cost; bc = c; }
+  }
+  return bc;
+}
+
+// ------------------------------------------------------------------------------------------
+template <class Fr>
+__global__ void __launch_bounds__(256) k_digits(const Fr* __restrict__ scal, int mont, MsmGeom g,
+                                                uint32_t* __restrict__ digits, uint32_t* __restrict__ hist) {
+  uint32_t i = blockIdx.x * blockDim.x + threadIdx.x;
+  if (i >= g.n) return;
+  Fr s = load_vec(scal + i);
+  if (mont) s = s.from_mont();
+  uint32_t limbs[9];
+#pragma unroll
+  for (int k = 0; k < 8; k++) limbs[k] = s.v[k];
+  limbs[8] = 0;
+  const uint32_t half = 1u << (g.c - 1);
+  const uint32_t mask = (1u << g.c) - 1;
+  uint32_t carry = 0;
+  for (int w = 0; w < g.W; w++) {
+    uint32_t bit = (uint32_t)w * g.c;
+    uint32_t limb = bit >> 5, sh = bit & 31;
+    uint32_t d = 0;
+    if (limb < 8) {
+      uint64_t two = (uint64_t)limbs[limb] | ((uint64_t)limbs[limb + 1] << 32);
+      d = (uint32_t)(two >> sh) & mask;
+    }
+    d += carry;
+    uint32_t mag, sign;
+    if (d > half) { mag = (mask + 1) - d; sign = 0x80000000u; carry = 1; }
+    else { mag = d; sign = 0; carry = 0; }
+    digits[(size_t)w * g.n + i] = mag ? (mag | sign) : 0u;
+    if (mag) atomicAdd(&hist[(size_t)w * g.nbp + mag], 1u);
+  }
+}
+
+__device__ __forceinline__ uint32_t block_excl_scan_1024(uint32_t v, uint32_t* total_out) {
+  __shared__ uint32_t warp_tot[32];
+  __shared__ uint32_t total;
+  const int lane = threadIdx.x & 31, wid = threadIdx.x >> 5;
+  uint32_t inc = v;
+#pragma unroll
+  for (int o = 1; o < 32; o <<= 1) {
+    uint32_t t = __shfl_up_sync(0xffffffffu, inc, o);
+    if (lane >= o) inc += t;
+  }
+  if (lane == 31) warp_tot[wid] = inc;
+  __syncthreads();
+  if (wid == 0) {
+    uint32_t wv = warp_tot[lane];
+    uint32_t winc = wv;
+#pragma unroll
+    for (int o = 1; o < 32; o <<= 1) {
+      uint32_t t = __shfl_up_sync(0xffffffffu, winc, o);
+      if (lane >= o) winc += t;
+    }
+    warp_tot[lane] = winc - wv;
+    if (lane == 31) total = winc;
+  }
+  __syncthreads();
+  uint32_t res = warp_tot[wid] + inc - v;
+  *total_out = total;
+  __syncthreads();
+  return res;
+}
+
+// one block of 1024 threads per window
+__global__ void __launch_bounds__(1024) k_scan(MsmGeom g, uint32_t* __restrict__ hist, uint32_t* __restrict__ bstart,
+                                               uint32_t* __restrict__ cursor, uint32_t* __restrict__ pstart) {
+  const int w = blockIdx.x;
+  uint32_t* h = hist + (size_t)w * g.nbp;
+  uint32_t* bs = bstart + (size_t)w * (g.nbp + 1);
+  uint32_t* cu = cursor + (size_t)w * g.nbp;
+  uint32_t* ps = pstart + (size_t)w * (g.nbp + 1);
+  const uint32_t per = (g.nbp + 1023) / 1024;
+  const uint32_t lo = threadIdx.x * per;
+  const uint32_t hi = min(lo + per, g.nbp);
+  uint32_t sum = 0;
+  for (uint32_t b = lo; b < hi; b++) sum += h[b];
+  uint32_t total;
+  uint32_t run = block_excl_scan_1024(sum, &total);
+  uint32_t npsum = 0;
+  for (uint32_t b = lo; b < hi; b++) {
+    uint32_t cnt = h[b];
+    bs[b] = run;
+    cu[b] = run;
+    uint32_t np = cnt ? ((run + cnt - 1) / g.S - run / g.S + 1) : 0;
+    h[b] = np;                       // the histogram slot now holds the partial count
+    npsum += np;
+    run += cnt;
+  }
+  if (threadIdx.x == 0) bs[g.nbp] = total;
+  uint32_t total2;
+  uint32_t run2 = block_excl_scan_1024(npsum, &total2);
+  for (uint32_t b = lo; b < hi; b++) { ps[b] = run2; run2 += h[b]; }
+  if (threadIdx.x == 0) ps[g.nbp] = total2;
+}
+
+__global__ void __launch_bounds__(256) k_scatter(MsmGeom g, const uint32_t* __restrict__ digits, uint32_t* __restrict__ cursor,
+                                                 uint32_t* __restrict__ sidx, uint32_t* __restrict__ skey) {
+  const size_t total = (size_t)g.W * g.n;
+  for (size_t t = (size_t)blockIdx.x * blockDim.x + threadIdx.x; t < total; t += (size_t)gridDim.x * blockDim.x) {
+    uint32_t d = digits[t];
+    if (!d) continue;
+    uint32_t w = (uint32_t)(t / g.n), i = (uint32_t)(t - (size_t)w * g.n);
+    uint32_t mag = d & 0x7fffffffu;
+    uint32_t pos = atomicAdd(&cursor[(size_t)w * g.nbp + mag], 1u);
+    sidx[(size_t)w * g.n + pos] = i | (d & 0x80000000u);
+    skey[(size_t)w * g.n + pos] = mag;
+  }
+}
+
+template <class Fq>
+__global__ void __launch_bounds__(128) k_chunk_acc(MsmGeom g, const Affine<Fq>* __restrict__ pts,
+                                                   const uint32_t* __restrict__ sidx, const uint32_t* __restrict__ skey,
+                                                   const uint32_t* __restrict__ bstart, const uint32_t* __restrict__ pstart,
+                                                   XYZZ<Fq>* __restrict__ partials) {
+  const uint32_t gid = blockIdx.x * blockDim.x + threadIdx.x;
+  if (gid >= (uint32_t)g.W * g.nchunk) return;
+  const uint32_t w = gid / g.nchunk, t = gid - w * g.nchunk;
+  const uint32_t* bs = bstart + (size_t)w * (g.nbp + 1);
+  const uint32_t* ps = pstart + (size_t)w * (g.nbp + 1);
+  const uint32_t cnt = bs[g.nbp];
+  const uint32_t e0 = t * g.S;
+  if (e0 >= cnt) return;
+  const uint32_t e1 = min(e0 + g.S, cnt);
+  const uint32_t* idx = sidx + (size_t)w * g.n;
+  const uint32_t* key = skey + (size_t)w * g.n;
+  XYZZ<Fq>* out = partials + (size_t)w * g.pcap;
+  XYZZ<Fq> acc = XYZZ<Fq>::inf();
+  uint32_t cur = key[e0];
+  for (uint32_t e = e0; e < e1; e++) {
+    uint32_t k = key[e];
+    if (k != cur) {
+      store_vec(out + ps[cur] + (t - bs[cur] / g.S), acc);
+      acc = XYZZ<Fq>::inf();
+      cur = k;
+    }
+    uint32_t id = idx[e];
+    Affine<Fq> P = load_vec_ro(pts + (id & 0x7fffffffu));
+    if (id >> 31) P.y = P.y.neg();
+    acc.madd(P);
+  }
+  store_vec(out + ps[cur] + (t - bs[cur] / g.S), acc);
+}
+
+template <class Fq>
+__global__ void __launch_bounds__(128) k_bucket_finish(MsmGeom g, const uint32_t* __restrict__ pstart,
+                                                       const XYZZ<Fq>* __restrict__ partials, XYZZ<Fq>* __restrict__ buckets,
+                                                       uint32_t* __restrict__ giant_count, uint32_t* __restrict__ giant_list) {
+  const uint32_t gid = blockIdx.x * blockDim.x + threadIdx.x;
+  if (gid >= (uint32_t)g.W * g.nbp) return;
+  const uint32_t w = gid / g.nbp, b = gid - w * g.nbp;
+  if (b == 0) return;
+  const uint32_t* ps = pstart + (size_t)w * (g.nbp + 1);
+  const uint32_t p0 = ps[b], p1 = ps[b + 1];
+  const XYZZ<Fq>* in = partials + (size_t)w * g.pcap;
+  const uint32_t cnt = p1 - p0;
+  if (cnt > (uint32_t)GIANT_T) {
+    uint32_t slot = atomicAdd(giant_count, 1u);
+    giant_list[slot] = gid;
+    return;
+  }
+  XYZZ<Fq> acc = XYZZ<Fq>::inf();
+  if (cnt) {
+    acc = load_vec(in + p0);
+    for (uint32_t k = 1; k < cnt; k++) { XYZZ<Fq> q = load_vec(in + p0 + k); acc.add(q); }
+  }
+  store_vec(buckets + gid, acc);
+}
+
+template <class Fq>
+__device__ __forceinline__ XYZZ<Fq> block_tree_sum(XYZZ<Fq> v, XYZZ<Fq>* sm) {
+  store_vec(sm + threadIdx.x, v);
+  __syncthreads();
+  for (int o = blockDim.x / 2; o > 0; o >>= 1) {
+    if ((int)threadIdx.x < o) {
+      XYZZ<Fq> a = load_vec(sm + threadIdx.x), b = load_vec(sm + threadIdx.x + o);
+      a.add(b);
+      store_vec(sm + threadIdx.x, a);
+    }
+    __syncthreads();
+  }
+  XYZZ<Fq> r = load_vec(sm);
+  __syncthreads();
+  return r;
+}
+
+template <class Fq>
+__global__ void __launch_bounds__(GIANT_BLOCK) k_giant(MsmGeom g, const uint32_t* __restrict__ pstart,
+                                                       const XYZZ<Fq>* __restrict__ partials, XYZZ<Fq>* __restrict__ buckets,
+                                                       const uint32_t* __restrict__ giant_count, const uint32_t* __restrict__ giant_list) {
+  __shared__ __align__(16) unsigned char smraw[GIANT_BLOCK * sizeof(XYZZ<Fq>)];
+  XYZZ<Fq>* sm = reinterpret_cast<XYZZ<Fq>*>(smraw);
+  const uint32_t ng = *giant_count;
+  for (uint32_t gi = blockIdx.x; gi < ng; gi += gridDim.x) {
+    const uint32_t gid = giant_list[gi];
+    const uint32_t w = gid / g.nbp, b = gid - w * g.nbp;
+    const uint32_t* ps = pstart + (size_t)w * (g.nbp + 1);
+    const uint32_t p0 = ps[b], p1 = ps[b + 1];
+    const XYZZ<Fq>* in = partials + (size_t)w * g.pcap;
+    XYZZ<Fq> acc = XYZZ<Fq>::inf();
+    for (uint32_t k = p0 + threadIdx.x; k < p1; k += blockDim.x) { XYZZ<Fq> q = load_vec(in + k); acc.add(q); }
+    XYZZ<Fq> tot = block_tree_sum(acc, sm);
+    if (threadIdx.x == 0) store_vec(buckets + gid, tot);
+  }
+}
+
+// sum_{b in chunk} b * B_b  for L consecutive buckets, one thread per chunk
+template <class Fq>
+__global__ void __launch_bounds__(128) k_reduce_chunks(MsmGeom g, const XYZZ<Fq>* __restrict__ buckets, XYZZ<Fq>* __restrict__ wpart) {
+  const uint32_t gid = blockIdx.x * blockDim.x + threadIdx.x;
+  if (gid >= (uint32_t)g.W * g.nrch) return;
+  const uint32_t w = gid / g.nrch, ch = gid - w * g.nrch;
+  const uint32_t lo = ch * g.L + 1;
+  const uint32_t hi = min(lo + g.L - 1, g.nbp - 1);
+  const XYZZ<Fq>* B = buckets + (size_t)w * g.nbp;
+  XYZZ<Fq> run = XYZZ<Fq>::inf(), acc = XYZZ<Fq>::inf();
+  for (uint32_t b = hi; b >= lo; b--) {
+    XYZZ<Fq> q = load_vec(B + b);
+    run.add(q);
+    acc.add(run);
+  }
+  if (lo > 1) { XYZZ<Fq> m = mul_small(run, lo - 1); acc.add(m); }
+  store_vec(wpart + gid, acc);
+}
+
+template <class Fq>
+__global__ void __launch_bounds__(GIANT_BLOCK) k_window_sum(MsmGeom g, const XYZZ<Fq>* __restrict__ wpart, XYZZ<Fq>* __restrict__ winsum) {
+  __shared__ __align__(16) unsigned char smraw[GIANT_BLOCK * sizeof(XYZZ<Fq>)];
+  XYZZ<Fq>* sm = reinterpret_cast<XYZZ<Fq>*>(smraw);
+  const uint32_t w = blockIdx.x;
+  XYZZ<Fq> acc = XYZZ<Fq>::inf();
+  for (uint32_t k = threadIdx.x; k < g.nrch; k += blockDim.x) { XYZZ<Fq> q = load_vec(wpart + (size_t)w * g.nrch + k); acc.add(q); }
+  XYZZ<Fq> tot = block_tree_sum(acc, sm);
+  if (threadIdx.x == 0) store_vec(winsum + w, tot);
+}
+
+// ------------------------------------------------------------------------------------------
+static inline size_t align256(size_t x) { return (x + 255) & ~(size_t)255; }
+
+struct StageTimer {
+  bool on;
+  cudaStream_t st;
+  std::vector<cudaEvent_t> ev;
+  std::vector<const char*> names;
+  StageTimer(cudaStream_t s) : on(getenv("BPGPU_PROFILE") != nullptr), st(s) { mark("start"); }
+  void mark(const char* name) {
+    if (!on) return;
+    cudaEvent_t e; cudaEventCreate(&e); cudaEventRecord(e, st);
+    ev.push_back(e); names.push_back(name);
+  }
+  void report(const MsmGeom& g) {
+    if (!on) return;
+    cudaEventSynchronize(ev.back());
+    fprintf(stderr, "[bpgpu msm n=%u c=%d W=%d S=%u L=%u]", g.n, g.c, g.W, g.S, g.L);
+    for (size_t i = 1; i < ev.size(); i++) { float ms; cudaEventElapsedTime(&ms, ev[i - 1], ev[i]); fprintf(stderr, " %s=%.3f", names[i], ms); }
+    float tot; cudaEventElapsedTime(&tot, ev.front(), ev.back());
+    fprintf(stderr, " total=%.3fms\n", tot);
+    for (auto e : ev) cudaEventDestroy(e);
+  }
+};
+
+// Leaves the W per-window sums (XYZZ, Montgomery form) in ctx scratch; the caller combines them
+// (Horner over windows + affine normalisation) on the host, see msm_finish_host in api.cu.
+template <class Curve>
+int msm_run(bpgpu_ctx* ctx, const Affine<typename Curve::Fq>* d_points, const void* d_scalars, bool scalars_mont, size_t n,
+            MsmResult* res) {
+  using Fq = typename Curve::Fq;
+  using Fr = typename Curve::Fr;
+  cudaStream_t st = ctx->stream;
+  res->W = 0; res->c = 0; res->d_winsum = nullptr;
+  if (n == 0) return BPGPU_OK;
+  if (n >= (1ull << 31)) return BPGPU_E_ARG;
+  MsmGeom g;
+  g.n = (uint32_t)n;
+  g.c = msm_window_bits(n);
+  g.W = (Curve::SCALAR_BITS + 1 + g.c - 1) / g.c;
+  g.nbp = (1u << (g.c - 1)) + 1;
+  {
+    // entries per chunk thread: keep >= ~64k chunk threads in flight when the problem allows it
+    uint64_t entries = (uint64_t)g.W * n;
+    uint64_t s = entries / 65536;
+    g.S = (uint32_t)(s < 4 ? 4 : (s > 32 ? 32 : s));
+  }
+  g.nchunk = (g.n + g.S - 1) / g.S;
+  g.pcap = g.nchunk + g.nbp;
+  {
+    uint64_t buckets = (uint64_t)g.W * (g.nbp - 1);
+    uint64_t l = buckets / 131072;
+    g.L = (uint32_t)(l < 2 ? 2 : (l > 16 ? 16 : l));
+  }
+  g.nrch = (g.nbp - 1 + g.L - 1) / g.L;
+
+  // ---- scratch layout
+  const size_t sz_digits = align256((size_t)g.W * n * 4);
+  const size_t sz_hist = align256((size_t)g.W * g.nbp * 4);
+  const size_t sz_bstart = align256((size_t)g.W * (g.nbp + 1) * 4);
+  const size_t sz_giant = align256(((size_t)g.W * g.nbp + 1) * 4);
+  int rc;
+  if ((rc = ctx->msm_a.reserve(sz_digits * 3 + sz_hist * 2 + sz_bstart * 2 + sz_giant))) return rc;
+  uint8_t* base = (uint8_t*)ctx->msm_a.p;
+  uint32_t* digits = (uint32_t*)base; base += sz_digits;
+  uint32_t* sidx = (uint32_t*)base; base += sz_digits;
+  uint32_t* skey = (uint32_t*)base; base += sz_digits;
+  uint32_t* hist = (uint32_t*)base; base += sz_hist;
+  uint32_t* cursor = (uint32_t*)base; base += sz_hist;
+  uint32_t* bstart = (uint32_t*)base; base += sz_bstart;
+  uint32_t* pstart = (uint32_t*)base; base += sz_bstart;
+  uint32_t* giant = (uint32_t*)base;  // [0] = count, [1..] = list
+  const size_t sz_part = align256((size_t)g.W * g.pcap * sizeof(XYZZ<Fq>));
+  const size_t sz_buck = align256((size_t)g.W * g.nbp * sizeof(XYZZ<Fq>));
+  const size_t sz_wpart = align256((size_t)g.W * g.nrch * sizeof(XYZZ<Fq>));
+  const size_t sz_wsum = align256((size_t)g.W * sizeof(XYZZ<Fq>));
+  if ((rc = ctx->msm_b.reserve(sz_part + sz_buck + sz_wpart + sz_wsum))) return rc;
+  uint8_t* b2 = (uint8_t*)ctx->msm_b.p;
+  XYZZ<Fq>* partials = (XYZZ<Fq>*)b2; b2 += sz_part;
+  XYZZ<Fq>* buckets = (XYZZ<Fq>*)b2; b2 += sz_buck;
+  XYZZ<Fq>* wpart = (XYZZ<Fq>*)b2; b2 += sz_wpart;
+  XYZZ<Fq>* winsum = (XYZZ<Fq>*)b2;
+
+  StageTimer tm(st);
+  BP_CUDA_OK(cudaMemsetAsync(hist, 0, sz_hist, st));
+  BP_CUDA_OK(cudaMemsetAsync(giant, 0, 4, st));
+
+  k_digits<Fr><<<(g.n + 255) / 256, 256, 0, st>>>((const Fr*)d_scalars, scalars_mont ? 1 : 0, g, digits, hist);
+  tm.mark("digits");
+  k_scan<<<g.W, 1024, 0, st>>>(g, hist, bstart, cursor, pstart);
+  tm.mark("scan");
+  {
+    size_t total = (size_t)g.W * n;
+    size_t blocks = (total + 255) / 256;
+    size_t cap = (size_t)ctx->sm_count * 32;
+    if (blocks > cap) blocks = cap;
+    k_scatter<<<(unsigned)blocks, 256, 0, st>>>(g, digits, cursor, sidx, skey);
+    tm.mark("scatter");
+  }
+  {
+    uint32_t threads = (uint32_t)g.W * g.nchunk;
+    k_chunk_acc<Fq><<<(threads + 127) / 128, 128, 0, st>>>(g, d_points, sidx, skey, bstart, pstart, partials);
+    tm.mark("chunk_acc");
+  }
+  {
+    uint32_t threads = (uint32_t)g.W * g.nbp;
+    k_bucket_finish<Fq><<<(threads + 127) / 128, 128, 0, st>>>(g, pstart, partials, buckets, giant, giant + 1);
+    k_giant<Fq><<<ctx->sm_count * 2, GIANT_BLOCK, 0, st>>>(g, pstart, partials, buckets, giant, giant + 1);
+    tm.mark("finish+giant");
+  }
+  {
+    uint32_t threads = (uint32_t)g.W * g.nrch;
+    k_reduce_chunks<Fq><<<(threads + 127) / 128, 128, 0, st>>>(g, buckets, wpart);
+    tm.mark("reduce_chunks");
+  }
+  k_window_sum<Fq><<<g.W, GIANT_BLOCK, 0, st>>>(g, wpart, winsum);
+  tm.mark("window_sum");
+  ctx->launches += 8;
+  res->W = g.W; res->c = g.c; res->d_winsum = winsum;
+  int lrc = launch_check(ctx, "msm");
+  tm.report(g);
+  return lrc;
+}
+
+template int msm_run<Bls>(bpgpu_ctx*, const Affine<Bls::Fq>*, const void*, bool, size_t, MsmResult*);
+template int msm_run<Bn>(bpgpu_ctx*, const Affine<Bn::Fq>*, const void*, bool, size_t, MsmResult*);
+
+}  // namespace bp

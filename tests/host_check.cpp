@@ -1,0 +1,53 @@
+// Host build of the device headers (fp.cuh / ec.cuh) so the exact limb schedule and group
+// formulas the kernels use can be unit-tested on a machine without a GPU.  Compiled by
+// tests/test_host_arith.py with g++; NOT part of the product library.
+#include <string.h>
+#include "../bulletproofs-amcl_b200/csrc/ec.cuh"
+
+using namespace bp;
+
+template <class F>
+static void fp_op(int op, const uint32_t* a, const uint32_t* b, uint32_t* out) {
+  F x, y, r;
+  memcpy(x.v, a, sizeof(x.v));
+  memcpy(y.v, b, sizeof(y.v));
+  switch (op) {
+    case 0: r = x * y; break;
+    case 1: r = x + y; break;
+    case 2: r = x - y; break;
+    case 3: r = x.to_mont(); break;
+    case 4: r = x.from_mont(); break;
+    case 5: r = x.inv(); break;
+    case 6: r = x.sqr(); break;
+    default: r = F::zero();
+  }
+  memcpy(out, r.v, sizeof(r.v));
+}
+
+// points are passed as Montgomery-form limbs: affine = x|y, xyzz = x|y|zz|zzz
+template <class F>
+static void ec_op(int op, const uint32_t* p, const uint32_t* q, uint32_t k, uint32_t* out) {
+  XYZZ<F> P;
+  memcpy(&P, p, sizeof(P));
+  if (op == 0) { Affine<F> A; memcpy(&A, q, sizeof(A)); P.madd(A); }
+  else if (op == 1) { XYZZ<F> Q; memcpy(&Q, q, sizeof(Q)); P.add(Q); }
+  else if (op == 2) { P.dbl(); }
+  else if (op == 3) { P = mul_small(P, k); }
+  else if (op == 4) { Affine<F> A = P.to_affine(); P = XYZZ<F>::from_affine(A); }
+  memcpy(out, &P, sizeof(P));
+}
+
+extern "C" {
+void hc_fp_op(int field, int op, const uint32_t* a, const uint32_t* b, uint32_t* out) {
+  switch (field) {
+    case 0: fp_op<Fp<BlsFq>>(op, a, b, out); break;
+    case 1: fp_op<Fp<BlsFr>>(op, a, b, out); break;
+    case 2: fp_op<Fp<BnFq>>(op, a, b, out); break;
+    case 3: fp_op<Fp<BnFr>>(op, a, b, out); break;
+  }
+}
+void hc_ec_op(int curve, int op, const uint32_t* p, const uint32_t* q, uint32_t k, uint32_t* out) {
+  if (curve == 0) ec_op<Fp<BlsFq>>(op, p, q, k, out);
+  else ec_op<Fp<BnFq>>(op, p, q, k, out);
+}
+}
