@@ -191,12 +191,14 @@ static int fetch_result(bpgpu_ctx* ctx, const void* d_src, size_t bytes, uint8_t
 
 // Horner over the per-window sums + affine normalisation, on the host (see host_fp.h for why)
 template <class FqParams>
-static void msm_finish_host(const uint8_t* winsum_bytes, int W, int c, int modbytes, uint8_t* out_xy) {
+static void msm_finish_host(const uint8_t* winsum_bytes, int W, int c, int qshift, int modbytes, uint8_t* out_xy) {
   using HP = host::HXYZZ<FqParams>;
   HP acc = HP::inf();
   const HP* ws = reinterpret_cast<const HP*>(winsum_bytes);
   for (int w = W - 1; w >= 0; w--) {
     if (w != W - 1) for (int k = 0; k < c; k++) acc.dbl();
+    HP q = ws[W + w];
+    if (!q.is_inf()) { for (int k = 0; k < qshift; k++) q.dbl(); acc.add(q); }
     acc.add(ws[w]);
   }
   acc.to_xy_be(modbytes, out_xy);
@@ -386,11 +388,11 @@ static int msm_dispatch(bpgpu_ctx* ctx, const void* d_pts, const void* d_scal, b
   if (rc) return rc;
   size_t psz = (ctx->curve == BPGPU_BLS12_381) ? sizeof(XYZZ<Bls::Fq>) : sizeof(XYZZ<Bn::Fq>);
   if (res.W) {
-    BP_CUDA_OK(cudaMemcpyAsync(ctx->pinned, res.d_winsum, res.W * psz, cudaMemcpyDeviceToHost, ctx->stream));
+    BP_CUDA_OK(cudaMemcpyAsync(ctx->pinned, res.d_winsum, 2 * res.W * psz, cudaMemcpyDeviceToHost, ctx->stream));
     BP_CUDA_OK(cudaStreamSynchronize(ctx->stream));
   }
-  if (ctx->curve == BPGPU_BLS12_381) msm_finish_host<BlsFq>(ctx->pinned, res.W, res.c, mb, out_xy);
-  else msm_finish_host<BnFq>(ctx->pinned, res.W, res.c, mb, out_xy);
+  if (ctx->curve == BPGPU_BLS12_381) msm_finish_host<BlsFq>(ctx->pinned, res.W, res.c, res.qshift, mb, out_xy);
+  else msm_finish_host<BnFq>(ctx->pinned, res.W, res.c, res.qshift, mb, out_xy);
   return BPGPU_OK;
 }
 

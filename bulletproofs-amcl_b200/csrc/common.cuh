@@ -139,7 +139,8 @@ __device__ __forceinline__ void canonicalise(F& x) {
 int launch_check(bpgpu_ctx* ctx, const char* what);
 
 // per-window sums an MSM leaves on the device: result = sum_w 2^(c*w) * winsum[w]
-struct MsmResult { int W; int c; const void* d_winsum; };
+// window w = P_w + 2^qshift * Q_w with P = d_winsum[0..W), Q = d_winsum[W..2W)
+struct MsmResult { int W; int c; int qshift; const void* d_winsum; };
 
 template <class Curve> int msm_run(bpgpu_ctx* ctx, const Affine<typename Curve::Fq>* d_points, const void* d_scalars,
                                    bool scalars_mont, size_t n, MsmResult* res);

@@ -15,10 +15,10 @@
 //                   each, whatever the bucket sizes are -> no divergence between lanes and no
 //                   serialisation on a hot bucket (0/1 witness scalars put half of all points
 //                   in one bucket: helper_constraints/positive_no.rs:18-24)
-//   k_bucket_finish per bucket: add the few chunk partials; buckets spanning > T chunks go to
-//   k_giant         a block-wide tree reduction
-//   k_reduce_chunks running-sum of L consecutive buckets + small multiple for the chunk offset
-//   k_window_sum    tree over a window's chunk results
+//   k_giant         buckets spanning > T chunks: block-wide tree reduction, collapsed in place
+//   k_reduce_l1     one WARP per 32*L1 buckets: lanes run top-down running sums over their buckets'
+//                   chunk partials, then a warp suffix-scan turns them into sum (b-base)*B_b
+//   k_reduce_l2     per window: combine the segment results (two warps)
 //   (host)          Horner over the W window sums + affine normalisation: a ~256-doubling
 //                   dependent chain, ~0.1 ms on one CPU core vs milliseconds on one GPU thread
 #include <stdlib.h>
@@ -35,11 +35,12 @@ struct MsmGeom {
   uint32_t S;       // sorted entries per chunk thread
   uint32_t nchunk;  // chunk threads per window = ceil(n / S)
   uint32_t pcap;    // partial-sum slots per window = nchunk + nbp
-  uint32_t L;       // buckets per reduce thread
-  uint32_t nrch;    // reduce threads per window = ceil((nbp - 1) / L)
+  int lgL1;         // log2(buckets per lane) in k_reduce_l1; a warp covers 32 << lgL1 buckets
+  uint32_t nseg;    // level-1 warps (segments) per window
+  int lgL2;         // log2(segments per lane) in k_reduce_l2
 };
 
-static const int GIANT_T = 8;          // buckets with more partials than this use k_giant
+static const int GIANT_T = 16;         // buckets with more partials than this are collapsed by k_giant
 static const int GIANT_BLOCK = 128;
 
 int msm_window_bits(size_t n) {
@@ -118,7 +119,8 @@ __device__ __forceinline__ uint32_t block_excl_scan_1024(uint32_t v, uint32_t* t
 
 // one block of 1024 threads per window
 __global__ void __launch_bounds__(1024) k_scan(MsmGeom g, uint32_t* __restrict__ hist, uint32_t* __restrict__ bstart,
-                                               uint32_t* __restrict__ cursor, uint32_t* __restrict__ pstart) {
+                                               uint32_t* __restrict__ cursor, uint32_t* __restrict__ pstart,
+                                               uint32_t* __restrict__ giant_count, uint32_t* __restrict__ giant_list) {
   const int w = blockIdx.x;
   uint32_t* h = hist + (size_t)w * g.nbp;
   uint32_t* bs = bstart + (size_t)w * (g.nbp + 1);
@@ -138,6 +140,7 @@ __global__ void __launch_bounds__(1024) k_scan(MsmGeom g, uint32_t* __restrict__
     cu[b] = run;
     uint32_t np = cnt ? ((run + cnt - 1) / g.S - run / g.S + 1) : 0;
     h[b] = np;                       // the histogram slot now holds the partial count
+    if (np > (uint32_t)GIANT_T) giant_list[atomicAdd(giant_count, 1u)] = (uint32_t)w * g.nbp + b;
     npsum += np;
     run += cnt;
   }
@@ -197,31 +200,6 @@ __global__ void __launch_bounds__(128) k_chunk_acc(MsmGeom g, const Affine<Fq>* 
 }
 
 template <class Fq>
-__global__ void __launch_bounds__(128) k_bucket_finish(MsmGeom g, const uint32_t* __restrict__ pstart,
-                                                       const XYZZ<Fq>* __restrict__ partials, XYZZ<Fq>* __restrict__ buckets,
-                                                       uint32_t* __restrict__ giant_count, uint32_t* __restrict__ giant_list) {
-  const uint32_t gid = blockIdx.x * blockDim.x + threadIdx.x;
-  if (gid >= (uint32_t)g.W * g.nbp) return;
-  const uint32_t w = gid / g.nbp, b = gid - w * g.nbp;
-  if (b == 0) return;
-  const uint32_t* ps = pstart + (size_t)w * (g.nbp + 1);
-  const uint32_t p0 = ps[b], p1 = ps[b + 1];
-  const XYZZ<Fq>* in = partials + (size_t)w * g.pcap;
-  const uint32_t cnt = p1 - p0;
-  if (cnt > (uint32_t)GIANT_T) {
-    uint32_t slot = atomicAdd(giant_count, 1u);
-    giant_list[slot] = gid;
-    return;
-  }
-  XYZZ<Fq> acc = XYZZ<Fq>::inf();
-  if (cnt) {
-    acc = load_vec(in + p0);
-    for (uint32_t k = 1; k < cnt; k++) { XYZZ<Fq> q = load_vec(in + p0 + k); acc.add(q); }
-  }
-  store_vec(buckets + gid, acc);
-}
-
-template <class Fq>
 __device__ __forceinline__ XYZZ<Fq> block_tree_sum(XYZZ<Fq> v, XYZZ<Fq>* sm) {
   store_vec(sm + threadIdx.x, v);
   __syncthreads();
@@ -238,9 +216,12 @@ __device__ __forceinline__ XYZZ<Fq> block_tree_sum(XYZZ<Fq> v, XYZZ<Fq>* sm) {
   return r;
 }
 
+// Buckets whose points span more than GIANT_T chunks (skewed scalars: 0/1 witnesses, equal
+// scalars) are collapsed by a whole block: the total goes to the bucket's first partial slot and
+// the bucket's partial count becomes 1, so k_reduce_l1 reads at most GIANT_T partials per bucket.
 template <class Fq>
-__global__ void __launch_bounds__(GIANT_BLOCK) k_giant(MsmGeom g, const uint32_t* __restrict__ pstart,
-                                                       const XYZZ<Fq>* __restrict__ partials, XYZZ<Fq>* __restrict__ buckets,
+__global__ void __launch_bounds__(GIANT_BLOCK) k_giant(MsmGeom g, const uint32_t* __restrict__ pstart, uint32_t* __restrict__ pcount,
+                                                       XYZZ<Fq>* __restrict__ partials,
                                                        const uint32_t* __restrict__ giant_count, const uint32_t* __restrict__ giant_list) {
   __shared__ __align__(16) unsigned char smraw[GIANT_BLOCK * sizeof(XYZZ<Fq>)];
   XYZZ<Fq>* sm = reinterpret_cast<XYZZ<Fq>*>(smraw);
@@ -250,42 +231,111 @@ __global__ void __launch_bounds__(GIANT_BLOCK) k_giant(MsmGeom g, const uint32_t
     const uint32_t w = gid / g.nbp, b = gid - w * g.nbp;
     const uint32_t* ps = pstart + (size_t)w * (g.nbp + 1);
     const uint32_t p0 = ps[b], p1 = ps[b + 1];
-    const XYZZ<Fq>* in = partials + (size_t)w * g.pcap;
+    XYZZ<Fq>* in = partials + (size_t)w * g.pcap;
     XYZZ<Fq> acc = XYZZ<Fq>::inf();
     for (uint32_t k = p0 + threadIdx.x; k < p1; k += blockDim.x) { XYZZ<Fq> q = load_vec(in + k); acc.add(q); }
     XYZZ<Fq> tot = block_tree_sum(acc, sm);
-    if (threadIdx.x == 0) store_vec(buckets + gid, tot);
+    if (threadIdx.x == 0) { store_vec(in + p0, tot); pcount[gid] = 1; }
+    __syncthreads();
   }
 }
 
-// sum_{b in chunk} b * B_b  for L consecutive buckets, one thread per chunk
 template <class Fq>
-__global__ void __launch_bounds__(128) k_reduce_chunks(MsmGeom g, const XYZZ<Fq>* __restrict__ buckets, XYZZ<Fq>* __restrict__ wpart) {
-  const uint32_t gid = blockIdx.x * blockDim.x + threadIdx.x;
-  if (gid >= (uint32_t)g.W * g.nrch) return;
-  const uint32_t w = gid / g.nrch, ch = gid - w * g.nrch;
-  const uint32_t lo = ch * g.L + 1;
-  const uint32_t hi = min(lo + g.L - 1, g.nbp - 1);
-  const XYZZ<Fq>* B = buckets + (size_t)w * g.nbp;
+__device__ __forceinline__ XYZZ<Fq> shfl_down_xyzz(const XYZZ<Fq>& v, int o) {
+  XYZZ<Fq> r;
+  const uint32_t* s = reinterpret_cast<const uint32_t*>(&v);
+  uint32_t* d = reinterpret_cast<uint32_t*>(&r);
+#pragma unroll
+  for (int i = 0; i < (int)(sizeof(XYZZ<Fq>) / 4); i++) d[i] = __shfl_down_sync(0xffffffffu, s[i], o);
+  return r;
+}
+
+// Warp-wide  sum_l ( acc_l + (l * 2^lgL) * run_l )  and  sum_l run_l, results valid on lane 0.
+// Uses  sum_l l*run_l = sum_{j>=1} suffix_j  with suffix_j = sum_{l>=j} run_l  (warp suffix scan).
+template <class Fq>
+__device__ __forceinline__ void warp_weighted_sum(XYZZ<Fq>& acc, XYZZ<Fq>& run, int lgL) {
+  const int lane = threadIdx.x & 31;
+  XYZZ<Fq> suf = run;
+#pragma unroll 1
+  for (int o = 1; o < 32; o <<= 1) {
+    XYZZ<Fq> t = shfl_down_xyzz(suf, o);
+    if (lane + o < 32) suf.add(t);
+  }
+  run = suf;                                   // lane 0: total
+  if (lane >= 1) {
+#pragma unroll 1
+    for (int k = 0; k < lgL; k++) suf.dbl();
+    acc.add(suf);
+  }
+#pragma unroll 1
+  for (int o = 16; o > 0; o >>= 1) {
+    XYZZ<Fq> t = shfl_down_xyzz(acc, o);
+    if (lane < o) acc.add(t);
+  }
+}
+
+// Level 1 of the bucket reduction: one warp per 32*L1 consecutive buckets of one window.
+// Lane l sums the chunk partials of its L1 buckets (top down) keeping run = sum B_b and
+// acc = sum (b - lo + 1) * B_b; the warp then combines lanes.  Output per segment:
+//   segA = sum (b - segbase) * B_b ,  segS = sum B_b      (segbase = first bucket - 1)
+template <class Fq>
+__global__ void __launch_bounds__(128) k_reduce_l1(MsmGeom g, const uint32_t* __restrict__ pstart, const uint32_t* __restrict__ pcount,
+                                                   const XYZZ<Fq>* __restrict__ partials, XYZZ<Fq>* __restrict__ segA,
+                                                   XYZZ<Fq>* __restrict__ segS) {
+  const uint32_t warp = (blockIdx.x * blockDim.x + threadIdx.x) >> 5;
+  const int lane = threadIdx.x & 31;
+  if (warp >= (uint32_t)g.W * g.nseg) return;
+  const uint32_t w = warp / g.nseg, seg = warp - w * g.nseg;
+  const uint32_t L1 = 1u << g.lgL1;
+  const uint32_t* ps = pstart + (size_t)w * (g.nbp + 1);
+  const uint32_t* pc = pcount + (size_t)w * g.nbp;
+  const XYZZ<Fq>* in = partials + (size_t)w * g.pcap;
+  const uint32_t lo = seg * 32 * L1 + (uint32_t)lane * L1 + 1;
   XYZZ<Fq> run = XYZZ<Fq>::inf(), acc = XYZZ<Fq>::inf();
-  for (uint32_t b = hi; b >= lo; b--) {
-    XYZZ<Fq> q = load_vec(B + b);
-    run.add(q);
-    acc.add(run);
+  if (lo <= g.nbp - 1) {
+    const uint32_t hi = min(lo + L1 - 1, g.nbp - 1);
+    for (uint32_t b = hi; b >= lo; b--) {
+      const uint32_t p0 = ps[b], p1 = p0 + pc[b];
+      for (uint32_t k = p0; k < p1; k++) { XYZZ<Fq> q = load_vec(in + k); run.add(q); }
+      acc.add(run);
+    }
   }
-  if (lo > 1) { XYZZ<Fq> m = mul_small(run, lo - 1); acc.add(m); }
-  store_vec(wpart + gid, acc);
+  warp_weighted_sum(acc, run, g.lgL1);
+  if (lane == 0) { store_vec(segA + warp, acc); store_vec(segS + warp, run); }
 }
 
+// Level 2: per window, combine the nseg segment results (one block of 64 threads per window):
+//   P_w = sum_seg segA ,  Q_w = sum_seg seg * segS ;  window sum = P_w + 2^(5+lgL1) * Q_w
+// warp 0 computes Q_w, warp 1 computes P_w.  The final shift-and-add is left to the host finish.
 template <class Fq>
-__global__ void __launch_bounds__(GIANT_BLOCK) k_window_sum(MsmGeom g, const XYZZ<Fq>* __restrict__ wpart, XYZZ<Fq>* __restrict__ winsum) {
-  __shared__ __align__(16) unsigned char smraw[GIANT_BLOCK * sizeof(XYZZ<Fq>)];
-  XYZZ<Fq>* sm = reinterpret_cast<XYZZ<Fq>*>(smraw);
+__global__ void __launch_bounds__(64) k_reduce_l2(MsmGeom g, const XYZZ<Fq>* __restrict__ segA, const XYZZ<Fq>* __restrict__ segS,
+                                                  XYZZ<Fq>* __restrict__ winP, XYZZ<Fq>* __restrict__ winQ) {
   const uint32_t w = blockIdx.x;
-  XYZZ<Fq> acc = XYZZ<Fq>::inf();
-  for (uint32_t k = threadIdx.x; k < g.nrch; k += blockDim.x) { XYZZ<Fq> q = load_vec(wpart + (size_t)w * g.nrch + k); acc.add(q); }
-  XYZZ<Fq> tot = block_tree_sum(acc, sm);
-  if (threadIdx.x == 0) store_vec(winsum + w, tot);
+  const int lane = threadIdx.x & 31, wid = threadIdx.x >> 5;
+  const uint32_t L2 = 1u << g.lgL2;
+  const uint32_t lo = (uint32_t)lane * L2;
+  if (wid == 0) {
+    // weights (seg + 1) via the generic routine, then subtract the plain total once
+    XYZZ<Fq> run = XYZZ<Fq>::inf(), acc = XYZZ<Fq>::inf();
+    if (lo < g.nseg) {
+      const uint32_t hi = min(lo + L2, g.nseg);
+      for (uint32_t s = hi; s-- > lo;) { XYZZ<Fq> q = load_vec(segS + (size_t)w * g.nseg + s); run.add(q); acc.add(run); }
+    }
+    warp_weighted_sum(acc, run, g.lgL2);
+    if (lane == 0) { XYZZ<Fq> neg = run.neg(); acc.add(neg); store_vec(winQ + w, acc); }
+  } else {
+    XYZZ<Fq> acc = XYZZ<Fq>::inf();
+    if (lo < g.nseg) {
+      const uint32_t hi = min(lo + L2, g.nseg);
+      for (uint32_t s = lo; s < hi; s++) { XYZZ<Fq> q = load_vec(segA + (size_t)w * g.nseg + s); acc.add(q); }
+    }
+#pragma unroll 1
+    for (int o = 16; o > 0; o >>= 1) {
+      XYZZ<Fq> t = shfl_down_xyzz(acc, o);
+      if (lane < o) acc.add(t);
+    }
+    if (lane == 0) store_vec(winP + w, acc);
+  }
 }
 
 // ------------------------------------------------------------------------------------------
@@ -305,7 +355,7 @@ struct StageTimer {
   void report(const MsmGeom& g) {
     if (!on) return;
     cudaEventSynchronize(ev.back());
-    fprintf(stderr, "[bpgpu msm n=%u c=%d W=%d S=%u L=%u]", g.n, g.c, g.W, g.S, g.L);
+    fprintf(stderr, "[bpgpu msm n=%u c=%d W=%d S=%u lgL1=%d nseg=%u]", g.n, g.c, g.W, g.S, g.lgL1, g.nseg);
     for (size_t i = 1; i < ev.size(); i++) { float ms; cudaEventElapsedTime(&ms, ev[i - 1], ev[i]); fprintf(stderr, " %s=%.3f", names[i], ms); }
     float tot; cudaEventElapsedTime(&tot, ev.front(), ev.back());
     fprintf(stderr, " total=%.3fms\n", tot);
@@ -321,7 +371,7 @@ int msm_run(bpgpu_ctx* ctx, const Affine<typename Curve::Fq>* d_points, const vo
   using Fq = typename Curve::Fq;
   using Fr = typename Curve::Fr;
   cudaStream_t st = ctx->stream;
-  res->W = 0; res->c = 0; res->d_winsum = nullptr;
+  res->W = 0; res->c = 0; res->qshift = 0; res->d_winsum = nullptr;
   if (n == 0) return BPGPU_OK;
   if (n >= (1ull << 31)) return BPGPU_E_ARG;
   MsmGeom g;
@@ -330,19 +380,22 @@ int msm_run(bpgpu_ctx* ctx, const Affine<typename Curve::Fq>* d_points, const vo
   g.W = (Curve::SCALAR_BITS + 1 + g.c - 1) / g.c;
   g.nbp = (1u << (g.c - 1)) + 1;
   {
-    // entries per chunk thread: keep >= ~64k chunk threads in flight when the problem allows it
-    uint64_t entries = (uint64_t)g.W * n;
-    uint64_t s = entries / 65536;
-    g.S = (uint32_t)(s < 4 ? 4 : (s > 32 ? 32 : s));
+    // about one chunk per average bucket: every bucket then has ~2 partial sums
+    uint64_t s = (uint64_t)n >> (g.c - 1);
+    g.S = (uint32_t)(s < 4 ? 4 : (s > 64 ? 64 : s));
   }
   g.nchunk = (g.n + g.S - 1) / g.S;
   g.pcap = g.nchunk + g.nbp;
   {
-    uint64_t buckets = (uint64_t)g.W * (g.nbp - 1);
-    uint64_t l = buckets / 131072;
-    g.L = (uint32_t)(l < 2 ? 2 : (l > 16 ? 16 : l));
+    uint32_t nb = g.nbp - 1;                       // 2^(c-1)
+    int lg = 0;                                    // buckets per lane: up to 16, but keep >= ~600 warps busy
+    while ((32u << (lg + 1)) <= nb && lg < 4 && ((uint64_t)g.W * nb >> (lg + 1 + 5)) >= 600) lg++;
+    g.lgL1 = lg;
+    g.nseg = (nb + (32u << lg) - 1) / (32u << lg);
+    int lg2 = 0;
+    while ((32u << lg2) < g.nseg) lg2++;
+    g.lgL2 = lg2;
   }
-  g.nrch = (g.nbp - 1 + g.L - 1) / g.L;
 
   // ---- scratch layout
   const size_t sz_digits = align256((size_t)g.W * n * 4);
@@ -361,15 +414,14 @@ int msm_run(bpgpu_ctx* ctx, const Affine<typename Curve::Fq>* d_points, const vo
   uint32_t* pstart = (uint32_t*)base; base += sz_bstart;
   uint32_t* giant = (uint32_t*)base;  // [0] = count, [1..] = list
   const size_t sz_part = align256((size_t)g.W * g.pcap * sizeof(XYZZ<Fq>));
-  const size_t sz_buck = align256((size_t)g.W * g.nbp * sizeof(XYZZ<Fq>));
-  const size_t sz_wpart = align256((size_t)g.W * g.nrch * sizeof(XYZZ<Fq>));
-  const size_t sz_wsum = align256((size_t)g.W * sizeof(XYZZ<Fq>));
-  if ((rc = ctx->msm_b.reserve(sz_part + sz_buck + sz_wpart + sz_wsum))) return rc;
+  const size_t sz_seg = align256((size_t)g.W * g.nseg * sizeof(XYZZ<Fq>));
+  const size_t sz_wsum = align256((size_t)2 * g.W * sizeof(XYZZ<Fq>));
+  if ((rc = ctx->msm_b.reserve(sz_part + 2 * sz_seg + sz_wsum))) return rc;
   uint8_t* b2 = (uint8_t*)ctx->msm_b.p;
   XYZZ<Fq>* partials = (XYZZ<Fq>*)b2; b2 += sz_part;
-  XYZZ<Fq>* buckets = (XYZZ<Fq>*)b2; b2 += sz_buck;
-  XYZZ<Fq>* wpart = (XYZZ<Fq>*)b2; b2 += sz_wpart;
-  XYZZ<Fq>* winsum = (XYZZ<Fq>*)b2;
+  XYZZ<Fq>* segA = (XYZZ<Fq>*)b2; b2 += sz_seg;
+  XYZZ<Fq>* segS = (XYZZ<Fq>*)b2; b2 += sz_seg;
+  XYZZ<Fq>* winsum = (XYZZ<Fq>*)b2;             // [0, W): P_w   [W, 2W): Q_w
 
   StageTimer tm(st);
   BP_CUDA_OK(cudaMemsetAsync(hist, 0, sz_hist, st));
@@ -377,7 +429,7 @@ int msm_run(bpgpu_ctx* ctx, const Affine<typename Curve::Fq>* d_points, const vo
 
   k_digits<Fr><<<(g.n + 255) / 256, 256, 0, st>>>((const Fr*)d_scalars, scalars_mont ? 1 : 0, g, digits, hist);
   tm.mark("digits");
-  k_scan<<<g.W, 1024, 0, st>>>(g, hist, bstart, cursor, pstart);
+  k_scan<<<g.W, 1024, 0, st>>>(g, hist, bstart, cursor, pstart, giant, giant + 1);
   tm.mark("scan");
   {
     size_t total = (size_t)g.W * n;
@@ -392,21 +444,17 @@ int msm_run(bpgpu_ctx* ctx, const Affine<typename Curve::Fq>* d_points, const vo
     k_chunk_acc<Fq><<<(threads + 127) / 128, 128, 0, st>>>(g, d_points, sidx, skey, bstart, pstart, partials);
     tm.mark("chunk_acc");
   }
+  k_giant<Fq><<<ctx->sm_count * 2, GIANT_BLOCK, 0, st>>>(g, pstart, hist, partials, giant, giant + 1);
+  tm.mark("giant");
   {
-    uint32_t threads = (uint32_t)g.W * g.nbp;
-    k_bucket_finish<Fq><<<(threads + 127) / 128, 128, 0, st>>>(g, pstart, partials, buckets, giant, giant + 1);
-    k_giant<Fq><<<ctx->sm_count * 2, GIANT_BLOCK, 0, st>>>(g, pstart, partials, buckets, giant, giant + 1);
-    tm.mark("finish+giant");
+    uint32_t warps = (uint32_t)g.W * g.nseg;
+    k_reduce_l1<Fq><<<(warps * 32 + 127) / 128, 128, 0, st>>>(g, pstart, hist, partials, segA, segS);
+    tm.mark("reduce_l1");
   }
-  {
-    uint32_t threads = (uint32_t)g.W * g.nrch;
-    k_reduce_chunks<Fq><<<(threads + 127) / 128, 128, 0, st>>>(g, buckets, wpart);
-    tm.mark("reduce_chunks");
-  }
-  k_window_sum<Fq><<<g.W, GIANT_BLOCK, 0, st>>>(g, wpart, winsum);
-  tm.mark("window_sum");
-  ctx->launches += 8;
-  res->W = g.W; res->c = g.c; res->d_winsum = winsum;
+  k_reduce_l2<Fq><<<g.W, 64, 0, st>>>(g, segA, segS, winsum, winsum + g.W);
+  tm.mark("reduce_l2");
+  ctx->launches += 7;
+  res->W = g.W; res->c = g.c; res->qshift = 5 + g.lgL1; res->d_winsum = winsum;
   int lrc = launch_check(ctx, "msm");
   tm.report(g);
   return lrc;
