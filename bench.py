@@ -1,0 +1,301 @@
+#!/usr/bin/env python3
+"""bench.py — headline benchmark: BLS12-381 G1 MSM points/s at 2^20 points (BASELINE.json `metric`).
+
+    python bench.py [--gpus N] [--steps K] [--warmup W] [--lg 20] [--impl ours|reference]
+
+One "step" = one multi-scalar multiplication sum_i s_i*P_i over `2^lg` synthetic points per GPU
+(what G1Vector::multi_scalar_mul_var_time / inner_product_var_time_with_ref_vecs compute:
+/root/reference/src/ipp.rs:251-253, src/r1cs/verifier.rs:451), through libbpgpu's C ABI.
+
+ * value  : whole-job points/s with points and scalars already resident in HBM (bpgpu_msm_device).
+ * e2e    : the same metric through bpgpu_msm_refs with HOST (pinned) point and scalar buffers:
+            H2D of both inputs every step, D2H of the per-window sums, host finish.
+ * N > 1  : one process per GPU (torchrun).  The MSM shards by points: every rank computes the
+            partial sum of its own 2^lg points (weak scaling), the 96-byte affine partials are
+            all-gathered over NCCL and summed on every rank.  Timed with barrier + sync on both
+            sides, max over ranks.
+ * roofline: the dominant kernel (k_chunk_acc, bucket accumulation) against the INTEGER pipe:
+            algorithmic IMADs = points * windows * 10 Fq-mul * (2*12^2+12) per launch, divided by
+            the kernel's average duration (CUDA events on the ctx stream, inside the timed
+            region); peak = IMAD.WIDE.U32 throughput measured in this same run by
+            bpgpu_int_pipe_bench (MEASURED_PEAKS.json carries no integer peak).  The HBM view of the
+            same kernel is reported next to it.
+ * cpu_baseline / --impl reference: the reference's own CPU algorithm (Straus, wNAF-5) restated in
+            C (oracle/c), timed on the box's host cores on a bounded sample of the same workload.
+"""
+import argparse
+import ctypes
+import json
+import os
+import statistics
+import subprocess
+import sys
+import threading
+import time
+
+ROOT = os.path.dirname(os.path.abspath(__file__))
+sys.path.insert(0, ROOT)
+
+METRIC = "G1 MSM points/s at 2^20 (BLS12-381)"
+UNIT = "points/s"
+FQ_LIMBS = 12
+IMAD_PER_FQMUL = 2 * FQ_LIMBS * FQ_LIMBS + FQ_LIMBS      # 300, SURVEY.md 8d
+FQMUL_PER_MADD = 10                                      # XYZZ mixed add 8M + 2S
+
+
+def synth_scalars_be(n, seed, modbytes=48):
+    """n uniform 254-bit scalars (< r for BLS12-381), big-endian MODBYTES each."""
+    import numpy as np
+    rng = np.random.default_rng(seed)
+    raw = rng.integers(0, 256, size=(n, 32), dtype=np.uint8)
+    raw[:, 0] &= 0x3F
+    out = np.zeros((n, modbytes), dtype=np.uint8)
+    out[:, modbytes - 32:] = raw
+    return out
+
+
+def gen_points(ctx, n, seed):
+    """n synthetic G1 points k_i*G, computed on the device (selftest_group op 2)."""
+    from bulletproofs_amcl_b200 import lib
+    mb = ctx.modbytes
+    gx = 0x17F1D3A73197D7942695638C4FA9AC0FC3688C4F9774B905A14E3A3F171BAC586C55E83FF97A1AEFFB3AF00ADB22C6BB
+    gy = 0x08B3F481E3AAA0F1A09E30ED741D8AE4FCF5E095D5D00AF600DB18CB2C04B3EDD03CC744A2888AE40CAA232946C5E7E1
+    g = gx.to_bytes(mb, "big") + gy.to_bytes(mb, "big")
+    ks = synth_scalars_be(n, seed, mb).tobytes()
+    return ctx.selftest_group(2, g * n, g * n, ks)
+
+
+class ClockSampler:
+    """Samples SM clock and throttle reasons through NVML every ~5 ms while the timed region runs."""
+
+    def __init__(self, index):
+        self.index, self.samples, self.stop_flag, self.th = index, [], False, None
+
+    def start(self):
+        try:
+            import pynvml
+            pynvml.nvmlInit()
+            self.nv = pynvml
+            self.h = pynvml.nvmlDeviceGetHandleByIndex(self.index)
+            self.th = threading.Thread(target=self._pump, daemon=True)
+            self.th.start()
+        except Exception as e:           # pragma: no cover
+            self.err = str(e)
+            self.th = None
+
+    def _pump(self):
+        nv = self.nv
+        while not self.stop_flag:
+            try:
+                sm = nv.nvmlDeviceGetClockInfo(self.h, nv.NVML_CLOCK_SM)
+                mx = nv.nvmlDeviceGetMaxClockInfo(self.h, nv.NVML_CLOCK_SM)
+                rs = nv.nvmlDeviceGetCurrentClocksEventReasons(self.h) if hasattr(nv, "nvmlDeviceGetCurrentClocksEventReasons") \
+                    else nv.nvmlDeviceGetCurrentClocksThrottleReasons(self.h)
+                self.samples.append((sm, mx, rs))
+            except Exception:
+                pass
+            time.sleep(0.005)
+
+    def stop(self):
+        if not self.th:
+            return {"sm_mhz": None, "sm_max_mhz": None, "reasons": ["nvml unavailable"]}
+        self.stop_flag = True
+        self.th.join(timeout=1)
+        nv = self.nv
+        names = {"hw_slowdown": getattr(nv, "nvmlClocksEventReasonHwSlowdown", 0x8),
+                 "hw_thermal_slowdown": getattr(nv, "nvmlClocksEventReasonHwThermalSlowdown", 0x40),
+                 "sw_thermal_slowdown": getattr(nv, "nvmlClocksEventReasonSwThermalSlowdown", 0x20),
+                 "sw_power_cap": getattr(nv, "nvmlClocksEventReasonSwPowerCap", 0x4)}
+        reasons = sorted(k for k, bit in names.items() if any(s[2] & bit for s in self.samples))
+        sm = [s[0] for s in self.samples]
+        return {"sm_mhz": statistics.median(sm) if sm else None, "sm_max_mhz": max(s[1] for s in self.samples) if sm else None,
+                "reasons": reasons, "samples": len(sm)}
+
+
+def cpu_reference(lg_sample, threads, curve_id=0, seed=5):
+    """Time the oracle's Straus/wNAF-5 MSM (the reference's CPU algorithm) on 2^lg_sample points."""
+    from oracle import cref
+    from oracle.curves import BLS12_381 as C
+    n = 1 << lg_sample
+    xy = cref.multiples(curve_id, C.g1_xy_bytes(C.mul(C.from_affine(C.g), 12345)), n)
+    sb = synth_scalars_be(n, seed).tobytes()
+    t0 = time.perf_counter()
+    cref.msm(curve_id, xy, sb, n, threads)
+    dt = time.perf_counter() - t0
+    return n / dt, dt
+
+
+def run_reference(args):
+    cores = os.cpu_count() or 1
+    rank = int(os.environ.get("RANK", "0"))
+    if rank != 0:
+        return
+    lg_s = args.ref_lg
+    vals = []
+    for i in range(args.warmup + args.steps):
+        v, dt = cpu_reference(lg_s, cores, seed=5 + i)
+        if i >= args.warmup:
+            vals.append((v, dt))
+    value = sum(1 << lg_s for _ in vals) / sum(dt for _, dt in vals)
+    sample = f"2^{lg_s} of the 2^{args.lg} points per step, Straus wNAF-5 (oracle/c), {cores} threads"
+    print(json.dumps({
+        "impl": "reference", "metric": METRIC, "value": value, "unit": UNIT, "n_gpus": args.gpus, "steps": args.steps,
+        "warmup": args.warmup, "ms_per_step": 1e3 * sum(dt for _, dt in vals) / len(vals), "higher_is_better": True,
+        "scaling": "weak", "vs_baseline": None, "dtype": "u32 limbs (host: u64)", "data": "synthetic",
+        "config": {"workload": f"G1 MSM, BLS12-381, 2^{args.lg} points (bounded sample 2^{lg_s} per step)"},
+        "cpu_baseline": {"value": value, "unit": UNIT, "cores": cores, "kind": "port", "sample": sample},
+        "e2e": {"value": value, "unit": UNIT, "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
+    }))
+
+
+def main():
+    ap = argparse.ArgumentParser()
+    ap.add_argument("--gpus", type=int, default=1)
+    ap.add_argument("--steps", type=int, default=10)
+    ap.add_argument("--warmup", type=int, default=3)
+    ap.add_argument("--lg", type=int, default=20)
+    ap.add_argument("--impl", default="ours")
+    ap.add_argument("--ref-lg", type=int, default=18)
+    ap.add_argument("--no-cpu-baseline", action="store_true")
+    args = ap.parse_args()
+    if args.impl == "reference":
+        return run_reference(args)
+
+    import torch
+    import bulletproofs_amcl_b200 as bp
+
+    world = int(os.environ.get("WORLD_SIZE", "1"))
+    rank = int(os.environ.get("RANK", "0"))
+    local = int(os.environ.get("LOCAL_RANK", "0"))
+    dist = None
+    torch.cuda.set_device(local)
+    if world > 1:
+        import torch.distributed as dist
+        dist.init_process_group("nccl", device_id=torch.device("cuda", local))
+    n = 1 << args.lg
+    ctx = bp.Context(bp.BLS12_381, local)
+    mb = ctx.modbytes
+
+    # ---- synthetic inputs: two independent input sets (2 x (96+32) MB at 2^20 > 126 MB L2), alternated
+    # between steps so no step finds its inputs in L2
+    NSETS = 2
+    pts_xy = [gen_points(ctx, n, 1000 + 17 * rank + s) for s in range(NSETS)]
+    sc_np = [synth_scalars_be(n, 2000 + 17 * rank + s, mb) for s in range(NSETS)]
+    dpts = [ctx.upload_points(x) for x in pts_xy]
+    dsc = [ctx.upload_scalars(s.tobytes()) for s in sc_np]
+    # pinned host copies for the end-to-end leg
+    hp, hs = [], []
+    for s in range(NSETS):
+        p = ctx.host_alloc(len(pts_xy[s]))
+        ctypes.memmove(p, pts_xy[s], len(pts_xy[s]))
+        hp.append(p)
+        q = ctx.host_alloc(sc_np[s].nbytes)
+        ctypes.memmove(q, sc_np[s].ctypes.data, sc_np[s].nbytes)
+        hs.append(q)
+
+    ones = (1).to_bytes(mb, "big") * world
+
+    def combine(partial_xy):
+        """N>1: all-gather the 2*MODBYTES-byte partial sums over NCCL, add them on every rank."""
+        if world == 1:
+            return partial_xy
+        t = torch.frombuffer(bytearray(partial_xy), dtype=torch.uint8).cuda()
+        out = torch.empty(world * t.numel(), dtype=torch.uint8, device="cuda")
+        dist.all_gather_into_tensor(out, t)
+        return ctx.msm_refs(out.cpu().numpy().tobytes(), ones)
+
+    def step_resident(i):
+        return combine(ctx.msm_device(dpts[i % NSETS], dsc[i % NSETS], n=n))
+
+    def step_e2e(i):
+        return combine(ctx.msm_refs(hp[i % NSETS], hs[i % NSETS], n=n))
+
+    stream = torch.cuda.ExternalStream(ctx.stream)
+
+    def timed(fn, steps, warmup, profile=False):
+        for i in range(warmup):
+            fn(i)
+        if world > 1:
+            dist.barrier()
+        torch.cuda.synchronize()
+        l0 = ctx.launches
+        if profile:
+            ctx.set_profile(True)
+        e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        t0 = time.perf_counter()
+        e0.record(stream)
+        for i in range(steps):
+            fn(warmup + i)
+        e1.record(stream)
+        e1.synchronize()
+        torch.cuda.synchronize()
+        wall_ms = (time.perf_counter() - t0) * 1e3
+        ms = max(e0.elapsed_time(e1), wall_ms)     # the host finish sits between kernels: never under-report
+        stages = ctx.msm_stage_ms() if profile else None
+        if profile:
+            ctx.set_profile(False)
+        if world > 1:
+            t = torch.tensor([ms], device="cuda", dtype=torch.float64)
+            dist.all_reduce(t, op=dist.ReduceOp.MAX)
+            ms = float(t.item())
+        return ms, ctx.launches - l0, stages
+
+    # integer-pipe peak, measured live
+    imad_peak, _ = ctx.int_pipe_bench(0, 2000)
+    fqmul_peak, _ = ctx.int_pipe_bench(1, 200)
+
+    sampler = ClockSampler(local)
+    sampler.start()
+    ms, launches, (runs, stages) = timed(step_resident, args.steps, args.warmup, profile=True)
+    clocks = sampler.stop()
+    ms_e2e, _, _ = timed(step_e2e, args.steps, args.warmup)
+
+    # parity guard inside the bench: both paths agree with each other on the same inputs
+    a = ctx.msm_device(dpts[0], dsc[0], n=n)
+    b = ctx.msm_refs(hp[0], hs[0], n=n)
+    assert a == b, "resident and host-buffer MSM disagree"
+
+    if rank == 0:
+        c = bp.lib().bpgpu_msm_window_bits(n)
+        W = (256 + c - 1) // c
+        total_points = n * world * args.steps
+        value = total_points / (ms * 1e-3)
+        e2e_value = total_points / (ms_e2e * 1e-3)
+        k_ms = stages["chunk_acc"]
+        alg_imad = n * W * FQMUL_PER_MADD * IMAD_PER_FQMUL
+        achieved = alg_imad / (k_ms * 1e-3)
+        alg_bytes = n * W * (2 * mb + 8) + n * 32      # gathered affine points + sorted (index,key) pairs, once per window
+        out = {
+            "metric": METRIC, "value": value, "unit": UNIT, "n_gpus": world, "steps": args.steps, "warmup": args.warmup,
+            "ms_per_step": ms / args.steps, "higher_is_better": True, "scaling": "weak", "vs_baseline": None,
+            "dtype": "u32 limbs (Montgomery Fq 12x32, Fr 8x32)", "data": "synthetic",
+            "config": {"workload": f"G1 MSM, BLS12-381, 2^{args.lg} random points x 255-bit scalars per GPU, general bases "
+                                   f"(no precomputation), signed {c}-bit windows x {W}",
+                       "l2": f"{NSETS} input sets alternated ({NSETS}x{(n * (2 * mb + 32)) >> 20} MiB > 126 MB L2), no explicit flush",
+                       "parallelism": f"points sharded over {world} GPU(s); partial sums all-gathered over NCCL" if world > 1 else "1 GPU"},
+            "e2e": {"value": e2e_value, "unit": UNIT, "h2d_bytes_per_step": n * 3 * mb, "d2h_bytes_per_step": 2 * W * 4 * mb,
+                    "ms_per_step": ms_e2e / args.steps, "api": "bpgpu_msm_refs (host points + host scalars, pinned)"},
+            "gpu_launches": int(launches),
+            "clocks": clocks,
+            "roofline": {"bound": "int32-imad", "kernel": "k_chunk_acc", "achieved": achieved, "peak": imad_peak,
+                         "unit": "IMAD.WIDE/s", "frac": achieved / imad_peak, "traffic": None,
+                         "peak_source": "bpgpu_int_pipe_bench(IMAD.WIDE.U32) measured in this run",
+                         "kernel_ms": k_ms, "kernel_share_of_step": k_ms / (ms / args.steps),
+                         "algorithmic_imad_per_launch": alg_imad, "fq_mul_per_s_peak_measured": fqmul_peak,
+                         "hbm": {"achieved_GBps": alg_bytes / (k_ms * 1e-3) / 1e9, "algorithmic_bytes": alg_bytes}},
+            "stages_ms": stages,
+        }
+        if world == 1 and not args.no_cpu_baseline:
+            cores = os.cpu_count() or 1
+            v1, dt1 = cpu_reference(15, 1)
+            vN, dtN = cpu_reference(19, cores)
+            out["cpu_baseline"] = {"value": vN, "unit": UNIT, "cores": cores, "kind": "port",
+                                   "sample": f"Straus wNAF-5 (oracle/c) on 2^19 of the 2^{args.lg} points, {cores} threads, {dtN:.1f} s",
+                                   "single_core": {"value": v1, "cores": 1, "sample": f"2^15 points, {dt1:.1f} s"}}
+        print(json.dumps(out))
+    if world > 1:
+        dist.destroy_process_group()
+
+
+if __name__ == "__main__":
+    main()

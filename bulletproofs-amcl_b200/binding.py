@@ -23,6 +23,8 @@ SYMBOLS = [
     ("bpgpu_ctx_sync", _INT, [_VP]),
     ("bpgpu_ctx_curve", _INT, [_VP]),
     ("bpgpu_ctx_launches", _c.c_uint64, [_VP]),
+    ("bpgpu_ctx_set_profile", _INT, [_VP, _INT]),
+    ("bpgpu_msm_stage_ms", _INT, [_VP, _c.POINTER(_c.c_double), _INT]),
     ("bpgpu_host_alloc", _VP, [_SZ]),
     ("bpgpu_host_free", None, [_VP]),
     ("bpgpu_points_upload", _INT, [_VP, _VP, _SZ, _c.POINTER(_VP)]),
@@ -154,6 +156,25 @@ class Context:
     @property
     def launches(self):
         return lib().bpgpu_ctx_launches(self.handle)
+
+    STAGES = ["digits", "scan", "scatter", "chunk_acc", "giant", "reduce_l1", "reduce_l2"]
+
+    def set_profile(self, on):
+        self._check(lib().bpgpu_ctx_set_profile(self.handle, 1 if on else 0), "set_profile")
+
+    def msm_stage_ms(self):
+        arr = (ctypes.c_double * 8)()
+        runs = lib().bpgpu_msm_stage_ms(self.handle, arr, 8)
+        return runs, dict(zip(self.STAGES, list(arr)[:7]))
+
+    def host_alloc(self, nbytes):
+        p = lib().bpgpu_host_alloc(nbytes)
+        if not p:
+            raise BpgpuError(-6, "bpgpu_host_alloc")
+        return p
+
+    def host_free(self, p):
+        lib().bpgpu_host_free(p)
 
     def sync(self):
         self._check(lib().bpgpu_ctx_sync(self.handle), "sync")

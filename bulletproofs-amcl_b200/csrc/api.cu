@@ -279,6 +279,19 @@ int bpgpu_ctx_sync(bpgpu_ctx* c) {
 int bpgpu_ctx_curve(const bpgpu_ctx* c) { return c ? c->curve : BPGPU_E_ARG; }
 uint64_t bpgpu_ctx_launches(const bpgpu_ctx* c) { return c ? c->launches : 0; }
 
+int bpgpu_ctx_set_profile(bpgpu_ctx* c, int on) {
+  if (!c) return BPGPU_E_ARG;
+  c->profile = on;
+  for (int i = 0; i < 8; i++) c->stage_ms_sum[i] = 0;
+  c->stage_runs = 0;
+  return BPGPU_OK;
+}
+int bpgpu_msm_stage_ms(const bpgpu_ctx* c, double* avg_ms, int cap) {
+  if (!c || !avg_ms) return BPGPU_E_ARG;
+  for (int i = 0; i < cap && i < 8; i++) avg_ms[i] = c->stage_runs ? c->stage_ms_sum[i] / (double)c->stage_runs : 0.0;
+  return (int)c->stage_runs;
+}
+
 void* bpgpu_host_alloc(size_t bytes) {
   void* p = nullptr;
   if (cudaHostAlloc(&p, bytes ? bytes : 1, cudaHostAllocDefault) != cudaSuccess) return nullptr;

@@ -65,6 +65,10 @@ struct bpgpu_ctx {
   bp::Scratch msm_a, msm_b, msm_c, msm_d, msm_e, io_dev, io_dev2;
   uint8_t* pinned = nullptr;      // small pinned staging (results, challenges)
   size_t pinned_cap = 0;
+  // per-stage CUDA-event timing of the MSM pipeline (bpgpu_ctx_set_profile)
+  int profile = 0;
+  double stage_ms_sum[8] = {0, 0, 0, 0, 0, 0, 0, 0};
+  uint64_t stage_runs = 0;
 };
 
 struct bpgpu_points {

@@ -346,15 +346,19 @@ struct StageTimer {
   cudaStream_t st;
   std::vector<cudaEvent_t> ev;
   std::vector<const char*> names;
-  StageTimer(cudaStream_t s) : on(getenv("BPGPU_PROFILE") != nullptr), st(s) { mark("start"); }
+  bool verbose;
+  StageTimer(cudaStream_t s, bool enable) : on(enable || getenv("BPGPU_PROFILE") != nullptr), st(s), verbose(getenv("BPGPU_PROFILE") != nullptr) { mark("start"); }
   void mark(const char* name) {
     if (!on) return;
     cudaEvent_t e; cudaEventCreate(&e); cudaEventRecord(e, st);
     ev.push_back(e); names.push_back(name);
   }
-  void report(const MsmGeom& g) {
+  void report(const MsmGeom& g, bpgpu_ctx* ctx) {
     if (!on) return;
     cudaEventSynchronize(ev.back());
+    for (size_t i = 1; i < ev.size() && i <= 8; i++) { float ms; cudaEventElapsedTime(&ms, ev[i - 1], ev[i]); ctx->stage_ms_sum[i - 1] += ms; }
+    ctx->stage_runs++;
+    if (!verbose) { for (auto e : ev) cudaEventDestroy(e); return; }
     fprintf(stderr, "[bpgpu msm n=%u c=%d W=%d S=%u lgL1=%d nseg=%u]", g.n, g.c, g.W, g.S, g.lgL1, g.nseg);
     for (size_t i = 1; i < ev.size(); i++) { float ms; cudaEventElapsedTime(&ms, ev[i - 1], ev[i]); fprintf(stderr, " %s=%.3f", names[i], ms); }
     float tot; cudaEventElapsedTime(&tot, ev.front(), ev.back());
@@ -423,7 +427,7 @@ int msm_run(bpgpu_ctx* ctx, const Affine<typename Curve::Fq>* d_points, const vo
   XYZZ<Fq>* segS = (XYZZ<Fq>*)b2; b2 += sz_seg;
   XYZZ<Fq>* winsum = (XYZZ<Fq>*)b2;             // [0, W): P_w   [W, 2W): Q_w
 
-  StageTimer tm(st);
+  StageTimer tm(st, ctx->profile != 0);
   BP_CUDA_OK(cudaMemsetAsync(hist, 0, sz_hist, st));
   BP_CUDA_OK(cudaMemsetAsync(giant, 0, 4, st));
 
@@ -456,7 +460,7 @@ int msm_run(bpgpu_ctx* ctx, const Affine<typename Curve::Fq>* d_points, const vo
   ctx->launches += 7;
   res->W = g.W; res->c = g.c; res->qshift = 5 + g.lgL1; res->d_winsum = winsum;
   int lrc = launch_check(ctx, "msm");
-  tm.report(g);
+  tm.report(g, ctx);
   return lrc;
 }
 

@@ -59,6 +59,12 @@ int bpgpu_ctx_curve(const bpgpu_ctx* ctx);
 /* number of kernels this ctx has launched so far (bench.py's gpu_launches) */
 uint64_t bpgpu_ctx_launches(const bpgpu_ctx* ctx);
 
+/* per-stage CUDA-event timing of the MSM pipeline on the ctx stream (roofline evidence for bench.py).
+ * stages: 0 digits, 1 scan, 2 scatter, 3 chunk_acc, 4 giant, 5 reduce_l1, 6 reduce_l2.
+ * bpgpu_msm_stage_ms writes the average ms per stage since set_profile(1) and returns the run count. */
+int bpgpu_ctx_set_profile(bpgpu_ctx* ctx, int on);
+int bpgpu_msm_stage_ms(const bpgpu_ctx* ctx, double* avg_ms, int cap);
+
 void* bpgpu_host_alloc(size_t bytes);       /* pinned host memory */
 void bpgpu_host_free(void* p);
 
