@@ -39,6 +39,23 @@ SYMBOLS = [
     ("bpgpu_msm_device", _INT, [_VP, _VP, _SZ, _SZ, _VP, _SZ, _VP]),
     ("bpgpu_msm_refs", _INT, [_VP, _VP, _VP, _SZ, _VP]),
     ("bpgpu_msm_window_bits", _INT, [_SZ]),
+    ("bpgpu_scalars_alloc", _INT, [_VP, _SZ, _c.POINTER(_VP)]),
+    ("bpgpu_fr_vandermonde", _INT, [_VP, _VP, _SZ, _c.POINTER(_VP)]),
+    ("bpgpu_fr_hadamard", _INT, [_VP, _VP, _SZ, _VP, _SZ, _SZ, _VP, _SZ]),
+    ("bpgpu_fr_add", _INT, [_VP, _VP, _SZ, _VP, _SZ, _SZ, _VP, _SZ]),
+    ("bpgpu_fr_sub", _INT, [_VP, _VP, _SZ, _VP, _SZ, _SZ, _VP, _SZ]),
+    ("bpgpu_fr_scale", _INT, [_VP, _VP, _SZ, _SZ, _VP, _VP, _SZ]),
+    ("bpgpu_fr_inner_product", _INT, [_VP, _VP, _SZ, _VP, _SZ, _SZ, _VP]),
+    ("bpgpu_fr_poly3_special_inner_product", _INT, [_VP, _VP, _VP, _VP, _VP, _VP, _VP, _SZ, _VP]),
+    ("bpgpu_fr_batch_invert", _INT, [_VP, _VP, _SZ, _SZ, _VP, _SZ, _VP]),
+    ("bpgpu_ipp_begin", _INT, [_VP, _VP, _SZ, _VP, _SZ, _VP, _VP, _VP, _VP, _VP, _SZ, _c.POINTER(_VP)]),
+    ("bpgpu_ipp_len", _SZ, [_VP]),
+    ("bpgpu_ipp_round_LR", _INT, [_VP, _VP, _VP]),
+    ("bpgpu_ipp_fold", _INT, [_VP, _VP, _VP]),
+    ("bpgpu_ipp_finish", _INT, [_VP, _VP, _VP]),
+    ("bpgpu_ipp_free", None, [_VP]),
+    ("bpgpu_ipp_verification_scalars", _INT, [_VP, _VP, _SZ, _c.POINTER(_VP)]),
+    ("bpgpu_ipp_verify_msm", _INT, [_VP, _VP, _SZ, _VP, _SZ, _VP, _VP, _VP, _VP, _VP, _VP, _VP, _VP, _SZ, _VP]),
     ("bpgpu_selftest_field", _INT, [_VP, _INT, _INT, _VP, _VP, _SZ, _VP]),
     ("bpgpu_selftest_group", _INT, [_VP, _INT, _VP, _VP, _VP, _SZ, _VP]),
     ("bpgpu_int_pipe_bench", _INT, [_VP, _INT, _INT, _c.POINTER(_c.c_double), _c.POINTER(_c.c_double)]),
@@ -191,6 +208,89 @@ class Context:
         h = ctypes.c_void_p()
         self._check(lib().bpgpu_scalars_upload(self.handle, _buf(be), n, ctypes.byref(h)), "scalars_upload")
         return DeviceScalars(self, h)
+
+    # ---- FieldElementVector algebra (device resident)
+    def alloc_scalars(self, n):
+        h = ctypes.c_void_p()
+        self._check(lib().bpgpu_scalars_alloc(self.handle, n, ctypes.byref(h)), "scalars_alloc")
+        return DeviceScalars(self, h)
+
+    def fr_vandermonde(self, x_be, n):
+        h = ctypes.c_void_p()
+        self._check(lib().bpgpu_fr_vandermonde(self.handle, _buf(x_be), n, ctypes.byref(h)), "fr_vandermonde")
+        return DeviceScalars(self, h)
+
+    def _fr_binop(self, fn, name, a, b, n=None, aoff=0, boff=0, out=None, ooff=0):
+        n = len(a) - aoff if n is None else n
+        out = out or self.alloc_scalars(n + ooff)
+        self._check(fn(self.handle, a.handle, aoff, b.handle, boff, n, out.handle, ooff), name)
+        return out
+
+    def fr_hadamard(self, a, b, **kw):
+        return self._fr_binop(lib().bpgpu_fr_hadamard, "fr_hadamard", a, b, **kw)
+
+    def fr_add(self, a, b, **kw):
+        return self._fr_binop(lib().bpgpu_fr_add, "fr_add", a, b, **kw)
+
+    def fr_sub(self, a, b, **kw):
+        return self._fr_binop(lib().bpgpu_fr_sub, "fr_sub", a, b, **kw)
+
+    def fr_scale(self, a, s_be, n=None, aoff=0, out=None, ooff=0):
+        n = len(a) - aoff if n is None else n
+        out = out or self.alloc_scalars(n + ooff)
+        self._check(lib().bpgpu_fr_scale(self.handle, a.handle, aoff, n, _buf(s_be), out.handle, ooff), "fr_scale")
+        return out
+
+    def fr_inner_product(self, a, b, n=None, aoff=0, boff=0):
+        n = len(a) - aoff if n is None else n
+        out = ctypes.create_string_buffer(self.modbytes)
+        self._check(lib().bpgpu_fr_inner_product(self.handle, a.handle, aoff, b.handle, boff, n, out), "fr_inner_product")
+        return out.raw
+
+    def fr_poly3_special_inner_product(self, l1, l2, l3, r0, r1, r3, n):
+        out = ctypes.create_string_buffer(6 * self.modbytes)
+        self._check(lib().bpgpu_fr_poly3_special_inner_product(self.handle, l1.handle, l2.handle, l3.handle, r0.handle,
+                                                               r1.handle, r3.handle, n, out), "fr_poly3_special_inner_product")
+        return out.raw
+
+    def fr_batch_invert(self, a, n=None, aoff=0):
+        n = len(a) - aoff if n is None else n
+        out = self.alloc_scalars(n)
+        prod = ctypes.create_string_buffer(self.modbytes)
+        self._check(lib().bpgpu_fr_batch_invert(self.handle, a.handle, aoff, n, out.handle, 0, prod), "fr_batch_invert")
+        return out, prod.raw
+
+    # ---- inner-product argument rounds (device resident)
+    def ipp_begin(self, G, H, Q_xy, Gf, Hf, a, b, n, goff=0, hoff=0):
+        h = ctypes.c_void_p()
+        self._check(lib().bpgpu_ipp_begin(self.handle, G.handle, goff, H.handle, hoff, _buf(Q_xy), Gf.handle, Hf.handle,
+                                          a.handle, b.handle, n, ctypes.byref(h)), "ipp_begin")
+        return h
+
+    def ipp_round_LR(self, st):
+        L, R = ctypes.create_string_buffer(2 * self.modbytes), ctypes.create_string_buffer(2 * self.modbytes)
+        self._check(lib().bpgpu_ipp_round_LR(st, L, R), "ipp_round_LR")
+        return L.raw, R.raw
+
+    def ipp_fold(self, st, u_be, u_inv_be):
+        self._check(lib().bpgpu_ipp_fold(st, _buf(u_be), _buf(u_inv_be)), "ipp_fold")
+
+    def ipp_finish(self, st):
+        a, b = ctypes.create_string_buffer(self.modbytes), ctypes.create_string_buffer(self.modbytes)
+        self._check(lib().bpgpu_ipp_finish(st, a, b), "ipp_finish")
+        lib().bpgpu_ipp_free(st)
+        return a.raw, b.raw
+
+    def ipp_verification_scalars(self, u_be, lg):
+        h = ctypes.c_void_p()
+        self._check(lib().bpgpu_ipp_verification_scalars(self.handle, _buf(u_be), lg, ctypes.byref(h)), "ipp_verification_scalars")
+        return DeviceScalars(self, h)
+
+    def ipp_verify_msm(self, G, H, Q_xy, Gf, Hf, a_be, b_be, u_be, L_xy, R_xy, lg, goff=0, hoff=0):
+        out = ctypes.create_string_buffer(2 * self.modbytes)
+        self._check(lib().bpgpu_ipp_verify_msm(self.handle, G.handle, goff, H.handle, hoff, _buf(Q_xy), Gf.handle, Hf.handle,
+                                               _buf(a_be), _buf(b_be), _buf(u_be), _buf(L_xy), _buf(R_xy), lg, out), "ipp_verify_msm")
+        return out.raw
 
     # ---- MSM (G1Vector::multi_scalar_mul_var_time & friends)
     def msm(self, points, scalars_be, off=0, n=None):

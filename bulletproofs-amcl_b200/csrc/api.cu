@@ -147,17 +147,45 @@ __global__ void __launch_bounds__(256) k_imad_wide(int iters, uint32_t seed, uin
   for (int k = 0; k < 8; k++) x ^= acc[k];
   if (x == 0x123456789abcdefull) sink[0] = x;
 }
-// kind 1: dependent chain of Fq Montgomery products per thread (2 interleaved chains)
-template <class F>
+// kind 2: plain 32-bit IMAD (mad.lo) chains; kind 3: 1 IMAD.WIDE : 2 IMAD mix
+__global__ void __launch_bounds__(256) k_imad_lo(int iters, uint32_t seed, int mix, uint64_t* sink) {
+  uint32_t a = seed + threadIdx.x, b = seed * 3 + blockIdx.x;
+  uint32_t acc[16];
+  uint64_t wacc[4];
+#pragma unroll
+  for (int k = 0; k < 16; k++) acc[k] = seed + k;
+#pragma unroll
+  for (int k = 0; k < 4; k++) wacc[k] = seed + k;
+  for (int it = 0; it < iters; it++) {
+#pragma unroll
+    for (int u = 0; u < 4; u++) {
+#pragma unroll
+      for (int k = 0; k < 16; k++) acc[k] = a * (b + k) + acc[k];            // IMAD
+      if (mix) {
+#pragma unroll
+        for (int k = 0; k < 4; k++) { wacc[k] = (uint64_t)a * (b + k) + wacc[k]; wacc[k] = (uint64_t)b * (a + k) + wacc[k]; }   // 8 IMAD.WIDE
+      }
+      a += acc[0];
+    }
+  }
+  uint64_t x = 0;
+#pragma unroll
+  for (int k = 0; k < 16; k++) x ^= acc[k];
+#pragma unroll
+  for (int k = 0; k < 4; k++) x ^= wacc[k];
+  if (x == 0x123456789abcdefull) sink[0] = x;
+}
+// kind 1 / 10+SP: dependent chains of Fq Montgomery products per thread (2 interleaved chains)
+template <class F, int SP>
 __global__ void __launch_bounds__(256) k_fq_mul_chain(int iters, const F* in, F* out) {
   size_t i = (size_t)blockIdx.x * blockDim.x + threadIdx.x;
   F x = load_vec(in + (i & 255)), y = load_vec(in + ((i + 7) & 255));
-  for (int it = 0; it < iters; it++) { x = x * y; y = y * x; }
+  for (int it = 0; it < iters; it++) { x = F::template mul_t<SP>(x, y); y = F::template mul_t<SP>(y, x); }
   if (x.is_zero() && y.is_zero()) store_vec(out, x);
 }
 
 template <class Curve>
-static int points_upload_t(bpgpu_ctx* ctx, const uint8_t* xy, size_t n, void* dst) {
+int points_from_host(bpgpu_ctx* ctx, const uint8_t* xy, size_t n, void* dst) {
   if (n == 0) return BPGPU_OK;
   size_t bytes = n * 2 * Curve::MODBYTES;
   int rc = ctx->io_dev.reserve(bytes);
@@ -168,6 +196,8 @@ static int points_upload_t(bpgpu_ctx* ctx, const uint8_t* xy, size_t n, void* ds
   ctx->launches++;
   return launch_check(ctx, "k_points_from_be");
 }
+template int points_from_host<Bls>(bpgpu_ctx*, const uint8_t*, size_t, void*);
+template int points_from_host<Bn>(bpgpu_ctx*, const uint8_t*, size_t, void*);
 
 template <class Curve>
 static int scalars_upload_t(bpgpu_ctx* ctx, const uint8_t* be, size_t n, int mont, void* dst, Scratch& stage) {
@@ -204,6 +234,25 @@ static void msm_finish_host(const uint8_t* winsum_bytes, int W, int c, int qshif
   acc.to_xy_be(modbytes, out_xy);
 }
 
+}  // namespace bp
+
+namespace bp {
+int msm_to_host(bpgpu_ctx* ctx, const void* d_pts, const void* d_scal, bool mont, size_t n, uint8_t* out_xy) {
+  int mb = bpgpu_modbytes(ctx->curve);
+  MsmResult res;
+  int rc;
+  if (ctx->curve == BPGPU_BLS12_381) rc = msm_run<Bls>(ctx, (const Affine<Bls::Fq>*)d_pts, d_scal, mont, n, &res);
+  else rc = msm_run<Bn>(ctx, (const Affine<Bn::Fq>*)d_pts, d_scal, mont, n, &res);
+  if (rc) return rc;
+  size_t psz = (ctx->curve == BPGPU_BLS12_381) ? sizeof(XYZZ<Bls::Fq>) : sizeof(XYZZ<Bn::Fq>);
+  if (res.W) {
+    BP_CUDA_OK(cudaMemcpyAsync(ctx->pinned, res.d_winsum, 2 * res.W * psz, cudaMemcpyDeviceToHost, ctx->stream));
+    BP_CUDA_OK(cudaStreamSynchronize(ctx->stream));
+  }
+  if (ctx->curve == BPGPU_BLS12_381) msm_finish_host<BlsFq>(ctx->pinned, res.W, res.c, res.qshift, mb, out_xy);
+  else msm_finish_host<BnFq>(ctx->pinned, res.W, res.c, res.qshift, mb, out_xy);
+  return BPGPU_OK;
+}
 }  // namespace bp
 
 using namespace bp;
@@ -253,7 +302,7 @@ int bpgpu_ctx_create(int curve, int device, bpgpu_ctx** out) {
   BP_CUDA_OK(cudaGetDeviceProperties(&prop, device));
   c->sm_count = prop.multiProcessorCount;
   BP_CUDA_OK(cudaStreamCreateWithFlags(&c->stream, cudaStreamNonBlocking));
-  c->pinned_cap = 1 << 16;
+  c->pinned_cap = 1 << 18;
   BP_CUDA_OK(cudaHostAlloc((void**)&c->pinned, c->pinned_cap, cudaHostAllocDefault));
   *out = c;
   return BPGPU_OK;
@@ -265,6 +314,8 @@ void bpgpu_ctx_destroy(bpgpu_ctx* c) {
   cudaStreamSynchronize(c->stream);
   c->msm_a.release(); c->msm_b.release(); c->msm_c.release(); c->msm_d.release(); c->msm_e.release();
   c->io_dev.release(); c->io_dev2.release();
+  c->ipp_pts.release(); c->ipp_scl.release();
+  c->fr_tmp.release(); c->fr_out.release(); c->fr_args.release(); c->fr_pow.release(); c->fr_pow2.release();
   if (c->pinned) cudaFreeHost(c->pinned);
   cudaStreamDestroy(c->stream);
   delete c;
@@ -309,7 +360,7 @@ int bpgpu_points_upload(bpgpu_ctx* ctx, const uint8_t* xy, size_t n, bpgpu_point
   p->ctx = ctx; p->n = n; p->d = nullptr;
   size_t psz = (ctx->curve == BPGPU_BLS12_381) ? sizeof(Affine<Bls::Fq>) : sizeof(Affine<Bn::Fq>);
   if (cudaMalloc(&p->d, n ? n * psz : 16) != cudaSuccess) { delete p; return BPGPU_E_CUDA; }
-#define CALL(C) points_upload_t<C>(ctx, xy, n, p->d)
+#define CALL(C) points_from_host<C>(ctx, xy, n, p->d)
   int rc = DISPATCH(ctx, CALL);
 #undef CALL
   if (rc == BPGPU_OK && cudaStreamSynchronize(ctx->stream) != cudaSuccess) rc = BPGPU_E_CUDA;
@@ -392,22 +443,6 @@ void bpgpu_scalars_free(bpgpu_scalars* s) {
 // ------------------------------------------------------------------ MSM
 int bpgpu_msm_window_bits(size_t n) { return msm_window_bits(n); }
 
-static int msm_dispatch(bpgpu_ctx* ctx, const void* d_pts, const void* d_scal, bool mont, size_t n, uint8_t* out_xy) {
-  int mb = bpgpu_modbytes(ctx->curve);
-  MsmResult res;
-  int rc;
-  if (ctx->curve == BPGPU_BLS12_381) rc = msm_run<Bls>(ctx, (const Affine<Bls::Fq>*)d_pts, d_scal, mont, n, &res);
-  else rc = msm_run<Bn>(ctx, (const Affine<Bn::Fq>*)d_pts, d_scal, mont, n, &res);
-  if (rc) return rc;
-  size_t psz = (ctx->curve == BPGPU_BLS12_381) ? sizeof(XYZZ<Bls::Fq>) : sizeof(XYZZ<Bn::Fq>);
-  if (res.W) {
-    BP_CUDA_OK(cudaMemcpyAsync(ctx->pinned, res.d_winsum, 2 * res.W * psz, cudaMemcpyDeviceToHost, ctx->stream));
-    BP_CUDA_OK(cudaStreamSynchronize(ctx->stream));
-  }
-  if (ctx->curve == BPGPU_BLS12_381) msm_finish_host<BlsFq>(ctx->pinned, res.W, res.c, res.qshift, mb, out_xy);
-  else msm_finish_host<BnFq>(ctx->pinned, res.W, res.c, res.qshift, mb, out_xy);
-  return BPGPU_OK;
-}
 
 int bpgpu_msm(bpgpu_ctx* ctx, const bpgpu_points* p, size_t off, size_t n, const uint8_t* scalars_be, uint8_t* out_xy) {
   if (!ctx || !p || !out_xy || (!scalars_be && n)) return BPGPU_E_ARG;
@@ -420,7 +455,7 @@ int bpgpu_msm(bpgpu_ctx* ctx, const bpgpu_points* p, size_t off, size_t n, const
 #undef CALL
   if (rc) return rc;
   size_t psz = (ctx->curve == BPGPU_BLS12_381) ? sizeof(Affine<Bls::Fq>) : sizeof(Affine<Bn::Fq>);
-  return msm_dispatch(ctx, (const uint8_t*)p->d + off * psz, ctx->msm_c.p, false, n, out_xy);
+  return msm_to_host(ctx, (const uint8_t*)p->d + off * psz, ctx->msm_c.p, false, n, out_xy);
 }
 
 int bpgpu_msm_device(bpgpu_ctx* ctx, const bpgpu_points* p, size_t poff, size_t n, const bpgpu_scalars* s, size_t soff,
@@ -429,7 +464,7 @@ int bpgpu_msm_device(bpgpu_ctx* ctx, const bpgpu_points* p, size_t poff, size_t 
   if (poff > p->n || n > p->n - poff || soff > s->n || n > s->n - soff) return BPGPU_E_LEN;
   BP_CUDA_OK(cudaSetDevice(ctx->device));
   size_t psz = (ctx->curve == BPGPU_BLS12_381) ? sizeof(Affine<Bls::Fq>) : sizeof(Affine<Bn::Fq>);
-  return msm_dispatch(ctx, (const uint8_t*)p->d + poff * psz, (const uint8_t*)s->d + soff * 32, true, n, out_xy);
+  return msm_to_host(ctx, (const uint8_t*)p->d + poff * psz, (const uint8_t*)s->d + soff * 32, true, n, out_xy);
 }
 
 int bpgpu_msm_refs(bpgpu_ctx* ctx, const uint8_t* points_xy, const uint8_t* scalars_be, size_t n, uint8_t* out_xy) {
@@ -439,7 +474,7 @@ int bpgpu_msm_refs(bpgpu_ctx* ctx, const uint8_t* points_xy, const uint8_t* scal
   int rc = ctx->msm_d.reserve(n * psz + 32);
   if (rc) return rc;
   if ((rc = ctx->msm_c.reserve(n * 32 + 32))) return rc;
-#define CALL(C) points_upload_t<C>(ctx, points_xy, n, ctx->msm_d.p)
+#define CALL(C) points_from_host<C>(ctx, points_xy, n, ctx->msm_d.p)
   rc = DISPATCH(ctx, CALL);
 #undef CALL
   if (rc) return rc;
@@ -447,7 +482,7 @@ int bpgpu_msm_refs(bpgpu_ctx* ctx, const uint8_t* points_xy, const uint8_t* scal
   rc = DISPATCH(ctx, CALL);
 #undef CALL
   if (rc) return rc;
-  return msm_dispatch(ctx, ctx->msm_d.p, ctx->msm_c.p, false, n, out_xy);
+  return msm_to_host(ctx, ctx->msm_d.p, ctx->msm_c.p, false, n, out_xy);
 }
 
 // ------------------------------------------------------------------ self tests
@@ -521,12 +556,23 @@ int bpgpu_int_pipe_bench(bpgpu_ctx* ctx, int kind, int iters, double* ops_per_s,
     if (kind == 0) {
       k_imad_wide<<<blocks, threads, 0, ctx->stream>>>(iters, 12345u + rep, (uint64_t*)ctx->io_dev.p);
       ops = (double)blocks * threads * (double)iters * 64.0;
+    } else if (kind == 2 || kind == 3) {
+      k_imad_lo<<<blocks, threads, 0, ctx->stream>>>(iters, 12345u + rep, kind == 3, (uint64_t*)ctx->io_dev.p);
+      ops = (double)blocks * threads * (double)iters * 4.0 * (kind == 3 ? 24.0 : 16.0);   // instructions
     } else {
       BP_CUDA_OK(cudaMemsetAsync(ctx->io_dev.p, 0x5a, 1 << 16, ctx->stream));
-      if (ctx->curve == BPGPU_BLS12_381)
-        k_fq_mul_chain<Bls::Fq><<<blocks, threads, 0, ctx->stream>>>(iters, (const Bls::Fq*)ctx->io_dev.p, (Bls::Fq*)ctx->io_dev.p);
-      else
-        k_fq_mul_chain<Bn::Fq><<<blocks, threads, 0, ctx->stream>>>(iters, (const Bn::Fq*)ctx->io_dev.p, (Bn::Fq*)ctx->io_dev.p);
+      const Bls::Fq* in = (const Bls::Fq*)ctx->io_dev.p;
+      Bls::Fq* o = (Bls::Fq*)ctx->io_dev.p;
+      switch (kind) {
+        case 11: k_fq_mul_chain<Bls::Fq, 1><<<blocks, threads, 0, ctx->stream>>>(iters, in, o); break;
+        case 12: k_fq_mul_chain<Bls::Fq, 2><<<blocks, threads, 0, ctx->stream>>>(iters, in, o); break;
+        case 13: k_fq_mul_chain<Bls::Fq, 3><<<blocks, threads, 0, ctx->stream>>>(iters, in, o); break;
+        case 14: k_fq_mul_chain<Bls::Fq, 4><<<blocks, threads, 0, ctx->stream>>>(iters, in, o); break;
+        case 16: k_fq_mul_chain<Bls::Fq, 6><<<blocks, threads, 0, ctx->stream>>>(iters, in, o); break;
+        case 20: k_fq_mul_chain<Bn::Fq, 0><<<blocks, threads, 0, ctx->stream>>>(iters, (const Bn::Fq*)ctx->io_dev.p, (Bn::Fq*)ctx->io_dev.p); break;
+        case 22: k_fq_mul_chain<Bn::Fq, 2><<<blocks, threads, 0, ctx->stream>>>(iters, (const Bn::Fq*)ctx->io_dev.p, (Bn::Fq*)ctx->io_dev.p); break;
+        default: k_fq_mul_chain<Bls::Fq, 0><<<blocks, threads, 0, ctx->stream>>>(iters, in, o); break;
+      }
       ops = (double)blocks * threads * (double)iters * 2.0;
     }
     ctx->launches++;

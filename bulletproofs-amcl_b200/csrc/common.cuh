@@ -3,6 +3,8 @@
 #include <cuda_runtime.h>
 #include <stdint.h>
 #include <stdio.h>
+#include <new>
+#include <type_traits>
 #include <vector>
 
 #include "../../include/bpgpu.h"
@@ -63,6 +65,7 @@ struct bpgpu_ctx {
   uint64_t launches = 0;
   // MSM scratch
   bp::Scratch msm_a, msm_b, msm_c, msm_d, msm_e, io_dev, io_dev2;
+  bp::Scratch fr_tmp, fr_out, fr_args, fr_pow, fr_pow2, ipp_pts, ipp_scl;
   uint8_t* pinned = nullptr;      // small pinned staging (results, challenges)
   size_t pinned_cap = 0;
   // per-stage CUDA-event timing of the MSM pipeline (bpgpu_ctx_set_profile)
@@ -145,6 +148,14 @@ int launch_check(bpgpu_ctx* ctx, const char* what);
 // per-window sums an MSM leaves on the device: result = sum_w 2^(c*w) * winsum[w]
 // window w = P_w + 2^qshift * Q_w with P = d_winsum[0..W), Q = d_winsum[W..2W)
 struct MsmResult { int W; int c; int qshift; const void* d_winsum; };
+
+// host X||Y big-endian points -> device affine Montgomery (api.cu)
+template <class Curve> int points_from_host(bpgpu_ctx* ctx, const uint8_t* xy, size_t n, void* dst);
+// full MSM: device pipeline + host finish; d_scal = Fr[n] (Montgomery if mont) (api.cu)
+int msm_to_host(bpgpu_ctx* ctx, const void* d_pts, const void* d_scal, bool mont, size_t n, uint8_t* out_xy);
+// host scalars -> device Montgomery argument block in ctx->fr_args (frvec.cu)
+template <class Curve> int fr_args_upload(bpgpu_ctx* ctx, const uint8_t* be, int cnt, typename Curve::Fr** d_out);
+template <class Curve> int fr_pow_table_upload(bpgpu_ctx* ctx, const uint8_t* x_be, Scratch& dst, typename Curve::Fr** d_out);
 
 template <class Curve> int msm_run(bpgpu_ctx* ctx, const Affine<typename Curve::Fq>* d_points, const void* d_scalars,
                                    bool scalars_mont, size_t n, MsmResult* res);

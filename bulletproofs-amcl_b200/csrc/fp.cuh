@@ -29,6 +29,10 @@
 
 #include "field_params.h"
 
+#ifndef BP_FQ_SPLIT
+#define BP_FQ_SPLIT 0
+#endif
+
 namespace bp {
 
 // ---------------------------------------------------------------------------------------------
@@ -48,6 +52,9 @@ struct CarryChain {
   BP_D uint32_t mad_hi_cc(uint32_t a, uint32_t b, uint32_t c) { uint32_t r; asm volatile("mad.hi.cc.u32 %0, %1, %2, %3;" : "=r"(r) : "r"(a), "r"(b), "r"(c)); return r; }
   BP_D uint32_t madc_hi_cc(uint32_t a, uint32_t b, uint32_t c) { uint32_t r; asm volatile("madc.hi.cc.u32 %0, %1, %2, %3;" : "=r"(r) : "r"(a), "r"(b), "r"(c)); return r; }
   BP_D uint32_t madc_hi(uint32_t a, uint32_t b, uint32_t c) { uint32_t r; asm volatile("madc.hi.u32 %0, %1, %2, %3;" : "=r"(r) : "r"(a), "r"(b), "r"(c)); return r; }
+  // un-fused halves of a product: plain IMAD / IMAD.HI that may issue on either FMA sub-pipe
+  BP_D static uint32_t mul_lo(uint32_t a, uint32_t b) { uint32_t r; asm("mul.lo.u32 %0, %1, %2;" : "=r"(r) : "r"(a), "r"(b)); return r; }
+  BP_D static uint32_t mul_hi(uint32_t a, uint32_t b) { uint32_t r; asm("mul.hi.u32 %0, %1, %2;" : "=r"(r) : "r"(a), "r"(b)); return r; }
 };
 #else
 struct CarryChain {
@@ -63,6 +70,8 @@ struct CarryChain {
   uint32_t mad_hi_cc(uint32_t a, uint32_t b, uint32_t c) { return add_cc((uint32_t)(((uint64_t)a * b) >> 32), c); }
   uint32_t madc_hi_cc(uint32_t a, uint32_t b, uint32_t c) { return addc_cc((uint32_t)(((uint64_t)a * b) >> 32), c); }
   uint32_t madc_hi(uint32_t a, uint32_t b, uint32_t c) { return addc((uint32_t)(((uint64_t)a * b) >> 32), c); }
+  static uint32_t mul_lo(uint32_t a, uint32_t b) { return (uint32_t)((uint64_t)a * b); }
+  static uint32_t mul_hi(uint32_t a, uint32_t b) { return (uint32_t)(((uint64_t)a * b) >> 32); }
 };
 #endif
 
@@ -121,7 +130,13 @@ struct Fp {
   BP_HD Fp dbl() const { return *this + *this; }
 
   // ---- Montgomery product, even/odd accumulator schedule (see file header)
-  BP_HD friend Fp operator*(const Fp& a, const Fp& b) {
+  BP_HD friend Fp operator*(const Fp& a, const Fp& b) { return mul_t<BP_FQ_SPLIT>(a, b); }
+
+  // SP = number of products per accumulate chain issued as separate IMAD + IMAD.HI (+2 IADD3.X)
+  // instead of one fused IMAD.WIDE.U32.X.  IMAD.WIDE only issues on the "fmaheavy" half of the FMA
+  // pipe (measured: half the IMAD rate); plain IMADs can use the other half, so a mix balances them.
+  template <int SP>
+  BP_HD static Fp mul_t(const Fp& a, const Fp& b) {
     static_assert(N % 2 == 0, "even limb count");
     uint32_t ev[N], od[N];
     // row 0: plain products, no accumulation
@@ -134,14 +149,14 @@ struct Fp {
         uint64_t po = (uint64_t)a.v[j + 1] * bi;
         od[j] = (uint32_t)po; od[j + 1] = (uint32_t)(po >> 32);
       }
-      reduce_row(ev, od);
+      reduce_row<SP>(ev, od);
     }
 #pragma unroll
     for (int i = 1; i < N; i++) {
       // roles alternate: after a reduction row the accumulator whose limb 0 was cleared is,
       // shifted right by one limb, the odd accumulator of the next row.
-      if (i & 1) { mul_row(od, ev, a.v, b.v[i]); reduce_row(od, ev); }
-      else       { mul_row(ev, od, a.v, b.v[i]); reduce_row(ev, od); }
+      if (i & 1) { mul_row<SP>(od, ev, a.v, b.v[i]); reduce_row<SP>(od, ev); }
+      else       { mul_row<SP>(ev, od, a.v, b.v[i]); reduce_row<SP>(ev, od); }
     }
     // after N rows (N even) the cleared accumulator is `od`... the last reduce_row call had
     // (even=od, odd=ev) when N-1 is odd.
@@ -187,13 +202,19 @@ struct Fp {
   // then even += a_even*bi, odd += a_odd*bi.
   //   `even` enters holding the previous odd accumulator, `odd` enters holding the previous even
   //   accumulator whose limb 0 is zero and whose limb 1 still has to be added at position 0.
+  template <int SP>
   BP_HD static void mul_row(uint32_t* even, uint32_t* odd, const uint32_t* a, uint32_t bi) {
     CarryChain c;
     even[0] = c.add_cc(even[0], odd[1]);                 // carry -> position 1 = first limb of the odd chain
 #pragma unroll
     for (int j = 0; j < N - 2; j += 2) {                 // odd[k] <- odd[k+2] + a[j+1]*bi  (shifted accumulate)
-      odd[j] = c.madc_lo_cc(a[j + 1], bi, odd[j + 2]);
-      odd[j + 1] = c.madc_hi_cc(a[j + 1], bi, odd[j + 3]);
+      if (j >= N - 2 * SP) {
+        odd[j] = c.addc_cc(CarryChain::mul_lo(a[j + 1], bi), odd[j + 2]);
+        odd[j + 1] = c.addc_cc(CarryChain::mul_hi(a[j + 1], bi), odd[j + 3]);
+      } else {
+        odd[j] = c.madc_lo_cc(a[j + 1], bi, odd[j + 2]);
+        odd[j + 1] = c.madc_hi_cc(a[j + 1], bi, odd[j + 3]);
+      }
     }
     odd[N - 2] = c.madc_lo_cc(a[N - 1], bi, 0);
     odd[N - 1] = c.madc_hi(a[N - 1], bi, 0);            // no carry out: value bound < 2^(32(N+1))
@@ -202,13 +223,19 @@ struct Fp {
     even[1] = d.madc_hi_cc(a[0], bi, even[1]);
 #pragma unroll
     for (int j = 2; j < N; j += 2) {
-      even[j] = d.madc_lo_cc(a[j], bi, even[j]);
-      even[j + 1] = d.madc_hi_cc(a[j], bi, even[j + 1]);
+      if (j >= N - 2 * SP) {
+        even[j] = d.addc_cc(CarryChain::mul_lo(a[j], bi), even[j]);
+        even[j + 1] = d.addc_cc(CarryChain::mul_hi(a[j], bi), even[j + 1]);
+      } else {
+        even[j] = d.madc_lo_cc(a[j], bi, even[j]);
+        even[j + 1] = d.madc_hi_cc(a[j], bi, even[j + 1]);
+      }
     }
     odd[N - 1] = d.addc(odd[N - 1], 0);                  // position N lives in odd[N-1]
   }
 
   // m = even[0] * (-p^-1); even += p_even*m (clears even[0]); odd += p_odd*m
+  template <int SP>
   BP_HD static void reduce_row(uint32_t* even, uint32_t* odd) {
     const uint32_t m = even[0] * P::INV;
     CarryChain c;
@@ -216,16 +243,26 @@ struct Fp {
     odd[1] = c.madc_hi_cc(P::PC(1), m, odd[1]);
 #pragma unroll
     for (int j = 2; j < N; j += 2) {
-      odd[j] = c.madc_lo_cc(P::PC(j + 1), m, odd[j]);
-      odd[j + 1] = c.madc_hi_cc(P::PC(j + 1), m, odd[j + 1]);
+      if (j >= N - 2 * SP) {
+        odd[j] = c.addc_cc(CarryChain::mul_lo(P::PC(j + 1), m), odd[j]);
+        odd[j + 1] = c.addc_cc(CarryChain::mul_hi(P::PC(j + 1), m), odd[j + 1]);
+      } else {
+        odd[j] = c.madc_lo_cc(P::PC(j + 1), m, odd[j]);
+        odd[j + 1] = c.madc_hi_cc(P::PC(j + 1), m, odd[j + 1]);
+      }
     }
     CarryChain d;
     even[0] = d.mad_lo_cc(P::PC(0), m, even[0]);
     even[1] = d.madc_hi_cc(P::PC(0), m, even[1]);
 #pragma unroll
     for (int j = 2; j < N; j += 2) {
-      even[j] = d.madc_lo_cc(P::PC(j), m, even[j]);
-      even[j + 1] = d.madc_hi_cc(P::PC(j), m, even[j + 1]);
+      if (j >= N - 2 * SP) {
+        even[j] = d.addc_cc(CarryChain::mul_lo(P::PC(j), m), even[j]);
+        even[j + 1] = d.addc_cc(CarryChain::mul_hi(P::PC(j), m), even[j + 1]);
+      } else {
+        even[j] = d.madc_lo_cc(P::PC(j), m, even[j]);
+        even[j + 1] = d.madc_hi_cc(P::PC(j), m, even[j + 1]);
+      }
     }
     odd[N - 1] = d.addc(odd[N - 1], 0);
   }

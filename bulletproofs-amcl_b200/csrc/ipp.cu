@@ -1,0 +1,345 @@
+// Inner-product-argument rounds with device-resident state (IPP::create_ipp,
+// /root/reference/src/ipp.rs:35-202) and the verifier's s-vector (ipp.rs:262-315).
+//
+// The reference folds the generator vectors every round with one two-scalar multiplication per
+// element (ipp.rs:119-129,185-187: ~255 doublings each, 85 % of its IPP time).  On a GPU that is a
+// 255-deep dependent chain on a shrinking number of threads.  This implementation NEVER
+// materialises folded generators.  After k rounds the folded generator is the fixed combination
+//     G^(k)[j] = sum_{i = j mod n_k} sG_k(i) * G[i],   sG_k(i) = Gf[i] * prod_{t<k} (bit_t(i) ? u_t : u_t^-1)
+// (bit_t(i) = bit lgN-1-t of i; for H the roles of u and u^-1 swap), hence
+//     L_k = sum_{i: bit_k(i)=1} a_k[i mod n_k/2] * sG_k(i) * G[i] + sum_{i: bit_k(i)=0} b_k[(i mod n_k/2) + n_k/2] * sH_k(i) * H[i] + c_L * Q
+// is ONE MSM over the ORIGINAL bases [G | H | Q] with per-index scalars built by a fused Fr kernel
+// (and R_k likewise on the complementary index set).  L_k, R_k are the same group elements the
+// reference computes, so the transcript, the challenges and the proof bytes are identical; only
+// a, b and the coefficient vectors sG, sH are folded (Fr work), all resident across the lg N
+// rounds.  Per round the host sees 2 points (D2H) and sends u, u^-1 (H2D), as in SURVEY.md 3.1.
+#include "common.cuh"
+#include "host_fp.h"
+
+struct bpgpu_ipp {
+  bpgpu_ctx* ctx;
+  size_t N, n_cur;
+  void* P;                 // Affine[2N+1] : G | H | Q
+  void *a, *b;             // Fr[N]
+  void *sG, *sH;           // Fr[N]
+  void *sclL, *sclR;       // Fr[2N+1]
+};
+
+namespace bp {
+
+// scalars of the L and R MSMs of the current round (length 2N+1 each; slot 2N is filled by k_ipp_cross)
+template <class Fr>
+__global__ void __launch_bounds__(128) k_ipp_build(uint32_t N, uint32_t n_cur, const Fr* __restrict__ a, const Fr* __restrict__ b,
+                                                   const Fr* __restrict__ sG, const Fr* __restrict__ sH,
+                                                   Fr* __restrict__ sclL, Fr* __restrict__ sclR) {
+  uint32_t i = blockIdx.x * blockDim.x + threadIdx.x;
+  if (i >= N) return;
+  const uint32_t half = n_cur >> 1;
+  const uint32_t p = i & (n_cur - 1);
+  const Fr zero = Fr::zero();
+  Fr g = load_vec(sG + i), h = load_vec(sH + i);
+  if (p < half) {
+    // i is in the left half: H_L takes b_R (L), G_L takes a_R (R)
+    store_vec(sclL + i, zero);
+    store_vec(sclL + N + i, load_vec(b + p + half) * h);
+    store_vec(sclR + i, load_vec(a + p + half) * g);
+    store_vec(sclR + N + i, zero);
+  } else {
+    // right half: G_R takes a_L (L), H_R takes b_L (R)
+    store_vec(sclL + i, load_vec(a + p - half) * g);
+    store_vec(sclL + N + i, zero);
+    store_vec(sclR + i, zero);
+    store_vec(sclR + N + i, load_vec(b + p - half) * h);
+  }
+}
+
+// c_L = <a_L, b_R>, c_R = <a_R, b_L>  (ipp.rs:77-78,145-146); one block, results to outL / outR
+template <class Fr>
+__global__ void __launch_bounds__(256) k_ipp_cross(uint32_t n_cur, const Fr* __restrict__ a, const Fr* __restrict__ b,
+                                                   Fr* __restrict__ outL, Fr* __restrict__ outR) {
+  __shared__ __align__(16) unsigned char smraw[256 * sizeof(Fr)];
+  Fr* sm = reinterpret_cast<Fr*>(smraw);
+  const uint32_t half = n_cur >> 1;
+  Fr cl = Fr::zero(), cr = Fr::zero();
+  for (uint32_t j = threadIdx.x; j < half; j += blockDim.x) {
+    Fr al = load_vec(a + j), ar = load_vec(a + j + half), bl = load_vec(b + j), br = load_vec(b + j + half);
+    cl = cl + al * br;
+    cr = cr + ar * bl;
+  }
+  for (int pass = 0; pass < 2; pass++) {
+    store_vec(sm + threadIdx.x, pass == 0 ? cl : cr);
+    __syncthreads();
+    for (int o = blockDim.x / 2; o > 0; o >>= 1) {
+      if ((int)threadIdx.x < o) store_vec(sm + threadIdx.x, load_vec(sm + threadIdx.x) + load_vec(sm + threadIdx.x + o));
+      __syncthreads();
+    }
+    if (threadIdx.x == 0) store_vec(pass == 0 ? outL : outR, load_vec(sm));
+    __syncthreads();
+  }
+}
+
+// fold a, b by (u, u^-1) and multiply the coefficient vectors (ipp.rs:115-130,181-188); uv = {u, u_inv}
+template <class Fr>
+__global__ void __launch_bounds__(128) k_ipp_fold(uint32_t N, uint32_t n_cur, const Fr* __restrict__ uv, Fr* __restrict__ a,
+                                                  Fr* __restrict__ b, Fr* __restrict__ sG, Fr* __restrict__ sH) {
+  uint32_t i = blockIdx.x * blockDim.x + threadIdx.x;
+  if (i >= N) return;
+  const uint32_t half = n_cur >> 1;
+  const uint32_t p = i & (n_cur - 1);
+  const Fr u = uv[0], ui = uv[1];
+  Fr g = load_vec(sG + i), h = load_vec(sH + i);
+  if (p < half) { g = g * ui; h = h * u; } else { g = g * u; h = h * ui; }
+  store_vec(sG + i, g);
+  store_vec(sH + i, h);
+  if (i < half) {
+    Fr al = load_vec(a + i), ar = load_vec(a + i + half), bl = load_vec(b + i), br = load_vec(b + i + half);
+    store_vec(a + i, al * u + ui * ar);
+    store_vec(b + i, bl * ui + u * br);
+  }
+}
+
+// s[i] = prod_t (bit_{lg-1-t}(i) ? u_t : u_t^-1)   (closed form of ipp.rs:303-312); uv = u[0..lg) | u_inv[0..lg)
+template <class Fr>
+__global__ void __launch_bounds__(128) k_ipp_s(uint32_t N, int lg, const Fr* __restrict__ uv, Fr* __restrict__ s) {
+  uint32_t i = blockIdx.x * blockDim.x + threadIdx.x;
+  if (i >= N) return;
+  Fr acc = Fr::one();
+  for (int t = 0; t < lg; t++) acc = acc * (((i >> (lg - 1 - t)) & 1) ? uv[t] : uv[lg + t]);
+  store_vec(s + i, acc);
+}
+
+// scalars of verify_ipp's MSM (ipp.rs:220-242) for points [Q | G | H | L | R]:
+//   [a*b | (a*s_i)*Gf_i | (b*s_{n-1-i})*Hf_i | -u_k^2 | -u_k^-2 ] ; args = {a, b} ; uv as in k_ipp_s
+template <class Fr>
+__global__ void __launch_bounds__(128) k_ipp_verify_scalars(uint32_t N, int lg, const Fr* __restrict__ ab, const Fr* __restrict__ uv,
+                                                            const Fr* __restrict__ s, const Fr* __restrict__ Gf,
+                                                            const Fr* __restrict__ Hf, Fr* __restrict__ out) {
+  uint32_t i = blockIdx.x * blockDim.x + threadIdx.x;
+  if (i < N) {
+    store_vec(out + 1 + i, (ab[0] * load_vec(s + i)) * load_vec(Gf + i));
+    store_vec(out + 1 + N + i, (ab[1] * load_vec(s + (N - 1 - i))) * load_vec(Hf + i));
+  }
+  if (i == 0) store_vec(out, ab[0] * ab[1]);
+  if (i < (uint32_t)lg) {
+    store_vec(out + 1 + 2 * N + i, uv[i].sqr().neg());
+    store_vec(out + 1 + 2 * N + lg + i, uv[lg + i].sqr().neg());
+  }
+}
+
+template <class Curve>
+static int ipp_begin_t(bpgpu_ipp* st, const void* G, const void* H, const uint8_t* Q_xy, const void* Gf, const void* Hf,
+                       const void* a, const void* b) {
+  using Fq = typename Curve::Fq;
+  using Fr = typename Curve::Fr;
+  bpgpu_ctx* ctx = st->ctx;
+  const size_t N = st->N;
+  cudaStream_t s = ctx->stream;
+  BP_CUDA_OK(cudaMalloc(&st->P, (2 * N + 1) * sizeof(Affine<Fq>)));
+  void* frs = nullptr;
+  BP_CUDA_OK(cudaMalloc(&frs, (4 * N + 2 * (2 * N + 1)) * sizeof(Fr)));
+  st->a = frs;
+  st->b = (Fr*)frs + N;
+  st->sG = (Fr*)frs + 2 * N;
+  st->sH = (Fr*)frs + 3 * N;
+  st->sclL = (Fr*)frs + 4 * N;
+  st->sclR = (Fr*)frs + 4 * N + (2 * N + 1);
+  BP_CUDA_OK(cudaMemcpyAsync(st->P, G, N * sizeof(Affine<Fq>), cudaMemcpyDeviceToDevice, s));
+  BP_CUDA_OK(cudaMemcpyAsync((Affine<Fq>*)st->P + N, H, N * sizeof(Affine<Fq>), cudaMemcpyDeviceToDevice, s));
+  int rc = points_from_host<Curve>(ctx, Q_xy, 1, (Affine<Fq>*)st->P + 2 * N);
+  if (rc) return rc;
+  BP_CUDA_OK(cudaMemcpyAsync(st->a, a, N * sizeof(Fr), cudaMemcpyDeviceToDevice, s));
+  BP_CUDA_OK(cudaMemcpyAsync(st->b, b, N * sizeof(Fr), cudaMemcpyDeviceToDevice, s));
+  BP_CUDA_OK(cudaMemcpyAsync(st->sG, Gf, N * sizeof(Fr), cudaMemcpyDeviceToDevice, s));
+  BP_CUDA_OK(cudaMemcpyAsync(st->sH, Hf, N * sizeof(Fr), cudaMemcpyDeviceToDevice, s));
+  return BPGPU_OK;
+}
+
+template <class Curve>
+static int ipp_round_t(bpgpu_ipp* st, uint8_t* L_xy, uint8_t* R_xy) {
+  using Fr = typename Curve::Fr;
+  bpgpu_ctx* ctx = st->ctx;
+  const uint32_t N = (uint32_t)st->N, n = (uint32_t)st->n_cur;
+  k_ipp_build<Fr><<<(N + 127) / 128, 128, 0, ctx->stream>>>(N, n, (const Fr*)st->a, (const Fr*)st->b, (const Fr*)st->sG,
+                                                           (const Fr*)st->sH, (Fr*)st->sclL, (Fr*)st->sclR);
+  k_ipp_cross<Fr><<<1, 256, 0, ctx->stream>>>(n, (const Fr*)st->a, (const Fr*)st->b, (Fr*)st->sclL + 2 * N, (Fr*)st->sclR + 2 * N);
+  ctx->launches += 2;
+  int rc = launch_check(ctx, "ipp_round");
+  if (rc) return rc;
+  if ((rc = msm_to_host(ctx, st->P, st->sclL, true, 2 * (size_t)N + 1, L_xy))) return rc;
+  return msm_to_host(ctx, st->P, st->sclR, true, 2 * (size_t)N + 1, R_xy);
+}
+
+template <class Curve>
+static int ipp_fold_t(bpgpu_ipp* st, const uint8_t* u_be, const uint8_t* ui_be) {
+  using Fr = typename Curve::Fr;
+  bpgpu_ctx* ctx = st->ctx;
+  uint8_t both[2 * 48];
+  memcpy(both, u_be, Curve::MODBYTES);
+  memcpy(both + Curve::MODBYTES, ui_be, Curve::MODBYTES);
+  Fr* uv;
+  int rc = fr_args_upload<Curve>(ctx, both, 2, &uv);
+  if (rc) return rc;
+  const uint32_t N = (uint32_t)st->N;
+  k_ipp_fold<Fr><<<(N + 127) / 128, 128, 0, ctx->stream>>>(N, (uint32_t)st->n_cur, uv, (Fr*)st->a, (Fr*)st->b, (Fr*)st->sG, (Fr*)st->sH);
+  ctx->launches++;
+  st->n_cur >>= 1;
+  return launch_check(ctx, "k_ipp_fold");
+}
+
+// u[0..lg) | u_inv[0..lg) as device Montgomery values in ctx->fr_args
+template <class Curve>
+static int upload_challenges(bpgpu_ctx* ctx, const uint8_t* u_be, size_t lg, typename Curve::Fr** uv) {
+  using HF = host::HFp<typename std::conditional<Curve::ID == BPGPU_BLS12_381, BlsFr, BnFr>::type>;
+  std::vector<uint8_t> both(2 * lg * Curve::MODBYTES + 1);
+  for (size_t k = 0; k < lg; k++) {
+    memcpy(both.data() + k * Curve::MODBYTES, u_be + k * Curve::MODBYTES, Curve::MODBYTES);
+    HF::from_be(u_be + k * Curve::MODBYTES, Curve::MODBYTES).inv().to_be(both.data() + (lg + k) * Curve::MODBYTES, Curve::MODBYTES);
+  }
+  return fr_args_upload<Curve>(ctx, both.data(), (int)(2 * lg), uv);
+}
+
+template <class Curve>
+static int ipp_s_t(bpgpu_ctx* ctx, const uint8_t* u_be, size_t lg, void* d_s) {
+  using Fr = typename Curve::Fr;
+  Fr* uv;
+  int rc = upload_challenges<Curve>(ctx, u_be, lg, &uv);
+  if (rc) return rc;
+  const uint32_t N = 1u << lg;
+  k_ipp_s<Fr><<<(N + 127) / 128, 128, 0, ctx->stream>>>(N, (int)lg, uv, (Fr*)d_s);
+  ctx->launches++;
+  return launch_check(ctx, "k_ipp_s");
+}
+
+template <class Curve>
+static int ipp_verify_t(bpgpu_ctx* ctx, const void* G, const void* H, const uint8_t* Q_xy, const void* Gf, const void* Hf,
+                        const uint8_t* a_be, const uint8_t* b_be, const uint8_t* u_be, const uint8_t* L_xy, const uint8_t* R_xy,
+                        size_t lg, uint8_t* out_xy) {
+  using Fq = typename Curve::Fq;
+  using Fr = typename Curve::Fr;
+  const size_t N = (size_t)1 << lg, total = 1 + 2 * N + 2 * lg;
+  int rc;
+  if ((rc = ctx->ipp_pts.reserve(total * sizeof(Affine<Fq>)))) return rc;
+  if ((rc = ctx->ipp_scl.reserve((total + N) * sizeof(Fr)))) return rc;
+  Affine<Fq>* P = (Affine<Fq>*)ctx->ipp_pts.p;
+  Fr* scl = (Fr*)ctx->ipp_scl.p;
+  Fr* s = scl + total;
+  if ((rc = points_from_host<Curve>(ctx, Q_xy, 1, P))) return rc;
+  BP_CUDA_OK(cudaMemcpyAsync(P + 1, G, N * sizeof(Affine<Fq>), cudaMemcpyDeviceToDevice, ctx->stream));
+  BP_CUDA_OK(cudaMemcpyAsync(P + 1 + N, H, N * sizeof(Affine<Fq>), cudaMemcpyDeviceToDevice, ctx->stream));
+  if (lg) {
+    if ((rc = points_from_host<Curve>(ctx, L_xy, lg, P + 1 + 2 * N))) return rc;
+    if ((rc = points_from_host<Curve>(ctx, R_xy, lg, P + 1 + 2 * N + lg))) return rc;
+  }
+  // argument block: u | u_inv | a | b
+  using HF = host::HFp<typename std::conditional<Curve::ID == BPGPU_BLS12_381, BlsFr, BnFr>::type>;
+  const int mb = Curve::MODBYTES;
+  std::vector<uint8_t> args((2 * lg + 2) * mb);
+  for (size_t k = 0; k < lg; k++) {
+    memcpy(args.data() + k * mb, u_be + k * mb, mb);
+    HF::from_be(u_be + k * mb, mb).inv().to_be(args.data() + (lg + k) * mb, mb);
+  }
+  memcpy(args.data() + 2 * lg * mb, a_be, mb);
+  memcpy(args.data() + (2 * lg + 1) * mb, b_be, mb);
+  Fr* dargs;
+  if ((rc = fr_args_upload<Curve>(ctx, args.data(), (int)(2 * lg + 2), &dargs))) return rc;
+  k_ipp_s<Fr><<<(unsigned)((N + 127) / 128), 128, 0, ctx->stream>>>((uint32_t)N, (int)lg, dargs, s);
+  k_ipp_verify_scalars<Fr><<<(unsigned)((N + 127) / 128), 128, 0, ctx->stream>>>((uint32_t)N, (int)lg, dargs + 2 * lg, dargs, s,
+                                                                            (const Fr*)Gf, (const Fr*)Hf, scl);
+  ctx->launches += 2;
+  if ((rc = launch_check(ctx, "ipp_verify"))) return rc;
+  return msm_to_host(ctx, P, scl, true, total, out_xy);
+}
+
+}  // namespace bp
+
+using namespace bp;
+
+static bool prange(const bpgpu_points* p, size_t off, size_t n) { return p && off <= p->n && n <= p->n - off; }
+static bool srange(const bpgpu_scalars* s, size_t off, size_t n) { return s && off <= s->n && n <= s->n - off; }
+static size_t psize(const bpgpu_ctx* c) { return c->curve == BPGPU_BLS12_381 ? sizeof(Affine<Bls::Fq>) : sizeof(Affine<Bn::Fq>); }
+
+extern "C" {
+
+int bpgpu_ipp_begin(bpgpu_ctx* ctx, const bpgpu_points* G, size_t goff, const bpgpu_points* H, size_t hoff, const uint8_t* Q_xy,
+                    const bpgpu_scalars* Gf, const bpgpu_scalars* Hf, const bpgpu_scalars* a, const bpgpu_scalars* b, size_t n,
+                    bpgpu_ipp** out) {
+  if (!ctx || !G || !H || !Q_xy || !Gf || !Hf || !a || !b || !out) return BPGPU_E_ARG;
+  *out = nullptr;
+  if (n == 0 || (n & (n - 1))) return BPGPU_E_NOT_POW2;                           // ipp.rs:48
+  if (!prange(G, goff, n) || !prange(H, hoff, n)) return BPGPU_E_LEN;             // ipp.rs:51
+  if (Gf->n != n || Hf->n != n || a->n != n || b->n != n) return BPGPU_E_LEN;     // ipp.rs:52-55
+  BP_CUDA_OK(cudaSetDevice(ctx->device));
+  bpgpu_ipp* st = new (std::nothrow) bpgpu_ipp();
+  if (!st) return BPGPU_E_CUDA;
+  memset(st, 0, sizeof *st);
+  st->ctx = ctx; st->N = n; st->n_cur = n;
+  const void* g = (const uint8_t*)G->d + goff * psize(ctx);
+  const void* h = (const uint8_t*)H->d + hoff * psize(ctx);
+  int rc = ctx->curve == BPGPU_BLS12_381 ? ipp_begin_t<Bls>(st, g, h, Q_xy, Gf->d, Hf->d, a->d, b->d)
+                                        : ipp_begin_t<Bn>(st, g, h, Q_xy, Gf->d, Hf->d, a->d, b->d);
+  if (rc) { bpgpu_ipp_free(st); return rc; }
+  *out = st;
+  return BPGPU_OK;
+}
+
+size_t bpgpu_ipp_len(const bpgpu_ipp* st) { return st ? st->n_cur : 0; }
+
+int bpgpu_ipp_round_LR(bpgpu_ipp* st, uint8_t* L_xy, uint8_t* R_xy) {
+  if (!st || !L_xy || !R_xy) return BPGPU_E_ARG;
+  if (st->n_cur < 2) return BPGPU_E_ARG;
+  BP_CUDA_OK(cudaSetDevice(st->ctx->device));
+  return st->ctx->curve == BPGPU_BLS12_381 ? ipp_round_t<Bls>(st, L_xy, R_xy) : ipp_round_t<Bn>(st, L_xy, R_xy);
+}
+
+int bpgpu_ipp_fold(bpgpu_ipp* st, const uint8_t* u_be, const uint8_t* u_inv_be) {
+  if (!st || !u_be || !u_inv_be) return BPGPU_E_ARG;
+  if (st->n_cur < 2) return BPGPU_E_ARG;
+  BP_CUDA_OK(cudaSetDevice(st->ctx->device));
+  return st->ctx->curve == BPGPU_BLS12_381 ? ipp_fold_t<Bls>(st, u_be, u_inv_be) : ipp_fold_t<Bn>(st, u_be, u_inv_be);
+}
+
+int bpgpu_ipp_finish(bpgpu_ipp* st, uint8_t* a_be, uint8_t* b_be) {
+  if (!st || !a_be || !b_be) return BPGPU_E_ARG;
+  if (st->n_cur != 1) return BPGPU_E_ARG;
+  bpgpu_scalars va{st->ctx, st->a, 1}, vb{st->ctx, st->b, 1};
+  int rc = bpgpu_scalars_download(st->ctx, &va, 0, 1, a_be);
+  if (rc) return rc;
+  return bpgpu_scalars_download(st->ctx, &vb, 0, 1, b_be);
+}
+
+void bpgpu_ipp_free(bpgpu_ipp* st) {
+  if (!st) return;
+  cudaSetDevice(st->ctx->device);
+  cudaStreamSynchronize(st->ctx->stream);
+  if (st->P) cudaFree(st->P);
+  if (st->a) cudaFree(st->a);
+  delete st;
+}
+
+int bpgpu_ipp_verification_scalars(bpgpu_ctx* ctx, const uint8_t* u_be, size_t lg, bpgpu_scalars** s_out) {
+  if (!ctx || (!u_be && lg) || !s_out) return BPGPU_E_ARG;
+  if (lg >= 32) return BPGPU_E_VERIFY;                                             // ipp.rs:269-273
+  int rc = bpgpu_scalars_alloc(ctx, (size_t)1 << lg, s_out);
+  if (rc) return rc;
+  rc = ctx->curve == BPGPU_BLS12_381 ? ipp_s_t<Bls>(ctx, u_be, lg, (*s_out)->d) : ipp_s_t<Bn>(ctx, u_be, lg, (*s_out)->d);
+  if (rc) { bpgpu_scalars_free(*s_out); *s_out = nullptr; }
+  return rc;
+}
+
+int bpgpu_ipp_verify_msm(bpgpu_ctx* ctx, const bpgpu_points* G, size_t goff, const bpgpu_points* H, size_t hoff,
+                         const uint8_t* Q_xy, const bpgpu_scalars* Gf, const bpgpu_scalars* Hf, const uint8_t* a_be,
+                         const uint8_t* b_be, const uint8_t* u_be, const uint8_t* L_xy, const uint8_t* R_xy, size_t lg,
+                         uint8_t* out_xy) {
+  if (!ctx || !G || !H || !Q_xy || !Gf || !Hf || !a_be || !b_be || !out_xy) return BPGPU_E_ARG;
+  if (lg && (!u_be || !L_xy || !R_xy)) return BPGPU_E_ARG;
+  if (lg >= 32) return BPGPU_E_VERIFY;
+  const size_t n = (size_t)1 << lg;
+  if (!prange(G, goff, n) || !prange(H, hoff, n) || !srange(Gf, 0, n) || !srange(Hf, 0, n)) return BPGPU_E_LEN;
+  BP_CUDA_OK(cudaSetDevice(ctx->device));
+  const void* g = (const uint8_t*)G->d + goff * psize(ctx);
+  const void* h = (const uint8_t*)H->d + hoff * psize(ctx);
+  return ctx->curve == BPGPU_BLS12_381 ? ipp_verify_t<Bls>(ctx, g, h, Q_xy, Gf->d, Hf->d, a_be, b_be, u_be, L_xy, R_xy, lg, out_xy)
+                                      : ipp_verify_t<Bn>(ctx, g, h, Q_xy, Gf->d, Hf->d, a_be, b_be, u_be, L_xy, R_xy, lg, out_xy);
+}
+
+}  // extern "C"

@@ -95,6 +95,57 @@ int bpgpu_msm_refs(bpgpu_ctx* ctx, const uint8_t* points_xy, const uint8_t* scal
 /* window width the MSM would use for n terms (reporting only) */
 int bpgpu_msm_window_bits(size_t n);
 
+/* ---- FieldElementVector algebra on device-resident vectors ------------------------------------
+ * Replaces FieldElementVector::{new_vandermonde_vector, hadamard_product, plus, scaled_by,
+ * inner_product} and FieldElement::batch_invert (ipp.rs:77-82,94-95,145-146,295; prover.rs:463,
+ * 472-485,513; verifier.rs:342-352,416) and VecPoly3::special_inner_product (vector_poly.rs:79-97).
+ * Length/offset violations return BPGPU_E_LEN (ValueError::UnequalSizeVectors). */
+int bpgpu_scalars_alloc(bpgpu_ctx* ctx, size_t n, bpgpu_scalars** out);                    /* zero vector */
+int bpgpu_fr_vandermonde(bpgpu_ctx* ctx, const uint8_t* x_be, size_t n, bpgpu_scalars** out); /* [1,x,..,x^(n-1)] */
+int bpgpu_fr_hadamard(bpgpu_ctx* ctx, const bpgpu_scalars* a, size_t aoff, const bpgpu_scalars* b, size_t boff,
+                      size_t n, bpgpu_scalars* out, size_t ooff);
+int bpgpu_fr_add(bpgpu_ctx* ctx, const bpgpu_scalars* a, size_t aoff, const bpgpu_scalars* b, size_t boff,
+                 size_t n, bpgpu_scalars* out, size_t ooff);
+int bpgpu_fr_sub(bpgpu_ctx* ctx, const bpgpu_scalars* a, size_t aoff, const bpgpu_scalars* b, size_t boff,
+                 size_t n, bpgpu_scalars* out, size_t ooff);
+int bpgpu_fr_scale(bpgpu_ctx* ctx, const bpgpu_scalars* a, size_t aoff, size_t n, const uint8_t* s_be,
+                   bpgpu_scalars* out, size_t ooff);
+int bpgpu_fr_inner_product(bpgpu_ctx* ctx, const bpgpu_scalars* a, size_t aoff, const bpgpu_scalars* b, size_t boff,
+                           size_t n, uint8_t* out_be);
+/* t1..t6 (6 x MODBYTES) from l1,l2,l3,r0,r1,r3: nine inner products in one pass */
+int bpgpu_fr_poly3_special_inner_product(bpgpu_ctx* ctx, const bpgpu_scalars* l1, const bpgpu_scalars* l2,
+                                         const bpgpu_scalars* l3, const bpgpu_scalars* r0, const bpgpu_scalars* r1,
+                                         const bpgpu_scalars* r3, size_t n, uint8_t* t_be);
+/* elementwise inverses (0 -> 0) into out, product of all inverses into prod_inv_be (may be NULL) */
+int bpgpu_fr_batch_invert(bpgpu_ctx* ctx, const bpgpu_scalars* a, size_t aoff, size_t n, bpgpu_scalars* out,
+                          size_t ooff, uint8_t* prod_inv_be);
+
+/* ---- inner-product argument, device-resident across rounds (IPP::create_ipp, ipp.rs:35-202) ----
+ * begin: clones G[goff..goff+n), H[hoff..), a, b and the factor vectors (ipp.rs:57-60); n must be a power
+ *        of two (BPGPU_E_NOT_POW2 = the assert at ipp.rs:48) and all vectors length n (BPGPU_E_LEN).
+ * round_LR: L and R of the current round (ipp.rs:80-104 / 148-170), as X||Y.  The host commits them to
+ *        its transcript, draws u (ipp.rs:106-113 / 172-179) and calls
+ * fold:  a, b and the generator coefficients are folded by (u, u^-1) (ipp.rs:115-130 / 181-188).
+ * finish: after lg n rounds, the proof's a and b (ipp.rs:196-201).
+ * The G_factors / H_factors are applied in the first round only, as in the reference (ipp.rs:74-129). */
+int bpgpu_ipp_begin(bpgpu_ctx* ctx, const bpgpu_points* G, size_t goff, const bpgpu_points* H, size_t hoff,
+                    const uint8_t* Q_xy, const bpgpu_scalars* G_factors, const bpgpu_scalars* H_factors,
+                    const bpgpu_scalars* a, const bpgpu_scalars* b, size_t n, bpgpu_ipp** out);
+size_t bpgpu_ipp_len(const bpgpu_ipp* ipp);           /* current vector length (n, n/2, ..., 1) */
+int bpgpu_ipp_round_LR(bpgpu_ipp* ipp, uint8_t* L_xy, uint8_t* R_xy);
+int bpgpu_ipp_fold(bpgpu_ipp* ipp, const uint8_t* u_be, const uint8_t* u_inv_be);
+int bpgpu_ipp_finish(bpgpu_ipp* ipp, uint8_t* a_be, uint8_t* b_be);
+void bpgpu_ipp_free(bpgpu_ipp* ipp);
+/* the s vector of IPP::verification_scalars (ipp.rs:303-312) from the lg challenges u_k (creation order);
+ * lg >= 32 -> BPGPU_E_VERIFY (ipp.rs:269-273).  The transcript replay that yields u_k stays on the host. */
+int bpgpu_ipp_verification_scalars(bpgpu_ctx* ctx, const uint8_t* u_be, size_t lg, bpgpu_scalars** s_out);
+/* expected_P of IPP::verify_ipp (ipp.rs:220-253): one MSM over [Q | G | H | L | R] with the scalars
+ * [a*b | a*s_i*Gf_i | b*s_(n-1-i)*Hf_i | -u_k^2 | -u_k^-2] built on the device; n = 2^lg. */
+int bpgpu_ipp_verify_msm(bpgpu_ctx* ctx, const bpgpu_points* G, size_t goff, const bpgpu_points* H, size_t hoff,
+                         const uint8_t* Q_xy, const bpgpu_scalars* G_factors, const bpgpu_scalars* H_factors,
+                         const uint8_t* a_be, const uint8_t* b_be, const uint8_t* u_be, const uint8_t* L_xy,
+                         const uint8_t* R_xy, size_t lg, uint8_t* out_xy);
+
 /* ---- self-test / measurement hooks (used by tests/ and bench.py; not part of the drop-in) ---- */
 /* field: 0 Fq, 1 Fr of the ctx curve; op: 0 mul 1 add 2 sub 3 inv 4 sqr; operands are canonical
  * big-endian MODBYTES values (converted to/from Montgomery form on the device). */
