@@ -29,6 +29,7 @@ SYMBOLS = [
     ("bpgpu_host_free", None, [_VP]),
     ("bpgpu_points_upload", _INT, [_VP, _VP, _SZ, _c.POINTER(_VP)]),
     ("bpgpu_points_download", _INT, [_VP, _VP, _SZ, _SZ, _VP]),
+    ("bpgpu_points_from_hashes", _INT, [_VP, _VP, _SZ, _c.POINTER(_VP)]),
     ("bpgpu_points_len", _SZ, [_VP]),
     ("bpgpu_points_free", None, [_VP]),
     ("bpgpu_scalars_upload", _INT, [_VP, _VP, _SZ, _c.POINTER(_VP)]),
@@ -56,10 +57,36 @@ SYMBOLS = [
     ("bpgpu_ipp_free", None, [_VP]),
     ("bpgpu_ipp_verification_scalars", _INT, [_VP, _VP, _SZ, _c.POINTER(_VP)]),
     ("bpgpu_ipp_verify_msm", _INT, [_VP, _VP, _SZ, _VP, _SZ, _VP, _VP, _VP, _VP, _VP, _VP, _VP, _VP, _SZ, _VP]),
+    ("bpgpu_msm_parts", _INT, [_VP, _VP, _SZ, _VP]),
+    ("bpgpu_r1cs_prover_polys", _INT, [_VP, _SZ, _VP, _VP, _VP, _VP, _VP, _VP, _VP] + [_c.POINTER(_VP)] * 4),
+    ("bpgpu_r1cs_prover_eval", _INT, [_VP, _SZ, _SZ, _SZ] + [_VP] * 6 + [_VP, _VP, _VP] + [_c.POINTER(_VP)] * 4),
+    ("bpgpu_r1cs_verifier_scalars", _INT, [_VP, _SZ, _SZ, _SZ] + [_VP] * 4 + [_VP] * 5 + [_c.POINTER(_VP), _VP]),
     ("bpgpu_selftest_field", _INT, [_VP, _INT, _INT, _VP, _VP, _SZ, _VP]),
     ("bpgpu_selftest_group", _INT, [_VP, _INT, _VP, _VP, _VP, _SZ, _VP]),
     ("bpgpu_int_pipe_bench", _INT, [_VP, _INT, _INT, _c.POINTER(_c.c_double), _c.POINTER(_c.c_double)]),
 ]
+
+# include/bphost.h: the host layer (C++ mirror of the reference's prover / verifier API)
+_CS, _U64 = _c.c_char_p, _c.c_uint64
+SYMBOLS_HOST = [
+    ("bph_merlin_kat", _INT, [_CS, _CS, _VP, _SZ, _CS, _VP, _SZ]),
+    ("bph_transcript_kat", _INT, [_INT, _CS, _VP, _VP, _VP]),
+    ("bph_get_generators", _INT, [_VP, _CS, _SZ, _c.POINTER(_VP)]),
+    ("bph_g1_from_msg_hash", _INT, [_VP, _VP, _SZ, _VP]),
+    ("bph_ipp_create", _INT, [_VP, _CS, _VP, _VP, _VP, _VP, _VP, _VP, _VP, _SZ, _VP, _SZ, _c.POINTER(_SZ)]),
+    ("bph_ipp_verify", _INT, [_VP, _CS, _SZ, _VP, _VP, _VP, _VP, _VP, _VP, _VP, _SZ]),
+    ("bph_bound_check_prove", _INT, [_VP, _CS, _VP, _VP, _VP, _VP, _U64, _VP, _U64, _U64, _SZ, _INT, _U64, _VP, _SZ,
+                                     _c.POINTER(_SZ), _VP]),
+    ("bph_bound_check_verify", _INT, [_VP, _CS, _VP, _VP, _VP, _VP, _U64, _U64, _SZ, _VP, _SZ, _VP, _VP]),
+    ("bph_range_prove", _INT, [_VP, _CS, _VP, _VP, _VP, _VP, _VP, _SZ, _SZ, _INT, _U64, _VP, _SZ, _c.POINTER(_SZ), _VP]),
+    ("bph_range_verify", _INT, [_VP, _CS, _VP, _VP, _VP, _VP, _SZ, _SZ, _VP, _SZ, _VP, _VP]),
+]
+
+
+class MsmPart(ctypes.Structure):
+    """bpgpu_msm_part"""
+    _fields_ = [("points", _VP), ("points_off", _SZ), ("host_points_xy", _VP),
+                ("scalars", _VP), ("scalars_off", _SZ), ("host_scalars_be", _VP), ("n", _SZ)]
 
 
 class BpgpuError(RuntimeError):
@@ -91,7 +118,7 @@ def lib():
         if not os.path.exists(path):
             raise RuntimeError(f"{path} is missing: run __graft_entry__.build() (there is no CPU fallback)")
         L = ctypes.CDLL(path)
-        for name, res, args in SYMBOLS:
+        for name, res, args in SYMBOLS + SYMBOLS_HOST:
             fn = getattr(L, name)
             fn.restype = res
             fn.argtypes = args
@@ -203,6 +230,13 @@ class Context:
         self._check(lib().bpgpu_points_upload(self.handle, _buf(xy), n, ctypes.byref(h)), "points_upload")
         return DevicePoints(self, h)
 
+    def points_from_hashes(self, hashes, n=None):
+        """ECP::mapit on n SHAKE256 digests (MODBYTES each) -> device generator table."""
+        n = len(hashes) // self.modbytes if n is None else n
+        h = ctypes.c_void_p()
+        self._check(lib().bpgpu_points_from_hashes(self.handle, _buf(hashes), n, ctypes.byref(h)), "points_from_hashes")
+        return DevicePoints(self, h)
+
     def upload_scalars(self, be, n=None):
         n = len(be) // self.modbytes if n is None else n
         h = ctypes.c_void_p()
@@ -310,6 +344,123 @@ class Context:
         out = ctypes.create_string_buffer(2 * self.modbytes)
         self._check(lib().bpgpu_msm_refs(self.handle, _buf(points_xy), _buf(scalars_be), n, out), "msm_refs")
         return out.raw
+
+    def msm_parts(self, parts):
+        """parts: list of (points, scalars, n[, points_off, scalars_off]); points is DevicePoints or bytes (X||Y),
+        scalars is DeviceScalars or bytes (big endian)."""
+        arr = (MsmPart * len(parts))()
+        keep = []
+        for i, p in enumerate(parts):
+            pts, sc, n = p[0], p[1], p[2]
+            poff = p[3] if len(p) > 3 else 0
+            soff = p[4] if len(p) > 4 else 0
+            if isinstance(pts, DevicePoints):
+                arr[i].points, arr[i].points_off = pts.handle, poff
+            else:
+                buf = ctypes.create_string_buffer(bytes(pts), len(pts))
+                keep.append(buf)
+                arr[i].host_points_xy = ctypes.cast(buf, ctypes.c_void_p)
+            if isinstance(sc, DeviceScalars):
+                arr[i].scalars, arr[i].scalars_off = sc.handle, soff
+            else:
+                buf = ctypes.create_string_buffer(bytes(sc), len(sc))
+                keep.append(buf)
+                arr[i].host_scalars_be = ctypes.cast(buf, ctypes.c_void_p)
+            arr[i].n = n
+        out = ctypes.create_string_buffer(2 * self.modbytes)
+        self._check(lib().bpgpu_msm_parts(self.handle, arr, len(parts), out), "msm_parts")
+        return out.raw
+
+    # ---- fused R1CS Fr kernels
+    def r1cs_prover_polys(self, n, aL, aR, sR, wL, wR, wO, y_be):
+        hs = [ctypes.c_void_p() for _ in range(4)]
+        self._check(lib().bpgpu_r1cs_prover_polys(self.handle, n, aL.handle, aR.handle, sR.handle, wL.handle, wR.handle, wO.handle,
+                                                  _buf(y_be), *[ctypes.byref(h) for h in hs]), "r1cs_prover_polys")
+        return [DeviceScalars(self, h) for h in hs]
+
+    def r1cs_prover_eval(self, n, n1, N, l1, l2, l3, r0, r1, r3, x_be, u_be, y_be):
+        hs = [ctypes.c_void_p() for _ in range(4)]
+        self._check(lib().bpgpu_r1cs_prover_eval(self.handle, n, n1, N, l1.handle, l2.handle, l3.handle, r0.handle, r1.handle, r3.handle,
+                                                 _buf(x_be), _buf(u_be), _buf(y_be), *[ctypes.byref(h) for h in hs]), "r1cs_prover_eval")
+        return [DeviceScalars(self, h) for h in hs]
+
+    def r1cs_verifier_scalars(self, n, n1, N, wL, wR, wO, s, y_be, x_be, a_be, b_be, u_be):
+        h = ctypes.c_void_p()
+        delta = ctypes.create_string_buffer(self.modbytes)
+        self._check(lib().bpgpu_r1cs_verifier_scalars(self.handle, n, n1, N, wL.handle, wR.handle, wO.handle, s.handle, _buf(y_be),
+                                                      _buf(x_be), _buf(a_be), _buf(b_be), _buf(u_be), ctypes.byref(h), delta),
+                    "r1cs_verifier_scalars")
+        return DeviceScalars(self, h), delta.raw
+
+    # ---- host layer (include/bphost.h): the reference's API end to end
+    def get_generators(self, prefix, n):
+        """utils::get_generators(prefix, n) as a device table (utils/mod.rs:16-23)."""
+        h = ctypes.c_void_p()
+        self._check(lib().bph_get_generators(self.handle, prefix.encode(), n, ctypes.byref(h)), "get_generators")
+        return DevicePoints(self, h)
+
+    def g1_from_msg_hash(self, msg):
+        out = ctypes.create_string_buffer(2 * self.modbytes)
+        self._check(lib().bph_g1_from_msg_hash(self.handle, _buf(msg), len(msg), out), "g1_from_msg_hash")
+        return out.raw
+
+    def _proof_call(self, fn, what, *args_before, extra_after=()):
+        cap = 1 << 16
+        while True:
+            buf, ln = ctypes.create_string_buffer(cap), ctypes.c_size_t()
+            rc = fn(*args_before, buf, cap, ctypes.byref(ln), *extra_after)
+            if rc == -10 and ln.value > cap:
+                cap = ln.value
+                continue
+            self._check(rc, what)
+            return buf.raw[:ln.value]
+
+    def ipp_create(self, label, G, H, Q_xy, Gf_be, Hf_be, a_be, b_be, n):
+        """IPP::create_ipp with a fresh Transcript::new(label) -> L.. | R.. | a | b"""
+        return self._proof_call(lib().bph_ipp_create, "ipp_create", self.handle, label, G.handle, H.handle, _buf(Q_xy), _buf(Gf_be),
+                                _buf(Hf_be), _buf(a_be), _buf(b_be), n)
+
+    def ipp_verify(self, label, n, Gf_be, Hf_be, P_xy, Q_xy, G, H, proof):
+        """IPP::verify_ipp -> True / False (VerificationError); other errors raise."""
+        rc = lib().bph_ipp_verify(self.handle, label, n, _buf(Gf_be), _buf(Hf_be), _buf(P_xy), _buf(Q_xy), G.handle, H.handle,
+                                  _buf(proof), len(proof))
+        if rc == -4:
+            return False
+        self._check(rc, "ipp_verify")
+        return True
+
+    def bound_check_prove(self, label, g_xy, h_xy, G, H, val, lower, upper, bits, seed=None, randomness_be=None):
+        """gen_proof_of_bounded_num -> (proof bytes, 3 commitments X||Y).  seed=None: OS entropy."""
+        comms = ctypes.create_string_buffer(3 * 2 * self.modbytes)
+        rnd = _buf(randomness_be) if randomness_be is not None else None
+        proof = self._proof_call(lib().bph_bound_check_prove, "bound_check_prove", self.handle, label, _buf(g_xy), _buf(h_xy), G.handle,
+                                 H.handle, val, rnd, lower, upper, bits, 0 if seed is None else 1, seed or 0, extra_after=(comms,))
+        return proof, comms.raw
+
+    def bound_check_verify(self, label, g_xy, h_xy, G, H, lower, upper, bits, proof, comms, r_be=None):
+        rc = lib().bph_bound_check_verify(self.handle, label, _buf(g_xy), _buf(h_xy), G.handle, H.handle, lower, upper, bits, _buf(proof),
+                                          len(proof), _buf(comms), _buf(r_be) if r_be is not None else None)
+        if rc == -4:
+            return False
+        self._check(rc, "bound_check_verify")
+        return True
+
+    def range_prove(self, label, g_xy, h_xy, G, H, values, bits, seed=None):
+        """m x positive_no_gadget in one constraint system -> (proof bytes, m commitments X||Y)."""
+        m = len(values)
+        arr = (ctypes.c_uint64 * max(1, m))(*values)
+        comms = ctypes.create_string_buffer(max(1, m * 2 * self.modbytes))
+        proof = self._proof_call(lib().bph_range_prove, "range_prove", self.handle, label, _buf(g_xy), _buf(h_xy), G.handle, H.handle,
+                                 ctypes.cast(arr, ctypes.c_void_p), m, bits, 0 if seed is None else 1, seed or 0, extra_after=(comms,))
+        return proof, comms.raw[:m * 2 * self.modbytes]
+
+    def range_verify(self, label, g_xy, h_xy, G, H, m, bits, proof, comms, r_be=None):
+        rc = lib().bph_range_verify(self.handle, label, _buf(g_xy), _buf(h_xy), G.handle, H.handle, m, bits, _buf(proof), len(proof),
+                                    _buf(comms), _buf(r_be) if r_be is not None else None)
+        if rc == -4:
+            return False
+        self._check(rc, "range_verify")
+        return True
 
     # ---- self-test hooks
     def selftest_field(self, field, op, a, b):

@@ -212,6 +212,13 @@ static int scalars_upload_t(bpgpu_ctx* ctx, const uint8_t* be, size_t n, int mon
   return launch_check(ctx, "k_scalars_from_be");
 }
 
+template <class Curve>
+int scalars_from_host(bpgpu_ctx* ctx, const uint8_t* be, size_t n, int mont, void* dst) {
+  return scalars_upload_t<Curve>(ctx, be, n, mont, dst, ctx->io_dev2);
+}
+template int scalars_from_host<Bls>(bpgpu_ctx*, const uint8_t*, size_t, int, void*);
+template int scalars_from_host<Bn>(bpgpu_ctx*, const uint8_t*, size_t, int, void*);
+
 static int fetch_result(bpgpu_ctx* ctx, const void* d_src, size_t bytes, uint8_t* host_out) {
   BP_CUDA_OK(cudaMemcpyAsync(ctx->pinned, d_src, bytes, cudaMemcpyDeviceToHost, ctx->stream));
   BP_CUDA_OK(cudaStreamSynchronize(ctx->stream));
@@ -314,7 +321,7 @@ void bpgpu_ctx_destroy(bpgpu_ctx* c) {
   cudaStreamSynchronize(c->stream);
   c->msm_a.release(); c->msm_b.release(); c->msm_c.release(); c->msm_d.release(); c->msm_e.release();
   c->io_dev.release(); c->io_dev2.release();
-  c->ipp_pts.release(); c->ipp_scl.release();
+  c->ipp_pts.release(); c->ipp_scl.release(); c->parts_pts.release(); c->parts_scl.release();
   c->fr_tmp.release(); c->fr_out.release(); c->fr_args.release(); c->fr_pow.release(); c->fr_pow2.release();
   if (c->pinned) cudaFreeHost(c->pinned);
   cudaStreamDestroy(c->stream);

@@ -65,7 +65,7 @@ struct bpgpu_ctx {
   uint64_t launches = 0;
   // MSM scratch
   bp::Scratch msm_a, msm_b, msm_c, msm_d, msm_e, io_dev, io_dev2;
-  bp::Scratch fr_tmp, fr_out, fr_args, fr_pow, fr_pow2, ipp_pts, ipp_scl;
+  bp::Scratch fr_tmp, fr_out, fr_args, fr_pow, fr_pow2, ipp_pts, ipp_scl, parts_pts, parts_scl;
   uint8_t* pinned = nullptr;      // small pinned staging (results, challenges)
   size_t pinned_cap = 0;
   // per-stage CUDA-event timing of the MSM pipeline (bpgpu_ctx_set_profile)
@@ -151,6 +151,8 @@ struct MsmResult { int W; int c; int qshift; const void* d_winsum; };
 
 // host X||Y big-endian points -> device affine Montgomery (api.cu)
 template <class Curve> int points_from_host(bpgpu_ctx* ctx, const uint8_t* xy, size_t n, void* dst);
+// host big-endian scalars -> device Fr (Montgomery if mont) (api.cu)
+template <class Curve> int scalars_from_host(bpgpu_ctx* ctx, const uint8_t* be, size_t n, int mont, void* dst);
 // full MSM: device pipeline + host finish; d_scal = Fr[n] (Montgomery if mont) (api.cu)
 int msm_to_host(bpgpu_ctx* ctx, const void* d_pts, const void* d_scal, bool mont, size_t n, uint8_t* out_xy);
 // host scalars -> device Montgomery argument block in ctx->fr_args (frvec.cu)

@@ -1,0 +1,264 @@
+// C entry points of the host layer (include/bphost.h): flatten the C++ mirror of the reference's API to bytes.
+#include <stdio.h>
+
+#include <string>
+#include <vector>
+
+#include "../../include/bphost.h"
+#include "gadgets.hpp"
+
+using namespace bph;
+
+namespace {
+
+template <class C>
+std::vector<FieldElement<C>> scalars_from(const uint8_t* be, size_t n) {
+  std::vector<FieldElement<C>> v(n);
+  for (size_t i = 0; i < n; i++) v[i] = FieldElement<C>::from_bytes(be + i * C::MODBYTES);
+  return v;
+}
+
+int emit(const std::vector<uint8_t>& bytes, uint8_t* out, size_t cap, size_t* len) {
+  if (len) *len = bytes.size();
+  if (!out || cap < bytes.size()) return BPH_E_BUFFER;
+  memcpy(out, bytes.data(), bytes.size());
+  return BPGPU_OK;
+}
+
+template <class C>
+std::vector<uint8_t> ipp_to_bytes(const InnerProductArgumentProof<C>& p) {
+  std::vector<uint8_t> out;
+  for (const auto& q : p.L) { auto b = q.to_bytes(); out.insert(out.end(), b.begin(), b.end()); }
+  for (const auto& q : p.R) { auto b = q.to_bytes(); out.insert(out.end(), b.begin(), b.end()); }
+  append_fe(out, p.a);
+  append_fe(out, p.b);
+  return out;
+}
+
+template <class C>
+int ipp_from_bytes(const uint8_t* buf, size_t len, InnerProductArgumentProof<C>* p) {
+  const size_t PB = 1 + 2 * C::MODBYTES, SB = C::MODBYTES;
+  if (len < 2 * SB || (len - 2 * SB) % (2 * PB)) return BPGPU_E_FORMAT;
+  size_t lg = (len - 2 * SB) / (2 * PB);
+  p->L.resize(lg);
+  p->R.resize(lg);
+  size_t off = 0;
+  for (size_t k = 0; k < lg; k++, off += PB) { if (buf[off] != 4) return BPGPU_E_FORMAT; p->L[k] = G1<C>::from_xy(buf + off + 1); }
+  for (size_t k = 0; k < lg; k++, off += PB) { if (buf[off] != 4) return BPGPU_E_FORMAT; p->R[k] = G1<C>::from_xy(buf + off + 1); }
+  p->a = FieldElement<C>::from_bytes(buf + off);
+  p->b = FieldElement<C>::from_bytes(buf + off + SB);
+  return BPGPU_OK;
+}
+
+template <class C>
+Rng<C> make_rng(int mode, uint64_t seed) { return mode == 1 ? Rng<C>(seed, "blind") : Rng<C>(); }
+
+template <class C>
+FieldElement<C> verifier_scalar(const uint8_t* r_be) {
+  if (r_be) return FieldElement<C>::from_bytes(r_be);
+  Rng<C> os;
+  return os.next();
+}
+
+template <class C>
+int ipp_create_t(bpgpu_ctx* ctx, const char* label, const bpgpu_points* G, const bpgpu_points* H, const uint8_t* Q_xy, const uint8_t* Gf,
+                 const uint8_t* Hf, const uint8_t* a, const uint8_t* b, size_t n, uint8_t* proof, size_t cap, size_t* len) {
+  FieldElementVector<C> dGf, dHf, da, db;
+  int rc;
+  if ((rc = FieldElementVector<C>::from_bytes(ctx, Gf, n, &dGf)) || (rc = FieldElementVector<C>::from_bytes(ctx, Hf, n, &dHf)) ||
+      (rc = FieldElementVector<C>::from_bytes(ctx, a, n, &da)) || (rc = FieldElementVector<C>::from_bytes(ctx, b, n, &db)))
+    return rc;
+  G1Vector<C> vG = G1Vector<C>::borrow(ctx, G), vH = G1Vector<C>::borrow(ctx, H);
+  Transcript t{std::string(label)};
+  InnerProductArgumentProof<C> p;
+  if ((rc = IPP<C>::create_ipp(ctx, t, G1<C>::from_xy(Q_xy), dGf, dHf, vG, 0, vH, 0, da, db, n, &p))) return rc;
+  return emit(ipp_to_bytes(p), proof, cap, len);
+}
+
+template <class C>
+int ipp_verify_t(bpgpu_ctx* ctx, const char* label, size_t n, const uint8_t* Gf, const uint8_t* Hf, const uint8_t* P_xy, const uint8_t* Q_xy,
+                 const bpgpu_points* G, const bpgpu_points* H, const uint8_t* proof, size_t len) {
+  InnerProductArgumentProof<C> p;
+  int rc = ipp_from_bytes<C>(proof, len, &p);
+  if (rc) return rc;
+  FieldElementVector<C> dGf, dHf;
+  if ((rc = FieldElementVector<C>::from_bytes(ctx, Gf, n, &dGf)) || (rc = FieldElementVector<C>::from_bytes(ctx, Hf, n, &dHf))) return rc;
+  G1Vector<C> vG = G1Vector<C>::borrow(ctx, G), vH = G1Vector<C>::borrow(ctx, H);
+  if (vG.len() < n || vH.len() < n) return BPGPU_E_LEN;
+  Transcript t{std::string(label)};
+  return IPP<C>::verify_ipp(ctx, n, t, dGf, dHf, G1<C>::from_xy(P_xy), G1<C>::from_xy(Q_xy), vG, 0, vH, 0, p.a, p.b, p.L, p.R);
+}
+
+template <class C>
+int bound_prove_t(bpgpu_ctx* ctx, const char* label, const uint8_t* g_xy, const uint8_t* h_xy, const bpgpu_points* G, const bpgpu_points* H,
+                  uint64_t val, const uint8_t* randomness_be, uint64_t lower, uint64_t upper, size_t bits, int rng_mode, uint64_t seed,
+                  uint8_t* proof, size_t cap, size_t* len, uint8_t* comms_xy) {
+  if (val < lower || val > upper) return BPH_E_GADGET;
+  Rng<C> rng = make_rng<C>(rng_mode, seed);
+  FieldElement<C> rnd;
+  if (randomness_be) rnd = FieldElement<C>::from_bytes(randomness_be);
+  G1Vector<C> vG = G1Vector<C>::borrow(ctx, G), vH = G1Vector<C>::borrow(ctx, H);
+  R1CSProof<C> p;
+  std::vector<G1<C>> comms;
+  int rc = gen_proof_of_bounded_num<C>(ctx, val, randomness_be ? &rnd : nullptr, lower, upper, bits, rng, label, G1<C>::from_xy(g_xy),
+                                       G1<C>::from_xy(h_xy), vG, vH, &p, &comms);
+  if (rc) return rc;
+  for (size_t k = 0; k < comms.size(); k++) memcpy(comms_xy + k * 2 * C::MODBYTES, comms[k].xy, 2 * C::MODBYTES);
+  return emit(p.to_bytes(), proof, cap, len);
+}
+
+template <class C>
+int bound_verify_t(bpgpu_ctx* ctx, const char* label, const uint8_t* g_xy, const uint8_t* h_xy, const bpgpu_points* G, const bpgpu_points* H,
+                   uint64_t lower, uint64_t upper, size_t bits, const uint8_t* proof, size_t len, const uint8_t* comms_xy, const uint8_t* r_be) {
+  R1CSProof<C> p;
+  int rc = R1CSProof<C>::from_bytes(proof, len, &p);
+  if (rc) return rc;
+  std::vector<G1<C>> comms(3);
+  for (int k = 0; k < 3; k++) comms[k] = G1<C>::from_xy(comms_xy + k * 2 * C::MODBYTES);
+  G1Vector<C> vG = G1Vector<C>::borrow(ctx, G), vH = G1Vector<C>::borrow(ctx, H);
+  return verify_proof_of_bounded_num<C>(ctx, lower, upper, bits, p, comms, label, G1<C>::from_xy(g_xy), G1<C>::from_xy(h_xy), vG, vH,
+                                        verifier_scalar<C>(r_be));
+}
+
+template <class C>
+int range_prove_t(bpgpu_ctx* ctx, const char* label, const uint8_t* g_xy, const uint8_t* h_xy, const bpgpu_points* G, const bpgpu_points* H,
+                  const uint64_t* values, size_t m, size_t bits, int rng_mode, uint64_t seed, uint8_t* proof, size_t cap, size_t* len,
+                  uint8_t* comms_xy) {
+  Rng<C> rng = make_rng<C>(rng_mode, seed);
+  G1Vector<C> vG = G1Vector<C>::borrow(ctx, G), vH = G1Vector<C>::borrow(ctx, H);
+  R1CSProof<C> p;
+  std::vector<G1<C>> comms;
+  std::vector<uint64_t> vals(values, values + m);
+  int rc = gen_proof_of_positive_nums<C>(ctx, vals, bits, rng, label, G1<C>::from_xy(g_xy), G1<C>::from_xy(h_xy), vG, vH, &p, &comms);
+  if (rc) return rc;
+  for (size_t k = 0; k < comms.size(); k++) memcpy(comms_xy + k * 2 * C::MODBYTES, comms[k].xy, 2 * C::MODBYTES);
+  return emit(p.to_bytes(), proof, cap, len);
+}
+
+template <class C>
+int range_verify_t(bpgpu_ctx* ctx, const char* label, const uint8_t* g_xy, const uint8_t* h_xy, const bpgpu_points* G, const bpgpu_points* H,
+                   size_t m, size_t bits, const uint8_t* proof, size_t len, const uint8_t* comms_xy, const uint8_t* r_be) {
+  R1CSProof<C> p;
+  int rc = R1CSProof<C>::from_bytes(proof, len, &p);
+  if (rc) return rc;
+  std::vector<G1<C>> comms(m);
+  for (size_t k = 0; k < m; k++) comms[k] = G1<C>::from_xy(comms_xy + k * 2 * C::MODBYTES);
+  G1Vector<C> vG = G1Vector<C>::borrow(ctx, G), vH = G1Vector<C>::borrow(ctx, H);
+  return verify_proof_of_positive_nums<C>(ctx, bits, p, comms, label, G1<C>::from_xy(g_xy), G1<C>::from_xy(h_xy), vG, vH, verifier_scalar<C>(r_be));
+}
+
+// hash_msg: SHAKE256(msg) squeezed to MODBYTES (G1::from_msg_hash / FieldElement::from_msg_hash)
+void hash_msg(const uint8_t* msg, size_t len, int modbytes, uint8_t* out) { shake256(msg, len, out, modbytes); }
+
+}  // namespace
+
+#define BY_CURVE(ctx, CALL) (bpgpu_ctx_curve(ctx) == BPGPU_BLS12_381 ? CALL(Bls381) : CALL(Bn254))
+
+extern "C" {
+
+int bph_merlin_kat(const char* label, const char* msg_label, const uint8_t* msg, size_t msg_len, const char* ch_label, uint8_t* out,
+                   size_t out_len) {
+  if (!label || !msg_label || !ch_label || !out) return BPGPU_E_ARG;
+  Transcript t{std::string(label)};
+  t.append_message(msg_label, msg, msg_len);
+  t.challenge_bytes(ch_label, out, out_len);
+  return BPGPU_OK;
+}
+
+int bph_transcript_kat(int curve, const char* label, const uint8_t* point_xy, const uint8_t* scalar_be, uint8_t* challenge_be) {
+  if (!label || !point_xy || !scalar_be || !challenge_be) return BPGPU_E_ARG;
+  Transcript t{std::string(label)};
+  if (curve == BPGPU_BLS12_381) {
+    using C = Bls381;
+    t.innerproduct_domain_sep(8);
+    TranscriptProtocol<C>::commit_point(t, "P", G1<C>::from_xy(point_xy));
+    TranscriptProtocol<C>::commit_scalar(t, "s", FieldElement<C>::from_bytes(scalar_be));
+    TranscriptProtocol<C>::challenge_scalar(t, "c").to_bytes(challenge_be);
+  } else if (curve == BPGPU_BN254) {
+    using C = Bn254;
+    t.innerproduct_domain_sep(8);
+    TranscriptProtocol<C>::commit_point(t, "P", G1<C>::from_xy(point_xy));
+    TranscriptProtocol<C>::commit_scalar(t, "s", FieldElement<C>::from_bytes(scalar_be));
+    TranscriptProtocol<C>::challenge_scalar(t, "c").to_bytes(challenge_be);
+  } else {
+    return BPGPU_E_ARG;
+  }
+  return BPGPU_OK;
+}
+
+int bph_get_generators(bpgpu_ctx* ctx, const char* prefix, size_t n, bpgpu_points** out) {
+  if (!ctx || !prefix || !out) return BPGPU_E_ARG;
+  const int mb = bpgpu_modbytes(bpgpu_ctx_curve(ctx));
+  std::vector<uint8_t> hashes(n * mb + 1);
+  for (size_t i = 1; i <= n; i++) {                       // utils/mod.rs:18-21: prefix || i.to_string()
+    std::string s = std::string(prefix) + std::to_string(i);
+    hash_msg((const uint8_t*)s.data(), s.size(), mb, hashes.data() + (i - 1) * mb);
+  }
+  return bpgpu_points_from_hashes(ctx, hashes.data(), n, out);
+}
+
+int bph_g1_from_msg_hash(bpgpu_ctx* ctx, const uint8_t* msg, size_t msg_len, uint8_t* out_xy) {
+  if (!ctx || (!msg && msg_len) || !out_xy) return BPGPU_E_ARG;
+  const int mb = bpgpu_modbytes(bpgpu_ctx_curve(ctx));
+  uint8_t h[48];
+  hash_msg(msg, msg_len, mb, h);
+  bpgpu_points* p = nullptr;
+  int rc = bpgpu_points_from_hashes(ctx, h, 1, &p);
+  if (rc) return rc;
+  rc = bpgpu_points_download(ctx, p, 0, 1, out_xy);
+  bpgpu_points_free(p);
+  return rc;
+}
+
+int bph_ipp_create(bpgpu_ctx* ctx, const char* label, const bpgpu_points* G, const bpgpu_points* H, const uint8_t* Q_xy, const uint8_t* Gf,
+                   const uint8_t* Hf, const uint8_t* a, const uint8_t* b, size_t n, uint8_t* proof, size_t cap, size_t* len) {
+  if (!ctx || !label || !G || !H || !Q_xy || !Gf || !Hf || !a || !b) return BPGPU_E_ARG;
+#define CALL(C) ipp_create_t<C>(ctx, label, G, H, Q_xy, Gf, Hf, a, b, n, proof, cap, len)
+  return BY_CURVE(ctx, CALL);
+#undef CALL
+}
+
+int bph_ipp_verify(bpgpu_ctx* ctx, const char* label, size_t n, const uint8_t* Gf, const uint8_t* Hf, const uint8_t* P_xy, const uint8_t* Q_xy,
+                   const bpgpu_points* G, const bpgpu_points* H, const uint8_t* proof, size_t len) {
+  if (!ctx || !label || !G || !H || !P_xy || !Q_xy || !Gf || !Hf || !proof) return BPGPU_E_ARG;
+#define CALL(C) ipp_verify_t<C>(ctx, label, n, Gf, Hf, P_xy, Q_xy, G, H, proof, len)
+  return BY_CURVE(ctx, CALL);
+#undef CALL
+}
+
+int bph_bound_check_prove(bpgpu_ctx* ctx, const char* label, const uint8_t* g_xy, const uint8_t* h_xy, const bpgpu_points* G,
+                          const bpgpu_points* H, uint64_t val, const uint8_t* randomness_be, uint64_t lower, uint64_t upper, size_t bits,
+                          int rng_mode, uint64_t seed, uint8_t* proof, size_t cap, size_t* len, uint8_t* comms_xy) {
+  if (!ctx || !label || !g_xy || !h_xy || !G || !H || !comms_xy) return BPGPU_E_ARG;
+#define CALL(C) bound_prove_t<C>(ctx, label, g_xy, h_xy, G, H, val, randomness_be, lower, upper, bits, rng_mode, seed, proof, cap, len, comms_xy)
+  return BY_CURVE(ctx, CALL);
+#undef CALL
+}
+
+int bph_bound_check_verify(bpgpu_ctx* ctx, const char* label, const uint8_t* g_xy, const uint8_t* h_xy, const bpgpu_points* G,
+                           const bpgpu_points* H, uint64_t lower, uint64_t upper, size_t bits, const uint8_t* proof, size_t len,
+                           const uint8_t* comms_xy, const uint8_t* r_be) {
+  if (!ctx || !label || !g_xy || !h_xy || !G || !H || !proof || !comms_xy) return BPGPU_E_ARG;
+#define CALL(C) bound_verify_t<C>(ctx, label, g_xy, h_xy, G, H, lower, upper, bits, proof, len, comms_xy, r_be)
+  return BY_CURVE(ctx, CALL);
+#undef CALL
+}
+
+int bph_range_prove(bpgpu_ctx* ctx, const char* label, const uint8_t* g_xy, const uint8_t* h_xy, const bpgpu_points* G, const bpgpu_points* H,
+                    const uint64_t* values, size_t m, size_t bits, int rng_mode, uint64_t seed, uint8_t* proof, size_t cap, size_t* len,
+                    uint8_t* comms_xy) {
+  if (!ctx || !label || !g_xy || !h_xy || !G || !H || (!values && m) || !comms_xy || bits > 64) return BPGPU_E_ARG;
+#define CALL(C) range_prove_t<C>(ctx, label, g_xy, h_xy, G, H, values, m, bits, rng_mode, seed, proof, cap, len, comms_xy)
+  return BY_CURVE(ctx, CALL);
+#undef CALL
+}
+
+int bph_range_verify(bpgpu_ctx* ctx, const char* label, const uint8_t* g_xy, const uint8_t* h_xy, const bpgpu_points* G, const bpgpu_points* H,
+                     size_t m, size_t bits, const uint8_t* proof, size_t len, const uint8_t* comms_xy, const uint8_t* r_be) {
+  if (!ctx || !label || !g_xy || !h_xy || !G || !H || !proof || (!comms_xy && m)) return BPGPU_E_ARG;
+#define CALL(C) range_verify_t<C>(ctx, label, g_xy, h_xy, G, H, m, bits, proof, len, comms_xy, r_be)
+  return BY_CURVE(ctx, CALL);
+#undef CALL
+}
+
+}  // extern "C"

@@ -1,0 +1,155 @@
+// The range gadgets that drive the benchmark configurations, mirrored from
+// /root/reference/src/r1cs/gadgets/helper_constraints/positive_no.rs:8-40, helper_constraints/mod.rs:16-22 and
+// src/r1cs/gadgets/bound_check.rs:13-178.  Written against the abstract ConstraintSystem, so the same code
+// builds the prover's and the verifier's circuit, as in the reference.
+#pragma once
+#include "r1cs.hpp"
+
+namespace bph {
+
+template <class C>
+inline bool fe_bit(const FieldElement<C>& q, size_t i) {       // q.shift_right(i).is_odd()
+  uint8_t be[C::MODBYTES];
+  q.to_bytes(be);
+  if (i >= 8 * (size_t)C::MODBYTES) return false;
+  return (be[C::MODBYTES - 1 - i / 8] >> (i % 8)) & 1;
+}
+
+// positive_no.rs:8-40 -- v in [0, 2^n)
+template <class C>
+int positive_no_gadget(ConstraintSystem<C>& cs, const AllocatedQuantity<C>& v, size_t n) {
+  using FE = FieldElement<C>;
+  using LC = LinearCombination<C>;
+  std::vector<std::pair<Variable, FE>> constraint_v = {{v.variable, FE::minus_one()}};
+  FE exp_2 = FE::one();
+  const FE zero = FE::zero(), one = FE::one();
+  for (size_t i = 0; i < n; i++) {
+    Variable a, b, o;
+    int rc;
+    if (v.has_assignment) {
+      bool odd = fe_bit(v.assignment, i);                        // :18-24: (left, right) = (1 - bit, bit)
+      rc = cs.allocate_multiplier(odd ? &zero : &one, odd ? &one : &zero, &a, &b, &o);
+    } else {
+      rc = cs.allocate_multiplier(nullptr, nullptr, &a, &b, &o);
+    }
+    if (rc) return rc;
+    cs.constrain(LC(o));                                         // :27   a * b = 0
+    cs.constrain(LC(a) + (LC(b) - LC(one)));                     // :30   a = 1 - b
+    constraint_v.emplace_back(b, exp_2);
+    exp_2 = exp_2 + exp_2;
+  }
+  cs.constrain(LC(constraint_v));                                // :37   sum b_i 2^i = v
+  return OK;
+}
+
+template <class C>
+void constrain_lc_with_scalar(ConstraintSystem<C>& cs, const LinearCombination<C>& lc, const FieldElement<C>& scalar) {   // helper_constraints/mod.rs:16-22
+  cs.constrain(lc - LinearCombination<C>(scalar));
+}
+
+// bound_check.rs:13-39 -- v in [min, max] via a = v - min, b = max - v, both n-bit
+template <class C>
+int bound_check_gadget(ConstraintSystem<C>& cs, const AllocatedQuantity<C>& v, const AllocatedQuantity<C>& a, const AllocatedQuantity<C>& b,
+                       uint64_t max, uint64_t min, size_t n) {
+  using FE = FieldElement<C>;
+  using LC = LinearCombination<C>;
+  cs.constrain(LC(v.variable) - LC(FE::from_u64(min)) - LC(a.variable));       // :26
+  cs.constrain(LC(FE::from_u64(max)) - LC(v.variable) - LC(b.variable));       // :28
+  constrain_lc_with_scalar<C>(cs, LC(a.variable) + LC(b.variable), FE::from_u64(max - min));   // :31
+  int rc = positive_no_gadget<C>(cs, a, n);                                     // :34
+  if (rc) return rc;
+  return positive_no_gadget<C>(cs, b, n);                                       // :36
+}
+
+// bound_check.rs:41-92.  `randomness` = blinding of the commitment to val (None -> drawn from rng);
+// the blindings of a and b are FieldElement::random() in the reference, here the next two draws of `rng`.
+template <class C>
+int prove_bounded_num(uint64_t val, const FieldElement<C>* randomness, uint64_t lower, uint64_t upper, size_t max_bits_in_val, Rng<C>& rng,
+                      Prover<C>& prover, std::vector<G1<C>>* comms) {
+  using FE = FieldElement<C>;
+  const uint64_t a = val - lower, b = upper - val;
+  comms->clear();
+  const FE vals[3] = {FE::from_u64(val), FE::from_u64(a), FE::from_u64(b)};
+  AllocatedQuantity<C> q[3];
+  for (int k = 0; k < 3; k++) {
+    FE blind = (k == 0 && randomness) ? *randomness : rng.next();
+    G1<C> com;
+    Variable var;
+    int rc = prover.commit(vals[k], blind, &com, &var);
+    if (rc) return rc;
+    q[k] = {var, true, vals[k]};
+    comms->push_back(com);
+  }
+  return bound_check_gadget<C>(prover, q[0], q[1], q[2], upper, lower, max_bits_in_val);
+}
+
+// bound_check.rs:94-129
+template <class C>
+int verify_bounded_num(uint64_t lower, uint64_t upper, size_t max_bits_in_val, const std::vector<G1<C>>& commitments, Verifier<C>& verifier) {
+  if (commitments.size() < 3) return E_FORMAT;
+  AllocatedQuantity<C> q[3];
+  for (int k = 0; k < 3; k++) q[k] = {verifier.commit(commitments[k]), false, FieldElement<C>::zero()};
+  return bound_check_gadget<C>(verifier, q[0], q[1], q[2], upper, lower, max_bits_in_val);
+}
+
+// bound_check.rs:133-161
+template <class C>
+int gen_proof_of_bounded_num(bpgpu_ctx* ctx, uint64_t val, const FieldElement<C>* randomness, uint64_t lower, uint64_t upper,
+                             size_t max_bits_in_val, Rng<C>& rng, const std::string& transcript_label, const G1<C>& g, const G1<C>& h,
+                             const G1Vector<C>& G, const G1Vector<C>& H, R1CSProof<C>* proof, std::vector<G1<C>>* comms) {
+  Transcript prover_transcript(transcript_label);
+  Prover<C> prover(ctx, g, h, prover_transcript, rng);
+  int rc = prove_bounded_num<C>(val, randomness, lower, upper, max_bits_in_val, rng, prover, comms);
+  if (rc) return rc;
+  return prover.prove(G, H, proof);
+}
+
+// bound_check.rs:163-178
+template <class C>
+int verify_proof_of_bounded_num(bpgpu_ctx* ctx, uint64_t lower, uint64_t upper, size_t max_bits_in_val, const R1CSProof<C>& proof,
+                                const std::vector<G1<C>>& commitments, const std::string& transcript_label, const G1<C>& g, const G1<C>& h,
+                                const G1Vector<C>& G, const G1Vector<C>& H, const FieldElement<C>& verifier_r) {
+  Transcript verifier_transcript(transcript_label);
+  Verifier<C> verifier(ctx, verifier_transcript);
+  int rc = verify_bounded_num<C>(lower, upper, max_bits_in_val, commitments, verifier);
+  if (rc) return rc;
+  return verifier.verify(proof, g, h, G, H, verifier_r);
+}
+
+// Aggregated range statement used by the benchmark configurations (BASELINE.json configs 2, 3, 5): m committed
+// values, each constrained to [0, 2^bits) by one positive_no_gadget -> n = m * bits multipliers.
+template <class C>
+int gen_proof_of_positive_nums(bpgpu_ctx* ctx, const std::vector<uint64_t>& vals, size_t bits, Rng<C>& rng, const std::string& transcript_label,
+                               const G1<C>& g, const G1<C>& h, const G1Vector<C>& G, const G1Vector<C>& H, R1CSProof<C>* proof,
+                               std::vector<G1<C>>* comms) {
+  using FE = FieldElement<C>;
+  Transcript prover_transcript(transcript_label);
+  Prover<C> prover(ctx, g, h, prover_transcript, rng);
+  comms->clear();
+  for (uint64_t v : vals) {
+    G1<C> com;
+    Variable var;
+    FE fv = FE::from_u64(v);
+    int rc = prover.commit(fv, rng.next(), &com, &var);
+    if (rc) return rc;
+    comms->push_back(com);
+    if ((rc = positive_no_gadget<C>(prover, AllocatedQuantity<C>{var, true, fv}, bits))) return rc;
+  }
+  return prover.prove(G, H, proof);
+}
+
+template <class C>
+int verify_proof_of_positive_nums(bpgpu_ctx* ctx, size_t bits, const R1CSProof<C>& proof, const std::vector<G1<C>>& commitments,
+                                  const std::string& transcript_label, const G1<C>& g, const G1<C>& h, const G1Vector<C>& G,
+                                  const G1Vector<C>& H, const FieldElement<C>& verifier_r) {
+  Transcript verifier_transcript(transcript_label);
+  Verifier<C> verifier(ctx, verifier_transcript);
+  for (const auto& com : commitments) {
+    Variable var = verifier.commit(com);
+    int rc = positive_no_gadget<C>(verifier, AllocatedQuantity<C>{var, false, FieldElement<C>::zero()}, bits);
+    if (rc) return rc;
+  }
+  return verifier.verify(proof, g, h, G, H, verifier_r);
+}
+
+}  // namespace bph

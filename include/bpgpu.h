@@ -71,6 +71,10 @@ void bpgpu_host_free(void* p);
 /* ---- G1Vector / FieldElementVector residency (G1Vector::from / FieldElementVector::from) ---- */
 int bpgpu_points_upload(bpgpu_ctx* ctx, const uint8_t* xy, size_t n, bpgpu_points** out);
 int bpgpu_points_download(bpgpu_ctx* ctx, const bpgpu_points* p, size_t off, size_t n, uint8_t* xy);
+/* G1Vector of hash-derived generators: out[i] = ECP::mapit(hashes[i]) where hashes[i] = SHAKE256(msg_i)[..MODBYTES] is
+ * computed by the caller (G1::from_msg_hash = hash_msg + mapit; utils/mod.rs:16-23 get_generators builds every
+ * generator table this way).  Try-and-increment, square root, even-y choice and cofactor clearing run on the device. */
+int bpgpu_points_from_hashes(bpgpu_ctx* ctx, const uint8_t* hashes, size_t n, bpgpu_points** out);
 size_t bpgpu_points_len(const bpgpu_points* p);
 void bpgpu_points_free(bpgpu_points* p);
 int bpgpu_scalars_upload(bpgpu_ctx* ctx, const uint8_t* be, size_t n, bpgpu_scalars** out);
@@ -92,6 +96,18 @@ int bpgpu_msm_device(bpgpu_ctx* ctx, const bpgpu_points* p, size_t poff, size_t 
 /* ad-hoc host point and scalar lists (`Vec<&G1>`, `Vec<&FieldElement>`) */
 int bpgpu_msm_refs(bpgpu_ctx* ctx, const uint8_t* points_xy, const uint8_t* scalars_be, size_t n,
                    uint8_t* out_xy);
+/* one MSM over the concatenation of several sources.  Each part takes its n points either from a
+ * device table (points != NULL, starting at points_off) or from host bytes (host_points_xy), and its n
+ * scalars either from a device vector (scalars != NULL) or from host bytes (host_scalars_be).  This is
+ * how the reference's `arg2`/`arg1` reference lists are assembled (verifier.rs:394-449: proof points and
+ * host scalars around the big G, H tables) and how commit_to_field_element_vectors(G, H, h, a, b, c)
+ * (prover.rs:347-362) maps onto cached generator tables. */
+typedef struct bpgpu_msm_part {
+  const bpgpu_points* points;   size_t points_off;   const uint8_t* host_points_xy;
+  const bpgpu_scalars* scalars; size_t scalars_off;  const uint8_t* host_scalars_be;
+  size_t n;
+} bpgpu_msm_part;
+int bpgpu_msm_parts(bpgpu_ctx* ctx, const bpgpu_msm_part* parts, size_t nparts, uint8_t* out_xy);
 /* window width the MSM would use for n terms (reporting only) */
 int bpgpu_msm_window_bits(size_t n);
 
@@ -145,6 +161,27 @@ int bpgpu_ipp_verify_msm(bpgpu_ctx* ctx, const bpgpu_points* G, size_t goff, con
                          const uint8_t* Q_xy, const bpgpu_scalars* G_factors, const bpgpu_scalars* H_factors,
                          const uint8_t* a_be, const uint8_t* b_be, const uint8_t* u_be, const uint8_t* L_xy,
                          const uint8_t* R_xy, size_t lg, uint8_t* out_xy);
+
+/* ---- fused Fr kernels of the R1CS prover / verifier ------------------------------------------------
+ * prover_polys (prover.rs:469-486): from a_L, a_R, s_R and the flattened weights wL, wR, wO (length n) and
+ *   the challenge y: l1 = a_L + y^-i*wR, r0 = wO - y^i, r1 = y^i*a_R + wL, r3 = y^i*s_R (l2 = a_O, l3 = s_L).
+ * prover_eval (prover.rs:524-535,552-563): l_vec = l(x) | 0^pad, r_vec = r(x) | (-y^i)_{i>=n},
+ *   G_factors = 1^n1 | u^(N-n1), H_factors = y^-i * G_factors, all of length padded_n, ready for bpgpu_ipp_begin.
+ * verifier_scalars (verifier.rs:341-390): g_scalars | h_scalars (2*padded_n) and delta from wL, wR, wO (length n),
+ *   the s vector (bpgpu_ipp_verification_scalars) and the challenges / proof scalars y, x, a, b, u. */
+int bpgpu_r1cs_prover_polys(bpgpu_ctx* ctx, size_t n, const bpgpu_scalars* a_L, const bpgpu_scalars* a_R,
+                            const bpgpu_scalars* s_R, const bpgpu_scalars* wL, const bpgpu_scalars* wR,
+                            const bpgpu_scalars* wO, const uint8_t* y_be, bpgpu_scalars** l1, bpgpu_scalars** r0,
+                            bpgpu_scalars** r1, bpgpu_scalars** r3);
+int bpgpu_r1cs_prover_eval(bpgpu_ctx* ctx, size_t n, size_t n1, size_t padded_n, const bpgpu_scalars* l1,
+                           const bpgpu_scalars* l2, const bpgpu_scalars* l3, const bpgpu_scalars* r0,
+                           const bpgpu_scalars* r1, const bpgpu_scalars* r3, const uint8_t* x_be, const uint8_t* u_be,
+                           const uint8_t* y_be, bpgpu_scalars** l_vec, bpgpu_scalars** r_vec,
+                           bpgpu_scalars** G_factors, bpgpu_scalars** H_factors);
+int bpgpu_r1cs_verifier_scalars(bpgpu_ctx* ctx, size_t n, size_t n1, size_t padded_n, const bpgpu_scalars* wL,
+                                const bpgpu_scalars* wR, const bpgpu_scalars* wO, const bpgpu_scalars* s,
+                                const uint8_t* y_be, const uint8_t* x_be, const uint8_t* a_be, const uint8_t* b_be,
+                                const uint8_t* u_be, bpgpu_scalars** gh_scalars, uint8_t* delta_be);
 
 /* ---- self-test / measurement hooks (used by tests/ and bench.py; not part of the drop-in) ---- */
 /* field: 0 Fq, 1 Fr of the ctx curve; op: 0 mul 1 add 2 sub 3 inv 4 sqr; operands are canonical

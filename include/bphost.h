@@ -1,0 +1,76 @@
+/* bphost.h — C entry points of the HOST layer of libbpgpu: the C++ mirror of lovesh/bulletproofs-amcl's
+ * prover / verifier API (the headers under bulletproofs-amcl_b200/host) flattened to plain bytes, so that it can be driven
+ * from C, Python (ctypes) or a Rust test harness.  Paths below are relative to /root/reference/src.
+ *
+ * The Rust crate keeps its own host side (Merlin transcript, constraint bookkeeping) and binds include/bpgpu.h
+ * directly; these entry points exist because no Rust toolchain is available where this library
+ * is built and tested: they run the reference's host logic restated in C++ above the same device ABI, so that the
+ * reference's own tests (ipp.rs:318-490, bound_check.rs:188-225) can be replayed end to end.
+ *
+ * Conventions: as include/bpgpu.h (scalars MODBYTES big endian, points X||Y).  A serialised IPP proof is
+ *   L_1..L_lg | R_1..R_lg  (G1::to_bytes(): 0x04||X||Y each)  |  a | b  (FieldElement::to_bytes()).
+ * A serialised R1CS proof is  A_I1 A_O1 S1 A_I2 A_O2 S2 T_1 T_3 T_4 T_5 T_6 | t_x t_x_blinding e_blinding | IPP proof
+ * (proof.rs:26-58 field order).  Return values: BPGPU_OK, or a negative BPGPU_E_* / BPH_E_* code.
+ *
+ * Randomness: the reference draws blindings from OS entropy (FieldElement::random()).  Every prover entry point
+ * takes (rng_mode, seed): mode 0 = OS entropy, mode 1 = the deterministic stream
+ * SHAKE256(seed_le64 || "blind" || i_le64) mod r consumed in the reference's draw order, which is what
+ * the parity tests use.  The verifier's batching scalar (verifier.rs:392) is an explicit argument (NULL = OS entropy).
+ */
+#ifndef BPHOST_H
+#define BPHOST_H
+
+#include "bpgpu.h"
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+#define BPH_E_MISSING_ASSIGNMENT (-8) /* R1CSError::MissingAssignment */
+#define BPH_E_GADGET (-9)             /* R1CSError::GadgetError */
+#define BPH_E_BUFFER (-10)            /* output buffer too small; *len holds the required size */
+
+/* merlin::Transcript known-answer hook: new(label); append_message(msg_label, msg); challenge_bytes(ch_label, out_len) */
+int bph_merlin_kat(const char* label, const char* msg_label, const uint8_t* msg, size_t msg_len, const char* ch_label,
+                   uint8_t* out, size_t out_len);
+/* TranscriptProtocol::challenge_scalar after commit_point / commit_scalar (transcript.rs:47-60) on the ctx curve */
+int bph_transcript_kat(int curve, const char* label, const uint8_t* point_xy, const uint8_t* scalar_be, uint8_t* challenge_be);
+
+/* utils/mod.rs:16-23 get_generators(prefix, n): G_i = G1::from_msg_hash(prefix || decimal(i)), i = 1..n, as a
+ * device-resident table.  SHAKE256 runs on the host, try-and-increment + sqrt + cofactor clearing on the device. */
+int bph_get_generators(bpgpu_ctx* ctx, const char* prefix, size_t n, bpgpu_points** out);
+/* G1::from_msg_hash(msg) */
+int bph_g1_from_msg_hash(bpgpu_ctx* ctx, const uint8_t* msg, size_t msg_len, uint8_t* out_xy);
+
+/* IPP::create_ipp (ipp.rs:35-202) with a fresh Transcript::new(transcript_label) */
+int bph_ipp_create(bpgpu_ctx* ctx, const char* transcript_label, const bpgpu_points* G, const bpgpu_points* H, const uint8_t* Q_xy,
+                   const uint8_t* G_factors_be, const uint8_t* H_factors_be, const uint8_t* a_be, const uint8_t* b_be, size_t n,
+                   uint8_t* proof, size_t cap, size_t* len);
+/* IPP::verify_ipp (ipp.rs:204-260): BPGPU_OK or BPGPU_E_VERIFY */
+int bph_ipp_verify(bpgpu_ctx* ctx, const char* transcript_label, size_t n, const uint8_t* G_factors_be, const uint8_t* H_factors_be,
+                   const uint8_t* P_xy, const uint8_t* Q_xy, const bpgpu_points* G, const bpgpu_points* H, const uint8_t* proof,
+                   size_t len);
+
+/* gen_proof_of_bounded_num / verify_proof_of_bounded_num (gadgets/bound_check.rs:133-178).
+ * randomness_be: blinding of the commitment to val (NULL = drawn from the rng).  comms_xy receives 3 points. */
+int bph_bound_check_prove(bpgpu_ctx* ctx, const char* transcript_label, const uint8_t* g_xy, const uint8_t* h_xy, const bpgpu_points* G,
+                          const bpgpu_points* H, uint64_t val, const uint8_t* randomness_be, uint64_t lower, uint64_t upper,
+                          size_t max_bits_in_val, int rng_mode, uint64_t seed, uint8_t* proof, size_t cap, size_t* len,
+                          uint8_t* comms_xy);
+int bph_bound_check_verify(bpgpu_ctx* ctx, const char* transcript_label, const uint8_t* g_xy, const uint8_t* h_xy, const bpgpu_points* G,
+                           const bpgpu_points* H, uint64_t lower, uint64_t upper, size_t max_bits_in_val, const uint8_t* proof,
+                           size_t len, const uint8_t* comms_xy, const uint8_t* verifier_r_be);
+
+/* m values, each proven in [0, 2^bits) with positive_no_gadget (helper_constraints/positive_no.rs:8-40) in ONE
+ * constraint system: n = m*bits multipliers (BASELINE.json configs 2, 3, 5).  comms_xy receives m points. */
+int bph_range_prove(bpgpu_ctx* ctx, const char* transcript_label, const uint8_t* g_xy, const uint8_t* h_xy, const bpgpu_points* G,
+                    const bpgpu_points* H, const uint64_t* values, size_t m, size_t bits, int rng_mode, uint64_t seed, uint8_t* proof,
+                    size_t cap, size_t* len, uint8_t* comms_xy);
+int bph_range_verify(bpgpu_ctx* ctx, const char* transcript_label, const uint8_t* g_xy, const uint8_t* h_xy, const bpgpu_points* G,
+                     const bpgpu_points* H, size_t m, size_t bits, const uint8_t* proof, size_t len, const uint8_t* comms_xy,
+                     const uint8_t* verifier_r_be);
+
+#ifdef __cplusplus
+}
+#endif
+#endif /* BPHOST_H */

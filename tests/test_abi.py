@@ -9,9 +9,12 @@ ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
 
 
 def _declared_symbols():
-    src = open(os.path.join(ROOT, "include", "bpgpu.h")).read()
-    src = re.sub(r"/\*.*?\*/", "", src, flags=re.S)
-    return sorted(set(re.findall(r"\b(bpgpu_[a-z0-9_]+)\s*\(", src)))
+    names = set()
+    for hdr, prefix in (("bpgpu.h", "bpgpu_"), ("bphost.h", "bph_")):
+        src = open(os.path.join(ROOT, "include", hdr)).read()
+        src = re.sub(r"/\*.*?\*/", "", src, flags=re.S)
+        names |= set(re.findall(r"\b(" + prefix + r"[A-Za-z0-9_]+)\s*\(", src))
+    return sorted(names)
 
 
 def test_library_exports_every_declared_symbol(bp):
@@ -23,7 +26,7 @@ def test_library_exports_every_declared_symbol(bp):
     for n in names:
         assert hasattr(lib, n), n
     from bulletproofs_amcl_b200 import binding
-    assert sorted(s[0] for s in binding.SYMBOLS) == names
+    assert sorted(s[0] for s in binding.SYMBOLS + binding.SYMBOLS_HOST) == names
 
 
 def test_constants_without_gpu(bp):

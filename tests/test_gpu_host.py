@@ -1,0 +1,160 @@
+"""GPU parity of the host layer (include/bphost.h): the reference's own tests replayed end to end through the
+C++ mirror of its API -- ipp.rs:318-490 (test_ipp, test_ipp_non_power_of_2), gadgets/bound_check.rs:188-225
+(test_bound_check_gadget) -- and compared BYTE FOR BYTE with the oracle's restatement on the same seeds."""
+import pytest
+
+from oracle import ipp as oipp
+from oracle import r1cs as or1cs
+from oracle.merlin import Transcript
+from tests.util import curve_of, enc_points, enc_scalars
+
+pytestmark = pytest.mark.gpu
+
+
+def ipp_bytes(C, pr):
+    return (b"".join(C.g1_to_bytes(p) for p in pr.L) + b"".join(C.g1_to_bytes(p) for p in pr.R)
+            + C.fr_to_bytes(pr.a) + C.fr_to_bytes(pr.b))
+
+
+@pytest.mark.parametrize("which", ["bls", "bn"])
+def test_get_generators_matches_oracle(which, ctx_bls, ctx_bn):
+    """utils::get_generators / G1::from_msg_hash: hash on the host, map-to-curve on the device."""
+    ctx = ctx_bls if which == "bls" else ctx_bn
+    C = curve_of(ctx)
+    for prefix, n in (("G", 40), ("h", 3), ("g", 0)):
+        t = ctx.get_generators(prefix, n)
+        assert t.download() == enc_points(C, C.get_generators(prefix, n))
+        t.free()
+    for msg in (b"g", b"h", b"Q", b"", b"a longer message that still hashes to one point"):
+        assert ctx.g1_from_msg_hash(msg) == C.g1_xy_bytes(C.g1_from_msg_hash(msg))
+
+
+@pytest.mark.parametrize("which", ["bls", "bn"])
+@pytest.mark.parametrize("case", ["n4", "n8_padded", "n64", "n1"])
+def test_ipp_like_reference_tests(which, case, ctx_bls, ctx_bn):
+    ctx = ctx_bls if which == "bls" else ctx_bn
+    C = curve_of(ctx)
+    if case == "n4":
+        a, b, k = [1, 2, 3, 4], [5, 6, 7, 8], 4                                   # ipp.rs:326-335
+    elif case == "n8_padded":
+        a, b, k = [1, 2, 3, 4, 9, 0, 0, 0], [5, 6, 7, 8, 10, 0, 0, 0], 5          # ipp.rs:395-402
+    elif case == "n1":
+        a, b, k = [7], [9], 1
+    else:
+        a, b, k = C.synth_scalars(11, 64, b"a"), C.synth_scalars(11, 64, b"b"), 64   # BASELINE config 1
+    n = len(a)
+    dG, dH = ctx.get_generators("g", n), ctx.get_generators("h", n)                # ipp.rs:339-341
+    G, H, Q = C.get_generators("g", n), C.get_generators("h", n), C.g1_from_msg_hash(b"Q")
+    y_inv = C.fr_inv(C.synth_scalar(9, 0))
+    Gf, Hf = [1] * n, C.vandermonde(y_inv, n)                                      # ipp.rs:344-348
+    exp = oipp.create_ipp(C, Transcript(b"innerproduct", C), Q, Gf, Hf, G, H, a, b)
+    proof = ctx.ipp_create(b"innerproduct", dG, dH, C.g1_xy_bytes(Q), enc_scalars(C, Gf), enc_scalars(C, Hf), enc_scalars(C, a),
+                           enc_scalars(C, b), n)
+    assert proof == ipp_bytes(C, exp)
+    # P = <a, G> + <b', H> + <a,b> Q with b' = b o H_factors, from the un-padded vectors (ipp.rs:354-372,458-471)
+    bp_ = [x * y % C.r for x, y in zip(b[:k], Hf)]
+    P = C.msm(G[:k] + H[:k] + [Q], a[:k] + bp_ + [C.inner_product(a, b)])
+    args = (b"innerproduct", n, enc_scalars(C, Gf), enc_scalars(C, Hf), C.g1_xy_bytes(P), C.g1_xy_bytes(Q), dG, dH)
+    assert ctx.ipp_verify(*args, proof) is True
+    mb = C.MODBYTES
+    bad = bytearray(proof)
+    bad[-1] ^= 1                                                                   # b -> b +- 1
+    assert ctx.ipp_verify(*args, bytes(bad)) is False
+    if n > 1:
+        bad = proof[:1] + proof[1 + 2 * mb + 1:1 + 4 * mb + 1] + proof[1 + 2 * mb:]    # L_1 replaced by L_2's bytes (shifted)
+        assert len(bad) == len(proof)
+        assert ctx.ipp_verify(*args, bad) is False
+        # verification_scalars' guard n == 2^lg (ipp.rs:274-276)
+        assert ctx.ipp_verify(b"innerproduct", 2 * n, enc_scalars(C, Gf + Gf), enc_scalars(C, Hf + Hf), C.g1_xy_bytes(P),
+                              C.g1_xy_bytes(Q), ctx.get_generators("g", 2 * n), ctx.get_generators("h", 2 * n), proof) is False
+    with pytest.raises(Exception):                                                 # assert!(n.is_power_of_two()) ipp.rs:48
+        ctx.ipp_create(b"innerproduct", dG, dH, C.g1_xy_bytes(Q), enc_scalars(C, Gf[:3]), enc_scalars(C, Hf[:3]),
+                       enc_scalars(C, a[:3]), enc_scalars(C, b[:3]), 3)
+
+
+@pytest.mark.parametrize("which", ["bls", "bn"])
+def test_bound_check_matches_oracle(which, ctx_bls, ctx_bn):
+    """gadgets/bound_check.rs:188-225 at 8 bits: proof bytes identical to the oracle's on the same blinding stream."""
+    ctx = ctx_bls if which == "bls" else ctx_bn
+    C = curve_of(ctx)
+    bits, seed = 8, 1
+    g, h = C.g1_from_msg_hash(b"g"), C.g1_from_msg_hash(b"h")
+    G, H = C.get_generators("G", 2 * bits), C.get_generators("H", 2 * bits)
+    rng = or1cs.make_rng(C, seed)
+    p = or1cs.Prover(C, g, h, Transcript(b"BoundsTest", C))
+    comms = or1cs.prove_bounded_num(p, 75, rng(), 10, 100, bits, rng)
+    exp = p.prove(G, H, rng)
+    dG, dH = ctx.get_generators("G", 2 * bits), ctx.get_generators("H", 2 * bits)
+    gx, hx = C.g1_xy_bytes(g), C.g1_xy_bytes(h)
+    proof, cb = ctx.bound_check_prove(b"BoundsTest", gx, hx, dG, dH, 75, 10, 100, bits, seed=seed)
+    assert cb == enc_points(C, comms)
+    assert proof == exp.to_bytes(C)
+    r_be = C.fr_to_bytes(C.synth_scalar(77, 0))
+    assert ctx.bound_check_verify(b"BoundsTest", gx, hx, dG, dH, 10, 100, bits, proof, cb, r_be) is True
+    assert ctx.bound_check_verify(b"BoundsTest", gx, hx, dG, dH, 10, 100, bits, proof, cb) is True          # OS-entropy r
+    # wrong statement / wrong transcript label / tampered scalar / tampered commitment -> VerificationError
+    assert ctx.bound_check_verify(b"BoundsTest", gx, hx, dG, dH, 11, 100, bits, proof, cb, r_be) is False
+    assert ctx.bound_check_verify(b"OtherLabel", gx, hx, dG, dH, 10, 100, bits, proof, cb, r_be) is False
+    mb = C.MODBYTES
+    off = 11 * (2 * mb + 1) + mb - 1                                              # last byte of t_x
+    bad = bytearray(proof)
+    bad[off] ^= 1
+    assert ctx.bound_check_verify(b"BoundsTest", gx, hx, dG, dH, 10, 100, bits, bytes(bad), cb, r_be) is False
+    assert ctx.bound_check_verify(b"BoundsTest", gx, hx, dG, dH, 10, 100, bits, proof, cb[2 * mb:4 * mb] + cb[:2 * mb] + cb[4 * mb:],
+                                  r_be) is False
+    # InvalidGeneratorsLength (prover.rs:332-334, verifier.rs:297-299)
+    small = ctx.get_generators("G", 5)
+    with pytest.raises(Exception) as e:
+        ctx.bound_check_prove(b"BoundsTest", gx, hx, small, small, 75, 10, 100, bits, seed=seed)
+    assert e.value.code == -3
+    with pytest.raises(Exception) as e:
+        ctx.bound_check_verify(b"BoundsTest", gx, hx, small, small, 10, 100, bits, proof, cb, r_be)
+    assert e.value.code == -3
+    # FormatError on a truncated proof
+    with pytest.raises(Exception) as e:
+        ctx.bound_check_verify(b"BoundsTest", gx, hx, dG, dH, 10, 100, bits, proof[:-3], cb, r_be)
+    assert e.value.code == -5
+
+
+def test_bound_check_reference_shape_32_bits(ctx_bls):
+    """the reference's own parameters: min 10, max 100, n = 32 bits, 128 generators (bound_check.rs:195-210): completeness
+    with OS randomness, and an out-of-range witness must not verify."""
+    ctx = ctx_bls
+    C = curve_of(ctx)
+    dG, dH = ctx.get_generators("G", 128), ctx.get_generators("H", 128)
+    gx, hx = ctx.g1_from_msg_hash(b"g"), ctx.g1_from_msg_hash(b"h")
+    for v in (10, 57, 100):
+        proof, cb = ctx.bound_check_prove(b"BoundsTest", gx, hx, dG, dH, v, 10, 100, 32)
+        assert ctx.bound_check_verify(b"BoundsTest", gx, hx, dG, dH, 10, 100, 32, proof, cb) is True
+    assert len(proof) == 11 * 97 + 3 * 48 + 2 * 6 * 97 + 2 * 48                      # proof.rs:26-58 with lg = 6
+
+
+@pytest.mark.parametrize("which", ["bls", "bn"])
+def test_range_proof_matches_oracle(which, ctx_bls, ctx_bn):
+    """m x positive_no_gadget in one constraint system (BASELINE configs 2/3/5 at reduced size), incl. a padded circuit
+    (n = 3*5 = 15 -> 16, prover.rs:527-535) and a value that is out of range."""
+    ctx = ctx_bls if which == "bls" else ctx_bn
+    C = curve_of(ctx)
+    g, h = C.g1_from_msg_hash(b"g"), C.g1_from_msg_hash(b"h")
+    gx, hx = C.g1_xy_bytes(g), C.g1_xy_bytes(h)
+    for vals, bits, seed in (([5, 200], 8, 3), ([1, 30, 17], 5, 4)):
+        n = len(vals) * bits
+        N = 1 << (n - 1).bit_length()
+        G, H = C.get_generators("G", N), C.get_generators("H", N)
+        rng = or1cs.make_rng(C, seed)
+        p = or1cs.Prover(C, g, h, Transcript(b"Range", C))
+        comms = []
+        for v in vals:
+            com, var = p.commit(v, rng())
+            comms.append(com)
+            or1cs.positive_no_gadget(p, or1cs.AllocatedQuantity(var, v), bits)
+        exp = p.prove(G, H, rng)
+        dG, dH = ctx.get_generators("G", N), ctx.get_generators("H", N)
+        proof, cb = ctx.range_prove(b"Range", gx, hx, dG, dH, vals, bits, seed=seed)
+        assert cb == enc_points(C, comms)
+        assert proof == exp.to_bytes(C)
+        assert ctx.range_verify(b"Range", gx, hx, dG, dH, len(vals), bits, proof, cb) is True
+    # 300 does not fit 8 bits: the prover still emits a proof (as the reference would) but it must not verify
+    dG, dH = ctx.get_generators("G", 16), ctx.get_generators("H", 16)
+    proof, cb = ctx.range_prove(b"Range", gx, hx, dG, dH, [5, 300], 8, seed=9)
+    assert ctx.range_verify(b"Range", gx, hx, dG, dH, 2, 8, proof, cb) is False

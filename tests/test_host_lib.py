@@ -1,0 +1,50 @@
+"""CPU tests of the host layer's transcript (bulletproofs-amcl_b200/host/merlin.hpp, curve.hpp) through
+include/bphost.h: Merlin's published known answer, and TranscriptProtocol (transcript.rs:29-61) against the
+oracle's restatement, including the 48-byte challenge reduced mod r on BLS12-381."""
+import ctypes
+
+import pytest
+
+from oracle.curves import BLS12_381, BN254
+from oracle.merlin import Transcript
+
+
+def test_merlin_equivalence_simple_kat(bp):
+    """merlin's own test `equivalence_simple`: new("test protocol"), append("some label","some data"),
+    32 challenge bytes under "challenge"."""
+    out = ctypes.create_string_buffer(32)
+    rc = bp.lib().bph_merlin_kat(b"test protocol", b"some label", b"some data", 9, b"challenge", out, 32)
+    assert rc == 0
+    assert out.raw.hex() == "d5a21972d0d5fe320c0d263fac7fffb8145aa640af6e9bca177c03c7efcf0615"
+
+
+def test_merlin_long_messages_cross_rate_boundary(bp):
+    """messages longer than the STROBE rate (166) exercise run_f inside absorb / squeeze."""
+    msg = bytes(range(256)) * 3
+    out = ctypes.create_string_buffer(400)
+    assert bp.lib().bph_merlin_kat(b"L", b"m", msg, len(msg), b"c", out, 400) == 0
+    t = Transcript(b"L")
+    t.append_message(b"m", msg)
+    assert out.raw == t.challenge_bytes(b"c", 400)
+
+
+@pytest.mark.parametrize("C", [BLS12_381, BN254], ids=lambda c: c.name)
+def test_transcript_protocol_matches_oracle(bp, C):
+    P = C.mul(C.from_affine(C.g), 123456789)
+    for s in (0, 1, C.r - 1, C.synth_scalar(9, 0)):
+        out = ctypes.create_string_buffer(C.MODBYTES)
+        rc = bp.lib().bph_transcript_kat(C.id, b"kat", C.g1_xy_bytes(P), C.fr_to_bytes(s), out)
+        assert rc == 0
+        t = Transcript(b"kat", C)
+        t.innerproduct_domain_sep(8)
+        t.commit_point(b"P", P)
+        t.commit_scalar(b"s", s)
+        assert out.raw == C.fr_to_bytes(t.challenge_scalar(b"c"))
+    # the identity point is absorbed as 04 || 0..0 || 0..01 (prover.rs:429-434)
+    out = ctypes.create_string_buffer(C.MODBYTES)
+    assert bp.lib().bph_transcript_kat(C.id, b"kat", C.g1_xy_bytes(C.INF), C.fr_to_bytes(5), out) == 0
+    t = Transcript(b"kat", C)
+    t.innerproduct_domain_sep(8)
+    t.commit_point(b"P", C.INF)
+    t.commit_scalar(b"s", 5)
+    assert out.raw == C.fr_to_bytes(t.challenge_scalar(b"c"))
