@@ -40,6 +40,10 @@ SYMBOLS = [
     ("bpgpu_msm_device", _INT, [_VP, _VP, _SZ, _SZ, _VP, _SZ, _VP]),
     ("bpgpu_msm_refs", _INT, [_VP, _VP, _VP, _SZ, _VP]),
     ("bpgpu_msm_window_bits", _INT, [_SZ]),
+    ("bpgpu_fixed_bases_create", _INT, [_VP, _VP, _SZ, _c.POINTER(_VP)]),
+    ("bpgpu_fixed_bases_get", _INT, [_VP, _VP, _SZ, _c.POINTER(_VP)]),
+    ("bpgpu_fixed_bases_commit", _INT, [_VP, _VP, _VP, _SZ, _VP]),
+    ("bpgpu_fixed_bases_free", None, [_VP]),
     ("bpgpu_scalars_alloc", _INT, [_VP, _SZ, _c.POINTER(_VP)]),
     ("bpgpu_fr_vandermonde", _INT, [_VP, _VP, _SZ, _c.POINTER(_VP)]),
     ("bpgpu_fr_hadamard", _INT, [_VP, _VP, _SZ, _VP, _SZ, _SZ, _VP, _SZ]),
@@ -80,6 +84,9 @@ SYMBOLS_HOST = [
     ("bph_bound_check_verify", _INT, [_VP, _CS, _VP, _VP, _VP, _VP, _U64, _U64, _SZ, _VP, _SZ, _VP, _VP]),
     ("bph_range_prove", _INT, [_VP, _CS, _VP, _VP, _VP, _VP, _VP, _SZ, _SZ, _INT, _U64, _VP, _SZ, _c.POINTER(_SZ), _VP]),
     ("bph_range_verify", _INT, [_VP, _CS, _VP, _VP, _VP, _VP, _SZ, _SZ, _VP, _SZ, _VP, _VP]),
+    ("bph_range_proof_len", _SZ, [_INT, _SZ, _SZ]),
+    ("bph_range_prove_many", _INT, [_VP, _SZ, _CS, _VP, _VP, _VP, _VP, _VP, _SZ, _SZ, _SZ, _INT, _U64, _VP, _SZ, _VP]),
+    ("bph_range_verify_many", _INT, [_VP, _SZ, _CS, _VP, _VP, _VP, _VP, _SZ, _SZ, _SZ, _VP, _SZ, _VP, _VP]),
 ]
 
 
@@ -87,6 +94,37 @@ class MsmPart(ctypes.Structure):
     """bpgpu_msm_part"""
     _fields_ = [("points", _VP), ("points_off", _SZ), ("host_points_xy", _VP),
                 ("scalars", _VP), ("scalars_off", _SZ), ("host_scalars_be", _VP), ("n", _SZ)]
+
+
+def _ctx_array(ctxs):
+    return (ctypes.c_void_p * len(ctxs))(*[c.handle for c in ctxs])
+
+
+def range_prove_many(ctxs, label, g_xy, h_xy, G, H, values, m, bits, seed=None):
+    """count = len(values)/m independent range proofs over len(ctxs) contexts (one host thread each).
+    Returns (proofs bytes, stride, commitments bytes)."""
+    count = len(values) // m
+    c0 = ctxs[0]
+    stride = lib().bph_range_proof_len(c0.curve, m, bits)
+    proofs = ctypes.create_string_buffer(max(1, count * stride))
+    comms = ctypes.create_string_buffer(max(1, count * m * 2 * c0.modbytes))
+    arr = (ctypes.c_uint64 * max(1, len(values)))(*values)
+    rc = lib().bph_range_prove_many(_ctx_array(ctxs), len(ctxs), label, _buf(g_xy), _buf(h_xy), G.handle, H.handle,
+                                    ctypes.cast(arr, ctypes.c_void_p), count, m, bits, 0 if seed is None else 1, seed or 0, proofs, stride,
+                                    comms)
+    if rc:
+        raise BpgpuError(rc, "range_prove_many")
+    return proofs.raw[:count * stride], stride, comms.raw[:count * m * 2 * c0.modbytes]
+
+
+def range_verify_many(ctxs, label, g_xy, h_xy, G, H, count, m, bits, proofs, stride, comms):
+    """per-proof verdicts (0 = Ok, -4 = VerificationError, ...) of `count` independent proofs."""
+    verdicts = (ctypes.c_int32 * max(1, count))()
+    rc = lib().bph_range_verify_many(_ctx_array(ctxs), len(ctxs), label, _buf(g_xy), _buf(h_xy), G.handle, H.handle, count, m, bits,
+                                     _buf(proofs), stride, _buf(comms), verdicts)
+    if rc:
+        raise BpgpuError(rc, "range_verify_many")
+    return list(verdicts)[:count]
 
 
 class BpgpuError(RuntimeError):
@@ -344,6 +382,15 @@ class Context:
         out = ctypes.create_string_buffer(2 * self.modbytes)
         self._check(lib().bpgpu_msm_refs(self.handle, _buf(points_xy), _buf(scalars_be), n, out), "msm_refs")
         return out.raw
+
+    def commit_batch(self, bases_xy, scalars_be, count):
+        """count independent combinations sum_j s[i*k+j] * B_j over k fixed bases (cached window tables)."""
+        k = len(bases_xy) // (2 * self.modbytes)
+        fb = ctypes.c_void_p()
+        self._check(lib().bpgpu_fixed_bases_get(self.handle, _buf(bases_xy), k, ctypes.byref(fb)), "fixed_bases_get")
+        out = ctypes.create_string_buffer(max(1, count * 2 * self.modbytes))
+        self._check(lib().bpgpu_fixed_bases_commit(self.handle, fb, _buf(scalars_be), count, out), "fixed_bases_commit")
+        return out.raw[:count * 2 * self.modbytes]
 
     def msm_parts(self, parts):
         """parts: list of (points, scalars, n[, points_off, scalars_off]); points is DevicePoints or bytes (X||Y),

@@ -184,6 +184,15 @@ __global__ void __launch_bounds__(256) k_fq_mul_chain(int iters, const F* in, F*
   if (x.is_zero() && y.is_zero()) store_vec(out, x);
 }
 
+// kind 33: a chain of dependent XYZZ doublings on one warp (latency of the serial part of a scalar multiplication)
+template <class F>
+__global__ void k_dbl_chain(int iters, const XYZZ<F>* in, XYZZ<F>* out) {
+  XYZZ<F> p = load_vec(in + threadIdx.x);
+  p.zz = p.zz + F::one();
+  for (int it = 0; it < iters; it++) p.dbl();
+  if (p.x.is_zero() && p.y.is_zero() && p.zzz.is_zero()) store_vec(out, p);
+}
+
 template <class Curve>
 int points_from_host(bpgpu_ctx* ctx, const uint8_t* xy, size_t n, void* dst) {
   if (n == 0) return BPGPU_OK;
@@ -309,6 +318,11 @@ int bpgpu_ctx_create(int curve, int device, bpgpu_ctx** out) {
   BP_CUDA_OK(cudaGetDeviceProperties(&prop, device));
   c->sm_count = prop.multiProcessorCount;
   BP_CUDA_OK(cudaStreamCreateWithFlags(&c->stream, cudaStreamNonBlocking));
+  {
+    cudaMemPool_t pool;
+    uint64_t keep = ~0ull;                      // keep freed blocks in the pool: the next proof reuses them
+    if (cudaDeviceGetDefaultMemPool(&pool, device) == cudaSuccess) cudaMemPoolSetAttribute(pool, cudaMemPoolAttrReleaseThreshold, &keep);
+  }
   c->pinned_cap = 1 << 18;
   BP_CUDA_OK(cudaHostAlloc((void**)&c->pinned, c->pinned_cap, cudaHostAllocDefault));
   *out = c;
@@ -319,6 +333,8 @@ void bpgpu_ctx_destroy(bpgpu_ctx* c) {
   if (!c) return;
   cudaSetDevice(c->device);
   cudaStreamSynchronize(c->stream);
+  for (bpgpu_fixed_bases* fb : c->fb_cache) bpgpu_fixed_bases_free(fb);
+  c->fb_cache.clear();
   c->msm_a.release(); c->msm_b.release(); c->msm_c.release(); c->msm_d.release(); c->msm_e.release();
   c->io_dev.release(); c->io_dev2.release();
   c->ipp_pts.release(); c->ipp_scl.release(); c->parts_pts.release(); c->parts_scl.release();
@@ -366,12 +382,12 @@ int bpgpu_points_upload(bpgpu_ctx* ctx, const uint8_t* xy, size_t n, bpgpu_point
   if (!p) return BPGPU_E_CUDA;
   p->ctx = ctx; p->n = n; p->d = nullptr;
   size_t psz = (ctx->curve == BPGPU_BLS12_381) ? sizeof(Affine<Bls::Fq>) : sizeof(Affine<Bn::Fq>);
-  if (cudaMalloc(&p->d, n ? n * psz : 16) != cudaSuccess) { delete p; return BPGPU_E_CUDA; }
+  if (dev_alloc(ctx, &p->d, n * psz) != cudaSuccess) { delete p; return BPGPU_E_CUDA; }
 #define CALL(C) points_from_host<C>(ctx, xy, n, p->d)
   int rc = DISPATCH(ctx, CALL);
 #undef CALL
   if (rc == BPGPU_OK && cudaStreamSynchronize(ctx->stream) != cudaSuccess) rc = BPGPU_E_CUDA;
-  if (rc) { cudaFree(p->d); delete p; return rc; }
+  if (rc) { dev_free(ctx, p->d); delete p; return rc; }
   *out = p;
   return BPGPU_OK;
 }
@@ -399,7 +415,7 @@ size_t bpgpu_points_len(const bpgpu_points* p) { return p ? p->n : 0; }
 void bpgpu_points_free(bpgpu_points* p) {
   if (!p) return;
   cudaSetDevice(p->ctx->device);
-  cudaFree(p->d);
+  dev_free(p->ctx, p->d);
   delete p;
 }
 
@@ -410,12 +426,12 @@ int bpgpu_scalars_upload(bpgpu_ctx* ctx, const uint8_t* be, size_t n, bpgpu_scal
   bpgpu_scalars* s = new (std::nothrow) bpgpu_scalars();
   if (!s) return BPGPU_E_CUDA;
   s->ctx = ctx; s->n = n; s->d = nullptr;
-  if (cudaMalloc(&s->d, n ? n * 32 : 16) != cudaSuccess) { delete s; return BPGPU_E_CUDA; }
+  if (dev_alloc(ctx, &s->d, n * 32) != cudaSuccess) { delete s; return BPGPU_E_CUDA; }
 #define CALL(C) scalars_upload_t<C>(ctx, be, n, 1, s->d, ctx->io_dev)
   int rc = DISPATCH(ctx, CALL);
 #undef CALL
   if (rc == BPGPU_OK && cudaStreamSynchronize(ctx->stream) != cudaSuccess) rc = BPGPU_E_CUDA;
-  if (rc) { cudaFree(s->d); delete s; return rc; }
+  if (rc) { dev_free(ctx, s->d); delete s; return rc; }
   *out = s;
   return BPGPU_OK;
 }
@@ -443,7 +459,7 @@ size_t bpgpu_scalars_len(const bpgpu_scalars* s) { return s ? s->n : 0; }
 void bpgpu_scalars_free(bpgpu_scalars* s) {
   if (!s) return;
   cudaSetDevice(s->ctx->device);
-  cudaFree(s->d);
+  dev_free(s->ctx, s->d);
   delete s;
 }
 
@@ -555,7 +571,8 @@ int bpgpu_int_pipe_bench(bpgpu_ctx* ctx, int kind, int iters, double* ops_per_s,
   cudaEvent_t e0, e1;
   BP_CUDA_OK(cudaEventCreate(&e0));
   BP_CUDA_OK(cudaEventCreate(&e1));
-  const int blocks = ctx->sm_count * 8, threads = 256;
+  int blocks = ctx->sm_count * 8, threads = 256;
+  if (kind == 31 || kind == 32 || kind == 33) { blocks = 1; threads = 32; }     // single-warp latency probes
   double ops = 0;
   float best = 1e30f;
   for (int rep = 0; rep < 5; rep++) {
@@ -576,6 +593,9 @@ int bpgpu_int_pipe_bench(bpgpu_ctx* ctx, int kind, int iters, double* ops_per_s,
         case 13: k_fq_mul_chain<Bls::Fq, 3><<<blocks, threads, 0, ctx->stream>>>(iters, in, o); break;
         case 14: k_fq_mul_chain<Bls::Fq, 4><<<blocks, threads, 0, ctx->stream>>>(iters, in, o); break;
         case 16: k_fq_mul_chain<Bls::Fq, 6><<<blocks, threads, 0, ctx->stream>>>(iters, in, o); break;
+        case 31: k_fq_mul_chain<Bls::Fq, 0><<<blocks, threads, 0, ctx->stream>>>(iters, in, o); break;
+        case 32: k_fq_mul_chain<Bn::Fq, 0><<<blocks, threads, 0, ctx->stream>>>(iters, (const Bn::Fq*)ctx->io_dev.p, (Bn::Fq*)ctx->io_dev.p); break;
+        case 33: k_dbl_chain<Bls::Fq><<<blocks, threads, 0, ctx->stream>>>(iters, (const XYZZ<Bls::Fq>*)ctx->io_dev.p, (XYZZ<Bls::Fq>*)ctx->io_dev.p); break;
         case 20: k_fq_mul_chain<Bn::Fq, 0><<<blocks, threads, 0, ctx->stream>>>(iters, (const Bn::Fq*)ctx->io_dev.p, (Bn::Fq*)ctx->io_dev.p); break;
         case 22: k_fq_mul_chain<Bn::Fq, 2><<<blocks, threads, 0, ctx->stream>>>(iters, (const Bn::Fq*)ctx->io_dev.p, (Bn::Fq*)ctx->io_dev.p); break;
         default: k_fq_mul_chain<Bls::Fq, 0><<<blocks, threads, 0, ctx->stream>>>(iters, in, o); break;

@@ -57,6 +57,8 @@ struct Scratch {
 
 }  // namespace bp
 
+struct bpgpu_fixed_bases;
+
 struct bpgpu_ctx {
   int curve = 0;
   int device = 0;
@@ -72,6 +74,7 @@ struct bpgpu_ctx {
   int profile = 0;
   double stage_ms_sum[8] = {0, 0, 0, 0, 0, 0, 0, 0};
   uint64_t stage_runs = 0;
+  std::vector<bpgpu_fixed_bases*> fb_cache;   // ctx-owned fixed-base tables (fixedbase.cu)
 };
 
 struct bpgpu_points {
@@ -86,6 +89,12 @@ struct bpgpu_scalars {
 };
 
 namespace bp {
+
+// Handle storage (G1Vector / FieldElementVector / IPP state) comes from the device's stream-ordered pool on the ctx
+// stream: allocation and release are queue operations (microseconds), not driver calls that synchronise the device.
+// The pool's release threshold is raised at ctx creation so freed blocks are reused by the next proof.
+inline cudaError_t dev_alloc(bpgpu_ctx* ctx, void** p, size_t bytes) { return cudaMallocAsync(p, bytes ? bytes : 16, ctx->stream); }
+inline void dev_free(bpgpu_ctx* ctx, void* p) { if (p) cudaFreeAsync(p, ctx->stream); }
 
 // ------------------------------------------------------------------ 128-bit vector I/O
 template <class T>

@@ -190,8 +190,8 @@ int bpgpu_scalars_alloc(bpgpu_ctx* ctx, size_t n, bpgpu_scalars** out) {
   bpgpu_scalars* s = new (std::nothrow) bpgpu_scalars();
   if (!s) return BPGPU_E_CUDA;
   s->ctx = ctx; s->n = n; s->d = nullptr;
-  if (cudaMalloc(&s->d, n ? n * 32 : 16) != cudaSuccess) { delete s; return BPGPU_E_CUDA; }
-  if (cudaMemsetAsync(s->d, 0, n ? n * 32 : 16, ctx->stream) != cudaSuccess) { cudaFree(s->d); delete s; return BPGPU_E_CUDA; }
+  if (dev_alloc(ctx, &s->d, n * 32) != cudaSuccess) { delete s; return BPGPU_E_CUDA; }
+  if (cudaMemsetAsync(s->d, 0, n ? n * 32 : 16, ctx->stream) != cudaSuccess) { dev_free(ctx, s->d); delete s; return BPGPU_E_CUDA; }
   *out = s;
   return BPGPU_OK;
 }

@@ -134,9 +134,9 @@ static int ipp_begin_t(bpgpu_ipp* st, const void* G, const void* H, const uint8_
   bpgpu_ctx* ctx = st->ctx;
   const size_t N = st->N;
   cudaStream_t s = ctx->stream;
-  BP_CUDA_OK(cudaMalloc(&st->P, (2 * N + 1) * sizeof(Affine<Fq>)));
+  BP_CUDA_OK(dev_alloc(ctx, &st->P, (2 * N + 1) * sizeof(Affine<Fq>)));
   void* frs = nullptr;
-  BP_CUDA_OK(cudaMalloc(&frs, (4 * N + 2 * (2 * N + 1)) * sizeof(Fr)));
+  BP_CUDA_OK(dev_alloc(ctx, &frs, (4 * N + 2 * (2 * N + 1)) * sizeof(Fr)));
   st->a = frs;
   st->b = (Fr*)frs + N;
   st->sG = (Fr*)frs + 2 * N;
@@ -310,9 +310,8 @@ int bpgpu_ipp_finish(bpgpu_ipp* st, uint8_t* a_be, uint8_t* b_be) {
 void bpgpu_ipp_free(bpgpu_ipp* st) {
   if (!st) return;
   cudaSetDevice(st->ctx->device);
-  cudaStreamSynchronize(st->ctx->stream);
-  if (st->P) cudaFree(st->P);
-  if (st->a) cudaFree(st->a);
+  dev_free(st->ctx, st->P);
+  dev_free(st->ctx, st->a);
   delete st;
 }
 

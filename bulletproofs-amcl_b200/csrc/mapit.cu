@@ -85,10 +85,10 @@ extern "C" int bpgpu_points_from_hashes(bpgpu_ctx* ctx, const uint8_t* hashes, s
   if (!p) return BPGPU_E_CUDA;
   p->ctx = ctx; p->n = n; p->d = nullptr;
   size_t psz = (ctx->curve == BPGPU_BLS12_381) ? sizeof(Affine<Bls::Fq>) : sizeof(Affine<Bn::Fq>);
-  if (cudaMalloc(&p->d, n ? n * psz : 16) != cudaSuccess) { delete p; return BPGPU_E_CUDA; }
+  if (dev_alloc(ctx, &p->d, n * psz) != cudaSuccess) { delete p; return BPGPU_E_CUDA; }
   int rc = ctx->curve == BPGPU_BLS12_381 ? mapit_t<Bls>(ctx, hashes, n, p->d) : mapit_t<Bn>(ctx, hashes, n, p->d);
   if (rc == BPGPU_OK && cudaStreamSynchronize(ctx->stream) != cudaSuccess) rc = BPGPU_E_CUDA;
-  if (rc) { cudaFree(p->d); delete p; return rc; }
+  if (rc) { dev_free(ctx, p->d); delete p; return rc; }
   *out = p;
   return BPGPU_OK;
 }

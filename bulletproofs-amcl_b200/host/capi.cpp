@@ -1,7 +1,9 @@
 // C entry points of the host layer (include/bphost.h): flatten the C++ mirror of the reference's API to bytes.
 #include <stdio.h>
 
+#include <atomic>
 #include <string>
+#include <thread>
 #include <vector>
 
 #include "../../include/bphost.h"
@@ -150,6 +152,26 @@ int range_verify_t(bpgpu_ctx* ctx, const char* label, const uint8_t* g_xy, const
 // hash_msg: SHAKE256(msg) squeezed to MODBYTES (G1::from_msg_hash / FieldElement::from_msg_hash)
 void hash_msg(const uint8_t* msg, size_t len, int modbytes, uint8_t* out) { shake256(msg, len, out, modbytes); }
 
+// run fn(i, ctx) for i in [0, count) on nctx worker threads (one context each); returns the first non-zero result
+template <class F>
+static int for_each_proof(bpgpu_ctx* const* ctxs, size_t nctx, size_t count, F fn) {
+  std::atomic<size_t> next{0};
+  std::atomic<int> err{0};
+  auto worker = [&](size_t k) {
+    for (;;) {
+      size_t i = next.fetch_add(1);
+      if (i >= count) break;
+      int rc = fn(i, ctxs[k]);
+      if (rc) { int z = 0; err.compare_exchange_strong(z, rc); }
+    }
+  };
+  std::vector<std::thread> th;
+  for (size_t k = 1; k < nctx; k++) th.emplace_back(worker, k);
+  worker(0);
+  for (auto& t : th) t.join();
+  return err.load();
+}
+
 }  // namespace
 
 #define BY_CURVE(ctx, CALL) (bpgpu_ctx_curve(ctx) == BPGPU_BLS12_381 ? CALL(Bls381) : CALL(Bn254))
@@ -259,6 +281,43 @@ int bph_range_verify(bpgpu_ctx* ctx, const char* label, const uint8_t* g_xy, con
 #define CALL(C) range_verify_t<C>(ctx, label, g_xy, h_xy, G, H, m, bits, proof, len, comms_xy, r_be)
   return BY_CURVE(ctx, CALL);
 #undef CALL
+}
+
+size_t bph_range_proof_len(int curve, size_t m, size_t bits) {
+  const size_t mb = curve == BPGPU_BLS12_381 ? 48 : 32;
+  const size_t N = next_power_of_two(m * bits);
+  size_t lg = 0;
+  while (((size_t)1 << lg) < N) lg++;
+  return 11 * (2 * mb + 1) + 3 * mb + 2 * lg * (2 * mb + 1) + 2 * mb;
+}
+
+int bph_range_prove_many(bpgpu_ctx* const* ctxs, size_t nctx, const char* label, const uint8_t* g_xy, const uint8_t* h_xy, const bpgpu_points* G,
+                         const bpgpu_points* H, const uint64_t* values, size_t count, size_t m, size_t bits, int rng_mode, uint64_t seed,
+                         uint8_t* proofs, size_t proof_stride, uint8_t* comms_xy) {
+  if (!ctxs || !nctx || !label || !g_xy || !h_xy || !G || !H || !values || !proofs || !comms_xy) return BPGPU_E_ARG;
+  const int curve = bpgpu_ctx_curve(ctxs[0]);
+  if (proof_stride < bph_range_proof_len(curve, m, bits)) return BPH_E_BUFFER;
+  const size_t cstride = m * 2 * bpgpu_modbytes(curve);
+  return for_each_proof(ctxs, nctx, count, [&](size_t i, bpgpu_ctx* ctx) {
+    size_t len = 0;
+    return bph_range_prove(ctx, label, g_xy, h_xy, G, H, values + i * m, m, bits, rng_mode, seed + i, proofs + i * proof_stride, proof_stride,
+                           &len, comms_xy + i * cstride);
+  });
+}
+
+int bph_range_verify_many(bpgpu_ctx* const* ctxs, size_t nctx, const char* label, const uint8_t* g_xy, const uint8_t* h_xy, const bpgpu_points* G,
+                          const bpgpu_points* H, size_t count, size_t m, size_t bits, const uint8_t* proofs, size_t proof_stride,
+                          const uint8_t* comms_xy, int32_t* verdicts) {
+  if (!ctxs || !nctx || !label || !g_xy || !h_xy || !G || !H || !proofs || !comms_xy || !verdicts) return BPGPU_E_ARG;
+  const int curve = bpgpu_ctx_curve(ctxs[0]);
+  const size_t plen = bph_range_proof_len(curve, m, bits);
+  if (proof_stride < plen) return BPH_E_BUFFER;
+  const size_t cstride = m * 2 * bpgpu_modbytes(curve);
+  for_each_proof(ctxs, nctx, count, [&](size_t i, bpgpu_ctx* ctx) {
+    verdicts[i] = bph_range_verify(ctx, label, g_xy, h_xy, G, H, m, bits, proofs + i * proof_stride, plen, comms_xy + i * cstride, nullptr);
+    return 0;
+  });
+  return BPGPU_OK;
 }
 
 }  // extern "C"

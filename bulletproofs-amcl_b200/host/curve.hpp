@@ -8,7 +8,12 @@
 #include <stdint.h>
 #include <string.h>
 
+#include <stdio.h>
+#include <stdlib.h>
+
+#include <chrono>
 #include <random>
+#include <string>
 #include <vector>
 
 #include "../../include/bpgpu.h"
@@ -26,6 +31,23 @@ struct Bn254 {
   using FrP = bp::BnFr;
   static constexpr int ID = BPGPU_BN254;
   static constexpr int MODBYTES = 32;
+};
+
+// BPH_TRACE=1 in the environment prints the wall time between milestones of prove / verify to stderr
+struct Trace {
+  bool on;
+  const char* what;
+  std::chrono::steady_clock::time_point t0, last;
+  explicit Trace(const char* w) : on(getenv("BPH_TRACE") != nullptr), what(w) { t0 = last = std::chrono::steady_clock::now(); }
+  void mark(const char* name) {
+    if (!on) return;
+    auto now = std::chrono::steady_clock::now();
+    fprintf(stderr, "[bph %s] %-22s %8.3f ms\n", what, name, std::chrono::duration<double, std::milli>(now - last).count());
+    last = now;
+  }
+  ~Trace() {
+    if (on) fprintf(stderr, "[bph %s] total %8.3f ms\n", what, std::chrono::duration<double, std::milli>(std::chrono::steady_clock::now() - t0).count());
+  }
 };
 
 // R1CSError (errors.rs:7-28) as the C ABI's status codes
@@ -117,20 +139,30 @@ template <class C>
 class Rng {
  public:
   Rng() : deterministic_(false), seed_(0), tag_("os") {
+    // SHAKE256 keyed with OS entropy, squeezed as one continuous stream (one permutation per 136 bytes)
     std::random_device rd;
-    seed_ = ((uint64_t)rd() << 32) ^ rd();
-    for (int i = 0; i < 8; i++) os_key_[i] = rd();
+    memset(st_, 0, sizeof st_);
+    uint8_t* b = reinterpret_cast<uint8_t*>(st_);
+    for (int i = 0; i < 16; i++) { uint32_t w = rd(); memcpy(b + 4 * i, &w, 4); }
+    b[64] ^= 0x1f; b[135] ^= 0x80;
+    keccak_f1600(st_);
+    pos_ = 0;
   }
   Rng(uint64_t seed, const std::string& tag) : deterministic_(true), seed_(seed), tag_(tag) {}
   FieldElement<C> next() {
-    std::vector<uint8_t> m;
-    for (int i = 0; i < 8; i++) m.push_back((uint8_t)(seed_ >> (8 * i)));
-    m.insert(m.end(), tag_.begin(), tag_.end());
-    for (int i = 0; i < 8; i++) m.push_back((uint8_t)(ctr_ >> (8 * i)));
-    if (!deterministic_) m.insert(m.end(), (const uint8_t*)os_key_, (const uint8_t*)os_key_ + sizeof os_key_);
-    ctr_++;
     uint8_t out[C::MODBYTES];
-    shake256(m.data(), m.size(), out, sizeof out);
+    if (deterministic_) {
+      uint8_t m[64];
+      size_t len = 0;
+      for (int i = 0; i < 8; i++) m[len++] = (uint8_t)(seed_ >> (8 * i));
+      for (char ch : tag_) if (len < 48) m[len++] = (uint8_t)ch;
+      for (int i = 0; i < 8; i++) m[len++] = (uint8_t)(ctr_ >> (8 * i));
+      ctr_++;
+      shake256(m, len, out, sizeof out);
+    } else {
+      const uint8_t* b = reinterpret_cast<const uint8_t*>(st_);
+      for (size_t i = 0; i < sizeof out; i++) { if (pos_ == 136) { keccak_f1600(st_); pos_ = 0; } out[i] = b[pos_++]; }
+    }
     return FieldElement<C>::from_bytes(out);
   }
 
@@ -139,7 +171,8 @@ class Rng {
   uint64_t seed_;
   std::string tag_;
   uint64_t ctr_ = 0;
-  uint32_t os_key_[8] = {0, 0, 0, 0, 0, 0, 0, 0};
+  uint64_t st_[25];
+  size_t pos_ = 0;
 };
 
 }  // namespace bph

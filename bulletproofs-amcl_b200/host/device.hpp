@@ -100,12 +100,37 @@ inline int binary_scalar_mul(bpgpu_ctx* ctx, const G1<C>& g, const G1<C>& h, con
   r2.to_bytes(sc + C::MODBYTES);
   return bpgpu_msm_refs(ctx, pts, sc, 2, out->xy);
 }
+// commitment::commit_to_field_element(g, h, v_i, r_i) for a batch of (v_i, r_i): the Pedersen pair is a fixed base
+// (prover.rs:123 V, :496-500 T_1..T_6), so the ctx keeps its window table and a commitment needs no doublings.
+template <class C>
+inline int commit_batch(bpgpu_ctx* ctx, const G1<C>& g, const G1<C>& h, const std::vector<FieldElement<C>>& v,
+                        const std::vector<FieldElement<C>>& r, std::vector<G1<C>>* out) {
+  if (v.size() != r.size()) return E_LEN;
+  uint8_t bases[4 * C::MODBYTES];
+  memcpy(bases, g.xy, sizeof g.xy);
+  memcpy(bases + sizeof g.xy, h.xy, sizeof h.xy);
+  bpgpu_fixed_bases* fb = nullptr;
+  int rc = bpgpu_fixed_bases_get(ctx, bases, 2, &fb);
+  if (rc) return rc;
+  std::vector<uint8_t> sc(2 * v.size() * C::MODBYTES + 1);
+  for (size_t i = 0; i < v.size(); i++) { v[i].to_bytes(sc.data() + 2 * i * C::MODBYTES); r[i].to_bytes(sc.data() + (2 * i + 1) * C::MODBYTES); }
+  out->resize(v.size());
+  return bpgpu_fixed_bases_commit(ctx, fb, sc.data(), v.size(), v.empty() ? nullptr : (*out)[0].xy);
+}
 template <class C>
 inline int commit_to_field_element(bpgpu_ctx* ctx, const G1<C>& g, const G1<C>& h, const FieldElement<C>& v, const FieldElement<C>& r,
                                    G1<C>* out) {
-  return binary_scalar_mul(ctx, g, h, v, r, out);
+  std::vector<G1<C>> o;
+  int rc = commit_batch<C>(ctx, g, h, {v}, {r}, &o);
+  if (!rc) *out = o[0];
+  return rc;
 }
-// &G1 * &FieldElement (prover.rs:550: Q = g * w)
+// &G1 * &FieldElement for a base that is part of a cached pair (prover.rs:550: Q = g * w)
+template <class C>
+inline int scalar_mul_fixed(bpgpu_ctx* ctx, const G1<C>& g, const G1<C>& h, const FieldElement<C>& s, G1<C>* out) {
+  return commit_to_field_element<C>(ctx, g, h, s, FieldElement<C>::zero(), out);
+}
+// &G1 * &FieldElement, arbitrary base
 template <class C>
 inline int scalar_mul(bpgpu_ctx* ctx, const G1<C>& g, const FieldElement<C>& s, G1<C>* out) {
   uint8_t sc[C::MODBYTES];

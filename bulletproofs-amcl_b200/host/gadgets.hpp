@@ -123,18 +123,19 @@ int gen_proof_of_positive_nums(bpgpu_ctx* ctx, const std::vector<uint64_t>& vals
                                const G1<C>& g, const G1<C>& h, const G1Vector<C>& G, const G1Vector<C>& H, R1CSProof<C>* proof,
                                std::vector<G1<C>>* comms) {
   using FE = FieldElement<C>;
+  Trace tr("range_prove");
   Transcript prover_transcript(transcript_label);
   Prover<C> prover(ctx, g, h, prover_transcript, rng);
-  comms->clear();
-  for (uint64_t v : vals) {
-    G1<C> com;
-    Variable var;
-    FE fv = FE::from_u64(v);
-    int rc = prover.commit(fv, rng.next(), &com, &var);
-    if (rc) return rc;
-    comms->push_back(com);
-    if ((rc = positive_no_gadget<C>(prover, AllocatedQuantity<C>{var, true, fv}, bits))) return rc;
-  }
+  // the reference would call prover.commit(v_j, FieldElement::random()) then the gadget, per value; the commitments do
+  // not depend on the gadget's allocations, so they are evaluated as one batch with the same transcript order
+  std::vector<FE> fv, blind;
+  for (uint64_t v : vals) { fv.push_back(FE::from_u64(v)); blind.push_back(rng.next()); }
+  std::vector<Variable> vars;
+  int rc = prover.commit_vec(fv, blind, comms, &vars);
+  if (rc) return rc;
+  for (size_t j = 0; j < vals.size(); j++)
+    if ((rc = positive_no_gadget<C>(prover, AllocatedQuantity<C>{vars[j], true, fv[j]}, bits))) return rc;
+  tr.mark("commit + gadget");
   return prover.prove(G, H, proof);
 }
 
@@ -142,6 +143,7 @@ template <class C>
 int verify_proof_of_positive_nums(bpgpu_ctx* ctx, size_t bits, const R1CSProof<C>& proof, const std::vector<G1<C>>& commitments,
                                   const std::string& transcript_label, const G1<C>& g, const G1<C>& h, const G1Vector<C>& G,
                                   const G1Vector<C>& H, const FieldElement<C>& verifier_r) {
+  Trace tr("range_verify");
   Transcript verifier_transcript(transcript_label);
   Verifier<C> verifier(ctx, verifier_transcript);
   for (const auto& com : commitments) {
@@ -149,6 +151,7 @@ int verify_proof_of_positive_nums(bpgpu_ctx* ctx, size_t bits, const R1CSProof<C
     int rc = positive_no_gadget<C>(verifier, AllocatedQuantity<C>{var, false, FieldElement<C>::zero()}, bits);
     if (rc) return rc;
   }
+  tr.mark("commit + gadget");
   return verifier.verify(proof, g, h, G, H, verifier_r);
 }
 

@@ -15,6 +15,8 @@ namespace bph {
 
 inline uint64_t rotl64(uint64_t x, int n) { return n ? (x << n) | (x >> (64 - n)) : x; }
 
+// Keccak-f[1600], 24 rounds.  State lanes live in locals and every loop has constant bounds, so the compiler keeps
+// the 25 lanes in registers and unrolls theta / rho-pi / chi completely.
 inline void keccak_f1600(uint64_t st[25]) {
   static const uint64_t RC[24] = {
       0x0000000000000001ULL, 0x0000000000008082ULL, 0x800000000000808AULL, 0x8000000080008000ULL, 0x000000000000808BULL,
@@ -22,23 +24,31 @@ inline void keccak_f1600(uint64_t st[25]) {
       0x0000000080008009ULL, 0x000000008000000AULL, 0x000000008000808BULL, 0x800000000000008BULL, 0x8000000000008089ULL,
       0x8000000000008003ULL, 0x8000000000008002ULL, 0x8000000000000080ULL, 0x000000000000800AULL, 0x800000008000000AULL,
       0x8000000080008081ULL, 0x8000000000008080ULL, 0x0000000080000001ULL, 0x8000000080008008ULL};
-  static const int ROTC[24] = {1, 3, 6, 10, 15, 21, 28, 36, 45, 55, 2, 14, 27, 41, 56, 8, 25, 43, 62, 18, 39, 61, 20, 44};
-  static const int PIL[24] = {10, 7, 11, 17, 18, 3, 5, 16, 8, 21, 24, 4, 15, 23, 19, 13, 12, 2, 20, 14, 22, 9, 6, 1};
+  // rotation offsets r[x + 5y] and the pi permutation: B[y + 5*((2x + 3y) % 5)] = rot(A[x + 5y])
+  constexpr int ROT[25] = {0, 1, 62, 28, 27, 36, 44, 6, 55, 20, 3, 10, 43, 25, 39, 41, 45, 15, 21, 8, 18, 2, 61, 56, 14};
+  uint64_t a[25];
+#pragma GCC unroll 25
+  for (int i = 0; i < 25; i++) a[i] = st[i];
   for (int r = 0; r < 24; r++) {
-    uint64_t bc[5];
-    for (int i = 0; i < 5; i++) bc[i] = st[i] ^ st[i + 5] ^ st[i + 10] ^ st[i + 15] ^ st[i + 20];
-    for (int i = 0; i < 5; i++) {
-      uint64_t t = bc[(i + 4) % 5] ^ rotl64(bc[(i + 1) % 5], 1);
-      for (int j = 0; j < 25; j += 5) st[j + i] ^= t;
+    uint64_t c[5], d[5], b[25];
+#pragma GCC unroll 5
+    for (int x = 0; x < 5; x++) c[x] = a[x] ^ a[x + 5] ^ a[x + 10] ^ a[x + 15] ^ a[x + 20];
+#pragma GCC unroll 5
+    for (int x = 0; x < 5; x++) d[x] = c[(x + 4) % 5] ^ rotl64(c[(x + 1) % 5], 1);
+#pragma GCC unroll 25
+    for (int i = 0; i < 25; i++) {
+      const int x = i % 5, y = i / 5;
+      b[y + 5 * ((2 * x + 3 * y) % 5)] = rotl64(a[i] ^ d[x], ROT[i]);
     }
-    uint64_t t = st[1];
-    for (int i = 0; i < 24; i++) { int j = PIL[i]; uint64_t b = st[j]; st[j] = rotl64(t, ROTC[i]); t = b; }
-    for (int j = 0; j < 25; j += 5) {
-      for (int i = 0; i < 5; i++) bc[i] = st[j + i];
-      for (int i = 0; i < 5; i++) st[j + i] ^= (~bc[(i + 1) % 5]) & bc[(i + 2) % 5];
+#pragma GCC unroll 25
+    for (int i = 0; i < 25; i++) {
+      const int x = i % 5, y5 = i - x;
+      a[i] = b[i] ^ (~b[y5 + (x + 1) % 5] & b[y5 + (x + 2) % 5]);
     }
-    st[0] ^= RC[r];
+    a[0] ^= RC[r];
   }
+#pragma GCC unroll 25
+  for (int i = 0; i < 25; i++) st[i] = a[i];
 }
 
 // SHAKE256 (used for the deterministic synthetic blinding streams of tests/bench)

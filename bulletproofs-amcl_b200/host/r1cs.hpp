@@ -175,6 +175,21 @@ class Prover : public ConstraintSystem<C> {
     return OK;
   }
 
+  // m calls of commit() with ONE device launch: V_j = commit_to_field_element(g, h, v_j, blinding_j), appended to the
+  // transcript in order -- byte-identical to calling commit() m times (prover.rs:119-129).
+  int commit_vec(const std::vector<FE>& v, const std::vector<FE>& v_blinding, std::vector<G1<C>>* V, std::vector<Variable>* vars) {
+    int rc = commit_batch<C>(ctx_, g_, h_, v, v_blinding, V);
+    if (rc) return rc;
+    vars->clear();
+    for (size_t j = 0; j < v.size(); j++) {
+      vars->push_back(Variable::committed(v_.size()));
+      v_.push_back(v[j]);
+      v_blinding_.push_back(v_blinding[j]);
+      TP::commit_point(transcript_, "V", (*V)[j]);
+    }
+    return OK;
+  }
+
   size_t num_constraints() const { return constraints_.size(); }     // prover.rs:595-597
   size_t num_multipliers() const { return a_O_.size(); }             // prover.rs:599-601
 
@@ -230,6 +245,7 @@ class Prover : public ConstraintSystem<C> {
 
   // prover.rs:322-593.  G, H are device-resident generator tables of length >= padded_n.
   int prove(const G1Vector<C>& G, const G1Vector<C>& H, R1CSProof<C>* proof) {
+    Trace tr("prove");
     transcript_.append_u64("m", v_.size());                            // :327
     const size_t n1 = a_L_.size();
     if (G.len() < n1 || H.len() < n1) return E_INVALID_GENERATORS_LENGTH;   // :332-334
@@ -241,6 +257,7 @@ class Prover : public ConstraintSystem<C> {
     // first-phase witness on the device; the same vectors later feed the polynomial kernels
     FieldElementVector<C> d_aL, d_aR, d_aO, d_sL, d_sR;
     if ((rc = phase_commit(G, H, 0, n1, s_L, s_R, i_blinding1, o_blinding1, s_blinding1, &proof->A_I1, &proof->A_O1, &proof->S1))) return rc;
+    tr.mark("A_I1 A_O1 S1");
     TP::commit_point(transcript_, "A_I1", proof->A_I1);                // :364-366
     TP::commit_point(transcript_, "A_O1", proof->A_O1);
     TP::commit_point(transcript_, "S1", proof->S1);
@@ -270,6 +287,7 @@ class Prover : public ConstraintSystem<C> {
     const FE z = TP::challenge_scalar(transcript_, "z");
     std::vector<FE> wL, wR, wO, wV;
     flattened_constraints(z, &wL, &wR, &wO, &wV);                      // :441
+    tr.mark("flattened_constraints");
 
     // l(x), r(x) coefficient vectors on the device (:458-486)
     FieldElementVector<C> d_wL, d_wR, d_wO;
@@ -290,14 +308,16 @@ class Prover : public ConstraintSystem<C> {
     uint8_t tb[6 * C::MODBYTES];
     if ((rc = bpgpu_fr_poly3_special_inner_product(ctx_, l1.handle(), d_aO.handle(), d_sL.handle(), r0.handle(), r1.handle(), r3.handle(), n, tb)))
       return rc;
+    tr.mark("polys + t_poly");
     FE t[7];
     for (int k = 1; k <= 6; k++) t[k] = FE::from_bytes(tb + (k - 1) * C::MODBYTES);
     FE tb_[7];
     tb_[1] = rng_.next(); tb_[3] = rng_.next(); tb_[4] = rng_.next(); tb_[5] = rng_.next(); tb_[6] = rng_.next();   // :490-494
-    if ((rc = commit_to_field_element(ctx_, g_, h_, t[1], tb_[1], &proof->T_1)) || (rc = commit_to_field_element(ctx_, g_, h_, t[3], tb_[3], &proof->T_3)) ||
-        (rc = commit_to_field_element(ctx_, g_, h_, t[4], tb_[4], &proof->T_4)) || (rc = commit_to_field_element(ctx_, g_, h_, t[5], tb_[5], &proof->T_5)) ||
-        (rc = commit_to_field_element(ctx_, g_, h_, t[6], tb_[6], &proof->T_6)))
-      return rc;                                                       // :496-500
+    {                                                                  // T_i = commit_to_field_element(g, h, t_i, blinding_i)  :496-500
+      std::vector<G1<C>> T;
+      if ((rc = commit_batch<C>(ctx_, g_, h_, {t[1], t[3], t[4], t[5], t[6]}, {tb_[1], tb_[3], tb_[4], tb_[5], tb_[6]}, &T))) return rc;
+      proof->T_1 = T[0]; proof->T_3 = T[1]; proof->T_4 = T[2]; proof->T_5 = T[3]; proof->T_6 = T[4];
+    }
     TP::commit_point(transcript_, "T_1", proof->T_1);                  // :502-506
     TP::commit_point(transcript_, "T_3", proof->T_3);
     TP::commit_point(transcript_, "T_4", proof->T_4);
@@ -319,7 +339,7 @@ class Prover : public ConstraintSystem<C> {
     TP::commit_scalar(transcript_, "e_blinding", proof->e_blinding);
     const FE w = TP::challenge_scalar(transcript_, "w");               // :549
     G1<C> Q;
-    if ((rc = scalar_mul(ctx_, g_, w, &Q))) return rc;                 // :550
+    if ((rc = scalar_mul_fixed<C>(ctx_, g_, h_, w, &Q))) return rc;       // :550
     // l_vec, r_vec (with padding), G_factors, H_factors on the device (:526-535, :552-563)
     uint8_t xb[C::MODBYTES], ub[C::MODBYTES];
     x.to_bytes(xb);
@@ -328,9 +348,12 @@ class Prover : public ConstraintSystem<C> {
     if ((rc = bpgpu_r1cs_prover_eval(ctx_, n, n1, padded_n, l1.handle(), d_aO.handle(), d_sL.handle(), r0.handle(), r1.handle(), r3.handle(), xb,
                                      ub, yb, &h_lv, &h_rv, &h_gf, &h_hf)))
       return rc;
+    tr.mark("T, Q, eval");
     FieldElementVector<C> l_vec = FieldElementVector<C>::adopt(ctx_, h_lv), r_vec = FieldElementVector<C>::adopt(ctx_, h_rv),
                           G_factors = FieldElementVector<C>::adopt(ctx_, h_gf), H_factors = FieldElementVector<C>::adopt(ctx_, h_hf);
-    return IPP<C>::create_ipp(ctx_, transcript_, Q, G_factors, H_factors, G, 0, H, 0, l_vec, r_vec, padded_n, &proof->ipp_proof);   // :565-574
+    rc = IPP<C>::create_ipp(ctx_, transcript_, Q, G_factors, H_factors, G, 0, H, 0, l_vec, r_vec, padded_n, &proof->ipp_proof);   // :565-574
+    tr.mark("create_ipp");
+    return rc;
   }
 
  private:
@@ -531,6 +554,7 @@ class Verifier : public ConstraintSystem<C> {
   int verification_msm(const R1CSProof<C>& proof, const G1<C>& g, const G1<C>& h, const G1Vector<C>& G, const G1Vector<C>& H, const FE& rnd,
                        bool* is_identity) {
     const size_t mb = C::MODBYTES;
+    Trace tr("verify");
     transcript_.append_u64("m", V_.size());                            // :279
     const size_t n1 = num_vars_;
     TP::commit_point(transcript_, "A_I1", proof.A_I1);                 // :282-284
@@ -559,7 +583,9 @@ class Verifier : public ConstraintSystem<C> {
     const FE w = TP::challenge_scalar(transcript_, "w");               // :323
     std::vector<FE> wL, wR, wO, wV;
     FE wc;
+    tr.mark("transcript");
     flattened_constraints(z, &wL, &wR, &wO, &wV, &wc);                 // :325
+    tr.mark("flattened_constraints");
     const FE a = proof.ipp_proof.a, b = proof.ipp_proof.b;
 
     // IPP challenges (transcript replay, host) and the s vector (device)  (:354-360)
@@ -567,6 +593,7 @@ class Verifier : public ConstraintSystem<C> {
     FieldElementVector<C> s;
     if ((rc = IPP<C>::verification_scalars(ctx_, proof.ipp_proof.L, proof.ipp_proof.R, padded_n, transcript_, &u_sq, &u_inv_sq, &s))) return rc;
 
+    tr.mark("ipp scalars");
     // g_scalars | h_scalars and delta on the device (:341-390)
     FieldElementVector<C> d_wL, d_wR, d_wO;
     if ((rc = FieldElementVector<C>::from_host(ctx_, wL, &d_wL)) || (rc = FieldElementVector<C>::from_host(ctx_, wR, &d_wR)) ||
@@ -581,6 +608,7 @@ class Verifier : public ConstraintSystem<C> {
     FieldElementVector<C> gh = FieldElementVector<C>::adopt(ctx_, h_gh);
     const FE delta = FE::from_bytes(deltab);
 
+    tr.mark("verifier_scalars");
     // the fixed scalars of arg1 (:392-429)
     const FE xx = x.square(), xxx = x * xx;
     const FE r_xx = rnd * xx;
@@ -611,6 +639,7 @@ class Verifier : public ConstraintSystem<C> {
     };
     G1<C> res;
     if ((rc = bpgpu_msm_parts(ctx_, parts, 4, res.xy))) return rc;
+    tr.mark("msm");
     *is_identity = res.is_identity();
     return OK;
   }

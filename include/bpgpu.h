@@ -46,6 +46,7 @@ typedef struct bpgpu_ctx bpgpu_ctx;
 typedef struct bpgpu_points bpgpu_points;   /* device-resident G1Vector (affine, Montgomery form) */
 typedef struct bpgpu_scalars bpgpu_scalars; /* device-resident FieldElementVector (Montgomery form) */
 typedef struct bpgpu_ipp bpgpu_ipp;         /* device-resident state of one create_ipp run */
+typedef struct bpgpu_fixed_bases bpgpu_fixed_bases; /* window tables of a few fixed bases, e.g. the Pedersen pair (g, h) */
 
 const char* bpgpu_strerror(int code);
 int bpgpu_modbytes(int curve);              /* amcl_wrapper::constants::MODBYTES */
@@ -110,6 +111,17 @@ typedef struct bpgpu_msm_part {
 int bpgpu_msm_parts(bpgpu_ctx* ctx, const bpgpu_msm_part* parts, size_t nparts, uint8_t* out_xy);
 /* window width the MSM would use for n terms (reporting only) */
 int bpgpu_msm_window_bits(size_t n);
+
+/* ---- fixed-base commitments ----------------------------------------------------------------------
+ * Replaces commitment::commit_to_field_element(g, h, v, r) = g.binary_scalar_mul(h, v, r) and `g * w`
+ * (prover.rs:123 V_i, :496-500 T_1..T_6, :550 Q = g*w; gadgets/poseidon_hash.rs:49-62) for bases that are reused:
+ * create builds T[j][w][d] = d * 2^(4w) * B_j once (k bases, k <= 64); commit then evaluates `count` independent
+ * combinations out_i = sum_j s[i*k + j] * B_j in one launch with no doublings.  bpgpu_fixed_bases_get returns a table
+ * cached inside the ctx (built on first use; valid until the ctx is destroyed or 16 newer tables evict it). */
+int bpgpu_fixed_bases_create(bpgpu_ctx* ctx, const uint8_t* bases_xy, size_t k, bpgpu_fixed_bases** out);
+int bpgpu_fixed_bases_get(bpgpu_ctx* ctx, const uint8_t* bases_xy, size_t k, bpgpu_fixed_bases** out);
+int bpgpu_fixed_bases_commit(bpgpu_ctx* ctx, bpgpu_fixed_bases* fb, const uint8_t* scalars_be, size_t count, uint8_t* out_xy);
+void bpgpu_fixed_bases_free(bpgpu_fixed_bases* fb);
 
 /* ---- FieldElementVector algebra on device-resident vectors ------------------------------------
  * Replaces FieldElementVector::{new_vandermonde_vector, hadamard_product, plus, scaled_by,

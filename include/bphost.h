@@ -70,6 +70,21 @@ int bph_range_verify(bpgpu_ctx* ctx, const char* transcript_label, const uint8_t
                      const bpgpu_points* H, size_t m, size_t bits, const uint8_t* proof, size_t len, const uint8_t* comms_xy,
                      const uint8_t* verifier_r_be);
 
+/* ---- batches of independent proofs (BASELINE.json config 5; throughput runs of configs 1-3) -----------------
+ * The reference verifies one proof per Verifier::verify call (verifier.rs:267) and has no batch API; per-proof verdicts are
+ * kept (proofs are NOT merged with random weights).  `count` proofs are spread over `nctx` contexts of ONE device, one host
+ * thread per context (a context = one CUDA stream), all sharing the generator tables G, H.  Proof i uses values
+ * values[i*m .. i*m+m), blinding seed seed+i (rng_mode 1) and the transcript label given.  Proofs are fixed-size records of
+ * `proof_stride` bytes (bph_range_proof_len), commitments m*2*MODBYTES bytes each.
+ * verdicts[i] = 0 (Ok), or the negative error code of proof i (BPGPU_E_VERIFY = VerificationError). */
+size_t bph_range_proof_len(int curve, size_t m, size_t bits);
+int bph_range_prove_many(bpgpu_ctx* const* ctxs, size_t nctx, const char* transcript_label, const uint8_t* g_xy, const uint8_t* h_xy,
+                         const bpgpu_points* G, const bpgpu_points* H, const uint64_t* values, size_t count, size_t m, size_t bits,
+                         int rng_mode, uint64_t seed, uint8_t* proofs, size_t proof_stride, uint8_t* comms_xy);
+int bph_range_verify_many(bpgpu_ctx* const* ctxs, size_t nctx, const char* transcript_label, const uint8_t* g_xy, const uint8_t* h_xy,
+                          const bpgpu_points* G, const bpgpu_points* H, size_t count, size_t m, size_t bits, const uint8_t* proofs,
+                          size_t proof_stride, const uint8_t* comms_xy, int32_t* verdicts);
+
 #ifdef __cplusplus
 }
 #endif

@@ -158,3 +158,28 @@ def test_range_proof_matches_oracle(which, ctx_bls, ctx_bn):
     dG, dH = ctx.get_generators("G", 16), ctx.get_generators("H", 16)
     proof, cb = ctx.range_prove(b"Range", gx, hx, dG, dH, [5, 300], 8, seed=9)
     assert ctx.range_verify(b"Range", gx, hx, dG, dH, 2, 8, proof, cb) is False
+
+
+def test_batch_prove_verify_keeps_per_proof_verdicts(bp, ctx_bls):
+    """BASELINE config 5 at reduced size: independent range proofs spread over several contexts (host threads / CUDA
+    streams) sharing one generator table; every proof keeps its own verdict (verifier.rs:267 has no batch API)."""
+    C = curve_of(ctx_bls)
+    ctxs = [ctx_bls] + [bp.Context(bp.BLS12_381, 0) for _ in range(2)]
+    bits, m, count = 8, 1, 12
+    dG, dH = ctx_bls.get_generators("G", m * bits), ctx_bls.get_generators("H", m * bits)
+    gx, hx = ctx_bls.g1_from_msg_hash(b"g"), ctx_bls.g1_from_msg_hash(b"h")
+    values = [(37 * i + 5) % 256 for i in range(count)]
+    proofs, stride, comms = bp.range_prove_many(ctxs, b"Batch", gx, hx, dG, dH, values, m, bits, seed=100)
+    assert stride == 11 * 97 + 3 * 48 + 2 * 3 * 97 + 2 * 48
+    # proof i is exactly what a single call with seed 100+i produces
+    for i in (0, 7):
+        p1, c1 = ctx_bls.range_prove(b"Batch", gx, hx, dG, dH, [values[i]], bits, seed=100 + i)
+        assert p1 == proofs[i * stride:(i + 1) * stride] and c1 == comms[i * 2 * 48:(i + 1) * 2 * 48]
+    assert bp.range_verify_many(ctxs, b"Batch", gx, hx, dG, dH, count, m, bits, proofs, stride, comms) == [0] * count
+    bad = bytearray(proofs)
+    bad[5 * stride + 11 * 97 + 47] ^= 1            # t_x of proof 5
+    bad[9 * stride] = 5                            # point tag of proof 9 -> FormatError
+    v = bp.range_verify_many(ctxs, b"Batch", gx, hx, dG, dH, count, m, bits, bytes(bad), stride, comms)
+    assert v == [0, 0, 0, 0, 0, -4, 0, 0, 0, -5, 0, 0]
+    for c in ctxs[1:]:
+        c.close()

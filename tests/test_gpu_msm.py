@@ -106,3 +106,22 @@ def test_msm_large_structured(which, lg, ctx_bls, ctx_bn):
         tot = sum(a * b for a, b in zip(s, ks)) % C.r
         assert ctx.msm(dp, enc_scalars(C, s)) == C.g1_xy_bytes(C.mul(G, tot)), (which, lg, mix)
     dp.free()
+
+
+@pytest.mark.parametrize("which", ["bls", "bn"])
+def test_fixed_base_commitments(which, ctx_bls, ctx_bn):
+    """commit_to_field_element(g, h, v, r) = v*g + r*h (prover.rs:123,496-500) and g*w (prover.rs:550) through the cached
+    window tables, incl. zero scalars (identity result), r-1 and a 3-base table."""
+    ctx = ctx_bls if which == "bls" else ctx_bn
+    C = curve_of(ctx)
+    g, h, k3 = C.g1_from_msg_hash(b"g"), C.g1_from_msg_hash(b"h"), C.g1_from_msg_hash(b"third")
+    pairs = [(0, 0), (1, 0), (0, 1), (C.r - 1, C.r - 1), (5, C.r - 5), (15, 16), (1 << 252, (1 << 253) + 12345)]
+    pairs += [(C.synth_scalar(8, 2 * i), C.synth_scalar(8, 2 * i + 1)) for i in range(9)]
+    sb = b"".join(C.fr_to_bytes(v) + C.fr_to_bytes(r) for v, r in pairs)
+    for _ in range(2):                                              # second call hits the ctx cache
+        got = ctx.commit_batch(enc_points(C, [g, h]), sb, len(pairs))
+        assert got == enc_points(C, [C.binary_scalar_mul(g, h, v, r) for v, r in pairs])
+    trip = [(C.synth_scalar(9, 3 * i), C.synth_scalar(9, 3 * i + 1), C.synth_scalar(9, 3 * i + 2)) for i in range(4)]
+    got = ctx.commit_batch(enc_points(C, [g, h, k3]), b"".join(b"".join(C.fr_to_bytes(x) for x in t) for t in trip), len(trip))
+    assert got == enc_points(C, [C.msm([g, h, k3], list(t)) for t in trip])
+    assert ctx.commit_batch(enc_points(C, [g, h]), b"", 0) == b""
