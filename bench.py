@@ -112,6 +112,81 @@ class ClockSampler:
                 "reasons": reasons, "samples": len(sm)}
 
 
+def ncu_traffic_bytes():
+    """dram__bytes_read.sum + dram__bytes_write.sum of k_chunk_acc per launch, from the committed `ncu --set full` capture
+    of this same command (profiles/k_chunk_acc_r01_raw.csv); None if the capture is missing."""
+    import csv
+    path = os.path.join(ROOT, "profiles", "k_chunk_acc_r01_raw.csv")
+    try:
+        rows = list(csv.reader(open(path)))
+        hdr, units, vals = rows[0], rows[1], rows[2]
+        scale = {"byte": 1, "Kbyte": 1e3, "Mbyte": 1e6, "Gbyte": 1e9}
+        tot = 0.0
+        for name in ("dram__bytes_read.sum", "dram__bytes_write.sum"):
+            i = hdr.index(name)
+            tot += float(vals[i]) * scale[units[i]]
+        return tot
+    except Exception:
+        return None
+
+
+def proof_section(bp, ctx, local, rank, world, dist, torch):
+    """IPP / R1CS prove+verify proofs/s (BASELINE.json metric, second half) through the host layer (include/bphost.h).
+    Independent proofs are spread over `nctx` contexts (one host thread + one CUDA stream each) of this rank's GPU; with N
+    ranks the batch-verification job is sharded by proofs and the verdict bytes are all-gathered over NCCL."""
+    import numpy as np
+    ncpu = os.cpu_count() or 1
+    nctx = max(1, min(16, ncpu // max(1, world)))
+    out = {"contexts_per_gpu": nctx, "host_cpus": ncpu}
+
+    def run(curve, m, bits, count, tag, verify_reps=1):
+        ctxs = [bp.Context(curve, local) for _ in range(nctx)]
+        c0 = ctxs[0]
+        gx, hx = c0.g1_from_msg_hash(b"g"), c0.g1_from_msg_hash(b"h")
+        n = m * bits
+        G, H = c0.get_generators("G", n), c0.get_generators("H", n)
+        rng = np.random.default_rng(4242 + rank)
+        vals = [int(x) for x in rng.integers(0, 1 << 63, size=count * m, dtype=np.uint64)]
+        bp.range_prove_many(ctxs, b"bench", gx, hx, G, H, vals[:m * min(count, 2 * nctx)], m, bits)      # warm-up
+        if dist is not None:
+            dist.barrier()
+        t0 = time.perf_counter()
+        proofs, stride, comms = bp.range_prove_many(ctxs, b"bench", gx, hx, G, H, vals, m, bits)
+        tp = time.perf_counter() - t0
+        bp.range_verify_many(ctxs, b"bench", gx, hx, G, H, min(count, 2 * nctx), m, bits, proofs, stride, comms)
+        if dist is not None:
+            dist.barrier()
+        t0 = time.perf_counter()
+        ok = True
+        for _ in range(verify_reps):
+            v = bp.range_verify_many(ctxs, b"bench", gx, hx, G, H, count, m, bits, proofs, stride, comms)
+            ok = ok and v == [0] * count
+        tv = time.perf_counter() - t0
+        if dist is not None:
+            # the exchange step of the sharded batch verification: verdict bytes of every rank, all-gathered
+            t = torch.tensor([1 if ok else 0] * count, dtype=torch.uint8, device="cuda")
+            allv = torch.empty(world * count, dtype=torch.uint8, device="cuda")
+            dist.all_gather_into_tensor(allv, t)
+            ok = bool(allv.min().item() == 1)
+            tt = torch.tensor([tp, tv], device="cuda", dtype=torch.float64)
+            dist.all_reduce(tt, op=dist.ReduceOp.MAX)
+            tp, tv = float(tt[0].item()), float(tt[1].item())
+        for c in ctxs:
+            c.close()
+        out[tag] = {"multipliers": n, "committed_values": m, "proofs": count * world, "prove_per_s": count * world / tp,
+                    "verify_per_s": count * world * verify_reps / tv, "verifications": count * world * verify_reps,
+                    "prove_verify_per_s": count * world / (tp + tv / verify_reps), "all_verified": ok, "proof_bytes": stride}
+
+    # config 5 unit / config 1 size: one 64-bit range proof = 64 multipliers, IPP of length 64; 4096 verifications in total
+    per_rank = max(nctx, 512 // world)
+    run(bp.BLS12_381, 1, 64, per_rank, "range64_bls12_381_n64", verify_reps=max(1, 4096 // (per_rank * world)))
+    # config 2: 16 x 64-bit values in one constraint system, 1024 generators
+    run(bp.BLS12_381, 16, 64, max(nctx, 64 // world), "range64x16_bls12_381_n1024")
+    # config 3: 2^14 multipliers on BN254 (256 x 64-bit values)
+    run(bp.BN254, 256, 64, max(nctx, 16 // world), "range64x256_bn254_n16384")
+    return out
+
+
 def cpu_reference(lg_sample, threads, curve_id=0, seed=5):
     """Time the oracle's Straus/wNAF-5 MSM (the reference's CPU algorithm) on 2^lg_sample points."""
     from oracle import cref
@@ -157,6 +232,7 @@ def main():
     ap.add_argument("--impl", default="ours")
     ap.add_argument("--ref-lg", type=int, default=18)
     ap.add_argument("--no-cpu-baseline", action="store_true")
+    ap.add_argument("--no-proofs", action="store_true", help="skip the IPP / R1CS proofs-per-second section")
     args = ap.parse_args()
     if args.impl == "reference":
         return run_reference(args)
@@ -193,16 +269,13 @@ def main():
         ctypes.memmove(q, sc_np[s].ctypes.data, sc_np[s].nbytes)
         hs.append(q)
 
-    ones = (1).to_bytes(mb, "big") * world
+    from bulletproofs_amcl_b200 import sharding
 
     def combine(partial_xy):
-        """N>1: all-gather the 2*MODBYTES-byte partial sums over NCCL, add them on every rank."""
+        """N>1: all-gather the 2*MODBYTES-byte partial sums over NCCL, add them on every rank (sharding.py)."""
         if world == 1:
             return partial_xy
-        t = torch.frombuffer(bytearray(partial_xy), dtype=torch.uint8).cuda()
-        out = torch.empty(world * t.numel(), dtype=torch.uint8, device="cuda")
-        dist.all_gather_into_tensor(out, t)
-        return ctx.msm_refs(out.cpu().numpy().tobytes(), ones)
+        return sharding.combine_partials(ctx, sharding.allgather_bytes(dist, partial_xy))
 
     def step_resident(i):
         return combine(ctx.msm_device(dpts[i % NSETS], dsc[i % NSETS], n=n))
@@ -220,7 +293,7 @@ def main():
         torch.cuda.synchronize()
         l0 = ctx.launches
         if profile:
-            ctx.set_profile(True)
+            ctx.set_profile(n)          # only the 2^lg-term MSMs, not the N-term combine of the multi-GPU path
         e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
         t0 = time.perf_counter()
         e0.record(stream)
@@ -233,7 +306,7 @@ def main():
         ms = max(e0.elapsed_time(e1), wall_ms)     # the host finish sits between kernels: never under-report
         stages = ctx.msm_stage_ms() if profile else None
         if profile:
-            ctx.set_profile(False)
+            ctx.set_profile(0)
         if world > 1:
             t = torch.tensor([ms], device="cuda", dtype=torch.float64)
             dist.all_reduce(t, op=dist.ReduceOp.MAX)
@@ -254,6 +327,8 @@ def main():
     a = ctx.msm_device(dpts[0], dsc[0], n=n)
     b = ctx.msm_refs(hp[0], hs[0], n=n)
     assert a == b, "resident and host-buffer MSM disagree"
+
+    proofs = None if args.no_proofs else proof_section(bp, ctx, local, rank, world, dist, torch)
 
     if rank == 0:
         c = bp.lib().bpgpu_msm_window_bits(n)
@@ -285,13 +360,16 @@ def main():
                          "hbm": {"achieved_GBps": alg_bytes / (k_ms * 1e-3) / 1e9, "algorithmic_bytes": alg_bytes}},
             "stages_ms": stages,
         }
+        if proofs is not None:
+            out["proofs"] = proofs
+        out["roofline"]["traffic"] = ncu_traffic_bytes()
         if world == 1 and not args.no_cpu_baseline:
             cores = os.cpu_count() or 1
-            v1, dt1 = cpu_reference(15, 1)
-            vN, dtN = cpu_reference(19, cores)
+            v1, dt1 = cpu_reference(16, 1)
+            vN, dtN = cpu_reference(args.lg, cores)
             out["cpu_baseline"] = {"value": vN, "unit": UNIT, "cores": cores, "kind": "port",
-                                   "sample": f"Straus wNAF-5 (oracle/c) on 2^19 of the 2^{args.lg} points, {cores} threads, {dtN:.1f} s",
-                                   "single_core": {"value": v1, "cores": 1, "sample": f"2^15 points, {dt1:.1f} s"}}
+                                   "sample": f"Straus wNAF-5 (oracle/c) on all 2^{args.lg} points, {cores} threads, {dtN:.1f} s",
+                                   "single_core": {"value": v1, "cores": 1, "sample": f"2^16 points, {dt1:.1f} s"}}
         print(json.dumps(out))
     if world > 1:
         dist.destroy_process_group()

@@ -241,8 +241,9 @@ class Context:
 
     STAGES = ["digits", "scan", "scatter", "chunk_acc", "giant", "reduce_l1", "reduce_l2"]
 
-    def set_profile(self, on):
-        self._check(lib().bpgpu_ctx_set_profile(self.handle, 1 if on else 0), "set_profile")
+    def set_profile(self, min_n):
+        """record per-stage times of every MSM with at least min_n terms (0 / False = off)"""
+        self._check(lib().bpgpu_ctx_set_profile(self.handle, int(min_n)), "set_profile")
 
     def msm_stage_ms(self):
         arr = (ctypes.c_double * 8)()

@@ -427,7 +427,7 @@ int msm_run(bpgpu_ctx* ctx, const Affine<typename Curve::Fq>* d_points, const vo
   XYZZ<Fq>* segS = (XYZZ<Fq>*)b2; b2 += sz_seg;
   XYZZ<Fq>* winsum = (XYZZ<Fq>*)b2;             // [0, W): P_w   [W, 2W): Q_w
 
-  StageTimer tm(st, ctx->profile != 0);
+  StageTimer tm(st, ctx->profile != 0 && n >= (size_t)ctx->profile);   // profile = smallest n that is recorded
   BP_CUDA_OK(cudaMemsetAsync(hist, 0, sz_hist, st));
   BP_CUDA_OK(cudaMemsetAsync(giant, 0, 4, st));
 

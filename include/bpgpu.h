@@ -62,8 +62,9 @@ uint64_t bpgpu_ctx_launches(const bpgpu_ctx* ctx);
 
 /* per-stage CUDA-event timing of the MSM pipeline on the ctx stream (roofline evidence for bench.py).
  * stages: 0 digits, 1 scan, 2 scatter, 3 chunk_acc, 4 giant, 5 reduce_l1, 6 reduce_l2.
- * bpgpu_msm_stage_ms writes the average ms per stage since set_profile(1) and returns the run count. */
-int bpgpu_ctx_set_profile(bpgpu_ctx* ctx, int on);
+ * set_profile(min_n > 0) records every MSM of at least min_n terms (0 = off); bpgpu_msm_stage_ms writes the average ms
+ * per stage since then and returns the run count. */
+int bpgpu_ctx_set_profile(bpgpu_ctx* ctx, int min_n);
 int bpgpu_msm_stage_ms(const bpgpu_ctx* ctx, double* avg_ms, int cap);
 
 void* bpgpu_host_alloc(size_t bytes);       /* pinned host memory */

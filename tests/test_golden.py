@@ -1,0 +1,123 @@
+"""Golden fixtures (tests/golden/*.json, made by tests/golden/make_golden.py from the oracle).
+
+CPU part: the oracle still reproduces the cheap fixtures (guards the checker against drift).
+GPU part: the CUDA path reproduces every fixture byte for byte, including the ones the Python oracle needs minutes for
+(BASELINE config 1: IPP n = 64; config 2: 16 x 64-bit range proof, n = 1024; config 3 reduced: BN254 n = 512)."""
+import json
+import os
+
+import pytest
+
+from oracle.curves import CURVES
+from tests.util import enc_scalars
+
+HERE = os.path.join(os.path.dirname(os.path.abspath(__file__)), "golden")
+
+
+def load(name):
+    path = os.path.join(HERE, name)
+    if not os.path.exists(path):
+        pytest.skip(f"{name} not generated")
+    return json.load(open(path))
+
+
+# ------------------------------------------------------------------ CPU: oracle vs fixtures
+def test_oracle_reproduces_generators():
+    fx = load("generators.json")
+    for cname, d in fx.items():
+        C = CURVES[cname]
+        for prefix in ("G", "H", "g", "h"):
+            assert [C.g1_xy_bytes(p).hex() for p in C.get_generators(prefix, 4)] == d[prefix]
+        assert C.g1_xy_bytes(C.g1_from_msg_hash(b"Q")).hex() == d["msg:Q"]
+
+
+def test_oracle_reproduces_small_proofs():
+    import importlib.util
+    spec = importlib.util.spec_from_file_location("make_golden", os.path.join(HERE, "make_golden.py"))
+    mg = importlib.util.module_from_spec(spec)
+    spec.loader.exec_module(mg)
+    assert mg.gen_ipp(8) == load("ipp_n8.json")
+    fx = load("bound_check_8bit.json")
+    for cname, d in fx.items():
+        assert mg.gen_bound(CURVES[cname], 8, 1) == d
+    assert mg.gen_msm() == load("msm_257.json")
+
+
+# ------------------------------------------------------------------ GPU: CUDA path vs fixtures
+def _ctx(name, ctx_bls, ctx_bn):
+    return ctx_bls if name == "BLS12_381" else ctx_bn
+
+
+@pytest.mark.gpu
+def test_gpu_generators_golden(ctx_bls, ctx_bn):
+    fx = load("generators.json")
+    for cname, d in fx.items():
+        ctx = _ctx(cname, ctx_bls, ctx_bn)
+        for prefix in ("G", "H", "g", "h"):
+            assert ctx.get_generators(prefix, 4).download().hex() == "".join(d[prefix])
+        for msg in ("g", "h", "Q", ""):
+            assert ctx.g1_from_msg_hash(msg.encode()).hex() == d["msg:" + msg]
+
+
+@pytest.mark.gpu
+def test_gpu_msm_golden(ctx_bls, ctx_bn):
+    fx = load("msm_257.json")
+    for cname, d in fx.items():
+        ctx = _ctx(cname, ctx_bls, ctx_bn)
+        C = CURVES[cname]
+        G = C.from_affine(C.g)
+        pts, cur = [], C.mul(G, 7)
+        for _ in range(d["n"]):
+            pts.append(cur)
+            cur = C.add(cur, G)
+        xy = b"".join(C.g1_xy_bytes(p) for p in pts)
+        assert ctx.msm_refs(xy, enc_scalars(C, C.synth_scalars(d["scalar_seed"], d["n"]))).hex() == d["result"]
+
+
+@pytest.mark.gpu
+@pytest.mark.parametrize("name", ["ipp_n8.json", "ipp_n64.json"])
+def test_gpu_ipp_golden(name, ctx_bls, ctx_bn):
+    fx = load(name)
+    for cname, d in fx.items():
+        ctx = _ctx(cname, ctx_bls, ctx_bn)
+        C = CURVES[cname]
+        n = d["n"]
+        dG, dH = ctx.get_generators("g", n), ctx.get_generators("h", n)
+        Q = ctx.g1_from_msg_hash(b"Q")
+        a, b = C.synth_scalars(d["a_seed"], n, b"a"), C.synth_scalars(d["a_seed"], n, b"b")
+        Gf, Hf = [1] * n, C.vandermonde(C.fr_inv(C.synth_scalar(*d["y_seed"])), n)
+        proof = ctx.ipp_create(d["label"].encode(), dG, dH, Q, enc_scalars(C, Gf), enc_scalars(C, Hf), enc_scalars(C, a), enc_scalars(C, b), n)
+        assert proof.hex() == d["proof"]
+        assert ctx.ipp_verify(d["label"].encode(), n, enc_scalars(C, Gf), enc_scalars(C, Hf), bytes.fromhex(d["P"]), Q, dG, dH, proof)
+
+
+@pytest.mark.gpu
+def test_gpu_bound_check_golden(ctx_bls, ctx_bn):
+    fx = load("bound_check_8bit.json")
+    for cname, d in fx.items():
+        ctx = _ctx(cname, ctx_bls, ctx_bn)
+        bits = d["bits"]
+        dG, dH = ctx.get_generators("G", 2 * bits), ctx.get_generators("H", 2 * bits)
+        gx, hx = ctx.g1_from_msg_hash(b"g"), ctx.g1_from_msg_hash(b"h")
+        proof, comms = ctx.bound_check_prove(d["label"].encode(), gx, hx, dG, dH, d["val"], d["lower"], d["upper"], bits, seed=d["seed"])
+        assert proof.hex() == d["proof"] and comms.hex() == d["commitments"]
+        assert ctx.bound_check_verify(d["label"].encode(), gx, hx, dG, dH, d["lower"], d["upper"], bits, proof, comms)
+
+
+@pytest.mark.gpu
+@pytest.mark.parametrize("name", ["range_small.json", "range_config5_unit.json", "range_config2.json", "range_config3_reduced.json",
+                                  "range_config3.json"])
+def test_gpu_range_proof_golden(name, ctx_bls, ctx_bn):
+    fx = load(name)
+    for _, d in fx.items():
+        ctx = _ctx(d["curve"], ctx_bls, ctx_bn)
+        m, bits = d["m"], d["bits"]
+        n = m * bits
+        N = 1 << max(0, (n - 1).bit_length())
+        dG, dH = ctx.get_generators("G", N), ctx.get_generators("H", N)
+        gx, hx = ctx.g1_from_msg_hash(b"g"), ctx.g1_from_msg_hash(b"h")
+        vals = [int(v) for v in d["values"]]
+        proof, comms = ctx.range_prove(d["label"].encode(), gx, hx, dG, dH, vals, bits, seed=d["seed"])
+        assert comms.hex() == d["commitments"]
+        assert proof.hex() == d["proof"]
+        assert ctx.range_verify(d["label"].encode(), gx, hx, dG, dH, m, bits, proof, comms)
