@@ -91,7 +91,9 @@ struct XYZZ {
   }
 
   // add-2008-s: this += q
-  BP_HD_COLD void add(const XYZZ& q) {
+  BP_HD_COLD void add(const XYZZ& q) { add_inl(q); }
+  // the same, inlined into the caller (hot loops whose operands live in registers)
+  BP_HD void add_inl(const XYZZ& q) {
     if (q.is_inf()) return;
     if (is_inf()) { *this = q; return; }
     F U1 = x * q.zz;
@@ -125,6 +127,19 @@ struct XYZZ {
     return a;
   }
 };
+
+// lane-wise select: c ? a : b  (keeps both operands in registers, no dynamic indexing)
+template <class F>
+BP_HD XYZZ<F> select(bool c, const XYZZ<F>& a, const XYZZ<F>& b) {
+  XYZZ<F> r;
+  for (int i = 0; i < F::N; i++) {
+    r.x.v[i] = c ? a.x.v[i] : b.x.v[i];
+    r.y.v[i] = c ? a.y.v[i] : b.y.v[i];
+    r.zz.v[i] = c ? a.zz.v[i] : b.zz.v[i];
+    r.zzz.v[i] = c ? a.zzz.v[i] : b.zzz.v[i];
+  }
+  return r;
+}
 
 // k * P for a small unsigned integer k (bucket-chunk offsets), double-and-add MSB first
 template <class F>

@@ -38,6 +38,7 @@ struct MsmGeom {
   int lgL1;         // log2(buckets per lane) in k_reduce_l1; a warp covers 32 << lgL1 buckets
   uint32_t nseg;    // level-1 warps (segments) per window
   int lgL2;         // log2(segments per lane) in k_reduce_l2
+  uint32_t nrows;   // row/column reduction (c >= 13): the 2^(c-1) buckets of a window form an nrows x 256 grid
 };
 
 static const int GIANT_T = 16;         // buckets with more partials than this are collapsed by k_giant
@@ -304,6 +305,49 @@ __global__ void __launch_bounds__(128) k_reduce_l1(MsmGeom g, const uint32_t* __
   if (lane == 0) { store_vec(segA + warp, acc); store_vec(segS + warp, run); }
 }
 
+
+// Variant with one merged stream of (partial | boundary) additions per lane and an inlined group law (BPGPU_L1EVENT=1).
+// Measured at 2^20: equal at 16 buckets per lane, faster at 8, never faster overall -- kept for the record.
+template <class Fq>
+__global__ void __launch_bounds__(32) k_reduce_l1_events(MsmGeom g, const uint32_t* __restrict__ pstart, const uint32_t* __restrict__ pcount,
+                                                  const XYZZ<Fq>* __restrict__ partials, XYZZ<Fq>* __restrict__ segA,
+                                                  XYZZ<Fq>* __restrict__ segS) {
+  // one warp per block: 1024 independent warps spread evenly over the SMs (no 2-vs-1 block quantisation)
+  const uint32_t warp = blockIdx.x;
+  const int lane = threadIdx.x & 31;
+  if (warp >= (uint32_t)g.W * g.nseg) return;
+  const uint32_t w = warp / g.nseg, seg = warp - w * g.nseg;
+  const uint32_t L1 = 1u << g.lgL1;
+  const uint32_t* ps = pstart + (size_t)w * (g.nbp + 1);
+  const uint32_t* pc = pcount + (size_t)w * g.nbp;
+  const XYZZ<Fq>* in = partials + (size_t)w * g.pcap;
+  const uint32_t lo = seg * 32 * L1 + (uint32_t)lane * L1 + 1;
+  XYZZ<Fq> run = XYZZ<Fq>::inf(), acc = XYZZ<Fq>::inf();
+  if (lo <= g.nbp - 1) {
+    // One stream of "events" per lane, top bucket first: every chunk partial of the bucket (run += partial), then the
+    // bucket boundary (acc += run).  Both kinds go through ONE inlined addition with lane-selected operands, so lanes
+    // whose buckets have different numbers of partials still execute the same instruction stream.
+    uint32_t b = min(lo + L1 - 1, g.nbp - 1);
+    uint32_t k0 = ps[b], k = k0 + pc[b];
+    for (;;) {
+      const bool is_partial = k > k0;
+      XYZZ<Fq> q = run;
+      if (is_partial) q = load_vec(in + (k - 1));
+      XYZZ<Fq> A = select(is_partial, run, acc);
+      A.add_inl(q);
+      run = select(is_partial, A, run);
+      acc = select(is_partial, acc, A);
+      if (is_partial) { k--; continue; }
+      if (b == lo) break;
+      b--;
+      k0 = ps[b];
+      k = k0 + pc[b];
+    }
+  }
+  warp_weighted_sum(acc, run, g.lgL1);
+  if (lane == 0) { store_vec(segA + warp, acc); store_vec(segS + warp, run); }
+}
+
 // Level 2: per window, combine the nseg segment results (one block of 64 threads per window):
 //   P_w = sum_seg segA ,  Q_w = sum_seg seg * segS ;  window sum = P_w + 2^(5+lgL1) * Q_w
 // warp 0 computes Q_w, warp 1 computes P_w.  The final shift-and-add is left to the host finish.
@@ -335,6 +379,91 @@ __global__ void __launch_bounds__(64) k_reduce_l2(MsmGeom g, const XYZZ<Fq>* __r
       if (lane < o) acc.add(t);
     }
     if (lane == 0) store_vec(winP + w, acc);
+  }
+}
+
+// ------------------------------------------------------------------------------------------
+// Row/column bucket reduction for large windows (c >= 13).
+// Write bucket number b = hi*256 + lo + 1.  Then  sum_b b*B_b = 256 * sum_hi hi*R_hi + sum_lo (lo+1)*C_lo  with the PLAIN
+// sums R_hi = sum_lo B (rows) and C_lo = sum_hi B (columns).  Plain sums have no order: they are block-wide trees, so the
+// 2^(c-1) buckets cost two additions each at full parallelism, and the only weighted (serial) sums left are over the
+// nrows + 256 row/column totals.  This replaces per-lane running sums over 16 buckets (a 60-addition dependent chain).
+template <class Fq>
+__global__ void __launch_bounds__(256) k_bucket_rows(MsmGeom g, const uint32_t* __restrict__ pstart, const uint32_t* __restrict__ pcount,
+                                                     const XYZZ<Fq>* __restrict__ partials, XYZZ<Fq>* __restrict__ D, XYZZ<Fq>* __restrict__ R) {
+  __shared__ __align__(16) unsigned char smraw[256 * sizeof(XYZZ<Fq>)];
+  XYZZ<Fq>* sm = reinterpret_cast<XYZZ<Fq>*>(smraw);
+  const uint32_t w = blockIdx.x / g.nrows, row = blockIdx.x - w * g.nrows;
+  const uint32_t idx = row * 256 + threadIdx.x;
+  const uint32_t b = idx + 1;
+  const uint32_t* ps = pstart + (size_t)w * (g.nbp + 1);
+  const uint32_t* pc = pcount + (size_t)w * g.nbp;
+  const XYZZ<Fq>* in = partials + (size_t)w * g.pcap;
+  XYZZ<Fq> acc = XYZZ<Fq>::inf();
+  const uint32_t p0 = ps[b], p1 = p0 + pc[b];
+  if (p1 > p0) {
+    acc = load_vec(in + p0);
+    for (uint32_t k = p0 + 1; k < p1; k++) { XYZZ<Fq> q = load_vec(in + k); acc.add(q); }
+  }
+  store_vec(D + (size_t)w * (g.nbp - 1) + idx, acc);
+  XYZZ<Fq> tot = block_tree_sum(acc, sm);
+  if (threadIdx.x == 0) store_vec(R + blockIdx.x, tot);
+}
+
+// column sums: a block handles 256 / nrows columns, nrows threads per column
+template <class Fq>
+__global__ void __launch_bounds__(256) k_bucket_cols(MsmGeom g, const XYZZ<Fq>* __restrict__ D, XYZZ<Fq>* __restrict__ C) {
+  __shared__ __align__(16) unsigned char smraw[256 * sizeof(XYZZ<Fq>)];
+  XYZZ<Fq>* sm = reinterpret_cast<XYZZ<Fq>*>(smraw);
+  const uint32_t cpb = 256 / g.nrows;                       // columns per block
+  const uint32_t bpw = 256 / cpb;                           // blocks per window
+  const uint32_t w = blockIdx.x / bpw, cb = blockIdx.x - w * bpw;
+  const uint32_t h = threadIdx.x % g.nrows, lo = cb * cpb + threadIdx.x / g.nrows;
+  store_vec(sm + threadIdx.x, load_vec(D + (size_t)w * (g.nbp - 1) + (size_t)h * 256 + lo));
+  __syncthreads();
+  for (uint32_t o = g.nrows / 2; o > 0; o >>= 1) {
+    if (h < o) {
+      XYZZ<Fq> a = load_vec(sm + threadIdx.x), b = load_vec(sm + threadIdx.x + o);
+      a.add(b);
+      store_vec(sm + threadIdx.x, a);
+    }
+    __syncthreads();
+  }
+  if (h == 0) store_vec(C + (size_t)w * 256 + lo, load_vec(sm + threadIdx.x));
+}
+
+// per window: win = sum_lo (lo+1)*C_lo + 2^8 * sum_hi hi*R_hi   (warp 0: columns, warp 1: rows)
+template <class Fq>
+__global__ void __launch_bounds__(64) k_rowcol_final(MsmGeom g, const XYZZ<Fq>* __restrict__ R, const XYZZ<Fq>* __restrict__ C,
+                                                     XYZZ<Fq>* __restrict__ winP, XYZZ<Fq>* __restrict__ winQ) {
+  __shared__ __align__(16) unsigned char smraw[sizeof(XYZZ<Fq>)];
+  XYZZ<Fq>* sm = reinterpret_cast<XYZZ<Fq>*>(smraw);
+  const uint32_t w = blockIdx.x;
+  const int lane = threadIdx.x & 31, wid = threadIdx.x >> 5;
+  const XYZZ<Fq>* src = wid == 0 ? C + (size_t)w * 256 : R + (size_t)w * g.nrows;
+  const uint32_t cnt = wid == 0 ? 256u : g.nrows;
+  int lgL = 0;
+  while ((32u << lgL) < cnt) lgL++;
+  const uint32_t L = 1u << lgL, lo = (uint32_t)lane * L;
+  XYZZ<Fq> run = XYZZ<Fq>::inf(), acc = XYZZ<Fq>::inf();
+  if (lo < cnt) {
+    const uint32_t hi = min(lo + L, cnt);
+    for (uint32_t s = hi; s-- > lo;) { XYZZ<Fq> q = load_vec(src + s); run.add(q); acc.add(run); }
+  }
+  warp_weighted_sum(acc, run, lgL);           // lane 0: acc = sum (i+1)*X_i, run = sum X_i
+  if (wid == 1 && lane == 0) {
+    XYZZ<Fq> neg = run.neg();
+    acc.add(neg);                             // weights hi = (i+1) - 1
+#pragma unroll 1
+    for (int k = 0; k < 8; k++) acc.dbl();
+    store_vec(sm, acc);
+  }
+  __syncthreads();
+  if (wid == 0 && lane == 0) {
+    XYZZ<Fq> q = load_vec(sm);
+    acc.add(q);
+    store_vec(winP + w, acc);
+    store_vec(winQ + w, XYZZ<Fq>::inf());
   }
 }
 
@@ -381,12 +510,22 @@ int msm_run(bpgpu_ctx* ctx, const Affine<typename Curve::Fq>* d_points, const vo
   MsmGeom g;
   g.n = (uint32_t)n;
   g.c = msm_window_bits(n);
+  // tuning overrides for tools/msm_sweep.py (unset in normal use)
+  static const char* env_c = getenv("BPGPU_C");
+  static const char* env_s = getenv("BPGPU_S");
+  static const char* env_l1 = getenv("BPGPU_LGL1");
+  static const char* env_rc = getenv("BPGPU_ROWCOL");
+  if (env_c) g.c = atoi(env_c);
   g.W = (Curve::SCALAR_BITS + 1 + g.c - 1) / g.c;
   g.nbp = (1u << (g.c - 1)) + 1;
   {
-    // about one chunk per average bucket: every bucket then has ~2 partial sums
-    uint64_t s = (uint64_t)n >> (g.c - 1);
+    // Chunk length: long enough that a bucket is split into few partial sums (the reduction reads them all), short enough
+    // that W*n/S chunk threads still fill the machine (a chunk is a serial chain of S mixed additions, ~10 us each).
+    // Measured at 2^20 (tools/msm_sweep.py): S = 64 beats 32 by 5 %; 96 and 128 lose in k_chunk_acc.
+    uint64_t fill = ((uint64_t)g.W * n) / ((uint64_t)ctx->sm_count * 8 * 32);
+    uint64_t s = fill;
     g.S = (uint32_t)(s < 4 ? 4 : (s > 64 ? 64 : s));
+    if (env_s) g.S = (uint32_t)atoi(env_s);
   }
   g.nchunk = (g.n + g.S - 1) / g.S;
   g.pcap = g.nchunk + g.nbp;
@@ -394,11 +533,13 @@ int msm_run(bpgpu_ctx* ctx, const Affine<typename Curve::Fq>* d_points, const vo
     uint32_t nb = g.nbp - 1;                       // 2^(c-1)
     int lg = 0;                                    // buckets per lane: up to 16, but keep >= ~600 warps busy
     while ((32u << (lg + 1)) <= nb && lg < 4 && ((uint64_t)g.W * nb >> (lg + 1 + 5)) >= 600) lg++;
+    if (env_l1) lg = atoi(env_l1);
     g.lgL1 = lg;
     g.nseg = (nb + (32u << lg) - 1) / (32u << lg);
     int lg2 = 0;
     while ((32u << lg2) < g.nseg) lg2++;
     g.lgL2 = lg2;
+    g.nrows = (env_rc && atoi(env_rc) && g.c >= 13) ? nb / 256 : 0;   // experimental row/column reduction (slower: see DESIGN.md)
   }
 
   // ---- scratch layout
@@ -420,12 +561,17 @@ int msm_run(bpgpu_ctx* ctx, const Affine<typename Curve::Fq>* d_points, const vo
   const size_t sz_part = align256((size_t)g.W * g.pcap * sizeof(XYZZ<Fq>));
   const size_t sz_seg = align256((size_t)g.W * g.nseg * sizeof(XYZZ<Fq>));
   const size_t sz_wsum = align256((size_t)2 * g.W * sizeof(XYZZ<Fq>));
-  if ((rc = ctx->msm_b.reserve(sz_part + 2 * sz_seg + sz_wsum))) return rc;
+  const size_t sz_dense = g.nrows ? align256((size_t)g.W * (g.nbp - 1) * sizeof(XYZZ<Fq>)) : 0;   // bucket sums D
+  const size_t sz_rc = g.nrows ? align256((size_t)g.W * (g.nrows + 256) * sizeof(XYZZ<Fq>)) : 0;   // row and column totals
+  if ((rc = ctx->msm_b.reserve(sz_part + 2 * sz_seg + sz_wsum + sz_dense + sz_rc))) return rc;
   uint8_t* b2 = (uint8_t*)ctx->msm_b.p;
   XYZZ<Fq>* partials = (XYZZ<Fq>*)b2; b2 += sz_part;
   XYZZ<Fq>* segA = (XYZZ<Fq>*)b2; b2 += sz_seg;
   XYZZ<Fq>* segS = (XYZZ<Fq>*)b2; b2 += sz_seg;
-  XYZZ<Fq>* winsum = (XYZZ<Fq>*)b2;             // [0, W): P_w   [W, 2W): Q_w
+  XYZZ<Fq>* winsum = (XYZZ<Fq>*)b2; b2 += sz_wsum;             // [0, W): P_w   [W, 2W): Q_w
+  XYZZ<Fq>* dense = (XYZZ<Fq>*)b2; b2 += sz_dense;
+  XYZZ<Fq>* rowsum = (XYZZ<Fq>*)b2;
+  XYZZ<Fq>* colsum = rowsum + (size_t)g.W * g.nrows;
 
   StageTimer tm(st, ctx->profile != 0 && n >= (size_t)ctx->profile);   // profile = smallest n that is recorded
   BP_CUDA_OK(cudaMemsetAsync(hist, 0, sz_hist, st));
@@ -450,15 +596,26 @@ int msm_run(bpgpu_ctx* ctx, const Affine<typename Curve::Fq>* d_points, const vo
   }
   k_giant<Fq><<<ctx->sm_count * 2, GIANT_BLOCK, 0, st>>>(g, pstart, hist, partials, giant, giant + 1);
   tm.mark("giant");
-  {
-    uint32_t warps = (uint32_t)g.W * g.nseg;
-    k_reduce_l1<Fq><<<(warps * 32 + 127) / 128, 128, 0, st>>>(g, pstart, hist, partials, segA, segS);
+  int qshift = 5 + g.lgL1;
+  if (g.nrows) {
+    k_bucket_rows<Fq><<<g.W * g.nrows, 256, 0, st>>>(g, pstart, hist, partials, dense, rowsum);
+    k_bucket_cols<Fq><<<g.W * g.nrows, 256, 0, st>>>(g, dense, colsum);
     tm.mark("reduce_l1");
+    k_rowcol_final<Fq><<<g.W, 64, 0, st>>>(g, rowsum, colsum, winsum, winsum + g.W);
+    tm.mark("reduce_l2");
+    ctx->launches++;
+    qshift = 0;
+  } else {
+    uint32_t warps = (uint32_t)g.W * g.nseg;
+    static const char* env_ev = getenv("BPGPU_L1EVENT");
+    if (env_ev && atoi(env_ev)) k_reduce_l1_events<Fq><<<warps, 32, 0, st>>>(g, pstart, hist, partials, segA, segS);
+    else k_reduce_l1<Fq><<<(warps * 32 + 127) / 128, 128, 0, st>>>(g, pstart, hist, partials, segA, segS);
+    tm.mark("reduce_l1");
+    k_reduce_l2<Fq><<<g.W, 64, 0, st>>>(g, segA, segS, winsum, winsum + g.W);
+    tm.mark("reduce_l2");
   }
-  k_reduce_l2<Fq><<<g.W, 64, 0, st>>>(g, segA, segS, winsum, winsum + g.W);
-  tm.mark("reduce_l2");
   ctx->launches += 7;
-  res->W = g.W; res->c = g.c; res->qshift = 5 + g.lgL1; res->d_winsum = winsum;
+  res->W = g.W; res->c = g.c; res->qshift = qshift; res->d_winsum = winsum;
   int lrc = launch_check(ctx, "msm");
   tm.report(g, ctx);
   return lrc;
