@@ -30,6 +30,8 @@ SYMBOLS = [
     ("bpgpu_points_upload", _INT, [_VP, _VP, _SZ, _c.POINTER(_VP)]),
     ("bpgpu_points_download", _INT, [_VP, _VP, _SZ, _SZ, _VP]),
     ("bpgpu_points_from_hashes", _INT, [_VP, _VP, _SZ, _c.POINTER(_VP)]),
+    ("bpgpu_points_precompute", _INT, [_VP, _VP]),
+    ("bpgpu_points_has_tables", _INT, [_VP]),
     ("bpgpu_points_len", _SZ, [_VP]),
     ("bpgpu_points_free", None, [_VP]),
     ("bpgpu_scalars_upload", _INT, [_VP, _VP, _SZ, _c.POINTER(_VP)]),
@@ -39,6 +41,7 @@ SYMBOLS = [
     ("bpgpu_msm", _INT, [_VP, _VP, _SZ, _SZ, _VP, _VP]),
     ("bpgpu_msm_device", _INT, [_VP, _VP, _SZ, _SZ, _VP, _SZ, _VP]),
     ("bpgpu_msm_refs", _INT, [_VP, _VP, _VP, _SZ, _VP]),
+    ("bpgpu_msm_parts_batch", _INT, [_VP, _VP, _VP, _SZ, _VP]),
     ("bpgpu_msm_window_bits", _INT, [_SZ]),
     ("bpgpu_fixed_bases_create", _INT, [_VP, _VP, _SZ, _c.POINTER(_VP)]),
     ("bpgpu_fixed_bases_get", _INT, [_VP, _VP, _SZ, _c.POINTER(_VP)]),
@@ -54,6 +57,7 @@ SYMBOLS = [
     ("bpgpu_fr_poly3_special_inner_product", _INT, [_VP, _VP, _VP, _VP, _VP, _VP, _VP, _SZ, _VP]),
     ("bpgpu_fr_batch_invert", _INT, [_VP, _VP, _SZ, _SZ, _VP, _SZ, _VP]),
     ("bpgpu_ipp_begin", _INT, [_VP, _VP, _SZ, _VP, _SZ, _VP, _VP, _VP, _VP, _VP, _SZ, _c.POINTER(_VP)]),
+    ("bpgpu_ipp_begin_fixed_q", _INT, [_VP, _VP, _SZ, _VP, _SZ, _VP, _VP, _VP, _VP, _VP, _VP, _SZ, _c.POINTER(_VP)]),
     ("bpgpu_ipp_len", _SZ, [_VP]),
     ("bpgpu_ipp_round_LR", _INT, [_VP, _VP, _VP]),
     ("bpgpu_ipp_fold", _INT, [_VP, _VP, _VP]),
@@ -179,6 +183,15 @@ class DevicePoints:
 
     def __len__(self):
         return lib().bpgpu_points_len(self.handle)
+
+    def precompute(self):
+        """build the window tables (bpgpu_points_precompute): later MSMs over this table need no doublings"""
+        self.ctx._check(lib().bpgpu_points_precompute(self.ctx.handle, self.handle), "points_precompute")
+        return self
+
+    @property
+    def has_tables(self):
+        return bool(lib().bpgpu_points_has_tables(self.handle))
 
     def download(self, off=0, n=None):
         n = len(self) - off if n is None else n
@@ -441,11 +454,15 @@ class Context:
         return DeviceScalars(self, h), delta.raw
 
     # ---- host layer (include/bphost.h): the reference's API end to end
-    def get_generators(self, prefix, n):
-        """utils::get_generators(prefix, n) as a device table (utils/mod.rs:16-23)."""
+    def get_generators(self, prefix, n, precompute=False):
+        """utils::get_generators(prefix, n) as a device table (utils/mod.rs:16-23); precompute=True also builds the window
+        tables (bpgpu_points_precompute)."""
         h = ctypes.c_void_p()
         self._check(lib().bph_get_generators(self.handle, prefix.encode(), n, ctypes.byref(h)), "get_generators")
-        return DevicePoints(self, h)
+        t = DevicePoints(self, h)
+        if os.environ.get("BPGPU_PRECOMPUTE") == "1" and n <= 4096:      # test switch: run every caller on the table path
+            precompute = True
+        return t.precompute() if precompute else t
 
     def g1_from_msg_hash(self, msg):
         out = ctypes.create_string_buffer(2 * self.modbytes)

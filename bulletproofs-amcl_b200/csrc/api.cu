@@ -235,9 +235,13 @@ static int fetch_result(bpgpu_ctx* ctx, const void* d_src, size_t bytes, uint8_t
   return BPGPU_OK;
 }
 
-// Horner over the per-window sums + affine normalisation, on the host (see host_fp.h for why)
+}  // namespace bp
+
+namespace bp {
+// Host finish of one MSM: Horner over the general path's window sums (if any) + the table path's sum (if any),
+// then one affine normalisation.
 template <class FqParams>
-static void msm_finish_host(const uint8_t* winsum_bytes, int W, int c, int qshift, int modbytes, uint8_t* out_xy) {
+static void msm_finish_mixed(const uint8_t* winsum_bytes, int W, int c, int qshift, const uint8_t* table_sum, int modbytes, uint8_t* out_xy) {
   using HP = host::HXYZZ<FqParams>;
   HP acc = HP::inf();
   const HP* ws = reinterpret_cast<const HP*>(winsum_bytes);
@@ -247,27 +251,39 @@ static void msm_finish_host(const uint8_t* winsum_bytes, int W, int c, int qshif
     if (!q.is_inf()) { for (int k = 0; k < qshift; k++) q.dbl(); acc.add(q); }
     acc.add(ws[w]);
   }
+  if (table_sum) acc.add(*reinterpret_cast<const HP*>(table_sum));
   acc.to_xy_be(modbytes, out_xy);
 }
 
-}  // namespace bp
-
-namespace bp {
-int msm_to_host(bpgpu_ctx* ctx, const void* d_pts, const void* d_scal, bool mont, size_t n, uint8_t* out_xy) {
-  int mb = bpgpu_modbytes(ctx->curve);
+int msm_mixed_to_host(bpgpu_ctx* ctx, const TableSeg* segs, int nsegs, const void* d_pts, const void* d_scal, bool mont, size_t n,
+                      uint8_t* out_xy) {
+  const int mb = bpgpu_modbytes(ctx->curve);
+  const bool bls = ctx->curve == BPGPU_BLS12_381;
+  const size_t psz = bls ? sizeof(XYZZ<Bls::Fq>) : sizeof(XYZZ<Bn::Fq>);
   MsmResult res;
+  res.W = 0; res.c = 0; res.qshift = 0; res.d_winsum = nullptr;
   int rc;
-  if (ctx->curve == BPGPU_BLS12_381) rc = msm_run<Bls>(ctx, (const Affine<Bls::Fq>*)d_pts, d_scal, mont, n, &res);
-  else rc = msm_run<Bn>(ctx, (const Affine<Bn::Fq>*)d_pts, d_scal, mont, n, &res);
-  if (rc) return rc;
-  size_t psz = (ctx->curve == BPGPU_BLS12_381) ? sizeof(XYZZ<Bls::Fq>) : sizeof(XYZZ<Bn::Fq>);
-  if (res.W) {
-    BP_CUDA_OK(cudaMemcpyAsync(ctx->pinned, res.d_winsum, 2 * res.W * psz, cudaMemcpyDeviceToHost, ctx->stream));
-    BP_CUDA_OK(cudaStreamSynchronize(ctx->stream));
+  size_t tn = 0;
+  for (int k = 0; k < nsegs; k++) tn += segs[k].n;
+  if (tn) {
+    rc = bls ? table_sum_run<Bls>(ctx, segs, nsegs) : table_sum_run<Bn>(ctx, segs, nsegs);
+    if (rc) return rc;
   }
-  if (ctx->curve == BPGPU_BLS12_381) msm_finish_host<BlsFq>(ctx->pinned, res.W, res.c, res.qshift, mb, out_xy);
-  else msm_finish_host<BnFq>(ctx->pinned, res.W, res.c, res.qshift, mb, out_xy);
+  if (n) {
+    rc = bls ? msm_run<Bls>(ctx, (const Affine<Bls::Fq>*)d_pts, d_scal, mont, n, &res) : msm_run<Bn>(ctx, (const Affine<Bn::Fq>*)d_pts, d_scal, mont, n, &res);
+    if (rc) return rc;
+  }
+  uint8_t* tsum = ctx->pinned + 2 * 128 * psz;      // after the window sums (W <= 86 at c = 3)
+  if (res.W) BP_CUDA_OK(cudaMemcpyAsync(ctx->pinned, res.d_winsum, 2 * res.W * psz, cudaMemcpyDeviceToHost, ctx->stream));
+  if (tn) BP_CUDA_OK(cudaMemcpyAsync(tsum, ctx->tbl_part.p, psz, cudaMemcpyDeviceToHost, ctx->stream));
+  if (res.W || tn) BP_CUDA_OK(cudaStreamSynchronize(ctx->stream));
+  if (bls) msm_finish_mixed<BlsFq>(ctx->pinned, res.W, res.c, res.qshift, tn ? tsum : nullptr, mb, out_xy);
+  else msm_finish_mixed<BnFq>(ctx->pinned, res.W, res.c, res.qshift, tn ? tsum : nullptr, mb, out_xy);
   return BPGPU_OK;
+}
+
+int msm_to_host(bpgpu_ctx* ctx, const void* d_pts, const void* d_scal, bool mont, size_t n, uint8_t* out_xy) {
+  return msm_mixed_to_host(ctx, nullptr, 0, d_pts, d_scal, mont, n, out_xy);
 }
 }  // namespace bp
 
@@ -337,7 +353,7 @@ void bpgpu_ctx_destroy(bpgpu_ctx* c) {
   c->fb_cache.clear();
   c->msm_a.release(); c->msm_b.release(); c->msm_c.release(); c->msm_d.release(); c->msm_e.release();
   c->io_dev.release(); c->io_dev2.release();
-  c->ipp_pts.release(); c->ipp_scl.release(); c->parts_pts.release(); c->parts_scl.release();
+  c->ipp_pts.release(); c->ipp_scl.release(); c->parts_pts.release(); c->parts_scl.release(); c->tbl_part.release();
   c->fr_tmp.release(); c->fr_out.release(); c->fr_args.release(); c->fr_pow.release(); c->fr_pow2.release();
   if (c->pinned) cudaFreeHost(c->pinned);
   cudaStreamDestroy(c->stream);
@@ -412,10 +428,19 @@ int bpgpu_points_download(bpgpu_ctx* ctx, const bpgpu_points* p, size_t off, siz
 }
 
 size_t bpgpu_points_len(const bpgpu_points* p) { return p ? p->n : 0; }
+
+int bpgpu_points_precompute(bpgpu_ctx* ctx, bpgpu_points* p) {
+  if (!ctx || !p) return BPGPU_E_ARG;
+  if (p->table || p->n == 0) return BPGPU_OK;
+  BP_CUDA_OK(cudaSetDevice(ctx->device));
+  return ctx->curve == BPGPU_BLS12_381 ? build_tables<Bls>(ctx, p->d, p->n, &p->table) : build_tables<Bn>(ctx, p->d, p->n, &p->table);
+}
+int bpgpu_points_has_tables(const bpgpu_points* p) { return p && p->table ? 1 : 0; }
 void bpgpu_points_free(bpgpu_points* p) {
   if (!p) return;
   cudaSetDevice(p->ctx->device);
   dev_free(p->ctx, p->d);
+  if (p->table) cudaFree(p->table);
   delete p;
 }
 
@@ -478,6 +503,10 @@ int bpgpu_msm(bpgpu_ctx* ctx, const bpgpu_points* p, size_t off, size_t n, const
 #undef CALL
   if (rc) return rc;
   size_t psz = (ctx->curve == BPGPU_BLS12_381) ? sizeof(Affine<Bls::Fq>) : sizeof(Affine<Bn::Fq>);
+  if (p->table && n) {
+    TableSeg seg{(const uint8_t*)p->table + off * TBL_ENTRIES * psz, ctx->msm_c.p, (uint32_t)n, 0};
+    return msm_mixed_to_host(ctx, &seg, 1, nullptr, nullptr, false, 0, out_xy);
+  }
   return msm_to_host(ctx, (const uint8_t*)p->d + off * psz, ctx->msm_c.p, false, n, out_xy);
 }
 
@@ -487,6 +516,10 @@ int bpgpu_msm_device(bpgpu_ctx* ctx, const bpgpu_points* p, size_t poff, size_t 
   if (poff > p->n || n > p->n - poff || soff > s->n || n > s->n - soff) return BPGPU_E_LEN;
   BP_CUDA_OK(cudaSetDevice(ctx->device));
   size_t psz = (ctx->curve == BPGPU_BLS12_381) ? sizeof(Affine<Bls::Fq>) : sizeof(Affine<Bn::Fq>);
+  if (p->table && n) {
+    TableSeg seg{(const uint8_t*)p->table + poff * TBL_ENTRIES * psz, (const uint8_t*)s->d + soff * 32, (uint32_t)n, 1};
+    return msm_mixed_to_host(ctx, &seg, 1, nullptr, nullptr, false, 0, out_xy);
+  }
   return msm_to_host(ctx, (const uint8_t*)p->d + poff * psz, (const uint8_t*)s->d + soff * 32, true, n, out_xy);
 }
 

@@ -67,7 +67,7 @@ struct bpgpu_ctx {
   uint64_t launches = 0;
   // MSM scratch
   bp::Scratch msm_a, msm_b, msm_c, msm_d, msm_e, io_dev, io_dev2;
-  bp::Scratch fr_tmp, fr_out, fr_args, fr_pow, fr_pow2, ipp_pts, ipp_scl, parts_pts, parts_scl;
+  bp::Scratch fr_tmp, fr_out, fr_args, fr_pow, fr_pow2, ipp_pts, ipp_scl, parts_pts, parts_scl, tbl_part;
   uint8_t* pinned = nullptr;      // small pinned staging (results, challenges)
   size_t pinned_cap = 0;
   // per-stage CUDA-event timing of the MSM pipeline (bpgpu_ctx_set_profile)
@@ -81,6 +81,7 @@ struct bpgpu_points {
   bpgpu_ctx* ctx;
   void* d;        // Affine<Fq>[n]
   size_t n;
+  void* table = nullptr;   // optional window tables Affine<Fq>[n][64][15] (bpgpu_points_precompute, fixedbase.cu)
 };
 struct bpgpu_scalars {
   bpgpu_ctx* ctx;
@@ -157,6 +158,27 @@ int launch_check(bpgpu_ctx* ctx, const char* what);
 // per-window sums an MSM leaves on the device: result = sum_w 2^(c*w) * winsum[w]
 // window w = P_w + 2^qshift * Q_w with P = d_winsum[0..W), Q = d_winsum[W..2W)
 struct MsmResult { int W; int c; int qshift; const void* d_winsum; };
+
+// ---- window tables of fixed points (fixedbase.cu): T[i][w][d-1] = d * 2^(4w) * P_i, w < 64, d = 1..15, affine
+static const int TBL_WINDOWS = 64;
+static const int TBL_DIGITS = 15;
+static const int TBL_ENTRIES = TBL_WINDOWS * TBL_DIGITS;      // per point
+static const int TBL_MAX_SEGS = 12;
+static const int TBL_MAX_GROUPS = 4;
+// one run of terms whose points have tables: table already offset to the first point, scalars = Fr[n];
+// group = which of the (up to 4) independent sums of one launch the run belongs to (segments sorted by group)
+struct TableSeg { const void* table; const void* scalars; uint32_t n; int mont; int group = 0; };
+template <class Curve> int build_tables(bpgpu_ctx* ctx, const void* d_affine, size_t n, void** table_out);
+// per group g: sum over its segments of sum_i s_i * P_i, left as XYZZ points at ctx->tbl_part.p[0 .. ngroups)
+// (no doublings, no buckets); one launch pair for all groups
+template <class Curve> int table_sum_run(bpgpu_ctx* ctx, const TableSeg* segs, int nsegs, int ngroups = 1);
+// table-only MSMs, one per group: device sums, one D2H, one shared inversion for the affine results
+int msm_tables_to_host(bpgpu_ctx* ctx, const TableSeg* segs, int nsegs, int ngroups, uint8_t* const* outs_xy);
+// (fixed-base cache lookup) table of a point that is one of the bases of a cached bpgpu_fixed_bases, or nullptr
+const void* fixed_table_lookup(bpgpu_ctx* ctx, const uint8_t* xy);
+// full MSM over table segments plus (optionally) a general run of device points/scalars; host finish
+int msm_mixed_to_host(bpgpu_ctx* ctx, const TableSeg* segs, int nsegs, const void* d_pts, const void* d_scal, bool mont, size_t n,
+                      uint8_t* out_xy);
 
 // host X||Y big-endian points -> device affine Montgomery (api.cu)
 template <class Curve> int points_from_host(bpgpu_ctx* ctx, const uint8_t* xy, size_t n, void* dst);

@@ -14,8 +14,8 @@
 
 namespace bp {
 
-static const int FB_WINDOWS = 64;      // 4-bit unsigned windows cover 256 bits
-static const int FB_DIGITS = 15;
+static const int FB_WINDOWS = TBL_WINDOWS;      // 4-bit unsigned windows cover 256 bits
+static const int FB_DIGITS = TBL_DIGITS;
 
 }  // namespace bp
 
@@ -28,10 +28,25 @@ struct bpgpu_fixed_bases {
 
 namespace bp {
 
+template <class Fq>
+__device__ __forceinline__ XYZZ<Fq> block_tree_sum_256(const XYZZ<Fq>& v, XYZZ<Fq>* sm) {
+  store_vec(sm + threadIdx.x, v);
+  __syncthreads();
+  for (int o = 128; o > 0; o >>= 1) {
+    if ((int)threadIdx.x < o) {
+      XYZZ<Fq> a = load_vec(sm + threadIdx.x), b = load_vec(sm + threadIdx.x + o);
+      a.add(b);
+      store_vec(sm + threadIdx.x, a);
+    }
+    __syncthreads();
+  }
+  return load_vec(sm);
+}
+
 // pow2[j][w] = 2^(4w) * B_j : one thread per base, a serial chain of 252 doublings (one-off)
 template <class Fq>
-__global__ void k_fb_pow2(const Affine<Fq>* __restrict__ bases, int k, XYZZ<Fq>* __restrict__ pow2) {
-  int j = blockIdx.x * blockDim.x + threadIdx.x;
+__global__ void k_fb_pow2(const Affine<Fq>* __restrict__ bases, size_t k, XYZZ<Fq>* __restrict__ pow2) {
+  size_t j = (size_t)blockIdx.x * blockDim.x + threadIdx.x;
   if (j >= k) return;
   XYZZ<Fq> p = XYZZ<Fq>::from_affine(load_vec(bases + j));
   for (int w = 0; w < FB_WINDOWS; w++) {
@@ -40,17 +55,93 @@ __global__ void k_fb_pow2(const Affine<Fq>* __restrict__ bases, int k, XYZZ<Fq>*
   }
 }
 
-// table[j][w][d-1] = d * pow2[j][w], normalised to affine: one thread per (j, w)
+// table[j][w][d-1] = d * pow2[j][w], normalised to affine: one thread per (j, w); the 15 multiples share ONE field
+// inversion (Montgomery's trick on the ZZZ coordinates)
 template <class Fq>
-__global__ void __launch_bounds__(64) k_fb_multiples(const XYZZ<Fq>* __restrict__ pow2, int total, Affine<Fq>* __restrict__ table) {
-  int t = blockIdx.x * blockDim.x + threadIdx.x;
+__global__ void __launch_bounds__(64) k_fb_multiples(const XYZZ<Fq>* __restrict__ pow2, size_t total, Affine<Fq>* __restrict__ table) {
+  size_t t = (size_t)blockIdx.x * blockDim.x + threadIdx.x;
   if (t >= total) return;
   const XYZZ<Fq> base = load_vec(pow2 + t);
-  XYZZ<Fq> acc = base;
-  for (int d = 1; d <= FB_DIGITS; d++) {
-    store_vec(table + (size_t)t * FB_DIGITS + (d - 1), acc.to_affine());
-    if (d < FB_DIGITS) acc.add(base);
+  Affine<Fq>* out = table + t * FB_DIGITS;
+  if (base.is_inf()) {
+    for (int d = 0; d < FB_DIGITS; d++) store_vec(out + d, Affine<Fq>::inf());
+    return;
   }
+  XYZZ<Fq> m[FB_DIGITS];
+  Fq pre[FB_DIGITS];                       // pre[d] = product of zzz_0 .. zzz_d over the finite multiples
+  XYZZ<Fq> acc = base;
+  Fq run = Fq::one();
+#pragma unroll 1
+  for (int d = 0; d < FB_DIGITS; d++) {
+    m[d] = acc;
+    if (!acc.is_inf()) run = run * acc.zzz;
+    pre[d] = run;
+    if (d + 1 < FB_DIGITS) acc.add(base);
+  }
+  Fq inv = run.inv();
+#pragma unroll 1
+  for (int d = FB_DIGITS - 1; d >= 0; d--) {
+    if (m[d].is_inf()) { store_vec(out + d, Affine<Fq>::inf()); continue; }      // only for points of order < 16: never on these curves
+    Fq i3 = d ? inv * pre[d - 1] : inv;     // 1 / zzz_d
+    inv = inv * m[d].zzz;
+    Fq i1 = i3 * m[d].zz;                   // 1 / z
+    Affine<Fq> a;
+    a.x = m[d].x * i1.sqr();
+    a.y = m[d].y * i3;
+    store_vec(out + d, a);
+  }
+}
+
+// 8 threads per term: thread (p, j) adds the table entries of windows 8j .. 8j+7 of term p; block tree; one XYZZ per block.
+// blockIdx.y selects the group (independent sum) the block works for.
+struct TableSegs {
+  const void* table[TBL_MAX_SEGS]; const void* scal[TBL_MAX_SEGS];
+  uint32_t mont[TBL_MAX_SEGS];
+  uint32_t start[TBL_MAX_SEGS + 1];            // first term of the segment within its group
+  uint32_t gfirst[TBL_MAX_GROUPS + 1];         // first segment of each group
+  uint32_t gtotal[TBL_MAX_GROUPS];             // terms per group
+};
+template <class Curve>
+__global__ void __launch_bounds__(256) k_table_sum(TableSegs segs, XYZZ<typename Curve::Fq>* __restrict__ partial) {
+  using Fq = typename Curve::Fq;
+  using Fr = typename Curve::Fr;
+  __shared__ __align__(16) unsigned char smraw[256 * sizeof(XYZZ<Fq>)];
+  XYZZ<Fq>* sm = reinterpret_cast<XYZZ<Fq>*>(smraw);
+  const uint32_t grp = blockIdx.y;
+  const uint32_t gid = blockIdx.x * blockDim.x + threadIdx.x;
+  const uint32_t p = gid >> 3, j = gid & 7;
+  XYZZ<Fq> acc = XYZZ<Fq>::inf();
+  if (p < segs.gtotal[grp]) {
+    uint32_t sg = segs.gfirst[grp];
+    const uint32_t last = segs.gfirst[grp + 1] - 1;
+    while (sg < last && p >= segs.start[sg + 1]) sg++;
+    const uint32_t idx = p - segs.start[sg];
+    Fr sc = load_vec((const Fr*)segs.scal[sg] + idx);
+    if (segs.mont[sg]) sc = sc.from_mont();
+    const uint32_t limb = sc.v[j];
+    if (limb) {
+      const Affine<Fq>* tb = (const Affine<Fq>*)segs.table[sg] + ((size_t)idx * TBL_WINDOWS + 8 * j) * TBL_DIGITS;
+#pragma unroll 1
+      for (int k = 0; k < 8; k++) {
+        const uint32_t d = (limb >> (4 * k)) & 15u;
+        if (d) acc.madd(load_vec_ro(tb + k * TBL_DIGITS + (d - 1)));
+      }
+    }
+  }
+  XYZZ<Fq> tot = block_tree_sum_256(acc, sm);
+  if (threadIdx.x == 0) store_vec(partial + (size_t)grp * gridDim.x + blockIdx.x, tot);
+}
+
+// block g sums the `count` block results of group g into out[g]
+template <class Fq>
+__global__ void __launch_bounds__(256) k_table_sum_final(const XYZZ<Fq>* __restrict__ partial, uint32_t count, XYZZ<Fq>* __restrict__ out) {
+  __shared__ __align__(16) unsigned char smraw[256 * sizeof(XYZZ<Fq>)];
+  XYZZ<Fq>* sm = reinterpret_cast<XYZZ<Fq>*>(smraw);
+  const XYZZ<Fq>* src = partial + (size_t)blockIdx.x * count;
+  XYZZ<Fq> acc = XYZZ<Fq>::inf();
+  for (uint32_t k = threadIdx.x; k < count; k += blockDim.x) { XYZZ<Fq> q = load_vec(src + k); acc.add(q); }
+  XYZZ<Fq> tot = block_tree_sum_256(acc, sm);
+  if (threadIdx.x == 0) store_vec(out + blockIdx.x, tot);
 }
 
 // one block of 64 threads per commitment: thread w sums the k table entries of window w, then a block tree
@@ -80,27 +171,94 @@ __global__ void __launch_bounds__(64) k_fb_commit(const Affine<Fq>* __restrict__
   if (w == 0) store_vec(out + inst, load_vec(sm));
 }
 
+// Builds the window tables of n affine points already on the device.  One-off: a 252-doubling chain per point (all
+// points in parallel), 14 additions and one inversion per (point, window).
+template <class Curve>
+int build_tables(bpgpu_ctx* ctx, const void* d_affine, size_t n, void** table_out) {
+  using Fq = typename Curve::Fq;
+  *table_out = nullptr;
+  if (n == 0) return BPGPU_OK;
+  const size_t tbytes = n * TBL_ENTRIES * sizeof(Affine<Fq>);
+  if (tbytes > ((size_t)96 << 30)) return BPGPU_E_ARG;                       // tables are for generator sets, not for 2^20-point inputs
+  void* d_pow2 = nullptr;
+  void* table = nullptr;
+  BP_CUDA_OK(cudaMalloc(&table, tbytes));
+  // the XYZZ powers are scratch: process the points in slabs of at most 2^16
+  const size_t slab = n < 65536 ? n : 65536;
+  if (cudaMalloc(&d_pow2, slab * FB_WINDOWS * sizeof(XYZZ<Fq>)) != cudaSuccess) { cudaFree(table); return BPGPU_E_CUDA; }
+  int rc = BPGPU_OK;
+  for (size_t lo = 0; lo < n && !rc; lo += slab) {
+    const size_t cnt = n - lo < slab ? n - lo : slab;
+    k_fb_pow2<Fq><<<(unsigned)((cnt + 63) / 64), 64, 0, ctx->stream>>>((const Affine<Fq>*)d_affine + lo, cnt, (XYZZ<Fq>*)d_pow2);
+    const size_t total = cnt * FB_WINDOWS;
+    k_fb_multiples<Fq><<<(unsigned)((total + 63) / 64), 64, 0, ctx->stream>>>((const XYZZ<Fq>*)d_pow2, total,
+                                                                               (Affine<Fq>*)table + lo * TBL_ENTRIES);
+    ctx->launches += 2;
+    rc = launch_check(ctx, "build_tables");
+  }
+  if (!rc && cudaStreamSynchronize(ctx->stream) != cudaSuccess) rc = BPGPU_E_CUDA;
+  cudaFree(d_pow2);
+  if (rc) { cudaFree(table); return rc; }
+  *table_out = table;
+  return BPGPU_OK;
+}
+template int build_tables<Bls>(bpgpu_ctx*, const void*, size_t, void**);
+template int build_tables<Bn>(bpgpu_ctx*, const void*, size_t, void**);
+
+template <class Curve>
+int table_sum_run(bpgpu_ctx* ctx, const TableSeg* segs, int nsegs, int ngroups) {
+  using Fq = typename Curve::Fq;
+  if (nsegs > TBL_MAX_SEGS || ngroups < 1 || ngroups > TBL_MAX_GROUPS) return BPGPU_E_ARG;
+  TableSegs ts;
+  int q = 0;
+  uint32_t maxtotal = 0;
+  for (int g = 0; g < ngroups; g++) {
+    ts.gfirst[g] = q;
+    uint32_t total = 0;
+    for (int k = 0; k < nsegs; k++) {
+      if (segs[k].group != g || segs[k].n == 0) continue;
+      ts.table[q] = segs[k].table; ts.scal[q] = segs[k].scalars; ts.mont[q] = segs[k].mont ? 1u : 0u;
+      ts.start[q] = total;
+      total += segs[k].n;
+      q++;
+    }
+    if (q == (int)ts.gfirst[g]) {                    // empty group: one dummy segment with no terms
+      ts.table[q] = nullptr; ts.scal[q] = nullptr; ts.mont[q] = 0; ts.start[q] = 0;
+      q++;
+    }
+    ts.gtotal[g] = total;
+    if (total > maxtotal) maxtotal = total;
+  }
+  ts.gfirst[ngroups] = q;
+  ts.start[q] = 0;
+  if (q > TBL_MAX_SEGS) return BPGPU_E_ARG;
+  uint32_t blocks = (maxtotal * 8 + 255) / 256;
+  if (blocks == 0) blocks = 1;
+  int rc = ctx->tbl_part.reserve(((size_t)blocks * ngroups + TBL_MAX_GROUPS) * sizeof(XYZZ<Fq>));
+  if (rc) return rc;
+  XYZZ<Fq>* out = (XYZZ<Fq>*)ctx->tbl_part.p;           // [0, ngroups) = results, then per-block sums
+  if (blocks == 1) {
+    k_table_sum<Curve><<<dim3(1, ngroups), 256, 0, ctx->stream>>>(ts, out);
+    ctx->launches += 1;
+  } else {
+    k_table_sum<Curve><<<dim3(blocks, ngroups), 256, 0, ctx->stream>>>(ts, out + TBL_MAX_GROUPS);
+    k_table_sum_final<Fq><<<ngroups, 256, 0, ctx->stream>>>(out + TBL_MAX_GROUPS, blocks, out);
+    ctx->launches += 2;
+  }
+  return launch_check(ctx, "table_sum");
+}
+template int table_sum_run<Bls>(bpgpu_ctx*, const TableSeg*, int, int);
+template int table_sum_run<Bn>(bpgpu_ctx*, const TableSeg*, int, int);
+
 template <class Curve>
 static int fb_build(bpgpu_fixed_bases* fb, const uint8_t* bases_xy) {
   using Fq = typename Curve::Fq;
   bpgpu_ctx* ctx = fb->ctx;
-  const int k = (int)fb->k;
   void* d_bases = nullptr;
-  void* d_pow2 = nullptr;
-  BP_CUDA_OK(cudaMalloc(&d_bases, k * sizeof(Affine<Fq>)));
-  BP_CUDA_OK(cudaMalloc(&d_pow2, (size_t)k * FB_WINDOWS * sizeof(XYZZ<Fq>)));
-  BP_CUDA_OK(cudaMalloc(&fb->table, (size_t)k * FB_WINDOWS * FB_DIGITS * sizeof(Affine<Fq>)));
-  int rc = points_from_host<Curve>(ctx, bases_xy, k, d_bases);
-  if (!rc) {
-    k_fb_pow2<Fq><<<(k + 31) / 32, 32, 0, ctx->stream>>>((const Affine<Fq>*)d_bases, k, (XYZZ<Fq>*)d_pow2);
-    const int total = k * FB_WINDOWS;
-    k_fb_multiples<Fq><<<(total + 63) / 64, 64, 0, ctx->stream>>>((const XYZZ<Fq>*)d_pow2, total, (Affine<Fq>*)fb->table);
-    ctx->launches += 2;
-    rc = launch_check(ctx, "fixed_bases build");
-  }
-  if (!rc && cudaStreamSynchronize(ctx->stream) != cudaSuccess) rc = BPGPU_E_CUDA;
+  BP_CUDA_OK(cudaMalloc(&d_bases, fb->k * sizeof(Affine<Fq>)));
+  int rc = points_from_host<Curve>(ctx, bases_xy, fb->k, d_bases);
+  if (!rc) rc = build_tables<Curve>(ctx, d_bases, fb->k, &fb->table);
   cudaFree(d_bases);
-  cudaFree(d_pow2);
   return rc;
 }
 
@@ -125,6 +283,23 @@ static void normalise_batch_host(const uint8_t* xyzz_bytes, size_t count, int mo
   }
 }
 
+}  // namespace bp
+namespace bp {
+int msm_tables_to_host(bpgpu_ctx* ctx, const TableSeg* segs, int nsegs, int ngroups, uint8_t* const* outs_xy) {
+  const bool bls = ctx->curve == BPGPU_BLS12_381;
+  const size_t psz = bls ? sizeof(XYZZ<Bls::Fq>) : sizeof(XYZZ<Bn::Fq>);
+  const int mb = bpgpu_modbytes(ctx->curve);
+  int rc = bls ? table_sum_run<Bls>(ctx, segs, nsegs, ngroups) : table_sum_run<Bn>(ctx, segs, nsegs, ngroups);
+  if (rc) return rc;
+  BP_CUDA_OK(cudaMemcpyAsync(ctx->pinned, ctx->tbl_part.p, ngroups * psz, cudaMemcpyDeviceToHost, ctx->stream));
+  BP_CUDA_OK(cudaStreamSynchronize(ctx->stream));
+  uint8_t tmp[TBL_MAX_GROUPS * 2 * 48];
+  if (bls) normalise_batch_host<BlsFq>(ctx->pinned, ngroups, mb, tmp);
+  else normalise_batch_host<BnFq>(ctx->pinned, ngroups, mb, tmp);
+  for (int g = 0; g < ngroups; g++) memcpy(outs_xy[g], tmp + (size_t)g * 2 * mb, 2 * mb);
+  return BPGPU_OK;
+}
+
 template <class Curve>
 static int fb_commit(bpgpu_fixed_bases* fb, const uint8_t* scalars_be, size_t count, uint8_t* out_xy) {
   using Fq = typename Curve::Fq;
@@ -147,6 +322,16 @@ static int fb_commit(bpgpu_fixed_bases* fb, const uint8_t* scalars_be, size_t co
   BP_CUDA_OK(cudaStreamSynchronize(ctx->stream));
   normalise_batch_host<FqParams>(stage, count, Curve::MODBYTES, out_xy);
   return BPGPU_OK;
+}
+
+// table of a host point that is one of the bases of a cached fixed-base set (e.g. h of the Pedersen pair)
+const void* fixed_table_lookup(bpgpu_ctx* ctx, const uint8_t* xy) {
+  const size_t pb = 2 * (size_t)bpgpu_modbytes(ctx->curve);
+  const size_t asz = ctx->curve == BPGPU_BLS12_381 ? sizeof(Affine<Bls::Fq>) : sizeof(Affine<Bn::Fq>);
+  for (bpgpu_fixed_bases* fb : ctx->fb_cache)
+    for (size_t j = 0; j < fb->k; j++)
+      if (memcmp(fb->key.data() + j * pb, xy, pb) == 0) return (const uint8_t*)fb->table + j * TBL_ENTRIES * asz;
+  return nullptr;
 }
 
 }  // namespace bp

@@ -144,22 +144,50 @@ static int verifier_scalars_t(bpgpu_ctx* ctx, size_t n, size_t n1, size_t N, con
   return launch_check(ctx, "k_r1cs_verifier_scalars");
 }
 
-// ---- composite MSM: concatenates device/host point and scalar sources into one MSM
+// ---- composite MSM: concatenates device/host point and scalar sources into one MSM.
+// Parts whose points carry window tables (bpgpu_points_precompute, or a host point that is a cached fixed base such as the
+// Pedersen h) go through the table path: no doublings, no buckets, no Horner tail.  Everything else is gathered into one
+// general Pippenger run.  The two partial results are added in the host finish.
 template <class Curve>
 static int msm_parts_t(bpgpu_ctx* ctx, const bpgpu_msm_part* parts, size_t np, uint8_t* out_xy) {
   using Fq = typename Curve::Fq;
   using Fr = typename Curve::Fr;
-  size_t total = 0;
-  for (size_t k = 0; k < np; k++) total += parts[k].n;
+  size_t total = 0, host_scalars = 0;
+  for (size_t k = 0; k < np; k++) { total += parts[k].n; if (!parts[k].scalars) host_scalars += parts[k].n; }
   int rc;
   if ((rc = ctx->parts_pts.reserve(total * sizeof(Affine<Fq>) + 64))) return rc;
-  if ((rc = ctx->parts_scl.reserve(total * sizeof(Fr) + 64))) return rc;
+  if ((rc = ctx->parts_scl.reserve((total + host_scalars) * sizeof(Fr) + 64))) return rc;
   Affine<Fq>* P = (Affine<Fq>*)ctx->parts_pts.p;
   Fr* S = (Fr*)ctx->parts_scl.p;
-  size_t off = 0;
+  Fr* S2 = S + total;                      // Montgomery copies of host scalars that feed table segments
+  TableSeg segs[TBL_MAX_SEGS];
+  int nsegs = 0;
+  size_t off = 0, off2 = 0;
+  // The table path pays off when it replaces the general run entirely, or when the table terms dominate: a small MSM that
+  // needs a general run anyway (verifier: proof points next to G, H) is cheaper as ONE general run (measured).
+  size_t table_terms = 0, general_terms = 0;
   for (size_t k = 0; k < np; k++) {
     const bpgpu_msm_part& p = parts[k];
     if (p.n == 0) continue;
+    bool t = (p.points && p.points->table) || (!p.points && p.n == 1 && fixed_table_lookup(ctx, p.host_points_xy));
+    (t ? table_terms : general_terms) += p.n;
+  }
+  const bool use_tables = general_terms == 0 || table_terms >= 4096;
+  for (size_t k = 0; k < np; k++) {
+    const bpgpu_msm_part& p = parts[k];
+    if (p.n == 0) continue;
+    const void* tbl = nullptr;
+    if (use_tables && nsegs < TBL_MAX_SEGS) {
+      if (p.points && p.points->table) tbl = (const uint8_t*)p.points->table + p.points_off * TBL_ENTRIES * sizeof(Affine<Fq>);
+      else if (!p.points && p.n == 1) tbl = fixed_table_lookup(ctx, p.host_points_xy);
+    }
+    if (tbl) {
+      const void* sc;
+      if (p.scalars) sc = (const Fr*)p.scalars->d + p.scalars_off;
+      else { if ((rc = scalars_from_host<Curve>(ctx, p.host_scalars_be, p.n, 1, S2 + off2))) return rc; sc = S2 + off2; off2 += p.n; }
+      segs[nsegs++] = TableSeg{tbl, sc, (uint32_t)p.n, 1};
+      continue;
+    }
     if (p.points) {
       BP_CUDA_OK(cudaMemcpyAsync(P + off, (const Affine<Fq>*)p.points->d + p.points_off, p.n * sizeof(Affine<Fq>), cudaMemcpyDeviceToDevice,
                                  ctx->stream));
@@ -173,7 +201,57 @@ static int msm_parts_t(bpgpu_ctx* ctx, const bpgpu_msm_part* parts, size_t np, u
     }
     off += p.n;
   }
-  return msm_to_host(ctx, P, S, true, total, out_xy);
+  return msm_mixed_to_host(ctx, segs, nsegs, P, S, true, off, out_xy);
+}
+
+// Several independent composite MSMs (prover.rs:347-362: A_I, A_O, S).  When every part of every MSM has window tables
+// they are evaluated by ONE launch pair (one group per MSM) with one D2H and one shared inversion; otherwise one by one.
+template <class Curve>
+static int msm_parts_batch_tables(bpgpu_ctx* ctx, const bpgpu_msm_part* parts, const size_t* counts, size_t nmsm, uint8_t* out_xy, bool* done) {
+  using Fq = typename Curve::Fq;
+  using Fr = typename Curve::Fr;
+  *done = false;
+  if (nmsm > TBL_MAX_GROUPS) return BPGPU_OK;
+  size_t np = 0, host_scalars = 0;
+  for (size_t m = 0; m < nmsm; m++) np += counts[m];
+  size_t live = 0;
+  for (size_t k = 0; k < np; k++) {
+    const bpgpu_msm_part& p = parts[k];
+    if (p.n == 0) continue;
+    live++;
+    bool t = (p.points && p.points->table) || (!p.points && p.n == 1 && fixed_table_lookup(ctx, p.host_points_xy));
+    if (!t) return BPGPU_OK;
+    if (!p.scalars) host_scalars += p.n;
+  }
+  if (live == 0 || live > (size_t)TBL_MAX_SEGS) return BPGPU_OK;
+  int rc;
+  if ((rc = ctx->parts_scl.reserve(host_scalars * sizeof(Fr) + 64))) return rc;
+  Fr* S2 = (Fr*)ctx->parts_scl.p;
+  // all host scalars of all parts in ONE upload: gather them on the host first
+  std::vector<uint8_t> hs(host_scalars * Curve::MODBYTES + 1);
+  size_t ho = 0;
+  for (size_t k = 0; k < np; k++)
+    if (parts[k].n && !parts[k].scalars) { memcpy(hs.data() + ho * Curve::MODBYTES, parts[k].host_scalars_be, parts[k].n * Curve::MODBYTES); ho += parts[k].n; }
+  if (host_scalars && (rc = scalars_from_host<Curve>(ctx, hs.data(), host_scalars, 1, S2))) return rc;
+  TableSeg segs[TBL_MAX_SEGS];
+  int nsegs = 0;
+  size_t k = 0, so = 0;
+  for (size_t m = 0; m < nmsm; m++) {
+    for (size_t q = 0; q < counts[m]; q++, k++) {
+      const bpgpu_msm_part& p = parts[k];
+      if (p.n == 0) continue;
+      const void* tbl = p.points ? (const uint8_t*)p.points->table + p.points_off * TBL_ENTRIES * sizeof(Affine<Fq>)
+                                 : fixed_table_lookup(ctx, p.host_points_xy);
+      const void* sc;
+      if (p.scalars) sc = (const Fr*)p.scalars->d + p.scalars_off; else { sc = S2 + so; so += p.n; }
+      segs[nsegs++] = TableSeg{tbl, sc, (uint32_t)p.n, 1, (int)m};
+    }
+  }
+  uint8_t* outs[TBL_MAX_GROUPS];
+  for (size_t m = 0; m < nmsm; m++) outs[m] = out_xy + m * 2 * Curve::MODBYTES;
+  rc = msm_tables_to_host(ctx, segs, nsegs, (int)nmsm, outs);
+  *done = rc == BPGPU_OK;
+  return rc;
 }
 
 }  // namespace bp
@@ -248,6 +326,30 @@ int bpgpu_r1cs_verifier_scalars(bpgpu_ctx* ctx, size_t n, size_t n1, size_t padd
   bpgpu_scalars_free(ywr);
   if (rc) { bpgpu_scalars_free(*gh_scalars); *gh_scalars = nullptr; }
   return rc;
+}
+
+int bpgpu_msm_parts_batch(bpgpu_ctx* ctx, const bpgpu_msm_part* parts, const size_t* counts, size_t nmsm, uint8_t* out_xy) {
+  if (!ctx || !parts || !counts || !out_xy) return BPGPU_E_ARG;
+  size_t np = 0;
+  for (size_t m = 0; m < nmsm; m++) np += counts[m];
+  for (size_t k = 0; k < np; k++) {
+    const bpgpu_msm_part& p = parts[k];
+    if (p.n == 0) continue;
+    if (p.points ? !(p.points_off <= p.points->n && p.n <= p.points->n - p.points_off) : !p.host_points_xy) return BPGPU_E_LEN;
+    if (p.scalars ? !(p.scalars_off <= p.scalars->n && p.n <= p.scalars->n - p.scalars_off) : !p.host_scalars_be) return BPGPU_E_LEN;
+  }
+  BP_CUDA_OK(cudaSetDevice(ctx->device));
+  bool done = false;
+  int rc = ctx->curve == BPGPU_BLS12_381 ? msm_parts_batch_tables<Bls>(ctx, parts, counts, nmsm, out_xy, &done)
+                                        : msm_parts_batch_tables<Bn>(ctx, parts, counts, nmsm, out_xy, &done);
+  if (rc || done) return rc;
+  const size_t pb = 2 * (size_t)bpgpu_modbytes(ctx->curve);
+  size_t k = 0;
+  for (size_t m = 0; m < nmsm; m++) {
+    if ((rc = bpgpu_msm_parts(ctx, parts + k, counts[m], out_xy + m * pb))) return rc;
+    k += counts[m];
+  }
+  return BPGPU_OK;
 }
 
 int bpgpu_msm_parts(bpgpu_ctx* ctx, const bpgpu_msm_part* parts, size_t nparts, uint8_t* out_xy) {

@@ -27,10 +27,20 @@ struct IPP {
   static int create_ipp(bpgpu_ctx* ctx, Transcript& transcript, const G1<C>& Q, const FieldElementVector<C>& G_factors,
                         const FieldElementVector<C>& H_factors, const G1Vector<C>& G_vec, size_t goff, const G1Vector<C>& H_vec,
                         size_t hoff, const FieldElementVector<C>& a_vec, const FieldElementVector<C>& b_vec, size_t n,
-                        InnerProductArgumentProof<C>* proof) {
+                        InnerProductArgumentProof<C>* proof, const G1<C>* q_base = nullptr, const FE* q_scalar = nullptr) {
+    // q_base / q_scalar: optional statement that Q == q_scalar * q_base for a fixed base (the R1CS prover's Q = g * w);
+    // it changes no output, it lets the device keep every round on its window tables
     bpgpu_ipp* st = nullptr;
-    int rc = bpgpu_ipp_begin(ctx, G_vec.handle(), goff, H_vec.handle(), hoff, Q.xy, G_factors.handle(), H_factors.handle(),
-                             a_vec.handle(), b_vec.handle(), n, &st);
+    int rc;
+    if (q_base && q_scalar) {
+      uint8_t qs[C::MODBYTES];
+      q_scalar->to_bytes(qs);
+      rc = bpgpu_ipp_begin_fixed_q(ctx, G_vec.handle(), goff, H_vec.handle(), hoff, q_base->xy, qs, G_factors.handle(), H_factors.handle(),
+                                   a_vec.handle(), b_vec.handle(), n, &st);
+    } else {
+      rc = bpgpu_ipp_begin(ctx, G_vec.handle(), goff, H_vec.handle(), hoff, Q.xy, G_factors.handle(), H_factors.handle(), a_vec.handle(),
+                           b_vec.handle(), n, &st);
+    }
     if (rc) return rc;
     transcript.innerproduct_domain_sep(n);                                   // ipp.rs:62
     proof->L.clear();

@@ -351,7 +351,7 @@ class Prover : public ConstraintSystem<C> {
     tr.mark("T, Q, eval");
     FieldElementVector<C> l_vec = FieldElementVector<C>::adopt(ctx_, h_lv), r_vec = FieldElementVector<C>::adopt(ctx_, h_rv),
                           G_factors = FieldElementVector<C>::adopt(ctx_, h_gf), H_factors = FieldElementVector<C>::adopt(ctx_, h_hf);
-    rc = IPP<C>::create_ipp(ctx_, transcript_, Q, G_factors, H_factors, G, 0, H, 0, l_vec, r_vec, padded_n, &proof->ipp_proof);   // :565-574
+    rc = IPP<C>::create_ipp(ctx_, transcript_, Q, G_factors, H_factors, G, 0, H, 0, l_vec, r_vec, padded_n, &proof->ipp_proof, &g_, &w);   // :565-574
     tr.mark("create_ipp");
     return rc;
   }
@@ -434,13 +434,17 @@ class Prover : public ConstraintSystem<C> {
     i_b.to_bytes(ib); o_b.to_bytes(ob); s_b.to_bytes(sb);
     auto part_dev = [&](const G1Vector<C>& T, const uint8_t* sc) { bpgpu_msm_part p{T.handle(), lo, nullptr, nullptr, 0, sc, k}; return p; };
     auto part_h = [&](const uint8_t* sc) { bpgpu_msm_part p{nullptr, 0, h_.xy, nullptr, 0, sc, 1}; return p; };
-    int rc;
-    bpgpu_msm_part pI[3] = {part_dev(G, aL.data()), part_dev(H, aR.data()), part_h(ib)};
-    if ((rc = bpgpu_msm_parts(ctx_, pI, 3, A_I->xy))) return rc;
-    bpgpu_msm_part pO[2] = {part_dev(G, aO.data()), part_h(ob)};
-    if ((rc = bpgpu_msm_parts(ctx_, pO, 2, A_O->xy))) return rc;
-    bpgpu_msm_part pS[3] = {part_dev(G, sL.data()), part_dev(H, sR.data()), part_h(sb)};
-    return bpgpu_msm_parts(ctx_, pS, 3, S->xy);
+    bpgpu_msm_part parts[8] = {part_dev(G, aL.data()), part_dev(H, aR.data()), part_h(ib),      // A_I
+                               part_dev(G, aO.data()), part_h(ob),                                // A_O
+                               part_dev(G, sL.data()), part_dev(H, sR.data()), part_h(sb)};      // S
+    const size_t counts[3] = {3, 2, 3};
+    uint8_t out[3 * 2 * C::MODBYTES];
+    int rc = bpgpu_msm_parts_batch(ctx_, parts, counts, 3, out);
+    if (rc) return rc;
+    *A_I = G1<C>::from_xy(out);
+    *A_O = G1<C>::from_xy(out + 2 * C::MODBYTES);
+    *S = G1<C>::from_xy(out + 4 * C::MODBYTES);
+    return OK;
   }
 };
 

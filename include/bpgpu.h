@@ -77,6 +77,13 @@ int bpgpu_points_download(bpgpu_ctx* ctx, const bpgpu_points* p, size_t off, siz
  * computed by the caller (G1::from_msg_hash = hash_msg + mapit; utils/mod.rs:16-23 get_generators builds every
  * generator table this way).  Try-and-increment, square root, even-y choice and cofactor clearing run on the device. */
 int bpgpu_points_from_hashes(bpgpu_ctx* ctx, const uint8_t* hashes, size_t n, bpgpu_points** out);
+/* Window tables for a generator table: T[i][w][d] = d * 2^(4w) * P_i (64 windows x 15 multiples, 960 affine points =
+ * 90 KB (BLS12-381) / 60 KB (BN254) per generator, built once on the device).  Afterwards every MSM whose points come from
+ * this handle -- bpgpu_msm, bpgpu_msm_device, the parts of bpgpu_msm_parts, the rounds of bpgpu_ipp_* and
+ * bpgpu_ipp_verify_msm -- is a plain sum of table entries: no doublings, no buckets, no Horner tail on the host.  Meant
+ * for the fixed generators G, H of the proof system (utils/mod.rs:16-23), i.e. up to ~2^16 points; trades HBM for latency. */
+int bpgpu_points_precompute(bpgpu_ctx* ctx, bpgpu_points* p);
+int bpgpu_points_has_tables(const bpgpu_points* p);
 size_t bpgpu_points_len(const bpgpu_points* p);
 void bpgpu_points_free(bpgpu_points* p);
 int bpgpu_scalars_upload(bpgpu_ctx* ctx, const uint8_t* be, size_t n, bpgpu_scalars** out);
@@ -110,6 +117,10 @@ typedef struct bpgpu_msm_part {
   size_t n;
 } bpgpu_msm_part;
 int bpgpu_msm_parts(bpgpu_ctx* ctx, const bpgpu_msm_part* parts, size_t nparts, uint8_t* out_xy);
+/* nmsm independent composite MSMs in one call: MSM m takes the next counts[m] entries of `parts`; out_xy receives nmsm
+ * points.  This is the prover's A_I, A_O, S triple (prover.rs:347-362, 404-427): with precomputed generator tables the
+ * three are evaluated by one launch pair. */
+int bpgpu_msm_parts_batch(bpgpu_ctx* ctx, const bpgpu_msm_part* parts, const size_t* counts, size_t nmsm, uint8_t* out_xy);
 /* window width the MSM would use for n terms (reporting only) */
 int bpgpu_msm_window_bits(size_t n);
 
@@ -160,6 +171,11 @@ int bpgpu_fr_batch_invert(bpgpu_ctx* ctx, const bpgpu_scalars* a, size_t aoff, s
 int bpgpu_ipp_begin(bpgpu_ctx* ctx, const bpgpu_points* G, size_t goff, const bpgpu_points* H, size_t hoff,
                     const uint8_t* Q_xy, const bpgpu_scalars* G_factors, const bpgpu_scalars* H_factors,
                     const bpgpu_scalars* a, const bpgpu_scalars* b, size_t n, bpgpu_ipp** out);
+/* the same with Q given as q_scalar * q_base for a fixed base (the R1CS prover's Q = g * w, prover.rs:549-550): with
+ * precomputed G and H every round is then table-only */
+int bpgpu_ipp_begin_fixed_q(bpgpu_ctx* ctx, const bpgpu_points* G, size_t goff, const bpgpu_points* H, size_t hoff,
+                            const uint8_t* q_base_xy, const uint8_t* q_scalar_be, const bpgpu_scalars* G_factors,
+                            const bpgpu_scalars* H_factors, const bpgpu_scalars* a, const bpgpu_scalars* b, size_t n, bpgpu_ipp** out);
 size_t bpgpu_ipp_len(const bpgpu_ipp* ipp);           /* current vector length (n, n/2, ..., 1) */
 int bpgpu_ipp_round_LR(bpgpu_ipp* ipp, uint8_t* L_xy, uint8_t* R_xy);
 int bpgpu_ipp_fold(bpgpu_ipp* ipp, const uint8_t* u_be, const uint8_t* u_inv_be);

@@ -125,3 +125,36 @@ def test_fixed_base_commitments(which, ctx_bls, ctx_bn):
     got = ctx.commit_batch(enc_points(C, [g, h, k3]), b"".join(b"".join(C.fr_to_bytes(x) for x in t) for t in trip), len(trip))
     assert got == enc_points(C, [C.msm([g, h, k3], list(t)) for t in trip])
     assert ctx.commit_batch(enc_points(C, [g, h]), b"", 0) == b""
+
+
+@pytest.mark.parametrize("which", ["bls", "bn"])
+def test_msm_over_precomputed_tables(which, ctx_bls, ctx_bn):
+    """bpgpu_points_precompute: the table path (no doublings, no buckets) gives the same bytes as the general path and as
+    the oracle, for host scalars, device scalars, offsets, edge scalars, and mixed table / general parts."""
+    ctx = ctx_bls if which == "bls" else ctx_bn
+    C = curve_of(ctx)
+    n = 100
+    pts = rand_points(C, n, 77)
+    s = C.synth_scalars(31, n)
+    s[0], s[1], s[2], s[3] = 0, 1, C.r - 1, 15
+    plain = ctx.upload_points(enc_points(C, pts))
+    tab = ctx.upload_points(enc_points(C, pts)).precompute()
+    assert tab.has_tables and not plain.has_tables
+    exp = C.g1_xy_bytes(C.msm(pts, s))
+    assert ctx.msm(plain, enc_scalars(C, s)) == exp
+    assert ctx.msm(tab, enc_scalars(C, s)) == exp
+    ds = ctx.upload_scalars(enc_scalars(C, s))
+    assert ctx.msm_device(tab, ds) == exp
+    # offsets into the table
+    assert ctx.msm(tab, enc_scalars(C, s[10:30]), off=40, n=20) == C.g1_xy_bytes(C.msm(pts[40:60], s[10:30]))
+    assert ctx.msm_device(tab, ds, poff=5, soff=7, n=33) == C.g1_xy_bytes(C.msm(pts[5:38], s[7:40]))
+    # all-zero scalars -> identity; single term
+    assert ctx.msm(tab, enc_scalars(C, [0] * n)) == C.g1_xy_bytes(C.INF)
+    assert ctx.msm(tab, enc_scalars(C, [C.r - 2]), off=99, n=1) == C.g1_xy_bytes(C.mul(pts[99], C.r - 2))
+    # mixed: table part + general host part + general device part, with cancelling terms
+    extra = rand_points(C, 5, 78)
+    es = C.synth_scalars(32, 5)
+    got = ctx.msm_parts([(tab, ds, n), (enc_points(C, extra), enc_scalars(C, es), 5), (plain, enc_scalars(C, [C.r - x for x in s]), n)])
+    assert got == C.g1_xy_bytes(C.msm(extra, es))
+    plain.free()
+    tab.free()

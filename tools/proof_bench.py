@@ -12,6 +12,9 @@ def t(fn, reps=3):
     return best * 1e3, r
 
 
+PRE = os.environ.get("PRE", "1") == "1"
+
+
 def main():
     for curve, name in ((bp.BLS12_381, "bls"), (bp.BN254, "bn")):
         ctx = bp.Context(curve, 0)
@@ -20,7 +23,7 @@ def main():
         for m, bits in ((1, 64), (16, 64), (256, 64)):
             n = m * bits
             t0 = time.perf_counter()
-            G, H = ctx.get_generators("G", n), ctx.get_generators("H", n)
+            G, H = ctx.get_generators("G", n, precompute=PRE), ctx.get_generators("H", n, precompute=PRE)
             tg = (time.perf_counter() - t0) * 1e3
             vals = [(12345678901234567 * (i + 1)) & ((1 << 64) - 1) for i in range(m)]
             l0 = ctx.launches

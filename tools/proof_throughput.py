@@ -12,7 +12,7 @@ for nctx in (1, 2, 4, 8, 16, 32):
     ctxs = [bp.Context(curve, 0) for _ in range(nctx)]
     c0 = ctxs[0]
     gx, hx = c0.g1_from_msg_hash(b"g"), c0.g1_from_msg_hash(b"h")
-    G, H = c0.get_generators("G", m * bits), c0.get_generators("H", m * bits)
+    G, H = c0.get_generators("G", m * bits, precompute=True), c0.get_generators("H", m * bits, precompute=True)
     vals = [(0x9E3779B97F4A7C15 * (i + 1)) & ((1 << 64) - 1) for i in range(count * m)]
     bp.range_prove_many(ctxs, b"tp", gx, hx, G, H, vals[:nctx * m * 2], m, bits)      # warm-up: tables, scratch
     t0 = time.perf_counter()
