@@ -144,7 +144,8 @@ def proof_section(bp, ctx, local, rank, world, dist, torch):
         c0 = ctxs[0]
         gx, hx = c0.g1_from_msg_hash(b"g"), c0.g1_from_msg_hash(b"h")
         n = m * bits
-        G, H = c0.get_generators("G", n), c0.get_generators("H", n)
+        pre = n <= 4096            # window tables in HBM where they pay off (latency-bound sizes), plain tables above
+        G, H = c0.get_generators("G", n, precompute=pre), c0.get_generators("H", n, precompute=pre)
         rng = np.random.default_rng(4242 + rank)
         vals = [int(x) for x in rng.integers(0, 1 << 63, size=count * m, dtype=np.uint64)]
         bp.range_prove_many(ctxs, b"bench", gx, hx, G, H, vals[:m * min(count, 2 * nctx)], m, bits)      # warm-up

@@ -167,7 +167,8 @@ static const int TBL_MAX_SEGS = 12;
 static const int TBL_MAX_GROUPS = 4;
 // one run of terms whose points have tables: table already offset to the first point, scalars = Fr[n];
 // group = which of the (up to 4) independent sums of one launch the run belongs to (segments sorted by group)
-struct TableSeg { const void* table; const void* scalars; uint32_t n; int mont; int group = 0; };
+// rows (optional): term t reads table row rows[t] instead of row t (compacted term lists of the IPP rounds)
+struct TableSeg { const void* table; const void* scalars; uint32_t n; int mont; int group = 0; const uint32_t* rows = nullptr; };
 template <class Curve> int build_tables(bpgpu_ctx* ctx, const void* d_affine, size_t n, void** table_out);
 // per group g: sum over its segments of sum_i s_i * P_i, left as XYZZ points at ctx->tbl_part.p[0 .. ngroups)
 // (no doublings, no buckets); one launch pair for all groups

@@ -95,7 +95,7 @@ __global__ void __launch_bounds__(64) k_fb_multiples(const XYZZ<Fq>* __restrict_
 // 8 threads per term: thread (p, j) adds the table entries of windows 8j .. 8j+7 of term p; block tree; one XYZZ per block.
 // blockIdx.y selects the group (independent sum) the block works for.
 struct TableSegs {
-  const void* table[TBL_MAX_SEGS]; const void* scal[TBL_MAX_SEGS];
+  const void* table[TBL_MAX_SEGS]; const void* scal[TBL_MAX_SEGS]; const uint32_t* rows[TBL_MAX_SEGS];
   uint32_t mont[TBL_MAX_SEGS];
   uint32_t start[TBL_MAX_SEGS + 1];            // first term of the segment within its group
   uint32_t gfirst[TBL_MAX_GROUPS + 1];         // first segment of each group
@@ -120,7 +120,8 @@ __global__ void __launch_bounds__(256) k_table_sum(TableSegs segs, XYZZ<typename
     if (segs.mont[sg]) sc = sc.from_mont();
     const uint32_t limb = sc.v[j];
     if (limb) {
-      const Affine<Fq>* tb = (const Affine<Fq>*)segs.table[sg] + ((size_t)idx * TBL_WINDOWS + 8 * j) * TBL_DIGITS;
+      const uint32_t row = segs.rows[sg] ? segs.rows[sg][idx] : idx;
+      const Affine<Fq>* tb = (const Affine<Fq>*)segs.table[sg] + ((size_t)row * TBL_WINDOWS + 8 * j) * TBL_DIGITS;
 #pragma unroll 1
       for (int k = 0; k < 8; k++) {
         const uint32_t d = (limb >> (4 * k)) & 15u;
@@ -217,13 +218,13 @@ int table_sum_run(bpgpu_ctx* ctx, const TableSeg* segs, int nsegs, int ngroups) 
     uint32_t total = 0;
     for (int k = 0; k < nsegs; k++) {
       if (segs[k].group != g || segs[k].n == 0) continue;
-      ts.table[q] = segs[k].table; ts.scal[q] = segs[k].scalars; ts.mont[q] = segs[k].mont ? 1u : 0u;
+      ts.table[q] = segs[k].table; ts.scal[q] = segs[k].scalars; ts.mont[q] = segs[k].mont ? 1u : 0u; ts.rows[q] = segs[k].rows;
       ts.start[q] = total;
       total += segs[k].n;
       q++;
     }
     if (q == (int)ts.gfirst[g]) {                    // empty group: one dummy segment with no terms
-      ts.table[q] = nullptr; ts.scal[q] = nullptr; ts.mont[q] = 0; ts.start[q] = 0;
+      ts.table[q] = nullptr; ts.scal[q] = nullptr; ts.mont[q] = 0; ts.start[q] = 0; ts.rows[q] = nullptr;
       q++;
     }
     ts.gtotal[g] = total;

@@ -22,6 +22,7 @@ struct bpgpu_ipp {
   // table mode (G and H carry window tables and Q = q_scalar * fixed base): no point copies at all
   const void *tG, *tH, *tQ;
   void* wq;                // Fr[1]: q_scalar (Montgomery) -- the Q terms c_L*Q, c_R*Q become (c*q_scalar) * base
+  void* rows;              // u32[N]: rows_lo[N/2] | rows_hi[N/2] of the current round (table mode)
   void* P;                 // Affine[2N+1] : G | H | Q   (general mode only)
   void *a, *b;             // Fr[N]
   void *sG, *sH;           // Fr[N]
@@ -54,6 +55,30 @@ __global__ void __launch_bounds__(128) k_ipp_build(uint32_t N, uint32_t n_cur, c
     store_vec(sclR + i, zero);
     store_vec(sclR + N + i, load_vec(b + p - half) * h);
   }
+}
+
+// Table mode: only the N + 1 non-zero terms of each side are listed.  With lo = {i : (i mod n_cur) < n_cur/2} and hi its
+// complement (N/2 indices each, written to rows_lo / rows_hi):
+//   L = sum_{i in hi} a[p - half] sG[i] * G[i] + sum_{i in lo} b[p + half] sH[i] * H[i]     -> sclL = [G part | H part | c_L]
+//   R = sum_{i in lo} a[p + half] sG[i] * G[i] + sum_{i in hi} b[p - half] sH[i] * H[i]     -> sclR = [G part | H part | c_R]
+template <class Fr>
+__global__ void __launch_bounds__(128) k_ipp_build_compact(uint32_t N, uint32_t n_cur, const Fr* __restrict__ a, const Fr* __restrict__ b,
+                                                           const Fr* __restrict__ sG, const Fr* __restrict__ sH, Fr* __restrict__ sclL,
+                                                           Fr* __restrict__ sclR, uint32_t* __restrict__ rows_lo,
+                                                           uint32_t* __restrict__ rows_hi) {
+  uint32_t t = blockIdx.x * blockDim.x + threadIdx.x;
+  const uint32_t Nh = N >> 1;
+  if (t >= Nh) return;
+  const uint32_t half = n_cur >> 1;
+  const uint32_t q = t / half, r = t - q * half;
+  const uint32_t ilo = q * n_cur + r, ihi = ilo + half;
+  rows_lo[t] = ilo;
+  rows_hi[t] = ihi;
+  const Fr aL = load_vec(a + r), aR = load_vec(a + r + half), bL = load_vec(b + r), bR = load_vec(b + r + half);
+  store_vec(sclL + t, aL * load_vec(sG + ihi));            // G_R takes a_L
+  store_vec(sclL + Nh + t, bR * load_vec(sH + ilo));       // H_L takes b_R
+  store_vec(sclR + t, aR * load_vec(sG + ilo));            // G_L takes a_R
+  store_vec(sclR + Nh + t, bL * load_vec(sH + ihi));       // H_R takes b_L
 }
 
 // c_L = <a_L, b_R>, c_R = <a_R, b_L>  (ipp.rs:77-78,145-146); one block, results to outL / outR
@@ -156,6 +181,7 @@ static int ipp_begin_t(bpgpu_ipp* st, const bpgpu_points* Gp, size_t goff, const
     st->tH = (const uint8_t*)Hp->table + hoff * TBL_ENTRIES * sizeof(Affine<Fq>);
     st->wq = (Fr*)frs + 4 * N + 2 * (2 * N + 1);
     if ((rc = scalars_from_host<Curve>(ctx, q_scalar_be, 1, 1, st->wq))) return rc;
+    BP_CUDA_OK(dev_alloc(ctx, &st->rows, (N + 1) * sizeof(uint32_t)));
   } else {
     const void* G = (const Affine<Fq>*)Gp->d + goff;
     const void* H = (const Affine<Fq>*)Hp->d + hoff;
@@ -184,22 +210,30 @@ static int ipp_round_t(bpgpu_ipp* st, uint8_t* L_xy, uint8_t* R_xy) {
   using Fr = typename Curve::Fr;
   bpgpu_ctx* ctx = st->ctx;
   const uint32_t N = (uint32_t)st->N, n = (uint32_t)st->n_cur;
+  int rc;
+  if (st->wq) {
+    // table mode: both sums in ONE launch (two groups) over the compacted term lists, one D2H, one shared inversion
+    const uint32_t Nh = N >> 1;
+    uint32_t* rows_lo = (uint32_t*)st->rows;
+    uint32_t* rows_hi = rows_lo + Nh;
+    Fr *sl = (Fr*)st->sclL, *sr = (Fr*)st->sclR;
+    k_ipp_build_compact<Fr><<<(Nh + 127) / 128, 128, 0, ctx->stream>>>(N, n, (const Fr*)st->a, (const Fr*)st->b, (const Fr*)st->sG,
+                                                                     (const Fr*)st->sH, sl, sr, rows_lo, rows_hi);
+    k_ipp_cross<Fr><<<1, 256, 0, ctx->stream>>>(n, (const Fr*)st->a, (const Fr*)st->b, (const Fr*)st->wq, sl + N, sr + N);
+    ctx->launches += 2;
+    if ((rc = launch_check(ctx, "ipp_round"))) return rc;
+    TableSeg segs[6] = {{st->tG, sl, Nh, 1, 0, rows_hi}, {st->tH, sl + Nh, Nh, 1, 0, rows_lo}, {st->tQ, sl + N, 1, 1, 0, nullptr},
+                        {st->tG, sr, Nh, 1, 1, rows_lo}, {st->tH, sr + Nh, Nh, 1, 1, rows_hi}, {st->tQ, sr + N, 1, 1, 1, nullptr}};
+    uint8_t* outs[2] = {L_xy, R_xy};
+    return msm_tables_to_host(ctx, segs, 6, 2, outs);
+  }
   k_ipp_build<Fr><<<(N + 127) / 128, 128, 0, ctx->stream>>>(N, n, (const Fr*)st->a, (const Fr*)st->b, (const Fr*)st->sG,
                                                            (const Fr*)st->sH, (Fr*)st->sclL, (Fr*)st->sclR);
   k_ipp_cross<Fr><<<1, 256, 0, ctx->stream>>>(n, (const Fr*)st->a, (const Fr*)st->b, (const Fr*)st->wq, (Fr*)st->sclL + 2 * N,
                                               (Fr*)st->sclR + 2 * N);
   ctx->launches += 2;
-  int rc = launch_check(ctx, "ipp_round");
+  rc = launch_check(ctx, "ipp_round");
   if (rc) return rc;
-  if (st->wq) {
-    // table mode: L = <sclL[0..N), G> + <sclL[N..2N), H> + (c_L * q_scalar) * q_base, and R likewise, all through window
-    // tables: both sums in ONE launch (two groups), one D2H, one shared inversion
-    const Fr *sl = (const Fr*)st->sclL, *sr = (const Fr*)st->sclR;
-    TableSeg segs[6] = {{st->tG, sl, N, 1, 0}, {st->tH, sl + N, N, 1, 0}, {st->tQ, sl + 2 * N, 1, 1, 0},
-                        {st->tG, sr, N, 1, 1}, {st->tH, sr + N, N, 1, 1}, {st->tQ, sr + 2 * N, 1, 1, 1}};
-    uint8_t* outs[2] = {L_xy, R_xy};
-    return msm_tables_to_host(ctx, segs, 6, 2, outs);
-  }
   if ((rc = msm_to_host(ctx, st->P, st->sclL, true, 2 * (size_t)N + 1, L_xy))) return rc;
   return msm_to_host(ctx, st->P, st->sclR, true, 2 * (size_t)N + 1, R_xy);
 }
@@ -245,39 +279,28 @@ static int ipp_s_t(bpgpu_ctx* ctx, const uint8_t* u_be, size_t lg, void* d_s) {
   return launch_check(ctx, "k_ipp_s");
 }
 
+// expected_P of verify_ipp.  Always ONE general Pippenger run over [Q | G | H | L | R]: the proof-specific points need the
+// general path anyway, and gathering G and H next to them is cheaper than an extra table launch pair (measured at n = 64:
+// 1.05 ms vs 1.21 ms; at n = 2^14 the 64 table entries per term cost 2.5x the bucket method's work).
 template <class Curve>
-static int ipp_verify_t(bpgpu_ctx* ctx, const void* G, const void* H, const void* tG, const void* tH, const uint8_t* Q_xy, const void* Gf,
-                        const void* Hf, const uint8_t* a_be, const uint8_t* b_be, const uint8_t* u_be, const uint8_t* L_xy,
-                        const uint8_t* R_xy, size_t lg, uint8_t* out_xy) {
+static int ipp_verify_t(bpgpu_ctx* ctx, const void* G, const void* H, const uint8_t* Q_xy, const void* Gf, const void* Hf,
+                        const uint8_t* a_be, const uint8_t* b_be, const uint8_t* u_be, const uint8_t* L_xy, const uint8_t* R_xy,
+                        size_t lg, uint8_t* out_xy) {
   using Fq = typename Curve::Fq;
   using Fr = typename Curve::Fr;
   const size_t N = (size_t)1 << lg, total = 1 + 2 * N + 2 * lg;
-  // G and H tables are used only when the general run (Q, L, R) is small next to them: below that the extra launch pair
-  // costs more latency than the gathered points cost work (measured: n = 64 verify 1.05 ms general vs 1.21 ms mixed)
-  const bool tables = tG && tH && N >= 4096;
   int rc;
-  if ((rc = ctx->ipp_pts.reserve((total + 1) * sizeof(Affine<Fq>)))) return rc;
-  if ((rc = ctx->ipp_scl.reserve((total + N + 2 * lg + 2) * sizeof(Fr)))) return rc;
+  if ((rc = ctx->ipp_pts.reserve(total * sizeof(Affine<Fq>)))) return rc;
+  if ((rc = ctx->ipp_scl.reserve((total + N) * sizeof(Fr)))) return rc;
   Affine<Fq>* P = (Affine<Fq>*)ctx->ipp_pts.p;
   Fr* scl = (Fr*)ctx->ipp_scl.p;
   Fr* s = scl + total;
-  // point order of ipp.rs:244-249 is [Q | G | H | L | R]; with tables the G and H runs are table segments and the general
-  // run is [Q | L | R] (scalar slots 0 and 1+2N ..)
-  Affine<Fq>* Pgen = tables ? P : nullptr;
-  if (tables) {
-    if ((rc = points_from_host<Curve>(ctx, Q_xy, 1, Pgen))) return rc;
-    if (lg) {
-      if ((rc = points_from_host<Curve>(ctx, L_xy, lg, Pgen + 1))) return rc;
-      if ((rc = points_from_host<Curve>(ctx, R_xy, lg, Pgen + 1 + lg))) return rc;
-    }
-  } else {
-    if ((rc = points_from_host<Curve>(ctx, Q_xy, 1, P))) return rc;
-    BP_CUDA_OK(cudaMemcpyAsync(P + 1, G, N * sizeof(Affine<Fq>), cudaMemcpyDeviceToDevice, ctx->stream));
-    BP_CUDA_OK(cudaMemcpyAsync(P + 1 + N, H, N * sizeof(Affine<Fq>), cudaMemcpyDeviceToDevice, ctx->stream));
-    if (lg) {
-      if ((rc = points_from_host<Curve>(ctx, L_xy, lg, P + 1 + 2 * N))) return rc;
-      if ((rc = points_from_host<Curve>(ctx, R_xy, lg, P + 1 + 2 * N + lg))) return rc;
-    }
+  if ((rc = points_from_host<Curve>(ctx, Q_xy, 1, P))) return rc;
+  BP_CUDA_OK(cudaMemcpyAsync(P + 1, G, N * sizeof(Affine<Fq>), cudaMemcpyDeviceToDevice, ctx->stream));
+  BP_CUDA_OK(cudaMemcpyAsync(P + 1 + N, H, N * sizeof(Affine<Fq>), cudaMemcpyDeviceToDevice, ctx->stream));
+  if (lg) {
+    if ((rc = points_from_host<Curve>(ctx, L_xy, lg, P + 1 + 2 * N))) return rc;
+    if ((rc = points_from_host<Curve>(ctx, R_xy, lg, P + 1 + 2 * N + lg))) return rc;
   }
   // argument block: u | u_inv | a | b
   using HF = host::HFp<typename std::conditional<Curve::ID == BPGPU_BLS12_381, BlsFr, BnFr>::type>;
@@ -296,16 +319,6 @@ static int ipp_verify_t(bpgpu_ctx* ctx, const void* G, const void* H, const void
                                                                             (const Fr*)Gf, (const Fr*)Hf, scl);
   ctx->launches += 2;
   if ((rc = launch_check(ctx, "ipp_verify"))) return rc;
-  if (tables) {
-    // general run = the proof-specific points.  A sum does not care about order: points [L | R | Q] (Q copied behind R),
-    // scalars [-u^2 | -u^-2 | a*b] gathered behind the s vector
-    Fr* gen = s + N;
-    if (lg) BP_CUDA_OK(cudaMemcpyAsync(gen, scl + 1 + 2 * N, 2 * lg * sizeof(Fr), cudaMemcpyDeviceToDevice, ctx->stream));
-    BP_CUDA_OK(cudaMemcpyAsync(gen + 2 * lg, scl, sizeof(Fr), cudaMemcpyDeviceToDevice, ctx->stream));
-    BP_CUDA_OK(cudaMemcpyAsync(P + 1 + 2 * lg, P, sizeof(Affine<Fq>), cudaMemcpyDeviceToDevice, ctx->stream));
-    TableSeg segs[2] = {{tG, scl + 1, (uint32_t)N, 1}, {tH, scl + 1 + N, (uint32_t)N, 1}};
-    return msm_mixed_to_host(ctx, segs, 2, P + 1, gen, true, 1 + 2 * lg, out_xy);
-  }
   return msm_to_host(ctx, P, scl, true, total, out_xy);
 }
 
@@ -384,6 +397,7 @@ void bpgpu_ipp_free(bpgpu_ipp* st) {
   cudaSetDevice(st->ctx->device);
   dev_free(st->ctx, st->P);
   dev_free(st->ctx, st->a);
+  dev_free(st->ctx, st->rows);
   delete st;
 }
 
@@ -409,10 +423,8 @@ int bpgpu_ipp_verify_msm(bpgpu_ctx* ctx, const bpgpu_points* G, size_t goff, con
   BP_CUDA_OK(cudaSetDevice(ctx->device));
   const void* g = (const uint8_t*)G->d + goff * psize(ctx);
   const void* h = (const uint8_t*)H->d + hoff * psize(ctx);
-  const void* tg = G->table ? (const uint8_t*)G->table + goff * TBL_ENTRIES * psize(ctx) : nullptr;
-  const void* th = H->table ? (const uint8_t*)H->table + hoff * TBL_ENTRIES * psize(ctx) : nullptr;
-  return ctx->curve == BPGPU_BLS12_381 ? ipp_verify_t<Bls>(ctx, g, h, tg, th, Q_xy, Gf->d, Hf->d, a_be, b_be, u_be, L_xy, R_xy, lg, out_xy)
-                                      : ipp_verify_t<Bn>(ctx, g, h, tg, th, Q_xy, Gf->d, Hf->d, a_be, b_be, u_be, L_xy, R_xy, lg, out_xy);
+  return ctx->curve == BPGPU_BLS12_381 ? ipp_verify_t<Bls>(ctx, g, h, Q_xy, Gf->d, Hf->d, a_be, b_be, u_be, L_xy, R_xy, lg, out_xy)
+                                      : ipp_verify_t<Bn>(ctx, g, h, Q_xy, Gf->d, Hf->d, a_be, b_be, u_be, L_xy, R_xy, lg, out_xy);
 }
 
 }  // extern "C"

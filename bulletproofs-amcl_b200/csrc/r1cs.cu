@@ -163,8 +163,9 @@ static int msm_parts_t(bpgpu_ctx* ctx, const bpgpu_msm_part* parts, size_t np, u
   TableSeg segs[TBL_MAX_SEGS];
   int nsegs = 0;
   size_t off = 0, off2 = 0;
-  // The table path pays off when it replaces the general run entirely, or when the table terms dominate: a small MSM that
-  // needs a general run anyway (verifier: proof points next to G, H) is cheaper as ONE general run (measured).
+  // The table path is used when it replaces the general run ENTIRELY.  An MSM that needs a general run anyway (verifier:
+  // proof points next to G, H) is cheaper as one general run: the extra launch pair costs latency at small n, and 64 table
+  // entries per term cost 2.5x the bucket method's work at large n (measured both ways).
   size_t table_terms = 0, general_terms = 0;
   for (size_t k = 0; k < np; k++) {
     const bpgpu_msm_part& p = parts[k];
@@ -172,7 +173,7 @@ static int msm_parts_t(bpgpu_ctx* ctx, const bpgpu_msm_part* parts, size_t np, u
     bool t = (p.points && p.points->table) || (!p.points && p.n == 1 && fixed_table_lookup(ctx, p.host_points_xy));
     (t ? table_terms : general_terms) += p.n;
   }
-  const bool use_tables = general_terms == 0 || table_terms >= 4096;
+  const bool use_tables = general_terms == 0 && table_terms > 0;
   for (size_t k = 0; k < np; k++) {
     const bpgpu_msm_part& p = parts[k];
     if (p.n == 0) continue;

@@ -23,7 +23,7 @@ def main():
         for m, bits in ((1, 64), (16, 64), (256, 64)):
             n = m * bits
             t0 = time.perf_counter()
-            G, H = ctx.get_generators("G", n, precompute=PRE), ctx.get_generators("H", n, precompute=PRE)
+            G, H = ctx.get_generators("G", n, precompute=PRE and n <= 4096), ctx.get_generators("H", n, precompute=PRE and n <= 4096)
             tg = (time.perf_counter() - t0) * 1e3
             vals = [(12345678901234567 * (i + 1)) & ((1 << 64) - 1) for i in range(m)]
             l0 = ctx.launches
