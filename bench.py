@@ -139,7 +139,7 @@ def proof_section(bp, ctx, local, rank, world, dist, torch):
     nctx = max(1, min(16, ncpu // max(1, world)))
     out = {"contexts_per_gpu": nctx, "host_cpus": ncpu}
 
-    def run(curve, m, bits, count, tag, verify_reps=1):
+    def run(curve, m, bits, count, tag, verify_reps=1, batch_call=False):
         ctxs = [bp.Context(curve, local) for _ in range(nctx)]
         c0 = ctxs[0]
         gx, hx = c0.g1_from_msg_hash(b"g"), c0.g1_from_msg_hash(b"h")
@@ -163,24 +163,41 @@ def proof_section(bp, ctx, local, rank, world, dist, torch):
             v = bp.range_verify_many(ctxs, b"bench", gx, hx, G, H, count, m, bits, proofs, stride, comms)
             ok = ok and v == [0] * count
         tv = time.perf_counter() - t0
+        tb = None
+        if batch_call:
+            # config 5: the whole batch through ONE device call (bph_range_verify_batch): host threads build the scalars,
+            # a launch pair evaluates every proof's verification MSM, one verdict byte per proof comes back
+            reps = verify_reps
+            big_p, big_c = proofs * reps, comms * reps
+            bp.range_verify_batch(c0, b"bench", gx, hx, G, H, count, m, bits, proofs, stride, comms)            # warm-up
+            if dist is not None:
+                dist.barrier()
+            t0 = time.perf_counter()
+            v = bp.range_verify_batch(c0, b"bench", gx, hx, G, H, count * reps, m, bits, big_p, stride, big_c)
+            tb = time.perf_counter() - t0
+            ok = ok and v == [0] * (count * reps)
         if dist is not None:
             # the exchange step of the sharded batch verification: verdict bytes of every rank, all-gathered
             t = torch.tensor([1 if ok else 0] * count, dtype=torch.uint8, device="cuda")
             allv = torch.empty(world * count, dtype=torch.uint8, device="cuda")
             dist.all_gather_into_tensor(allv, t)
             ok = bool(allv.min().item() == 1)
-            tt = torch.tensor([tp, tv], device="cuda", dtype=torch.float64)
+            tt = torch.tensor([tp, tv, tb or 0.0], device="cuda", dtype=torch.float64)
             dist.all_reduce(tt, op=dist.ReduceOp.MAX)
             tp, tv = float(tt[0].item()), float(tt[1].item())
+            tb = float(tt[2].item()) if tb is not None else None
         for c in ctxs:
             c.close()
         out[tag] = {"multipliers": n, "committed_values": m, "proofs": count * world, "prove_per_s": count * world / tp,
                     "verify_per_s": count * world * verify_reps / tv, "verifications": count * world * verify_reps,
                     "prove_verify_per_s": count * world / (tp + tv / verify_reps), "all_verified": ok, "proof_bytes": stride}
+        if tb is not None:
+            out[tag]["verify_batch_call_per_s"] = count * world * verify_reps / tb
 
     # config 5 unit / config 1 size: one 64-bit range proof = 64 multipliers, IPP of length 64; 4096 verifications in total
     per_rank = max(nctx, 512 // world)
-    run(bp.BLS12_381, 1, 64, per_rank, "range64_bls12_381_n64", verify_reps=max(1, 4096 // (per_rank * world)))
+    run(bp.BLS12_381, 1, 64, per_rank, "range64_bls12_381_n64", verify_reps=max(1, 4096 // (per_rank * world)),
+        batch_call=True)
     # config 2: 16 x 64-bit values in one constraint system, 1024 generators
     run(bp.BLS12_381, 16, 64, max(nctx, 64 // world), "range64x16_bls12_381_n1024")
     # config 3: 2^14 multipliers on BN254 (256 x 64-bit values)
@@ -237,6 +254,12 @@ def main():
     args = ap.parse_args()
     if args.impl == "reference":
         return run_reference(args)
+
+    # stdout carries exactly ONE JSON line: anything libraries print while we run (NCCL's version banner goes to
+    # stdout) is sent to stderr instead, and the real stdout is restored just before the result is printed
+    sys.stdout.flush()
+    real_stdout = os.dup(1)
+    os.dup2(2, 1)
 
     import torch
     import bulletproofs_amcl_b200 as bp
@@ -371,7 +394,10 @@ def main():
             out["cpu_baseline"] = {"value": vN, "unit": UNIT, "cores": cores, "kind": "port",
                                    "sample": f"Straus wNAF-5 (oracle/c) on all 2^{args.lg} points, {cores} threads, {dtN:.1f} s",
                                    "single_core": {"value": v1, "cores": 1, "sample": f"2^16 points, {dt1:.1f} s"}}
-        print(json.dumps(out))
+        sys.stdout.flush()
+        os.dup2(real_stdout, 1)
+        print(json.dumps(out), flush=True)
+        os.dup2(2, 1)
     if world > 1:
         dist.destroy_process_group()
 

@@ -42,6 +42,7 @@ SYMBOLS = [
     ("bpgpu_msm_device", _INT, [_VP, _VP, _SZ, _SZ, _VP, _SZ, _VP]),
     ("bpgpu_msm_refs", _INT, [_VP, _VP, _VP, _SZ, _VP]),
     ("bpgpu_msm_parts_batch", _INT, [_VP, _VP, _VP, _SZ, _VP]),
+    ("bpgpu_msm_batch_is_identity", _INT, [_VP, _VP, _SZ, _SZ, _VP, _VP, _VP, _SZ, _VP]),
     ("bpgpu_msm_window_bits", _INT, [_SZ]),
     ("bpgpu_fixed_bases_create", _INT, [_VP, _VP, _SZ, _c.POINTER(_VP)]),
     ("bpgpu_fixed_bases_get", _INT, [_VP, _VP, _SZ, _c.POINTER(_VP)]),
@@ -90,8 +91,14 @@ SYMBOLS_HOST = [
     ("bph_range_verify", _INT, [_VP, _CS, _VP, _VP, _VP, _VP, _SZ, _SZ, _VP, _SZ, _VP, _VP]),
     ("bph_range_proof_len", _SZ, [_INT, _SZ, _SZ]),
     ("bph_range_prove_many", _INT, [_VP, _SZ, _CS, _VP, _VP, _VP, _VP, _VP, _SZ, _SZ, _SZ, _INT, _U64, _VP, _SZ, _VP]),
+    ("bph_range_verify_batch", _INT, [_VP, _CS, _VP, _VP, _VP, _VP, _SZ, _SZ, _SZ, _VP, _SZ, _VP, _SZ, _VP]),
     ("bph_range_verify_many", _INT, [_VP, _SZ, _CS, _VP, _VP, _VP, _VP, _SZ, _SZ, _SZ, _VP, _SZ, _VP, _VP]),
 ]
+
+
+class FixedRun(ctypes.Structure):
+    """bpgpu_fixed_run"""
+    _fields_ = [("points", _VP), ("off", _SZ), ("n", _SZ), ("host_base_xy", _VP)]
 
 
 class MsmPart(ctypes.Structure):
@@ -128,6 +135,16 @@ def range_verify_many(ctxs, label, g_xy, h_xy, G, H, count, m, bits, proofs, str
                                      _buf(proofs), stride, _buf(comms), verdicts)
     if rc:
         raise BpgpuError(rc, "range_verify_many")
+    return list(verdicts)[:count]
+
+
+def range_verify_batch(ctx, label, g_xy, h_xy, G, H, count, m, bits, proofs, stride, comms, nthreads=0):
+    """per-proof verdicts of `count` independent proofs from ONE device call (host threads only build the scalars)."""
+    verdicts = (ctypes.c_int32 * max(1, count))()
+    rc = lib().bph_range_verify_batch(ctx.handle, label, _buf(g_xy), _buf(h_xy), G.handle, H.handle, count, m, bits, _buf(proofs), stride,
+                                      _buf(comms), nthreads, verdicts)
+    if rc:
+        raise BpgpuError(rc, "range_verify_batch")
     return list(verdicts)[:count]
 
 
@@ -405,6 +422,22 @@ class Context:
         out = ctypes.create_string_buffer(max(1, count * 2 * self.modbytes))
         self._check(lib().bpgpu_fixed_bases_commit(self.handle, fb, _buf(scalars_be), count, out), "fixed_bases_commit")
         return out.raw[:count * 2 * self.modbytes]
+
+    def msm_batch_is_identity(self, runs, batch, fixed_scalars_be, var_points_xy, var_scalars_be, vn):
+        """runs: list of (DevicePoints with tables, off, n) or bytes (one host base X||Y).  Returns `batch` verdict bytes."""
+        arr = (FixedRun * max(1, len(runs)))()
+        keep = []
+        for i, r in enumerate(runs):
+            if isinstance(r, (bytes, bytearray)):
+                buf = ctypes.create_string_buffer(bytes(r), len(r))
+                keep.append(buf)
+                arr[i].host_base_xy, arr[i].n = ctypes.cast(buf, ctypes.c_void_p), 1
+            else:
+                arr[i].points, arr[i].off, arr[i].n = r[0].handle, r[1], r[2]
+        out = ctypes.create_string_buffer(max(1, batch))
+        self._check(lib().bpgpu_msm_batch_is_identity(self.handle, arr, len(runs), batch, _buf(fixed_scalars_be), _buf(var_points_xy),
+                                                      _buf(var_scalars_be), vn, out), "msm_batch_is_identity")
+        return out.raw[:batch]
 
     def msm_parts(self, parts):
         """parts: list of (points, scalars, n[, points_off, scalars_off]); points is DevicePoints or bytes (X||Y),

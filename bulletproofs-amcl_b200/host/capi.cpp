@@ -172,6 +172,73 @@ static int for_each_proof(bpgpu_ctx* const* ctxs, size_t nctx, size_t count, F f
   return err.load();
 }
 
+template <class C>
+int range_verify_batch_t(bpgpu_ctx* ctx, const char* label, const uint8_t* g_xy, const uint8_t* h_xy, bpgpu_points* G, bpgpu_points* H,
+                         size_t count, size_t m, size_t bits, const uint8_t* proofs, size_t stride, const uint8_t* comms_xy, size_t nthreads,
+                         int32_t* verdicts) {
+  const size_t mb = C::MODBYTES, pb = 2 * mb;
+  const size_t n = m * bits, N = next_power_of_two(n);
+  if (bpgpu_points_len(G) < N || bpgpu_points_len(H) < N) {            // InvalidGeneratorsLength for every proof
+    for (size_t i = 0; i < count; i++) verdicts[i] = BPGPU_E_GENS_LEN;
+    return BPGPU_OK;
+  }
+  int rc;
+  if ((rc = bpgpu_points_precompute(ctx, G)) || (rc = bpgpu_points_precompute(ctx, H))) return rc;
+  size_t lg = 0;
+  while (((size_t)1 << lg) < N) lg++;
+  const size_t F = 2 * N + 2, vn = 6 + m + 5 + 2 * lg;
+  const size_t plen = bph_range_proof_len(C::ID, m, bits);
+  std::vector<uint8_t> fixed(count * F * mb), vpts(count * vn * pb), vscal(count * vn * mb);
+  const G1<C> ident = G1<C>::identity();
+  if (nthreads == 0) nthreads = std::thread::hardware_concurrency();
+  if (nthreads == 0) nthreads = 1;
+  if (nthreads > count) nthreads = count ? count : 1;
+  std::atomic<size_t> next{0};
+  auto worker = [&]() {
+    for (;;) {
+      const size_t i = next.fetch_add(1);
+      if (i >= count) break;
+      uint8_t* fo = fixed.data() + i * F * mb;
+      uint8_t* po = vpts.data() + i * vn * pb;
+      uint8_t* so = vscal.data() + i * vn * mb;
+      R1CSProof<C> p;
+      int st = R1CSProof<C>::from_bytes(proofs + i * stride, plen, &p);
+      typename Verifier<C>::VerificationTerms t;
+      if (!st) {
+        Transcript tr{std::string(label)};
+        Verifier<C> verifier(ctx, tr);
+        for (size_t k = 0; k < m && !st; k++) {
+          Variable var = verifier.commit(G1<C>::from_xy(comms_xy + (i * m + k) * pb));
+          st = positive_no_gadget<C>(verifier, AllocatedQuantity<C>{var, false, FieldElement<C>::zero()}, bits);
+        }
+        Rng<C> os;
+        if (!st) st = verifier.verification_terms_host(p, N, os.next(), &t);
+        if (!st && (t.fixed.size() != F || t.var_points.size() != vn)) st = BPGPU_E_FORMAT;
+      }
+      verdicts[i] = st;
+      if (st) {                                   // keep the device input well formed; the verdict is already decided
+        memset(fo, 0, F * mb);
+        memset(so, 0, vn * mb);
+        for (size_t k = 0; k < vn; k++) memcpy(po + k * pb, ident.xy, pb);
+        continue;
+      }
+      for (size_t k = 0; k < F; k++) t.fixed[k].to_bytes(fo + k * mb);
+      for (size_t k = 0; k < vn; k++) { memcpy(po + k * pb, t.var_points[k].xy, pb); t.var_scalars[k].to_bytes(so + k * mb); }
+    }
+  };
+  std::vector<std::thread> th;
+  for (size_t k = 1; k < nthreads; k++) th.emplace_back(worker);
+  worker();
+  for (auto& x : th) x.join();
+  // [G[..N] | H[..N] | g | h]
+  bpgpu_fixed_run runs[4] = {{G, 0, N, nullptr}, {H, 0, N, nullptr}, {nullptr, 0, 1, g_xy}, {nullptr, 0, 1, h_xy}};
+  std::vector<uint8_t> ident_flags(count + 1);
+  if ((rc = bpgpu_msm_batch_is_identity(ctx, runs, 4, count, fixed.data(), vpts.data(), vscal.data(), vn, ident_flags.data()))) return rc;
+  for (size_t i = 0; i < count; i++)
+    if (verdicts[i] == 0 && !ident_flags[i]) verdicts[i] = BPGPU_E_VERIFY;
+  return BPGPU_OK;
+}
+
 }  // namespace
 
 #define BY_CURVE(ctx, CALL) (bpgpu_ctx_curve(ctx) == BPGPU_BLS12_381 ? CALL(Bls381) : CALL(Bn254))
@@ -318,6 +385,17 @@ int bph_range_verify_many(bpgpu_ctx* const* ctxs, size_t nctx, const char* label
     return 0;
   });
   return BPGPU_OK;
+}
+
+int bph_range_verify_batch(bpgpu_ctx* ctx, const char* label, const uint8_t* g_xy, const uint8_t* h_xy, bpgpu_points* G, bpgpu_points* H,
+                           size_t count, size_t m, size_t bits, const uint8_t* proofs, size_t proof_stride, const uint8_t* comms_xy,
+                           size_t nthreads, int32_t* verdicts) {
+  if (!ctx || !label || !g_xy || !h_xy || !G || !H || (count && (!proofs || !comms_xy || !verdicts))) return BPGPU_E_ARG;
+  if (proof_stride < bph_range_proof_len(bpgpu_ctx_curve(ctx), m, bits)) return BPH_E_BUFFER;
+  if (count == 0) return BPGPU_OK;
+#define CALL(C) range_verify_batch_t<C>(ctx, label, g_xy, h_xy, G, H, count, m, bits, proofs, proof_stride, comms_xy, nthreads, verdicts)
+  return BY_CURVE(ctx, CALL);
+#undef CALL
 }
 
 }  // extern "C"

@@ -555,36 +555,126 @@ class Verifier : public ConstraintSystem<C> {
     return rc;
   }
 
-  int verification_msm(const R1CSProof<C>& proof, const G1<C>& g, const G1<C>& h, const G1Vector<C>& G, const G1Vector<C>& H, const FE& rnd,
-                       bool* is_identity) {
-    const size_t mb = C::MODBYTES;
-    Trace tr("verify");
+  struct Challenges { FE y, z, u, x, w; size_t n1, n, padded_n; };
+  // verifier.rs:279-323: absorb the proof, derive y, z, u, x, w (and run the deferred constraints in between)
+  int replay_transcript(const R1CSProof<C>& proof, size_t gens_len, Challenges* c) {
     transcript_.append_u64("m", V_.size());                            // :279
-    const size_t n1 = num_vars_;
+    c->n1 = num_vars_;
     TP::commit_point(transcript_, "A_I1", proof.A_I1);                 // :282-284
     TP::commit_point(transcript_, "A_O1", proof.A_O1);
     TP::commit_point(transcript_, "S1", proof.S1);
     int rc = create_randomized_constraints();                          // :287
     if (rc) return rc;
-    const size_t n = num_vars_;
-    const size_t padded_n = next_power_of_two(n);
-    if (G.len() < padded_n || H.len() < padded_n) return E_INVALID_GENERATORS_LENGTH;   // :297-299
+    c->n = num_vars_;
+    c->padded_n = next_power_of_two(c->n);
+    if (gens_len < c->padded_n) return E_INVALID_GENERATORS_LENGTH;    // :297-299
     TP::commit_point(transcript_, "A_I2", proof.A_I2);                 // :301-303
     TP::commit_point(transcript_, "A_O2", proof.A_O2);
     TP::commit_point(transcript_, "S2", proof.S2);
-    const FE y = TP::challenge_scalar(transcript_, "y");               // :305-306
-    const FE z = TP::challenge_scalar(transcript_, "z");
+    c->y = TP::challenge_scalar(transcript_, "y");                     // :305-306
+    c->z = TP::challenge_scalar(transcript_, "z");
     TP::commit_point(transcript_, "T_1", proof.T_1);                   // :308-312
     TP::commit_point(transcript_, "T_3", proof.T_3);
     TP::commit_point(transcript_, "T_4", proof.T_4);
     TP::commit_point(transcript_, "T_5", proof.T_5);
     TP::commit_point(transcript_, "T_6", proof.T_6);
-    const FE u = TP::challenge_scalar(transcript_, "u");               // :314-315
-    const FE x = TP::challenge_scalar(transcript_, "x");
+    c->u = TP::challenge_scalar(transcript_, "u");                     // :314-315
+    c->x = TP::challenge_scalar(transcript_, "x");
     TP::commit_scalar(transcript_, "t_x", proof.t_x);                  // :317-321
     TP::commit_scalar(transcript_, "t_x_blinding", proof.t_x_blinding);
     TP::commit_scalar(transcript_, "e_blinding", proof.e_blinding);
-    const FE w = TP::challenge_scalar(transcript_, "w");               // :323
+    c->w = TP::challenge_scalar(transcript_, "w");                     // :323
+    return OK;
+  }
+
+ public:
+  // The terms of the verification MSM (verifier.rs:394-449) computed entirely on the host, split by kind, for the batched
+  // device check (bpgpu_msm_batch_is_identity): `fixed` are the scalars of [G[..N] | H[..N] | g | h], `var_*` the
+  // proof's own points A_I1, A_O1, S1, A_I2, A_O2, S2, V.., T_1, T_3, T_4, T_5, T_6, L.., R.. with their scalars.
+  // Same arithmetic as verify(); meant for small circuits verified in bulk, where a per-proof device round trip costs
+  // more than these O(N) host loops.
+  struct VerificationTerms { size_t padded_n; std::vector<FE> fixed; std::vector<G1<C>> var_points; std::vector<FE> var_scalars; };
+  int verification_terms_host(const R1CSProof<C>& proof, size_t gens_len, const FE& rnd, VerificationTerms* out) {
+    Challenges ch;
+    int rc = replay_transcript(proof, gens_len, &ch);
+    if (rc) return rc;
+    const size_t n1 = ch.n1, n = ch.n, N = ch.padded_n;
+    const FE y = ch.y, z = ch.z, u = ch.u, x = ch.x, w = ch.w;
+    std::vector<FE> wL, wR, wO, wV;
+    FE wc;
+    flattened_constraints(z, &wL, &wR, &wO, &wV, &wc);                 // :325
+    const FE a = proof.ipp_proof.a, b = proof.ipp_proof.b;
+    // ipp.rs:262-312 on the host: challenges, one shared inversion, s[i] = s[i - 2^lg_i] * u^2_{(lg-1) - lg_i}
+    const size_t lg = proof.ipp_proof.L.size();
+    if (lg >= 32 || proof.ipp_proof.R.size() != lg || N != ((size_t)1 << lg)) return E_VERIFICATION;
+    transcript_.innerproduct_domain_sep(N);
+    std::vector<FE> uk(lg), uinv(lg);
+    for (size_t k = 0; k < lg; k++) {
+      TP::commit_point(transcript_, "L", proof.ipp_proof.L[k]);
+      TP::commit_point(transcript_, "R", proof.ipp_proof.R[k]);
+      uk[k] = TP::challenge_scalar(transcript_, "u");
+    }
+    FE prod_inv = FE::one();
+    {                                                                  // FieldElement::batch_invert (ipp.rs:295); y^-1 rides along
+      std::vector<FE> pre(lg + 1);
+      FE run = y;
+      for (size_t k = 0; k < lg; k++) { pre[k] = run; run = run * uk[k]; }
+      FE inv = run.inverse();
+      for (size_t k = lg; k-- > 0;) { uinv[k] = inv * pre[k]; inv = inv * uk[k]; }
+      // inv is now y^-1 (0 if any factor was 0, as batch inversion of a zero would be)
+      pre[lg] = inv;
+      for (size_t k = 0; k < lg; k++) prod_inv = prod_inv * uinv[k];
+      uinv.push_back(inv);
+    }
+    const FE y_inv = uinv[lg];
+    std::vector<FE> s(N);
+    s[0] = prod_inv;
+    for (size_t i = 1; i < N; i++) {
+      size_t lg_i = 0;
+      while (((size_t)2 << lg_i) <= i) lg_i++;
+      s[i] = s[i - ((size_t)1 << lg_i)] * uk[(lg - 1) - lg_i].square();
+    }
+    // verifier.rs:341-390
+    out->padded_n = N;
+    out->fixed.assign(2 * N + 2, FE::zero());
+    FE yinv_i = FE::one(), delta = FE::zero();
+    const FE one = FE::one();
+    for (size_t i = 0; i < N; i++) {
+      const FE wl = i < n ? wL[i] : FE::zero(), wr = i < n ? wR[i] : FE::zero(), wo = i < n ? wO[i] : FE::zero();
+      const FE yw = wr * yinv_i;
+      if (i < n) delta = delta + yw * wl;
+      FE gs = x * yw - a * s[i];
+      FE hs = yinv_i * (x * wl + wo - b * s[N - 1 - i]) - one;
+      if (i >= n1) { gs = u * gs; hs = u * hs; }
+      out->fixed[i] = gs;
+      out->fixed[N + i] = hs;
+      yinv_i = yinv_i * y_inv;
+    }
+    const FE xx = x.square(), xxx = x * xx;
+    const FE r_xx = rnd * xx, rx = rnd * x, rx3 = rnd * xxx, rx4 = rx3 * x, rx5 = rx4 * x, rx6 = rx5 * x;
+    out->fixed[2 * N] = w * (proof.t_x - a * b) + rnd * (xx * (wc + delta) - proof.t_x);      // scalar of g  (:421)
+    out->fixed[2 * N + 1] = (proof.e_blinding + rnd * proof.t_x_blinding).negation();         // scalar of h  (:424)
+    out->var_points = {proof.A_I1, proof.A_O1, proof.S1, proof.A_I2, proof.A_O2, proof.S2};
+    out->var_scalars = {x, xx, xxx, u * x, u * xx, u * xxx};
+    for (size_t j = 0; j < V_.size(); j++) { out->var_points.push_back(V_[j]); out->var_scalars.push_back(wV[j] * r_xx); }
+    const G1<C>* T[5] = {&proof.T_1, &proof.T_3, &proof.T_4, &proof.T_5, &proof.T_6};
+    const FE ts[5] = {rx, rx3, rx4, rx5, rx6};
+    for (int k = 0; k < 5; k++) { out->var_points.push_back(*T[k]); out->var_scalars.push_back(ts[k]); }
+    for (size_t k = 0; k < lg; k++) { out->var_points.push_back(proof.ipp_proof.L[k]); out->var_scalars.push_back(uk[k].square()); }
+    for (size_t k = 0; k < lg; k++) { out->var_points.push_back(proof.ipp_proof.R[k]); out->var_scalars.push_back(uinv[k].square()); }
+    return OK;
+  }
+
+ private:
+  int verification_msm(const R1CSProof<C>& proof, const G1<C>& g, const G1<C>& h, const G1Vector<C>& G, const G1Vector<C>& H, const FE& rnd,
+                       bool* is_identity) {
+    const size_t mb = C::MODBYTES;
+    Trace tr("verify");
+    Challenges ch;
+    int rc = replay_transcript(proof, G.len() < H.len() ? G.len() : H.len(), &ch);
+    if (rc) return rc;
+    const size_t n1 = ch.n1, n = ch.n, padded_n = ch.padded_n;
+    const FE y = ch.y, z = ch.z, u = ch.u, x = ch.x, w = ch.w;
     std::vector<FE> wL, wR, wO, wV;
     FE wc;
     tr.mark("transcript");

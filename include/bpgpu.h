@@ -123,6 +123,15 @@ int bpgpu_msm_parts(bpgpu_ctx* ctx, const bpgpu_msm_part* parts, size_t nparts, 
  * points.  This is the prover's A_I, A_O, S triple (prover.rs:347-362, 404-427): with precomputed generator tables the
  * three are evaluated by one launch pair. */
 int bpgpu_msm_parts_batch(bpgpu_ctx* ctx, const bpgpu_msm_part* parts, const size_t* counts, size_t nmsm, uint8_t* out_xy);
+/* ---- batches of verification MSMs sharing the fixed generators (verifier.rs:451-456 for many proofs at once) -------
+ * R_b = sum_i f[b][i] * F_i + sum_j v[b][j] * V[b][j] for b < batch, reduced to is_identity[b] = (R_b == identity).
+ * The fixed terms F are the concatenation of `runs` (device tables WITH window tables: bpgpu_points_precompute; or a single
+ * host base, whose table is built and cached in the ctx) -- F = sum of runs[k].n; fixed_scalars_be is batch x F scalars,
+ * var_points_xy / var_scalars_be are batch x vn proof-specific points and scalars.  Every proof keeps its own verdict:
+ * nothing is merged with random weights (the reference has no batch API). */
+typedef struct bpgpu_fixed_run { const bpgpu_points* points; size_t off; size_t n; const uint8_t* host_base_xy; } bpgpu_fixed_run;
+int bpgpu_msm_batch_is_identity(bpgpu_ctx* ctx, const bpgpu_fixed_run* runs, size_t nruns, size_t batch, const uint8_t* fixed_scalars_be,
+                                const uint8_t* var_points_xy, const uint8_t* var_scalars_be, size_t vn, uint8_t* is_identity);
 /* window width the MSM would use for n terms (reporting only) */
 int bpgpu_msm_window_bits(size_t n);
 

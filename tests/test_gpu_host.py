@@ -181,5 +181,16 @@ def test_batch_prove_verify_keeps_per_proof_verdicts(bp, ctx_bls):
     bad[9 * stride] = 5                            # point tag of proof 9 -> FormatError
     v = bp.range_verify_many(ctxs, b"Batch", gx, hx, dG, dH, count, m, bits, bytes(bad), stride, comms)
     assert v == [0, 0, 0, 0, 0, -4, 0, 0, 0, -5, 0, 0]
+    # the same verdicts from ONE device call for the whole batch (bph_range_verify_batch); the tables it needs are built on
+    # first use, and the generator-length guard (verifier.rs:297-299) applies per proof
+    dG2, dH2 = ctx_bls.get_generators("G", m * bits), ctx_bls.get_generators("H", m * bits)
+    assert bp.range_verify_batch(ctx_bls, b"Batch", gx, hx, dG2, dH2, count, m, bits, proofs, stride, comms) == [0] * count
+    assert bp.range_verify_batch(ctx_bls, b"Batch", gx, hx, dG2, dH2, count, m, bits, bytes(bad), stride, comms, nthreads=3) == v
+    assert bp.range_verify_batch(ctx_bls, b"Other", gx, hx, dG2, dH2, 3, m, bits, proofs, stride, comms) == [-4] * 3
+    swapped = comms[2 * 48:4 * 48] + comms[:2 * 48] + comms[4 * 48:]
+    assert bp.range_verify_batch(ctx_bls, b"Batch", gx, hx, dG2, dH2, 3, m, bits, proofs, stride, swapped) == [-4, -4, 0]
+    small = ctx_bls.get_generators("G", 4)
+    assert bp.range_verify_batch(ctx_bls, b"Batch", gx, hx, small, small, 2, m, bits, proofs, stride, comms) == [-3, -3]
+    assert bp.range_verify_batch(ctx_bls, b"Batch", gx, hx, dG2, dH2, 0, m, bits, b"", stride, b"") == []
     for c in ctxs[1:]:
         c.close()

@@ -158,3 +158,41 @@ def test_msm_over_precomputed_tables(which, ctx_bls, ctx_bn):
     assert got == C.g1_xy_bytes(C.msm(extra, es))
     plain.free()
     tab.free()
+
+
+@pytest.mark.parametrize("which", ["bls", "bn"])
+def test_batch_identity_check(which, ctx_bls, ctx_bn):
+    """bpgpu_msm_batch_is_identity: per-instance verdict of sum f_i*F_i + sum v_j*V_j == identity, with fixed terms from a
+    precomputed table (at an offset) and from a host base, variable points incl. the identity and repeated points."""
+    ctx = ctx_bls if which == "bls" else ctx_bn
+    C = curve_of(ctx)
+    nf, vn, batch = 9, 5, 7
+    fixed = rand_points(C, nf + 3, 5)
+    hb = C.g1_from_msg_hash(b"h")
+    tab = ctx.upload_points(enc_points(C, fixed)).precompute()
+    fs, vp, vs, expect = [], [], [], []
+    for b in range(batch):
+        f = C.synth_scalars(40 + b, nf + 1)
+        if b == 2:
+            f = [0] * (nf + 1)
+        V = rand_points(C, vn - 1, 100 + b)
+        if b == 3:
+            V[1] = C.INF
+            V[2] = V[0]
+        v = C.synth_scalars(60 + b, vn - 1)
+        R = C.msm(fixed[2:2 + nf] + [hb] + V, f + v)
+        last_s = C.r - 1
+        if b % 2 == 1:
+            last_s = C.r - 2                                # wrong: sum is R - 2R = -R, not the identity
+        fs += f
+        vp += V + [R]
+        vs += v + [last_s]
+        expect.append(1 if (b % 2 == 0 or C.is_inf(R)) else 0)
+    got = ctx.msm_batch_is_identity([(tab, 2, nf), C.g1_xy_bytes(hb)], batch, enc_scalars(C, fs), enc_points(C, vp), enc_scalars(C, vs), vn)
+    assert list(got) == expect
+    # no variable part at all: only the all-zero instance is the identity
+    got = ctx.msm_batch_is_identity([(tab, 2, nf), C.g1_xy_bytes(hb)], batch, enc_scalars(C, fs), b"", b"", 0)
+    assert list(got) == [1 if b == 2 else 0 for b in range(batch)]
+    plain = ctx.upload_points(enc_points(C, fixed))
+    with pytest.raises(Exception):                          # tables are required
+        ctx.msm_batch_is_identity([(plain, 0, nf)], 1, enc_scalars(C, fs[:nf]), b"", b"", 0)
