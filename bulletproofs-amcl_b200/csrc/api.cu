@@ -194,16 +194,19 @@ __global__ void k_dbl_chain(int iters, const XYZZ<F>* in, XYZZ<F>* out) {
 }
 
 template <class Curve>
-int points_from_host(bpgpu_ctx* ctx, const uint8_t* xy, size_t n, void* dst) {
+static int points_from_host_on(bpgpu_ctx* ctx, cudaStream_t st, const uint8_t* xy, size_t n, void* dst) {
   if (n == 0) return BPGPU_OK;
   size_t bytes = n * 2 * Curve::MODBYTES;
   int rc = ctx->io_dev.reserve(bytes);
   if (rc) return rc;
-  BP_CUDA_OK(cudaMemcpyAsync(ctx->io_dev.p, xy, bytes, cudaMemcpyHostToDevice, ctx->stream));
-  k_points_from_be<Curve><<<(unsigned)((n + 127) / 128), 128, 0, ctx->stream>>>((const uint8_t*)ctx->io_dev.p, n,
-                                                                              (Affine<typename Curve::Fq>*)dst);
+  BP_CUDA_OK(cudaMemcpyAsync(ctx->io_dev.p, xy, bytes, cudaMemcpyHostToDevice, st));
+  k_points_from_be<Curve><<<(unsigned)((n + 127) / 128), 128, 0, st>>>((const uint8_t*)ctx->io_dev.p, n, (Affine<typename Curve::Fq>*)dst);
   ctx->launches++;
   return launch_check(ctx, "k_points_from_be");
+}
+template <class Curve>
+int points_from_host(bpgpu_ctx* ctx, const uint8_t* xy, size_t n, void* dst) {
+  return points_from_host_on<Curve>(ctx, ctx->stream, xy, n, dst);
 }
 template int points_from_host<Bls>(bpgpu_ctx*, const uint8_t*, size_t, void*);
 template int points_from_host<Bn>(bpgpu_ctx*, const uint8_t*, size_t, void*);
@@ -334,6 +337,8 @@ int bpgpu_ctx_create(int curve, int device, bpgpu_ctx** out) {
   BP_CUDA_OK(cudaGetDeviceProperties(&prop, device));
   c->sm_count = prop.multiProcessorCount;
   BP_CUDA_OK(cudaStreamCreateWithFlags(&c->stream, cudaStreamNonBlocking));
+  BP_CUDA_OK(cudaStreamCreateWithFlags(&c->copy_stream, cudaStreamNonBlocking));
+  BP_CUDA_OK(cudaEventCreateWithFlags(&c->points_ready, cudaEventDisableTiming));
   {
     cudaMemPool_t pool;
     uint64_t keep = ~0ull;                      // keep freed blocks in the pool: the next proof reuses them
@@ -357,6 +362,8 @@ void bpgpu_ctx_destroy(bpgpu_ctx* c) {
   c->fr_tmp.release(); c->fr_out.release(); c->fr_args.release(); c->fr_pow.release(); c->fr_pow2.release();
   if (c->pinned) cudaFreeHost(c->pinned);
   cudaStreamDestroy(c->stream);
+  if (c->copy_stream) cudaStreamDestroy(c->copy_stream);
+  if (c->points_ready) cudaEventDestroy(c->points_ready);
   delete c;
 }
 
@@ -530,15 +537,28 @@ int bpgpu_msm_refs(bpgpu_ctx* ctx, const uint8_t* points_xy, const uint8_t* scal
   int rc = ctx->msm_d.reserve(n * psz + 32);
   if (rc) return rc;
   if ((rc = ctx->msm_c.reserve(n * 32 + 32))) return rc;
-#define CALL(C) points_from_host<C>(ctx, points_xy, n, ctx->msm_d.p)
-  rc = DISPATCH(ctx, CALL);
-#undef CALL
-  if (rc) return rc;
+  // Scalars first: the digit / sort stages need only them.  For large n the points follow on the copy queue, so their
+  // transfer and conversion run under k_digits / k_scan / k_scatter; k_chunk_acc waits for `points_ready`.
+  // (Every entry point returns with the ctx idle, so the staging buffers are free when we get here.)
+  const bool overlap = n >= ((size_t)1 << 14);
 #define CALL(C) scalars_upload_t<C>(ctx, scalars_be, n, 0, ctx->msm_c.p, ctx->io_dev2)
   rc = DISPATCH(ctx, CALL);
 #undef CALL
   if (rc) return rc;
-  return msm_to_host(ctx, ctx->msm_d.p, ctx->msm_c.p, false, n, out_xy);
+#define CALL(C) points_from_host_on<C>(ctx, overlap ? ctx->copy_stream : ctx->stream, points_xy, n, ctx->msm_d.p)
+  rc = DISPATCH(ctx, CALL);
+#undef CALL
+  if (rc) { if (overlap) cudaStreamSynchronize(ctx->copy_stream); return rc; }
+  if (overlap) {
+    BP_CUDA_OK(cudaEventRecord(ctx->points_ready, ctx->copy_stream));
+    ctx->wait_points = true;
+  }
+  rc = msm_to_host(ctx, ctx->msm_d.p, ctx->msm_c.p, false, n, out_xy);
+  if (ctx->wait_points) {                  // msm_run did not get as far as the wait (error path): drain the copy queue
+    ctx->wait_points = false;
+    cudaStreamSynchronize(ctx->copy_stream);
+  }
+  return rc;
 }
 
 // ------------------------------------------------------------------ self tests

@@ -64,6 +64,11 @@ struct bpgpu_ctx {
   int device = 0;
   int sm_count = 148;
   cudaStream_t stream = nullptr;
+  // second queue for the host->device copy of the points of a large bpgpu_msm_refs: the copy and the byte->limb
+  // conversion overlap the scalar pipeline (digits, scan, scatter) on `stream`; k_chunk_acc waits on `points_ready`
+  cudaStream_t copy_stream = nullptr;
+  cudaEvent_t points_ready = nullptr;
+  bool wait_points = false;        // consumed by the next msm_run
   uint64_t launches = 0;
   // MSM scratch
   bp::Scratch msm_a, msm_b, msm_c, msm_d, msm_e, io_dev, io_dev2;

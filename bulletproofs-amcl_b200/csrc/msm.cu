@@ -16,8 +16,9 @@
 //                   serialisation on a hot bucket (0/1 witness scalars put half of all points
 //                   in one bucket: helper_constraints/positive_no.rs:18-24)
 //   k_giant         buckets spanning > T chunks: block-wide tree reduction, collapsed in place
-//   k_reduce_l1     one WARP per 32*L1 buckets: lanes run top-down running sums over their buckets'
-//                   chunk partials, then a warp suffix-scan turns them into sum (b-base)*B_b
+//   k_merge         one thread per chunk boundary a bucket straddles: its partial sums folded into one
+//   k_reduce_l1     one WARP per 32*L1 buckets: lanes run top-down running sums over their buckets
+//                   (two additions per bucket), then a warp suffix-scan turns them into sum (b-base)*B_b
 //   k_reduce_l2     per window: combine the segment results (two warps)
 //   (host)          Horner over the W window sums + affine normalisation: a ~256-doubling
 //                   dependent chain, ~0.1 ms on one CPU core vs milliseconds on one GPU thread
@@ -166,8 +167,8 @@ __global__ void __launch_bounds__(256) k_scatter(MsmGeom g, const uint32_t* __re
   }
 }
 
-template <class Fq>
-__global__ void __launch_bounds__(128) k_chunk_acc(MsmGeom g, const Affine<Fq>* __restrict__ pts,
+template <class Fq, int MINB>
+__global__ void __launch_bounds__(128, MINB) k_chunk_acc(MsmGeom g, const Affine<Fq>* __restrict__ pts,
                                                    const uint32_t* __restrict__ sidx, const uint32_t* __restrict__ skey,
                                                    const uint32_t* __restrict__ bstart, const uint32_t* __restrict__ pstart,
                                                    XYZZ<Fq>* __restrict__ partials) {
@@ -241,6 +242,36 @@ __global__ void __launch_bounds__(GIANT_BLOCK) k_giant(MsmGeom g, const uint32_t
   }
 }
 
+// Buckets that straddle chunk boundaries have several partial sums (one per chunk they touch).  Phase A of the bucket
+// reduction folds them into ONE sum per bucket, in place at the bucket's first partial slot, with full parallelism: the
+// thread of the chunk in which the bucket STARTS does it, and only if the bucket continues into the next chunk (so a
+// thread has at most one bucket to fold, and -- the chunk length being about two buckets -- almost always exactly one
+// addition: no divergence, W * n / S independent threads).  k_giant has already collapsed the > GIANT_T cases.
+// Afterwards pcount[b] is 0 or 1 for every bucket and k_reduce_l1 is two additions per bucket with no inner loop.
+template <class Fq>
+__global__ void __launch_bounds__(128) k_merge(MsmGeom g, const uint32_t* __restrict__ skey, const uint32_t* __restrict__ bstart,
+                                               const uint32_t* __restrict__ pstart, uint32_t* __restrict__ pcount,
+                                               XYZZ<Fq>* __restrict__ partials) {
+  const uint32_t gid = blockIdx.x * blockDim.x + threadIdx.x;
+  if (gid >= (uint32_t)g.W * g.nchunk) return;
+  const uint32_t w = gid / g.nchunk, t = gid - w * g.nchunk;
+  const uint32_t* bs = bstart + (size_t)w * (g.nbp + 1);
+  const uint32_t cnt = bs[g.nbp];
+  const uint64_t e1 = (uint64_t)(t + 1) * g.S;              // first entry of the next chunk
+  if (e1 >= cnt) return;
+  const uint32_t* key = skey + (size_t)w * g.n;
+  const uint32_t b = key[e1 - 1];
+  if (key[e1] != b || bs[b] / g.S != t) return;             // no straddle, or the bucket began in an earlier chunk
+  uint32_t* pc = pcount + (size_t)w * g.nbp;
+  const uint32_t np = pc[b];
+  if (np <= 1) return;                                      // collapsed by k_giant
+  XYZZ<Fq>* in = partials + (size_t)w * g.pcap + pstart[(size_t)w * (g.nbp + 1) + b];
+  XYZZ<Fq> acc = load_vec(in);
+  for (uint32_t k = 1; k < np; k++) { XYZZ<Fq> q = load_vec(in + k); acc.add_inl(q); }
+  store_vec(in, acc);
+  pc[b] = 1;
+}
+
 template <class Fq>
 __device__ __forceinline__ XYZZ<Fq> shfl_down_xyzz(const XYZZ<Fq>& v, int o) {
   XYZZ<Fq> r;
@@ -296,57 +327,14 @@ __global__ void __launch_bounds__(128) k_reduce_l1(MsmGeom g, const uint32_t* __
   if (lo <= g.nbp - 1) {
     const uint32_t hi = min(lo + L1 - 1, g.nbp - 1);
     for (uint32_t b = hi; b >= lo; b--) {
-      const uint32_t p0 = ps[b], p1 = p0 + pc[b];
-      for (uint32_t k = p0; k < p1; k++) { XYZZ<Fq> q = load_vec(in + k); run.add(q); }
-      acc.add(run);
+      if (pc[b]) { XYZZ<Fq> q = load_vec(in + ps[b]); run.add_inl(q); }      // k_merge left ONE sum per bucket
+      acc.add_inl(run);
     }
   }
   warp_weighted_sum(acc, run, g.lgL1);
   if (lane == 0) { store_vec(segA + warp, acc); store_vec(segS + warp, run); }
 }
 
-
-// Variant with one merged stream of (partial | boundary) additions per lane and an inlined group law (BPGPU_L1EVENT=1).
-// Measured at 2^20: equal at 16 buckets per lane, faster at 8, never faster overall -- kept for the record.
-template <class Fq>
-__global__ void __launch_bounds__(32) k_reduce_l1_events(MsmGeom g, const uint32_t* __restrict__ pstart, const uint32_t* __restrict__ pcount,
-                                                  const XYZZ<Fq>* __restrict__ partials, XYZZ<Fq>* __restrict__ segA,
-                                                  XYZZ<Fq>* __restrict__ segS) {
-  // one warp per block: 1024 independent warps spread evenly over the SMs (no 2-vs-1 block quantisation)
-  const uint32_t warp = blockIdx.x;
-  const int lane = threadIdx.x & 31;
-  if (warp >= (uint32_t)g.W * g.nseg) return;
-  const uint32_t w = warp / g.nseg, seg = warp - w * g.nseg;
-  const uint32_t L1 = 1u << g.lgL1;
-  const uint32_t* ps = pstart + (size_t)w * (g.nbp + 1);
-  const uint32_t* pc = pcount + (size_t)w * g.nbp;
-  const XYZZ<Fq>* in = partials + (size_t)w * g.pcap;
-  const uint32_t lo = seg * 32 * L1 + (uint32_t)lane * L1 + 1;
-  XYZZ<Fq> run = XYZZ<Fq>::inf(), acc = XYZZ<Fq>::inf();
-  if (lo <= g.nbp - 1) {
-    // One stream of "events" per lane, top bucket first: every chunk partial of the bucket (run += partial), then the
-    // bucket boundary (acc += run).  Both kinds go through ONE inlined addition with lane-selected operands, so lanes
-    // whose buckets have different numbers of partials still execute the same instruction stream.
-    uint32_t b = min(lo + L1 - 1, g.nbp - 1);
-    uint32_t k0 = ps[b], k = k0 + pc[b];
-    for (;;) {
-      const bool is_partial = k > k0;
-      XYZZ<Fq> q = run;
-      if (is_partial) q = load_vec(in + (k - 1));
-      XYZZ<Fq> A = select(is_partial, run, acc);
-      A.add_inl(q);
-      run = select(is_partial, A, run);
-      acc = select(is_partial, acc, A);
-      if (is_partial) { k--; continue; }
-      if (b == lo) break;
-      b--;
-      k0 = ps[b];
-      k = k0 + pc[b];
-    }
-  }
-  warp_weighted_sum(acc, run, g.lgL1);
-  if (lane == 0) { store_vec(segA + warp, acc); store_vec(segS + warp, run); }
-}
 
 // Level 2: per window, combine the nseg segment results (one block of 64 threads per window):
 //   P_w = sum_seg segA ,  Q_w = sum_seg seg * segS ;  window sum = P_w + 2^(5+lgL1) * Q_w
@@ -589,13 +577,23 @@ int msm_run(bpgpu_ctx* ctx, const Affine<typename Curve::Fq>* d_points, const vo
     k_scatter<<<(unsigned)blocks, 256, 0, st>>>(g, digits, cursor, sidx, skey);
     tm.mark("scatter");
   }
+  if (ctx->wait_points) {                    // points still arriving on the copy queue (bpgpu_msm_refs)
+    ctx->wait_points = false;
+    BP_CUDA_OK(cudaStreamWaitEvent(st, ctx->points_ready, 0));
+  }
   {
     uint32_t threads = (uint32_t)g.W * g.nchunk;
-    k_chunk_acc<Fq><<<(threads + 127) / 128, 128, 0, st>>>(g, d_points, sidx, skey, bstart, pstart, partials);
+    static const char* env_mb = getenv("BPGPU_CHUNK_MINB");
+    if (env_mb && atoi(env_mb) == 3) k_chunk_acc<Fq, 3><<<(threads + 127) / 128, 128, 0, st>>>(g, d_points, sidx, skey, bstart, pstart, partials);
+    else k_chunk_acc<Fq, 2><<<(threads + 127) / 128, 128, 0, st>>>(g, d_points, sidx, skey, bstart, pstart, partials);
     tm.mark("chunk_acc");
   }
   k_giant<Fq><<<ctx->sm_count * 2, GIANT_BLOCK, 0, st>>>(g, pstart, hist, partials, giant, giant + 1);
-  tm.mark("giant");
+  {
+    uint32_t threads = (uint32_t)g.W * g.nchunk;
+    k_merge<Fq><<<(threads + 127) / 128, 128, 0, st>>>(g, skey, bstart, pstart, hist, partials);
+  }
+  tm.mark("giant");                                          // stage 4 = k_giant + k_merge
   int qshift = 5 + g.lgL1;
   if (g.nrows) {
     k_bucket_rows<Fq><<<g.W * g.nrows, 256, 0, st>>>(g, pstart, hist, partials, dense, rowsum);
@@ -607,14 +605,12 @@ int msm_run(bpgpu_ctx* ctx, const Affine<typename Curve::Fq>* d_points, const vo
     qshift = 0;
   } else {
     uint32_t warps = (uint32_t)g.W * g.nseg;
-    static const char* env_ev = getenv("BPGPU_L1EVENT");
-    if (env_ev && atoi(env_ev)) k_reduce_l1_events<Fq><<<warps, 32, 0, st>>>(g, pstart, hist, partials, segA, segS);
-    else k_reduce_l1<Fq><<<(warps * 32 + 127) / 128, 128, 0, st>>>(g, pstart, hist, partials, segA, segS);
+    k_reduce_l1<Fq><<<(warps * 32 + 127) / 128, 128, 0, st>>>(g, pstart, hist, partials, segA, segS);
     tm.mark("reduce_l1");
     k_reduce_l2<Fq><<<g.W, 64, 0, st>>>(g, segA, segS, winsum, winsum + g.W);
     tm.mark("reduce_l2");
   }
-  ctx->launches += 7;
+  ctx->launches += 8;
   res->W = g.W; res->c = g.c; res->qshift = qshift; res->d_winsum = winsum;
   int lrc = launch_check(ctx, "msm");
   tm.report(g, ctx);
