@@ -37,7 +37,20 @@ static void ec_op(int op, const uint32_t* p, const uint32_t* q, uint32_t k, uint
   memcpy(out, &P, sizeof(P));
 }
 
+template <class F>
+static void fp_mul2(const uint32_t* a, const uint32_t* b, const uint32_t* c, const uint32_t* d, uint32_t* out) {
+  F x, y, z, w;
+  memcpy(x.v, a, sizeof(x.v)); memcpy(y.v, b, sizeof(y.v)); memcpy(z.v, c, sizeof(z.v)); memcpy(w.v, d, sizeof(w.v));
+  F r = F::mul2(x, y, z, w);
+  memcpy(out, r.v, sizeof(r.v));
+}
+
 extern "C" {
+// (a*b + c*d) / R mod p, curve fields only (field 0 = BLS12-381 Fq, 2 = BN254 Fq)
+void hc_fp_mul2(int field, const uint32_t* a, const uint32_t* b, const uint32_t* c, const uint32_t* d, uint32_t* out) {
+  if (field == 0) fp_mul2<Fp<BlsFq>>(a, b, c, d, out);
+  else fp_mul2<Fp<BnFq>>(a, b, c, d, out);
+}
 void hc_fp_op(int field, int op, const uint32_t* a, const uint32_t* b, uint32_t* out) {
   switch (field) {
     case 0: fp_op<Fp<BlsFq>>(op, a, b, out); break;

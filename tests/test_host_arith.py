@@ -51,6 +51,29 @@ def test_montgomery_schedule(hc, fid, p, n):
         assert op(5, a * R % p) == pow(a, p - 2, p) * R % p
 
 
+@pytest.mark.parametrize("fid,p,n", [(0, B.p, 12), (2, N.p, 8)])
+def test_fused_two_product_reduction(hc, fid, p, n):
+    """Fp::mul2 = (a*b + c*d)/R mod p with one reduction (the Y3 term of the group law), incl. the extreme operands
+    p-1 and the non-canonical multiplicand p that a negated zero could produce."""
+    R = 1 << (32 * n)
+    Rinv = pow(R, -1, p)
+    rnd = random.Random(100 + fid)
+    edge = [0, 1, p - 1, p - 2, R % p]
+    vals = edge + [rnd.randrange(p) for _ in range(60)]
+
+    def mul2(a, b, c, d):
+        out = (ctypes.c_uint32 * n)()
+        hc.hc_fp_mul2(fid, _L(a, n), _L(b, n), _L(c, n), _L(d, n), out)
+        return _I(out)
+    for a in vals:
+        for _ in range(6):
+            b, c, d = rnd.choice(vals), rnd.choice(vals), rnd.choice(vals)
+            assert mul2(a, b, c, d) == (a * b + c * d) * Rinv % p
+    for x in edge:
+        assert mul2(p - 1, p - 1, p - 1, p - 1) == 2 * (p - 1) * (p - 1) * Rinv % p
+        assert mul2(x, p - 1, p, p - 1) == (x * (p - 1)) * Rinv % p          # c = p acts as 0
+
+
 @pytest.mark.parametrize("cid,C,n", [(0, B, 12), (1, N, 8)])
 def test_xyzz_group_law(hc, cid, C, n):
     p, R = C.p, 1 << (32 * n)
