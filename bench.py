@@ -261,6 +261,8 @@ def main():
     real_stdout = os.dup(1)
     os.dup2(2, 1)
 
+    # 16 contexts (streams) per GPU submit small launches concurrently: give them their own hardware queues (default 8)
+    os.environ.setdefault("CUDA_DEVICE_MAX_CONNECTIONS", "32")
     import torch
     import bulletproofs_amcl_b200 as bp
 

@@ -268,8 +268,9 @@ int msm_mixed_to_host(bpgpu_ctx* ctx, const TableSeg* segs, int nsegs, const voi
   int rc;
   size_t tn = 0;
   for (int k = 0; k < nsegs; k++) tn += segs[k].n;
+  int hp = 0;
   if (tn) {
-    rc = bls ? table_sum_run<Bls>(ctx, segs, nsegs) : table_sum_run<Bn>(ctx, segs, nsegs);
+    rc = bls ? table_sum_run<Bls>(ctx, segs, nsegs, 1, &hp) : table_sum_run<Bn>(ctx, segs, nsegs, 1, &hp);
     if (rc) return rc;
   }
   if (n) {
@@ -278,8 +279,13 @@ int msm_mixed_to_host(bpgpu_ctx* ctx, const TableSeg* segs, int nsegs, const voi
   }
   uint8_t* tsum = ctx->pinned + 2 * 128 * psz;      // after the window sums (W <= 86 at c = 3)
   if (res.W) BP_CUDA_OK(cudaMemcpyAsync(ctx->pinned, res.d_winsum, 2 * res.W * psz, cudaMemcpyDeviceToHost, ctx->stream));
-  if (tn) BP_CUDA_OK(cudaMemcpyAsync(tsum, ctx->tbl_part.p, psz, cudaMemcpyDeviceToHost, ctx->stream));
+  if (tn) {
+    if (hp) BP_CUDA_OK(cudaMemcpyAsync(tsum, (const uint8_t*)ctx->tbl_part.p + TBL_MAX_GROUPS * psz, (size_t)hp * psz, cudaMemcpyDeviceToHost,
+                                       ctx->stream));
+    else BP_CUDA_OK(cudaMemcpyAsync(tsum, ctx->tbl_part.p, psz, cudaMemcpyDeviceToHost, ctx->stream));
+  }
   if (res.W || tn) BP_CUDA_OK(cudaStreamSynchronize(ctx->stream));
+  if (hp) { if (bls) host_sum_partials<BlsFq>(tsum, 1, hp); else host_sum_partials<BnFq>(tsum, 1, hp); }
   if (bls) msm_finish_mixed<BlsFq>(ctx->pinned, res.W, res.c, res.qshift, tn ? tsum : nullptr, mb, out_xy);
   else msm_finish_mixed<BnFq>(ctx->pinned, res.W, res.c, res.qshift, tn ? tsum : nullptr, mb, out_xy);
   return BPGPU_OK;

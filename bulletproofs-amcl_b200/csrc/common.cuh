@@ -177,7 +177,12 @@ struct TableSeg { const void* table; const void* scalars; uint32_t n; int mont; 
 template <class Curve> int build_tables(bpgpu_ctx* ctx, const void* d_affine, size_t n, void** table_out);
 // per group g: sum over its segments of sum_i s_i * P_i, left as XYZZ points at ctx->tbl_part.p[0 .. ngroups)
 // (no doublings, no buckets); one launch pair for all groups
-template <class Curve> int table_sum_run(bpgpu_ctx* ctx, const TableSeg* segs, int nsegs, int ngroups = 1);
+// host_partials (optional): the caller finishes on the host; if the launch leaves per-block sums instead of the group
+// totals, *host_partials = blocks per group and group g's sums are at tbl_part.p[TBL_MAX_GROUPS + g * blocks + b]
+// (at most TBL_HOST_PARTIALS in all), else *host_partials = 0 and the totals are at tbl_part.p[g]
+static const int TBL_HOST_PARTIALS = 160;
+template <class Curve> int table_sum_run(bpgpu_ctx* ctx, const TableSeg* segs, int nsegs, int ngroups = 1, int* host_partials = nullptr);
+template <class FqParams> void host_sum_partials(uint8_t* xyzz_bytes, int ngroups, int per);
 // table-only MSMs, one per group: device sums, one D2H, one shared inversion for the affine results
 int msm_tables_to_host(bpgpu_ctx* ctx, const TableSeg* segs, int nsegs, int ngroups, uint8_t* const* outs_xy);
 // (fixed-base cache lookup) table of a point that is one of the bases of a cached bpgpu_fixed_bases, or nullptr

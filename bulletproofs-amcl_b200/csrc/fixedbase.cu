@@ -32,7 +32,7 @@ template <class Fq>
 __device__ __forceinline__ XYZZ<Fq> block_tree_sum_256(const XYZZ<Fq>& v, XYZZ<Fq>* sm) {
   store_vec(sm + threadIdx.x, v);
   __syncthreads();
-  for (int o = 128; o > 0; o >>= 1) {
+  for (int o = (int)blockDim.x / 2; o > 0; o >>= 1) {      // blockDim.x = 64 or 256
     if ((int)threadIdx.x < o) {
       XYZZ<Fq> a = load_vec(sm + threadIdx.x), b = load_vec(sm + threadIdx.x + o);
       a.add(b);
@@ -207,7 +207,7 @@ template int build_tables<Bls>(bpgpu_ctx*, const void*, size_t, void**);
 template int build_tables<Bn>(bpgpu_ctx*, const void*, size_t, void**);
 
 template <class Curve>
-int table_sum_run(bpgpu_ctx* ctx, const TableSeg* segs, int nsegs, int ngroups) {
+int table_sum_run(bpgpu_ctx* ctx, const TableSeg* segs, int nsegs, int ngroups, int* host_partials) {
   using Fq = typename Curve::Fq;
   if (nsegs > TBL_MAX_SEGS || ngroups < 1 || ngroups > TBL_MAX_GROUPS) return BPGPU_E_ARG;
   TableSegs ts;
@@ -233,23 +233,34 @@ int table_sum_run(bpgpu_ctx* ctx, const TableSeg* segs, int nsegs, int ngroups) 
   ts.gfirst[ngroups] = q;
   ts.start[q] = 0;
   if (q > TBL_MAX_SEGS) return BPGPU_E_ARG;
-  uint32_t blocks = (maxtotal * 8 + 255) / 256;
+  // Every level of a block tree is one dependent XYZZ addition (~15 us): these sums are latency bound, so when the
+  // caller finishes on the host anyway (host_partials) small sums use 64-thread blocks (6 tree levels instead of 8) and
+  // the block results go to the host as they are -- it adds a few dozen points in less time than a second launch takes.
+  const uint32_t threads = maxtotal * 8;
+  uint32_t bs = 256;
+  if (host_partials && (threads + 63) / 64 * ngroups <= (uint32_t)TBL_HOST_PARTIALS) bs = 64;
+  uint32_t blocks = (threads + bs - 1) / bs;
   if (blocks == 0) blocks = 1;
   int rc = ctx->tbl_part.reserve(((size_t)blocks * ngroups + TBL_MAX_GROUPS) * sizeof(XYZZ<Fq>));
   if (rc) return rc;
   XYZZ<Fq>* out = (XYZZ<Fq>*)ctx->tbl_part.p;           // [0, ngroups) = results, then per-block sums
+  if (host_partials) *host_partials = 0;
   if (blocks == 1) {
-    k_table_sum<Curve><<<dim3(1, ngroups), 256, 0, ctx->stream>>>(ts, out);
+    k_table_sum<Curve><<<dim3(1, ngroups), bs, 0, ctx->stream>>>(ts, out);
     ctx->launches += 1;
+  } else if (host_partials && blocks * ngroups <= (uint32_t)TBL_HOST_PARTIALS) {
+    k_table_sum<Curve><<<dim3(blocks, ngroups), bs, 0, ctx->stream>>>(ts, out + TBL_MAX_GROUPS);
+    ctx->launches += 1;
+    *host_partials = (int)blocks;                       // group g: out[TBL_MAX_GROUPS + g * blocks + b], b < blocks
   } else {
-    k_table_sum<Curve><<<dim3(blocks, ngroups), 256, 0, ctx->stream>>>(ts, out + TBL_MAX_GROUPS);
+    k_table_sum<Curve><<<dim3(blocks, ngroups), bs, 0, ctx->stream>>>(ts, out + TBL_MAX_GROUPS);
     k_table_sum_final<Fq><<<ngroups, 256, 0, ctx->stream>>>(out + TBL_MAX_GROUPS, blocks, out);
     ctx->launches += 2;
   }
   return launch_check(ctx, "table_sum");
 }
-template int table_sum_run<Bls>(bpgpu_ctx*, const TableSeg*, int, int);
-template int table_sum_run<Bn>(bpgpu_ctx*, const TableSeg*, int, int);
+template int table_sum_run<Bls>(bpgpu_ctx*, const TableSeg*, int, int, int*);
+template int table_sum_run<Bn>(bpgpu_ctx*, const TableSeg*, int, int, int*);
 
 template <class Curve>
 static int fb_build(bpgpu_fixed_bases* fb, const uint8_t* bases_xy) {
@@ -284,16 +295,39 @@ static void normalise_batch_host(const uint8_t* xyzz_bytes, size_t count, int mo
   }
 }
 
+// in place: entry g of `xyzz_bytes` becomes the sum of entries [g * per, (g + 1) * per)
+template <class FqParams>
+void host_sum_partials(uint8_t* xyzz_bytes, int ngroups, int per) {
+  using HP = host::HXYZZ<FqParams>;
+  HP* p = reinterpret_cast<HP*>(xyzz_bytes);
+  for (int g = 0; g < ngroups; g++) {
+    HP acc = p[(size_t)g * per];
+    for (int b = 1; b < per; b++) acc.add(p[(size_t)g * per + b]);
+    p[g] = acc;
+  }
+}
+template void host_sum_partials<BlsFq>(uint8_t*, int, int);
+template void host_sum_partials<BnFq>(uint8_t*, int, int);
+
 }  // namespace bp
 namespace bp {
 int msm_tables_to_host(bpgpu_ctx* ctx, const TableSeg* segs, int nsegs, int ngroups, uint8_t* const* outs_xy) {
   const bool bls = ctx->curve == BPGPU_BLS12_381;
   const size_t psz = bls ? sizeof(XYZZ<Bls::Fq>) : sizeof(XYZZ<Bn::Fq>);
   const int mb = bpgpu_modbytes(ctx->curve);
-  int rc = bls ? table_sum_run<Bls>(ctx, segs, nsegs, ngroups) : table_sum_run<Bn>(ctx, segs, nsegs, ngroups);
+  int hp = 0;
+  int rc = bls ? table_sum_run<Bls>(ctx, segs, nsegs, ngroups, &hp) : table_sum_run<Bn>(ctx, segs, nsegs, ngroups, &hp);
   if (rc) return rc;
-  BP_CUDA_OK(cudaMemcpyAsync(ctx->pinned, ctx->tbl_part.p, ngroups * psz, cudaMemcpyDeviceToHost, ctx->stream));
-  BP_CUDA_OK(cudaStreamSynchronize(ctx->stream));
+  if (hp) {
+    BP_CUDA_OK(cudaMemcpyAsync(ctx->pinned, (const uint8_t*)ctx->tbl_part.p + TBL_MAX_GROUPS * psz, (size_t)ngroups * hp * psz,
+                               cudaMemcpyDeviceToHost, ctx->stream));
+    BP_CUDA_OK(cudaStreamSynchronize(ctx->stream));
+    if (bls) host_sum_partials<BlsFq>(ctx->pinned, ngroups, hp);
+    else host_sum_partials<BnFq>(ctx->pinned, ngroups, hp);
+  } else {
+    BP_CUDA_OK(cudaMemcpyAsync(ctx->pinned, ctx->tbl_part.p, ngroups * psz, cudaMemcpyDeviceToHost, ctx->stream));
+    BP_CUDA_OK(cudaStreamSynchronize(ctx->stream));
+  }
   uint8_t tmp[TBL_MAX_GROUPS * 2 * 48];
   if (bls) normalise_batch_host<BlsFq>(ctx->pinned, ngroups, mb, tmp);
   else normalise_batch_host<BnFq>(ctx->pinned, ngroups, mb, tmp);

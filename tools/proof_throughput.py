@@ -8,7 +8,7 @@ m = int(sys.argv[2]) if len(sys.argv) > 2 else 1
 count = int(sys.argv[3]) if len(sys.argv) > 3 else 256
 bits = 64
 print("cpus", os.cpu_count())
-for nctx in (1, 2, 4, 8, 16, 32):
+for nctx in (8, 16, 32, 64):
     ctxs = [bp.Context(curve, 0) for _ in range(nctx)]
     c0 = ctxs[0]
     gx, hx = c0.g1_from_msg_hash(b"g"), c0.g1_from_msg_hash(b"h")
