@@ -130,7 +130,7 @@ def ncu_traffic_bytes():
         return None
 
 
-def proof_section(bp, ctx, local, rank, world, dist, torch):
+def proof_section(bp, ctx, local, rank, world, dist, torch, no_cpu=False):
     """IPP / R1CS prove+verify proofs/s (BASELINE.json metric, second half) through the host layer (include/bphost.h).
     Independent proofs are spread over `nctx` contexts (one host thread + one CUDA stream each) of this rank's GPU; with N
     ranks the batch-verification job is sharded by proofs and the verdict bytes are all-gathered over NCCL."""
@@ -139,7 +139,7 @@ def proof_section(bp, ctx, local, rank, world, dist, torch):
     nctx = max(1, min(16, ncpu // max(1, world)))
     out = {"contexts_per_gpu": nctx, "host_cpus": ncpu}
 
-    def run(curve, m, bits, count, tag, verify_reps=1, batch_call=False):
+    def run(curve, m, bits, count, tag, verify_reps=1, batch_call=False, cpu_base=0):
         ctxs = [bp.Context(curve, local) for _ in range(nctx)]
         c0 = ctxs[0]
         gx, hx = c0.g1_from_msg_hash(b"g"), c0.g1_from_msg_hash(b"h")
@@ -193,15 +193,30 @@ def proof_section(bp, ctx, local, rank, world, dist, torch):
                     "prove_verify_per_s": count * world / (tp + tv / verify_reps), "all_verified": ok, "proof_bytes": stride}
         if tb is not None:
             out[tag]["verify_batch_call_per_s"] = count * world * verify_reps / tb
+        if cpu_base and rank == 0 and world == 1:
+            # the reference's algorithm for the same proof on the host cores (oracle/fast.py: ipp.rs / prover.rs /
+            # verifier.rs restated, group operations in oracle/c), one independent proof stream per core
+            import subprocess
+            cname = "BLS12_381" if curve == bp.BLS12_381 else "BN254"
+            r = subprocess.run([sys.executable, "-m", "oracle.fast", cname, str(m), str(bits), str(cpu_base), str(ncpu)],
+                               capture_output=True, text=True, cwd=ROOT)
+            try:
+                d = json.loads(r.stdout.strip().splitlines()[-1])
+                out[tag]["cpu_baseline"] = {"prove_per_s": d["prove_per_s"], "verify_per_s": d["verify_per_s"],
+                                            "prove_verify_per_s": d["prove_verify_per_s"], "unit": "proofs/s", "cores": ncpu,
+                                            "kind": "port", "sample": f"{d['proofs']} proofs, {ncpu} processes x {cpu_base}, "
+                                            f"{d['wall_s']:.1f} s wall incl. generator set-up (not in the rates)"}
+            except Exception:
+                out[tag]["cpu_baseline"] = {"error": (r.stderr or r.stdout)[-300:]}
 
     # config 5 unit / config 1 size: one 64-bit range proof = 64 multipliers, IPP of length 64; 4096 verifications in total
     per_rank = max(nctx, 512 // world)
     run(bp.BLS12_381, 1, 64, per_rank, "range64_bls12_381_n64", verify_reps=max(1, 4096 // (per_rank * world)),
-        batch_call=True)
+        batch_call=True, cpu_base=0 if no_cpu else 4)
     # config 2: 16 x 64-bit values in one constraint system, 1024 generators
-    run(bp.BLS12_381, 16, 64, max(nctx, 64 // world), "range64x16_bls12_381_n1024")
+    run(bp.BLS12_381, 16, 64, max(nctx, 64 // world), "range64x16_bls12_381_n1024", cpu_base=0 if no_cpu else 1)
     # config 3: 2^14 multipliers on BN254 (256 x 64-bit values)
-    run(bp.BN254, 256, 64, max(nctx, 16 // world), "range64x256_bn254_n16384")
+    run(bp.BN254, 256, 64, max(nctx, 16 // world), "range64x256_bn254_n16384", cpu_base=0 if no_cpu else 1)
     return out
 
 
@@ -354,7 +369,7 @@ def main():
     b = ctx.msm_refs(hp[0], hs[0], n=n)
     assert a == b, "resident and host-buffer MSM disagree"
 
-    proofs = None if args.no_proofs else proof_section(bp, ctx, local, rank, world, dist, torch)
+    proofs = None if args.no_proofs else proof_section(bp, ctx, local, rank, world, dist, torch, no_cpu=args.no_cpu_baseline)
 
     if rank == 0:
         c = bp.lib().bpgpu_msm_window_bits(n)

@@ -220,3 +220,32 @@ int orc_fr_op(int curve, int op, const uint8_t* a_be, const uint8_t* b_be, uint8
   }
   return 0;
 }
+
+/* Keccak-f[1600] in place on a 200-byte little-endian state (FIPS 202): lets the Python Merlin transcript of the
+ * CPU-baseline runs spend its time in the group operations, as the reference does, not in a Python permutation */
+void orc_keccak_f1600(uint8_t* state) {
+  static const uint64_t RC[24] = {0x0000000000000001ULL, 0x0000000000008082ULL, 0x800000000000808aULL, 0x8000000080008000ULL,
+                                  0x000000000000808bULL, 0x0000000080000001ULL, 0x8000000080008081ULL, 0x8000000000008009ULL,
+                                  0x000000000000008aULL, 0x0000000000000088ULL, 0x0000000080008009ULL, 0x000000008000000aULL,
+                                  0x000000008000808bULL, 0x800000000000008bULL, 0x8000000000008089ULL, 0x8000000000008003ULL,
+                                  0x8000000000008002ULL, 0x8000000000000080ULL, 0x000000000000800aULL, 0x800000008000000aULL,
+                                  0x8000000080008081ULL, 0x8000000000008080ULL, 0x0000000080000001ULL, 0x8000000080008008ULL};
+  static const int ROT[25] = {0, 1, 62, 28, 27, 36, 44, 6, 55, 20, 3, 10, 43, 25, 39, 41, 45, 15, 21, 8, 18, 2, 61, 56, 14};
+  uint64_t a[25], b[25], c[5], d[5];
+  memcpy(a, state, 200);                       /* x86-64: little endian, as the state is defined */
+  for (int r = 0; r < 24; r++) {
+    for (int x = 0; x < 5; x++) c[x] = a[x] ^ a[x + 5] ^ a[x + 10] ^ a[x + 15] ^ a[x + 20];
+    for (int x = 0; x < 5; x++) d[x] = c[(x + 4) % 5] ^ ((c[(x + 1) % 5] << 1) | (c[(x + 1) % 5] >> 63));
+    for (int i = 0; i < 25; i++) a[i] ^= d[i % 5];
+    for (int x = 0; x < 5; x++)
+      for (int y = 0; y < 5; y++) {
+        const int i = x + 5 * y, rot = ROT[i];
+        const uint64_t v = rot ? ((a[i] << rot) | (a[i] >> (64 - rot))) : a[i];
+        b[y + 5 * ((2 * x + 3 * y) % 5)] = v;
+      }
+    for (int y = 0; y < 5; y++)
+      for (int x = 0; x < 5; x++) a[x + 5 * y] = b[x + 5 * y] ^ (~b[(x + 1) % 5 + 5 * y] & b[(x + 2) % 5 + 5 * y]);
+    a[0] ^= RC[r];
+  }
+  memcpy(state, a, 200);
+}

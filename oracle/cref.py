@@ -26,6 +26,8 @@ def lib():
         L.orc_binary_scalar_mul.argtypes = [i, vp, vp, vp, vp, vp]
         L.orc_multiples.argtypes = [i, vp, sz, vp]
         L.orc_fr_op.argtypes = [i, i, vp, vp, vp]
+        L.orc_keccak_f1600.argtypes = [vp]
+        L.orc_keccak_f1600.restype = None
         _LIB = L
     return _LIB
 
@@ -69,3 +71,9 @@ def fr_op(curve_id, op, a_be, b_be):
     out = ctypes.create_string_buffer(mb)
     lib().orc_fr_op(curve_id, op, _p(a_be), _p(b_be), out)
     return out.raw
+
+
+def keccak_f1600(state):
+    """in-place Keccak-f[1600] on a 200-byte bytearray (same contract as oracle.merlin.keccak_f1600)."""
+    buf = (ctypes.c_uint8 * 200).from_buffer(state)
+    lib().orc_keccak_f1600(ctypes.addressof(buf))

@@ -43,6 +43,24 @@ def test_oracle_reproduces_small_proofs():
     assert mg.gen_msm() == load("msm_257.json")
 
 
+@pytest.mark.parametrize("name,key,cname,m,seed", [("range_config5_unit.json", "bls_m1_b64", "BLS12_381", 1, 5),
+                                                  ("range_config3_reduced.json", "bn_m8_b64", "BN254", 8, 6),
+                                                  ("range_config2.json", "bls_m16_b64", "BLS12_381", 16, 2)])
+def test_c_accelerated_oracle_reproduces_config_proofs(name, key, cname, m, seed):
+    """The fixtures at BASELINE's config sizes took the pure-Python oracle minutes; the C-accelerated oracle
+    (oracle/fast.py: same protocol code, group operations and Keccak in oracle/c) must arrive at the same bytes.
+    A Python-vs-C cross check of the whole prover and verifier, and the guard for bench.py's CPU proof baseline."""
+    import importlib.util
+    from oracle import fast
+    spec = importlib.util.spec_from_file_location("make_golden", os.path.join(HERE, "make_golden.py"))
+    mg = importlib.util.module_from_spec(spec)
+    spec.loader.exec_module(mg)
+    fx = load(name)[key]
+    with fast.c_keccak():
+        got = mg.gen_range(fast.FastCurve(CURVES[cname]), m, 64, seed, b"Range")
+    assert got == fx
+
+
 # ------------------------------------------------------------------ GPU: CUDA path vs fixtures
 def _ctx(name, ctx_bls, ctx_bn):
     return ctx_bls if name == "BLS12_381" else ctx_bn
