@@ -165,11 +165,12 @@ def proof_section(bp, ctx, local, rank, world, dist, torch, no_cpu=False):
         tv = time.perf_counter() - t0
         tb = None
         if batch_call:
-            # config 5: the whole batch through ONE device call (bph_range_verify_batch): host threads build the scalars,
-            # a launch pair evaluates every proof's verification MSM, one verdict byte per proof comes back
+            # config 5: the whole batch through bph_range_verify_batch: host threads build the scalars slab by slab, the
+            # device evaluates every proof's verification MSM of a slab in one group of launches (one verdict byte per
+            # proof), overlapped with the host work on the next slab
             reps = verify_reps
             big_p, big_c = proofs * reps, comms * reps
-            bp.range_verify_batch(c0, b"bench", gx, hx, G, H, count, m, bits, proofs, stride, comms)            # warm-up
+            bp.range_verify_batch(c0, b"bench", gx, hx, G, H, count * reps, m, bits, big_p, stride, big_c)      # warm-up (scratch sized)
             if dist is not None:
                 dist.barrier()
             t0 = time.perf_counter()

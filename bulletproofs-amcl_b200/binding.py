@@ -139,7 +139,8 @@ def range_verify_many(ctxs, label, g_xy, h_xy, G, H, count, m, bits, proofs, str
 
 
 def range_verify_batch(ctx, label, g_xy, h_xy, G, H, count, m, bits, proofs, stride, comms, nthreads=0):
-    """per-proof verdicts of `count` independent proofs from ONE device call (host threads only build the scalars)."""
+    """per-proof verdicts of `count` independent proofs from batched device calls, one per slab of 512 proofs, overlapped
+    with the host threads that build the scalars."""
     verdicts = (ctypes.c_int32 * max(1, count))()
     rc = lib().bph_range_verify_batch(ctx.handle, label, _buf(g_xy), _buf(h_xy), G.handle, H.handle, count, m, bits, _buf(proofs), stride,
                                       _buf(comms), nthreads, verdicts)

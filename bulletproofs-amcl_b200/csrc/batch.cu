@@ -8,10 +8,10 @@
 // merging).  F_i are the proof system's generators G[..N], H[..N], g, h (window tables: no doublings); V[b][j] are the
 // proof's own points A_I1.., V_k, T_i, L_k, R_k, which need real scalar multiplications:
 //   k_batch_fixed : one block per proof, sum of 64 table entries per fixed term, block tree
-//   k_batch_var   : one block of 64 threads per proof: 15 multiples of every point, one 4-bit window per thread,
-//                   then ONE thread runs the 252-doubling Horner chain -- ~3 ms of latency, but for thousands of
-//                   proofs at once (the chain is what a GPU is bad at per proof and good at per batch)
+//   k_batch_multiples / k_batch_windows / k_batch_horner : Straus with 4-bit windows for the proof's own points, laid
+//                   out so that each stage has one independent item per lane (see below)
 // Nothing returns to the host but `batch` verdict bytes.
+#include <stdlib.h>
 #include <string.h>
 
 #include "common.cuh"
@@ -61,52 +61,70 @@ __global__ void __launch_bounds__(256) k_batch_fixed(FixedRuns runs, uint32_t F,
   if (threadIdx.x == 0) store_vec(out + b, load_vec(sm));
 }
 
-// one block of 64 threads per proof; mult = scratch for vn * 15 XYZZ multiples per proof
+// Variable part, three launches so that every stage has one independent item per LANE:
+//   k_batch_multiples : thread per (proof, point): the 15 small multiples of the point (14 mixed additions)
+//   k_batch_windows   : thread per (proof, 4-bit window): sum over the points of the multiple its digit selects
+//   k_batch_horner    : thread per proof: the 252-doubling Horner chain over the 64 window sums, plus the fixed part,
+//                       then the verdict.  The chain is serial per proof, but 4096 proofs are 4096 chains: 128 warps
+//                       running flat out instead of one lane of a block holding its registers for 3 ms.
 template <class Curve>
-__global__ void __launch_bounds__(64) k_batch_var(uint32_t vn, const Affine<typename Curve::Fq>* __restrict__ pts,
-                                                  const typename Curve::Fr* __restrict__ scal, XYZZ<typename Curve::Fq>* __restrict__ mult,
-                                                  const XYZZ<typename Curve::Fq>* __restrict__ fixed_sum, uint8_t* __restrict__ is_identity) {
+__global__ void __launch_bounds__(64) k_batch_multiples(size_t total, const Affine<typename Curve::Fq>* __restrict__ pts,
+                                                        XYZZ<typename Curve::Fq>* __restrict__ mult) {
+  using Fq = typename Curve::Fq;
+  const size_t t = (size_t)blockIdx.x * blockDim.x + threadIdx.x;      // (proof, point) flattened
+  if (t >= total) return;
+  const Affine<Fq> a = load_vec(pts + t);
+  XYZZ<Fq> acc = XYZZ<Fq>::from_affine(a);
+  XYZZ<Fq>* M = mult + t * TBL_DIGITS;
+#pragma unroll 1
+  for (int d = 0; d < TBL_DIGITS; d++) {
+    store_vec(M + d, acc);
+    if (d + 1 < TBL_DIGITS) acc.madd(a);
+  }
+}
+
+// wsum[w * batch + b] = sum_i M[b][i][digit_w(s[b][i]) - 1]
+template <class Curve>
+__global__ void __launch_bounds__(128) k_batch_windows(size_t batch, uint32_t vn, const typename Curve::Fr* __restrict__ scal,
+                                                       const XYZZ<typename Curve::Fq>* __restrict__ mult,
+                                                       XYZZ<typename Curve::Fq>* __restrict__ wsum) {
   using Fq = typename Curve::Fq;
   using Fr = typename Curve::Fr;
-  __shared__ __align__(16) unsigned char smraw[64 * sizeof(XYZZ<Fq>)];
-  XYZZ<Fq>* sm = reinterpret_cast<XYZZ<Fq>*>(smraw);
-  const size_t b = blockIdx.x;
-  const Affine<Fq>* P = pts + b * vn;
+  const size_t t = (size_t)blockIdx.x * blockDim.x + threadIdx.x;
+  if (t >= batch * TBL_WINDOWS) return;
+  const size_t b = t / TBL_WINDOWS;
+  const uint32_t w = (uint32_t)(t - b * TBL_WINDOWS);
   const Fr* sc = scal + b * vn;
-  XYZZ<Fq>* M = mult + b * (size_t)vn * TBL_DIGITS;
-  // phase 1: multiples 1..15 of every point (thread i takes points i, i+64, ..)
-  for (uint32_t i = threadIdx.x; i < vn; i += blockDim.x) {
-    const Affine<Fq> a = load_vec(P + i);
-    XYZZ<Fq> acc = XYZZ<Fq>::from_affine(a);
-    for (int d = 0; d < TBL_DIGITS; d++) {
-      store_vec(M + (size_t)i * TBL_DIGITS + d, acc);
-      if (d + 1 < TBL_DIGITS) acc.madd(a);
-    }
+  const XYZZ<Fq>* M = mult + b * (size_t)vn * TBL_DIGITS;
+  XYZZ<Fq> acc = XYZZ<Fq>::inf();
+#pragma unroll 1
+  for (uint32_t i = 0; i < vn; i++) {
+    const uint32_t d = (sc[i].v[w >> 3] >> ((w & 7) * 4)) & 15u;
+    if (d) { XYZZ<Fq> q = load_vec(M + (size_t)i * TBL_DIGITS + (d - 1)); acc.add(q); }
   }
-  __syncthreads();
-  // phase 2: thread w sums the window-w digits of all points
-  {
-    const uint32_t w = threadIdx.x;
-    XYZZ<Fq> acc = XYZZ<Fq>::inf();
-    for (uint32_t i = 0; i < vn; i++) {
-      const uint32_t d = (sc[i].v[w >> 3] >> ((w & 7) * 4)) & 15u;
-      if (d) { XYZZ<Fq> q = load_vec(M + (size_t)i * TBL_DIGITS + (d - 1)); acc.add(q); }
-    }
-    store_vec(sm + w, acc);
-  }
-  __syncthreads();
-  // phase 3: Horner over the 64 windows, then the fixed part, then the verdict
-  if (threadIdx.x == 0) {
-    XYZZ<Fq> acc = load_vec(sm + 63);
-    for (int w = 62; w >= 0; w--) {
+  store_vec(wsum + (size_t)w * batch + b, acc);
+}
+
+template <class Curve>
+__global__ void __launch_bounds__(32) k_batch_horner(size_t batch, uint32_t vn, const XYZZ<typename Curve::Fq>* __restrict__ wsum,
+                                                     const XYZZ<typename Curve::Fq>* __restrict__ fixed_sum,
+                                                     uint8_t* __restrict__ is_identity) {
+  using Fq = typename Curve::Fq;
+  const size_t b = (size_t)blockIdx.x * blockDim.x + threadIdx.x;
+  if (b >= batch) return;
+  XYZZ<Fq> acc = XYZZ<Fq>::inf();
+  if (vn) {
+    acc = load_vec(wsum + (size_t)(TBL_WINDOWS - 1) * batch + b);
+#pragma unroll 1
+    for (int w = TBL_WINDOWS - 2; w >= 0; w--) {
       acc.dbl(); acc.dbl(); acc.dbl(); acc.dbl();
-      XYZZ<Fq> q = load_vec(sm + w);
+      XYZZ<Fq> q = load_vec(wsum + (size_t)w * batch + b);
       acc.add(q);
     }
-    XYZZ<Fq> f = load_vec(fixed_sum + b);
-    acc.add(f);
-    is_identity[b] = acc.is_inf() ? 1 : 0;
   }
+  XYZZ<Fq> f = load_vec(fixed_sum + b);
+  acc.add(f);
+  is_identity[b] = acc.is_inf() ? 1 : 0;
 }
 
 template <class Curve>
@@ -120,15 +138,17 @@ static int batch_identity_t(bpgpu_ctx* ctx, const FixedRuns& runs, uint32_t F, s
   // scratch: fixed scalars | var scalars | var points | fixed sums | verdicts | multiples
   const size_t sz_fs = (slab * F * sizeof(Fr) + 255) & ~(size_t)255, sz_vs = (slab * vn * sizeof(Fr) + 255) & ~(size_t)255;
   const size_t sz_vp = (slab * vn * sizeof(Affine<Fq>) + 255) & ~(size_t)255, sz_sum = (slab * sizeof(XYZZ<Fq>) + 255) & ~(size_t)255;
-  const size_t sz_v = (slab + 255) & ~(size_t)255, sz_m = slab * (size_t)vn * TBL_DIGITS * sizeof(XYZZ<Fq>);
-  if ((rc = ctx->msm_b.reserve(sz_fs + sz_vs + sz_vp + sz_sum + sz_v + sz_m + 256))) return rc;
+  const size_t sz_v = (slab + 255) & ~(size_t)255, sz_m = (slab * (size_t)vn * TBL_DIGITS * sizeof(XYZZ<Fq>) + 255) & ~(size_t)255;
+  const size_t sz_w = vn ? slab * (size_t)TBL_WINDOWS * sizeof(XYZZ<Fq>) : 0;
+  if ((rc = ctx->msm_b.reserve(sz_fs + sz_vs + sz_vp + sz_sum + sz_v + sz_m + sz_w + 256))) return rc;
   uint8_t* base = (uint8_t*)ctx->msm_b.p;
   Fr* d_fs = (Fr*)base; base += sz_fs;
   Fr* d_vs = (Fr*)base; base += sz_vs;
   Affine<Fq>* d_vp = (Affine<Fq>*)base; base += sz_vp;
   XYZZ<Fq>* d_sum = (XYZZ<Fq>*)base; base += sz_sum;
   uint8_t* d_v = base; base += sz_v;
-  XYZZ<Fq>* d_m = (XYZZ<Fq>*)base;
+  XYZZ<Fq>* d_m = (XYZZ<Fq>*)base; base += sz_m;
+  XYZZ<Fq>* d_w = (XYZZ<Fq>*)base;
   const int mb = Curve::MODBYTES;
   for (size_t lo = 0; lo < batch; lo += slab) {
     const size_t cnt = batch - lo < slab ? batch - lo : slab;
@@ -138,8 +158,26 @@ static int batch_identity_t(bpgpu_ctx* ctx, const FixedRuns& runs, uint32_t F, s
       if ((rc = scalars_from_host<Curve>(ctx, var_scalars_be + lo * vn * mb, cnt * vn, 0, d_vs))) return rc;
       if ((rc = points_from_host<Curve>(ctx, var_points_xy + lo * vn * 2 * mb, cnt * vn, d_vp))) return rc;
     }
+    static const bool prof = getenv("BPGPU_PROFILE") != nullptr;
+    cudaEvent_t ev[3];
+    if (prof) { for (auto& e : ev) cudaEventCreate(&e); cudaEventRecord(ev[0], ctx->stream); }
     k_batch_fixed<Curve><<<(unsigned)cnt, 256, 0, ctx->stream>>>(runs, F, d_fs, d_sum);
-    k_batch_var<Curve><<<(unsigned)cnt, 64, 0, ctx->stream>>>(vn, d_vp, d_vs, d_m, d_sum, d_v);
+    if (prof) cudaEventRecord(ev[1], ctx->stream);
+    if (vn) {
+      const size_t np = cnt * vn, nw = cnt * TBL_WINDOWS;
+      k_batch_multiples<Curve><<<(unsigned)((np + 63) / 64), 64, 0, ctx->stream>>>(np, d_vp, d_m);
+      k_batch_windows<Curve><<<(unsigned)((nw + 127) / 128), 128, 0, ctx->stream>>>(cnt, vn, d_vs, d_m, d_w);
+      ctx->launches += 2;
+    }
+    k_batch_horner<Curve><<<(unsigned)((cnt + 31) / 32), 32, 0, ctx->stream>>>(cnt, vn, d_w, d_sum, d_v);
+    if (prof) {
+      cudaEventRecord(ev[2], ctx->stream);
+      cudaEventSynchronize(ev[2]);
+      float a, b;
+      cudaEventElapsedTime(&a, ev[0], ev[1]); cudaEventElapsedTime(&b, ev[1], ev[2]);
+      fprintf(stderr, "[bpgpu batch_identity n=%zu F=%u vn=%u] fixed=%.3f ms var=%.3f ms\n", cnt, F, vn, a, b);
+      for (auto& e : ev) cudaEventDestroy(e);
+    }
     ctx->launches += 2;
     if ((rc = launch_check(ctx, "batch_identity"))) return rc;
     BP_CUDA_OK(cudaMemcpyAsync(is_identity + lo, d_v, cnt, cudaMemcpyDeviceToHost, ctx->stream));

@@ -193,6 +193,12 @@ int range_verify_batch_t(bpgpu_ctx* ctx, const char* label, const uint8_t* g_xy,
   if (nthreads == 0) nthreads = std::thread::hardware_concurrency();
   if (nthreads == 0) nthreads = 1;
   if (nthreads > count) nthreads = count ? count : 1;
+  // Host and device overlap: the proofs are cut into slabs; worker threads fill them in index order while this thread
+  // hands every completed slab to the device, so the device evaluates slab k while the workers build slab k+1...
+  const size_t SLAB = count >= 4096 ? 1024 : 512;   // the Horner stage of a slab is ~3 ms of latency whatever its size
+  const size_t nslab = (count + SLAB - 1) / SLAB;
+  std::vector<std::atomic<size_t>> done(nslab);
+  for (auto& d : done) d.store(0);
   std::atomic<size_t> next{0};
   auto worker = [&]() {
     for (;;) {
@@ -220,20 +226,30 @@ int range_verify_batch_t(bpgpu_ctx* ctx, const char* label, const uint8_t* g_xy,
         memset(fo, 0, F * mb);
         memset(so, 0, vn * mb);
         for (size_t k = 0; k < vn; k++) memcpy(po + k * pb, ident.xy, pb);
-        continue;
+      } else {
+        for (size_t k = 0; k < F; k++) t.fixed[k].to_bytes(fo + k * mb);
+        for (size_t k = 0; k < vn; k++) { memcpy(po + k * pb, t.var_points[k].xy, pb); t.var_scalars[k].to_bytes(so + k * mb); }
       }
-      for (size_t k = 0; k < F; k++) t.fixed[k].to_bytes(fo + k * mb);
-      for (size_t k = 0; k < vn; k++) { memcpy(po + k * pb, t.var_points[k].xy, pb); t.var_scalars[k].to_bytes(so + k * mb); }
+      done[i / SLAB].fetch_add(1, std::memory_order_release);
     }
   };
+  Trace tr("range_verify_batch");
   std::vector<std::thread> th;
-  for (size_t k = 1; k < nthreads; k++) th.emplace_back(worker);
-  worker();
-  for (auto& x : th) x.join();
+  for (size_t k = 0; k < nthreads; k++) th.emplace_back(worker);
   // [G[..N] | H[..N] | g | h]
   bpgpu_fixed_run runs[4] = {{G, 0, N, nullptr}, {H, 0, N, nullptr}, {nullptr, 0, 1, g_xy}, {nullptr, 0, 1, h_xy}};
   std::vector<uint8_t> ident_flags(count + 1);
-  if ((rc = bpgpu_msm_batch_is_identity(ctx, runs, 4, count, fixed.data(), vpts.data(), vscal.data(), vn, ident_flags.data()))) return rc;
+  rc = BPGPU_OK;
+  for (size_t k = 0; k < nslab; k++) {
+    const size_t lo = k * SLAB, cnt = count - lo < SLAB ? count - lo : SLAB;
+    while (done[k].load(std::memory_order_acquire) < cnt) std::this_thread::yield();
+    if (rc) continue;                             // after a device error: just let the workers drain
+    rc = bpgpu_msm_batch_is_identity(ctx, runs, 4, cnt, fixed.data() + lo * F * mb, vpts.data() + lo * vn * pb, vscal.data() + lo * vn * mb, vn,
+                                     ident_flags.data() + lo);
+  }
+  for (auto& x : th) x.join();
+  if (rc) return rc;
+  tr.mark("host + device, overlapped");
   for (size_t i = 0; i < count; i++)
     if (verdicts[i] == 0 && !ident_flags[i]) verdicts[i] = BPGPU_E_VERIFY;
   return BPGPU_OK;

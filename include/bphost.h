@@ -85,11 +85,12 @@ int bph_range_verify_many(bpgpu_ctx* const* ctxs, size_t nctx, const char* trans
                           const bpgpu_points* G, const bpgpu_points* H, size_t count, size_t m, size_t bits, const uint8_t* proofs,
                           size_t proof_stride, const uint8_t* comms_xy, int32_t* verdicts);
 
-/* The same verdicts as bph_range_verify_many, computed by ONE device call for the whole batch
- * (bpgpu_msm_batch_is_identity): `nthreads` host threads (0 = all cores) replay the transcripts and build every proof's
- * verification scalars on the host (O(n) field operations per proof), then a single launch pair evaluates all `count`
- * verification MSMs and returns one verdict byte per proof.  G and H get window tables on first use
- * (bpgpu_points_precompute).  Meant for small circuits verified in bulk (config 5: 64-bit range proofs, n = 64). */
+/* The same verdicts as bph_range_verify_many from batched device calls (bpgpu_msm_batch_is_identity): `nthreads` host
+ * threads (0 = all cores) replay the transcripts and build every proof's verification scalars on the host (O(n) field
+ * operations per proof) in slabs of 512 or 1024 proofs; every completed slab is evaluated by one group of launches (all of
+ * its verification MSMs at once, one verdict byte per proof) while the threads build the next slab.  G and H get
+ * window tables on first use (bpgpu_points_precompute).  Meant for small circuits verified in bulk (config 5: 64-bit
+ * range proofs, n = 64). */
 int bph_range_verify_batch(bpgpu_ctx* ctx, const char* transcript_label, const uint8_t* g_xy, const uint8_t* h_xy, bpgpu_points* G,
                            bpgpu_points* H, size_t count, size_t m, size_t bits, const uint8_t* proofs, size_t proof_stride,
                            const uint8_t* comms_xy, size_t nthreads, int32_t* verdicts);
