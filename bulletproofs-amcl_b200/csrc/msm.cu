@@ -154,7 +154,7 @@ __global__ void __launch_bounds__(1024) k_scan(MsmGeom g, uint32_t* __restrict__
 }
 
 __global__ void __launch_bounds__(256) k_scatter(MsmGeom g, const uint32_t* __restrict__ digits, uint32_t* __restrict__ cursor,
-                                                 uint32_t* __restrict__ sidx, uint32_t* __restrict__ skey) {
+                                                 uint32_t* __restrict__ sidx) {
   const size_t total = (size_t)g.W * g.n;
   for (size_t t = (size_t)blockIdx.x * blockDim.x + threadIdx.x; t < total; t += (size_t)gridDim.x * blockDim.x) {
     uint32_t d = digits[t];
@@ -162,14 +162,24 @@ __global__ void __launch_bounds__(256) k_scatter(MsmGeom g, const uint32_t* __re
     uint32_t w = (uint32_t)(t / g.n), i = (uint32_t)(t - (size_t)w * g.n);
     uint32_t mag = d & 0x7fffffffu;
     uint32_t pos = atomicAdd(&cursor[(size_t)w * g.nbp + mag], 1u);
-    sidx[(size_t)w * g.n + pos] = i | (d & 0x80000000u);
-    skey[(size_t)w * g.n + pos] = mag;
+    sidx[(size_t)w * g.n + pos] = i | (d & 0x80000000u);      // the bucket is implied by the position (bstart)
   }
+}
+
+// bucket of sorted entry e: the largest b with bstart[b] <= e (empty buckets share their successor's start, so the
+// largest such index is the non-empty bucket that holds e); bs has nbp + 1 entries, bs[nbp] = number of entries > e
+__device__ __forceinline__ uint32_t bucket_of(const uint32_t* __restrict__ bs, uint32_t nbp, uint32_t e) {
+  uint32_t lo = 0, hi = nbp;                    // invariant: bs[lo] <= e < bs[hi]
+  while (hi - lo > 1) {
+    const uint32_t mid = (lo + hi) >> 1;
+    if (bs[mid] <= e) lo = mid; else hi = mid;
+  }
+  return lo;
 }
 
 template <class Fq, int MINB>
 __global__ void __launch_bounds__(128, MINB) k_chunk_acc(MsmGeom g, const Affine<Fq>* __restrict__ pts,
-                                                   const uint32_t* __restrict__ sidx, const uint32_t* __restrict__ skey,
+                                                   const uint32_t* __restrict__ sidx,
                                                    const uint32_t* __restrict__ bstart, const uint32_t* __restrict__ pstart,
                                                    XYZZ<Fq>* __restrict__ partials) {
   const uint32_t gid = blockIdx.x * blockDim.x + threadIdx.x;
@@ -182,16 +192,17 @@ __global__ void __launch_bounds__(128, MINB) k_chunk_acc(MsmGeom g, const Affine
   if (e0 >= cnt) return;
   const uint32_t e1 = min(e0 + g.S, cnt);
   const uint32_t* idx = sidx + (size_t)w * g.n;
-  const uint32_t* key = skey + (size_t)w * g.n;
   XYZZ<Fq>* out = partials + (size_t)w * g.pcap;
   XYZZ<Fq> acc = XYZZ<Fq>::inf();
-  uint32_t cur = key[e0];
+  uint32_t cur = bucket_of(bs, g.nbp, e0);
+  uint32_t end = bs[cur + 1];                   // first entry past bucket `cur`
   for (uint32_t e = e0; e < e1; e++) {
-    uint32_t k = key[e];
-    if (k != cur) {
+    if (e >= end) {                             // next bucket: almost always cur + 1, else search past the empty ones
       store_vec(out + ps[cur] + (t - bs[cur] / g.S), acc);
       acc = XYZZ<Fq>::inf();
-      cur = k;
+      cur++;
+      end = bs[cur + 1];
+      if (e >= end) { cur = bucket_of(bs, g.nbp, e); end = bs[cur + 1]; }
     }
     uint32_t id = idx[e];
     Affine<Fq> P = load_vec_ro(pts + (id & 0x7fffffffu));
@@ -249,7 +260,7 @@ __global__ void __launch_bounds__(GIANT_BLOCK) k_giant(MsmGeom g, const uint32_t
 // addition: no divergence, W * n / S independent threads).  k_giant has already collapsed the > GIANT_T cases.
 // Afterwards pcount[b] is 0 or 1 for every bucket and k_reduce_l1 is two additions per bucket with no inner loop.
 template <class Fq>
-__global__ void __launch_bounds__(128) k_merge(MsmGeom g, const uint32_t* __restrict__ skey, const uint32_t* __restrict__ bstart,
+__global__ void __launch_bounds__(128) k_merge(MsmGeom g, const uint32_t* __restrict__ bstart,
                                                const uint32_t* __restrict__ pstart, uint32_t* __restrict__ pcount,
                                                XYZZ<Fq>* __restrict__ partials) {
   const uint32_t gid = blockIdx.x * blockDim.x + threadIdx.x;
@@ -259,9 +270,8 @@ __global__ void __launch_bounds__(128) k_merge(MsmGeom g, const uint32_t* __rest
   const uint32_t cnt = bs[g.nbp];
   const uint64_t e1 = (uint64_t)(t + 1) * g.S;              // first entry of the next chunk
   if (e1 >= cnt) return;
-  const uint32_t* key = skey + (size_t)w * g.n;
-  const uint32_t b = key[e1 - 1];
-  if (key[e1] != b || bs[b] / g.S != t) return;             // no straddle, or the bucket began in an earlier chunk
+  const uint32_t b = bucket_of(bs, g.nbp, (uint32_t)(e1 - 1));
+  if (bs[b + 1] <= e1 || bs[b] / g.S != t) return;          // no straddle, or the bucket began in an earlier chunk
   uint32_t* pc = pcount + (size_t)w * g.nbp;
   const uint32_t np = pc[b];
   if (np <= 1) return;                                      // collapsed by k_giant
@@ -536,11 +546,10 @@ int msm_run(bpgpu_ctx* ctx, const Affine<typename Curve::Fq>* d_points, const vo
   const size_t sz_bstart = align256((size_t)g.W * (g.nbp + 1) * 4);
   const size_t sz_giant = align256(((size_t)g.W * g.nbp + 1) * 4);
   int rc;
-  if ((rc = ctx->msm_a.reserve(sz_digits * 3 + sz_hist * 2 + sz_bstart * 2 + sz_giant))) return rc;
+  if ((rc = ctx->msm_a.reserve(sz_digits * 2 + sz_hist * 2 + sz_bstart * 2 + sz_giant))) return rc;
   uint8_t* base = (uint8_t*)ctx->msm_a.p;
   uint32_t* digits = (uint32_t*)base; base += sz_digits;
   uint32_t* sidx = (uint32_t*)base; base += sz_digits;
-  uint32_t* skey = (uint32_t*)base; base += sz_digits;
   uint32_t* hist = (uint32_t*)base; base += sz_hist;
   uint32_t* cursor = (uint32_t*)base; base += sz_hist;
   uint32_t* bstart = (uint32_t*)base; base += sz_bstart;
@@ -574,7 +583,7 @@ int msm_run(bpgpu_ctx* ctx, const Affine<typename Curve::Fq>* d_points, const vo
     size_t blocks = (total + 255) / 256;
     size_t cap = (size_t)ctx->sm_count * 32;
     if (blocks > cap) blocks = cap;
-    k_scatter<<<(unsigned)blocks, 256, 0, st>>>(g, digits, cursor, sidx, skey);
+    k_scatter<<<(unsigned)blocks, 256, 0, st>>>(g, digits, cursor, sidx);
     tm.mark("scatter");
   }
   if (ctx->wait_points) {                    // points still arriving on the copy queue (bpgpu_msm_refs)
@@ -584,14 +593,14 @@ int msm_run(bpgpu_ctx* ctx, const Affine<typename Curve::Fq>* d_points, const vo
   {
     uint32_t threads = (uint32_t)g.W * g.nchunk;
     static const char* env_mb = getenv("BPGPU_CHUNK_MINB");
-    if (env_mb && atoi(env_mb) == 3) k_chunk_acc<Fq, 3><<<(threads + 127) / 128, 128, 0, st>>>(g, d_points, sidx, skey, bstart, pstart, partials);
-    else k_chunk_acc<Fq, 2><<<(threads + 127) / 128, 128, 0, st>>>(g, d_points, sidx, skey, bstart, pstart, partials);
+    if (env_mb && atoi(env_mb) == 3) k_chunk_acc<Fq, 3><<<(threads + 127) / 128, 128, 0, st>>>(g, d_points, sidx, bstart, pstart, partials);
+    else k_chunk_acc<Fq, 2><<<(threads + 127) / 128, 128, 0, st>>>(g, d_points, sidx, bstart, pstart, partials);
     tm.mark("chunk_acc");
   }
   k_giant<Fq><<<ctx->sm_count * 2, GIANT_BLOCK, 0, st>>>(g, pstart, hist, partials, giant, giant + 1);
   {
     uint32_t threads = (uint32_t)g.W * g.nchunk;
-    k_merge<Fq><<<(threads + 127) / 128, 128, 0, st>>>(g, skey, bstart, pstart, hist, partials);
+    k_merge<Fq><<<(threads + 127) / 128, 128, 0, st>>>(g, bstart, pstart, hist, partials);
   }
   tm.mark("giant");                                          // stage 4 = k_giant + k_merge
   int qshift = 5 + g.lgL1;
