@@ -270,7 +270,7 @@ class Context:
     def launches(self):
         return lib().bpgpu_ctx_launches(self.handle)
 
-    STAGES = ["digits", "scan", "scatter", "chunk_acc", "giant", "reduce_l1", "reduce_l2"]
+    STAGES = ["digits", "scan", "scatter", "chunk_acc", "giant", "merge", "reduce_l1", "reduce_l2"]
 
     def set_profile(self, min_n):
         """record per-stage times of every MSM with at least min_n terms (0 / False = off)"""
@@ -279,7 +279,7 @@ class Context:
     def msm_stage_ms(self):
         arr = (ctypes.c_double * 8)()
         runs = lib().bpgpu_msm_stage_ms(self.handle, arr, 8)
-        return runs, dict(zip(self.STAGES, list(arr)[:7]))
+        return runs, dict(zip(self.STAGES, list(arr)[:8]))
 
     def host_alloc(self, nbytes):
         p = lib().bpgpu_host_alloc(nbytes)

@@ -248,10 +248,15 @@ static void msm_finish_mixed(const uint8_t* winsum_bytes, int W, int c, int qshi
   using HP = host::HXYZZ<FqParams>;
   HP acc = HP::inf();
   const HP* ws = reinterpret_cast<const HP*>(winsum_bytes);
+  // acc * 2^c + P_w + 2^q * Q_w = ((acc * 2^(c-q)) + Q_w) * 2^q + P_w : the shift of Q_w rides the window's own c doublings
+  // (q = 5 + lgL1 < c always: a level-1 segment is at most half a window)
+  const int q = qshift < c ? qshift : 0;
   for (int w = W - 1; w >= 0; w--) {
-    if (w != W - 1) for (int k = 0; k < c; k++) acc.dbl();
-    HP q = ws[W + w];
-    if (!q.is_inf()) { for (int k = 0; k < qshift; k++) q.dbl(); acc.add(q); }
+    HP qw = ws[W + w];
+    if (q == 0 && !qw.is_inf()) for (int k = 0; k < qshift; k++) qw.dbl();
+    if (w != W - 1) for (int k = 0; k < c - q; k++) acc.dbl();
+    acc.add(qw);
+    for (int k = 0; k < q; k++) acc.dbl();
     acc.add(ws[w]);
   }
   if (table_sum) acc.add(*reinterpret_cast<const HP*>(table_sum));

@@ -41,15 +41,15 @@ struct XYZZ {
     if (is_inf()) return;
     if (y.is_zero()) { *this = inf(); return; }
     F U = y.dbl();
-    F V = U.sqr();
-    F W = U * V;
-    F S = x * V;
-    F X2 = x.sqr();
+    F V = F::mulc(U, U);
+    F W = F::mulc(U, V);
+    F S = F::mulc(x, V);
+    F X2 = F::mulc(x, x);
     F M = X2.dbl() + X2;
-    F X3 = M.sqr() - S.dbl();
-    F Y3 = F::mul2(M, S - X3, W, y.neg());              // M*(S - X3) - W*y, one reduction
-    zz = V * zz;
-    zzz = W * zzz;
+    F X3 = F::mulc(M, M) - S.dbl();
+    F Y3 = F::mul2c(M, S - X3, W, y.neg());             // M*(S - X3) - W*y, one reduction
+    zz = F::mulc(V, zz);
+    zzz = F::mulc(W, zzz);
     x = X3; y = Y3;
   }
 
@@ -58,13 +58,13 @@ struct XYZZ {
     if (a.is_inf() || a.y.is_zero()) return inf();
     XYZZ p;
     F U = a.y.dbl();
-    F V = U.sqr();
-    F W = U * V;
-    F S = a.x * V;
-    F X2 = a.x.sqr();
+    F V = F::mulc(U, U);
+    F W = F::mulc(U, V);
+    F S = F::mulc(a.x, V);
+    F X2 = F::mulc(a.x, a.x);
     F M = X2.dbl() + X2;
-    p.x = M.sqr() - S.dbl();
-    p.y = F::mul2(M, S - p.x, W, a.y.neg());
+    p.x = F::mulc(M, M) - S.dbl();
+    p.y = F::mul2c(M, S - p.x, W, a.y.neg());
     p.zz = V; p.zzz = W;
     return p;
   }
@@ -92,30 +92,35 @@ struct XYZZ {
   }
 
   // add-2008-s: this += q
-  BP_HD_COLD void add(const XYZZ& q) { add_inl(q); }
-  // the same, inlined into the caller (hot loops whose operands live in registers)
-  BP_HD void add_inl(const XYZZ& q) {
+  // compact form: a real call whose products are real calls too (see Fp::mulc) -- for latency-bound code
+  BP_HD_COLD void add(const XYZZ& q) { add_t<true>(q); }
+  // fully inlined into the caller (throughput loops whose operands live in registers)
+  BP_HD void add_inl(const XYZZ& q) { add_t<false>(q); }
+  template <bool COMPACT>
+  BP_HD void add_t(const XYZZ& q) {
     if (q.is_inf()) return;
     if (is_inf()) { *this = q; return; }
-    F U1 = x * q.zz;
-    F U2 = q.x * zz;
-    F S1 = y * q.zzz;
-    F S2 = q.y * zzz;
+    F U1 = mul_sel<COMPACT>(x, q.zz);
+    F U2 = mul_sel<COMPACT>(q.x, zz);
+    F S1 = mul_sel<COMPACT>(y, q.zzz);
+    F S2 = mul_sel<COMPACT>(q.y, zzz);
     F Pd = U2 - U1;
     F R = S2 - S1;
     if (Pd.is_zero()) {
       if (R.is_zero()) dbl(); else *this = inf();
       return;
     }
-    F PP = Pd.sqr();
-    F PPP = Pd * PP;
-    F Q = U1 * PP;
-    F X3 = R.sqr() - PPP - Q.dbl();
-    F Y3 = F::mul2(R, Q - X3, S1.neg(), PPP);
-    zz = zz * q.zz * PP;
-    zzz = zzz * q.zzz * PPP;
+    F PP = mul_sel<COMPACT>(Pd, Pd);
+    F PPP = mul_sel<COMPACT>(Pd, PP);
+    F Q = mul_sel<COMPACT>(U1, PP);
+    F X3 = mul_sel<COMPACT>(R, R) - PPP - Q.dbl();
+    F Y3 = COMPACT ? F::mul2c(R, Q - X3, S1.neg(), PPP) : F::mul2(R, Q - X3, S1.neg(), PPP);
+    zz = mul_sel<COMPACT>(mul_sel<COMPACT>(zz, q.zz), PP);
+    zzz = mul_sel<COMPACT>(mul_sel<COMPACT>(zzz, q.zzz), PPP);
     x = X3; y = Y3;
   }
+  template <bool COMPACT>
+  BP_HD static F mul_sel(const F& a, const F& b) { return COMPACT ? F::mulc(a, b) : a * b; }
 
   // normalise; one field inversion
   BP_HD_COLD Affine<F> to_affine() const {

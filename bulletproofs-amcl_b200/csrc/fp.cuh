@@ -176,6 +176,14 @@ struct Fp {
 
   BP_HD Fp sqr() const { return (*this) * (*this); }
 
+  // The same products as REAL CALLS on the device.  An inlined product is ~400 straight-line instructions (6 KB); a
+  // group addition built from inlined products is ~90 KB of code that a latency-bound kernel (tree levels, the bucket
+  // reduction's tail, single additions) runs through once per warp, so it waits on instruction fetch rather than on
+  // the multiplier.  The cold-path group operations (XYZZ::add / dbl) are built from these instead: one 6 KB body
+  // that stays in the instruction cache.  Throughput kernels keep the inlined forms.
+  BP_HD_COLD static Fp mulc(Fp a, Fp b) { return mul_t<0>(a, b); }
+  BP_HD_COLD static Fp mul2c(Fp a, Fp b, Fp c, Fp d) { return mul2(a, b, c, d); }
+
   // (a*b + c*d) / 2^(32N) mod p with ONE Montgomery reduction: every row adds a*b_i AND c*d_i to the accumulators
   // before its reduction row, so the sum of two products costs 2*N*N + N*N + N wide multiply-adds instead of
   // 2 * (2*N*N + N) -- 444 instead of 600 for the 12-limb field.  The running value stays below 3p

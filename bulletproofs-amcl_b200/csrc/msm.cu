@@ -42,7 +42,7 @@ struct MsmGeom {
   uint32_t nrows;   // row/column reduction (c >= 13): the 2^(c-1) buckets of a window form an nrows x 256 grid
 };
 
-static const int GIANT_T = 16;         // buckets with more partials than this are collapsed by k_giant
+static const int GIANT_T = 16;         // buckets with more partials than this are collapsed by k_giant (a block tree: ~9 dependent additions)
 static const int GIANT_BLOCK = 128;
 
 int msm_window_bits(size_t n) {
@@ -277,7 +277,7 @@ __global__ void __launch_bounds__(128) k_merge(MsmGeom g, const uint32_t* __rest
   if (np <= 1) return;                                      // collapsed by k_giant
   XYZZ<Fq>* in = partials + (size_t)w * g.pcap + pstart[(size_t)w * (g.nbp + 1) + b];
   XYZZ<Fq> acc = load_vec(in);
-  for (uint32_t k = 1; k < np; k++) { XYZZ<Fq> q = load_vec(in + k); acc.add_inl(q); }
+  for (uint32_t k = 1; k < np; k++) { XYZZ<Fq> q = load_vec(in + k); acc.add(q); }   // one addition per thread: compact code, see Fp::mulc
   store_vec(in, acc);
   pc[b] = 1;
 }
@@ -522,7 +522,7 @@ int msm_run(bpgpu_ctx* ctx, const Affine<typename Curve::Fq>* d_points, const vo
     // Measured at 2^20 (tools/msm_sweep.py): S = 64 beats 32 by 5 %; 96 and 128 lose in k_chunk_acc.
     uint64_t fill = ((uint64_t)g.W * n) / ((uint64_t)ctx->sm_count * 8 * 32);
     uint64_t s = fill;
-    g.S = (uint32_t)(s < 4 ? 4 : (s > 64 ? 64 : s));
+    g.S = (uint32_t)(s < 8 ? 8 : (s > 64 ? 64 : s));   // below 8 a bucket splits into so many partial sums that merging them dominates
     if (env_s) g.S = (uint32_t)atoi(env_s);
   }
   g.nchunk = (g.n + g.S - 1) / g.S;
@@ -598,11 +598,12 @@ int msm_run(bpgpu_ctx* ctx, const Affine<typename Curve::Fq>* d_points, const vo
     tm.mark("chunk_acc");
   }
   k_giant<Fq><<<ctx->sm_count * 2, GIANT_BLOCK, 0, st>>>(g, pstart, hist, partials, giant, giant + 1);
+  tm.mark("giant");
   {
     uint32_t threads = (uint32_t)g.W * g.nchunk;
     k_merge<Fq><<<(threads + 127) / 128, 128, 0, st>>>(g, bstart, pstart, hist, partials);
   }
-  tm.mark("giant");                                          // stage 4 = k_giant + k_merge
+  tm.mark("merge");
   int qshift = 5 + g.lgL1;
   if (g.nrows) {
     k_bucket_rows<Fq><<<g.W * g.nrows, 256, 0, st>>>(g, pstart, hist, partials, dense, rowsum);

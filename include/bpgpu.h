@@ -61,7 +61,7 @@ int bpgpu_ctx_curve(const bpgpu_ctx* ctx);
 uint64_t bpgpu_ctx_launches(const bpgpu_ctx* ctx);
 
 /* per-stage CUDA-event timing of the MSM pipeline on the ctx stream (roofline evidence for bench.py).
- * stages: 0 digits, 1 scan, 2 scatter, 3 chunk_acc, 4 giant, 5 reduce_l1, 6 reduce_l2.
+ * stages: 0 digits, 1 scan, 2 scatter, 3 chunk_acc, 4 giant, 5 merge, 6 reduce_l1, 7 reduce_l2.
  * set_profile(min_n > 0) records every MSM of at least min_n terms (0 = off); bpgpu_msm_stage_ms writes the average ms
  * per stage since then and returns the run count. */
 int bpgpu_ctx_set_profile(bpgpu_ctx* ctx, int min_n);
