@@ -44,6 +44,7 @@ SYMBOLS = [
     ("bpgpu_msm_parts_batch", _INT, [_VP, _VP, _VP, _SZ, _VP]),
     ("bpgpu_msm_batch_is_identity", _INT, [_VP, _VP, _SZ, _SZ, _VP, _VP, _VP, _SZ, _VP]),
     ("bpgpu_msm_window_bits", _INT, [_SZ]),
+    ("bpgpu_fr_random", _INT, [_VP, _VP, _SZ, _c.c_uint64, _SZ, _c.POINTER(_VP)]),
     ("bpgpu_fixed_bases_create", _INT, [_VP, _VP, _SZ, _c.POINTER(_VP)]),
     ("bpgpu_fixed_bases_get", _INT, [_VP, _VP, _SZ, _c.POINTER(_VP)]),
     ("bpgpu_fixed_bases_commit", _INT, [_VP, _VP, _VP, _SZ, _VP]),
@@ -317,6 +318,12 @@ class Context:
     def alloc_scalars(self, n):
         h = ctypes.c_void_p()
         self._check(lib().bpgpu_scalars_alloc(self.handle, n, ctypes.byref(h)), "scalars_alloc")
+        return DeviceScalars(self, h)
+
+    def fr_random(self, key, ctr0, n):
+        """n scalars of the counter-mode stream SHAKE256(key || le64(ctr0 + i)) mod r, generated on the device"""
+        h = ctypes.c_void_p()
+        self._check(lib().bpgpu_fr_random(self.handle, _buf(key), len(key), ctr0, n, ctypes.byref(h)), "fr_random")
         return DeviceScalars(self, h)
 
     def fr_vandermonde(self, x_be, n):

@@ -133,46 +133,43 @@ struct TranscriptProtocol {
 
 // Source of the prover's blinding scalars and the verifier's batching scalar
 // (FieldElement::random(): prover.rs:336-341,389-402,490-494; verifier.rs:392).
-// mode 0: OS entropy expanded through SHAKE256; mode 1: the deterministic stream the oracle and the tests use,
-// scalar_i = SHAKE256(seed_le64 || tag || i_le64)[..MODBYTES] mod r  (oracle/r1cs.py make_rng).
+// One counter-mode stream in both modes: scalar_i = be_int(SHAKE256(key || le64(i))[..MODBYTES]) mod r.
+//   mode 1 (tests, oracle/r1cs.py make_rng): key = seed_le64 || tag -- the deterministic stream of the parity tests;
+//   mode 0: key = 32 bytes of OS entropy || "os".
+// Counter mode lets the long draws (the blinding VECTORS s_L, s_R) be generated on the device, element i by thread i
+// (fill_device -> bpgpu_fr_random), at the place in the stream where the same number of next() calls would have been.
 template <class C>
 class Rng {
  public:
-  Rng() : deterministic_(false), seed_(0), tag_("os") {
-    // SHAKE256 keyed with OS entropy, squeezed as one continuous stream (one permutation per 136 bytes)
+  Rng() {
     std::random_device rd;
-    memset(st_, 0, sizeof st_);
-    uint8_t* b = reinterpret_cast<uint8_t*>(st_);
-    for (int i = 0; i < 16; i++) { uint32_t w = rd(); memcpy(b + 4 * i, &w, 4); }
-    b[64] ^= 0x1f; b[135] ^= 0x80;
-    keccak_f1600(st_);
-    pos_ = 0;
+    for (int i = 0; i < 8; i++) { uint32_t w = rd(); memcpy(key_ + 4 * i, &w, 4); }
+    key_[32] = 'o'; key_[33] = 's';
+    key_len_ = 34;
   }
-  Rng(uint64_t seed, const std::string& tag) : deterministic_(true), seed_(seed), tag_(tag) {}
+  Rng(uint64_t seed, const std::string& tag) {
+    for (int i = 0; i < 8; i++) key_[key_len_++] = (uint8_t)(seed >> (8 * i));
+    for (char ch : tag) if (key_len_ < 48) key_[key_len_++] = (uint8_t)ch;
+  }
   FieldElement<C> next() {
-    uint8_t out[C::MODBYTES];
-    if (deterministic_) {
-      uint8_t m[64];
-      size_t len = 0;
-      for (int i = 0; i < 8; i++) m[len++] = (uint8_t)(seed_ >> (8 * i));
-      for (char ch : tag_) if (len < 48) m[len++] = (uint8_t)ch;
-      for (int i = 0; i < 8; i++) m[len++] = (uint8_t)(ctr_ >> (8 * i));
-      ctr_++;
-      shake256(m, len, out, sizeof out);
-    } else {
-      const uint8_t* b = reinterpret_cast<const uint8_t*>(st_);
-      for (size_t i = 0; i < sizeof out; i++) { if (pos_ == 136) { keccak_f1600(st_); pos_ = 0; } out[i] = b[pos_++]; }
-    }
+    uint8_t m[64], out[C::MODBYTES];
+    memcpy(m, key_, key_len_);
+    for (int i = 0; i < 8; i++) m[key_len_ + i] = (uint8_t)(ctr_ >> (8 * i));
+    ctr_++;
+    shake256(m, key_len_ + 8, out, sizeof out);
     return FieldElement<C>::from_bytes(out);
+  }
+  // the next n draws as a device-resident vector (FieldElementVector::random); *out is owned by the caller
+  int fill_device(bpgpu_ctx* ctx, size_t n, bpgpu_scalars** out) {
+    int rc = bpgpu_fr_random(ctx, key_, key_len_, ctr_, n, out);
+    if (!rc) ctr_ += n;
+    return rc;
   }
 
  private:
-  bool deterministic_;
-  uint64_t seed_;
-  std::string tag_;
+  uint8_t key_[56] = {0};
+  size_t key_len_ = 0;
   uint64_t ctr_ = 0;
-  uint64_t st_[25];
-  size_t pos_ = 0;
 };
 
 }  // namespace bph

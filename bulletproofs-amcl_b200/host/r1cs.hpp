@@ -250,13 +250,25 @@ class Prover : public ConstraintSystem<C> {
     const size_t n1 = a_L_.size();
     if (G.len() < n1 || H.len() < n1) return E_INVALID_GENERATORS_LENGTH;   // :332-334
     const FE i_blinding1 = rng_.next(), o_blinding1 = rng_.next(), s_blinding1 = rng_.next();   // :336-338
-    std::vector<FE> s_L(n1), s_R(n1);
-    for (auto& s : s_L) s = rng_.next();                               // :340
-    for (auto& s : s_R) s = rng_.next();                               // :341
     int rc;
-    // first-phase witness on the device; the same vectors later feed the polynomial kernels
+    // The first-phase witness goes to the device once and stays: the same vectors feed the commitment MSMs here and the
+    // polynomial kernels later.  s_L, s_R (:340-341) are DRAWN on the device (FieldElementVector::random as
+    // bpgpu_fr_random: the same stream positions n1 + n1 host draws would use), so they never exist on the host.
     FieldElementVector<C> d_aL, d_aR, d_aO, d_sL, d_sR;
-    if ((rc = phase_commit(G, H, 0, n1, s_L, s_R, i_blinding1, o_blinding1, s_blinding1, &proof->A_I1, &proof->A_O1, &proof->S1))) return rc;
+    if ((rc = FieldElementVector<C>::from_host(ctx_, a_L_, &d_aL)) || (rc = FieldElementVector<C>::from_host(ctx_, a_R_, &d_aR)) ||
+        (rc = FieldElementVector<C>::from_host(ctx_, a_O_, &d_aO)))
+      return rc;
+    {
+      bpgpu_scalars *hl = nullptr, *hr = nullptr;
+      if ((rc = rng_.fill_device(ctx_, n1, &hl))) return rc;                                    // :340
+      d_sL = FieldElementVector<C>::adopt(ctx_, hl);
+      if ((rc = rng_.fill_device(ctx_, n1, &hr))) return rc;                                    // :341
+      d_sR = FieldElementVector<C>::adopt(ctx_, hr);
+    }
+    tr.mark("witness upload + blindings");
+    if ((rc = phase_commit_device(G, H, n1, d_aL, d_aR, d_aO, d_sL, d_sR, i_blinding1, o_blinding1, s_blinding1, &proof->A_I1, &proof->A_O1,
+                                  &proof->S1)))
+      return rc;
     tr.mark("A_I1 A_O1 S1");
     TP::commit_point(transcript_, "A_I1", proof->A_I1);                // :364-366
     TP::commit_point(transcript_, "A_O1", proof->A_O1);
@@ -271,11 +283,19 @@ class Prover : public ConstraintSystem<C> {
     const bool has_2nd = n2 > 0;
     FE i_blinding2 = FE::zero(), o_blinding2 = FE::zero(), s_blinding2 = FE::zero();
     if (has_2nd) { i_blinding2 = rng_.next(); o_blinding2 = rng_.next(); s_blinding2 = rng_.next(); }   // :387-399
-    s_L.resize(n); s_R.resize(n);
-    for (size_t i = n1; i < n; i++) s_L[i] = rng_.next();              // :401
-    for (size_t i = n1; i < n; i++) s_R[i] = rng_.next();              // :402
-    if (has_2nd) {                                                     // :404-427
+    if (has_2nd) {                                                     // :401-427
+      // two-phase circuits (randomised constraints): the second-phase variables are few; bring s_L, s_R to the host,
+      // extend them (:401-402), commit the second phase from host vectors and re-upload the full-length witness
+      std::vector<FE> s_L, s_R;
+      if ((rc = d_sL.to_host(&s_L)) || (rc = d_sR.to_host(&s_R))) return rc;
+      s_L.resize(n); s_R.resize(n);
+      for (size_t i = n1; i < n; i++) s_L[i] = rng_.next();            // :401
+      for (size_t i = n1; i < n; i++) s_R[i] = rng_.next();            // :402
       if ((rc = phase_commit(G, H, n1, n, s_L, s_R, i_blinding2, o_blinding2, s_blinding2, &proof->A_I2, &proof->A_O2, &proof->S2))) return rc;
+      if ((rc = FieldElementVector<C>::from_host(ctx_, a_L_, &d_aL)) || (rc = FieldElementVector<C>::from_host(ctx_, a_R_, &d_aR)) ||
+          (rc = FieldElementVector<C>::from_host(ctx_, a_O_, &d_aO)) || (rc = FieldElementVector<C>::from_host(ctx_, s_L, &d_sL)) ||
+          (rc = FieldElementVector<C>::from_host(ctx_, s_R, &d_sR)))
+        return rc;
     } else {
       proof->A_I2 = proof->A_O2 = proof->S2 = G1<C>::identity();      // :429
     }
@@ -291,10 +311,8 @@ class Prover : public ConstraintSystem<C> {
 
     // l(x), r(x) coefficient vectors on the device (:458-486)
     FieldElementVector<C> d_wL, d_wR, d_wO;
-    if ((rc = FieldElementVector<C>::from_host(ctx_, a_L_, &d_aL)) || (rc = FieldElementVector<C>::from_host(ctx_, a_R_, &d_aR)) ||
-        (rc = FieldElementVector<C>::from_host(ctx_, a_O_, &d_aO)) || (rc = FieldElementVector<C>::from_host(ctx_, s_L, &d_sL)) ||
-        (rc = FieldElementVector<C>::from_host(ctx_, s_R, &d_sR)) || (rc = FieldElementVector<C>::from_host(ctx_, wL, &d_wL)) ||
-        (rc = FieldElementVector<C>::from_host(ctx_, wR, &d_wR)) || (rc = FieldElementVector<C>::from_host(ctx_, wO, &d_wO)))
+    if ((rc = FieldElementVector<C>::from_host(ctx_, wL, &d_wL)) || (rc = FieldElementVector<C>::from_host(ctx_, wR, &d_wR)) ||
+        (rc = FieldElementVector<C>::from_host(ctx_, wO, &d_wO)))
       return rc;
     uint8_t yb[C::MODBYTES];
     y.to_bytes(yb);
@@ -421,6 +439,26 @@ class Prover : public ConstraintSystem<C> {
   }
   // A_I = <a_L, G> + <a_R, H> + i_b*h ; A_O = <a_O, G> + o_b*h ; S = <s_L, G> + <s_R, H> + s_b*h over the
   // multipliers [lo, hi)  (prover.rs:347-362 and :404-427): three composite MSMs on cached generator tables
+  // the same three commitments from device-resident scalar vectors (first phase: generators and scalars at offset 0)
+  int phase_commit_device(const G1Vector<C>& G, const G1Vector<C>& H, size_t k, const FieldElementVector<C>& aL, const FieldElementVector<C>& aR,
+                          const FieldElementVector<C>& aO, const FieldElementVector<C>& sL, const FieldElementVector<C>& sR, const FE& i_b,
+                          const FE& o_b, const FE& s_b, G1<C>* A_I, G1<C>* A_O, G1<C>* S) {
+    uint8_t ib[C::MODBYTES], ob[C::MODBYTES], sb[C::MODBYTES];
+    i_b.to_bytes(ib); o_b.to_bytes(ob); s_b.to_bytes(sb);
+    auto part_dev = [&](const G1Vector<C>& T, const FieldElementVector<C>& sc) { bpgpu_msm_part p{T.handle(), 0, nullptr, sc.handle(), 0, nullptr, k}; return p; };
+    auto part_h = [&](const uint8_t* sc) { bpgpu_msm_part p{nullptr, 0, h_.xy, nullptr, 0, sc, 1}; return p; };
+    bpgpu_msm_part parts[8] = {part_dev(G, aL), part_dev(H, aR), part_h(ib),      // A_I  (prover.rs:347-355)
+                               part_dev(G, aO), part_h(ob),                       // A_O  (:358)
+                               part_dev(G, sL), part_dev(H, sR), part_h(sb)};    // S    (:361-362)
+    const size_t counts[3] = {3, 2, 3};
+    uint8_t out[3 * 2 * C::MODBYTES];
+    int rc = bpgpu_msm_parts_batch(ctx_, parts, counts, 3, out);
+    if (rc) return rc;
+    *A_I = G1<C>::from_xy(out);
+    *A_O = G1<C>::from_xy(out + 2 * C::MODBYTES);
+    *S = G1<C>::from_xy(out + 4 * C::MODBYTES);
+    return OK;
+  }
   int phase_commit(const G1Vector<C>& G, const G1Vector<C>& H, size_t lo, size_t hi, const std::vector<FE>& s_L, const std::vector<FE>& s_R,
                    const FE& i_b, const FE& o_b, const FE& s_b, G1<C>* A_I, G1<C>* A_O, G1<C>* S) {
     const size_t k = hi - lo, mb = C::MODBYTES;
@@ -429,7 +467,9 @@ class Prover : public ConstraintSystem<C> {
       for (size_t i = 0; i < k; i++) v[lo + i].to_bytes(be.data() + i * mb);
       return be;
     };
+    Trace tr("phase_commit");
     std::vector<uint8_t> aL = pack(a_L_), aR = pack(a_R_), aO = pack(a_O_), sL = pack(s_L), sR = pack(s_R);
+    tr.mark("pack to bytes");
     uint8_t ib[C::MODBYTES], ob[C::MODBYTES], sb[C::MODBYTES];
     i_b.to_bytes(ib); o_b.to_bytes(ob); s_b.to_bytes(sb);
     auto part_dev = [&](const G1Vector<C>& T, const uint8_t* sc) { bpgpu_msm_part p{T.handle(), lo, nullptr, nullptr, 0, sc, k}; return p; };

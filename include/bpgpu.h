@@ -170,6 +170,11 @@ int bpgpu_fr_poly3_special_inner_product(bpgpu_ctx* ctx, const bpgpu_scalars* l1
 /* elementwise inverses (0 -> 0) into out, product of all inverses into prod_inv_be (may be NULL) */
 int bpgpu_fr_batch_invert(bpgpu_ctx* ctx, const bpgpu_scalars* a, size_t aoff, size_t n, bpgpu_scalars* out,
                           size_t ooff, uint8_t* prod_inv_be);
+/* FieldElementVector::random (the blinding vectors s_L, s_R: prover.rs:340-341, 401-402) generated on the device:
+ * out[i] = be_int(SHAKE256(key || le64(ctr0 + i))[..MODBYTES]) mod r, i < n -- the counter-mode stream of the host
+ * layer's Rng (host/curve.hpp), so a prover that draws a vector here gets exactly the scalars n host draws would give.
+ * key_len <= 64.  The vector never exists on the host. */
+int bpgpu_fr_random(bpgpu_ctx* ctx, const uint8_t* key, size_t key_len, uint64_t ctr0, size_t n, bpgpu_scalars** out);
 
 /* ---- inner-product argument, device-resident across rounds (IPP::create_ipp, ipp.rs:35-202) ----
  * begin: clones G[goff..goff+n), H[hoff..), a, b and the factor vectors (ipp.rs:57-60); n must be a power

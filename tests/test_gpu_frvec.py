@@ -56,3 +56,24 @@ def test_special_inner_product_and_batch_invert(which, ctx_bls, ctx_bn):
     inv, prod = ctx.fr_batch_invert(ctx.upload_scalars(enc_scalars(C, ch)))
     einv, eprod = C.fr_batch_invert(ch)
     assert dec_scalars(C, inv.download()) == einv and int.from_bytes(prod, "big") == eprod
+
+
+@pytest.mark.parametrize("which", ["bls", "bn"])
+def test_device_random_vector_is_the_host_stream(which, ctx_bls, ctx_bn):
+    """bpgpu_fr_random (FieldElementVector::random on the device, prover.rs:340-341): element i is
+    SHAKE256(key || le64(ctr0 + i)) reduced mod r -- for key = seed_le64 || "blind" that is the oracle's blinding stream
+    (oracle/r1cs.py make_rng), including the 384 -> 255 bit reduction on BLS12-381."""
+    ctx = ctx_bls if which == "bls" else ctx_bn
+    C = curve_of(ctx)
+    for seed, ctr0, n in ((1, 0, 300), (77, 5, 33), (2**63 + 5, 2**40, 4), (3, 0, 0)):
+        key = (seed % 2**64).to_bytes(8, "little") + b"blind"
+        v = ctx.fr_random(key, ctr0, n)
+        assert len(v) == n
+        exp = [C.synth_scalar(seed % 2**64, ctr0 + i, b"blind") for i in range(n)]
+        assert v.download() == enc_scalars(C, exp)
+        v.free()
+    # any key up to 64 bytes; distinct keys give distinct streams
+    a, b = ctx.fr_random(b"k" * 64, 0, 8), ctx.fr_random(b"k" * 63 + b"j", 0, 8)
+    assert a.download() != b.download()
+    with pytest.raises(Exception):
+        ctx.fr_random(b"k" * 65, 0, 1)
