@@ -243,21 +243,24 @@ static int fetch_result(bpgpu_ctx* ctx, const void* d_src, size_t bytes, uint8_t
 namespace bp {
 // Host finish of one MSM: Horner over the general path's window sums (if any) + the table path's sum (if any),
 // then one affine normalisation.
+// set / nsets: which scalar set of a multi-set run (MsmResult::nsets) the W windows belong to
 template <class FqParams>
-static void msm_finish_mixed(const uint8_t* winsum_bytes, int W, int c, int qshift, const uint8_t* table_sum, int modbytes, uint8_t* out_xy) {
+static void msm_finish_mixed(const uint8_t* winsum_bytes, int W, int c, int qshift, const uint8_t* table_sum, int modbytes, uint8_t* out_xy,
+                             int set = 0, int nsets = 1) {
   using HP = host::HXYZZ<FqParams>;
   HP acc = HP::inf();
-  const HP* ws = reinterpret_cast<const HP*>(winsum_bytes);
+  const HP* wp = reinterpret_cast<const HP*>(winsum_bytes) + (size_t)set * W;            // P_w of this set
+  const HP* wq = reinterpret_cast<const HP*>(winsum_bytes) + (size_t)(nsets + set) * W;  // Q_w of this set
   // acc * 2^c + P_w + 2^q * Q_w = ((acc * 2^(c-q)) + Q_w) * 2^q + P_w : the shift of Q_w rides the window's own c doublings
   // (q = 5 + lgL1 < c always: a level-1 segment is at most half a window)
   const int q = qshift < c ? qshift : 0;
   for (int w = W - 1; w >= 0; w--) {
-    HP qw = ws[W + w];
+    HP qw = wq[w];
     if (q == 0 && !qw.is_inf()) for (int k = 0; k < qshift; k++) qw.dbl();
     if (w != W - 1) for (int k = 0; k < c - q; k++) acc.dbl();
     acc.add(qw);
     for (int k = 0; k < q; k++) acc.dbl();
-    acc.add(ws[w]);
+    acc.add(wp[w]);
   }
   if (table_sum) acc.add(*reinterpret_cast<const HP*>(table_sum));
   acc.to_xy_be(modbytes, out_xy);
@@ -293,6 +296,28 @@ int msm_mixed_to_host(bpgpu_ctx* ctx, const TableSeg* segs, int nsegs, const voi
   if (hp) { if (bls) host_sum_partials<BlsFq>(tsum, 1, hp); else host_sum_partials<BnFq>(tsum, 1, hp); }
   if (bls) msm_finish_mixed<BlsFq>(ctx->pinned, res.W, res.c, res.qshift, tn ? tsum : nullptr, mb, out_xy);
   else msm_finish_mixed<BnFq>(ctx->pinned, res.W, res.c, res.qshift, tn ? tsum : nullptr, mb, out_xy);
+  return BPGPU_OK;
+}
+
+int msm_pair_to_host(bpgpu_ctx* ctx, const void* d_pts, const void* d_scal_a, const void* d_scal_b, bool mont, size_t n, uint8_t* out_a_xy,
+                     uint8_t* out_b_xy) {
+  const int mb = bpgpu_modbytes(ctx->curve);
+  const bool bls = ctx->curve == BPGPU_BLS12_381;
+  const size_t psz = bls ? sizeof(XYZZ<Bls::Fq>) : sizeof(XYZZ<Bn::Fq>);
+  MsmResult res;
+  int rc = bls ? msm_run<Bls>(ctx, (const Affine<Bls::Fq>*)d_pts, d_scal_a, mont, n, &res, d_scal_b)
+               : msm_run<Bn>(ctx, (const Affine<Bn::Fq>*)d_pts, d_scal_a, mont, n, &res, d_scal_b);
+  if (rc) return rc;
+  if (res.W) {
+    if ((size_t)4 * res.W * psz > ctx->pinned_cap / 2) return BPGPU_E_ARG;
+    BP_CUDA_OK(cudaMemcpyAsync(ctx->pinned, res.d_winsum, (size_t)4 * res.W * psz, cudaMemcpyDeviceToHost, ctx->stream));
+    BP_CUDA_OK(cudaStreamSynchronize(ctx->stream));
+  }
+  uint8_t* outs[2] = {out_a_xy, out_b_xy};
+  for (int s = 0; s < 2; s++) {
+    if (bls) msm_finish_mixed<BlsFq>(ctx->pinned, res.W, res.c, res.qshift, nullptr, mb, outs[s], s, 2);
+    else msm_finish_mixed<BnFq>(ctx->pinned, res.W, res.c, res.qshift, nullptr, mb, outs[s], s, 2);
+  }
   return BPGPU_OK;
 }
 

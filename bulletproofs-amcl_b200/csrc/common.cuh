@@ -162,7 +162,9 @@ int launch_check(bpgpu_ctx* ctx, const char* what);
 
 // per-window sums an MSM leaves on the device: result = sum_w 2^(c*w) * winsum[w]
 // window w = P_w + 2^qshift * Q_w with P = d_winsum[0..W), Q = d_winsum[W..2W)
-struct MsmResult { int W; int c; int qshift; const void* d_winsum; };
+// with nsets scalar sets (msm_run d_scalars2) set s owns windows [s*W, (s+1)*W) of the nsets*W in all: P = d_winsum[0, nsets*W),
+// Q = d_winsum[nsets*W, 2*nsets*W)
+struct MsmResult { int W; int c; int qshift; const void* d_winsum; int nsets = 1; };
 
 // ---- window tables of fixed points (fixedbase.cu): T[i][w][d-1] = d * 2^(4w) * P_i, w < 64, d = 1..15, affine
 static const int TBL_WINDOWS = 64;
@@ -202,6 +204,9 @@ template <class Curve> int fr_args_upload(bpgpu_ctx* ctx, const uint8_t* be, int
 template <class Curve> int fr_pow_table_upload(bpgpu_ctx* ctx, const uint8_t* x_be, Scratch& dst, typename Curve::Fr** d_out);
 
 template <class Curve> int msm_run(bpgpu_ctx* ctx, const Affine<typename Curve::Fq>* d_points, const void* d_scalars,
-                                   bool scalars_mont, size_t n, MsmResult* res);
+                                   bool scalars_mont, size_t n, MsmResult* res, const void* d_scalars2 = nullptr);
+// two MSMs over the same device points (scalars Fr[n] each) from ONE pipeline run and one synchronisation (api.cu)
+int msm_pair_to_host(bpgpu_ctx* ctx, const void* d_pts, const void* d_scal_a, const void* d_scal_b, bool mont, size_t n, uint8_t* out_a_xy,
+                     uint8_t* out_b_xy);
 
 }  // namespace bp

@@ -234,8 +234,8 @@ static int ipp_round_t(bpgpu_ipp* st, uint8_t* L_xy, uint8_t* R_xy) {
   ctx->launches += 2;
   rc = launch_check(ctx, "ipp_round");
   if (rc) return rc;
-  if ((rc = msm_to_host(ctx, st->P, st->sclL, true, 2 * (size_t)N + 1, L_xy))) return rc;
-  return msm_to_host(ctx, st->P, st->sclR, true, 2 * (size_t)N + 1, R_xy);
+  // L and R share the points: one pipeline run with the R scalars as extra windows, one synchronisation
+  return msm_pair_to_host(ctx, st->P, st->sclL, st->sclR, true, 2 * (size_t)N + 1, L_xy, R_xy);
 }
 
 template <class Curve>

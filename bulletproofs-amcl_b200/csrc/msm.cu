@@ -31,7 +31,8 @@ namespace bp {
 struct MsmGeom {
   uint32_t n;       // number of terms
   int c;            // window bits
-  int W;            // windows
+  int W;            // windows in all (W0 per scalar set)
+  int W0;           // windows of ONE scalar: several scalar sets over the same points are extra windows (msm_run nsets)
   uint32_t nbp;     // bucket slots per window = 2^(c-1) + 1 (slot 0 unused)
   uint32_t S;       // sorted entries per chunk thread
   uint32_t nchunk;  // chunk threads per window = ceil(n / S)
@@ -59,10 +60,14 @@ int msm_window_bits(size_t n) {
 
 // ------------------------------------------------------------------------------------------
 template <class Fr>
-__global__ void __launch_bounds__(256) k_digits(const Fr* __restrict__ scal, int mont, MsmGeom g,
+__global__ void __launch_bounds__(256) k_digits(const Fr* __restrict__ scal0, const Fr* __restrict__ scal1, int mont, MsmGeom g,
                                                 uint32_t* __restrict__ digits, uint32_t* __restrict__ hist) {
   uint32_t i = blockIdx.x * blockDim.x + threadIdx.x;
   if (i >= g.n) return;
+  const int set = blockIdx.y;                   // scalar set: its digits are windows [set * W0, (set + 1) * W0)
+  const Fr* scal = set ? scal1 : scal0;
+  digits += (size_t)set * g.W0 * g.n;
+  hist += (size_t)set * g.W0 * g.nbp;
   Fr s = load_vec(scal + i);
   if (mont) s = s.from_mont();
   uint32_t limbs[9];
@@ -72,7 +77,7 @@ __global__ void __launch_bounds__(256) k_digits(const Fr* __restrict__ scal, int
   const uint32_t half = 1u << (g.c - 1);
   const uint32_t mask = (1u << g.c) - 1;
   uint32_t carry = 0;
-  for (int w = 0; w < g.W; w++) {
+  for (int w = 0; w < g.W0; w++) {
     uint32_t bit = (uint32_t)w * g.c;
     uint32_t limb = bit >> 5, sh = bit & 31;
     uint32_t d = 0;
@@ -496,13 +501,15 @@ struct StageTimer {
 
 // Leaves the W per-window sums (XYZZ, Montgomery form) in ctx scratch; the caller combines them
 // (Horner over windows + affine normalisation) on the host, see msm_finish_host in api.cu.
+// d_scalars2 (optional): a SECOND scalar vector over the same points (the L and R of an IPP round): its windows are
+// appended to the first one's, every later stage just sees 2 * W0 windows, and one pipeline run yields both sums.
 template <class Curve>
 int msm_run(bpgpu_ctx* ctx, const Affine<typename Curve::Fq>* d_points, const void* d_scalars, bool scalars_mont, size_t n,
-            MsmResult* res) {
+            MsmResult* res, const void* d_scalars2) {
   using Fq = typename Curve::Fq;
   using Fr = typename Curve::Fr;
   cudaStream_t st = ctx->stream;
-  res->W = 0; res->c = 0; res->qshift = 0; res->d_winsum = nullptr;
+  res->W = 0; res->c = 0; res->qshift = 0; res->d_winsum = nullptr; res->nsets = d_scalars2 ? 2 : 1;
   if (n == 0) return BPGPU_OK;
   if (n >= (1ull << 31)) return BPGPU_E_ARG;
   MsmGeom g;
@@ -514,7 +521,8 @@ int msm_run(bpgpu_ctx* ctx, const Affine<typename Curve::Fq>* d_points, const vo
   static const char* env_l1 = getenv("BPGPU_LGL1");
   static const char* env_rc = getenv("BPGPU_ROWCOL");
   if (env_c) g.c = atoi(env_c);
-  g.W = (Curve::SCALAR_BITS + 1 + g.c - 1) / g.c;
+  g.W0 = (Curve::SCALAR_BITS + 1 + g.c - 1) / g.c;
+  g.W = g.W0 * (d_scalars2 ? 2 : 1);
   g.nbp = (1u << (g.c - 1)) + 1;
   {
     // Chunk length: long enough that a bucket is split into few partial sums (the reduction reads them all), short enough
@@ -574,7 +582,7 @@ int msm_run(bpgpu_ctx* ctx, const Affine<typename Curve::Fq>* d_points, const vo
   BP_CUDA_OK(cudaMemsetAsync(hist, 0, sz_hist, st));
   BP_CUDA_OK(cudaMemsetAsync(giant, 0, 4, st));
 
-  k_digits<Fr><<<(g.n + 255) / 256, 256, 0, st>>>((const Fr*)d_scalars, scalars_mont ? 1 : 0, g, digits, hist);
+  k_digits<Fr><<<dim3((g.n + 255) / 256, d_scalars2 ? 2 : 1), 256, 0, st>>>((const Fr*)d_scalars, (const Fr*)d_scalars2, scalars_mont ? 1 : 0, g, digits, hist);
   tm.mark("digits");
   k_scan<<<g.W, 1024, 0, st>>>(g, hist, bstart, cursor, pstart, giant, giant + 1);
   tm.mark("scan");
@@ -621,13 +629,13 @@ int msm_run(bpgpu_ctx* ctx, const Affine<typename Curve::Fq>* d_points, const vo
     tm.mark("reduce_l2");
   }
   ctx->launches += 8;
-  res->W = g.W; res->c = g.c; res->qshift = qshift; res->d_winsum = winsum;
+  res->W = g.W0; res->c = g.c; res->qshift = qshift; res->d_winsum = winsum;    // P at [0, nsets*W), Q at [nsets*W, 2*nsets*W)
   int lrc = launch_check(ctx, "msm");
   tm.report(g, ctx);
   return lrc;
 }
 
-template int msm_run<Bls>(bpgpu_ctx*, const Affine<Bls::Fq>*, const void*, bool, size_t, MsmResult*);
-template int msm_run<Bn>(bpgpu_ctx*, const Affine<Bn::Fq>*, const void*, bool, size_t, MsmResult*);
+template int msm_run<Bls>(bpgpu_ctx*, const Affine<Bls::Fq>*, const void*, bool, size_t, MsmResult*, const void*);
+template int msm_run<Bn>(bpgpu_ctx*, const Affine<Bn::Fq>*, const void*, bool, size_t, MsmResult*, const void*);
 
 }  // namespace bp
