@@ -93,6 +93,8 @@ SYMBOLS_HOST = [
     ("bph_range_proof_len", _SZ, [_INT, _SZ, _SZ]),
     ("bph_range_prove_many", _INT, [_VP, _SZ, _CS, _VP, _VP, _VP, _VP, _VP, _SZ, _SZ, _SZ, _INT, _U64, _VP, _SZ, _VP]),
     ("bph_range_verify_batch", _INT, [_VP, _CS, _VP, _VP, _VP, _VP, _SZ, _SZ, _SZ, _VP, _SZ, _VP, _SZ, _VP]),
+    ("bph_msm_sharded", _INT, [_VP, _SZ, _VP, _VP, _VP, _VP]),
+    ("bph_g1_sum", _INT, [_INT, _VP, _SZ, _VP]),
     ("bph_range_verify_many", _INT, [_VP, _SZ, _CS, _VP, _VP, _VP, _VP, _SZ, _SZ, _SZ, _VP, _SZ, _VP, _VP]),
 ]
 
@@ -137,6 +139,31 @@ def range_verify_many(ctxs, label, g_xy, h_xy, G, H, count, m, bits, proofs, str
     if rc:
         raise BpgpuError(rc, "range_verify_many")
     return list(verdicts)[:count]
+
+
+def msm_sharded(ctxs, shards, scalars_be):
+    """sum over all shards of <shard points, their scalars>: shards[k] is a DevicePoints resident on ctxs[k]'s device, the
+    scalars follow the shards in order.  One host thread per context; the partial sums are combined on the host."""
+    n = len(ctxs)
+    mb = ctxs[0].modbytes
+    arr_c = (ctypes.c_void_p * n)(*[c.handle for c in ctxs])
+    arr_p = (ctypes.c_void_p * n)(*[s.handle for s in shards])
+    arr_n = (ctypes.c_size_t * n)(*[len(s) for s in shards])
+    out = ctypes.create_string_buffer(2 * mb)
+    rc = lib().bph_msm_sharded(arr_c, n, arr_p, arr_n, _buf(scalars_be), out)
+    if rc:
+        raise BpgpuError(rc, "msm_sharded")
+    return out.raw
+
+
+def g1_sum(curve, points_xy):
+    """host-side sum of affine points X||Y (the combine step of a sharded MSM)"""
+    mb = 48 if curve == BLS12_381 else 32
+    out = ctypes.create_string_buffer(2 * mb)
+    rc = lib().bph_g1_sum(curve, _buf(points_xy), len(points_xy) // (2 * mb), out)
+    if rc:
+        raise BpgpuError(rc, "g1_sum")
+    return out.raw
 
 
 def range_verify_batch(ctx, label, g_xy, h_xy, G, H, count, m, bits, proofs, stride, comms, nthreads=0):

@@ -255,6 +255,26 @@ int range_verify_batch_t(bpgpu_ctx* ctx, const char* label, const uint8_t* g_xy,
   return BPGPU_OK;
 }
 
+template <class FqP>
+void g1_sum_host(const uint8_t* xy, size_t count, int mb, uint8_t* out) {
+  using HP = bp::host::HXYZZ<FqP>;
+  using F = typename HP::F;
+  HP acc = HP::inf();
+  for (size_t i = 0; i < count; i++) {
+    const uint8_t* p = xy + i * 2 * mb;
+    bool ident = p[2 * mb - 1] == 1;                                    // AMCL's identity encoding: x = 0, y = 1
+    for (int k = 0; k < 2 * mb - 1 && ident; k++) ident = p[k] == 0;
+    if (ident) continue;
+    HP q;
+    q.x = F::from_be(p, mb);
+    q.y = F::from_be(p + mb, mb);
+    q.zz = F::one();
+    q.zzz = F::one();
+    acc.add(q);
+  }
+  acc.to_xy_be(mb, out);
+}
+
 }  // namespace
 
 #define BY_CURVE(ctx, CALL) (bpgpu_ctx_curve(ctx) == BPGPU_BLS12_381 ? CALL(Bls381) : CALL(Bn254))
@@ -401,6 +421,39 @@ int bph_range_verify_many(bpgpu_ctx* const* ctxs, size_t nctx, const char* label
     return 0;
   });
   return BPGPU_OK;
+}
+
+int bph_g1_sum(int curve, const uint8_t* points_xy, size_t count, uint8_t* out_xy) {
+  if ((!points_xy && count) || !out_xy || (curve != BPGPU_BLS12_381 && curve != BPGPU_BN254)) return BPGPU_E_ARG;
+  if (curve == BPGPU_BLS12_381) g1_sum_host<bp::BlsFq>(points_xy, count, 48, out_xy);
+  else g1_sum_host<bp::BnFq>(points_xy, count, 32, out_xy);
+  return BPGPU_OK;
+}
+
+int bph_msm_sharded(bpgpu_ctx* const* ctxs, size_t nctx, const bpgpu_points* const* shards, const size_t* counts, const uint8_t* scalars_be,
+                    uint8_t* out_xy) {
+  if (!ctxs || !nctx || !shards || !counts || !out_xy) return BPGPU_E_ARG;
+  const int curve = bpgpu_ctx_curve(ctxs[0]);
+  const size_t mb = (size_t)bpgpu_modbytes(curve);
+  std::vector<size_t> off(nctx + 1, 0);
+  for (size_t k = 0; k < nctx; k++) {
+    if (!ctxs[k] || bpgpu_ctx_curve(ctxs[k]) != curve || (counts[k] && !shards[k])) return BPGPU_E_ARG;
+    if (counts[k] && bpgpu_points_len(shards[k]) < counts[k]) return BPGPU_E_LEN;
+    off[k + 1] = off[k] + counts[k];
+  }
+  if (off[nctx] && !scalars_be) return BPGPU_E_ARG;
+  std::vector<uint8_t> partial(nctx * 2 * mb);
+  std::vector<int> rcs(nctx, BPGPU_OK);
+  auto work = [&](size_t k) {
+    static const uint8_t none = 0;
+    rcs[k] = bpgpu_msm(ctxs[k], shards[k], 0, counts[k], counts[k] ? scalars_be + off[k] * mb : &none, partial.data() + k * 2 * mb);
+  };
+  std::vector<std::thread> th;
+  for (size_t k = 1; k < nctx; k++) th.emplace_back(work, k);
+  work(0);
+  for (auto& t : th) t.join();
+  for (int rc : rcs) if (rc) return rc;
+  return bph_g1_sum(curve, partial.data(), nctx, out_xy);
 }
 
 int bph_range_verify_batch(bpgpu_ctx* ctx, const char* label, const uint8_t* g_xy, const uint8_t* h_xy, bpgpu_points* G, bpgpu_points* H,

@@ -34,11 +34,12 @@ def allgather_bytes(dist, payload, device=None):
 
 
 def combine_partials(ctx, partials):
-    """sum of the per-rank affine partial sums, on the device (an N-term MSM with unit scalars)"""
+    """sum of the per-rank affine partial sums (2*MODBYTES bytes each): at most 8 additions, done on the host
+    (bph_g1_sum) -- a device launch pipeline would cost more than the additions.  `ctx` is a Context or a curve id."""
     if len(partials) == 1:
         return partials[0]
-    one = (1).to_bytes(ctx.modbytes, "big")
-    return ctx.msm_refs(b"".join(partials), one * len(partials), n=len(partials))
+    from .binding import g1_sum
+    return g1_sum(ctx if isinstance(ctx, int) else ctx.curve, b"".join(partials))
 
 
 def sharded_msm(ctx, dist, local_msm):

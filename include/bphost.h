@@ -95,6 +95,17 @@ int bph_range_verify_batch(bpgpu_ctx* ctx, const char* transcript_label, const u
                            bpgpu_points* H, size_t count, size_t m, size_t bits, const uint8_t* proofs, size_t proof_stride,
                            const uint8_t* comms_xy, size_t nthreads, int32_t* verdicts);
 
+/* ---- MSM sharded by points over several contexts: one process, one context per GPU (or several per GPU) ----
+ * shard k = `counts[k]` points resident on ctxs[k]'s device (bpgpu_points_upload there), its scalars are the next counts[k]
+ * entries of scalars_be.  One host thread per context runs bpgpu_msm on its shard; the affine partial sums (2*MODBYTES
+ * bytes each -- the only data that leaves a GPU) are added on the host.  The total is a group element, so the result
+ * bytes do not depend on how the points were split.  (With one PROCESS per GPU the same partials travel through
+ * ncclAllGather instead: bulletproofs-amcl_b200/sharding.py, bench.py.) */
+int bph_msm_sharded(bpgpu_ctx* const* ctxs, size_t nctx, const bpgpu_points* const* shards, const size_t* counts, const uint8_t* scalars_be,
+                    uint8_t* out_xy);
+/* sum of `count` affine points given as X||Y (identity = (0, 1)), on the host: the combine step of the sharded MSM */
+int bph_g1_sum(int curve, const uint8_t* points_xy, size_t count, uint8_t* out_xy);
+
 #ifdef __cplusplus
 }
 #endif

@@ -196,3 +196,25 @@ def test_batch_identity_check(which, ctx_bls, ctx_bn):
     plain = ctx.upload_points(enc_points(C, fixed))
     with pytest.raises(Exception):                          # tables are required
         ctx.msm_batch_is_identity([(plain, 0, nf)], 1, enc_scalars(C, fs[:nf]), b"", b"", 0)
+
+
+@pytest.mark.parametrize("which", ["bls", "bn"])
+def test_msm_sharded_over_contexts(which, bp, ctx_bls, ctx_bn):
+    """bph_msm_sharded: the points split unevenly over three contexts (here three streams of one GPU; one
+    per GPU in production), an empty shard included -- the bytes equal the unsharded MSM's and the oracle's."""
+    ctx = ctx_bls if which == "bls" else ctx_bn
+    C = curve_of(ctx)
+    cid = bp.BLS12_381 if which == "bls" else bp.BN254
+    n = 700
+    P = rand_points(C, n, 31)
+    s = C.synth_scalars(8, n)
+    exp = C.g1_xy_bytes(C.msm(P, s))
+    ctxs = [ctx, bp.Context(cid, 0), bp.Context(cid, 0), bp.Context(cid, 0)]
+    cuts = [0, 300, 301, 301, n]
+    shards = [ctxs[k].upload_points(enc_points(C, P[cuts[k]:cuts[k + 1]])) for k in range(4)]
+    assert bp.msm_sharded(ctxs, shards, enc_scalars(C, s)) == exp
+    assert ctx.msm_refs(enc_points(C, P), enc_scalars(C, s)) == exp
+    for sh in shards:
+        sh.free()
+    for c in ctxs[1:]:
+        c.close()

@@ -48,3 +48,19 @@ def test_transcript_protocol_matches_oracle(bp, C):
     t.commit_point(b"P", C.INF)
     t.commit_scalar(b"s", 5)
     assert out.raw == C.fr_to_bytes(t.challenge_scalar(b"c"))
+
+
+@pytest.mark.parametrize("C", [BLS12_381, BN254], ids=lambda c: c.name)
+def test_host_g1_sum_is_the_combine_step(bp, C):
+    """bph_g1_sum: the host-side addition of per-shard partial sums, incl. identity entries, a repeated
+    point (P + P), an inverse pair and the empty list."""
+    G = C.from_affine(C.g)
+    pts = [C.mul(G, k) for k in (5, 11, 11, 1234567)] + [C.INF, C.neg(C.mul(G, 5))]
+    exp = C.INF
+    for P in pts:
+        exp = C.add(exp, P)
+    xy = b"".join(C.g1_xy_bytes(P) for P in pts)
+    cid = bp.BLS12_381 if C.id == 0 else bp.BN254
+    assert bp.g1_sum(cid, xy) == C.g1_xy_bytes(exp)
+    assert bp.g1_sum(cid, b"") == C.g1_xy_bytes(C.INF)
+    assert bp.g1_sum(cid, C.g1_xy_bytes(G) + C.g1_xy_bytes(C.neg(G))) == C.g1_xy_bytes(C.INF)

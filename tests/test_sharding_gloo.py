@@ -37,6 +37,8 @@ def _worker(rank, world, port, q):
         for p in parts:
             total = C.add(total, C.g1_from_xy_bytes(p))
         ok_msm = C.g1_xy_bytes(total) == C.g1_xy_bytes(C.msm(pts, sc)) and len(parts) == world
+        # the product's own combine step (host-side bph_g1_sum; needs no GPU) gives the same bytes on every rank
+        ok_msm = ok_msm and sharding.combine_partials(0, parts) == C.g1_xy_bytes(total)
         # proof-sharded verdicts: rank 1 holds the failing proof
         count = 6
         lo, hi = sharding.shard_bounds(count, world, rank)
