@@ -233,7 +233,7 @@ template int scalars_from_host<Bn>(bpgpu_ctx*, const uint8_t*, size_t, int, void
 
 static int fetch_result(bpgpu_ctx* ctx, const void* d_src, size_t bytes, uint8_t* host_out) {
   BP_CUDA_OK(cudaMemcpyAsync(ctx->pinned, d_src, bytes, cudaMemcpyDeviceToHost, ctx->stream));
-  BP_CUDA_OK(cudaStreamSynchronize(ctx->stream));
+  BP_CUDA_OK(stream_sync(ctx));
   memcpy(host_out, ctx->pinned, bytes);
   return BPGPU_OK;
 }
@@ -292,7 +292,7 @@ int msm_mixed_to_host(bpgpu_ctx* ctx, const TableSeg* segs, int nsegs, const voi
                                        ctx->stream));
     else BP_CUDA_OK(cudaMemcpyAsync(tsum, ctx->tbl_part.p, psz, cudaMemcpyDeviceToHost, ctx->stream));
   }
-  if (res.W || tn) BP_CUDA_OK(cudaStreamSynchronize(ctx->stream));
+  if (res.W || tn) BP_CUDA_OK(stream_sync(ctx));
   if (hp) { if (bls) host_sum_partials<BlsFq>(tsum, 1, hp); else host_sum_partials<BnFq>(tsum, 1, hp); }
   if (bls) msm_finish_mixed<BlsFq>(ctx->pinned, res.W, res.c, res.qshift, tn ? tsum : nullptr, mb, out_xy);
   else msm_finish_mixed<BnFq>(ctx->pinned, res.W, res.c, res.qshift, tn ? tsum : nullptr, mb, out_xy);
@@ -311,7 +311,7 @@ int msm_pair_to_host(bpgpu_ctx* ctx, const void* d_pts, const void* d_scal_a, co
   if (res.W) {
     if ((size_t)4 * res.W * psz > ctx->pinned_cap / 2) return BPGPU_E_ARG;
     BP_CUDA_OK(cudaMemcpyAsync(ctx->pinned, res.d_winsum, (size_t)4 * res.W * psz, cudaMemcpyDeviceToHost, ctx->stream));
-    BP_CUDA_OK(cudaStreamSynchronize(ctx->stream));
+    BP_CUDA_OK(stream_sync(ctx));
   }
   uint8_t* outs[2] = {out_a_xy, out_b_xy};
   for (int s = 0; s < 2; s++) {
@@ -375,6 +375,8 @@ int bpgpu_ctx_create(int curve, int device, bpgpu_ctx** out) {
   BP_CUDA_OK(cudaStreamCreateWithFlags(&c->stream, cudaStreamNonBlocking));
   BP_CUDA_OK(cudaStreamCreateWithFlags(&c->copy_stream, cudaStreamNonBlocking));
   BP_CUDA_OK(cudaEventCreateWithFlags(&c->points_ready, cudaEventDisableTiming));
+  BP_CUDA_OK(cudaEventCreateWithFlags(&c->sync_event, cudaEventDisableTiming | cudaEventBlockingSync));
+  { const char* e = getenv("BPGPU_BLOCKING_SYNC"); c->blocking_sync = e && atoi(e) != 0; }
   {
     cudaMemPool_t pool;
     uint64_t keep = ~0ull;                      // keep freed blocks in the pool: the next proof reuses them
@@ -400,6 +402,7 @@ void bpgpu_ctx_destroy(bpgpu_ctx* c) {
   cudaStreamDestroy(c->stream);
   if (c->copy_stream) cudaStreamDestroy(c->copy_stream);
   if (c->points_ready) cudaEventDestroy(c->points_ready);
+  if (c->sync_event) cudaEventDestroy(c->sync_event);
   delete c;
 }
 
@@ -445,7 +448,7 @@ int bpgpu_points_upload(bpgpu_ctx* ctx, const uint8_t* xy, size_t n, bpgpu_point
 #define CALL(C) points_from_host<C>(ctx, xy, n, p->d)
   int rc = DISPATCH(ctx, CALL);
 #undef CALL
-  if (rc == BPGPU_OK && cudaStreamSynchronize(ctx->stream) != cudaSuccess) rc = BPGPU_E_CUDA;
+  if (rc == BPGPU_OK && stream_sync(ctx) != cudaSuccess) rc = BPGPU_E_CUDA;
   if (rc) { dev_free(ctx, p->d); delete p; return rc; }
   *out = p;
   return BPGPU_OK;
@@ -466,7 +469,7 @@ int bpgpu_points_download(bpgpu_ctx* ctx, const bpgpu_points* p, size_t off, siz
   ctx->launches++;
   if ((rc = launch_check(ctx, "k_points_to_be"))) return rc;
   BP_CUDA_OK(cudaMemcpyAsync(xy, ctx->io_dev.p, bytes, cudaMemcpyDeviceToHost, ctx->stream));
-  BP_CUDA_OK(cudaStreamSynchronize(ctx->stream));
+  BP_CUDA_OK(stream_sync(ctx));
   return BPGPU_OK;
 }
 
@@ -498,7 +501,7 @@ int bpgpu_scalars_upload(bpgpu_ctx* ctx, const uint8_t* be, size_t n, bpgpu_scal
 #define CALL(C) scalars_upload_t<C>(ctx, be, n, 1, s->d, ctx->io_dev)
   int rc = DISPATCH(ctx, CALL);
 #undef CALL
-  if (rc == BPGPU_OK && cudaStreamSynchronize(ctx->stream) != cudaSuccess) rc = BPGPU_E_CUDA;
+  if (rc == BPGPU_OK && stream_sync(ctx) != cudaSuccess) rc = BPGPU_E_CUDA;
   if (rc) { dev_free(ctx, s->d); delete s; return rc; }
   *out = s;
   return BPGPU_OK;
@@ -519,7 +522,7 @@ int bpgpu_scalars_download(bpgpu_ctx* ctx, const bpgpu_scalars* s, size_t off, s
   ctx->launches++;
   if ((rc = launch_check(ctx, "k_scalars_to_be"))) return rc;
   BP_CUDA_OK(cudaMemcpyAsync(be, ctx->io_dev.p, bytes, cudaMemcpyDeviceToHost, ctx->stream));
-  BP_CUDA_OK(cudaStreamSynchronize(ctx->stream));
+  BP_CUDA_OK(stream_sync(ctx));
   return BPGPU_OK;
 }
 
@@ -619,7 +622,7 @@ int bpgpu_selftest_field(bpgpu_ctx* ctx, int field, int op, const uint8_t* a, co
   ctx->launches++;
   if ((rc = launch_check(ctx, "k_field_op"))) return rc;
   BP_CUDA_OK(cudaMemcpyAsync(out, dout, bytes, cudaMemcpyDeviceToHost, ctx->stream));
-  BP_CUDA_OK(cudaStreamSynchronize(ctx->stream));
+  BP_CUDA_OK(stream_sync(ctx));
   return BPGPU_OK;
 }
 

@@ -181,7 +181,7 @@ static int batch_identity_t(bpgpu_ctx* ctx, const FixedRuns& runs, uint32_t F, s
     ctx->launches += 2;
     if ((rc = launch_check(ctx, "batch_identity"))) return rc;
     BP_CUDA_OK(cudaMemcpyAsync(is_identity + lo, d_v, cnt, cudaMemcpyDeviceToHost, ctx->stream));
-    BP_CUDA_OK(cudaStreamSynchronize(ctx->stream));
+    BP_CUDA_OK(stream_sync(ctx));
   }
   return BPGPU_OK;
 }

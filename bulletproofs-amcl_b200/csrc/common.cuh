@@ -69,6 +69,10 @@ struct bpgpu_ctx {
   cudaStream_t copy_stream = nullptr;
   cudaEvent_t points_ready = nullptr;
   bool wait_points = false;        // consumed by the next msm_run
+  // waiting for the stream: spin (lowest latency, one core per context) or sleep on a blocking event (BPGPU_BLOCKING_SYNC=1 /
+  // bpgpu_ctx_set_blocking_sync: lets more contexts than cores keep launches in flight)
+  bool blocking_sync = false;
+  cudaEvent_t sync_event = nullptr;
   uint64_t launches = 0;
   // MSM scratch
   bp::Scratch msm_a, msm_b, msm_c, msm_d, msm_e, io_dev, io_dev2;
@@ -99,6 +103,11 @@ namespace bp {
 // Handle storage (G1Vector / FieldElementVector / IPP state) comes from the device's stream-ordered pool on the ctx
 // stream: allocation and release are queue operations (microseconds), not driver calls that synchronise the device.
 // The pool's release threshold is raised at ctx creation so freed blocks are reused by the next proof.
+inline cudaError_t stream_sync(bpgpu_ctx* ctx) {
+  if (!ctx->blocking_sync) return cudaStreamSynchronize(ctx->stream);
+  cudaError_t e = cudaEventRecord(ctx->sync_event, ctx->stream);
+  return e != cudaSuccess ? e : cudaEventSynchronize(ctx->sync_event);
+}
 inline cudaError_t dev_alloc(bpgpu_ctx* ctx, void** p, size_t bytes) { return cudaMallocAsync(p, bytes ? bytes : 16, ctx->stream); }
 inline void dev_free(bpgpu_ctx* ctx, void* p) { if (p) cudaFreeAsync(p, ctx->stream); }
 

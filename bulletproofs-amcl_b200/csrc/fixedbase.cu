@@ -197,7 +197,7 @@ int build_tables(bpgpu_ctx* ctx, const void* d_affine, size_t n, void** table_ou
     ctx->launches += 2;
     rc = launch_check(ctx, "build_tables");
   }
-  if (!rc && cudaStreamSynchronize(ctx->stream) != cudaSuccess) rc = BPGPU_E_CUDA;
+  if (!rc && stream_sync(ctx) != cudaSuccess) rc = BPGPU_E_CUDA;
   cudaFree(d_pow2);
   if (rc) { cudaFree(table); return rc; }
   *table_out = table;
@@ -321,12 +321,12 @@ int msm_tables_to_host(bpgpu_ctx* ctx, const TableSeg* segs, int nsegs, int ngro
   if (hp) {
     BP_CUDA_OK(cudaMemcpyAsync(ctx->pinned, (const uint8_t*)ctx->tbl_part.p + TBL_MAX_GROUPS * psz, (size_t)ngroups * hp * psz,
                                cudaMemcpyDeviceToHost, ctx->stream));
-    BP_CUDA_OK(cudaStreamSynchronize(ctx->stream));
+    BP_CUDA_OK(stream_sync(ctx));
     if (bls) host_sum_partials<BlsFq>(ctx->pinned, ngroups, hp);
     else host_sum_partials<BnFq>(ctx->pinned, ngroups, hp);
   } else {
     BP_CUDA_OK(cudaMemcpyAsync(ctx->pinned, ctx->tbl_part.p, ngroups * psz, cudaMemcpyDeviceToHost, ctx->stream));
-    BP_CUDA_OK(cudaStreamSynchronize(ctx->stream));
+    BP_CUDA_OK(stream_sync(ctx));
   }
   uint8_t tmp[TBL_MAX_GROUPS * 2 * 48];
   if (bls) normalise_batch_host<BlsFq>(ctx->pinned, ngroups, mb, tmp);
@@ -354,7 +354,7 @@ static int fb_commit(bpgpu_fixed_bases* fb, const uint8_t* scalars_be, size_t co
   uint8_t* stage = ctx->pinned;
   if (bytes > ctx->pinned_cap / 2) { big.resize(bytes); stage = big.data(); }
   BP_CUDA_OK(cudaMemcpyAsync(stage, ctx->msm_e.p, bytes, cudaMemcpyDeviceToHost, ctx->stream));
-  BP_CUDA_OK(cudaStreamSynchronize(ctx->stream));
+  BP_CUDA_OK(stream_sync(ctx));
   normalise_batch_host<FqParams>(stage, count, Curve::MODBYTES, out_xy);
   return BPGPU_OK;
 }

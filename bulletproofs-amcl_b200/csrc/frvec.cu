@@ -108,7 +108,7 @@ int fr_dots_to_host(bpgpu_ctx* ctx, const DotPtrs& p, int np, size_t n, uint8_t*
   if (rc) return rc;
   if ((rc = fr_dots<Curve>(ctx, p, np, n, (Fr*)ctx->fr_out.p))) return rc;
   BP_CUDA_OK(cudaMemcpyAsync(ctx->pinned, ctx->fr_out.p, np * sizeof(Fr), cudaMemcpyDeviceToHost, ctx->stream));
-  BP_CUDA_OK(cudaStreamSynchronize(ctx->stream));
+  BP_CUDA_OK(stream_sync(ctx));
   using HF = host::HFp<typename std::conditional<Curve::ID == BPGPU_BLS12_381, BlsFr, BnFr>::type>;
   for (int k = 0; k < np; k++) reinterpret_cast<const HF*>(ctx->pinned)[k].to_be(out_be + (size_t)k * Curve::MODBYTES, Curve::MODBYTES);
   return BPGPU_OK;
@@ -126,7 +126,7 @@ int fr_args_upload(bpgpu_ctx* ctx, const uint8_t* be, int cnt, typename Curve::F
   if ((size_t)cnt * sizeof(Fr) > ctx->pinned_cap / 2) return BPGPU_E_ARG;
   // staging lives in the upper half of the pinned buffer; results use the lower half
   uint8_t* stage = ctx->pinned + ctx->pinned_cap / 2;
-  BP_CUDA_OK(cudaStreamSynchronize(ctx->stream));     // previous use of the staging area is complete
+  BP_CUDA_OK(stream_sync(ctx));     // previous use of the staging area is complete
   for (int k = 0; k < cnt; k++) reinterpret_cast<HF*>(stage)[k] = HF::from_be(be + (size_t)k * Curve::MODBYTES, Curve::MODBYTES);
   BP_CUDA_OK(cudaMemcpyAsync(ctx->fr_args.p, stage, (size_t)cnt * sizeof(Fr), cudaMemcpyHostToDevice, ctx->stream));
   *d_out = (Fr*)ctx->fr_args.p;
@@ -142,12 +142,12 @@ int fr_pow_table_upload(bpgpu_ctx* ctx, const uint8_t* x_be, Scratch& dst, typen
   using HF = host::HFp<typename std::conditional<Curve::ID == BPGPU_BLS12_381, BlsFr, BnFr>::type>;
   int rc = dst.reserve(32 * sizeof(Fr));
   if (rc) return rc;
-  BP_CUDA_OK(cudaStreamSynchronize(ctx->stream));
+  BP_CUDA_OK(stream_sync(ctx));
   HF* stage = reinterpret_cast<HF*>(ctx->pinned + ctx->pinned_cap / 2);
   HF cur = HF::from_be(x_be, Curve::MODBYTES);
   for (int k = 0; k < 32; k++) { stage[k] = cur; cur = cur.sqr(); }
   BP_CUDA_OK(cudaMemcpyAsync(dst.p, stage, 32 * sizeof(Fr), cudaMemcpyHostToDevice, ctx->stream));
-  BP_CUDA_OK(cudaStreamSynchronize(ctx->stream));
+  BP_CUDA_OK(stream_sync(ctx));
   *d_out = (Fr*)dst.p;
   return BPGPU_OK;
 }

@@ -27,6 +27,11 @@ struct bpgpu_ipp {
   void *a, *b;             // Fr[N]
   void *sG, *sH;           // Fr[N]
   void *sclL, *sclR;       // Fr[2N+1]
+  // bpgpu_ipp_fold only records the challenge: the fold runs at the head of the next round's kernel (or of finish), so a
+  // round is fold + scalar build + cross products in ONE launch, with u, u^-1 as kernel arguments (no H2D copy)
+  bool pending;            // a fold by (pu, pui) has been requested but not executed
+  size_t n_dev;            // vector length on the device (n_cur once the pending fold has run)
+  uint32_t pu[8], pui[8];  // canonical limbs of u, u^-1
 };
 
 namespace bp {
@@ -107,22 +112,86 @@ __global__ void __launch_bounds__(256) k_ipp_cross(uint32_t n_cur, const Fr* __r
 }
 
 // fold a, b by (u, u^-1) and multiply the coefficient vectors (ipp.rs:115-130,181-188); uv = {u, u_inv}
+struct FrArg { uint32_t v[8]; };             // a canonical scalar passed by value
 template <class Fr>
-__global__ void __launch_bounds__(128) k_ipp_fold(uint32_t N, uint32_t n_cur, const Fr* __restrict__ uv, Fr* __restrict__ a,
-                                                  Fr* __restrict__ b, Fr* __restrict__ sG, Fr* __restrict__ sH) {
-  uint32_t i = blockIdx.x * blockDim.x + threadIdx.x;
-  if (i >= N) return;
+__device__ __forceinline__ Fr arg_to_mont(const FrArg& x) {
+  Fr t;
+#pragma unroll
+  for (int k = 0; k < 8; k++) t.v[k] = x.v[k];
+  return t.to_mont();
+}
+
+template <class Fr>
+__device__ __forceinline__ void fold_element(uint32_t i, uint32_t n_cur, const Fr& u, const Fr& ui, Fr* __restrict__ a, Fr* __restrict__ b,
+                                             Fr* __restrict__ sG, Fr* __restrict__ sH, Fr* __restrict__ ab_out) {
   const uint32_t half = n_cur >> 1;
   const uint32_t p = i & (n_cur - 1);
-  const Fr u = uv[0], ui = uv[1];
   Fr g = load_vec(sG + i), h = load_vec(sH + i);
   if (p < half) { g = g * ui; h = h * u; } else { g = g * u; h = h * ui; }
   store_vec(sG + i, g);
   store_vec(sH + i, h);
   if (i < half) {
     Fr al = load_vec(a + i), ar = load_vec(a + i + half), bl = load_vec(b + i), br = load_vec(b + i + half);
-    store_vec(a + i, al * u + ui * ar);
-    store_vec(b + i, bl * ui + u * br);
+    const Fr na = al * u + ui * ar, nb = bl * ui + u * br;
+    store_vec(a + i, na);
+    store_vec(b + i, nb);
+    if (half == 1 && ab_out) { store_vec(ab_out, na); store_vec(ab_out + 1, nb); }   // the proof's a, b side by side
+  }
+}
+
+// fold a, b by (u, u^-1) and multiply the coefficient vectors (ipp.rs:115-130,181-188)
+template <class Fr>
+__global__ void __launch_bounds__(128) k_ipp_fold(uint32_t N, uint32_t n_cur, FrArg uc, FrArg uic, Fr* __restrict__ a, Fr* __restrict__ b,
+                                                  Fr* __restrict__ sG, Fr* __restrict__ sH, Fr* __restrict__ ab_out) {
+  uint32_t i = blockIdx.x * blockDim.x + threadIdx.x;
+  if (i >= N) return;
+  const Fr u = arg_to_mont<Fr>(uc), ui = arg_to_mont<Fr>(uic);
+  fold_element(i, n_cur, u, ui, a, b, sG, sH, ab_out);
+}
+
+// One launch per round for N <= 4096 in table mode: [pending fold] -> compacted L / R scalar lists -> cross products.
+// A single block, so __syncthreads orders the fold's writes before the build's reads.
+template <class Fr>
+__global__ void __launch_bounds__(512) k_ipp_round_fused(uint32_t N, uint32_t n_in, int do_fold, FrArg uc, FrArg uic, Fr* __restrict__ a,
+                                                         Fr* __restrict__ b, Fr* __restrict__ sG, Fr* __restrict__ sH,
+                                                         const Fr* __restrict__ wq, Fr* __restrict__ sclL, Fr* __restrict__ sclR,
+                                                         uint32_t* __restrict__ rows_lo, uint32_t* __restrict__ rows_hi) {
+  __shared__ __align__(16) unsigned char smraw[512 * sizeof(Fr)];
+  Fr* sm = reinterpret_cast<Fr*>(smraw);
+  uint32_t n_cur = n_in;
+  if (do_fold) {
+    const Fr u = arg_to_mont<Fr>(uc), ui = arg_to_mont<Fr>(uic);
+    for (uint32_t i = threadIdx.x; i < N; i += blockDim.x) fold_element(i, n_cur, u, ui, a, b, sG, sH, (Fr*)nullptr);
+    n_cur >>= 1;
+    __syncthreads();
+  }
+  const uint32_t Nh = N >> 1, half = n_cur >> 1;
+  for (uint32_t t = threadIdx.x; t < Nh; t += blockDim.x) {             // k_ipp_build_compact
+    const uint32_t q = t / half, r = t - q * half;
+    const uint32_t ilo = q * n_cur + r, ihi = ilo + half;
+    rows_lo[t] = ilo;
+    rows_hi[t] = ihi;
+    const Fr aL = load_vec(a + r), aR = load_vec(a + r + half), bL = load_vec(b + r), bR = load_vec(b + r + half);
+    store_vec(sclL + t, aL * load_vec(sG + ihi));
+    store_vec(sclL + Nh + t, bR * load_vec(sH + ilo));
+    store_vec(sclR + t, aR * load_vec(sG + ilo));
+    store_vec(sclR + Nh + t, bL * load_vec(sH + ihi));
+  }
+  Fr cl = Fr::zero(), cr = Fr::zero();                                  // k_ipp_cross
+  for (uint32_t j = threadIdx.x; j < half; j += blockDim.x) {
+    Fr al = load_vec(a + j), ar = load_vec(a + j + half), bl = load_vec(b + j), br = load_vec(b + j + half);
+    cl = cl + al * br;
+    cr = cr + ar * bl;
+  }
+  for (int pass = 0; pass < 2; pass++) {
+    store_vec(sm + threadIdx.x, pass == 0 ? cl : cr);
+    __syncthreads();
+    for (int o = blockDim.x / 2; o > 0; o >>= 1) {
+      if ((int)threadIdx.x < o) store_vec(sm + threadIdx.x, load_vec(sm + threadIdx.x) + load_vec(sm + threadIdx.x + o));
+      __syncthreads();
+    }
+    if (threadIdx.x == 0) { Fr c = load_vec(sm) * wq[0]; store_vec((pass == 0 ? sclL : sclR) + N, c); }
+    __syncthreads();
   }
 }
 
@@ -211,6 +280,33 @@ static int ipp_round_t(bpgpu_ipp* st, uint8_t* L_xy, uint8_t* R_xy) {
   bpgpu_ctx* ctx = st->ctx;
   const uint32_t N = (uint32_t)st->N, n = (uint32_t)st->n_cur;
   int rc;
+  FrArg uc, uic;
+  memcpy(uc.v, st->pu, sizeof uc.v);
+  memcpy(uic.v, st->pui, sizeof uic.v);
+  if (st->wq && N <= 4096) {
+    // small table mode: [fold] + scalar lists + cross products in one launch, both sums in one more (two groups)
+    const uint32_t Nh = N >> 1;
+    uint32_t* rows_lo = (uint32_t*)st->rows;
+    uint32_t* rows_hi = rows_lo + Nh;
+    Fr *sl = (Fr*)st->sclL, *sr = (Fr*)st->sclR;
+    k_ipp_round_fused<Fr><<<1, 512, 0, ctx->stream>>>(N, (uint32_t)st->n_dev, st->pending ? 1 : 0, uc, uic, (Fr*)st->a, (Fr*)st->b, (Fr*)st->sG,
+                                                      (Fr*)st->sH, (const Fr*)st->wq, sl, sr, rows_lo, rows_hi);
+    ctx->launches += 1;
+    st->pending = false;
+    st->n_dev = n;
+    if ((rc = launch_check(ctx, "ipp_round"))) return rc;
+    TableSeg segs[6] = {{st->tG, sl, Nh, 1, 0, rows_hi}, {st->tH, sl + Nh, Nh, 1, 0, rows_lo}, {st->tQ, sl + N, 1, 1, 0, nullptr},
+                        {st->tG, sr, Nh, 1, 1, rows_lo}, {st->tH, sr + Nh, Nh, 1, 1, rows_hi}, {st->tQ, sr + N, 1, 1, 1, nullptr}};
+    uint8_t* outs[2] = {L_xy, R_xy};
+    return msm_tables_to_host(ctx, segs, 6, 2, outs);
+  }
+  if (st->pending) {
+    k_ipp_fold<Fr><<<(N + 127) / 128, 128, 0, ctx->stream>>>(N, (uint32_t)st->n_dev, uc, uic, (Fr*)st->a, (Fr*)st->b, (Fr*)st->sG, (Fr*)st->sH,
+                                                             (Fr*)nullptr);
+    ctx->launches++;
+    st->pending = false;
+    st->n_dev = n;
+  }
   if (st->wq) {
     // table mode: both sums in ONE launch (two groups) over the compacted term lists, one D2H, one shared inversion
     const uint32_t Nh = N >> 1;
@@ -238,21 +334,49 @@ static int ipp_round_t(bpgpu_ipp* st, uint8_t* L_xy, uint8_t* R_xy) {
   return msm_pair_to_host(ctx, st->P, st->sclL, st->sclR, true, 2 * (size_t)N + 1, L_xy, R_xy);
 }
 
+// records the challenge; the fold itself runs at the head of the next round's launch (ipp_round_t) or of finish
 template <class Curve>
 static int ipp_fold_t(bpgpu_ipp* st, const uint8_t* u_be, const uint8_t* ui_be) {
+  const int mb = Curve::MODBYTES;
+  for (int k = 0; k < 8; k++) {
+    const uint8_t *p = u_be + mb - 4 * (k + 1), *q = ui_be + mb - 4 * (k + 1);
+    st->pu[k] = ((uint32_t)p[0] << 24) | ((uint32_t)p[1] << 16) | ((uint32_t)p[2] << 8) | p[3];
+    st->pui[k] = ((uint32_t)q[0] << 24) | ((uint32_t)q[1] << 16) | ((uint32_t)q[2] << 8) | q[3];
+  }
+  st->pending = true;
+  st->n_cur >>= 1;
+  return BPGPU_OK;
+}
+
+template <class Curve>
+static int ipp_finish_t(bpgpu_ipp* st, uint8_t* a_be, uint8_t* b_be) {
   using Fr = typename Curve::Fr;
   bpgpu_ctx* ctx = st->ctx;
-  uint8_t both[2 * 48];
-  memcpy(both, u_be, Curve::MODBYTES);
-  memcpy(both + Curve::MODBYTES, ui_be, Curve::MODBYTES);
-  Fr* uv;
-  int rc = fr_args_upload<Curve>(ctx, both, 2, &uv);
-  if (rc) return rc;
   const uint32_t N = (uint32_t)st->N;
-  k_ipp_fold<Fr><<<(N + 127) / 128, 128, 0, ctx->stream>>>(N, (uint32_t)st->n_cur, uv, (Fr*)st->a, (Fr*)st->b, (Fr*)st->sG, (Fr*)st->sH);
-  ctx->launches++;
-  st->n_cur >>= 1;
-  return launch_check(ctx, "k_ipp_fold");
+  Fr* ab = (Fr*)st->sclL;                              // a, b side by side for ONE download
+  if (st->pending) {
+    FrArg uc, uic;
+    memcpy(uc.v, st->pu, sizeof uc.v);
+    memcpy(uic.v, st->pui, sizeof uic.v);
+    k_ipp_fold<Fr><<<(N + 127) / 128, 128, 0, ctx->stream>>>(N, (uint32_t)st->n_dev, uc, uic, (Fr*)st->a, (Fr*)st->b, (Fr*)st->sG, (Fr*)st->sH,
+                                                             st->n_dev == 2 ? ab : (Fr*)nullptr);
+    ctx->launches++;
+    st->pending = false;
+    st->n_dev = st->n_cur;
+    int rc = launch_check(ctx, "k_ipp_fold");
+    if (rc) return rc;
+  }
+  if (N == 1) {                                        // no round ever ran: a, b are the inputs
+    BP_CUDA_OK(cudaMemcpyAsync(ab, st->a, sizeof(Fr), cudaMemcpyDeviceToDevice, ctx->stream));
+    BP_CUDA_OK(cudaMemcpyAsync(ab + 1, st->b, sizeof(Fr), cudaMemcpyDeviceToDevice, ctx->stream));
+  }
+  uint8_t both[2 * 48];
+  bpgpu_scalars v{ctx, ab, 2};
+  int rc = bpgpu_scalars_download(ctx, &v, 0, 2, both);
+  if (rc) return rc;
+  memcpy(a_be, both, Curve::MODBYTES);
+  memcpy(b_be, both + Curve::MODBYTES, Curve::MODBYTES);
+  return BPGPU_OK;
 }
 
 // u[0..lg) | u_inv[0..lg) as device Montgomery values in ctx->fr_args
@@ -345,7 +469,7 @@ static int ipp_begin_common(bpgpu_ctx* ctx, const bpgpu_points* G, size_t goff, 
   bpgpu_ipp* st = new (std::nothrow) bpgpu_ipp();
   if (!st) return BPGPU_E_CUDA;
   memset(st, 0, sizeof *st);
-  st->ctx = ctx; st->N = n; st->n_cur = n;
+  st->ctx = ctx; st->N = n; st->n_cur = n; st->n_dev = n; st->pending = false;
   int rc = ctx->curve == BPGPU_BLS12_381 ? ipp_begin_t<Bls>(st, G, goff, H, hoff, Q_xy, q_base_xy, q_scalar_be, Gf->d, Hf->d, a->d, b->d)
                                         : ipp_begin_t<Bn>(st, G, goff, H, hoff, Q_xy, q_base_xy, q_scalar_be, Gf->d, Hf->d, a->d, b->d);
   if (rc) { bpgpu_ipp_free(st); return rc; }
@@ -386,10 +510,8 @@ int bpgpu_ipp_fold(bpgpu_ipp* st, const uint8_t* u_be, const uint8_t* u_inv_be) 
 int bpgpu_ipp_finish(bpgpu_ipp* st, uint8_t* a_be, uint8_t* b_be) {
   if (!st || !a_be || !b_be) return BPGPU_E_ARG;
   if (st->n_cur != 1) return BPGPU_E_ARG;
-  bpgpu_scalars va{st->ctx, st->a, 1}, vb{st->ctx, st->b, 1};
-  int rc = bpgpu_scalars_download(st->ctx, &va, 0, 1, a_be);
-  if (rc) return rc;
-  return bpgpu_scalars_download(st->ctx, &vb, 0, 1, b_be);
+  BP_CUDA_OK(cudaSetDevice(st->ctx->device));
+  return st->ctx->curve == BPGPU_BLS12_381 ? ipp_finish_t<Bls>(st, a_be, b_be) : ipp_finish_t<Bn>(st, a_be, b_be);
 }
 
 void bpgpu_ipp_free(bpgpu_ipp* st) {

@@ -87,7 +87,7 @@ extern "C" int bpgpu_points_from_hashes(bpgpu_ctx* ctx, const uint8_t* hashes, s
   size_t psz = (ctx->curve == BPGPU_BLS12_381) ? sizeof(Affine<Bls::Fq>) : sizeof(Affine<Bn::Fq>);
   if (dev_alloc(ctx, &p->d, n * psz) != cudaSuccess) { delete p; return BPGPU_E_CUDA; }
   int rc = ctx->curve == BPGPU_BLS12_381 ? mapit_t<Bls>(ctx, hashes, n, p->d) : mapit_t<Bn>(ctx, hashes, n, p->d);
-  if (rc == BPGPU_OK && cudaStreamSynchronize(ctx->stream) != cudaSuccess) rc = BPGPU_E_CUDA;
+  if (rc == BPGPU_OK && stream_sync(ctx) != cudaSuccess) rc = BPGPU_E_CUDA;
   if (rc) { dev_free(ctx, p->d); delete p; return rc; }
   *out = p;
   return BPGPU_OK;

@@ -86,12 +86,12 @@ static int ypow_tables(bpgpu_ctx* ctx, const uint8_t* y_be, typename Curve::Fr**
   using HF = host::HFp<typename std::conditional<Curve::ID == BPGPU_BLS12_381, BlsFr, BnFr>::type>;
   int rc = ctx->fr_pow2.reserve(64 * sizeof(Fr));
   if (rc) return rc;
-  BP_CUDA_OK(cudaStreamSynchronize(ctx->stream));
+  BP_CUDA_OK(stream_sync(ctx));
   HF* stage = reinterpret_cast<HF*>(ctx->pinned + ctx->pinned_cap / 2);
   HF cur = HF::from_be(y_be, Curve::MODBYTES), cinv = cur.inv();
   for (int k = 0; k < 32; k++) { stage[k] = cur; stage[32 + k] = cinv; cur = cur.sqr(); cinv = cinv.sqr(); }
   BP_CUDA_OK(cudaMemcpyAsync(ctx->fr_pow2.p, stage, 64 * sizeof(Fr), cudaMemcpyHostToDevice, ctx->stream));
-  BP_CUDA_OK(cudaStreamSynchronize(ctx->stream));
+  BP_CUDA_OK(stream_sync(ctx));
   *tab = (Fr*)ctx->fr_pow2.p;
   return BPGPU_OK;
 }
