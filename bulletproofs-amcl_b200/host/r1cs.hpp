@@ -26,6 +26,16 @@ struct Variable {
   bool operator==(const Variable& o) const { return kind == o.kind && (kind == One || index == o.index); }
 };
 
+// z^(q+1) * coeff for the flattening loops (prover.rs:142-184, verifier.rs:149-193): nine coefficients in ten of the range
+// gadgets are +1 or -1, where the product is a copy or a negation
+template <class C>
+inline FieldElement<C> scaled_coeff(const FieldElement<C>& exp_z, const FieldElement<C>& coeff) {
+  static const FieldElement<C> one = FieldElement<C>::one(), minus_one = FieldElement<C>::minus_one();
+  if (coeff == one) return exp_z;
+  if (coeff == minus_one) return exp_z.negation();
+  return exp_z * coeff;
+}
+
 template <class C>
 struct LinearCombination {
   using FE = FieldElement<C>;
@@ -414,10 +424,10 @@ class Prover : public ConstraintSystem<C> {
     for (const LC& lc : constraints_) {
       for (const auto& t : lc.terms) {
         switch (t.first.kind) {
-          case Variable::MultiplierLeft: (*wL)[t.first.index] = (*wL)[t.first.index] + exp_z * t.second; break;
-          case Variable::MultiplierRight: (*wR)[t.first.index] = (*wR)[t.first.index] + exp_z * t.second; break;
-          case Variable::MultiplierOutput: (*wO)[t.first.index] = (*wO)[t.first.index] + exp_z * t.second; break;
-          case Variable::Committed: (*wV)[t.first.index] = (*wV)[t.first.index] - exp_z * t.second; break;
+          case Variable::MultiplierLeft: (*wL)[t.first.index] = (*wL)[t.first.index] + scaled_coeff<C>(exp_z, t.second); break;
+          case Variable::MultiplierRight: (*wR)[t.first.index] = (*wR)[t.first.index] + scaled_coeff<C>(exp_z, t.second); break;
+          case Variable::MultiplierOutput: (*wO)[t.first.index] = (*wO)[t.first.index] + scaled_coeff<C>(exp_z, t.second); break;
+          case Variable::Committed: (*wV)[t.first.index] = (*wV)[t.first.index] - scaled_coeff<C>(exp_z, t.second); break;
           default: break;                                               // the prover ignores constant terms
         }
       }
@@ -572,11 +582,11 @@ class Verifier : public ConstraintSystem<C> {
     for (const LC& lc : constraints_) {
       for (const auto& t : lc.terms) {
         switch (t.first.kind) {
-          case Variable::MultiplierLeft: (*wL)[t.first.index] = (*wL)[t.first.index] + exp_z * t.second; break;
-          case Variable::MultiplierRight: (*wR)[t.first.index] = (*wR)[t.first.index] + exp_z * t.second; break;
-          case Variable::MultiplierOutput: (*wO)[t.first.index] = (*wO)[t.first.index] + exp_z * t.second; break;
-          case Variable::Committed: (*wV)[t.first.index] = (*wV)[t.first.index] - exp_z * t.second; break;
-          default: *wc = *wc - exp_z * t.second; break;
+          case Variable::MultiplierLeft: (*wL)[t.first.index] = (*wL)[t.first.index] + scaled_coeff<C>(exp_z, t.second); break;
+          case Variable::MultiplierRight: (*wR)[t.first.index] = (*wR)[t.first.index] + scaled_coeff<C>(exp_z, t.second); break;
+          case Variable::MultiplierOutput: (*wO)[t.first.index] = (*wO)[t.first.index] + scaled_coeff<C>(exp_z, t.second); break;
+          case Variable::Committed: (*wV)[t.first.index] = (*wV)[t.first.index] - scaled_coeff<C>(exp_z, t.second); break;
+          default: *wc = *wc - scaled_coeff<C>(exp_z, t.second); break;
         }
       }
       exp_z = exp_z * z;
