@@ -7,7 +7,7 @@
 // range proofs".  The reference has no batch API; every proof keeps its own verdict (no random-linear-combination
 // merging).  F_i are the proof system's generators G[..N], H[..N], g, h (window tables: no doublings); V[b][j] are the
 // proof's own points A_I1.., V_k, T_i, L_k, R_k, which need real scalar multiplications:
-//   k_batch_fixed : one block per proof, sum of 64 table entries per fixed term, block tree
+//   k_batch_fixed : one block per proof, sum of 32 table entries per fixed term, block tree
 //   k_batch_multiples / k_batch_windows / k_batch_horner : Straus with 4-bit windows for the proof's own points, laid
 //                   out so that each stage has one independent item per lane (see below)
 // Nothing returns to the host but `batch` verdict bytes.
@@ -41,10 +41,10 @@ __global__ void __launch_bounds__(256) k_batch_fixed(FixedRuns runs, uint32_t F,
     const uint32_t row = p - runs.start[rg];
     const uint32_t limb = sc[p].v[j];                       // canonical scalars (not Montgomery)
     if (!limb) continue;
-    const Affine<Fq>* tb = (const Affine<Fq>*)runs.table[rg] + ((size_t)row * TBL_WINDOWS + 8 * j) * TBL_DIGITS;
+    const Affine<Fq>* tb = (const Affine<Fq>*)runs.table[rg] + ((size_t)row * TBL_WINDOWS + TBL_PER_LIMB * j) * TBL_DIGITS;
 #pragma unroll 1
-    for (int k = 0; k < 8; k++) {
-      const uint32_t d = (limb >> (4 * k)) & 15u;
+    for (int k = 0; k < TBL_PER_LIMB; k++) {
+      const uint32_t d = (limb >> (TBL_BITS * k)) & (uint32_t)TBL_DIGITS;
       if (d) acc.madd(load_vec_ro(tb + k * TBL_DIGITS + (d - 1)));
     }
   }
@@ -61,6 +61,10 @@ __global__ void __launch_bounds__(256) k_batch_fixed(FixedRuns runs, uint32_t F,
   if (threadIdx.x == 0) store_vec(out + b, load_vec(sm));
 }
 
+// the proof's own points: Straus with 4-bit windows (15 multiples per point, 64 windows), independent of the table geometry
+static const int VAR_WINDOWS = 64;
+static const int VAR_DIGITS = 15;
+
 // Variable part, three launches so that every stage has one independent item per LANE:
 //   k_batch_multiples : thread per (proof, point): the 15 small multiples of the point (14 mixed additions)
 //   k_batch_windows   : thread per (proof, 4-bit window): sum over the points of the multiple its digit selects
@@ -75,11 +79,11 @@ __global__ void __launch_bounds__(64) k_batch_multiples(size_t total, const Affi
   if (t >= total) return;
   const Affine<Fq> a = load_vec(pts + t);
   XYZZ<Fq> acc = XYZZ<Fq>::from_affine(a);
-  XYZZ<Fq>* M = mult + t * TBL_DIGITS;
+  XYZZ<Fq>* M = mult + t * VAR_DIGITS;
 #pragma unroll 1
-  for (int d = 0; d < TBL_DIGITS; d++) {
+  for (int d = 0; d < VAR_DIGITS; d++) {
     store_vec(M + d, acc);
-    if (d + 1 < TBL_DIGITS) acc.madd(a);
+    if (d + 1 < VAR_DIGITS) acc.madd(a);
   }
 }
 
@@ -91,16 +95,16 @@ __global__ void __launch_bounds__(128) k_batch_windows(size_t batch, uint32_t vn
   using Fq = typename Curve::Fq;
   using Fr = typename Curve::Fr;
   const size_t t = (size_t)blockIdx.x * blockDim.x + threadIdx.x;
-  if (t >= batch * TBL_WINDOWS) return;
-  const size_t b = t / TBL_WINDOWS;
-  const uint32_t w = (uint32_t)(t - b * TBL_WINDOWS);
+  if (t >= batch * VAR_WINDOWS) return;
+  const size_t b = t / VAR_WINDOWS;
+  const uint32_t w = (uint32_t)(t - b * VAR_WINDOWS);
   const Fr* sc = scal + b * vn;
-  const XYZZ<Fq>* M = mult + b * (size_t)vn * TBL_DIGITS;
+  const XYZZ<Fq>* M = mult + b * (size_t)vn * VAR_DIGITS;
   XYZZ<Fq> acc = XYZZ<Fq>::inf();
 #pragma unroll 1
   for (uint32_t i = 0; i < vn; i++) {
     const uint32_t d = (sc[i].v[w >> 3] >> ((w & 7) * 4)) & 15u;
-    if (d) { XYZZ<Fq> q = load_vec(M + (size_t)i * TBL_DIGITS + (d - 1)); acc.add(q); }
+    if (d) { XYZZ<Fq> q = load_vec(M + (size_t)i * VAR_DIGITS + (d - 1)); acc.add(q); }
   }
   store_vec(wsum + (size_t)w * batch + b, acc);
 }
@@ -114,9 +118,9 @@ __global__ void __launch_bounds__(32) k_batch_horner(size_t batch, uint32_t vn, 
   if (b >= batch) return;
   XYZZ<Fq> acc = XYZZ<Fq>::inf();
   if (vn) {
-    acc = load_vec(wsum + (size_t)(TBL_WINDOWS - 1) * batch + b);
+    acc = load_vec(wsum + (size_t)(VAR_WINDOWS - 1) * batch + b);
 #pragma unroll 1
-    for (int w = TBL_WINDOWS - 2; w >= 0; w--) {
+    for (int w = VAR_WINDOWS - 2; w >= 0; w--) {
       acc.dbl(); acc.dbl(); acc.dbl(); acc.dbl();
       XYZZ<Fq> q = load_vec(wsum + (size_t)w * batch + b);
       acc.add(q);
@@ -138,8 +142,8 @@ static int batch_identity_t(bpgpu_ctx* ctx, const FixedRuns& runs, uint32_t F, s
   // scratch: fixed scalars | var scalars | var points | fixed sums | verdicts | multiples
   const size_t sz_fs = (slab * F * sizeof(Fr) + 255) & ~(size_t)255, sz_vs = (slab * vn * sizeof(Fr) + 255) & ~(size_t)255;
   const size_t sz_vp = (slab * vn * sizeof(Affine<Fq>) + 255) & ~(size_t)255, sz_sum = (slab * sizeof(XYZZ<Fq>) + 255) & ~(size_t)255;
-  const size_t sz_v = (slab + 255) & ~(size_t)255, sz_m = (slab * (size_t)vn * TBL_DIGITS * sizeof(XYZZ<Fq>) + 255) & ~(size_t)255;
-  const size_t sz_w = vn ? slab * (size_t)TBL_WINDOWS * sizeof(XYZZ<Fq>) : 0;
+  const size_t sz_v = (slab + 255) & ~(size_t)255, sz_m = (slab * (size_t)vn * VAR_DIGITS * sizeof(XYZZ<Fq>) + 255) & ~(size_t)255;
+  const size_t sz_w = vn ? slab * (size_t)VAR_WINDOWS * sizeof(XYZZ<Fq>) : 0;
   if ((rc = ctx->msm_b.reserve(sz_fs + sz_vs + sz_vp + sz_sum + sz_v + sz_m + sz_w + 256))) return rc;
   uint8_t* base = (uint8_t*)ctx->msm_b.p;
   Fr* d_fs = (Fr*)base; base += sz_fs;
@@ -164,7 +168,7 @@ static int batch_identity_t(bpgpu_ctx* ctx, const FixedRuns& runs, uint32_t F, s
     k_batch_fixed<Curve><<<(unsigned)cnt, 256, 0, ctx->stream>>>(runs, F, d_fs, d_sum);
     if (prof) cudaEventRecord(ev[1], ctx->stream);
     if (vn) {
-      const size_t np = cnt * vn, nw = cnt * TBL_WINDOWS;
+      const size_t np = cnt * vn, nw = cnt * VAR_WINDOWS;
       k_batch_multiples<Curve><<<(unsigned)((np + 63) / 64), 64, 0, ctx->stream>>>(np, d_vp, d_m);
       k_batch_windows<Curve><<<(unsigned)((nw + 127) / 128), 128, 0, ctx->stream>>>(cnt, vn, d_vs, d_m, d_w);
       ctx->launches += 2;

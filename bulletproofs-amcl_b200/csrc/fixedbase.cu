@@ -5,8 +5,8 @@
 // (/root/reference/src/r1cs/prover.rs:123 V_i, :496-500 T_1..T_6, :550 Q; gadgets/poseidon_hash.rs:49-62), which AMCL
 // computes with a 255-step double-and-add each.  A doubling chain is the one thing a GPU thread is bad at (measured:
 // 9 us per dependent XYZZ doubling, tools/latency_probe.py), so for fixed bases the doublings are done ONCE:
-// the table T[j][w][d-1] = d * 2^(4w) * B_j (w < 64, d = 1..15, affine) turns every later commitment into a sum of
-// <= 64k table entries, reduced by a block-wide tree: no doublings, one launch for a whole batch.
+// the table T[j][w][d-1] = d * 2^(8w) * B_j (w < 32, d = 1..255, affine) turns every later commitment into a sum of
+// <= 32k table entries, reduced by a block-wide tree: no doublings, one launch for a whole batch.
 #include <string.h>
 
 #include "common.cuh"
@@ -14,15 +14,17 @@
 
 namespace bp {
 
-static const int FB_WINDOWS = TBL_WINDOWS;      // 4-bit unsigned windows cover 256 bits
+static const int FB_WINDOWS = TBL_WINDOWS;      // 8-bit unsigned windows cover 256 bits
 static const int FB_DIGITS = TBL_DIGITS;
+static const int FB_GROUP = 15;                 // multiples normalised together by one thread (one shared inversion)
+static const int FB_GROUPS = TBL_DIGITS / FB_GROUP;   // 17
 
 }  // namespace bp
 
 struct bpgpu_fixed_bases {
   bpgpu_ctx* ctx;
   size_t k;
-  void* table;                   // Affine[k][64][15]
+  void* table;                   // Affine[k][32][255]
   std::vector<uint8_t> key;      // the k bases as X||Y bytes (cache key)
 };
 
@@ -43,7 +45,7 @@ __device__ __forceinline__ XYZZ<Fq> block_tree_sum_256(const XYZZ<Fq>& v, XYZZ<F
   return load_vec(sm);
 }
 
-// pow2[j][w] = 2^(4w) * B_j : one thread per base, a serial chain of 252 doublings (one-off)
+// pow2[j][w] = 2^(8w) * B_j : one thread per base, a serial chain of 248 doublings (one-off)
 template <class Fq>
 __global__ void k_fb_pow2(const Affine<Fq>* __restrict__ bases, size_t k, XYZZ<Fq>* __restrict__ pow2) {
   size_t j = (size_t)blockIdx.x * blockDim.x + threadIdx.x;
@@ -51,37 +53,39 @@ __global__ void k_fb_pow2(const Affine<Fq>* __restrict__ bases, size_t k, XYZZ<F
   XYZZ<Fq> p = XYZZ<Fq>::from_affine(load_vec(bases + j));
   for (int w = 0; w < FB_WINDOWS; w++) {
     store_vec(pow2 + (size_t)j * FB_WINDOWS + w, p);
-    if (w + 1 < FB_WINDOWS) for (int b = 0; b < 4; b++) p.dbl();
+    if (w + 1 < FB_WINDOWS) for (int b = 0; b < TBL_BITS; b++) p.dbl();
   }
 }
 
-// table[j][w][d-1] = d * pow2[j][w], normalised to affine: one thread per (j, w); the 15 multiples share ONE field
-// inversion (Montgomery's trick on the ZZZ coordinates)
+// table[j][w][d-1] = d * pow2[j][w], normalised to affine: one thread per (j, w, group of 15 consecutive multiples); the
+// 15 multiples of a thread share ONE field inversion (Montgomery's trick on the ZZZ coordinates)
 template <class Fq>
 __global__ void __launch_bounds__(64) k_fb_multiples(const XYZZ<Fq>* __restrict__ pow2, size_t total, Affine<Fq>* __restrict__ table) {
-  size_t t = (size_t)blockIdx.x * blockDim.x + threadIdx.x;
-  if (t >= total) return;
-  const XYZZ<Fq> base = load_vec(pow2 + t);
-  Affine<Fq>* out = table + t * FB_DIGITS;
+  size_t t = (size_t)blockIdx.x * blockDim.x + threadIdx.x;             // (j * W + w) * FB_GROUPS + g
+  if (t >= total * FB_GROUPS) return;
+  const size_t jw = t / FB_GROUPS;
+  const uint32_t g = (uint32_t)(t - jw * FB_GROUPS);
+  const XYZZ<Fq> base = load_vec(pow2 + jw);
+  Affine<Fq>* out = table + jw * FB_DIGITS + (size_t)g * FB_GROUP;      // multiples 15g+1 .. 15g+15
   if (base.is_inf()) {
-    for (int d = 0; d < FB_DIGITS; d++) store_vec(out + d, Affine<Fq>::inf());
+    for (int d = 0; d < FB_GROUP; d++) store_vec(out + d, Affine<Fq>::inf());
     return;
   }
-  XYZZ<Fq> m[FB_DIGITS];
-  Fq pre[FB_DIGITS];                       // pre[d] = product of zzz_0 .. zzz_d over the finite multiples
-  XYZZ<Fq> acc = base;
+  XYZZ<Fq> m[FB_GROUP];
+  Fq pre[FB_GROUP];                        // pre[d] = product of zzz_0 .. zzz_d over the finite multiples
+  XYZZ<Fq> acc = g ? mul_small(base, g * FB_GROUP + 1) : base;
   Fq run = Fq::one();
 #pragma unroll 1
-  for (int d = 0; d < FB_DIGITS; d++) {
+  for (int d = 0; d < FB_GROUP; d++) {
     m[d] = acc;
     if (!acc.is_inf()) run = run * acc.zzz;
     pre[d] = run;
-    if (d + 1 < FB_DIGITS) acc.add(base);
+    if (d + 1 < FB_GROUP) acc.add(base);
   }
   Fq inv = run.inv();
 #pragma unroll 1
-  for (int d = FB_DIGITS - 1; d >= 0; d--) {
-    if (m[d].is_inf()) { store_vec(out + d, Affine<Fq>::inf()); continue; }      // only for points of order < 16: never on these curves
+  for (int d = FB_GROUP - 1; d >= 0; d--) {
+    if (m[d].is_inf()) { store_vec(out + d, Affine<Fq>::inf()); continue; }      // only for points of small order: never on these curves
     Fq i3 = d ? inv * pre[d - 1] : inv;     // 1 / zzz_d
     inv = inv * m[d].zzz;
     Fq i1 = i3 * m[d].zz;                   // 1 / z
@@ -92,7 +96,8 @@ __global__ void __launch_bounds__(64) k_fb_multiples(const XYZZ<Fq>* __restrict_
   }
 }
 
-// 8 threads per term: thread (p, j) adds the table entries of windows 8j .. 8j+7 of term p; block tree; one XYZZ per block.
+// 8 threads per term: thread (p, j) adds the table entries of the 4 byte-windows of scalar limb j of term p; block tree;
+// one XYZZ per block.
 // blockIdx.y selects the group (independent sum) the block works for.
 struct TableSegs {
   const void* table[TBL_MAX_SEGS]; const void* scal[TBL_MAX_SEGS]; const uint32_t* rows[TBL_MAX_SEGS];
@@ -121,10 +126,10 @@ __global__ void __launch_bounds__(256) k_table_sum(TableSegs segs, XYZZ<typename
     const uint32_t limb = sc.v[j];
     if (limb) {
       const uint32_t row = segs.rows[sg] ? segs.rows[sg][idx] : idx;
-      const Affine<Fq>* tb = (const Affine<Fq>*)segs.table[sg] + ((size_t)row * TBL_WINDOWS + 8 * j) * TBL_DIGITS;
+      const Affine<Fq>* tb = (const Affine<Fq>*)segs.table[sg] + ((size_t)row * TBL_WINDOWS + TBL_PER_LIMB * j) * TBL_DIGITS;
 #pragma unroll 1
-      for (int k = 0; k < 8; k++) {
-        const uint32_t d = (limb >> (4 * k)) & 15u;
+      for (int k = 0; k < TBL_PER_LIMB; k++) {
+        const uint32_t d = (limb >> (TBL_BITS * k)) & (uint32_t)TBL_DIGITS;
         if (d) acc.madd(load_vec_ro(tb + k * TBL_DIGITS + (d - 1)));
       }
     }
@@ -145,23 +150,23 @@ __global__ void __launch_bounds__(256) k_table_sum_final(const XYZZ<Fq>* __restr
   if (threadIdx.x == 0) store_vec(out + blockIdx.x, tot);
 }
 
-// one block of 64 threads per commitment: thread w sums the k table entries of window w, then a block tree
+// one block of FB_WINDOWS (32) threads per commitment: thread w sums the k table entries of window w, then a block tree
 template <class Fq>
-__global__ void __launch_bounds__(64) k_fb_commit(const Affine<Fq>* __restrict__ table, int k, const ScalarInt* __restrict__ scalars,
-                                                  XYZZ<Fq>* __restrict__ out) {
-  __shared__ __align__(16) unsigned char smraw[64 * sizeof(XYZZ<Fq>)];
+__global__ void __launch_bounds__(FB_WINDOWS) k_fb_commit(const Affine<Fq>* __restrict__ table, int k, const ScalarInt* __restrict__ scalars,
+                                                          XYZZ<Fq>* __restrict__ out) {
+  __shared__ __align__(16) unsigned char smraw[FB_WINDOWS * sizeof(XYZZ<Fq>)];
   XYZZ<Fq>* sm = reinterpret_cast<XYZZ<Fq>*>(smraw);
   const int w = threadIdx.x;
   const size_t inst = blockIdx.x;
   XYZZ<Fq> acc = XYZZ<Fq>::inf();
   for (int j = 0; j < k; j++) {
-    const uint32_t limb = scalars[inst * k + j].v[w >> 3];
-    const uint32_t d = (limb >> ((w & 7) * 4)) & 15u;
+    const uint32_t limb = scalars[inst * k + j].v[w / TBL_PER_LIMB];
+    const uint32_t d = (limb >> ((w % TBL_PER_LIMB) * TBL_BITS)) & (uint32_t)TBL_DIGITS;
     if (d) acc.madd(load_vec_ro(table + ((size_t)j * FB_WINDOWS + w) * FB_DIGITS + (d - 1)));
   }
   store_vec(sm + w, acc);
   __syncthreads();
-  for (int o = 32; o > 0; o >>= 1) {
+  for (int o = FB_WINDOWS / 2; o > 0; o >>= 1) {
     if (w < o) {
       XYZZ<Fq> a = load_vec(sm + w), b = load_vec(sm + w + o);
       a.add(b);
@@ -172,8 +177,8 @@ __global__ void __launch_bounds__(64) k_fb_commit(const Affine<Fq>* __restrict__
   if (w == 0) store_vec(out + inst, load_vec(sm));
 }
 
-// Builds the window tables of n affine points already on the device.  One-off: a 252-doubling chain per point (all
-// points in parallel), 14 additions and one inversion per (point, window).
+// Builds the window tables of n affine points already on the device.  One-off: a 248-doubling chain per point (all
+// points in parallel), then 17 threads per (point, window) with 14 additions and one inversion each.
 template <class Curve>
 int build_tables(bpgpu_ctx* ctx, const void* d_affine, size_t n, void** table_out) {
   using Fq = typename Curve::Fq;
@@ -192,7 +197,7 @@ int build_tables(bpgpu_ctx* ctx, const void* d_affine, size_t n, void** table_ou
     const size_t cnt = n - lo < slab ? n - lo : slab;
     k_fb_pow2<Fq><<<(unsigned)((cnt + 63) / 64), 64, 0, ctx->stream>>>((const Affine<Fq>*)d_affine + lo, cnt, (XYZZ<Fq>*)d_pow2);
     const size_t total = cnt * FB_WINDOWS;
-    k_fb_multiples<Fq><<<(unsigned)((total + 63) / 64), 64, 0, ctx->stream>>>((const XYZZ<Fq>*)d_pow2, total,
+    k_fb_multiples<Fq><<<(unsigned)((total * FB_GROUPS + 63) / 64), 64, 0, ctx->stream>>>((const XYZZ<Fq>*)d_pow2, total,
                                                                                (Affine<Fq>*)table + lo * TBL_ENTRIES);
     ctx->launches += 2;
     rc = launch_check(ctx, "build_tables");
@@ -345,7 +350,7 @@ static int fb_commit(bpgpu_fixed_bases* fb, const uint8_t* scalars_be, size_t co
   if ((rc = ctx->msm_c.reserve(ns * 32 + 32))) return rc;
   if ((rc = ctx->msm_e.reserve(count * sizeof(XYZZ<Fq>) + 32))) return rc;
   if ((rc = scalars_from_host<Curve>(ctx, scalars_be, ns, 0, ctx->msm_c.p))) return rc;
-  k_fb_commit<Fq><<<(unsigned)count, 64, 0, ctx->stream>>>((const Affine<Fq>*)fb->table, (int)fb->k, (const ScalarInt*)ctx->msm_c.p,
+  k_fb_commit<Fq><<<(unsigned)count, FB_WINDOWS, 0, ctx->stream>>>((const Affine<Fq>*)fb->table, (int)fb->k, (const ScalarInt*)ctx->msm_c.p,
                                                          (XYZZ<Fq>*)ctx->msm_e.p);
   ctx->launches++;
   if ((rc = launch_check(ctx, "k_fb_commit"))) return rc;

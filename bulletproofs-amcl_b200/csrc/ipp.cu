@@ -405,7 +405,7 @@ static int ipp_s_t(bpgpu_ctx* ctx, const uint8_t* u_be, size_t lg, void* d_s) {
 
 // expected_P of verify_ipp.  Always ONE general Pippenger run over [Q | G | H | L | R]: the proof-specific points need the
 // general path anyway, and gathering G and H next to them is cheaper than an extra table launch pair (measured at n = 64:
-// 1.05 ms vs 1.21 ms; at n = 2^14 the 64 table entries per term cost 2.5x the bucket method's work).
+// 1.05 ms vs 1.21 ms; at n = 2^14 the table entries per term still cost more than the bucket method's work).
 template <class Curve>
 static int ipp_verify_t(bpgpu_ctx* ctx, const void* G, const void* H, const uint8_t* Q_xy, const void* Gf, const void* Hf,
                         const uint8_t* a_be, const uint8_t* b_be, const uint8_t* u_be, const uint8_t* L_xy, const uint8_t* R_xy,

@@ -77,13 +77,13 @@ int bpgpu_points_download(bpgpu_ctx* ctx, const bpgpu_points* p, size_t off, siz
  * computed by the caller (G1::from_msg_hash = hash_msg + mapit; utils/mod.rs:16-23 get_generators builds every
  * generator table this way).  Try-and-increment, square root, even-y choice and cofactor clearing run on the device. */
 int bpgpu_points_from_hashes(bpgpu_ctx* ctx, const uint8_t* hashes, size_t n, bpgpu_points** out);
-/* Window tables for a generator table: T[i][w][d] = d * 2^(4w) * P_i (64 windows x 15 multiples, 960 affine points =
- * 90 KB (BLS12-381) / 60 KB (BN254) per generator, built once on the device).  Afterwards every MSM whose points come from
+/* Window tables for a generator table: T[i][w][d] = d * 2^(8w) * P_i (32 windows x 255 multiples, 8160 affine points =
+ * 765 KB (BLS12-381) / 510 KB (BN254) per generator, built once on the device).  Afterwards every MSM whose points come from
  * this handle -- bpgpu_msm, bpgpu_msm_device, bpgpu_msm_parts(_batch) when ALL its parts have tables, and the rounds of
- * bpgpu_ipp_begin_fixed_q -- is a plain sum of table entries: no doublings, no buckets, no Horner tail on the host.
- * Meant for the fixed generators G, H of the proof system (utils/mod.rs:16-23).  It trades HBM and ~2.5x the bucket
- * method's additions for latency: a clear win up to a few thousand generators (prove n = 64: 10.4 -> 3.8 ms, n = 1024:
- * 29.6 -> 8.5 ms), a loss in throughput mode at 2^14 -- callers precompute accordingly. */
+ * bpgpu_ipp_begin_fixed_q -- is a plain sum of 32 table entries per term: no doublings, no buckets, no Horner tail on the
+ * host.  Meant for the fixed generators G, H of the proof system (utils/mod.rs:16-23).  It trades HBM (1.6 GB for the 2048
+ * generators of a 1024-multiplier circuit) for latency: a clear win up to a few thousand generators (prove n = 64:
+ * 10.4 -> 2.4 ms, n = 1024: 29.6 -> 5.3 ms), a loss in throughput mode at 2^14 -- callers precompute accordingly. */
 int bpgpu_points_precompute(bpgpu_ctx* ctx, bpgpu_points* p);
 int bpgpu_points_has_tables(const bpgpu_points* p);
 size_t bpgpu_points_len(const bpgpu_points* p);
