@@ -40,7 +40,6 @@ struct MsmGeom {
   int lgL1;         // log2(buckets per lane) in k_reduce_l1; a warp covers 32 << lgL1 buckets
   uint32_t nseg;    // level-1 warps (segments) per window
   int lgL2;         // log2(segments per lane) in k_reduce_l2
-  uint32_t nrows;   // row/column reduction (c >= 13): the 2^(c-1) buckets of a window form an nrows x 256 grid
 };
 
 static const int GIANT_T = 16;         // buckets with more partials than this are collapsed by k_giant (a block tree: ~9 dependent additions)
@@ -386,91 +385,6 @@ __global__ void __launch_bounds__(64) k_reduce_l2(MsmGeom g, const XYZZ<Fq>* __r
 }
 
 // ------------------------------------------------------------------------------------------
-// Row/column bucket reduction for large windows (c >= 13).
-// Write bucket number b = hi*256 + lo + 1.  Then  sum_b b*B_b = 256 * sum_hi hi*R_hi + sum_lo (lo+1)*C_lo  with the PLAIN
-// sums R_hi = sum_lo B (rows) and C_lo = sum_hi B (columns).  Plain sums have no order: they are block-wide trees, so the
-// 2^(c-1) buckets cost two additions each at full parallelism, and the only weighted (serial) sums left are over the
-// nrows + 256 row/column totals.  This replaces per-lane running sums over 16 buckets (a 60-addition dependent chain).
-template <class Fq>
-__global__ void __launch_bounds__(256) k_bucket_rows(MsmGeom g, const uint32_t* __restrict__ pstart, const uint32_t* __restrict__ pcount,
-                                                     const XYZZ<Fq>* __restrict__ partials, XYZZ<Fq>* __restrict__ D, XYZZ<Fq>* __restrict__ R) {
-  __shared__ __align__(16) unsigned char smraw[256 * sizeof(XYZZ<Fq>)];
-  XYZZ<Fq>* sm = reinterpret_cast<XYZZ<Fq>*>(smraw);
-  const uint32_t w = blockIdx.x / g.nrows, row = blockIdx.x - w * g.nrows;
-  const uint32_t idx = row * 256 + threadIdx.x;
-  const uint32_t b = idx + 1;
-  const uint32_t* ps = pstart + (size_t)w * (g.nbp + 1);
-  const uint32_t* pc = pcount + (size_t)w * g.nbp;
-  const XYZZ<Fq>* in = partials + (size_t)w * g.pcap;
-  XYZZ<Fq> acc = XYZZ<Fq>::inf();
-  const uint32_t p0 = ps[b], p1 = p0 + pc[b];
-  if (p1 > p0) {
-    acc = load_vec(in + p0);
-    for (uint32_t k = p0 + 1; k < p1; k++) { XYZZ<Fq> q = load_vec(in + k); acc.add(q); }
-  }
-  store_vec(D + (size_t)w * (g.nbp - 1) + idx, acc);
-  XYZZ<Fq> tot = block_tree_sum(acc, sm);
-  if (threadIdx.x == 0) store_vec(R + blockIdx.x, tot);
-}
-
-// column sums: a block handles 256 / nrows columns, nrows threads per column
-template <class Fq>
-__global__ void __launch_bounds__(256) k_bucket_cols(MsmGeom g, const XYZZ<Fq>* __restrict__ D, XYZZ<Fq>* __restrict__ C) {
-  __shared__ __align__(16) unsigned char smraw[256 * sizeof(XYZZ<Fq>)];
-  XYZZ<Fq>* sm = reinterpret_cast<XYZZ<Fq>*>(smraw);
-  const uint32_t cpb = 256 / g.nrows;                       // columns per block
-  const uint32_t bpw = 256 / cpb;                           // blocks per window
-  const uint32_t w = blockIdx.x / bpw, cb = blockIdx.x - w * bpw;
-  const uint32_t h = threadIdx.x % g.nrows, lo = cb * cpb + threadIdx.x / g.nrows;
-  store_vec(sm + threadIdx.x, load_vec(D + (size_t)w * (g.nbp - 1) + (size_t)h * 256 + lo));
-  __syncthreads();
-  for (uint32_t o = g.nrows / 2; o > 0; o >>= 1) {
-    if (h < o) {
-      XYZZ<Fq> a = load_vec(sm + threadIdx.x), b = load_vec(sm + threadIdx.x + o);
-      a.add(b);
-      store_vec(sm + threadIdx.x, a);
-    }
-    __syncthreads();
-  }
-  if (h == 0) store_vec(C + (size_t)w * 256 + lo, load_vec(sm + threadIdx.x));
-}
-
-// per window: win = sum_lo (lo+1)*C_lo + 2^8 * sum_hi hi*R_hi   (warp 0: columns, warp 1: rows)
-template <class Fq>
-__global__ void __launch_bounds__(64) k_rowcol_final(MsmGeom g, const XYZZ<Fq>* __restrict__ R, const XYZZ<Fq>* __restrict__ C,
-                                                     XYZZ<Fq>* __restrict__ winP, XYZZ<Fq>* __restrict__ winQ) {
-  __shared__ __align__(16) unsigned char smraw[sizeof(XYZZ<Fq>)];
-  XYZZ<Fq>* sm = reinterpret_cast<XYZZ<Fq>*>(smraw);
-  const uint32_t w = blockIdx.x;
-  const int lane = threadIdx.x & 31, wid = threadIdx.x >> 5;
-  const XYZZ<Fq>* src = wid == 0 ? C + (size_t)w * 256 : R + (size_t)w * g.nrows;
-  const uint32_t cnt = wid == 0 ? 256u : g.nrows;
-  int lgL = 0;
-  while ((32u << lgL) < cnt) lgL++;
-  const uint32_t L = 1u << lgL, lo = (uint32_t)lane * L;
-  XYZZ<Fq> run = XYZZ<Fq>::inf(), acc = XYZZ<Fq>::inf();
-  if (lo < cnt) {
-    const uint32_t hi = min(lo + L, cnt);
-    for (uint32_t s = hi; s-- > lo;) { XYZZ<Fq> q = load_vec(src + s); run.add(q); acc.add(run); }
-  }
-  warp_weighted_sum(acc, run, lgL);           // lane 0: acc = sum (i+1)*X_i, run = sum X_i
-  if (wid == 1 && lane == 0) {
-    XYZZ<Fq> neg = run.neg();
-    acc.add(neg);                             // weights hi = (i+1) - 1
-#pragma unroll 1
-    for (int k = 0; k < 8; k++) acc.dbl();
-    store_vec(sm, acc);
-  }
-  __syncthreads();
-  if (wid == 0 && lane == 0) {
-    XYZZ<Fq> q = load_vec(sm);
-    acc.add(q);
-    store_vec(winP + w, acc);
-    store_vec(winQ + w, XYZZ<Fq>::inf());
-  }
-}
-
-// ------------------------------------------------------------------------------------------
 static inline size_t align256(size_t x) { return (x + 255) & ~(size_t)255; }
 
 struct StageTimer {
@@ -519,7 +433,6 @@ int msm_run(bpgpu_ctx* ctx, const Affine<typename Curve::Fq>* d_points, const vo
   static const char* env_c = getenv("BPGPU_C");
   static const char* env_s = getenv("BPGPU_S");
   static const char* env_l1 = getenv("BPGPU_LGL1");
-  static const char* env_rc = getenv("BPGPU_ROWCOL");
   if (env_c) g.c = atoi(env_c);
   g.W0 = (Curve::SCALAR_BITS + 1 + g.c - 1) / g.c;
   g.W = g.W0 * (d_scalars2 ? 2 : 1);
@@ -545,7 +458,6 @@ int msm_run(bpgpu_ctx* ctx, const Affine<typename Curve::Fq>* d_points, const vo
     int lg2 = 0;
     while ((32u << lg2) < g.nseg) lg2++;
     g.lgL2 = lg2;
-    g.nrows = (env_rc && atoi(env_rc) && g.c >= 13) ? nb / 256 : 0;   // experimental row/column reduction (slower: see DESIGN.md)
   }
 
   // ---- scratch layout
@@ -566,17 +478,12 @@ int msm_run(bpgpu_ctx* ctx, const Affine<typename Curve::Fq>* d_points, const vo
   const size_t sz_part = align256((size_t)g.W * g.pcap * sizeof(XYZZ<Fq>));
   const size_t sz_seg = align256((size_t)g.W * g.nseg * sizeof(XYZZ<Fq>));
   const size_t sz_wsum = align256((size_t)2 * g.W * sizeof(XYZZ<Fq>));
-  const size_t sz_dense = g.nrows ? align256((size_t)g.W * (g.nbp - 1) * sizeof(XYZZ<Fq>)) : 0;   // bucket sums D
-  const size_t sz_rc = g.nrows ? align256((size_t)g.W * (g.nrows + 256) * sizeof(XYZZ<Fq>)) : 0;   // row and column totals
-  if ((rc = ctx->msm_b.reserve(sz_part + 2 * sz_seg + sz_wsum + sz_dense + sz_rc))) return rc;
+  if ((rc = ctx->msm_b.reserve(sz_part + 2 * sz_seg + sz_wsum))) return rc;
   uint8_t* b2 = (uint8_t*)ctx->msm_b.p;
   XYZZ<Fq>* partials = (XYZZ<Fq>*)b2; b2 += sz_part;
   XYZZ<Fq>* segA = (XYZZ<Fq>*)b2; b2 += sz_seg;
   XYZZ<Fq>* segS = (XYZZ<Fq>*)b2; b2 += sz_seg;
-  XYZZ<Fq>* winsum = (XYZZ<Fq>*)b2; b2 += sz_wsum;             // [0, W): P_w   [W, 2W): Q_w
-  XYZZ<Fq>* dense = (XYZZ<Fq>*)b2; b2 += sz_dense;
-  XYZZ<Fq>* rowsum = (XYZZ<Fq>*)b2;
-  XYZZ<Fq>* colsum = rowsum + (size_t)g.W * g.nrows;
+  XYZZ<Fq>* winsum = (XYZZ<Fq>*)b2;                            // [0, W): P_w   [W, 2W): Q_w
 
   StageTimer tm(st, ctx->profile != 0 && n >= (size_t)ctx->profile);   // profile = smallest n that is recorded
   BP_CUDA_OK(cudaMemsetAsync(hist, 0, sz_hist, st));
@@ -612,16 +519,8 @@ int msm_run(bpgpu_ctx* ctx, const Affine<typename Curve::Fq>* d_points, const vo
     k_merge<Fq><<<(threads + 127) / 128, 128, 0, st>>>(g, bstart, pstart, hist, partials);
   }
   tm.mark("merge");
-  int qshift = 5 + g.lgL1;
-  if (g.nrows) {
-    k_bucket_rows<Fq><<<g.W * g.nrows, 256, 0, st>>>(g, pstart, hist, partials, dense, rowsum);
-    k_bucket_cols<Fq><<<g.W * g.nrows, 256, 0, st>>>(g, dense, colsum);
-    tm.mark("reduce_l1");
-    k_rowcol_final<Fq><<<g.W, 64, 0, st>>>(g, rowsum, colsum, winsum, winsum + g.W);
-    tm.mark("reduce_l2");
-    ctx->launches++;
-    qshift = 0;
-  } else {
+  const int qshift = 5 + g.lgL1;
+  {
     uint32_t warps = (uint32_t)g.W * g.nseg;
     k_reduce_l1<Fq><<<(warps * 32 + 127) / 128, 128, 0, st>>>(g, pstart, hist, partials, segA, segS);
     tm.mark("reduce_l1");
