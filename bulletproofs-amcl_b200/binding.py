@@ -88,6 +88,8 @@ SYMBOLS_HOST = [
     ("bph_bound_check_prove", _INT, [_VP, _CS, _VP, _VP, _VP, _VP, _U64, _VP, _U64, _U64, _SZ, _INT, _U64, _VP, _SZ,
                                      _c.POINTER(_SZ), _VP]),
     ("bph_bound_check_verify", _INT, [_VP, _CS, _VP, _VP, _VP, _VP, _U64, _U64, _SZ, _VP, _SZ, _VP, _VP]),
+    ("bph_shuffle_prove", _INT, [_VP, _CS, _VP, _VP, _VP, _VP, _VP, _VP, _SZ, _SZ, _INT, _U64, _VP, _SZ, _c.POINTER(_SZ), _VP]),
+    ("bph_shuffle_verify", _INT, [_VP, _CS, _VP, _VP, _VP, _VP, _SZ, _SZ, _VP, _SZ, _VP, _VP]),
     ("bph_range_prove", _INT, [_VP, _CS, _VP, _VP, _VP, _VP, _VP, _SZ, _SZ, _INT, _U64, _VP, _SZ, _c.POINTER(_SZ), _VP]),
     ("bph_range_verify", _INT, [_VP, _CS, _VP, _VP, _VP, _VP, _SZ, _SZ, _VP, _SZ, _VP, _VP]),
     ("bph_range_proof_len", _SZ, [_INT, _SZ, _SZ]),
@@ -593,6 +595,24 @@ class Context:
         if rc == -4:
             return False
         self._check(rc, "range_verify")
+        return True
+
+    def shuffle_prove(self, label, g_xy, h_xy, G, H, xs, ys, bits=0, seed=None):
+        """two-phase circuit: {ys} is a permutation of {xs}, xs[0] range-checked to `bits` bits -> (proof, 2k commitments)"""
+        k = len(xs)
+        ax, ay = (ctypes.c_uint64 * k)(*xs), (ctypes.c_uint64 * k)(*ys)
+        comms = ctypes.create_string_buffer(2 * k * 2 * self.modbytes)
+        proof = self._proof_call(lib().bph_shuffle_prove, "shuffle_prove", self.handle, label, _buf(g_xy), _buf(h_xy), G.handle, H.handle,
+                                 ctypes.cast(ax, ctypes.c_void_p), ctypes.cast(ay, ctypes.c_void_p), k, bits, 0 if seed is None else 1,
+                                 seed or 0, extra_after=(comms,))
+        return proof, comms.raw
+
+    def shuffle_verify(self, label, g_xy, h_xy, G, H, k, bits, proof, comms, r_be=None):
+        rc = lib().bph_shuffle_verify(self.handle, label, _buf(g_xy), _buf(h_xy), G.handle, H.handle, k, bits, _buf(proof), len(proof),
+                                      _buf(comms), _buf(r_be) if r_be is not None else None)
+        if rc == -4:
+            return False
+        self._check(rc, "shuffle_verify")
         return True
 
     # ---- self-test hooks

@@ -149,6 +149,33 @@ int range_verify_t(bpgpu_ctx* ctx, const char* label, const uint8_t* g_xy, const
   return verify_proof_of_positive_nums<C>(ctx, bits, p, comms, label, G1<C>::from_xy(g_xy), G1<C>::from_xy(h_xy), vG, vH, verifier_scalar<C>(r_be));
 }
 
+template <class C>
+int shuffle_prove_t(bpgpu_ctx* ctx, const char* label, const uint8_t* g_xy, const uint8_t* h_xy, const bpgpu_points* G, const bpgpu_points* H,
+                    const uint64_t* x, const uint64_t* y, size_t k, size_t bits, int rng_mode, uint64_t seed, uint8_t* proof, size_t cap,
+                    size_t* len, uint8_t* comms_xy) {
+  Rng<C> rng = make_rng<C>(rng_mode, seed);
+  G1Vector<C> vG = G1Vector<C>::borrow(ctx, G), vH = G1Vector<C>::borrow(ctx, H);
+  R1CSProof<C> p;
+  std::vector<G1<C>> comms;
+  int rc = gen_proof_of_shuffle<C>(ctx, std::vector<uint64_t>(x, x + k), std::vector<uint64_t>(y, y + k), bits, rng, label, G1<C>::from_xy(g_xy),
+                                   G1<C>::from_xy(h_xy), vG, vH, &p, &comms);
+  if (rc) return rc;
+  for (size_t j = 0; j < comms.size(); j++) memcpy(comms_xy + j * 2 * C::MODBYTES, comms[j].xy, 2 * C::MODBYTES);
+  return emit(p.to_bytes(), proof, cap, len);
+}
+
+template <class C>
+int shuffle_verify_t(bpgpu_ctx* ctx, const char* label, const uint8_t* g_xy, const uint8_t* h_xy, const bpgpu_points* G, const bpgpu_points* H,
+                     size_t k, size_t bits, const uint8_t* proof, size_t len, const uint8_t* comms_xy, const uint8_t* r_be) {
+  R1CSProof<C> p;
+  int rc = R1CSProof<C>::from_bytes(proof, len, &p);
+  if (rc) return rc;
+  std::vector<G1<C>> comms(2 * k);
+  for (size_t j = 0; j < 2 * k; j++) comms[j] = G1<C>::from_xy(comms_xy + j * 2 * C::MODBYTES);
+  G1Vector<C> vG = G1Vector<C>::borrow(ctx, G), vH = G1Vector<C>::borrow(ctx, H);
+  return verify_proof_of_shuffle<C>(ctx, k, bits, p, comms, label, G1<C>::from_xy(g_xy), G1<C>::from_xy(h_xy), vG, vH, verifier_scalar<C>(r_be));
+}
+
 // hash_msg: SHAKE256(msg) squeezed to MODBYTES (G1::from_msg_hash / FieldElement::from_msg_hash)
 void hash_msg(const uint8_t* msg, size_t len, int modbytes, uint8_t* out) { shake256(msg, len, out, modbytes); }
 
@@ -382,6 +409,23 @@ int bph_range_verify(bpgpu_ctx* ctx, const char* label, const uint8_t* g_xy, con
                      size_t m, size_t bits, const uint8_t* proof, size_t len, const uint8_t* comms_xy, const uint8_t* r_be) {
   if (!ctx || !label || !g_xy || !h_xy || !G || !H || !proof || (!comms_xy && m)) return BPGPU_E_ARG;
 #define CALL(C) range_verify_t<C>(ctx, label, g_xy, h_xy, G, H, m, bits, proof, len, comms_xy, r_be)
+  return BY_CURVE(ctx, CALL);
+#undef CALL
+}
+
+int bph_shuffle_prove(bpgpu_ctx* ctx, const char* label, const uint8_t* g_xy, const uint8_t* h_xy, const bpgpu_points* G, const bpgpu_points* H,
+                      const uint64_t* x, const uint64_t* y, size_t k, size_t bits, int rng_mode, uint64_t seed, uint8_t* proof, size_t cap,
+                      size_t* len, uint8_t* comms_xy) {
+  if (!ctx || !label || !g_xy || !h_xy || !G || !H || !x || !y || !k || !comms_xy || bits > 64) return BPGPU_E_ARG;
+#define CALL(C) shuffle_prove_t<C>(ctx, label, g_xy, h_xy, G, H, x, y, k, bits, rng_mode, seed, proof, cap, len, comms_xy)
+  return BY_CURVE(ctx, CALL);
+#undef CALL
+}
+
+int bph_shuffle_verify(bpgpu_ctx* ctx, const char* label, const uint8_t* g_xy, const uint8_t* h_xy, const bpgpu_points* G, const bpgpu_points* H,
+                       size_t k, size_t bits, const uint8_t* proof, size_t len, const uint8_t* comms_xy, const uint8_t* r_be) {
+  if (!ctx || !label || !g_xy || !h_xy || !G || !H || !proof || !k || !comms_xy) return BPGPU_E_ARG;
+#define CALL(C) shuffle_verify_t<C>(ctx, label, g_xy, h_xy, G, H, k, bits, proof, len, comms_xy, r_be)
   return BY_CURVE(ctx, CALL);
 #undef CALL
 }

@@ -155,4 +155,70 @@ int verify_proof_of_positive_nums(bpgpu_ctx* ctx, size_t bits, const R1CSProof<C
   return verifier.verify(proof, g, h, G, H, verifier_r);
 }
 
+// k-shuffle: {y} is a permutation of {x}.  The TWO-PHASE gadget of the reference's ConstraintSystem documentation
+// (constraint_system.rs:86-135): the challenge z exists only after the first-phase commitments A_I1, A_O1, S1, and
+// prod (x_i - z) = prod (y_i - z) costs 2(k-1) second-phase multipliers -- the path through
+// specify_randomized_constraints, RandomizedConstraintSystem::challenge_scalar and the A_I2 / A_O2 / S2 commitments
+// (prover.rs:300-319,384-436; verifier.rs:245-264).
+template <class C>
+int shuffle_gadget(ConstraintSystem<C>& cs, const std::vector<Variable>& x, const std::vector<Variable>& y) {
+  using FE = FieldElement<C>;
+  using LC = LinearCombination<C>;
+  if (x.size() != y.size() || x.empty()) return E_ARG;
+  return cs.specify_randomized_constraints([x, y](ConstraintSystem<C>& cs) -> int {
+    const size_t k = x.size();
+    FE z;
+    int rc = cs.challenge_scalar("shuffle challenge", &z);
+    if (rc) return rc;
+    if (k == 1) { cs.constrain(LC(y[0]) - LC(x[0])); return OK; }
+    auto chain = [&](const std::vector<Variable>& v) {
+      Variable l, r, o;
+      cs.multiply(LC(v[k - 1]) - LC(z), LC(v[k - 2]) - LC(z), &l, &r, &o);
+      for (size_t i = k - 2; i-- > 0;) cs.multiply(LC(o), LC(v[i]) - LC(z), &l, &r, &o);
+      return o;
+    };
+    const Variable ox = chain(x), oy = chain(y);
+    cs.constrain(LC(ox) - LC(oy));
+    return OK;
+  });
+}
+
+// shuffle statement over 2k committed values, with x[0] additionally range-checked to `bits` bits in the FIRST phase
+// (bits = 0: no first-phase multipliers at all) -- a circuit with n1 = bits and n2 = 2(k-1)
+template <class C>
+int gen_proof_of_shuffle(bpgpu_ctx* ctx, const std::vector<uint64_t>& xs, const std::vector<uint64_t>& ys, size_t bits, Rng<C>& rng,
+                         const std::string& transcript_label, const G1<C>& g, const G1<C>& h, const G1Vector<C>& G, const G1Vector<C>& H,
+                         R1CSProof<C>* proof, std::vector<G1<C>>* comms) {
+  using FE = FieldElement<C>;
+  Transcript prover_transcript(transcript_label);
+  Prover<C> prover(ctx, g, h, prover_transcript, rng);
+  std::vector<FE> fv, blind;
+  for (uint64_t v : xs) { fv.push_back(FE::from_u64(v)); blind.push_back(rng.next()); }
+  for (uint64_t v : ys) { fv.push_back(FE::from_u64(v)); blind.push_back(rng.next()); }
+  std::vector<Variable> vars;
+  int rc = prover.commit_vec(fv, blind, comms, &vars);
+  if (rc) return rc;
+  const size_t k = xs.size();
+  if (bits && (rc = positive_no_gadget<C>(prover, AllocatedQuantity<C>{vars[0], true, fv[0]}, bits))) return rc;
+  std::vector<Variable> vx(vars.begin(), vars.begin() + k), vy(vars.begin() + k, vars.end());
+  if ((rc = shuffle_gadget<C>(prover, vx, vy))) return rc;
+  return prover.prove(G, H, proof);
+}
+
+template <class C>
+int verify_proof_of_shuffle(bpgpu_ctx* ctx, size_t k, size_t bits, const R1CSProof<C>& proof, const std::vector<G1<C>>& commitments,
+                            const std::string& transcript_label, const G1<C>& g, const G1<C>& h, const G1Vector<C>& G, const G1Vector<C>& H,
+                            const FieldElement<C>& verifier_r) {
+  if (commitments.size() != 2 * k || k == 0) return E_ARG;
+  Transcript verifier_transcript(transcript_label);
+  Verifier<C> verifier(ctx, verifier_transcript);
+  std::vector<Variable> vars;
+  for (const auto& com : commitments) vars.push_back(verifier.commit(com));
+  int rc;
+  if (bits && (rc = positive_no_gadget<C>(verifier, AllocatedQuantity<C>{vars[0], false, FieldElement<C>::zero()}, bits))) return rc;
+  std::vector<Variable> vx(vars.begin(), vars.begin() + k), vy(vars.begin() + k, vars.end());
+  if ((rc = shuffle_gadget<C>(verifier, vx, vy))) return rc;
+  return verifier.verify(proof, g, h, G, H, verifier_r);
+}
+
 }  // namespace bph

@@ -95,6 +95,18 @@ int bph_range_verify_batch(bpgpu_ctx* ctx, const char* transcript_label, const u
                            bpgpu_points* H, size_t count, size_t m, size_t bits, const uint8_t* proofs, size_t proof_stride,
                            const uint8_t* comms_xy, size_t nthreads, int32_t* verdicts);
 
+/* ---- a TWO-PHASE circuit: k-shuffle ({y} is a permutation of {x}) over 2k committed values, x[0] range-checked to `bits`
+ * bits in the first phase (0 = none).  The gadget is the example of the reference's ConstraintSystem documentation
+ * (constraint_system.rs:86-135); it exercises specify_randomized_constraints, the challenge drawn between the phases and
+ * the second-phase commitments A_I2, A_O2, S2 (prover.rs:300-319,384-436; verifier.rs:245-264).  n = bits + 2(k-1)
+ * multipliers; comms_xy = the 2k commitments, x first.  Proof layout as bph_range_proof_len(curve, 1, n) bytes. */
+int bph_shuffle_prove(bpgpu_ctx* ctx, const char* transcript_label, const uint8_t* g_xy, const uint8_t* h_xy, const bpgpu_points* G,
+                      const bpgpu_points* H, const uint64_t* x, const uint64_t* y, size_t k, size_t bits, int rng_mode, uint64_t seed,
+                      uint8_t* proof, size_t cap, size_t* len, uint8_t* comms_xy);
+int bph_shuffle_verify(bpgpu_ctx* ctx, const char* transcript_label, const uint8_t* g_xy, const uint8_t* h_xy, const bpgpu_points* G,
+                       const bpgpu_points* H, size_t k, size_t bits, const uint8_t* proof, size_t len, const uint8_t* comms_xy,
+                       const uint8_t* verifier_r_be);
+
 /* ---- MSM sharded by points over several contexts: one process, one context per GPU (or several per GPU) ----
  * shard k = `counts[k]` points resident on ctxs[k]'s device (bpgpu_points_upload there), its scalars are the next counts[k]
  * entries of scalars_be.  One host thread per context runs bpgpu_msm on its shard; the affine partial sums (2*MODBYTES

@@ -84,6 +84,17 @@ class Prover:
         self.a_L, self.a_R, self.a_O = [], [], []
         self.v, self.v_blinding = [], []
         self.pending_multiplier = None
+        self.deferred = []                                 # prover.rs:665-671 deferred_constraints
+
+    def specify_randomized_constraints(self, callback):    # prover.rs:665-671 (1st phase) / :740-745 (inside a callback)
+        if getattr(self, "randomizing", False):
+            callback(self)
+        else:
+            self.deferred.append(callback)
+
+    def challenge_scalar(self, label):                     # RandomizedConstraintSystem, prover.rs:759-763
+        assert getattr(self, "randomizing", False)
+        return self.transcript.challenge_scalar(label)
 
     def commit(self, v, v_blinding):                       # prover.rs:119-129
         C = self.C
@@ -143,7 +154,7 @@ class Prover:
             exp_z = exp_z * z % r
         return wL, wR, wO, wV
 
-    def prove(self, G, H, rng):                            # prover.rs:322-593 (1-phase circuits)
+    def prove(self, G, H, rng):                            # prover.rs:322-593 (1- and 2-phase circuits)
         C, r, T = self.C, self.C.r, self.transcript
         T.append_u64(b"m", len(self.v))                    # :327
         n1 = len(self.a_L)
@@ -160,16 +171,35 @@ class Prover:
         T.commit_point(b"A_I1", A_I1)
         T.commit_point(b"A_O1", A_O1)
         T.commit_point(b"S1", S1)
-        T.r1cs_1phase_domain_sep()                         # :300-306 (no gadget defers constraints)
+        if not self.deferred:                              # create_randomized_constraints, :300-319
+            T.r1cs_1phase_domain_sep()
+        else:
+            T.r1cs_2phase_domain_sep()
+            callbacks, self.deferred = self.deferred, []
+            self.randomizing = True
+            for cb in callbacks:
+                cb(self)
+            self.randomizing = False
         n = len(self.a_L)
         n2 = n - n1
         padded_n = 1 if n == 0 else 1 << (n - 1).bit_length()   # usize::next_power_of_two
         pad = padded_n - n
         if len(G) < padded_n:
             raise InvalidGeneratorsLength()
-        assert n2 == 0
-        i_blinding2 = o_blinding2 = s_blinding2 = 0        # :398-404
-        A_I2 = A_O2 = S2 = C.INF                           # :429
+        if n2 > 0:                                         # :384-427
+            i_blinding2, o_blinding2, s_blinding2 = rng(), rng(), rng()
+        else:
+            i_blinding2 = o_blinding2 = s_blinding2 = 0    # :398-404
+        s_L2 = [rng() for _ in range(n2)]                  # :401
+        s_R2 = [rng() for _ in range(n2)]                  # :402
+        if n2 > 0:
+            G2_, H2_ = G[n1:n], H[n1:n]
+            A_I2 = C.msm(G2_ + H2_ + [self.h], self.a_L[n1:] + self.a_R[n1:] + [i_blinding2])
+            A_O2 = C.msm(G2_ + [self.h], self.a_O[n1:] + [o_blinding2])
+            S2 = C.msm(G2_ + H2_ + [self.h], s_L2 + s_R2 + [s_blinding2])
+        else:
+            A_I2 = A_O2 = S2 = C.INF                       # :429
+        s_L1, s_R1 = s_L1 + s_L2, s_R1 + s_R2              # s_L, s_R over all n multipliers (:474, :484)
         T.commit_point(b"A_I2", A_I2)
         T.commit_point(b"A_O2", A_O2)
         T.commit_point(b"S2", S2)
@@ -236,6 +266,17 @@ class Verifier:
         self.num_vars = 0
         self.V = []
         self.constraints = []
+        self.deferred = []                                 # verifier.rs:508-514
+
+    def specify_randomized_constraints(self, callback):    # verifier.rs:508-514 / :577-582
+        if getattr(self, "randomizing", False):
+            callback(self)
+        else:
+            self.deferred.append(callback)
+
+    def challenge_scalar(self, label):                     # verifier.rs:596-600
+        assert getattr(self, "randomizing", False)
+        return self.transcript.challenge_scalar(label)
 
     def commit(self, commitment):                          # verifier.rs:124-132
         i = len(self.V)
@@ -285,7 +326,15 @@ class Verifier:
         T.commit_point(b"A_I1", proof.A_I1)
         T.commit_point(b"A_O1", proof.A_O1)
         T.commit_point(b"S1", proof.S1)
-        T.r1cs_1phase_domain_sep()
+        if not self.deferred:                              # create_randomized_constraints, verifier.rs:245-264
+            T.r1cs_1phase_domain_sep()
+        else:
+            T.r1cs_2phase_domain_sep()
+            callbacks, self.deferred = self.deferred, []
+            self.randomizing = True
+            for cb in callbacks:
+                cb(self)
+            self.randomizing = False
         n = self.num_vars
         n2 = n - n1
         padded_n = 1 if n == 0 else 1 << (n - 1).bit_length()
@@ -394,6 +443,31 @@ def verify_bounded_num(verifier, lower, upper, bits, commitments):
     """gadgets/bound_check.rs:94-129."""
     qs = [AllocatedQuantity(verifier.commit(c), None) for c in commitments[:3]]
     bound_check_gadget(verifier, qs[0], qs[1], qs[2], upper, lower, bits)
+
+
+def shuffle_gadget(cs, xs, ys):
+    """k-shuffle: {ys} is a permutation of {xs}.  The classic TWO-PHASE gadget (the example in the reference's
+    constraint_system.rs:86-135 doc comments): the challenge z is drawn after the first-phase commitments, then
+    prod (x_i - z) = prod (y_i - z) is enforced with 2(k-1) second-phase multipliers."""
+    C = cs.C
+    assert len(xs) == len(ys) and len(xs) >= 1
+    k = len(xs)
+
+    def cb(cs):
+        z = cs.challenge_scalar(b"shuffle challenge")
+        mz = (-z) % C.r
+        if k == 1:
+            cs.constrain(LC([(ys[0], 1), (xs[0], C.r - 1)]))
+            return
+
+        def chain(vs):
+            _, _, out = cs.multiply(LC([(vs[k - 1], 1), (VAR_ONE, mz)]), LC([(vs[k - 2], 1), (VAR_ONE, mz)]))
+            for i in range(k - 3, -1, -1):
+                _, _, out = cs.multiply(LC([(out, 1)]), LC([(vs[i], 1), (VAR_ONE, mz)]))
+            return out
+        ox, oy = chain(xs), chain(ys)
+        cs.constrain(LC([(ox, 1), (oy, C.r - 1)]))
+    cs.specify_randomized_constraints(cb)
 
 
 def make_rng(C, seed, tag=b"blind"):

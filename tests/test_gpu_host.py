@@ -194,3 +194,55 @@ def test_batch_prove_verify_keeps_per_proof_verdicts(bp, ctx_bls):
     assert bp.range_verify_batch(ctx_bls, b"Batch", gx, hx, dG2, dH2, 0, m, bits, b"", stride, b"") == []
     for c in ctxs[1:]:
         c.close()
+
+
+@pytest.mark.parametrize("which", ["bls", "bn"])
+@pytest.mark.parametrize("k,bits,pre", [(2, 0, False), (3, 4, False), (5, 8, True)])
+def test_two_phase_shuffle_matches_oracle(which, k, bits, pre, ctx_bls, ctx_bn):
+    """A circuit with RANDOMISED constraints (the shuffle example of constraint_system.rs:86-135): first-phase commitments,
+    2-phase domain separator, challenge z, 2(k-1) second-phase multipliers, A_I2 / A_O2 / S2 (prover.rs:300-319,384-436;
+    verifier.rs:245-264), n padded to a power of two.  Proof bytes equal the oracle's; a non-permutation does not verify."""
+    ctx = ctx_bls if which == "bls" else ctx_bn
+    C = curve_of(ctx)
+    g, h = C.g1_from_msg_hash(b"g"), C.g1_from_msg_hash(b"h")
+    gx, hx = C.g1_xy_bytes(g), C.g1_xy_bytes(h)
+    n = bits + 2 * (k - 1)
+    N = 1 << max(0, (n - 1).bit_length())
+    G, H = C.get_generators("G", N), C.get_generators("H", N)
+    dG, dH = ctx.get_generators("G", N, precompute=pre), ctx.get_generators("H", N, precompute=pre)
+    xs = [(7 + 13 * i) % (1 << max(bits, 6)) for i in range(k)]
+    if bits:
+        xs[0] %= 1 << bits
+    ys = xs[1:] + xs[:1]                                     # a rotation: a permutation
+    seed = 40 + k
+    rng = or1cs.make_rng(C, seed)
+    p = or1cs.Prover(C, g, h, Transcript(b"Shuffle", C))
+    comms, vars_ = [], []
+    blinds = [rng() for _ in range(2 * k)]
+    for v, bl in zip(xs + ys, blinds):
+        com, var = p.commit(v, bl)
+        comms.append(com)
+        vars_.append(var)
+    if bits:
+        or1cs.positive_no_gadget(p, or1cs.AllocatedQuantity(vars_[0], xs[0]), bits)
+    or1cs.shuffle_gadget(p, vars_[:k], vars_[k:])
+    exp = p.prove(G, H, rng)
+    assert not C.is_inf(exp.A_I2) or k == 1                  # the second phase really committed something
+    # the oracle's verifier accepts its own proof
+    v = or1cs.Verifier(C, Transcript(b"Shuffle", C))
+    vv = [v.commit(c) for c in comms]
+    if bits:
+        or1cs.positive_no_gadget(v, or1cs.AllocatedQuantity(vv[0], None), bits)
+    or1cs.shuffle_gadget(v, vv[:k], vv[k:])
+    v.verify(exp, g, h, G, H, C.synth_scalar(3, 0))
+    proof, cb = ctx.shuffle_prove(b"Shuffle", gx, hx, dG, dH, xs, ys, bits, seed=seed)
+    assert cb == enc_points(C, comms)
+    assert proof == exp.to_bytes(C)
+    assert ctx.shuffle_verify(b"Shuffle", gx, hx, dG, dH, k, bits, proof, cb) is True
+    # not a permutation: the prover still emits a proof, the verifier rejects it
+    bad_y = list(ys)
+    bad_y[0] += 1
+    proof2, cb2 = ctx.shuffle_prove(b"Shuffle", gx, hx, dG, dH, xs, bad_y, bits, seed=seed)
+    assert ctx.shuffle_verify(b"Shuffle", gx, hx, dG, dH, k, bits, proof2, cb2) is False
+    # a proof for other commitments does not transfer
+    assert ctx.shuffle_verify(b"Shuffle", gx, hx, dG, dH, k, bits, proof, cb2) is False

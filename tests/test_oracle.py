@@ -123,3 +123,39 @@ def test_c_oracle_matches_python():
         assert cref.msm(C.id, xy, sb, n, 1) == exp
         assert cref.msm(C.id, xy, sb, n, 4) == exp
         assert cref.msm(C.id, xy, sb, 0, 1) == C.g1_xy_bytes(C.INF)
+
+
+def test_two_phase_circuit_round_trip():
+    """Randomised constraints (prover.rs:300-319,384-436; verifier.rs:245-264) in the oracle: a 3-shuffle with a 4-bit range
+    check in the first phase proves and verifies (n = 4 + 4 = 8), the second phase commits something, and a
+    non-permutation is rejected.  Group operations through oracle/c to keep the CPU suite fast."""
+    from oracle import fast, r1cs as or1cs
+    from oracle.curves import BN254
+    from oracle.merlin import Transcript
+    C = fast.FastCurve(BN254)
+    with fast.c_keccak():
+        g, h = C.g1_from_msg_hash(b"g"), C.g1_from_msg_hash(b"h")
+        k, bits = 3, 4
+        G, H = C.get_generators("G", 8), C.get_generators("H", 8)
+        xs = [7, 20, 33]
+        for ys, ok in (([20, 33, 7], True), ([21, 33, 7], False)):
+            rng = or1cs.make_rng(C, 5)
+            p = or1cs.Prover(C, g, h, Transcript(b"S", C))
+            comms, vs = [], []
+            for v in xs + ys:
+                com, var = p.commit(v, rng())
+                comms.append(com)
+                vs.append(var)
+            or1cs.positive_no_gadget(p, or1cs.AllocatedQuantity(vs[0], xs[0]), bits)
+            or1cs.shuffle_gadget(p, vs[:k], vs[k:])
+            proof = p.prove(G, H, rng)
+            assert len(p.a_L) == 8 and not C.is_inf(proof.A_I2) and not C.is_inf(proof.S2)
+            v = or1cs.Verifier(C, Transcript(b"S", C))
+            vv = [v.commit(c) for c in comms]
+            or1cs.positive_no_gadget(v, or1cs.AllocatedQuantity(vv[0], None), bits)
+            or1cs.shuffle_gadget(v, vv[:k], vv[k:])
+            if ok:
+                v.verify(proof, g, h, G, H, 12345)
+            else:
+                with pytest.raises(or1cs.R1CSError):
+                    v.verify(proof, g, h, G, H, 12345)
