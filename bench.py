@@ -215,7 +215,8 @@ def proof_section(bp, ctx, local, rank, world, dist, torch, no_cpu=False):
     run(bp.BLS12_381, 1, 64, per_rank, "range64_bls12_381_n64", verify_reps=max(1, 4096 // (per_rank * world)),
         batch_call=True, cpu_base=0 if no_cpu else 4)
     # config 2: 16 x 64-bit values in one constraint system, 1024 generators
-    run(bp.BLS12_381, 16, 64, max(nctx, 64 // world), "range64x16_bls12_381_n1024", cpu_base=0 if no_cpu else 1)
+    run(bp.BLS12_381, 16, 64, max(nctx, 64 // world), "range64x16_bls12_381_n1024", verify_reps=4, batch_call=True,
+        cpu_base=0 if no_cpu else 1)
     # config 3: 2^14 multipliers on BN254 (256 x 64-bit values)
     run(bp.BN254, 256, 64, max(nctx, 16 // world), "range64x256_bn254_n16384", cpu_base=0 if no_cpu else 1)
     return out

@@ -181,8 +181,10 @@ __device__ __forceinline__ uint32_t bucket_of(const uint32_t* __restrict__ bs, u
   return lo;
 }
 
-template <class Fq, int MINB>
-__global__ void __launch_bounds__(128, MINB) k_chunk_acc(MsmGeom g, const Affine<Fq>* __restrict__ pts,
+// 2 blocks of 128 threads per SM (186 registers); forcing 3 blocks (168 registers) measures the same: the kernel is bound by
+// the multiplier pipe, not by occupancy
+template <class Fq>
+__global__ void __launch_bounds__(128, 2) k_chunk_acc(MsmGeom g, const Affine<Fq>* __restrict__ pts,
                                                    const uint32_t* __restrict__ sidx,
                                                    const uint32_t* __restrict__ bstart, const uint32_t* __restrict__ pstart,
                                                    XYZZ<Fq>* __restrict__ partials) {
@@ -507,9 +509,7 @@ int msm_run(bpgpu_ctx* ctx, const Affine<typename Curve::Fq>* d_points, const vo
   }
   {
     uint32_t threads = (uint32_t)g.W * g.nchunk;
-    static const char* env_mb = getenv("BPGPU_CHUNK_MINB");
-    if (env_mb && atoi(env_mb) == 3) k_chunk_acc<Fq, 3><<<(threads + 127) / 128, 128, 0, st>>>(g, d_points, sidx, bstart, pstart, partials);
-    else k_chunk_acc<Fq, 2><<<(threads + 127) / 128, 128, 0, st>>>(g, d_points, sidx, bstart, pstart, partials);
+    k_chunk_acc<Fq><<<(threads + 127) / 128, 128, 0, st>>>(g, d_points, sidx, bstart, pstart, partials);
     tm.mark("chunk_acc");
   }
   k_giant<Fq><<<ctx->sm_count * 2, GIANT_BLOCK, 0, st>>>(g, pstart, hist, partials, giant, giant + 1);

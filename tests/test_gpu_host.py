@@ -246,3 +246,20 @@ def test_two_phase_shuffle_matches_oracle(which, k, bits, pre, ctx_bls, ctx_bn):
     assert ctx.shuffle_verify(b"Shuffle", gx, hx, dG, dH, k, bits, proof2, cb2) is False
     # a proof for other commitments does not transfer
     assert ctx.shuffle_verify(b"Shuffle", gx, hx, dG, dH, k, bits, proof, cb2) is False
+
+
+def test_batch_verification_on_bn254_and_larger_circuits(bp, ctx_bn):
+    """bph_range_verify_batch beyond the config-5 shape: AMCL BN254, two committed values per proof (n = 16, lg = 4),
+    a batch that is not a multiple of anything, one tampered proof."""
+    ctx = ctx_bn
+    bits, m, count = 8, 2, 11
+    dG, dH = ctx.get_generators("G", m * bits), ctx.get_generators("H", m * bits)
+    gx, hx = ctx.g1_from_msg_hash(b"g"), ctx.g1_from_msg_hash(b"h")
+    values = [(29 * i + 3) % 256 for i in range(count * m)]
+    proofs, stride, comms = bp.range_prove_many([ctx], b"BatchBn", gx, hx, dG, dH, values, m, bits, seed=7)
+    assert bp.range_verify_many([ctx], b"BatchBn", gx, hx, dG, dH, count, m, bits, proofs, stride, comms) == [0] * count
+    assert bp.range_verify_batch(ctx, b"BatchBn", gx, hx, dG, dH, count, m, bits, proofs, stride, comms) == [0] * count
+    bad = bytearray(proofs)
+    bad[3 * stride + stride - 1] ^= 1              # the IPP's b of proof 3
+    assert bp.range_verify_batch(ctx, b"BatchBn", gx, hx, dG, dH, count, m, bits, bytes(bad), stride, comms, nthreads=2) == \
+        [0, 0, 0, -4] + [0] * (count - 4)
