@@ -44,6 +44,7 @@ SYMBOLS = [
     ("bpgpu_msm_parts_batch", _INT, [_VP, _VP, _VP, _SZ, _VP]),
     ("bpgpu_msm_batch_is_identity", _INT, [_VP, _VP, _SZ, _SZ, _VP, _VP, _VP, _SZ, _VP]),
     ("bpgpu_msm_window_bits", _INT, [_SZ]),
+    ("bpgpu_scalars_view", _INT, [_VP, _SZ, _SZ, _c.POINTER(_VP)]),
     ("bpgpu_fr_random", _INT, [_VP, _VP, _SZ, _c.c_uint64, _SZ, _c.POINTER(_VP)]),
     ("bpgpu_fixed_bases_create", _INT, [_VP, _VP, _SZ, _c.POINTER(_VP)]),
     ("bpgpu_fixed_bases_get", _INT, [_VP, _VP, _SZ, _c.POINTER(_VP)]),
@@ -265,6 +266,12 @@ class DeviceScalars:
         out = ctypes.create_string_buffer(max(1, n * self.ctx.modbytes))
         self.ctx._check(lib().bpgpu_scalars_download(self.ctx.handle, self.handle, off, n, out), "scalars_download")
         return out.raw[:n * self.ctx.modbytes]
+
+    def view(self, off, n):
+        """a second handle onto self[off:off+n]; the storage lives until the last handle is freed"""
+        h = ctypes.c_void_p()
+        self.ctx._check(lib().bpgpu_scalars_view(self.handle, off, n, ctypes.byref(h)), "scalars_view")
+        return DeviceScalars(self.ctx, h)
 
     def free(self):
         if self.handle:

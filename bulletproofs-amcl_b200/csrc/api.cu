@@ -530,8 +530,28 @@ size_t bpgpu_scalars_len(const bpgpu_scalars* s) { return s ? s->n : 0; }
 void bpgpu_scalars_free(bpgpu_scalars* s) {
   if (!s) return;
   cudaSetDevice(s->ctx->device);
-  dev_free(s->ctx, s->d);
+  if (s->blk) {
+    if (--s->blk->refs == 0) { dev_free(s->ctx, s->blk->base); delete s->blk; }
+  } else {
+    dev_free(s->ctx, s->d);
+  }
   delete s;
+}
+
+int bpgpu_scalars_view(bpgpu_scalars* s, size_t off, size_t n, bpgpu_scalars** out) {
+  if (!s || !out) return BPGPU_E_ARG;
+  *out = nullptr;
+  if (off > s->n || n > s->n - off) return BPGPU_E_LEN;
+  if (!s->blk) {                                   // first view: the allocation becomes shared, s holds one reference
+    s->blk = new (std::nothrow) bpgpu_shared_block{s->d, 1};
+    if (!s->blk) return BPGPU_E_CUDA;
+  }
+  bpgpu_scalars* v = new (std::nothrow) bpgpu_scalars();
+  if (!v) return BPGPU_E_CUDA;
+  v->ctx = s->ctx; v->d = (uint8_t*)s->d + off * 32; v->n = n; v->blk = s->blk;
+  s->blk->refs++;
+  *out = v;
+  return BPGPU_OK;
 }
 
 // ------------------------------------------------------------------ MSM

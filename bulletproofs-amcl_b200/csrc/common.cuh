@@ -92,10 +92,13 @@ struct bpgpu_points {
   size_t n;
   void* table = nullptr;   // optional window tables Affine<Fq>[n][64][15] (bpgpu_points_precompute, fixedbase.cu)
 };
+// a device allocation shared by several bpgpu_scalars handles (bpgpu_scalars_view): released with the last of them
+struct bpgpu_shared_block { void* base; int refs; };
 struct bpgpu_scalars {
   bpgpu_ctx* ctx;
   void* d;        // Fr[n] Montgomery
   size_t n;
+  bpgpu_shared_block* blk = nullptr;   // null: the handle owns d outright
 };
 
 namespace bp {

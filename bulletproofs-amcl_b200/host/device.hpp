@@ -2,6 +2,7 @@
 // /root/reference/src/ipp.rs:35-60, src/r1cs/prover.rs:322) as thin RAII handles over the C ABI of
 // include/bpgpu.h, plus the handful of group operations the host layer needs, all executed on the device.
 #pragma once
+#include <initializer_list>
 #include <utility>
 #include <vector>
 
@@ -65,6 +66,31 @@ class FieldElementVector {
     out->ctx_ = ctx;
     static const uint8_t dummy = 0;
     return bpgpu_scalars_upload(ctx, n ? be : &dummy, n, &out->h_);
+  }
+  // several host vectors in ONE upload (one copy, one conversion launch, one synchronisation), handed out as views
+  static int from_host_many(bpgpu_ctx* ctx, std::initializer_list<const std::vector<FieldElement<C>>*> vs,
+                            std::initializer_list<FieldElementVector*> outs) {
+    size_t total = 0;
+    for (auto v : vs) total += v->size();
+    std::vector<uint8_t> be(total * C::MODBYTES + 1);
+    size_t o = 0;
+    for (auto v : vs) for (const auto& x : *v) { x.to_bytes(be.data() + o * C::MODBYTES); o++; }
+    FieldElementVector all;
+    int rc = from_bytes(ctx, be.data(), total, &all);
+    if (rc) return rc;
+    o = 0;
+    auto out = outs.begin();
+    for (auto v : vs) {
+      if ((rc = all.view(o, v->size(), *out))) return rc;
+      o += v->size();
+      ++out;
+    }
+    return OK;
+  }
+  int view(size_t off, size_t n, FieldElementVector* out) {
+    out->reset();
+    out->ctx_ = ctx_;
+    return bpgpu_scalars_view(h_, off, n, &out->h_);
   }
   static FieldElementVector adopt(bpgpu_ctx* ctx, bpgpu_scalars* h) { FieldElementVector v; v.ctx_ = ctx; v.h_ = h; return v; }
   static FieldElementVector borrow(bpgpu_ctx* ctx, const bpgpu_scalars* h) { FieldElementVector v; v.ctx_ = ctx; v.h_ = const_cast<bpgpu_scalars*>(h); v.borrowed_ = true; return v; }

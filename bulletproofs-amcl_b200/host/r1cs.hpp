@@ -265,15 +265,12 @@ class Prover : public ConstraintSystem<C> {
     // polynomial kernels later.  s_L, s_R (:340-341) are DRAWN on the device (FieldElementVector::random as
     // bpgpu_fr_random: the same stream positions n1 + n1 host draws would use), so they never exist on the host.
     FieldElementVector<C> d_aL, d_aR, d_aO, d_sL, d_sR;
-    if ((rc = FieldElementVector<C>::from_host(ctx_, a_L_, &d_aL)) || (rc = FieldElementVector<C>::from_host(ctx_, a_R_, &d_aR)) ||
-        (rc = FieldElementVector<C>::from_host(ctx_, a_O_, &d_aO)))
-      return rc;
+    if ((rc = FieldElementVector<C>::from_host_many(ctx_, {&a_L_, &a_R_, &a_O_}, {&d_aL, &d_aR, &d_aO}))) return rc;
     {
-      bpgpu_scalars *hl = nullptr, *hr = nullptr;
-      if ((rc = rng_.fill_device(ctx_, n1, &hl))) return rc;                                    // :340
-      d_sL = FieldElementVector<C>::adopt(ctx_, hl);
-      if ((rc = rng_.fill_device(ctx_, n1, &hr))) return rc;                                    // :341
-      d_sR = FieldElementVector<C>::adopt(ctx_, hr);
+      bpgpu_scalars* hs = nullptr;                                     // s_L (:340) then s_R (:341): 2*n1 consecutive draws
+      if ((rc = rng_.fill_device(ctx_, 2 * n1, &hs))) return rc;
+      FieldElementVector<C> both = FieldElementVector<C>::adopt(ctx_, hs);
+      if ((rc = both.view(0, n1, &d_sL)) || (rc = both.view(n1, n1, &d_sR))) return rc;
     }
     tr.mark("witness upload + blindings");
     if ((rc = phase_commit_device(G, H, n1, d_aL, d_aR, d_aO, d_sL, d_sR, i_blinding1, o_blinding1, s_blinding1, &proof->A_I1, &proof->A_O1,
@@ -321,9 +318,7 @@ class Prover : public ConstraintSystem<C> {
 
     // l(x), r(x) coefficient vectors on the device (:458-486)
     FieldElementVector<C> d_wL, d_wR, d_wO;
-    if ((rc = FieldElementVector<C>::from_host(ctx_, wL, &d_wL)) || (rc = FieldElementVector<C>::from_host(ctx_, wR, &d_wR)) ||
-        (rc = FieldElementVector<C>::from_host(ctx_, wO, &d_wO)))
-      return rc;
+    if ((rc = FieldElementVector<C>::from_host_many(ctx_, {&wL, &wR, &wO}, {&d_wL, &d_wR, &d_wO}))) return rc;
     uint8_t yb[C::MODBYTES];
     y.to_bytes(yb);
     bpgpu_scalars *h_l1 = nullptr, *h_r0 = nullptr, *h_r1 = nullptr, *h_r3 = nullptr;
@@ -366,8 +361,9 @@ class Prover : public ConstraintSystem<C> {
     TP::commit_scalar(transcript_, "t_x_blinding", proof->t_x_blinding);
     TP::commit_scalar(transcript_, "e_blinding", proof->e_blinding);
     const FE w = TP::challenge_scalar(transcript_, "w");               // :549
-    G1<C> Q;
-    if ((rc = scalar_mul_fixed<C>(ctx_, g_, h_, w, &Q))) return rc;       // :550
+    // Q = g * w (:550) is handed to the IPP as the pair (g, w): with window tables the device never needs the point
+    // itself (c_L * Q = (c_L * w) * g), without them bpgpu_ipp_begin_fixed_q evaluates it once
+    const G1<C> Q = G1<C>::identity();
     // l_vec, r_vec (with padding), G_factors, H_factors on the device (:526-535, :552-563)
     uint8_t xb[C::MODBYTES], ub[C::MODBYTES];
     x.to_bytes(xb);

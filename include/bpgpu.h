@@ -90,6 +90,11 @@ size_t bpgpu_points_len(const bpgpu_points* p);
 void bpgpu_points_free(bpgpu_points* p);
 int bpgpu_scalars_upload(bpgpu_ctx* ctx, const uint8_t* be, size_t n, bpgpu_scalars** out);
 int bpgpu_scalars_download(bpgpu_ctx* ctx, const bpgpu_scalars* s, size_t off, size_t n, uint8_t* be);
+/* a second handle onto s[off .. off+n) (FieldElementVector::split_at without the copies, ipp.rs:70-73): the storage is
+ * reference counted and released when the last handle -- s or any view, in any order -- is freed.  Lets several vectors
+ * travel in ONE upload (one copy, one conversion launch, one synchronisation) and be handed out as separate vectors.
+ * Handles of one allocation must be freed from one thread at a time (as everything on a ctx). */
+int bpgpu_scalars_view(bpgpu_scalars* s, size_t off, size_t n, bpgpu_scalars** out);
 size_t bpgpu_scalars_len(const bpgpu_scalars* s);
 void bpgpu_scalars_free(bpgpu_scalars* s);
 

@@ -77,3 +77,25 @@ def test_device_random_vector_is_the_host_stream(which, ctx_bls, ctx_bn):
     assert a.download() != b.download()
     with pytest.raises(Exception):
         ctx.fr_random(b"k" * 65, 0, 1)
+
+
+def test_scalar_views_share_storage(ctx_bls):
+    """bpgpu_scalars_view: handles onto slices of one allocation, freed in any order."""
+    ctx = ctx_bls
+    C = curve_of(ctx)
+    vals = C.synth_scalars(12, 10)
+    s = ctx.upload_scalars(enc_scalars(C, vals))
+    a, b = s.view(0, 4), s.view(4, 6)
+    assert len(a) == 4 and len(b) == 6
+    s.free()                                            # the views keep the storage alive
+    assert dec_scalars(C, a.download()) == vals[:4]
+    c = b.view(1, 2)
+    b.free()
+    assert dec_scalars(C, c.download()) == vals[5:7]
+    out = ctx.fr_hadamard(c, c)
+    assert dec_scalars(C, out.download()) == [v * v % C.r for v in vals[5:7]]
+    a.free()
+    c.free()
+    out.free()
+    with pytest.raises(Exception):
+        ctx.upload_scalars(enc_scalars(C, vals)).view(8, 3)
