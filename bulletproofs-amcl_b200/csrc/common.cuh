@@ -171,6 +171,9 @@ __device__ __forceinline__ void canonicalise(F& x) {
 }
 
 int launch_check(bpgpu_ctx* ctx, const char* what);
+}  // namespace bp
+extern "C" int scalars_alloc_many(bpgpu_ctx* ctx, size_t n, int k, bpgpu_scalars** const* outs);   // frvec.cu
+namespace bp {
 
 // per-window sums an MSM leaves on the device: result = sum_w 2^(c*w) * winsum[w]
 // window w = P_w + 2^qshift * Q_w with P = d_winsum[0..W), Q = d_winsum[W..2W)

@@ -196,6 +196,31 @@ int bpgpu_scalars_alloc(bpgpu_ctx* ctx, size_t n, bpgpu_scalars** out) {
   return BPGPU_OK;
 }
 
+// k zeroed vectors of n elements carved out of ONE allocation (one pool request, one memset, one release with the last
+// handle) -- the four outputs of the R1CS polynomial kernels
+int scalars_alloc_many(bpgpu_ctx* ctx, size_t n, int k, bpgpu_scalars** const* outs) {
+  for (int i = 0; i < k; i++) *outs[i] = nullptr;
+  void* base = nullptr;
+  const size_t bytes = (size_t)k * n * 32;
+  if (dev_alloc(ctx, &base, bytes) != cudaSuccess) return BPGPU_E_CUDA;
+  if (cudaMemsetAsync(base, 0, bytes ? bytes : 16, ctx->stream) != cudaSuccess) { dev_free(ctx, base); return BPGPU_E_CUDA; }
+  bpgpu_shared_block* blk = new (std::nothrow) bpgpu_shared_block{base, 0};
+  if (!blk) { dev_free(ctx, base); return BPGPU_E_CUDA; }
+  for (int i = 0; i < k; i++) {
+    bpgpu_scalars* s = new (std::nothrow) bpgpu_scalars();
+    if (!s) {
+      for (int j = 0; j < i; j++) { delete *outs[j]; *outs[j] = nullptr; }
+      dev_free(ctx, base);
+      delete blk;
+      return BPGPU_E_CUDA;
+    }
+    s->ctx = ctx; s->d = (uint8_t*)base + (size_t)i * n * 32; s->n = n; s->blk = blk;
+    blk->refs++;
+    *outs[i] = s;
+  }
+  return BPGPU_OK;
+}
+
 int bpgpu_fr_vandermonde(bpgpu_ctx* ctx, const uint8_t* x_be, size_t n, bpgpu_scalars** out) {
   if (!ctx || !x_be || !out) return BPGPU_E_ARG;
   if (n >= (1ull << 32)) return BPGPU_E_ARG;

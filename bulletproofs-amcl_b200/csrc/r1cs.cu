@@ -271,9 +271,7 @@ int bpgpu_r1cs_prover_polys(bpgpu_ctx* ctx, size_t n, const bpgpu_scalars* a_L, 
   for (auto v : in) if (!srange(v, n)) return BPGPU_E_LEN;
   if (n >= (1ull << 31)) return BPGPU_E_ARG;
   bpgpu_scalars** outs[4] = {l1, r0, r1, r3};
-  for (auto o : outs) *o = nullptr;
-  int rc = BPGPU_OK;
-  for (auto o : outs) if (!rc) rc = bpgpu_scalars_alloc(ctx, n, o);
+  int rc = scalars_alloc_many(ctx, n, 4, outs);
   if (!rc)
     rc = ctx->curve == BPGPU_BLS12_381
              ? prover_polys_t<Bls>(ctx, n, a_L->d, a_R->d, s_R->d, wL->d, wR->d, wO->d, y_be, (*l1)->d, (*r0)->d, (*r1)->d, (*r3)->d)
@@ -291,9 +289,7 @@ int bpgpu_r1cs_prover_eval(bpgpu_ctx* ctx, size_t n, size_t n1, size_t padded_n,
   for (auto v : in) if (!srange(v, n)) return BPGPU_E_LEN;
   if (n > padded_n || n1 > n || padded_n >= (1ull << 31) || padded_n == 0) return BPGPU_E_ARG;
   bpgpu_scalars** outs[4] = {l_vec, r_vec, G_factors, H_factors};
-  for (auto o : outs) *o = nullptr;
-  int rc = BPGPU_OK;
-  for (auto o : outs) if (!rc) rc = bpgpu_scalars_alloc(ctx, padded_n, o);
+  int rc = scalars_alloc_many(ctx, padded_n, 4, outs);
   if (!rc)
     rc = ctx->curve == BPGPU_BLS12_381
              ? prover_eval_t<Bls>(ctx, n, n1, padded_n, l1->d, l2->d, l3->d, r0->d, r1->d, r3->d, x_be, u_be, y_be, (*l_vec)->d, (*r_vec)->d,
