@@ -177,6 +177,36 @@ __global__ void __launch_bounds__(FB_WINDOWS) k_fb_commit(const Affine<Fq>* __re
   if (w == 0) store_vec(out + inst, load_vec(sm));
 }
 
+// the same for a SMALL batch whose scalars arrive as kernel arguments: the 2 scalars of one commitment or the 10 of
+// T_1..T_6 need no staging copy and no conversion launch
+static const int FB_INLINE_SCALARS = 16;
+struct InlineScalars { ScalarInt s[FB_INLINE_SCALARS]; };
+template <class Fq>
+__global__ void __launch_bounds__(FB_WINDOWS) k_fb_commit_inline(const Affine<Fq>* __restrict__ table, int k, InlineScalars sc,
+                                                                 XYZZ<Fq>* __restrict__ out) {
+  __shared__ __align__(16) unsigned char smraw[FB_WINDOWS * sizeof(XYZZ<Fq>)];
+  XYZZ<Fq>* sm = reinterpret_cast<XYZZ<Fq>*>(smraw);
+  const int w = threadIdx.x;
+  const size_t inst = blockIdx.x;
+  XYZZ<Fq> acc = XYZZ<Fq>::inf();
+  for (int j = 0; j < k; j++) {
+    const uint32_t limb = sc.s[inst * k + j].v[w / TBL_PER_LIMB];
+    const uint32_t d = (limb >> ((w % TBL_PER_LIMB) * TBL_BITS)) & (uint32_t)TBL_DIGITS;
+    if (d) acc.madd(load_vec_ro(table + ((size_t)j * FB_WINDOWS + w) * FB_DIGITS + (d - 1)));
+  }
+  store_vec(sm + w, acc);
+  __syncthreads();
+  for (int o = FB_WINDOWS / 2; o > 0; o >>= 1) {
+    if (w < o) {
+      XYZZ<Fq> a = load_vec(sm + w), b = load_vec(sm + w + o);
+      a.add(b);
+      store_vec(sm + w, a);
+    }
+    __syncthreads();
+  }
+  if (w == 0) store_vec(out + inst, load_vec(sm));
+}
+
 // Builds the window tables of n affine points already on the device.  One-off: a 248-doubling chain per point (all
 // points in parallel), then 17 threads per (point, window) with 14 additions and one inversion each.
 template <class Curve>
@@ -349,9 +379,23 @@ static int fb_commit(bpgpu_fixed_bases* fb, const uint8_t* scalars_be, size_t co
   int rc;
   if ((rc = ctx->msm_c.reserve(ns * 32 + 32))) return rc;
   if ((rc = ctx->msm_e.reserve(count * sizeof(XYZZ<Fq>) + 32))) return rc;
-  if ((rc = scalars_from_host<Curve>(ctx, scalars_be, ns, 0, ctx->msm_c.p))) return rc;
-  k_fb_commit<Fq><<<(unsigned)count, FB_WINDOWS, 0, ctx->stream>>>((const Affine<Fq>*)fb->table, (int)fb->k, (const ScalarInt*)ctx->msm_c.p,
-                                                         (XYZZ<Fq>*)ctx->msm_e.p);
+  if (ns <= (size_t)FB_INLINE_SCALARS) {
+    // scalars on the ABI are canonical (< r), big endian, MODBYTES long: the low 32 bytes are the 8 limbs
+    InlineScalars sc;
+    memset(&sc, 0, sizeof sc);
+    for (size_t i = 0; i < ns; i++) {
+      const uint8_t* be = scalars_be + i * Curve::MODBYTES;
+      for (int k = 0; k < 8; k++) {
+        const uint8_t* p = be + Curve::MODBYTES - 4 * (k + 1);
+        sc.s[i].v[k] = ((uint32_t)p[0] << 24) | ((uint32_t)p[1] << 16) | ((uint32_t)p[2] << 8) | p[3];
+      }
+    }
+    k_fb_commit_inline<Fq><<<(unsigned)count, FB_WINDOWS, 0, ctx->stream>>>((const Affine<Fq>*)fb->table, (int)fb->k, sc, (XYZZ<Fq>*)ctx->msm_e.p);
+  } else {
+    if ((rc = scalars_from_host<Curve>(ctx, scalars_be, ns, 0, ctx->msm_c.p))) return rc;
+    k_fb_commit<Fq><<<(unsigned)count, FB_WINDOWS, 0, ctx->stream>>>((const Affine<Fq>*)fb->table, (int)fb->k, (const ScalarInt*)ctx->msm_c.p,
+                                                           (XYZZ<Fq>*)ctx->msm_e.p);
+  }
   ctx->launches++;
   if ((rc = launch_check(ctx, "k_fb_commit"))) return rc;
   const size_t bytes = count * sizeof(XYZZ<Fq>);

@@ -122,6 +122,19 @@ __device__ __forceinline__ Fr arg_to_mont(const FrArg& x) {
 }
 
 template <class Fr>
+__global__ void __launch_bounds__(128) k_ipp_init(uint32_t N, const Fr* __restrict__ a, const Fr* __restrict__ b, const Fr* __restrict__ Gf,
+                                                  const Fr* __restrict__ Hf, FrArg q, Fr* __restrict__ da, Fr* __restrict__ db,
+                                                  Fr* __restrict__ dG, Fr* __restrict__ dH, Fr* __restrict__ wq) {
+  const uint32_t i = blockIdx.x * blockDim.x + threadIdx.x;
+  if (i == 0) store_vec(wq, arg_to_mont<Fr>(q));
+  if (i >= N) return;
+  store_vec(da + i, load_vec(a + i));
+  store_vec(db + i, load_vec(b + i));
+  store_vec(dG + i, load_vec(Gf + i));
+  store_vec(dH + i, load_vec(Hf + i));
+}
+
+template <class Fr>
 __device__ __forceinline__ void fold_element(uint32_t i, uint32_t n_cur, const Fr& u, const Fr& ui, Fr* __restrict__ a, Fr* __restrict__ b,
                                              Fr* __restrict__ sG, Fr* __restrict__ sH, Fr* __restrict__ ab_out) {
   const uint32_t half = n_cur >> 1;
@@ -234,7 +247,8 @@ static int ipp_begin_t(bpgpu_ipp* st, const bpgpu_points* Gp, size_t goff, const
   int rc;
   const bool tables = Gp->table && Hp->table && q_base_xy && q_scalar_be;
   void* frs = nullptr;
-  BP_CUDA_OK(dev_alloc(ctx, &frs, (4 * N + 2 * (2 * N + 1) + 1) * sizeof(Fr)));
+  const size_t fr_count = 4 * N + 2 * (2 * N + 1) + 1;
+  BP_CUDA_OK(dev_alloc(ctx, &frs, fr_count * sizeof(Fr) + (tables ? (N + 1) * sizeof(uint32_t) : 0)));   // + the row lists (table mode)
   st->a = frs;
   st->b = (Fr*)frs + N;
   st->sG = (Fr*)frs + 2 * N;
@@ -249,8 +263,17 @@ static int ipp_begin_t(bpgpu_ipp* st, const bpgpu_points* Gp, size_t goff, const
     st->tG = (const uint8_t*)Gp->table + goff * TBL_ENTRIES * sizeof(Affine<Fq>);
     st->tH = (const uint8_t*)Hp->table + hoff * TBL_ENTRIES * sizeof(Affine<Fq>);
     st->wq = (Fr*)frs + 4 * N + 2 * (2 * N + 1);
-    if ((rc = scalars_from_host<Curve>(ctx, q_scalar_be, 1, 1, st->wq))) return rc;
-    BP_CUDA_OK(dev_alloc(ctx, &st->rows, (N + 1) * sizeof(uint32_t)));
+    st->rows = (Fr*)frs + fr_count;                       // same allocation: released with it
+    // one launch: the four vector clones of ipp.rs:57-60 and q_scalar (a kernel argument) in Montgomery form
+    FrArg qa;
+    for (int k = 0; k < 8; k++) {
+      const uint8_t* p = q_scalar_be + Curve::MODBYTES - 4 * (k + 1);
+      qa.v[k] = ((uint32_t)p[0] << 24) | ((uint32_t)p[1] << 16) | ((uint32_t)p[2] << 8) | p[3];
+    }
+    k_ipp_init<Fr><<<(unsigned)((N + 127) / 128), 128, 0, s>>>((uint32_t)N, (const Fr*)a, (const Fr*)b, (const Fr*)Gf, (const Fr*)Hf, qa, (Fr*)st->a,
+                                                               (Fr*)st->b, (Fr*)st->sG, (Fr*)st->sH, (Fr*)st->wq);
+    ctx->launches++;
+    return launch_check(ctx, "k_ipp_init");
   } else {
     const void* G = (const Affine<Fq>*)Gp->d + goff;
     const void* H = (const Affine<Fq>*)Hp->d + hoff;
@@ -518,8 +541,7 @@ void bpgpu_ipp_free(bpgpu_ipp* st) {
   if (!st) return;
   cudaSetDevice(st->ctx->device);
   dev_free(st->ctx, st->P);
-  dev_free(st->ctx, st->a);
-  dev_free(st->ctx, st->rows);
+  dev_free(st->ctx, st->a);                              // a, b, sG, sH, the scalar lists and the row lists: one allocation
   delete st;
 }
 
