@@ -9,8 +9,13 @@
 
 namespace bp {
 
+// Challenge-derived constants travel as KERNEL ARGUMENTS (2 KB of power table, up to four scalars): no staging buffer,
+// no host-to-device copy and no stream synchronisation around them
+template <class Fr> struct YTab { Fr t[64]; };       // y^(2^k) [32] | y^-(2^k) [32], Montgomery form
+template <class Fr> struct FrArgs4 { Fr a[4]; };
+
 template <class Fr>
-__device__ __forceinline__ Fr pow_tab(const Fr* __restrict__ pw, uint32_t e) {
+__device__ __forceinline__ Fr pow_tab(const Fr* pw, uint32_t e) {
   Fr acc = Fr::one();
   for (int k = 0; e; k++, e >>= 1)
     if (e & 1) acc = acc * pw[k];
@@ -20,12 +25,13 @@ __device__ __forceinline__ Fr pow_tab(const Fr* __restrict__ pw, uint32_t e) {
 // prover.rs:469-486 : l1 = a_L + y^-i * wR ; r0 = wO - y^i ; r1 = y^i * a_R + wL ; r3 = y^i * s_R
 // (l2 = a_O and l3 = s_L are the inputs themselves).  tab = y^(2^k) [32] | y^-(2^k) [32]
 template <class Fr>
-__global__ void __launch_bounds__(128) k_r1cs_polys(uint32_t n, const Fr* __restrict__ tab, const Fr* __restrict__ aL,
+__global__ void __launch_bounds__(128) k_r1cs_polys(uint32_t n, const __grid_constant__ YTab<Fr> ytab, const Fr* __restrict__ aL,
                                                     const Fr* __restrict__ aR, const Fr* __restrict__ sR, const Fr* __restrict__ wL,
                                                     const Fr* __restrict__ wR, const Fr* __restrict__ wO, Fr* __restrict__ l1,
                                                     Fr* __restrict__ r0, Fr* __restrict__ r1, Fr* __restrict__ r3) {
   uint32_t i = blockIdx.x * blockDim.x + threadIdx.x;
   if (i >= n) return;
+  const Fr* tab = ytab.t;
   Fr yi = pow_tab(tab, i), yinv = pow_tab(tab + 32, i);
   store_vec(l1 + i, load_vec(aL + i) + yinv * load_vec(wR + i));
   store_vec(r0 + i, load_vec(wO + i) - yi);
@@ -36,14 +42,15 @@ __global__ void __launch_bounds__(128) k_r1cs_polys(uint32_t n, const Fr* __rest
 // prover.rs:524-535,552-563 : l_vec = l(x) | 0^pad ; r_vec = r(x) | (-y^i)_{i >= n} ;
 // G_factors = 1^{n1} | u^{N-n1} ; H_factors[i] = y^-i * G_factors[i].   args = {x, u}
 template <class Fr>
-__global__ void __launch_bounds__(128) k_r1cs_eval(uint32_t n, uint32_t n1, uint32_t N, const Fr* __restrict__ tab,
-                                                   const Fr* __restrict__ args, const Fr* __restrict__ l1, const Fr* __restrict__ l2,
+__global__ void __launch_bounds__(128) k_r1cs_eval(uint32_t n, uint32_t n1, uint32_t N, const __grid_constant__ YTab<Fr> ytab,
+                                                   const __grid_constant__ FrArgs4<Fr> fargs, const Fr* __restrict__ l1, const Fr* __restrict__ l2,
                                                    const Fr* __restrict__ l3, const Fr* __restrict__ r0, const Fr* __restrict__ r1,
                                                    const Fr* __restrict__ r3, Fr* __restrict__ lvec, Fr* __restrict__ rvec,
                                                    Fr* __restrict__ Gf, Fr* __restrict__ Hf) {
   uint32_t i = blockIdx.x * blockDim.x + threadIdx.x;
   if (i >= N) return;
-  const Fr x = args[0], u = args[1];
+  const Fr* tab = ytab.t;
+  const Fr x = fargs.a[0], u = fargs.a[1];
   if (i < n) {
     // VecPoly3::eval (vector_poly.rs:99-106) with l.0 = 0 and r.2 = 0
     store_vec(lvec + i, x * (load_vec(l1 + i) + x * (load_vec(l2 + i) + x * load_vec(l3 + i))));
@@ -60,13 +67,14 @@ __global__ void __launch_bounds__(128) k_r1cs_eval(uint32_t n, uint32_t n1, uint
 // verifier.rs:341-390.  args = {x, a, b, u}.  Outputs gh = g_scalars[N] | h_scalars[N] and
 // ywr[i] = y^-i * wR[i] (i < n) for the delta inner product.  wL/wR/wO have length n.
 template <class Fr>
-__global__ void __launch_bounds__(128) k_r1cs_verifier_scalars(uint32_t n, uint32_t n1, uint32_t N, const Fr* __restrict__ tab,
-                                                               const Fr* __restrict__ args, const Fr* __restrict__ wL,
+__global__ void __launch_bounds__(128) k_r1cs_verifier_scalars(uint32_t n, uint32_t n1, uint32_t N, const __grid_constant__ YTab<Fr> ytab,
+                                                               const __grid_constant__ FrArgs4<Fr> fargs, const Fr* __restrict__ wL,
                                                                const Fr* __restrict__ wR, const Fr* __restrict__ wO,
                                                                const Fr* __restrict__ s, Fr* __restrict__ gh, Fr* __restrict__ ywr) {
   uint32_t i = blockIdx.x * blockDim.x + threadIdx.x;
   if (i >= N) return;
-  const Fr x = args[0], a = args[1], b = args[2], u = args[3];
+  const Fr* tab = ytab.t;
+  const Fr x = fargs.a[0], a = fargs.a[1], b = fargs.a[2], u = fargs.a[3];
   const Fr yinv = pow_tab(tab + 32, i);
   Fr wl = Fr::zero(), wr = Fr::zero(), wo = Fr::zero();
   if (i < n) { wl = load_vec(wL + i); wr = load_vec(wR + i); wo = load_vec(wO + i); }
@@ -79,30 +87,29 @@ __global__ void __launch_bounds__(128) k_r1cs_verifier_scalars(uint32_t n, uint3
   store_vec(gh + N + i, h);
 }
 
-// y^(2^k) | y^-(2^k), k < 32, in ctx->fr_pow
+// y^(2^k) | y^-(2^k), k < 32, computed on the host (one inversion, 62 squarings) into a by-value kernel argument.
+// Host and device share the limb radix and the Montgomery constant, so the host values are the device values.
 template <class Curve>
-static int ypow_tables(bpgpu_ctx* ctx, const uint8_t* y_be, typename Curve::Fr** tab) {
-  using Fr = typename Curve::Fr;
+static void ypow_tables(const uint8_t* y_be, YTab<typename Curve::Fr>* tab) {
   using HF = host::HFp<typename std::conditional<Curve::ID == BPGPU_BLS12_381, BlsFr, BnFr>::type>;
-  int rc = ctx->fr_pow2.reserve(64 * sizeof(Fr));
-  if (rc) return rc;
-  BP_CUDA_OK(stream_sync(ctx));
-  HF* stage = reinterpret_cast<HF*>(ctx->pinned + ctx->pinned_cap / 2);
+  static_assert(sizeof(HF) == sizeof(typename Curve::Fr), "same layout");
+  HF* out = reinterpret_cast<HF*>(tab->t);
   HF cur = HF::from_be(y_be, Curve::MODBYTES), cinv = cur.inv();
-  for (int k = 0; k < 32; k++) { stage[k] = cur; stage[32 + k] = cinv; cur = cur.sqr(); cinv = cinv.sqr(); }
-  BP_CUDA_OK(cudaMemcpyAsync(ctx->fr_pow2.p, stage, 64 * sizeof(Fr), cudaMemcpyHostToDevice, ctx->stream));
-  BP_CUDA_OK(stream_sync(ctx));
-  *tab = (Fr*)ctx->fr_pow2.p;
-  return BPGPU_OK;
+  for (int k = 0; k < 32; k++) { out[k] = cur; out[32 + k] = cinv; cur = cur.sqr(); cinv = cinv.sqr(); }
+}
+template <class Curve>
+static void fr_args_host(const uint8_t* be, int cnt, FrArgs4<typename Curve::Fr>* args) {
+  using HF = host::HFp<typename std::conditional<Curve::ID == BPGPU_BLS12_381, BlsFr, BnFr>::type>;
+  HF* out = reinterpret_cast<HF*>(args->a);
+  for (int k = 0; k < 4; k++) out[k] = k < cnt ? HF::from_be(be + (size_t)k * Curve::MODBYTES, Curve::MODBYTES) : HF::zero();
 }
 
 template <class Curve>
 static int prover_polys_t(bpgpu_ctx* ctx, size_t n, const void* aL, const void* aR, const void* sR, const void* wL, const void* wR,
                           const void* wO, const uint8_t* y_be, void* l1, void* r0, void* r1, void* r3) {
   using Fr = typename Curve::Fr;
-  Fr* tab;
-  int rc = ypow_tables<Curve>(ctx, y_be, &tab);
-  if (rc) return rc;
+  YTab<Fr> tab;
+  ypow_tables<Curve>(y_be, &tab);
   if (n) k_r1cs_polys<Fr><<<(unsigned)((n + 127) / 128), 128, 0, ctx->stream>>>((uint32_t)n, tab, (const Fr*)aL, (const Fr*)aR, (const Fr*)sR,
                                                                               (const Fr*)wL, (const Fr*)wR, (const Fr*)wO, (Fr*)l1, (Fr*)r0,
                                                                               (Fr*)r1, (Fr*)r3);
@@ -115,13 +122,13 @@ static int prover_eval_t(bpgpu_ctx* ctx, size_t n, size_t n1, size_t N, const vo
                          const void* r1, const void* r3, const uint8_t* x_be, const uint8_t* u_be, const uint8_t* y_be, void* lvec,
                          void* rvec, void* Gf, void* Hf) {
   using Fr = typename Curve::Fr;
-  Fr *tab, *args;
-  int rc = ypow_tables<Curve>(ctx, y_be, &tab);
-  if (rc) return rc;
+  YTab<Fr> tab;
+  FrArgs4<Fr> args;
+  ypow_tables<Curve>(y_be, &tab);
   uint8_t both[2 * 48];
   memcpy(both, x_be, Curve::MODBYTES);
   memcpy(both + Curve::MODBYTES, u_be, Curve::MODBYTES);
-  if ((rc = fr_args_upload<Curve>(ctx, both, 2, &args))) return rc;
+  fr_args_host<Curve>(both, 2, &args);
   k_r1cs_eval<Fr><<<(unsigned)((N + 127) / 128), 128, 0, ctx->stream>>>((uint32_t)n, (uint32_t)n1, (uint32_t)N, tab, args, (const Fr*)l1,
                                                                       (const Fr*)l2, (const Fr*)l3, (const Fr*)r0, (const Fr*)r1,
                                                                       (const Fr*)r3, (Fr*)lvec, (Fr*)rvec, (Fr*)Gf, (Fr*)Hf);
@@ -133,10 +140,10 @@ template <class Curve>
 static int verifier_scalars_t(bpgpu_ctx* ctx, size_t n, size_t n1, size_t N, const void* wL, const void* wR, const void* wO, const void* s,
                               const uint8_t* y_be, const uint8_t* xabu_be, void* gh, void* ywr) {
   using Fr = typename Curve::Fr;
-  Fr *tab, *args;
-  int rc = ypow_tables<Curve>(ctx, y_be, &tab);
-  if (rc) return rc;
-  if ((rc = fr_args_upload<Curve>(ctx, xabu_be, 4, &args))) return rc;
+  YTab<Fr> tab;
+  FrArgs4<Fr> args;
+  ypow_tables<Curve>(y_be, &tab);
+  fr_args_host<Curve>(xabu_be, 4, &args);
   k_r1cs_verifier_scalars<Fr><<<(unsigned)((N + 127) / 128), 128, 0, ctx->stream>>>((uint32_t)n, (uint32_t)n1, (uint32_t)N, tab, args,
                                                                                   (const Fr*)wL, (const Fr*)wR, (const Fr*)wO,
                                                                                   (const Fr*)s, (Fr*)gh, (Fr*)ywr);
