@@ -736,9 +736,7 @@ class Verifier : public ConstraintSystem<C> {
     tr.mark("ipp scalars");
     // g_scalars | h_scalars and delta on the device (:341-390)
     FieldElementVector<C> d_wL, d_wR, d_wO;
-    if ((rc = FieldElementVector<C>::from_host(ctx_, wL, &d_wL)) || (rc = FieldElementVector<C>::from_host(ctx_, wR, &d_wR)) ||
-        (rc = FieldElementVector<C>::from_host(ctx_, wO, &d_wO)))
-      return rc;
+    if ((rc = FieldElementVector<C>::from_host_many(ctx_, {&wL, &wR, &wO}, {&d_wL, &d_wR, &d_wO}))) return rc;
     uint8_t yb[C::MODBYTES], xb[C::MODBYTES], ab[C::MODBYTES], bb[C::MODBYTES], ub[C::MODBYTES], deltab[C::MODBYTES];
     y.to_bytes(yb); x.to_bytes(xb); a.to_bytes(ab); b.to_bytes(bb); u.to_bytes(ub);
     bpgpu_scalars* h_gh = nullptr;
