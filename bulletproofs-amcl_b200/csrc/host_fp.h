@@ -22,9 +22,8 @@ struct HFp {
   static constexpr int NL = P::N / 2;
   uint64_t v[NL];
 
-  static uint64_t limb(uint32_t (*f)(int), int i) { return (uint64_t)f(2 * i) | ((uint64_t)f(2 * i + 1) << 32); }
-  static uint64_t pl(int i) { return (uint64_t)P::P(2 * i) | ((uint64_t)P::P(2 * i + 1) << 32); }
-  static uint64_t inv64() {
+  static constexpr uint64_t pl(int i) { return (uint64_t)P::P(2 * i) | ((uint64_t)P::P(2 * i + 1) << 32); }
+  static constexpr uint64_t inv64() {
     // -p^-1 mod 2^64 by Newton iteration from the 32-bit constant
     uint64_t p0 = pl(0), x = (uint64_t)(0u - P::INV);  // x = p^-1 mod 2^32
     x *= 2 - p0 * x;                                    // mod 2^64
@@ -61,23 +60,29 @@ struct HFp {
   }
   HFp neg() const { return zero() - *this; }
   HFp dbl() const { return *this + *this; }
+  // CIOS Montgomery product; constants are compile-time, loops have constant bounds and are unrolled, so the NL + 1
+  // accumulator limbs stay in registers (mulx / adc chains with -march=x86-64-v3)
   friend HFp operator*(const HFp& a, const HFp& b) {
-    static const uint64_t INV = inv64();
-    uint64_t p[NL];
-    for (int i = 0; i < NL; i++) p[i] = pl(i);
-    uint64_t t[NL + 2];
-    memset(t, 0, sizeof t);
+    constexpr uint64_t INV = inv64();
+    uint64_t t[NL + 1] = {0};
+#pragma GCC unroll 8
     for (int i = 0; i < NL; i++) {
+      const uint64_t bi = b.v[i];
       unsigned __int128 c = 0;
-      for (int j = 0; j < NL; j++) { c += (unsigned __int128)a.v[j] * b.v[i] + t[j]; t[j] = (uint64_t)c; c >>= 64; }
-      c += t[NL]; t[NL] = (uint64_t)c; t[NL + 1] = (uint64_t)(c >> 64);
-      uint64_t m = t[0] * INV;
-      c = (unsigned __int128)m * p[0] + t[0]; c >>= 64;
-      for (int j = 1; j < NL; j++) { c += (unsigned __int128)m * p[j] + t[j]; t[j - 1] = (uint64_t)c; c >>= 64; }
-      c += t[NL]; t[NL - 1] = (uint64_t)c; t[NL] = t[NL + 1] + (uint64_t)(c >> 64);
+#pragma GCC unroll 8
+      for (int j = 0; j < NL; j++) { c += (unsigned __int128)a.v[j] * bi + t[j]; t[j] = (uint64_t)c; c >>= 64; }
+      c += t[NL];
+      const uint64_t tn = (uint64_t)c, top = (uint64_t)(c >> 64);
+      const uint64_t m = t[0] * INV;
+      c = (unsigned __int128)m * pl(0) + t[0]; c >>= 64;
+#pragma GCC unroll 8
+      for (int j = 1; j < NL; j++) { c += (unsigned __int128)m * pl(j) + t[j]; t[j - 1] = (uint64_t)c; c >>= 64; }
+      c += tn; t[NL - 1] = (uint64_t)c; t[NL] = top + (uint64_t)(c >> 64);
     }
     if (t[NL] || geq_p(t)) sub_p(t);
-    HFp r; memcpy(r.v, t, sizeof r.v);
+    HFp r;
+#pragma GCC unroll 8
+    for (int i = 0; i < NL; i++) r.v[i] = t[i];
     return r;
   }
   HFp sqr() const { return (*this) * (*this); }
