@@ -6,7 +6,7 @@ There is no CPU fallback: importing works anywhere (so the ABI can be inspected)
 a context without the built library or without a CUDA device raises.
 """
 from .binding import (BLS12_381, BN254, BpgpuError, Context, DevicePoints, DeviceScalars, build_library, lib,
-                      library_path, g1_sum, msm_sharded, range_prove_many, range_verify_batch, range_verify_many)
+                      library_path, g1_sum, msm_sharded, range_prove_batch, range_prove_many, range_verify_batch, range_verify_many)
 
 __all__ = ["BLS12_381", "BN254", "BpgpuError", "Context", "DevicePoints", "DeviceScalars", "build_library", "lib",
-           "library_path", "g1_sum", "msm_sharded", "range_prove_many", "range_verify_batch", "range_verify_many"]
+           "library_path", "g1_sum", "msm_sharded", "range_prove_batch", "range_prove_many", "range_verify_batch", "range_verify_many"]

@@ -44,6 +44,13 @@ SYMBOLS = [
     ("bpgpu_msm_parts_batch", _INT, [_VP, _VP, _VP, _SZ, _VP]),
     ("bpgpu_msm_batch_is_identity", _INT, [_VP, _VP, _SZ, _SZ, _VP, _VP, _VP, _SZ, _VP]),
     ("bpgpu_msm_window_bits", _INT, [_SZ]),
+    ("bpgpu_pbatch_create", _INT, [_VP, _VP, _VP, _VP, _VP, _SZ, _SZ, _c.POINTER(_VP)]),
+    ("bpgpu_pbatch_free", None, [_VP]),
+    ("bpgpu_pbatch_commit3", _INT, [_VP, _VP, _VP, _SZ, _VP, _VP, _VP]),
+    ("bpgpu_pbatch_polys", _INT, [_VP, _VP, _VP, _VP]),
+    ("bpgpu_pbatch_eval", _INT, [_VP, _VP]),
+    ("bpgpu_pbatch_ipp_round", _INT, [_VP, _VP, _VP]),
+    ("bpgpu_pbatch_ipp_finish", _INT, [_VP, _VP, _VP]),
     ("bpgpu_scalars_view", _INT, [_VP, _SZ, _SZ, _c.POINTER(_VP)]),
     ("bpgpu_fr_random", _INT, [_VP, _VP, _SZ, _c.c_uint64, _SZ, _c.POINTER(_VP)]),
     ("bpgpu_fixed_bases_create", _INT, [_VP, _VP, _SZ, _c.POINTER(_VP)]),
@@ -95,6 +102,7 @@ SYMBOLS_HOST = [
     ("bph_range_verify", _INT, [_VP, _CS, _VP, _VP, _VP, _VP, _SZ, _SZ, _VP, _SZ, _VP, _VP]),
     ("bph_range_proof_len", _SZ, [_INT, _SZ, _SZ]),
     ("bph_range_prove_many", _INT, [_VP, _SZ, _CS, _VP, _VP, _VP, _VP, _VP, _SZ, _SZ, _SZ, _INT, _U64, _VP, _SZ, _VP]),
+    ("bph_range_prove_batch", _INT, [_VP, _CS, _VP, _VP, _VP, _VP, _VP, _SZ, _SZ, _SZ, _INT, _U64, _SZ, _VP, _SZ, _VP]),
     ("bph_range_verify_batch", _INT, [_VP, _CS, _VP, _VP, _VP, _VP, _SZ, _SZ, _SZ, _VP, _SZ, _VP, _SZ, _VP]),
     ("bph_msm_sharded", _INT, [_VP, _SZ, _VP, _VP, _VP, _VP]),
     ("bph_g1_sum", _INT, [_INT, _VP, _SZ, _VP]),
@@ -132,6 +140,21 @@ def range_prove_many(ctxs, label, g_xy, h_xy, G, H, values, m, bits, seed=None):
     if rc:
         raise BpgpuError(rc, "range_prove_many")
     return proofs.raw[:count * stride], stride, comms.raw[:count * m * 2 * c0.modbytes]
+
+
+def range_prove_batch(ctx, label, g_xy, h_xy, G, H, values, m, bits, seed=None, nthreads=0):
+    """the same proofs as range_prove_many, proved in lock-step on ONE context (one device call per prover stage and IPP
+    round for the whole batch).  Returns (proofs bytes, stride, commitments bytes)."""
+    count = len(values) // m
+    stride = lib().bph_range_proof_len(ctx.curve, m, bits)
+    proofs = ctypes.create_string_buffer(max(1, count * stride))
+    comms = ctypes.create_string_buffer(max(1, count * m * 2 * ctx.modbytes))
+    arr = (ctypes.c_uint64 * max(1, len(values)))(*values)
+    rc = lib().bph_range_prove_batch(ctx.handle, label, _buf(g_xy), _buf(h_xy), G.handle, H.handle, ctypes.cast(arr, ctypes.c_void_p), count, m,
+                                     bits, 0 if seed is None else 1, seed or 0, nthreads, proofs, stride, comms)
+    if rc:
+        raise BpgpuError(rc, "range_prove_batch")
+    return proofs.raw[:count * stride], stride, comms.raw[:count * m * 2 * ctx.modbytes]
 
 
 def range_verify_many(ctxs, label, g_xy, h_xy, G, H, count, m, bits, proofs, stride, comms):

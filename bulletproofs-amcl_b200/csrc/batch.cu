@@ -14,52 +14,9 @@
 #include <stdlib.h>
 #include <string.h>
 
-#include "common.cuh"
+#include "batchsum.cuh"
 
 namespace bp {
-
-struct FixedRuns {
-  const void* table[TBL_MAX_SEGS];
-  uint32_t start[TBL_MAX_SEGS + 1];
-  int nruns;
-};
-
-template <class Curve>
-__global__ void __launch_bounds__(256) k_batch_fixed(FixedRuns runs, uint32_t F, const typename Curve::Fr* __restrict__ scal,
-                                                     XYZZ<typename Curve::Fq>* __restrict__ out) {
-  using Fq = typename Curve::Fq;
-  using Fr = typename Curve::Fr;
-  __shared__ __align__(16) unsigned char smraw[256 * sizeof(XYZZ<Fq>)];
-  XYZZ<Fq>* sm = reinterpret_cast<XYZZ<Fq>*>(smraw);
-  const size_t b = blockIdx.x;
-  const Fr* sc = scal + b * F;
-  XYZZ<Fq> acc = XYZZ<Fq>::inf();
-  for (uint32_t t = threadIdx.x; t < F * 8; t += blockDim.x) {
-    const uint32_t p = t >> 3, j = t & 7;
-    int rg = 0;
-    while (rg + 1 < runs.nruns && p >= runs.start[rg + 1]) rg++;
-    const uint32_t row = p - runs.start[rg];
-    const uint32_t limb = sc[p].v[j];                       // canonical scalars (not Montgomery)
-    if (!limb) continue;
-    const Affine<Fq>* tb = (const Affine<Fq>*)runs.table[rg] + ((size_t)row * TBL_WINDOWS + TBL_PER_LIMB * j) * TBL_DIGITS;
-#pragma unroll 1
-    for (int k = 0; k < TBL_PER_LIMB; k++) {
-      const uint32_t d = (limb >> (TBL_BITS * k)) & (uint32_t)TBL_DIGITS;
-      if (d) acc.madd(load_vec_ro(tb + k * TBL_DIGITS + (d - 1)));
-    }
-  }
-  store_vec(sm + threadIdx.x, acc);
-  __syncthreads();
-  for (int o = 128; o > 0; o >>= 1) {
-    if ((int)threadIdx.x < o) {
-      XYZZ<Fq> a = load_vec(sm + threadIdx.x), c = load_vec(sm + threadIdx.x + o);
-      a.add(c);
-      store_vec(sm + threadIdx.x, a);
-    }
-    __syncthreads();
-  }
-  if (threadIdx.x == 0) store_vec(out + b, load_vec(sm));
-}
 
 // the proof's own points: Straus with 4-bit windows (15 multiples per point, 64 windows), independent of the table geometry
 static const int VAR_WINDOWS = 64;
@@ -165,7 +122,7 @@ static int batch_identity_t(bpgpu_ctx* ctx, const FixedRuns& runs, uint32_t F, s
     static const bool prof = getenv("BPGPU_PROFILE") != nullptr;
     cudaEvent_t ev[3];
     if (prof) { for (auto& e : ev) cudaEventCreate(&e); cudaEventRecord(ev[0], ctx->stream); }
-    k_batch_fixed<Curve><<<(unsigned)cnt, 256, 0, ctx->stream>>>(runs, F, d_fs, d_sum);
+    k_batch_fixed<Curve><<<(unsigned)cnt, 256, 0, ctx->stream>>>(runs, F, d_fs, 0, d_sum);
     if (prof) cudaEventRecord(ev[1], ctx->stream);
     if (vn) {
       const size_t np = cnt * vn, nw = cnt * VAR_WINDOWS;

@@ -212,6 +212,11 @@ const void* fixed_table_lookup(bpgpu_ctx* ctx, const uint8_t* xy);
 int msm_mixed_to_host(bpgpu_ctx* ctx, const TableSeg* segs, int nsegs, const void* d_pts, const void* d_scal, bool mont, size_t n,
                       uint8_t* out_xy);
 
+// XYZZ points (device layout, read back to the host) -> affine X||Y big endian with one shared inversion (fixedbase.cu)
+void normalise_points_host(int curve, const uint8_t* xyzz_bytes, size_t count, uint8_t* out_xy);
+// one counter-mode stream per proof of a batch: out[b][i] = SHAKE256(keys[b] || le64(ctr0[b] + i)) mod r  (rng.cu)
+template <class Curve> int fr_random_batch_run(bpgpu_ctx* ctx, const uint8_t* d_keys, uint32_t klen, const uint64_t* d_ctr0, size_t batch, size_t n,
+                                               void* d_out);
 // host X||Y big-endian points -> device affine Montgomery (api.cu)
 template <class Curve> int points_from_host(bpgpu_ctx* ctx, const uint8_t* xy, size_t n, void* dst);
 // host big-endian scalars -> device Fr (Montgomery if mont) (api.cu)

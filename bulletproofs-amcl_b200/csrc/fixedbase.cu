@@ -344,6 +344,11 @@ void host_sum_partials(uint8_t* xyzz_bytes, int ngroups, int per) {
 template void host_sum_partials<BlsFq>(uint8_t*, int, int);
 template void host_sum_partials<BnFq>(uint8_t*, int, int);
 
+void normalise_points_host(int curve, const uint8_t* xyzz_bytes, size_t count, uint8_t* out_xy) {
+  if (curve == BPGPU_BLS12_381) normalise_batch_host<BlsFq>(xyzz_bytes, count, 48, out_xy);
+  else normalise_batch_host<BnFq>(xyzz_bytes, count, 32, out_xy);
+}
+
 }  // namespace bp
 namespace bp {
 int msm_tables_to_host(bpgpu_ctx* ctx, const TableSeg* segs, int nsegs, int ngroups, uint8_t* const* outs_xy) {

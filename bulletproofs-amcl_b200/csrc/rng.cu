@@ -49,19 +49,17 @@ __device__ void keccak_f1600_dev(uint64_t* a) {
 
 struct RngKey { uint8_t b[64]; uint32_t len; };
 
+// be_int(SHAKE256(key || le64(ctr))[..MODBYTES]) mod r, Montgomery form
 template <class Curve>
-__global__ void __launch_bounds__(128) k_fr_random(RngKey key, uint64_t ctr0, size_t n, typename Curve::Fr* __restrict__ out) {
+__device__ typename Curve::Fr fr_from_shake(const uint8_t* key, uint32_t klen, uint64_t ctr) {
   using Fr = typename Curve::Fr;
-  const size_t i = (size_t)blockIdx.x * blockDim.x + threadIdx.x;
-  if (i >= n) return;
   // SHAKE256 of one short block: msg || 0x1f .. 0x80 at the end of the 136-byte rate
   uint8_t m[136];
 #pragma unroll 1
   for (int k = 0; k < 136; k++) m[k] = 0;
-  uint32_t len = key.len;
+  uint32_t len = klen;
 #pragma unroll 1
-  for (uint32_t k = 0; k < len; k++) m[k] = key.b[k];
-  const uint64_t ctr = ctr0 + i;
+  for (uint32_t k = 0; k < len; k++) m[k] = key[k];
 #pragma unroll 1
   for (int k = 0; k < 8; k++) m[len + k] = (uint8_t)(ctr >> (8 * k));
   len += 8;
@@ -93,8 +91,36 @@ __global__ void __launch_bounds__(128) k_fr_random(RngKey key, uint64_t ctr0, si
     for (int k = 8; k < MB / 4; k++) hi.v[k - 8] = limbs[k];
     res = res + (hi * Fr::r2()) * Fr::r2();
   }
-  store_vec(out + i, res);
+  return res;
 }
+
+template <class Curve>
+__global__ void __launch_bounds__(128) k_fr_random(RngKey key, uint64_t ctr0, size_t n, typename Curve::Fr* __restrict__ out) {
+  const size_t i = (size_t)blockIdx.x * blockDim.x + threadIdx.x;
+  if (i >= n) return;
+  store_vec(out + i, fr_from_shake<Curve>(key.b, key.len, ctr0 + i));
+}
+
+// one stream per proof of a batch (blockIdx.y): keys = batch x 64 bytes (device), out = batch x n
+template <class Curve>
+__global__ void __launch_bounds__(128) k_fr_random_batch(const uint8_t* __restrict__ keys, uint32_t klen, const uint64_t* __restrict__ ctr0,
+                                                         size_t n, typename Curve::Fr* __restrict__ out) {
+  const size_t i = (size_t)blockIdx.x * blockDim.x + threadIdx.x;
+  if (i >= n) return;
+  const size_t b = blockIdx.y;
+  store_vec(out + b * n + i, fr_from_shake<Curve>(keys + b * 64, klen, ctr0[b] + i));
+}
+
+template <class Curve>
+int fr_random_batch_run(bpgpu_ctx* ctx, const uint8_t* d_keys, uint32_t klen, const uint64_t* d_ctr0, size_t batch, size_t n, void* d_out) {
+  if (!batch || !n) return BPGPU_OK;
+  k_fr_random_batch<Curve><<<dim3((unsigned)((n + 127) / 128), (unsigned)batch), 128, 0, ctx->stream>>>(d_keys, klen, d_ctr0, n,
+                                                                                                        (typename Curve::Fr*)d_out);
+  ctx->launches++;
+  return launch_check(ctx, "k_fr_random_batch");
+}
+template int fr_random_batch_run<Bls>(bpgpu_ctx*, const uint8_t*, uint32_t, const uint64_t*, size_t, size_t, void*);
+template int fr_random_batch_run<Bn>(bpgpu_ctx*, const uint8_t*, uint32_t, const uint64_t*, size_t, size_t, void*);
 
 }  // namespace bp
 

@@ -8,6 +8,7 @@
 
 #include "../../include/bphost.h"
 #include "gadgets.hpp"
+#include "prove_batch.hpp"
 
 using namespace bph;
 
@@ -282,6 +283,32 @@ int range_verify_batch_t(bpgpu_ctx* ctx, const char* label, const uint8_t* g_xy,
   return BPGPU_OK;
 }
 
+template <class C>
+int range_prove_batch_t(bpgpu_ctx* ctx, const char* label, const uint8_t* g_xy, const uint8_t* h_xy, bpgpu_points* G, bpgpu_points* H,
+                        const uint64_t* values, size_t count, size_t m, size_t bits, int rng_mode, uint64_t seed, size_t nthreads,
+                        uint8_t* proofs, size_t stride, uint8_t* comms_xy) {
+  const size_t SLAB = 1024;
+  const size_t B = count < SLAB ? count : SLAB;
+  if (nthreads == 0) nthreads = std::thread::hardware_concurrency();
+  if (nthreads == 0) nthreads = 1;
+  bpgpu_pbatch* pb = nullptr;
+  int rc = bpgpu_pbatch_create(ctx, G, H, g_xy, h_xy, B, m * bits, &pb);
+  if (rc) return rc;
+  const G1<C> g = G1<C>::from_xy(g_xy), h = G1<C>::from_xy(h_xy);
+  for (size_t lo = 0; lo < count && !rc; lo += B) {
+    size_t cnt = count - lo < B ? count - lo : B;
+    if (cnt != B) {                                   // last, shorter slab: its own handle (the scratch layout depends on B)
+      bpgpu_pbatch_free(pb);
+      pb = nullptr;
+      if ((rc = bpgpu_pbatch_create(ctx, G, H, g_xy, h_xy, cnt, m * bits, &pb))) break;
+    }
+    rc = BatchProverAccess<C>::prove_slab(ctx, pb, label, g, h, values + lo * m, cnt, m, bits, rng_mode, seed + lo, nthreads, proofs + lo * stride,
+                                          stride, comms_xy + lo * m * 2 * C::MODBYTES);
+  }
+  bpgpu_pbatch_free(pb);
+  return rc;
+}
+
 template <class FqP>
 void g1_sum_host(const uint8_t* xy, size_t count, int mb, uint8_t* out) {
   using HP = bp::host::HXYZZ<FqP>;
@@ -465,6 +492,17 @@ int bph_range_verify_many(bpgpu_ctx* const* ctxs, size_t nctx, const char* label
     return 0;
   });
   return BPGPU_OK;
+}
+
+int bph_range_prove_batch(bpgpu_ctx* ctx, const char* label, const uint8_t* g_xy, const uint8_t* h_xy, bpgpu_points* G, bpgpu_points* H,
+                          const uint64_t* values, size_t count, size_t m, size_t bits, int rng_mode, uint64_t seed, size_t nthreads,
+                          uint8_t* proofs, size_t proof_stride, uint8_t* comms_xy) {
+  if (!ctx || !label || !g_xy || !h_xy || !G || !H || (count && (!values || !proofs || !comms_xy)) || !m || !bits || bits > 64) return BPGPU_E_ARG;
+  if (proof_stride < bph_range_proof_len(bpgpu_ctx_curve(ctx), m, bits)) return BPH_E_BUFFER;
+  if (count == 0) return BPGPU_OK;
+#define CALL(C) range_prove_batch_t<C>(ctx, label, g_xy, h_xy, G, H, values, count, m, bits, rng_mode, seed, nthreads, proofs, proof_stride, comms_xy)
+  return BY_CURVE(ctx, CALL);
+#undef CALL
 }
 
 int bph_g1_sum(int curve, const uint8_t* points_xy, size_t count, uint8_t* out_xy) {

@@ -159,6 +159,11 @@ class Rng {
     shake256(m, key_len_ + 8, out, sizeof out);
     return FieldElement<C>::from_bytes(out);
   }
+  // stream position, for callers that generate a run of draws elsewhere (the batched prover's device kernels)
+  const uint8_t* key() const { return key_; }
+  size_t key_len() const { return key_len_; }
+  uint64_t counter() const { return ctr_; }
+  void skip(uint64_t n) { ctr_ += n; }
   // the next n draws as a device-resident vector (FieldElementVector::random); *out is owned by the caller
   int fill_device(bpgpu_ctx* ctx, size_t n, bpgpu_scalars** out) {
     int rc = bpgpu_fr_random(ctx, key_, key_len_, ctr_, n, out);

@@ -159,8 +159,11 @@ struct R1CSProof {
 inline size_t next_power_of_two(size_t n) { size_t p = 1; while (p < n) p <<= 1; return p; }   // usize::next_power_of_two (0 -> 1)
 
 // ---- prover.rs ---------------------------------------------------------------------------------------
+template <class C> struct BatchProverAccess;    // prove_batch.hpp: the lock-step batched prover drives these stages itself
+
 template <class C>
 class Prover : public ConstraintSystem<C> {
+  friend struct BatchProverAccess<C>;
  public:
   using FE = FieldElement<C>;
   using LC = LinearCombination<C>;
@@ -198,6 +201,15 @@ class Prover : public ConstraintSystem<C> {
       TP::commit_point(transcript_, "V", (*V)[j]);
     }
     return OK;
+  }
+
+  // commit (prover.rs:119-129) with the commitment point already evaluated (a batch evaluates them all in one call)
+  Variable commit_precomputed(const FE& v, const FE& v_blinding, const G1<C>& V) {
+    Variable var = Variable::committed(v_.size());
+    v_.push_back(v);
+    v_blinding_.push_back(v_blinding);
+    TP::commit_point(transcript_, "V", V);
+    return var;
   }
 
   size_t num_constraints() const { return constraints_.size(); }     // prover.rs:595-597

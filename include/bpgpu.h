@@ -181,6 +181,29 @@ int bpgpu_fr_batch_invert(bpgpu_ctx* ctx, const bpgpu_scalars* a, size_t aoff, s
  * key_len <= 64.  The vector never exists on the host. */
 int bpgpu_fr_random(bpgpu_ctx* ctx, const uint8_t* key, size_t key_len, uint64_t ctr0, size_t n, bpgpu_scalars** out);
 
+/* ---- lock-step proving of a BATCH of independent one-phase R1CS proofs of one shape (n multipliers; csrc/provebatch.cu) ----
+ * Every stage of Prover::prove (prover.rs:322-593) and every round of IPP::create_ipp (ipp.rs:68-194) is ONE device call
+ * for all `batch` proofs; the caller runs the transcripts in between (host/prove_batch.hpp is that caller).  G and H get
+ * window tables (bpgpu_points_precompute); g, h are the Pedersen pair.  All scalar arguments are big endian, MODBYTES
+ * each, proof-major:
+ *   commit3   : witness = batch x [a_L | a_R | a_O] (3n), keys = batch x key_len bytes and ctr0[batch] = where each proof's
+ *               blinding stream stands (s_L, s_R = the next 2n draws, made on the device as by bpgpu_fr_random),
+ *               blind = batch x [i_b, o_b, s_b]; out = batch x [A_I, A_O, S]
+ *   polys     : weights = batch x [wL | wR | wO] (3n), y[batch]; out t = batch x [t_1 .. t_6]
+ *   eval      : xuw = batch x [x, u, w] -> l_vec, r_vec, G_factors, H_factors become the IPP state (Q = w * g)
+ *   ipp_round : uv = batch x [u, u^-1] of the previous round (NULL for the first); out = batch x [L, R]
+ *   ipp_finish: uv of the last round; out = batch x [a, b] */
+typedef struct bpgpu_pbatch bpgpu_pbatch;
+int bpgpu_pbatch_create(bpgpu_ctx* ctx, bpgpu_points* G, bpgpu_points* H, const uint8_t* g_xy, const uint8_t* h_xy, size_t batch, size_t n,
+                        bpgpu_pbatch** out);
+void bpgpu_pbatch_free(bpgpu_pbatch* pb);
+int bpgpu_pbatch_commit3(bpgpu_pbatch* pb, const uint8_t* witness_be, const uint8_t* keys, size_t key_len, const uint64_t* ctr0,
+                         const uint8_t* blind_be, uint8_t* out_xy);
+int bpgpu_pbatch_polys(bpgpu_pbatch* pb, const uint8_t* weights_be, const uint8_t* y_be, uint8_t* t_be);
+int bpgpu_pbatch_eval(bpgpu_pbatch* pb, const uint8_t* xuw_be);
+int bpgpu_pbatch_ipp_round(bpgpu_pbatch* pb, const uint8_t* uv_be, uint8_t* out_xy);
+int bpgpu_pbatch_ipp_finish(bpgpu_pbatch* pb, const uint8_t* uv_be, uint8_t* ab_be);
+
 /* ---- inner-product argument, device-resident across rounds (IPP::create_ipp, ipp.rs:35-202) ----
  * begin: clones G[goff..goff+n), H[hoff..), a, b and the factor vectors (ipp.rs:57-60); n must be a power
  *        of two (BPGPU_E_NOT_POW2 = the assert at ipp.rs:48) and all vectors length n (BPGPU_E_LEN).

@@ -95,6 +95,14 @@ int bph_range_verify_batch(bpgpu_ctx* ctx, const char* transcript_label, const u
                            bpgpu_points* H, size_t count, size_t m, size_t bits, const uint8_t* proofs, size_t proof_stride,
                            const uint8_t* comms_xy, size_t nthreads, int32_t* verdicts);
 
+/* `count` independent range proofs (m x `bits`-bit values each) proved in LOCK-STEP on one context (bpgpu_pbatch_*): one
+ * device call per prover stage and per IPP round for a whole slab of proofs, the transcripts on `nthreads` host threads
+ * (0 = all cores) in between.  Same arguments and same bytes as bph_range_prove_many (proof i uses seed + i); G and H get
+ * window tables on first use.  For small circuits proved in bulk, where a proof of its own is bound by launch latency. */
+int bph_range_prove_batch(bpgpu_ctx* ctx, const char* transcript_label, const uint8_t* g_xy, const uint8_t* h_xy, bpgpu_points* G,
+                          bpgpu_points* H, const uint64_t* values, size_t count, size_t m, size_t bits, int rng_mode, uint64_t seed,
+                          size_t nthreads, uint8_t* proofs, size_t proof_stride, uint8_t* comms_xy);
+
 /* ---- a TWO-PHASE circuit: k-shuffle ({y} is a permutation of {x}) over 2k committed values, x[0] range-checked to `bits`
  * bits in the first phase (0 = none).  The gadget is the example of the reference's ConstraintSystem documentation
  * (constraint_system.rs:86-135); it exercises specify_randomized_constraints, the challenge drawn between the phases and

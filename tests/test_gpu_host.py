@@ -263,3 +263,27 @@ def test_batch_verification_on_bn254_and_larger_circuits(bp, ctx_bn):
     bad[3 * stride + stride - 1] ^= 1              # the IPP's b of proof 3
     assert bp.range_verify_batch(ctx, b"BatchBn", gx, hx, dG, dH, count, m, bits, bytes(bad), stride, comms, nthreads=2) == \
         [0, 0, 0, -4] + [0] * (count - 4)
+
+
+@pytest.mark.parametrize("which,m,bits,count", [("bls", 1, 8, 9), ("bn", 2, 8, 5), ("bls", 3, 5, 4), ("bls", 1, 64, 3)])
+def test_lock_step_batch_prover_equals_single_proofs(which, m, bits, count, bp, ctx_bls, ctx_bn):
+    """bph_range_prove_batch: every stage of the prover and every IPP round as ONE device call for the whole batch.  Proof i
+    must be byte-identical to the single-context proof with seed + i (which is itself oracle-checked), also for a padded
+    circuit (n = 15 -> 16), and the batch verifier accepts them."""
+    ctx = ctx_bls if which == "bls" else ctx_bn
+    n = m * bits
+    N = 1 << max(0, (n - 1).bit_length())
+    dG, dH = ctx.get_generators("G", N), ctx.get_generators("H", N)
+    gx, hx = ctx.g1_from_msg_hash(b"g"), ctx.g1_from_msg_hash(b"h")
+    values = [(0x9E3779B97F4A7C15 * (i + 1)) % (1 << bits) for i in range(count * m)]
+    ref_p, stride, ref_c = bp.range_prove_many([ctx], b"Batch", gx, hx, dG, dH, values, m, bits, seed=300)
+    got_p, stride2, got_c = bp.range_prove_batch(ctx, b"Batch", gx, hx, dG, dH, values, m, bits, seed=300, nthreads=3)
+    assert stride2 == stride
+    assert got_c == ref_c
+    for i in range(count):
+        assert got_p[i * stride:(i + 1) * stride] == ref_p[i * stride:(i + 1) * stride], i
+    assert bp.range_verify_batch(ctx, b"Batch", gx, hx, dG, dH, count, m, bits, got_p, stride, got_c) == [0] * count
+    # OS-entropy blindings: proofs differ from run to run and verify
+    p1, _, c1 = bp.range_prove_batch(ctx, b"Batch", gx, hx, dG, dH, values, m, bits)
+    assert p1 != got_p
+    assert bp.range_verify_many([ctx], b"Batch", gx, hx, dG, dH, count, m, bits, p1, stride, c1) == [0] * count
