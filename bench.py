@@ -163,7 +163,20 @@ def proof_section(bp, ctx, local, rank, world, dist, torch, no_cpu=False):
             v = bp.range_verify_many(ctxs, b"bench", gx, hx, G, H, count, m, bits, proofs, stride, comms)
             ok = ok and v == [0] * count
         tv = time.perf_counter() - t0
-        tb = None
+        tb = tpb = None
+        if batch_call:
+            # the same statement proved in lock-step on ONE context (bph_range_prove_batch): every prover stage and IPP round
+            # is one device call for the whole batch, the transcripts run on the host threads in between
+            nb = count * verify_reps
+            bvals = [int(x) for x in rng.integers(0, 1 << 63, size=nb * m, dtype=np.uint64)]
+            bp.range_prove_batch(c0, b"bench", gx, hx, G, H, bvals, m, bits)                                   # warm-up (scratch sized)
+            if dist is not None:
+                dist.barrier()
+            t0 = time.perf_counter()
+            bproofs, bstride, bcomms = bp.range_prove_batch(c0, b"bench", gx, hx, G, H, bvals, m, bits)
+            tpb = time.perf_counter() - t0
+            v = bp.range_verify_batch(c0, b"bench", gx, hx, G, H, nb, m, bits, bproofs, bstride, bcomms)
+            ok = ok and v == [0] * nb
         if batch_call:
             # config 5: the whole batch through bph_range_verify_batch: host threads build the scalars slab by slab, the
             # device evaluates every proof's verification MSM of a slab in one group of launches (one verdict byte per
@@ -183,10 +196,11 @@ def proof_section(bp, ctx, local, rank, world, dist, torch, no_cpu=False):
             allv = torch.empty(world * count, dtype=torch.uint8, device="cuda")
             dist.all_gather_into_tensor(allv, t)
             ok = bool(allv.min().item() == 1)
-            tt = torch.tensor([tp, tv, tb or 0.0], device="cuda", dtype=torch.float64)
+            tt = torch.tensor([tp, tv, tb or 0.0, tpb or 0.0], device="cuda", dtype=torch.float64)
             dist.all_reduce(tt, op=dist.ReduceOp.MAX)
             tp, tv = float(tt[0].item()), float(tt[1].item())
             tb = float(tt[2].item()) if tb is not None else None
+            tpb = float(tt[3].item()) if tpb is not None else None
         for c in ctxs:
             c.close()
         out[tag] = {"multipliers": n, "committed_values": m, "proofs": count * world, "prove_per_s": count * world / tp,
@@ -194,6 +208,8 @@ def proof_section(bp, ctx, local, rank, world, dist, torch, no_cpu=False):
                     "prove_verify_per_s": count * world / (tp + tv / verify_reps), "all_verified": ok, "proof_bytes": stride}
         if tb is not None:
             out[tag]["verify_batch_call_per_s"] = count * world * verify_reps / tb
+        if tpb is not None:
+            out[tag]["prove_batch_call_per_s"] = count * world * verify_reps / tpb
         if cpu_base and rank == 0 and world == 1:
             # the reference's algorithm for the same proof on the host cores (oracle/fast.py: ipp.rs / prover.rs /
             # verifier.rs restated, group operations in oracle/c), one independent proof stream per core

@@ -122,7 +122,7 @@ static int batch_identity_t(bpgpu_ctx* ctx, const FixedRuns& runs, uint32_t F, s
     static const bool prof = getenv("BPGPU_PROFILE") != nullptr;
     cudaEvent_t ev[3];
     if (prof) { for (auto& e : ev) cudaEventCreate(&e); cudaEventRecord(ev[0], ctx->stream); }
-    k_batch_fixed<Curve><<<(unsigned)cnt, 256, 0, ctx->stream>>>(runs, F, d_fs, 0, d_sum);
+    k_batch_fixed<Curve><<<(unsigned)cnt, BATCH_FIXED_THREADS, 0, ctx->stream>>>(runs, F, d_fs, 0, d_sum);
     if (prof) cudaEventRecord(ev[1], ctx->stream);
     if (vn) {
       const size_t np = cnt * vn, nw = cnt * VAR_WINDOWS;

@@ -6,6 +6,10 @@
 
 namespace bp {
 
+// 128 threads per row: 8 table lookups per (term, limb) item and a 7-level tree -- two to three blocks fit an SM, and a
+// thread spends more of its time adding table entries than waiting in the tree (256 threads: one block per SM, 8 levels)
+static const int BATCH_FIXED_THREADS = 128;
+
 struct FixedRuns {
   const void* table[TBL_MAX_SEGS];
   uint32_t start[TBL_MAX_SEGS + 1];
@@ -13,16 +17,19 @@ struct FixedRuns {
 };
 
 template <class Curve>
-__global__ void __launch_bounds__(256) k_batch_fixed(FixedRuns runs, uint32_t F, const typename Curve::Fr* __restrict__ scal, int mont,
+__global__ void __launch_bounds__(BATCH_FIXED_THREADS) k_batch_fixed(FixedRuns runs, uint32_t F, const typename Curve::Fr* __restrict__ scal, int mont,
                                                      XYZZ<typename Curve::Fq>* __restrict__ out) {
   using Fq = typename Curve::Fq;
   using Fr = typename Curve::Fr;
-  __shared__ __align__(16) unsigned char smraw[256 * sizeof(XYZZ<Fq>)];
+  __shared__ __align__(16) unsigned char smraw[BATCH_FIXED_THREADS * sizeof(XYZZ<Fq>)];
   XYZZ<Fq>* sm = reinterpret_cast<XYZZ<Fq>*>(smraw);
   const size_t b = blockIdx.x;
   const Fr* sc = scal + b * F;
   XYZZ<Fq> acc = XYZZ<Fq>::inf();
-  for (uint32_t t = threadIdx.x; t < F * 8; t += blockDim.x) {
+  // long rows are cut into gridDim.y term ranges (one block each; the caller adds the gridDim.y sums of a row)
+  const uint32_t per = (F + gridDim.y - 1) / gridDim.y;
+  const uint32_t p_lo = blockIdx.y * per, p_hi = min(F, p_lo + per);
+  for (uint32_t t = p_lo * 8 + threadIdx.x; t < p_hi * 8; t += blockDim.x) {
     const uint32_t p = t >> 3, j = t & 7;
     int rg = 0;
     while (rg + 1 < runs.nruns && p >= runs.start[rg + 1]) rg++;
@@ -39,7 +46,7 @@ __global__ void __launch_bounds__(256) k_batch_fixed(FixedRuns runs, uint32_t F,
   }
   store_vec(sm + threadIdx.x, acc);
   __syncthreads();
-  for (int o = 128; o > 0; o >>= 1) {
+  for (int o = BATCH_FIXED_THREADS / 2; o > 0; o >>= 1) {
     if ((int)threadIdx.x < o) {
       XYZZ<Fq> a = load_vec(sm + threadIdx.x), c = load_vec(sm + threadIdx.x + o);
       a.add(c);
@@ -47,8 +54,19 @@ __global__ void __launch_bounds__(256) k_batch_fixed(FixedRuns runs, uint32_t F,
     }
     __syncthreads();
   }
-  if (threadIdx.x == 0) store_vec(out + b, load_vec(sm));
+  if (threadIdx.x == 0) store_vec(out + b * gridDim.y + blockIdx.y, load_vec(sm));
 }
 
+
+
+// out[r] = sum of the `splits` partial sums of row r (in place at parts[r * splits])
+template <class Fq>
+__global__ void __launch_bounds__(64) k_batch_fixed_combine(uint32_t rows, uint32_t splits, XYZZ<Fq>* __restrict__ parts, XYZZ<Fq>* __restrict__ out) {
+  const uint32_t r = blockIdx.x * blockDim.x + threadIdx.x;
+  if (r >= rows) return;
+  XYZZ<Fq> acc = load_vec(parts + (size_t)r * splits);
+  for (uint32_t k = 1; k < splits; k++) { XYZZ<Fq> q = load_vec(parts + (size_t)r * splits + k); acc.add(q); }
+  store_vec(out + r, acc);
+}
 
 }  // namespace bp

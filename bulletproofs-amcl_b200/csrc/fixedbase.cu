@@ -8,6 +8,7 @@
 // the table T[j][w][d-1] = d * 2^(8w) * B_j (w < 32, d = 1..255, affine) turns every later commitment into a sum of
 // <= 32k table entries, reduced by a block-wide tree: no doublings, one launch for a whole batch.
 #include <string.h>
+#include <thread>
 
 #include "common.cuh"
 #include "host_fp.h"
@@ -344,9 +345,28 @@ void host_sum_partials(uint8_t* xyzz_bytes, int ngroups, int per) {
 template void host_sum_partials<BlsFq>(uint8_t*, int, int);
 template void host_sum_partials<BnFq>(uint8_t*, int, int);
 
+// large batches (the lock-step prover reads back thousands of sums per stage) are cut into chunks of >= 128 points, one
+// host thread and one inversion each
 void normalise_points_host(int curve, const uint8_t* xyzz_bytes, size_t count, uint8_t* out_xy) {
-  if (curve == BPGPU_BLS12_381) normalise_batch_host<BlsFq>(xyzz_bytes, count, 48, out_xy);
-  else normalise_batch_host<BnFq>(xyzz_bytes, count, 32, out_xy);
+  const size_t mb = curve == BPGPU_BLS12_381 ? 48 : 32;
+  const size_t psz = curve == BPGPU_BLS12_381 ? sizeof(XYZZ<Bls::Fq>) : sizeof(XYZZ<Bn::Fq>);
+  auto run = [&](size_t lo, size_t cnt) {
+    if (curve == BPGPU_BLS12_381) normalise_batch_host<BlsFq>(xyzz_bytes + lo * psz, cnt, 48, out_xy + lo * 2 * mb);
+    else normalise_batch_host<BnFq>(xyzz_bytes + lo * psz, cnt, 32, out_xy + lo * 2 * mb);
+  };
+  size_t nt = std::thread::hardware_concurrency();
+  if (nt > 16) nt = 16;
+  if (nt > count / 128) nt = count / 128;
+  if (nt <= 1) { run(0, count); return; }
+  std::vector<std::thread> th;
+  const size_t per = (count + nt - 1) / nt;
+  for (size_t k = 1; k < nt; k++) {
+    const size_t lo = k * per;
+    if (lo >= count) break;
+    th.emplace_back(run, lo, count - lo < per ? count - lo : per);
+  }
+  run(0, per < count ? per : count);
+  for (auto& t : th) t.join();
 }
 
 }  // namespace bp

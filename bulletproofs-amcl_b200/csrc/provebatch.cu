@@ -22,7 +22,9 @@ struct bpgpu_pbatch {
   size_t B, n, N;
   bp::FixedRuns runs1, runs2;        // [G[..n) | H[..n) | h] and [G[..N) | H[..N) | g]
   void* mem;                         // one allocation for everything below
-  void *W, *S, *blind, *rows1, *wts, *ytab, *polys, *tout, *params, *vecs, *rows2, *uv, *about, *sums, *keys, *ctr0;
+  void *W, *S, *blind, *rows1, *wts, *ytab, *polys, *tout, *params, *vecs, *rows2, *uv, *about, *sums, *keys, *ctr0, *parts;
+  // a row of F terms is summed by ceil(F / 256) blocks (long rows need more than one block to fill the machine)
+  static uint32_t splits_for(size_t F) { return (uint32_t)((F + 255) / 256); }
   size_t n_dev;                      // IPP vector length currently on the device
   bool started;
 };
@@ -127,6 +129,16 @@ __global__ void __launch_bounds__(128) k_pb_eval(uint32_t n, uint32_t N, const F
   store_vec(v + 3 * N + i, pb_pow_tab(tab + 32, i) * gf);
 }
 
+// ytab[b] = y^(2^k) [32] | y^-(2^k) [32] from yy[b] = {y, y^-1}: two threads per proof, 31 squarings each
+template <class Fr>
+__global__ void __launch_bounds__(128) k_pb_ytab(uint32_t B, const Fr* __restrict__ yy, Fr* __restrict__ ytab) {
+  const uint32_t t = blockIdx.x * blockDim.x + threadIdx.x;
+  if (t >= 2 * B) return;
+  Fr cur = load_vec(yy + t);
+  Fr* out = ytab + (size_t)(t >> 1) * 64 + (t & 1) * 32;
+  for (int k = 0; k < 32; k++) { store_vec(out + k, cur); cur = cur.sqr(); }
+}
+
 template <class Fr>
 __device__ __forceinline__ void pb_fold_element(uint32_t i, uint32_t n_cur, const Fr& u, const Fr& ui, Fr* a, Fr* b, Fr* sG, Fr* sH, Fr* ab_out) {
   const uint32_t half = n_cur >> 1;
@@ -215,7 +227,15 @@ template <class Curve>
 static int pb_sums(bpgpu_pbatch* pb, const FixedRuns& runs, uint32_t F, size_t rows, const void* d_rows, uint8_t* out_xy) {
   using Fq = typename Curve::Fq;
   bpgpu_ctx* ctx = pb->ctx;
-  k_batch_fixed<Curve><<<(unsigned)rows, 256, 0, ctx->stream>>>(runs, F, (const typename Curve::Fr*)d_rows, 1, (XYZZ<Fq>*)pb->sums);
+  const uint32_t splits = pb->splits_for(F);
+  if (splits == 1) {
+    k_batch_fixed<Curve><<<(unsigned)rows, BATCH_FIXED_THREADS, 0, ctx->stream>>>(runs, F, (const typename Curve::Fr*)d_rows, 1, (XYZZ<Fq>*)pb->sums);
+  } else {
+    k_batch_fixed<Curve><<<dim3((unsigned)rows, splits), BATCH_FIXED_THREADS, 0, ctx->stream>>>(runs, F, (const typename Curve::Fr*)d_rows, 1,
+                                                                                               (XYZZ<Fq>*)pb->parts);
+    k_batch_fixed_combine<Fq><<<(unsigned)((rows + 63) / 64), 64, 0, ctx->stream>>>((uint32_t)rows, splits, (XYZZ<Fq>*)pb->parts, (XYZZ<Fq>*)pb->sums);
+    ctx->launches++;
+  }
   ctx->launches++;
   int rc = launch_check(ctx, "pb_sums");
   if (rc) return rc;
@@ -260,14 +280,6 @@ static int pb_commit3_t(bpgpu_pbatch* pb, const uint8_t* witness_be, const uint8
 }
 
 template <class Curve>
-static void pb_ytab_host(const uint8_t* y_be, void* out64) {
-  using HF = host::HFp<typename std::conditional<Curve::ID == BPGPU_BLS12_381, BlsFr, BnFr>::type>;
-  HF* out = reinterpret_cast<HF*>(out64);
-  HF cur = HF::from_be(y_be, Curve::MODBYTES), cinv = cur.inv();
-  for (int k = 0; k < 32; k++) { out[k] = cur; out[32 + k] = cinv; cur = cur.sqr(); cinv = cinv.sqr(); }
-}
-
-template <class Curve>
 static int pb_polys_t(bpgpu_pbatch* pb, const uint8_t* weights_be, const uint8_t* y_be, uint8_t* t_be) {
   using Fr = typename Curve::Fr;
   using HF = host::HFp<typename std::conditional<Curve::ID == BPGPU_BLS12_381, BlsFr, BnFr>::type>;
@@ -275,9 +287,9 @@ static int pb_polys_t(bpgpu_pbatch* pb, const uint8_t* weights_be, const uint8_t
   const size_t B = pb->B, n = pb->n;
   int rc;
   if ((rc = scalars_from_host<Curve>(ctx, weights_be, B * 3 * n, 1, pb->wts))) return rc;
-  std::vector<HF> tabs(B * 64);
-  for (size_t b = 0; b < B; b++) pb_ytab_host<Curve>(y_be + b * Curve::MODBYTES, &tabs[b * 64]);
-  BP_CUDA_OK(cudaMemcpyAsync(pb->ytab, tabs.data(), tabs.size() * sizeof(HF), cudaMemcpyHostToDevice, ctx->stream));
+  if ((rc = pb_upload_mont<Curve>(pb, y_be, B * 2, pb->uv))) return rc;          // {y, y^-1} per proof (uv is free until the IPP)
+  k_pb_ytab<Fr><<<(unsigned)((2 * B + 127) / 128), 128, 0, ctx->stream>>>((uint32_t)B, (const Fr*)pb->uv, (Fr*)pb->ytab);
+  ctx->launches++;
   k_pb_polys<Fr><<<dim3((unsigned)((n + 127) / 128), (unsigned)B), 128, 0, ctx->stream>>>((uint32_t)n, (const Fr*)pb->ytab, (const Fr*)pb->W,
                                                                                          (const Fr*)pb->S, (const Fr*)pb->wts, (Fr*)pb->polys);
   k_pb_tpoly<Fr><<<(unsigned)B, 128, 0, ctx->stream>>>((uint32_t)n, (const Fr*)pb->W, (const Fr*)pb->S, (const Fr*)pb->polys, (Fr*)pb->tout);
@@ -387,15 +399,16 @@ int bpgpu_pbatch_create(bpgpu_ctx* ctx, bpgpu_points* G, bpgpu_points* H, const 
   pb->runs2.start[0] = 0; pb->runs2.start[1] = (uint32_t)N; pb->runs2.start[2] = (uint32_t)(2 * N); pb->runs2.start[3] = (uint32_t)(2 * N + 1);
   const size_t fr = 32, xz = ctx->curve == BPGPU_BLS12_381 ? sizeof(XYZZ<Bls::Fq>) : sizeof(XYZZ<Bn::Fq>);
   const size_t B = batch;
-  const size_t sizes[16] = {B * 3 * n * fr, B * 2 * n * fr, B * 3 * fr, 3 * B * (2 * n + 1) * fr, B * 3 * n * fr, B * 64 * fr, B * 4 * n * fr, B * 6 * fr,
-                            B * 4 * fr, B * 4 * N * fr, 2 * B * (2 * N + 1) * fr, B * 2 * fr, B * 2 * fr, 3 * B * xz, B * 64, B * 8};
+  const size_t sizes[17] = {B * 3 * n * fr, B * 2 * n * fr, B * 3 * fr, 3 * B * (2 * n + 1) * fr, B * 3 * n * fr, B * 64 * fr, B * 4 * n * fr, B * 6 * fr,
+                            B * 4 * fr, B * 4 * N * fr, 2 * B * (2 * N + 1) * fr, B * 2 * fr, B * 2 * fr, 3 * B * xz, B * 64, B * 8,
+                            3 * B * xz * bpgpu_pbatch::splits_for(2 * N + 1)};
   size_t total = 0;
   for (size_t s : sizes) total += up256(s);
-  if (cudaMalloc(&pb->mem, total) != cudaSuccess) { delete pb; return BPGPU_E_CUDA; }
-  void** slots[16] = {&pb->W, &pb->S, &pb->blind, &pb->rows1, &pb->wts, &pb->ytab, &pb->polys, &pb->tout, &pb->params, &pb->vecs, &pb->rows2,
-                      &pb->uv, &pb->about, &pb->sums, &pb->keys, &pb->ctr0};
+  if (dev_alloc(ctx, &pb->mem, total) != cudaSuccess) { delete pb; return BPGPU_E_CUDA; }   // stream-ordered pool: no driver round trip
+  void** slots[17] = {&pb->W, &pb->S, &pb->blind, &pb->rows1, &pb->wts, &pb->ytab, &pb->polys, &pb->tout, &pb->params, &pb->vecs, &pb->rows2,
+                      &pb->uv, &pb->about, &pb->sums, &pb->keys, &pb->ctr0, &pb->parts};
   uint8_t* p = (uint8_t*)pb->mem;
-  for (int k = 0; k < 16; k++) { *slots[k] = p; p += up256(sizes[k]); }
+  for (int k = 0; k < 17; k++) { *slots[k] = p; p += up256(sizes[k]); }
   *out = pb;
   return BPGPU_OK;
 }
@@ -403,7 +416,7 @@ int bpgpu_pbatch_create(bpgpu_ctx* ctx, bpgpu_points* G, bpgpu_points* H, const 
 void bpgpu_pbatch_free(bpgpu_pbatch* pb) {
   if (!pb) return;
   cudaSetDevice(pb->ctx->device);
-  if (pb->mem) cudaFree(pb->mem);
+  if (pb->mem) dev_free(pb->ctx, pb->mem);
   delete pb;
 }
 

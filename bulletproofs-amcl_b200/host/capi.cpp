@@ -292,9 +292,12 @@ int range_prove_batch_t(bpgpu_ctx* ctx, const char* label, const uint8_t* g_xy, 
   if (nthreads == 0) nthreads = std::thread::hardware_concurrency();
   if (nthreads == 0) nthreads = 1;
   bpgpu_pbatch* pb = nullptr;
+  Trace tr("range_prove_batch");
   int rc = bpgpu_pbatch_create(ctx, G, H, g_xy, h_xy, B, m * bits, &pb);
   if (rc) return rc;
+  tr.mark("create");
   const G1<C> g = G1<C>::from_xy(g_xy), h = G1<C>::from_xy(h_xy);
+  typename BatchProverAccess<C>::Pool pool(nthreads < B ? nthreads : B);
   for (size_t lo = 0; lo < count && !rc; lo += B) {
     size_t cnt = count - lo < B ? count - lo : B;
     if (cnt != B) {                                   // last, shorter slab: its own handle (the scratch layout depends on B)
@@ -302,10 +305,12 @@ int range_prove_batch_t(bpgpu_ctx* ctx, const char* label, const uint8_t* g_xy, 
       pb = nullptr;
       if ((rc = bpgpu_pbatch_create(ctx, G, H, g_xy, h_xy, cnt, m * bits, &pb))) break;
     }
-    rc = BatchProverAccess<C>::prove_slab(ctx, pb, label, g, h, values + lo * m, cnt, m, bits, rng_mode, seed + lo, nthreads, proofs + lo * stride,
+    rc = BatchProverAccess<C>::prove_slab(ctx, pb, label, g, h, values + lo * m, cnt, m, bits, rng_mode, seed + lo, pool, proofs + lo * stride,
                                           stride, comms_xy + lo * m * 2 * C::MODBYTES);
   }
+  tr.mark("slabs");
   bpgpu_pbatch_free(pb);
+  tr.mark("free");
   return rc;
 }
 

@@ -189,7 +189,7 @@ int bpgpu_fr_random(bpgpu_ctx* ctx, const uint8_t* key, size_t key_len, uint64_t
  *   commit3   : witness = batch x [a_L | a_R | a_O] (3n), keys = batch x key_len bytes and ctr0[batch] = where each proof's
  *               blinding stream stands (s_L, s_R = the next 2n draws, made on the device as by bpgpu_fr_random),
  *               blind = batch x [i_b, o_b, s_b]; out = batch x [A_I, A_O, S]
- *   polys     : weights = batch x [wL | wR | wO] (3n), y[batch]; out t = batch x [t_1 .. t_6]
+ *   polys     : weights = batch x [wL | wR | wO] (3n), y = batch x [y, y^-1]; out t = batch x [t_1 .. t_6]
  *   eval      : xuw = batch x [x, u, w] -> l_vec, r_vec, G_factors, H_factors become the IPP state (Q = w * g)
  *   ipp_round : uv = batch x [u, u^-1] of the previous round (NULL for the first); out = batch x [L, R]
  *   ipp_finish: uv of the last round; out = batch x [a, b] */
