@@ -22,6 +22,7 @@ SYMBOLS = [
     ("bpgpu_ctx_stream", _VP, [_VP]),
     ("bpgpu_ctx_sync", _INT, [_VP]),
     ("bpgpu_ctx_curve", _INT, [_VP]),
+    ("bpgpu_ctx_device", _INT, [_VP]),
     ("bpgpu_ctx_launches", _c.c_uint64, [_VP]),
     ("bpgpu_ctx_set_profile", _INT, [_VP, _INT]),
     ("bpgpu_msm_stage_ms", _INT, [_VP, _c.POINTER(_c.c_double), _INT]),

@@ -1,6 +1,7 @@
 // C entry points of the host layer (include/bphost.h): flatten the C++ mirror of the reference's API to bytes.
 #include <stdio.h>
 
+#include <algorithm>
 #include <atomic>
 #include <string>
 #include <thread>
@@ -287,31 +288,50 @@ template <class C>
 int range_prove_batch_t(bpgpu_ctx* ctx, const char* label, const uint8_t* g_xy, const uint8_t* h_xy, bpgpu_points* G, bpgpu_points* H,
                         const uint64_t* values, size_t count, size_t m, size_t bits, int rng_mode, uint64_t seed, size_t nthreads,
                         uint8_t* proofs, size_t stride, uint8_t* comms_xy) {
-  const size_t SLAB = 1024;
-  const size_t B = count < SLAB ? count : SLAB;
   if (nthreads == 0) nthreads = std::thread::hardware_concurrency();
   if (nthreads == 0) nthreads = 1;
-  bpgpu_pbatch* pb = nullptr;
-  Trace tr("range_prove_batch");
-  int rc = bpgpu_pbatch_create(ctx, G, H, g_xy, h_xy, B, m * bits, &pb);
-  if (rc) return rc;
-  tr.mark("create");
+  // Two drivers (this thread on `ctx`, a second thread on a context of its own on the same device) take alternate slabs:
+  // while one slab's transcripts run on the host, the other slab's stage runs on the device.
+  const size_t ndrv = (count >= 4096 && nthreads >= 2) ? 2 : 1;      // a second context costs ~20 ms to set up
+  const size_t SLAB = 1024;
+  size_t B = (count + ndrv - 1) / ndrv;
+  if (B > SLAB) B = SLAB;
+  const size_t nslab = (count + B - 1) / B;
   const G1<C> g = G1<C>::from_xy(g_xy), h = G1<C>::from_xy(h_xy);
-  typename BatchProverAccess<C>::Pool pool(nthreads < B ? nthreads : B);
-  for (size_t lo = 0; lo < count && !rc; lo += B) {
-    size_t cnt = count - lo < B ? count - lo : B;
-    if (cnt != B) {                                   // last, shorter slab: its own handle (the scratch layout depends on B)
-      bpgpu_pbatch_free(pb);
-      pb = nullptr;
-      if ((rc = bpgpu_pbatch_create(ctx, G, H, g_xy, h_xy, cnt, m * bits, &pb))) break;
+  bpgpu_ctx* ctx2 = nullptr;
+  int rc = BPGPU_OK;
+  if (ndrv == 2 && (rc = bpgpu_ctx_create(bpgpu_ctx_curve(ctx), bpgpu_ctx_device(ctx), &ctx2))) return rc;
+  if ((rc = bpgpu_points_precompute(ctx, G)) || (rc = bpgpu_points_precompute(ctx, H))) { if (ctx2) bpgpu_ctx_destroy(ctx2); return rc; }
+  std::atomic<int> err{0};
+  auto driver = [&](size_t k, bpgpu_ctx* dctx) {
+    typename BatchProverAccess<C>::Pool pool(std::max<size_t>(1, nthreads / ndrv));
+    bpgpu_pbatch* pb = nullptr;
+    size_t pb_size = 0;
+    for (size_t sl = k; sl < nslab && !err.load(); sl += ndrv) {
+      const size_t lo = sl * B, cnt = count - lo < B ? count - lo : B;
+      int r = BPGPU_OK;
+      if (cnt != pb_size) {                           // the scratch layout depends on the slab size
+        bpgpu_pbatch_free(pb);
+        pb = nullptr;
+        r = bpgpu_pbatch_create(dctx, G, H, g_xy, h_xy, cnt, m * bits, &pb);
+        pb_size = cnt;
+      }
+      if (!r)
+        r = BatchProverAccess<C>::prove_slab(dctx, pb, label, g, h, values + lo * m, cnt, m, bits, rng_mode, seed + lo, pool, proofs + lo * stride,
+                                             stride, comms_xy + lo * m * 2 * C::MODBYTES);
+      if (r) { int z = 0; err.compare_exchange_strong(z, r); }
     }
-    rc = BatchProverAccess<C>::prove_slab(ctx, pb, label, g, h, values + lo * m, cnt, m, bits, rng_mode, seed + lo, pool, proofs + lo * stride,
-                                          stride, comms_xy + lo * m * 2 * C::MODBYTES);
+    bpgpu_pbatch_free(pb);
+  };
+  if (ndrv == 2) {
+    std::thread other(driver, 1, ctx2);
+    driver(0, ctx);
+    other.join();
+    bpgpu_ctx_destroy(ctx2);
+  } else {
+    driver(0, ctx);
   }
-  tr.mark("slabs");
-  bpgpu_pbatch_free(pb);
-  tr.mark("free");
-  return rc;
+  return err.load();
 }
 
 template <class FqP>

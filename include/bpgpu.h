@@ -57,6 +57,7 @@ void bpgpu_ctx_destroy(bpgpu_ctx* ctx);
 void* bpgpu_ctx_stream(bpgpu_ctx* ctx);     /* the cudaStream_t all work of this ctx is issued on */
 int bpgpu_ctx_sync(bpgpu_ctx* ctx);
 int bpgpu_ctx_curve(const bpgpu_ctx* ctx);
+int bpgpu_ctx_device(const bpgpu_ctx* ctx);
 /* number of kernels this ctx has launched so far (bench.py's gpu_launches) */
 uint64_t bpgpu_ctx_launches(const bpgpu_ctx* ctx);
 

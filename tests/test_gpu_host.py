@@ -287,3 +287,20 @@ def test_lock_step_batch_prover_equals_single_proofs(which, m, bits, count, bp, 
     p1, _, c1 = bp.range_prove_batch(ctx, b"Batch", gx, hx, dG, dH, values, m, bits)
     assert p1 != got_p
     assert bp.range_verify_many([ctx], b"Batch", gx, hx, dG, dH, count, m, bits, p1, stride, c1) == [0] * count
+
+
+def test_lock_step_batch_prover_two_drivers(bp, ctx_bls):
+    """4100 proofs: the batch is split over two interleaved drivers (two contexts, alternating slabs of 1024, a short last
+    slab); still byte-identical to the single-context proofs with seed + i."""
+    ctx = ctx_bls
+    m, bits, count = 1, 8, 4100
+    dG, dH = ctx.get_generators("G", 8), ctx.get_generators("H", 8)
+    gx, hx = ctx.g1_from_msg_hash(b"g"), ctx.g1_from_msg_hash(b"h")
+    values = [(37 * i + 11) % 256 for i in range(count)]
+    ctxs = [ctx] + [bp.Context(bp.BLS12_381, 0) for _ in range(3)]
+    ref_p, stride, ref_c = bp.range_prove_many(ctxs, b"Batch2", gx, hx, dG, dH, values, m, bits, seed=9000)
+    got_p, _, got_c = bp.range_prove_batch(ctx, b"Batch2", gx, hx, dG, dH, values, m, bits, seed=9000)
+    assert got_c == ref_c and got_p == ref_p
+    assert bp.range_verify_batch(ctx, b"Batch2", gx, hx, dG, dH, count, m, bits, got_p, stride, got_c) == [0] * count
+    for c in ctxs[1:]:
+        c.close()
