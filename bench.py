@@ -137,7 +137,8 @@ def proof_section(bp, ctx, local, rank, world, dist, torch, no_cpu=False):
     import numpy as np
     ncpu = os.cpu_count() or 1
     nctx = max(1, min(16, ncpu // max(1, world)))
-    out = {"contexts_per_gpu": nctx, "host_cpus": ncpu}
+    hthreads = max(1, ncpu // max(1, world))          # host threads of the batch calls: this rank's share of the cores
+    out = {"contexts_per_gpu": nctx, "host_cpus": ncpu, "host_threads_per_rank": hthreads}
 
     def run(curve, m, bits, count, tag, verify_reps=1, batch_call=False, cpu_base=0):
         ctxs = [bp.Context(curve, local) for _ in range(nctx)]
@@ -169,13 +170,13 @@ def proof_section(bp, ctx, local, rank, world, dist, torch, no_cpu=False):
             # is one device call for the whole batch, the transcripts run on the host threads in between
             nb = count * verify_reps
             bvals = [int(x) for x in rng.integers(0, 1 << 63, size=nb * m, dtype=np.uint64)]
-            bp.range_prove_batch(c0, b"bench", gx, hx, G, H, bvals, m, bits)                                   # warm-up (scratch sized)
+            bp.range_prove_batch(c0, b"bench", gx, hx, G, H, bvals, m, bits, nthreads=hthreads)                # warm-up (scratch sized)
             if dist is not None:
                 dist.barrier()
             t0 = time.perf_counter()
-            bproofs, bstride, bcomms = bp.range_prove_batch(c0, b"bench", gx, hx, G, H, bvals, m, bits)
+            bproofs, bstride, bcomms = bp.range_prove_batch(c0, b"bench", gx, hx, G, H, bvals, m, bits, nthreads=hthreads)
             tpb = time.perf_counter() - t0
-            v = bp.range_verify_batch(c0, b"bench", gx, hx, G, H, nb, m, bits, bproofs, bstride, bcomms)
+            v = bp.range_verify_batch(c0, b"bench", gx, hx, G, H, nb, m, bits, bproofs, bstride, bcomms, nthreads=hthreads)
             ok = ok and v == [0] * nb
         if batch_call:
             # config 5: the whole batch through bph_range_verify_batch: host threads build the scalars slab by slab, the
@@ -183,11 +184,11 @@ def proof_section(bp, ctx, local, rank, world, dist, torch, no_cpu=False):
             # proof), overlapped with the host work on the next slab
             reps = verify_reps
             big_p, big_c = proofs * reps, comms * reps
-            bp.range_verify_batch(c0, b"bench", gx, hx, G, H, count * reps, m, bits, big_p, stride, big_c)      # warm-up (scratch sized)
+            bp.range_verify_batch(c0, b"bench", gx, hx, G, H, count * reps, m, bits, big_p, stride, big_c, nthreads=hthreads)   # warm-up
             if dist is not None:
                 dist.barrier()
             t0 = time.perf_counter()
-            v = bp.range_verify_batch(c0, b"bench", gx, hx, G, H, count * reps, m, bits, big_p, stride, big_c)
+            v = bp.range_verify_batch(c0, b"bench", gx, hx, G, H, count * reps, m, bits, big_p, stride, big_c, nthreads=hthreads)
             tb = time.perf_counter() - t0
             ok = ok and v == [0] * (count * reps)
         if dist is not None:
