@@ -22,7 +22,8 @@ int positive_no_gadget(ConstraintSystem<C>& cs, const AllocatedQuantity<C>& v, s
   using LC = LinearCombination<C>;
   std::vector<std::pair<Variable, FE>> constraint_v = {{v.variable, FE::minus_one()}};
   FE exp_2 = FE::one();
-  const FE zero = FE::zero(), one = FE::one();
+  const FE zero = FE::zero(), one = FE::one(), minus_one = FE::minus_one();
+  constraint_v.reserve(n + 1);
   for (size_t i = 0; i < n; i++) {
     Variable a, b, o;
     int rc;
@@ -34,7 +35,8 @@ int positive_no_gadget(ConstraintSystem<C>& cs, const AllocatedQuantity<C>& v, s
     }
     if (rc) return rc;
     cs.constrain(LC(o));                                         // :27   a * b = 0
-    cs.constrain(LC(a) + (LC(b) - LC(one)));                     // :30   a = 1 - b
+    // :30   a = 1 - b, i.e. the terms of `a + (b - 1)` in the reference's order, built without the temporaries
+    cs.constrain(LC(std::vector<std::pair<Variable, FE>>{{a, one}, {b, one}, {Variable::one(), minus_one}}));
     constraint_v.emplace_back(b, exp_2);
     exp_2 = exp_2 + exp_2;
   }

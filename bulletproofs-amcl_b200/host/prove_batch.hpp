@@ -179,9 +179,20 @@ struct BatchProverAccess {
         wR[k].to_bytes(w + (n + k) * mb);
         wO[k].to_bytes(w + (2 * n + k) * mb);
       }
-      s.y.to_bytes(yb.data() + (i * 2) * mb);
-      s.y.inverse().to_bytes(yb.data() + (i * 2 + 1) * mb);
     });
+    {                                                                    // y^-1 of every proof with one inversion
+      std::vector<FE> pre(B + 1);
+      pre[0] = FE::one();
+      for (size_t i = 0; i < B; i++) pre[i + 1] = st[i]->y.is_zero() ? pre[i] : pre[i] * st[i]->y;
+      FE inv = pre[B].inverse();
+      for (size_t i = B; i-- > 0;) {
+        const FE& y = st[i]->y;
+        FE yi = FE::zero();
+        if (!y.is_zero()) { yi = inv * pre[i]; inv = inv * y; }
+        y.to_bytes(yb.data() + (i * 2) * mb);
+        yi.to_bytes(yb.data() + (i * 2 + 1) * mb);
+      }
+    }
     if (err.load()) return err.load();
     tr_.mark("host: y z, flatten");
     std::vector<uint8_t> tbe(B * 6 * mb);
