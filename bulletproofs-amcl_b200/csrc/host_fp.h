@@ -88,8 +88,39 @@ struct HFp {
   HFp sqr() const { return (*this) * (*this); }
   HFp to_mont() const { return (*this) * r2(); }
   HFp from_mont() const { HFp o = zero(); o.v[0] = 1; return (*this) * o; }
-  // Fermat inverse, 0 -> 0 (FieldElement::inverse of zero is zero in AMCL)
+  // Inverse, 0 -> 0 (FieldElement::inverse of zero is zero in AMCL): binary extended Euclid on the Montgomery
+  // representative m = aR (HAC 14.61: ~2 * bits shift / subtract steps on NL limbs -- a few microseconds where the
+  // Fermat ladder below needs bits squarings + bits/2 products), then (aR)^-1 * R^3 / R = a^-1 R.  Variable time: the
+  // host inverts challenges and the Z coordinates of results that are about to be published.
   HFp inv() const {
+    if (is_zero()) return zero();
+    uint64_t u[NL], v[NL], x1[NL], x2[NL];
+    for (int i = 0; i < NL; i++) { u[i] = this->v[i]; v[i] = pl(i); x1[i] = 0; x2[i] = 0; }
+    x1[0] = 1;
+    auto is_one = [](const uint64_t* a) { uint64_t o = a[0] ^ 1; for (int i = 1; i < NL; i++) o |= a[i]; return o == 0; };
+    auto shr1 = [](uint64_t* a, uint64_t top) { for (int i = 0; i < NL - 1; i++) a[i] = (a[i] >> 1) | (a[i + 1] << 63); a[NL - 1] = (a[NL - 1] >> 1) | (top << 63); };
+    auto half_mod = [&](uint64_t* x) {            // x / 2 mod p for x < p
+      uint64_t top = 0;
+      if (x[0] & 1) { unsigned __int128 c = 0; for (int i = 0; i < NL; i++) { c += (unsigned __int128)x[i] + pl(i); x[i] = (uint64_t)c; c >>= 64; } top = (uint64_t)c; }
+      shr1(x, top);
+    };
+    auto geq = [](const uint64_t* a, const uint64_t* b) { for (int i = NL - 1; i >= 0; i--) { if (a[i] > b[i]) return true; if (a[i] < b[i]) return false; } return true; };
+    auto sub = [](uint64_t* a, const uint64_t* b) { unsigned __int128 br = 0; for (int i = 0; i < NL; i++) { unsigned __int128 t = (unsigned __int128)a[i] - b[i] - (uint64_t)br; a[i] = (uint64_t)t; br = (t >> 64) & 1; } return (uint64_t)br; };
+    auto sub_mod = [&](uint64_t* a, const uint64_t* b) {   // a - b mod p for a, b < p
+      if (sub(a, b)) { unsigned __int128 c = 0; for (int i = 0; i < NL; i++) { c += (unsigned __int128)a[i] + pl(i); a[i] = (uint64_t)c; c >>= 64; } }
+    };
+    while (!is_one(u) && !is_one(v)) {
+      while (!(u[0] & 1)) { shr1(u, 0); half_mod(x1); }
+      while (!(v[0] & 1)) { shr1(v, 0); half_mod(x2); }
+      if (geq(u, v)) { sub(u, v); sub_mod(x1, x2); } else { sub(v, u); sub_mod(x2, x1); }
+    }
+    HFp w;
+    for (int i = 0; i < NL; i++) w.v[i] = is_one(u) ? x1[i] : x2[i];
+    static const HFp R3 = r2() * r2();             // R^2 * R^2 / R
+    return w * R3;
+  }
+  // Fermat ladder (kept as the cross-check of inv() in the CPU tests)
+  HFp inv_fermat() const {
     uint64_t e[NL];
     for (int i = 0; i < NL; i++) e[i] = pl(i);
     e[0] -= 2;

@@ -3,6 +3,7 @@
 // tests/test_host_arith.py with g++; NOT part of the product library.
 #include <string.h>
 #include "../bulletproofs-amcl_b200/csrc/ec.cuh"
+#include "../bulletproofs-amcl_b200/csrc/host_fp.h"
 
 using namespace bp;
 
@@ -45,7 +46,27 @@ static void fp_mul2(const uint32_t* a, const uint32_t* b, const uint32_t* c, con
   memcpy(out, r.v, sizeof(r.v));
 }
 
+// host-side field code (host_fp.h, 64-bit limbs): inv() by binary extended Euclid against the Fermat ladder; in/out are
+// the 32-bit little-endian limbs of the Montgomery form
+template <class P>
+static int hostfp_inv(const uint32_t* a, uint32_t* out) {
+  using H = host::HFp<P>;
+  H x;
+  memcpy(x.v, a, sizeof x.v);
+  H i1 = x.inv(), i2 = x.inv_fermat();
+  memcpy(out, i1.v, sizeof i1.v);
+  return i1 == i2 ? 1 : 0;
+}
+
 extern "C" {
+int hc_hostfp_inv(int field, const uint32_t* a, uint32_t* out) {
+  switch (field) {
+    case 0: return hostfp_inv<BlsFq>(a, out);
+    case 1: return hostfp_inv<BlsFr>(a, out);
+    case 2: return hostfp_inv<BnFq>(a, out);
+    default: return hostfp_inv<BnFr>(a, out);
+  }
+}
 // (a*b + c*d) / R mod p, curve fields only (field 0 = BLS12-381 Fq, 2 = BN254 Fq)
 void hc_fp_mul2(int field, const uint32_t* a, const uint32_t* b, const uint32_t* c, const uint32_t* d, uint32_t* out) {
   if (field == 0) fp_mul2<Fp<BlsFq>>(a, b, c, d, out);

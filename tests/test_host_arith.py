@@ -51,6 +51,20 @@ def test_montgomery_schedule(hc, fid, p, n):
         assert op(5, a * R % p) == pow(a, p - 2, p) * R % p
 
 
+@pytest.mark.parametrize("fid,p,n", [(0, B.p, 12), (1, B.r, 8), (2, N.p, 8), (3, N.r, 8)])
+def test_host_field_inverse(hc, fid, p, n):
+    """host_fp.h (the host layer's 64-bit-limb field code): inv() by binary extended Euclid equals the Fermat ladder and the
+    integers, incl. 0 -> 0, 1, p - 1 and values with long runs of zero bits."""
+    R = 1 << (32 * n)
+    rnd = random.Random(50 + fid)
+    vals = [0, 1, 2, p - 1, p - 2, (p + 1) // 2, 1 << 200, (1 << 250) % p, R % p] + [rnd.randrange(p) for _ in range(200)]
+    for a in vals:
+        out = (ctypes.c_uint32 * n)()
+        same = hc.hc_hostfp_inv(fid, _L(a * R % p, n), out)
+        assert same == 1
+        assert _I(out) == (pow(a, p - 2, p) * R % p if a else 0)
+
+
 @pytest.mark.parametrize("fid,p,n", [(0, B.p, 12), (2, N.p, 8)])
 def test_fused_two_product_reduction(hc, fid, p, n):
     """Fp::mul2 = (a*b + c*d)/R mod p with one reduction (the Y3 term of the group law), incl. the extreme operands
