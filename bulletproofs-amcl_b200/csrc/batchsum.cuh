@@ -17,7 +17,7 @@ struct FixedRuns {
 };
 
 template <class Curve>
-__global__ void __launch_bounds__(BATCH_FIXED_THREADS) k_batch_fixed(FixedRuns runs, uint32_t F, const typename Curve::Fr* __restrict__ scal, int mont,
+__global__ void __launch_bounds__(BATCH_FIXED_THREADS, 3) k_batch_fixed(FixedRuns runs, uint32_t F, const typename Curve::Fr* __restrict__ scal, int mont,
                                                      XYZZ<typename Curve::Fq>* __restrict__ out) {
   using Fq = typename Curve::Fq;
   using Fr = typename Curve::Fr;
