@@ -49,6 +49,6 @@ def test_product_never_imports_oracle():
     pkg = os.path.join(ROOT, "bulletproofs-amcl_b200")
     for dirpath, _, files in os.walk(pkg):
         for f in files:
-            if f.endswith((".py", ".cu", ".cuh", ".h", ".cpp")):
+            if f.endswith((".py", ".cu", ".cuh", ".h", ".hpp", ".cpp")):
                 txt = open(os.path.join(dirpath, f)).read()
                 assert "import oracle" not in txt and "from oracle" not in txt and "liboracle" not in txt, f
