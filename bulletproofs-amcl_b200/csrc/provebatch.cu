@@ -23,8 +23,9 @@ struct bpgpu_pbatch {
   bp::FixedRuns runs1, runs2;        // [G[..n) | H[..n) | h] and [G[..N) | H[..N) | g]
   void* mem;                         // one allocation for everything below
   void *W, *S, *blind, *rows1, *wts, *ytab, *polys, *tout, *params, *vecs, *rows2, *uv, *about, *sums, *keys, *ctr0, *parts;
-  // a row of F terms is summed by ceil(F / 256) blocks (long rows need more than one block to fill the machine)
-  static uint32_t splits_for(size_t F) { return (uint32_t)((F + 255) / 256); }
+  // a row of F terms is summed by ceil(F / 512) blocks: long rows need more than one block to fill the machine, but every
+  // block ends in a 7-level tree, so its 512 terms (32 table additions per thread on average) should outweigh that
+  static uint32_t splits_for(size_t F) { return (uint32_t)((F + 511) / 512); }
   size_t n_dev;                      // IPP vector length currently on the device
   bool started;
 };
