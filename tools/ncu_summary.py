@@ -38,8 +38,11 @@ KEYS = ["gpu__time_duration.sum", "launch__registers_per_thread", "launch__grid_
         "dram__throughput.avg.pct_of_peak_sustained_elapsed", "lts__t_bytes.sum", "l1tex__t_sectors_pipe_lsu_mem_global_op_st.sum",
         "smsp__average_warps_issue_stalled_long_scoreboard_per_issue_active.ratio", "smsp__average_warps_issue_stalled_wait_per_issue_active.ratio",
         "smsp__average_warps_issue_stalled_math_pipe_throttle_per_issue_active.ratio"]
-lines = ["# key metrics of the ncu --set full captures (one launch each, 2^20-term BLS12-381 MSM); raw pages: profiles/k_*_r01_raw.csv"]
-for f in ("k_chunk_acc", "k_reduce_l1", "k_scatter"):
+lines = ["# key metrics of the ncu --set full captures (one launch each; MSM kernels: 2^20-term BLS12-381 MSM; k_batch_fixed: an IPP round of",
+         "# the lock-step batch prover, 2048 rows x 129 terms); raw pages: profiles/k_*_r01_raw.csv"]
+for f in ("k_chunk_acc", "k_reduce_l1", "k_scatter", "k_batch_fixed"):
+    if not os.path.exists(os.path.join(P, f + "_r01_raw.csv")):
+        continue
     rows = list(csv.reader(open(os.path.join(P, f + "_r01_raw.csv"))))
     d = {n: (rows[2][i], rows[1][i]) for i, n in enumerate(rows[0])}
     lines.append("== " + f)
