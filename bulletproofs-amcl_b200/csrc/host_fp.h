@@ -60,26 +60,33 @@ struct HFp {
   }
   HFp neg() const { return zero() - *this; }
   HFp dbl() const { return *this + *this; }
-  // CIOS Montgomery product; constants are compile-time, loops have constant bounds and are unrolled, so the NL + 1
-  // accumulator limbs stay in registers (mulx / adc chains with -march=x86-64-v3)
+  // Montgomery product, multiplication and reduction fused limb by limb (the "no-carry" form: the top bit of every modulus
+  // here is clear, so t[NL-1] = c1 + c2 cannot overflow and no extra accumulator limb is needed).  Constants are
+  // compile-time, loops have constant bounds and are unrolled: the NL accumulator limbs stay in registers.
   friend HFp operator*(const HFp& a, const HFp& b) {
+    static_assert((P::P(P::N - 1) >> 31) == 0, "top bit of the modulus must be clear");
     constexpr uint64_t INV = inv64();
-    uint64_t t[NL + 1] = {0};
+    uint64_t t[NL] = {0};
 #pragma GCC unroll 8
     for (int i = 0; i < NL; i++) {
       const uint64_t bi = b.v[i];
-      unsigned __int128 c = 0;
+      unsigned __int128 c = (unsigned __int128)a.v[0] * bi + t[0];
+      const uint64_t t0 = (uint64_t)c;
+      uint64_t c1 = (uint64_t)(c >> 64);
+      const uint64_t m = t0 * INV;
+      unsigned __int128 d = (unsigned __int128)m * pl(0) + t0;
+      uint64_t c2 = (uint64_t)(d >> 64);
 #pragma GCC unroll 8
-      for (int j = 0; j < NL; j++) { c += (unsigned __int128)a.v[j] * bi + t[j]; t[j] = (uint64_t)c; c >>= 64; }
-      c += t[NL];
-      const uint64_t tn = (uint64_t)c, top = (uint64_t)(c >> 64);
-      const uint64_t m = t[0] * INV;
-      c = (unsigned __int128)m * pl(0) + t[0]; c >>= 64;
-#pragma GCC unroll 8
-      for (int j = 1; j < NL; j++) { c += (unsigned __int128)m * pl(j) + t[j]; t[j - 1] = (uint64_t)c; c >>= 64; }
-      c += tn; t[NL - 1] = (uint64_t)c; t[NL] = top + (uint64_t)(c >> 64);
+      for (int j = 1; j < NL; j++) {
+        c = (unsigned __int128)a.v[j] * bi + t[j] + c1;
+        c1 = (uint64_t)(c >> 64);
+        d = (unsigned __int128)m * pl(j) + (uint64_t)c + c2;
+        c2 = (uint64_t)(d >> 64);
+        t[j - 1] = (uint64_t)d;
+      }
+      t[NL - 1] = c1 + c2;
     }
-    if (t[NL] || geq_p(t)) sub_p(t);
+    if (geq_p(t)) sub_p(t);
     HFp r;
 #pragma GCC unroll 8
     for (int i = 0; i < NL; i++) r.v[i] = t[i];

@@ -58,7 +58,32 @@ static int hostfp_inv(const uint32_t* a, uint32_t* out) {
   return i1 == i2 ? 1 : 0;
 }
 
+template <class P>
+static void hostfp_op(int op, const uint32_t* a, const uint32_t* b, uint32_t* out) {
+  using H = host::HFp<P>;
+  H x, y, r;
+  memcpy(x.v, a, sizeof x.v);
+  memcpy(y.v, b, sizeof y.v);
+  switch (op) {
+    case 0: r = x * y; break;
+    case 1: r = x + y; break;
+    case 2: r = x - y; break;
+    case 3: r = x.to_mont(); break;
+    case 4: r = x.from_mont(); break;
+    default: r = x.sqr();
+  }
+  memcpy(out, r.v, sizeof r.v);
+}
+
 extern "C" {
+void hc_hostfp_op(int field, int op, const uint32_t* a, const uint32_t* b, uint32_t* out) {
+  switch (field) {
+    case 0: hostfp_op<BlsFq>(op, a, b, out); break;
+    case 1: hostfp_op<BlsFr>(op, a, b, out); break;
+    case 2: hostfp_op<BnFq>(op, a, b, out); break;
+    default: hostfp_op<BnFr>(op, a, b, out);
+  }
+}
 int hc_hostfp_inv(int field, const uint32_t* a, uint32_t* out) {
   switch (field) {
     case 0: return hostfp_inv<BlsFq>(a, out);

@@ -52,6 +52,30 @@ def test_montgomery_schedule(hc, fid, p, n):
 
 
 @pytest.mark.parametrize("fid,p,n", [(0, B.p, 12), (1, B.r, 8), (2, N.p, 8), (3, N.r, 8)])
+def test_host_field_ops(hc, fid, p, n):
+    """host_fp.h on 64-bit limbs (the host finish of every MSM, challenge arithmetic): Montgomery product, sum, difference and
+    the conversions against the integers, with the extreme operands 0, 1, p - 1 and R mod p."""
+    R = 1 << (32 * n)
+    Rinv = pow(R, -1, p)
+    rnd = random.Random(70 + fid)
+
+    def op(o, a, b=0):
+        out = (ctypes.c_uint32 * n)()
+        hc.hc_hostfp_op(fid, o, _L(a, n), _L(b, n), out)
+        return _I(out)
+    edge = [0, 1, p - 1, p - 2, R % p, (p - 1) // 2, ((1 << (32 * n - 1)) - 1) % p]
+    vals = edge + [rnd.randrange(p) for _ in range(150)]
+    for a in vals:
+        for b in rnd.sample(vals, 5) + edge:
+            assert op(0, a, b) == a * b * Rinv % p
+            assert op(1, a, b) == (a + b) % p
+            assert op(2, a, b) == (a - b) % p
+        assert op(3, a) == a * R % p
+        assert op(4, a) == a * Rinv % p
+        assert op(5, a) == a * a * Rinv % p
+
+
+@pytest.mark.parametrize("fid,p,n", [(0, B.p, 12), (1, B.r, 8), (2, N.p, 8), (3, N.r, 8)])
 def test_host_field_inverse(hc, fid, p, n):
     """host_fp.h (the host layer's 64-bit-limb field code): inv() by binary extended Euclid equals the Fermat ladder and the
     integers, incl. 0 -> 0, 1, p - 1 and values with long runs of zero bits."""
