@@ -107,6 +107,40 @@ def gen_msm():
     return out
 
 
+def gen_shuffle(C, k, bits, seed):
+    """two-phase circuit: k-shuffle with x[0] range-checked to `bits` bits (the statement of bph_shuffle_prove, with the
+    same value and draw order as tests/test_gpu_host.py::test_two_phase_shuffle_matches_oracle)"""
+    g, h = C.g1_from_msg_hash(b"g"), C.g1_from_msg_hash(b"h")
+    n = bits + 2 * (k - 1)
+    N = 1 << max(0, (n - 1).bit_length())
+    G, H = C.get_generators("G", N), C.get_generators("H", N)
+    xs = [(7 + 13 * i) % (1 << max(bits, 6)) for i in range(k)]
+    if bits:
+        xs[0] %= 1 << bits
+    ys = xs[1:] + xs[:1]
+    rng = or1cs.make_rng(C, seed)
+    p = or1cs.Prover(C, g, h, Transcript(b"Shuffle", C))
+    blinds = [rng() for _ in range(2 * k)]
+    comms, vars_ = [], []
+    for v, bl in zip(xs + ys, blinds):
+        com, var = p.commit(v, bl)
+        comms.append(com)
+        vars_.append(var)
+    if bits:
+        or1cs.positive_no_gadget(p, or1cs.AllocatedQuantity(vars_[0], xs[0]), bits)
+    or1cs.shuffle_gadget(p, vars_[:k], vars_[k:])
+    proof = p.prove(G, H, rng)
+    v_ = or1cs.Verifier(C, Transcript(b"Shuffle", C))
+    vv = [v_.commit(c) for c in comms]
+    if bits:
+        or1cs.positive_no_gadget(v_, or1cs.AllocatedQuantity(vv[0], None), bits)
+    or1cs.shuffle_gadget(v_, vv[:k], vv[k:])
+    v_.verify(proof, g, h, G, H, C.synth_scalar(seed, 0, b"verifier"))
+    pb = proof.to_bytes(C)
+    return {"curve": C.name, "k": k, "bits": bits, "seed": seed, "label": "Shuffle", "x": xs, "y": ys,
+            "commitments": b"".join(C.g1_xy_bytes(c) for c in comms).hex(), "proof": pb.hex(), "proof_sha256": hashlib.sha256(pb).hexdigest()}
+
+
 def write(name, obj):
     with open(os.path.join(HERE, name), "w") as f:
         json.dump(obj, f, indent=1)
@@ -125,6 +159,7 @@ def main():
     write("ipp_n8.json", gen_ipp(8))
     write("bound_check_8bit.json", {C.name: gen_bound(C, 8, 1) for C in (BLS12_381, BN254)})
     write("range_small.json", {"bls_m2_b8": gen_range(BLS12_381, 2, 8, 3, b"Range"), "bn_m3_b5": gen_range(BN254, 3, 5, 4, b"Range")})
+    write("shuffle_two_phase.json", {"bls_k3_b4": gen_shuffle(BLS12_381, 3, 4, 43), "bn_k3_b4": gen_shuffle(BN254, 3, 4, 43)})
     if not quick:
         write("ipp_n64.json", gen_ipp(64))                                                   # BASELINE config 1
         write("range_config5_unit.json", {"bls_m1_b64": gen_range(BLS12_381, 1, 64, 5, b"Range")})   # config 5 unit

@@ -43,6 +43,20 @@ def test_oracle_reproduces_small_proofs():
     assert mg.gen_msm() == load("msm_257.json")
 
 
+def test_oracle_reproduces_two_phase_fixture():
+    """the two-phase (randomised constraints) shuffle proof: pure-Python oracle and C-accelerated oracle both reproduce the
+    committed bytes (the GPU path is compared with the live oracle on the same statement in tests/test_gpu_host.py)."""
+    import importlib.util
+    from oracle import fast
+    spec = importlib.util.spec_from_file_location("make_golden", os.path.join(HERE, "make_golden.py"))
+    mg = importlib.util.module_from_spec(spec)
+    spec.loader.exec_module(mg)
+    fx = load("shuffle_two_phase.json")
+    assert mg.gen_shuffle(CURVES["BN254"], 3, 4, 43) == fx["bn_k3_b4"]
+    with fast.c_keccak():
+        assert mg.gen_shuffle(fast.FastCurve(CURVES["BLS12_381"]), 3, 4, 43) == fx["bls_k3_b4"]
+
+
 @pytest.mark.parametrize("name,key,cname,m,seed", [("range_config5_unit.json", "bls_m1_b64", "BLS12_381", 1, 5),
                                                   ("range_config3_reduced.json", "bn_m8_b64", "BN254", 8, 6),
                                                   ("range_config2.json", "bls_m16_b64", "BLS12_381", 16, 2)])
