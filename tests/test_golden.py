@@ -153,3 +153,22 @@ def test_gpu_range_proof_golden(name, ctx_bls, ctx_bn):
         assert comms.hex() == d["commitments"]
         assert proof.hex() == d["proof"]
         assert ctx.range_verify(d["label"].encode(), gx, hx, dG, dH, m, bits, proof, comms)
+
+
+@pytest.mark.gpu
+def test_gpu_two_phase_shuffle_golden(ctx_bls, ctx_bn):
+    """the CUDA path reproduces the committed two-phase proof (second-phase commitments A_I2 / A_O2 / S2 included)"""
+    fx = load("shuffle_two_phase.json")
+    for key, d in fx.items():
+        ctx = _ctx(d["curve"], ctx_bls, ctx_bn)
+        k, bits = d["k"], d["bits"]
+        n = bits + 2 * (k - 1)
+        N = 1 << max(0, (n - 1).bit_length())
+        G, H = ctx.get_generators("G", N), ctx.get_generators("H", N)
+        gx, hx = ctx.g1_from_msg_hash(b"g"), ctx.g1_from_msg_hash(b"h")
+        proof, comms = ctx.shuffle_prove(d["label"].encode(), gx, hx, G, H, d["x"], d["y"], bits, seed=d["seed"])
+        assert comms.hex() == d["commitments"], key
+        assert proof.hex() == d["proof"], key
+        assert ctx.shuffle_verify(d["label"].encode(), gx, hx, G, H, k, bits, proof, comms) is True
+        G.free()
+        H.free()
