@@ -45,6 +45,13 @@ SYMBOLS = [
     ("bpgpu_msm_parts_batch", _INT, [_VP, _VP, _VP, _SZ, _VP]),
     ("bpgpu_msm_batch_is_identity", _INT, [_VP, _VP, _SZ, _SZ, _VP, _VP, _VP, _SZ, _VP]),
     ("bpgpu_msm_window_bits", _INT, [_SZ]),
+    ("bpgpu_circuit_create", _INT, [_VP, _SZ, _SZ, _SZ, _VP, _VP, _VP, _c.POINTER(_VP)]),
+    ("bpgpu_circuit_free", None, [_VP]),
+    ("bpgpu_circuit_multipliers", _SZ, [_VP]),
+    ("bpgpu_circuit_commitments", _SZ, [_VP]),
+    ("bpgpu_circuit_flatten", _INT, [_VP, _VP, _VP, _c.POINTER(_VP)]),
+    ("bpgpu_r1cs_verify_batch", _INT, [_VP, _VP, _VP, _VP, _VP, _VP, _SZ, _VP, _SZ, _VP, _VP, _VP, _VP, _SZ, _VP]),
+    ("bpgpu_r1cs_verify_batch_terms", _INT, [_VP, _VP, _VP, _VP, _VP, _VP, _SZ, _VP, _SZ, _VP, _VP, _VP, _VP, _SZ, _VP, _VP, _VP]),
     ("bpgpu_pbatch_create", _INT, [_VP, _VP, _VP, _VP, _VP, _SZ, _SZ, _c.POINTER(_VP)]),
     ("bpgpu_pbatch_free", None, [_VP]),
     ("bpgpu_pbatch_commit3", _INT, [_VP, _VP, _VP, _SZ, _VP, _VP, _VP]),
@@ -105,6 +112,12 @@ SYMBOLS_HOST = [
     ("bph_range_prove_many", _INT, [_VP, _SZ, _CS, _VP, _VP, _VP, _VP, _VP, _SZ, _SZ, _SZ, _INT, _U64, _VP, _SZ, _VP]),
     ("bph_range_prove_batch", _INT, [_VP, _CS, _VP, _VP, _VP, _VP, _VP, _SZ, _SZ, _SZ, _INT, _U64, _SZ, _VP, _SZ, _VP]),
     ("bph_range_verify_batch", _INT, [_VP, _CS, _VP, _VP, _VP, _VP, _SZ, _SZ, _SZ, _VP, _SZ, _VP, _SZ, _VP]),
+    ("bph_range_verify_batch_mode", _INT, [_VP, _CS, _VP, _VP, _VP, _VP, _SZ, _SZ, _SZ, _VP, _SZ, _VP, _INT, _SZ, _VP]),
+    ("bph_bound_check_verify_batch", _INT, [_VP, _CS, _VP, _VP, _VP, _VP, _SZ, _U64, _U64, _SZ, _VP, _SZ, _VP, _INT, _SZ, _VP]),
+    ("bph_range_circuit_csr", _INT, [_INT, _SZ, _SZ] + [_c.POINTER(_SZ)] * 4 + [_VP, _VP, _VP]),
+    ("bph_bound_check_circuit_csr", _INT, [_INT, _U64, _U64, _SZ] + [_c.POINTER(_SZ)] * 4 + [_VP, _VP, _VP]),
+    ("bph_r1cs_transcript_state", None, [_CS, _VP]),
+    ("bph_r1cs_replay_challenges", _INT, [_INT, _CS, _VP, _VP, _SZ, _SZ, _VP]),
     ("bph_msm_sharded", _INT, [_VP, _SZ, _VP, _VP, _VP, _VP]),
     ("bph_g1_sum", _INT, [_INT, _VP, _SZ, _VP]),
     ("bph_range_verify_many", _INT, [_VP, _SZ, _CS, _VP, _VP, _VP, _VP, _SZ, _SZ, _SZ, _VP, _SZ, _VP, _VP]),
@@ -193,15 +206,114 @@ def g1_sum(curve, points_xy):
     return out.raw
 
 
-def range_verify_batch(ctx, label, g_xy, h_xy, G, H, count, m, bits, proofs, stride, comms, nthreads=0):
-    """per-proof verdicts of `count` independent proofs from batched device calls, one per slab of 512 proofs, overlapped
-    with the host threads that build the scalars."""
+def range_verify_batch(ctx, label, g_xy, h_xy, G, H, count, m, bits, proofs, stride, comms, nthreads=0, mode=0):
+    """per-proof verdicts of `count` independent proofs from batched device calls (bph_range_verify_batch_mode):
+    mode 0 = transcripts and scalars on the device, 1 = transcripts on host threads, 2 = round 1's host-built scalars."""
     verdicts = (ctypes.c_int32 * max(1, count))()
-    rc = lib().bph_range_verify_batch(ctx.handle, label, _buf(g_xy), _buf(h_xy), G.handle, H.handle, count, m, bits, _buf(proofs), stride,
-                                      _buf(comms), nthreads, verdicts)
+    rc = lib().bph_range_verify_batch_mode(ctx.handle, label, _buf(g_xy), _buf(h_xy), G.handle, H.handle, count, m, bits, _buf(proofs), stride,
+                                           _buf(comms), mode, nthreads, verdicts)
     if rc:
         raise BpgpuError(rc, "range_verify_batch")
     return list(verdicts)[:count]
+
+
+def bound_check_verify_batch(ctx, label, g_xy, h_xy, G, H, count, lower, upper, bits, proofs, stride, comms, nthreads=0, mode=0):
+    """verify_proof_of_bounded_num for `count` proofs over the same bounds, one batched device call per slab"""
+    verdicts = (ctypes.c_int32 * max(1, count))()
+    rc = lib().bph_bound_check_verify_batch(ctx.handle, label, _buf(g_xy), _buf(h_xy), G.handle, H.handle, count, lower, upper, bits,
+                                            _buf(proofs), stride, _buf(comms), mode, nthreads, verdicts)
+    if rc:
+        raise BpgpuError(rc, "bound_check_verify_batch")
+    return list(verdicts)[:count]
+
+
+def _csr_call(fn, *args):
+    n, m, q, nnz = (ctypes.c_size_t() for _ in range(4))
+    refs = [ctypes.byref(x) for x in (n, m, q, nnz)]
+    rc = fn(*args, *refs, None, None, None)
+    if rc:
+        raise BpgpuError(rc, "circuit_csr")
+    mb = 48 if args[0] == BLS12_381 else 32
+    rows = (ctypes.c_uint32 * (3 * n.value + m.value + 2))()
+    eq = (ctypes.c_uint32 * max(1, nnz.value))()
+    ec = ctypes.create_string_buffer(max(1, nnz.value * mb))
+    rc = fn(*args, *refs, ctypes.cast(rows, ctypes.c_void_p), ctypes.cast(eq, ctypes.c_void_p), ctypes.cast(ec, ctypes.c_void_p))
+    if rc:
+        raise BpgpuError(rc, "circuit_csr")
+    return {"n": n.value, "m": m.value, "q": q.value, "row_start": list(rows), "ent_q": list(eq)[:nnz.value], "ent_c_be": ec.raw[:nnz.value * mb]}
+
+
+def range_circuit_csr(curve, m, bits):
+    """the flattened-constraints matrix of m x positive_no_gadget(bits) as CSR arrays (host only)"""
+    return _csr_call(lib().bph_range_circuit_csr, curve, m, bits)
+
+
+def bound_check_circuit_csr(curve, lower, upper, bits):
+    return _csr_call(lib().bph_bound_check_circuit_csr, curve, lower, upper, bits)
+
+
+def r1cs_transcript_state(label):
+    """exported Merlin state after Transcript::new(label) + r1cs_domain_sep() (203 bytes)"""
+    out = ctypes.create_string_buffer(203)
+    lib().bph_r1cs_transcript_state(label, out)
+    return out.raw
+
+
+def r1cs_replay_challenges(curve, label, proof, comms, m, lg):
+    """y, z, u, x, w, u_1..u_lg of one proof from a host transcript (big-endian scalars)"""
+    mb = 48 if curve == BLS12_381 else 32
+    out = ctypes.create_string_buffer((5 + lg) * mb)
+    rc = lib().bph_r1cs_replay_challenges(curve, label, _buf(proof), _buf(comms), m, lg, out)
+    if rc:
+        raise BpgpuError(rc, "r1cs_replay_challenges")
+    return out.raw
+
+
+class Circuit:
+    """bpgpu_circuit: a one-phase constraint system as a device-resident sparse matrix"""
+
+    def __init__(self, ctx, csr):
+        self.ctx, self.csr = ctx, csr
+        rows = (ctypes.c_uint32 * len(csr["row_start"]))(*csr["row_start"])
+        eq = (ctypes.c_uint32 * max(1, len(csr["ent_q"])))(*csr["ent_q"])
+        h = ctypes.c_void_p()
+        ctx._check(lib().bpgpu_circuit_create(ctx.handle, csr["n"], csr["m"], csr["q"], ctypes.cast(rows, ctypes.c_void_p),
+                                              ctypes.cast(eq, ctypes.c_void_p), _buf(csr["ent_c_be"]), ctypes.byref(h)), "circuit_create")
+        self.handle = h
+
+    def flatten(self, z_be):
+        """[wL | wR | wO | wV | wc] for the challenge z, as a DeviceScalars of 3n + m + 1 entries"""
+        h = ctypes.c_void_p()
+        self.ctx._check(lib().bpgpu_circuit_flatten(self.ctx.handle, self.handle, _buf(z_be), ctypes.byref(h)), "circuit_flatten")
+        return DeviceScalars(self.ctx, h)
+
+    def verify_batch(self, G, H, g_xy, h_xy, count, proofs, stride, comms, state=None, challenges=None, key=b"", terms=False):
+        """bpgpu_r1cs_verify_batch(_terms): verdict list (and, with terms=True, the fixed and variable scalars the device built)"""
+        verdicts = (ctypes.c_int32 * max(1, count))()
+        st = _buf(state) if state is not None else None
+        ch = _buf(challenges) if challenges is not None else None
+        if not terms:
+            self.ctx._check(lib().bpgpu_r1cs_verify_batch(self.ctx.handle, self.handle, G.handle, H.handle, _buf(g_xy), _buf(h_xy), count,
+                                                          _buf(proofs), stride, _buf(comms), st, ch, _buf(key), len(key), verdicts),
+                            "r1cs_verify_batch")
+            return list(verdicts)[:count]
+        n, m, mb = self.csr["n"], self.csr["m"], self.ctx.modbytes
+        N = 1
+        while N < n:
+            N <<= 1
+        lg = N.bit_length() - 1
+        F, vn = 2 * N + 2, 6 + m + 5 + 2 * lg
+        fixed = ctypes.create_string_buffer(max(1, count * F * mb))
+        var = ctypes.create_string_buffer(max(1, count * vn * mb))
+        self.ctx._check(lib().bpgpu_r1cs_verify_batch_terms(self.ctx.handle, self.handle, G.handle, H.handle, _buf(g_xy), _buf(h_xy), count,
+                                                            _buf(proofs), stride, _buf(comms), st, ch, _buf(key), len(key), verdicts, fixed,
+                                                            var), "r1cs_verify_batch_terms")
+        return list(verdicts)[:count], fixed.raw[:count * F * mb], var.raw[:count * vn * mb]
+
+    def free(self):
+        if self.handle:
+            lib().bpgpu_circuit_free(self.handle)
+            self.handle = None
 
 
 class BpgpuError(RuntimeError):

@@ -398,6 +398,7 @@ void bpgpu_ctx_destroy(bpgpu_ctx* c) {
   c->io_dev.release(); c->io_dev2.release();
   c->ipp_pts.release(); c->ipp_scl.release(); c->parts_pts.release(); c->parts_scl.release(); c->tbl_part.release();
   c->fr_tmp.release(); c->fr_out.release(); c->fr_args.release(); c->fr_pow.release(); c->fr_pow2.release();
+  c->vb.release();
   if (c->pinned) cudaFreeHost(c->pinned);
   cudaStreamDestroy(c->stream);
   if (c->copy_stream) cudaStreamDestroy(c->copy_stream);

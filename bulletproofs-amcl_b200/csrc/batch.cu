@@ -88,79 +88,94 @@ __global__ void __launch_bounds__(32) k_batch_horner(size_t batch, uint32_t vn, 
   is_identity[b] = acc.is_inf() ? 1 : 0;
 }
 
+// the launches for one slab whose inputs are already on the device: fixed scalars d_fs (cnt x F, canonical), the proofs' own
+// points d_vp / scalars d_vs (cnt x vn); scratch d_sum (cnt), d_m (cnt x vn x 15), d_w (64 x cnt); verdict bytes to d_v
+template <class Curve>
+int batch_identity_launch(bpgpu_ctx* ctx, const FixedRuns& runs, uint32_t F, size_t cnt, const void* d_fs, const void* d_vp, const void* d_vs,
+                          uint32_t vn, void* d_sum_, void* d_m_, void* d_w_, uint8_t* d_v) {
+  using Fq = typename Curve::Fq;
+  using Fr = typename Curve::Fr;
+  XYZZ<Fq>*d_sum = (XYZZ<Fq>*)d_sum_, *d_m = (XYZZ<Fq>*)d_m_, *d_w = (XYZZ<Fq>*)d_w_;
+  static const bool prof = getenv("BPGPU_PROFILE") != nullptr;
+  cudaEvent_t ev[3];
+  if (prof) { for (auto& e : ev) cudaEventCreate(&e); cudaEventRecord(ev[0], ctx->stream); }
+  k_batch_fixed<Curve><<<(unsigned)cnt, BATCH_FIXED_THREADS, 0, ctx->stream>>>(runs, F, (const Fr*)d_fs, 0, d_sum);
+  if (prof) cudaEventRecord(ev[1], ctx->stream);
+  if (vn) {
+    const size_t np = cnt * vn, nw = cnt * VAR_WINDOWS;
+    k_batch_multiples<Curve><<<(unsigned)((np + 63) / 64), 64, 0, ctx->stream>>>(np, (const Affine<Fq>*)d_vp, d_m);
+    k_batch_windows<Curve><<<(unsigned)((nw + 127) / 128), 128, 0, ctx->stream>>>(cnt, vn, (const Fr*)d_vs, d_m, d_w);
+    ctx->launches += 2;
+  }
+  k_batch_horner<Curve><<<(unsigned)((cnt + 31) / 32), 32, 0, ctx->stream>>>(cnt, vn, d_w, d_sum, d_v);
+  if (prof) {
+    cudaEventRecord(ev[2], ctx->stream);
+    cudaEventSynchronize(ev[2]);
+    float a, b;
+    cudaEventElapsedTime(&a, ev[0], ev[1]); cudaEventElapsedTime(&b, ev[1], ev[2]);
+    fprintf(stderr, "[bpgpu batch_identity n=%zu F=%u vn=%u] fixed=%.3f ms var=%.3f ms\n", cnt, F, vn, a, b);
+    for (auto& e : ev) cudaEventDestroy(e);
+  }
+  ctx->launches += 2;
+  return launch_check(ctx, "batch_identity");
+}
+template int batch_identity_launch<Bls>(bpgpu_ctx*, const FixedRuns&, uint32_t, size_t, const void*, const void*, const void*, uint32_t, void*, void*,
+                                        void*, uint8_t*);
+template int batch_identity_launch<Bn>(bpgpu_ctx*, const FixedRuns&, uint32_t, size_t, const void*, const void*, const void*, uint32_t, void*, void*,
+                                       void*, uint8_t*);
+
+template <class Curve>
+BatchScratch batch_scratch_layout(size_t slab, uint32_t F, uint32_t vn) {
+  using Fq = typename Curve::Fq;
+  using Fr = typename Curve::Fr;
+  auto up = [](size_t x) { return (x + 255) & ~(size_t)255; };
+  BatchScratch L;
+  size_t off = 0;
+  L.fs = off; off += up(slab * F * sizeof(Fr));
+  L.vs = off; off += up(slab * vn * sizeof(Fr));
+  L.vp = off; off += up(slab * vn * sizeof(Affine<Fq>));
+  L.sum = off; off += up(slab * sizeof(XYZZ<Fq>));
+  L.v = off; off += up(slab);
+  L.m = off; off += up(slab * (size_t)vn * VAR_DIGITS * sizeof(XYZZ<Fq>));
+  L.w = off; off += vn ? up(slab * (size_t)VAR_WINDOWS * sizeof(XYZZ<Fq>)) : 0;
+  L.total = off + 256;
+  return L;
+}
+template BatchScratch batch_scratch_layout<Bls>(size_t, uint32_t, uint32_t);
+template BatchScratch batch_scratch_layout<Bn>(size_t, uint32_t, uint32_t);
+
 template <class Curve>
 static int batch_identity_t(bpgpu_ctx* ctx, const FixedRuns& runs, uint32_t F, size_t batch, const uint8_t* fixed_scalars_be,
                             const uint8_t* var_points_xy, const uint8_t* var_scalars_be, uint32_t vn, uint8_t* is_identity) {
-  using Fq = typename Curve::Fq;
-  using Fr = typename Curve::Fr;
   const size_t SLAB = 4096;                               // proofs per launch pair: bounds the multiples scratch
   int rc;
   const size_t slab = batch < SLAB ? batch : SLAB;
-  // scratch: fixed scalars | var scalars | var points | fixed sums | verdicts | multiples
-  const size_t sz_fs = (slab * F * sizeof(Fr) + 255) & ~(size_t)255, sz_vs = (slab * vn * sizeof(Fr) + 255) & ~(size_t)255;
-  const size_t sz_vp = (slab * vn * sizeof(Affine<Fq>) + 255) & ~(size_t)255, sz_sum = (slab * sizeof(XYZZ<Fq>) + 255) & ~(size_t)255;
-  const size_t sz_v = (slab + 255) & ~(size_t)255, sz_m = (slab * (size_t)vn * VAR_DIGITS * sizeof(XYZZ<Fq>) + 255) & ~(size_t)255;
-  const size_t sz_w = vn ? slab * (size_t)VAR_WINDOWS * sizeof(XYZZ<Fq>) : 0;
-  if ((rc = ctx->msm_b.reserve(sz_fs + sz_vs + sz_vp + sz_sum + sz_v + sz_m + sz_w + 256))) return rc;
+  const BatchScratch L = batch_scratch_layout<Curve>(slab, F, vn);
+  if ((rc = ctx->msm_b.reserve(L.total))) return rc;
   uint8_t* base = (uint8_t*)ctx->msm_b.p;
-  Fr* d_fs = (Fr*)base; base += sz_fs;
-  Fr* d_vs = (Fr*)base; base += sz_vs;
-  Affine<Fq>* d_vp = (Affine<Fq>*)base; base += sz_vp;
-  XYZZ<Fq>* d_sum = (XYZZ<Fq>*)base; base += sz_sum;
-  uint8_t* d_v = base; base += sz_v;
-  XYZZ<Fq>* d_m = (XYZZ<Fq>*)base; base += sz_m;
-  XYZZ<Fq>* d_w = (XYZZ<Fq>*)base;
   const int mb = Curve::MODBYTES;
   for (size_t lo = 0; lo < batch; lo += slab) {
     const size_t cnt = batch - lo < slab ? batch - lo : slab;
     // canonical (non-Montgomery) scalars: the kernels only take digits
-    if ((rc = scalars_from_host<Curve>(ctx, fixed_scalars_be + lo * F * mb, cnt * F, 0, d_fs))) return rc;
+    if ((rc = scalars_from_host<Curve>(ctx, fixed_scalars_be + lo * F * mb, cnt * F, 0, base + L.fs))) return rc;
     if (vn) {
-      if ((rc = scalars_from_host<Curve>(ctx, var_scalars_be + lo * vn * mb, cnt * vn, 0, d_vs))) return rc;
-      if ((rc = points_from_host<Curve>(ctx, var_points_xy + lo * vn * 2 * mb, cnt * vn, d_vp))) return rc;
+      if ((rc = scalars_from_host<Curve>(ctx, var_scalars_be + lo * vn * mb, cnt * vn, 0, base + L.vs))) return rc;
+      if ((rc = points_from_host<Curve>(ctx, var_points_xy + lo * vn * 2 * mb, cnt * vn, base + L.vp))) return rc;
     }
-    static const bool prof = getenv("BPGPU_PROFILE") != nullptr;
-    cudaEvent_t ev[3];
-    if (prof) { for (auto& e : ev) cudaEventCreate(&e); cudaEventRecord(ev[0], ctx->stream); }
-    k_batch_fixed<Curve><<<(unsigned)cnt, BATCH_FIXED_THREADS, 0, ctx->stream>>>(runs, F, d_fs, 0, d_sum);
-    if (prof) cudaEventRecord(ev[1], ctx->stream);
-    if (vn) {
-      const size_t np = cnt * vn, nw = cnt * VAR_WINDOWS;
-      k_batch_multiples<Curve><<<(unsigned)((np + 63) / 64), 64, 0, ctx->stream>>>(np, d_vp, d_m);
-      k_batch_windows<Curve><<<(unsigned)((nw + 127) / 128), 128, 0, ctx->stream>>>(cnt, vn, d_vs, d_m, d_w);
-      ctx->launches += 2;
-    }
-    k_batch_horner<Curve><<<(unsigned)((cnt + 31) / 32), 32, 0, ctx->stream>>>(cnt, vn, d_w, d_sum, d_v);
-    if (prof) {
-      cudaEventRecord(ev[2], ctx->stream);
-      cudaEventSynchronize(ev[2]);
-      float a, b;
-      cudaEventElapsedTime(&a, ev[0], ev[1]); cudaEventElapsedTime(&b, ev[1], ev[2]);
-      fprintf(stderr, "[bpgpu batch_identity n=%zu F=%u vn=%u] fixed=%.3f ms var=%.3f ms\n", cnt, F, vn, a, b);
-      for (auto& e : ev) cudaEventDestroy(e);
-    }
-    ctx->launches += 2;
-    if ((rc = launch_check(ctx, "batch_identity"))) return rc;
-    BP_CUDA_OK(cudaMemcpyAsync(is_identity + lo, d_v, cnt, cudaMemcpyDeviceToHost, ctx->stream));
+    if ((rc = batch_identity_launch<Curve>(ctx, runs, F, cnt, base + L.fs, base + L.vp, base + L.vs, vn, base + L.sum, base + L.m, base + L.w,
+                                           base + L.v)))
+      return rc;
+    BP_CUDA_OK(cudaMemcpyAsync(is_identity + lo, base + L.v, cnt, cudaMemcpyDeviceToHost, ctx->stream));
     BP_CUDA_OK(stream_sync(ctx));
   }
   return BPGPU_OK;
 }
 
-}  // namespace bp
-
-using namespace bp;
-
-extern "C" int bpgpu_msm_batch_is_identity(bpgpu_ctx* ctx, const bpgpu_fixed_run* runs, size_t nruns, size_t batch,
-                                           const uint8_t* fixed_scalars_be, const uint8_t* var_points_xy, const uint8_t* var_scalars_be,
-                                           size_t vn, uint8_t* is_identity) {
-  if (!ctx || (!runs && nruns) || (batch && (!is_identity || (!fixed_scalars_be && nruns) || (vn && (!var_points_xy || !var_scalars_be)))))
-    return BPGPU_E_ARG;
-  if (nruns > (size_t)TBL_MAX_SEGS || vn > 4096) return BPGPU_E_ARG;
-  if (batch == 0) return BPGPU_OK;
-  BP_CUDA_OK(cudaSetDevice(ctx->device));
+// the fixed terms of a batch call: device tables (bpgpu_points_precompute) or single host bases (tables cached in the ctx)
+int resolve_fixed_runs(bpgpu_ctx* ctx, const bpgpu_fixed_run* runs, size_t nruns, FixedRuns* out, uint32_t* F_out) {
+  if (nruns > (size_t)TBL_MAX_SEGS) return BPGPU_E_ARG;
   const size_t asz = ctx->curve == BPGPU_BLS12_381 ? sizeof(Affine<Bls::Fq>) : sizeof(Affine<Bn::Fq>);
-  FixedRuns fr;
+  FixedRuns& fr = *out;
   fr.nruns = 0;
   uint32_t F = 0;
   for (size_t k = 0; k < nruns; k++) {
@@ -188,6 +203,26 @@ extern "C" int bpgpu_msm_batch_is_identity(bpgpu_ctx* ctx, const bpgpu_fixed_run
   }
   fr.start[fr.nruns] = F;
   if (fr.nruns == 0) { fr.nruns = 1; fr.table[0] = nullptr; fr.start[0] = 0; fr.start[1] = 0; }
+  *F_out = F;
+  return BPGPU_OK;
+}
+
+}  // namespace bp
+
+using namespace bp;
+
+extern "C" int bpgpu_msm_batch_is_identity(bpgpu_ctx* ctx, const bpgpu_fixed_run* runs, size_t nruns, size_t batch,
+                                           const uint8_t* fixed_scalars_be, const uint8_t* var_points_xy, const uint8_t* var_scalars_be,
+                                           size_t vn, uint8_t* is_identity) {
+  if (!ctx || (!runs && nruns) || (batch && (!is_identity || (!fixed_scalars_be && nruns) || (vn && (!var_points_xy || !var_scalars_be)))))
+    return BPGPU_E_ARG;
+  if (nruns > (size_t)TBL_MAX_SEGS || vn > 4096) return BPGPU_E_ARG;
+  if (batch == 0) return BPGPU_OK;
+  BP_CUDA_OK(cudaSetDevice(ctx->device));
+  FixedRuns fr;
+  uint32_t F = 0;
+  int rrc = resolve_fixed_runs(ctx, runs, nruns, &fr, &F);
+  if (rrc) return rrc;
   return ctx->curve == BPGPU_BLS12_381
              ? batch_identity_t<Bls>(ctx, fr, F, batch, fixed_scalars_be, var_points_xy, var_scalars_be, (uint32_t)vn, is_identity)
              : batch_identity_t<Bn>(ctx, fr, F, batch, fixed_scalars_be, var_points_xy, var_scalars_be, (uint32_t)vn, is_identity);

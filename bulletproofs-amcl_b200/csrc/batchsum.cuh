@@ -16,6 +16,14 @@ struct FixedRuns {
   int nruns;
 };
 
+// batch.cu: the verification MSMs of a slab of proofs from device-resident scalars and points (see batch.cu)
+struct BatchScratch { size_t fs, vs, vp, sum, v, m, w, total; };      // byte offsets into one scratch block
+template <class Curve> BatchScratch batch_scratch_layout(size_t slab, uint32_t F, uint32_t vn);
+template <class Curve>
+int batch_identity_launch(bpgpu_ctx* ctx, const FixedRuns& runs, uint32_t F, size_t cnt, const void* d_fs, const void* d_vp, const void* d_vs,
+                          uint32_t vn, void* d_sum, void* d_m, void* d_w, uint8_t* d_v);
+int resolve_fixed_runs(bpgpu_ctx* ctx, const bpgpu_fixed_run* runs, size_t nruns, FixedRuns* out, uint32_t* F_out);
+
 template <class Curve>
 __global__ void __launch_bounds__(BATCH_FIXED_THREADS, 3) k_batch_fixed(FixedRuns runs, uint32_t F, const typename Curve::Fr* __restrict__ scal, int mont,
                                                      XYZZ<typename Curve::Fq>* __restrict__ out) {

@@ -77,6 +77,7 @@ struct CarryChain {
 
 template <class P>
 struct Fp {
+  using Params = P;
   static constexpr int N = P::N;
   uint32_t v[N];
 

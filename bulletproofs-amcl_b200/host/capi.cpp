@@ -202,7 +202,7 @@ static int for_each_proof(bpgpu_ctx* const* ctxs, size_t nctx, size_t count, F f
 }
 
 template <class C>
-int range_verify_batch_t(bpgpu_ctx* ctx, const char* label, const uint8_t* g_xy, const uint8_t* h_xy, bpgpu_points* G, bpgpu_points* H,
+int range_verify_batch_hostscalars_t(bpgpu_ctx* ctx, const char* label, const uint8_t* g_xy, const uint8_t* h_xy, bpgpu_points* G, bpgpu_points* H,
                          size_t count, size_t m, size_t bits, const uint8_t* proofs, size_t stride, const uint8_t* comms_xy, size_t nthreads,
                          int32_t* verdicts) {
   const size_t mb = C::MODBYTES, pb = 2 * mb;
@@ -281,6 +281,144 @@ int range_verify_batch_t(bpgpu_ctx* ctx, const char* label, const uint8_t* g_xy,
   tr.mark("host + device, overlapped");
   for (size_t i = 0; i < count; i++)
     if (verdicts[i] == 0 && !ident_flags[i]) verdicts[i] = BPGPU_E_VERIFY;
+  return BPGPU_OK;
+}
+
+
+// circuit of `m` values range-checked to `bits` bits each (m x positive_no_gadget), recorded once for a whole batch
+template <class C>
+int range_circuit_csr(size_t m, size_t bits, typename Verifier<C>::CircuitCSR* csr) {
+  Transcript scratch{std::string("circuit")};
+  Verifier<C> rec(nullptr, scratch);
+  for (size_t k = 0; k < m; k++) {
+    Variable var = rec.commit(G1<C>::identity());
+    int st = positive_no_gadget<C>(rec, AllocatedQuantity<C>{var, false, FieldElement<C>::zero()}, bits);
+    if (st) return st;
+  }
+  return rec.export_csr(csr);
+}
+// bound_check_gadget over three commitments (v, v - min, max - v): gadgets/bound_check.rs:94-129
+template <class C>
+int bound_circuit_csr(uint64_t lower, uint64_t upper, size_t bits, typename Verifier<C>::CircuitCSR* csr) {
+  Transcript scratch{std::string("circuit")};
+  Verifier<C> rec(nullptr, scratch);
+  std::vector<G1<C>> comms(3, G1<C>::identity());
+  int st = verify_bounded_num<C>(lower, upper, bits, comms, rec);
+  if (st) return st;
+  return rec.export_csr(csr);
+}
+
+// the challenges of one proof from a host transcript (mode 1): y, z, u, x, w, u_1..u_lg as big-endian scalars.
+// Same appends as Verifier::replay_transcript + IPP::verification_challenges, on the raw proof bytes.
+template <class C>
+void replay_challenges_host(Transcript t, const uint8_t* proof, const uint8_t* comms_xy, size_t m, size_t lg, size_t N, uint8_t* out_be) {
+  const size_t mb = C::MODBYTES, PB = 2 * mb + 1;
+  uint8_t tagged[1 + 2 * 48];
+  tagged[0] = 4;
+  for (size_t j = 0; j < m; j++) { memcpy(tagged + 1, comms_xy + j * 2 * mb, 2 * mb); t.append_message("V", tagged, PB); }
+  t.append_u64("m", m);
+  auto pt = [&](const char* label, size_t k) { t.append_message(label, proof + k * PB, PB); };
+  auto ch = [&](const char* label, size_t slot) {
+    uint8_t buf[48];
+    t.challenge_bytes(label, buf, mb);
+    FieldElement<C>::from_bytes(buf).to_bytes(out_be + slot * mb);
+  };
+  pt("A_I1", 0); pt("A_O1", 1); pt("S1", 2);
+  t.r1cs_1phase_domain_sep();
+  pt("A_I2", 3); pt("A_O2", 4); pt("S2", 5);
+  ch("y", 0); ch("z", 1);
+  pt("T_1", 6); pt("T_3", 7); pt("T_4", 8); pt("T_5", 9); pt("T_6", 10);
+  ch("u", 2); ch("x", 3);
+  const uint8_t* sc = proof + 11 * PB;
+  t.append_message("t_x", sc, mb);
+  t.append_message("t_x_blinding", sc + mb, mb);
+  t.append_message("e_blinding", sc + 2 * mb, mb);
+  ch("w", 4);
+  t.innerproduct_domain_sep(N);
+  const uint8_t* L = sc + 3 * mb;
+  for (size_t k = 0; k < lg; k++) {
+    t.append_message("L", L + k * PB, PB);
+    t.append_message("R", L + (lg + k) * PB, PB);
+    ch("u", 5 + k);
+  }
+}
+
+// mode 0: transcripts replayed on the device; mode 1: transcripts on `nthreads` host threads, challenges uploaded
+template <class C>
+int verify_batch_device_t(bpgpu_ctx* ctx, const char* label, const uint8_t* g_xy, const uint8_t* h_xy, bpgpu_points* G, bpgpu_points* H,
+                          const typename Verifier<C>::CircuitCSR& csr, size_t count, const uint8_t* proofs, size_t stride, const uint8_t* comms_xy,
+                          int mode, size_t nthreads, int32_t* verdicts) {
+  const size_t mb = C::MODBYTES;
+  const size_t m = csr.m, N = next_power_of_two(csr.n);
+  size_t lg = 0;
+  while (((size_t)1 << lg) < N) lg++;
+  Trace tr("verify_batch_device");
+  bpgpu_circuit* circ = nullptr;
+  int rc = bpgpu_circuit_create(ctx, csr.n, csr.m, csr.q, csr.row_start.data(), csr.ent_q.data(), csr.ent_c_be.data(), &circ);
+  if (rc) return rc;
+  Transcript t0{std::string(label)};
+  t0.r1cs_domain_sep();                                   // Verifier::new (verifier.rs:97-108)
+  Rng<C> os;                                              // one key per call; proof i takes draw i (verifier.rs:392)
+  if (mode == 0) {
+    uint8_t state0[203];
+    t0.export_state(state0);
+    rc = bpgpu_r1cs_verify_batch(ctx, circ, G, H, g_xy, h_xy, count, proofs, stride, comms_xy, state0, nullptr, os.key(), os.key_len(), verdicts);
+  } else {
+    const size_t nch = 5 + lg;
+    std::vector<uint8_t> chal(count * nch * mb);
+    if (nthreads == 0) nthreads = std::thread::hardware_concurrency();
+    if (nthreads == 0) nthreads = 1;
+    if (nthreads > count) nthreads = count;
+    std::atomic<size_t> next{0};
+    auto worker = [&]() {
+      for (;;) {
+        const size_t lo = next.fetch_add(64);
+        if (lo >= count) break;
+        const size_t hi = lo + 64 < count ? lo + 64 : count;
+        for (size_t i = lo; i < hi; i++)
+          replay_challenges_host<C>(t0, proofs + i * stride, comms_xy + i * m * 2 * mb, m, lg, N, chal.data() + i * nch * mb);
+      }
+    };
+    std::vector<std::thread> th;
+    for (size_t k = 1; k < nthreads; k++) th.emplace_back(worker);
+    worker();
+    for (auto& x : th) x.join();
+    tr.mark("host transcripts");
+    rc = bpgpu_r1cs_verify_batch(ctx, circ, G, H, g_xy, h_xy, count, proofs, stride, comms_xy, nullptr, chal.data(), os.key(), os.key_len(), verdicts);
+  }
+  tr.mark("device");
+  bpgpu_circuit_free(circ);
+  return rc;
+}
+
+template <class C>
+int range_verify_batch_t(bpgpu_ctx* ctx, const char* label, const uint8_t* g_xy, const uint8_t* h_xy, bpgpu_points* G, bpgpu_points* H,
+                         size_t count, size_t m, size_t bits, const uint8_t* proofs, size_t stride, const uint8_t* comms_xy, int mode,
+                         size_t nthreads, int32_t* verdicts) {
+  if (mode == 2) return range_verify_batch_hostscalars_t<C>(ctx, label, g_xy, h_xy, G, H, count, m, bits, proofs, stride, comms_xy, nthreads, verdicts);
+  typename Verifier<C>::CircuitCSR csr;
+  int rc = range_circuit_csr<C>(m, bits, &csr);
+  if (rc) return rc;
+  return verify_batch_device_t<C>(ctx, label, g_xy, h_xy, G, H, csr, count, proofs, stride, comms_xy, mode, nthreads, verdicts);
+}
+
+template <class C>
+int bound_verify_batch_t(bpgpu_ctx* ctx, const char* label, const uint8_t* g_xy, const uint8_t* h_xy, bpgpu_points* G, bpgpu_points* H,
+                         size_t count, uint64_t lower, uint64_t upper, size_t bits, const uint8_t* proofs, size_t stride, const uint8_t* comms_xy,
+                         int mode, size_t nthreads, int32_t* verdicts) {
+  typename Verifier<C>::CircuitCSR csr;
+  int rc = bound_circuit_csr<C>(lower, upper, bits, &csr);
+  if (rc) return rc;
+  return verify_batch_device_t<C>(ctx, label, g_xy, h_xy, G, H, csr, count, proofs, stride, comms_xy, mode ? 1 : 0, nthreads, verdicts);
+}
+
+template <class C>
+int circuit_csr_export(const typename Verifier<C>::CircuitCSR& csr, size_t* n, size_t* m, size_t* q, size_t* nnz, uint32_t* row_start,
+                       uint32_t* ent_q, uint8_t* ent_c_be) {
+  *n = csr.n; *m = csr.m; *q = csr.q; *nnz = csr.ent_q.size();
+  if (row_start) memcpy(row_start, csr.row_start.data(), csr.row_start.size() * 4);
+  if (ent_q) memcpy(ent_q, csr.ent_q.data(), csr.ent_q.size() * 4);
+  if (ent_c_be) memcpy(ent_c_be, csr.ent_c_be.data(), csr.ent_q.size() * C::MODBYTES);
   return BPGPU_OK;
 }
 
@@ -563,15 +701,77 @@ int bph_msm_sharded(bpgpu_ctx* const* ctxs, size_t nctx, const bpgpu_points* con
   return bph_g1_sum(curve, partial.data(), nctx, out_xy);
 }
 
+int bph_range_verify_batch_mode(bpgpu_ctx* ctx, const char* label, const uint8_t* g_xy, const uint8_t* h_xy, bpgpu_points* G, bpgpu_points* H,
+                                size_t count, size_t m, size_t bits, const uint8_t* proofs, size_t proof_stride, const uint8_t* comms_xy,
+                                int mode, size_t nthreads, int32_t* verdicts) {
+  if (!ctx || !label || !g_xy || !h_xy || !G || !H || (count && (!proofs || !comms_xy || !verdicts)) || mode < 0 || mode > 2) return BPGPU_E_ARG;
+  if (!m || !bits || bits > 64) return BPGPU_E_ARG;
+  if (proof_stride < bph_range_proof_len(bpgpu_ctx_curve(ctx), m, bits)) return BPH_E_BUFFER;
+  if (count == 0) return BPGPU_OK;
+#define CALL(C) range_verify_batch_t<C>(ctx, label, g_xy, h_xy, G, H, count, m, bits, proofs, proof_stride, comms_xy, mode, nthreads, verdicts)
+  return BY_CURVE(ctx, CALL);
+#undef CALL
+}
+
 int bph_range_verify_batch(bpgpu_ctx* ctx, const char* label, const uint8_t* g_xy, const uint8_t* h_xy, bpgpu_points* G, bpgpu_points* H,
                            size_t count, size_t m, size_t bits, const uint8_t* proofs, size_t proof_stride, const uint8_t* comms_xy,
                            size_t nthreads, int32_t* verdicts) {
-  if (!ctx || !label || !g_xy || !h_xy || !G || !H || (count && (!proofs || !comms_xy || !verdicts))) return BPGPU_E_ARG;
-  if (proof_stride < bph_range_proof_len(bpgpu_ctx_curve(ctx), m, bits)) return BPH_E_BUFFER;
+  return bph_range_verify_batch_mode(ctx, label, g_xy, h_xy, G, H, count, m, bits, proofs, proof_stride, comms_xy, 0, nthreads, verdicts);
+}
+
+int bph_bound_check_verify_batch(bpgpu_ctx* ctx, const char* label, const uint8_t* g_xy, const uint8_t* h_xy, bpgpu_points* G, bpgpu_points* H,
+                                 size_t count, uint64_t lower, uint64_t upper, size_t bits, const uint8_t* proofs, size_t proof_stride,
+                                 const uint8_t* comms_xy, int mode, size_t nthreads, int32_t* verdicts) {
+  if (!ctx || !label || !g_xy || !h_xy || !G || !H || (count && (!proofs || !comms_xy || !verdicts)) || mode < 0 || mode > 1) return BPGPU_E_ARG;
+  if (!bits || bits > 64 || lower > upper) return BPGPU_E_ARG;
+  if (proof_stride < bph_range_proof_len(bpgpu_ctx_curve(ctx), 2, bits)) return BPH_E_BUFFER;
   if (count == 0) return BPGPU_OK;
-#define CALL(C) range_verify_batch_t<C>(ctx, label, g_xy, h_xy, G, H, count, m, bits, proofs, proof_stride, comms_xy, nthreads, verdicts)
+#define CALL(C) bound_verify_batch_t<C>(ctx, label, g_xy, h_xy, G, H, count, lower, upper, bits, proofs, proof_stride, comms_xy, mode, nthreads, verdicts)
   return BY_CURVE(ctx, CALL);
 #undef CALL
+}
+
+int bph_range_circuit_csr(int curve, size_t m, size_t bits, size_t* n, size_t* m_out, size_t* q, size_t* nnz, uint32_t* row_start, uint32_t* ent_q,
+                          uint8_t* ent_coeff_be) {
+  if (!n || !m_out || !q || !nnz || !m || !bits || bits > 64 || (curve != BPGPU_BLS12_381 && curve != BPGPU_BN254)) return BPGPU_E_ARG;
+  int rc;
+  if (curve == BPGPU_BLS12_381) {
+    Verifier<Bls381>::CircuitCSR csr;
+    if ((rc = range_circuit_csr<Bls381>(m, bits, &csr))) return rc;
+    return circuit_csr_export<Bls381>(csr, n, m_out, q, nnz, row_start, ent_q, ent_coeff_be);
+  }
+  Verifier<Bn254>::CircuitCSR csr;
+  if ((rc = range_circuit_csr<Bn254>(m, bits, &csr))) return rc;
+  return circuit_csr_export<Bn254>(csr, n, m_out, q, nnz, row_start, ent_q, ent_coeff_be);
+}
+
+int bph_bound_check_circuit_csr(int curve, uint64_t lower, uint64_t upper, size_t bits, size_t* n, size_t* m_out, size_t* q, size_t* nnz,
+                                uint32_t* row_start, uint32_t* ent_q, uint8_t* ent_coeff_be) {
+  if (!n || !m_out || !q || !nnz || !bits || bits > 64 || lower > upper || (curve != BPGPU_BLS12_381 && curve != BPGPU_BN254)) return BPGPU_E_ARG;
+  int rc;
+  if (curve == BPGPU_BLS12_381) {
+    Verifier<Bls381>::CircuitCSR csr;
+    if ((rc = bound_circuit_csr<Bls381>(lower, upper, bits, &csr))) return rc;
+    return circuit_csr_export<Bls381>(csr, n, m_out, q, nnz, row_start, ent_q, ent_coeff_be);
+  }
+  Verifier<Bn254>::CircuitCSR csr;
+  if ((rc = bound_circuit_csr<Bn254>(lower, upper, bits, &csr))) return rc;
+  return circuit_csr_export<Bn254>(csr, n, m_out, q, nnz, row_start, ent_q, ent_coeff_be);
+}
+
+int bph_r1cs_replay_challenges(int curve, const char* label, const uint8_t* proof, const uint8_t* comms_xy, size_t m, size_t lg, uint8_t* out_be) {
+  if (!label || !proof || (!comms_xy && m) || !out_be || lg >= 32 || (curve != BPGPU_BLS12_381 && curve != BPGPU_BN254)) return BPGPU_E_ARG;
+  Transcript t{std::string(label)};
+  t.r1cs_domain_sep();
+  if (curve == BPGPU_BLS12_381) replay_challenges_host<Bls381>(t, proof, comms_xy, m, lg, (size_t)1 << lg, out_be);
+  else replay_challenges_host<Bn254>(t, proof, comms_xy, m, lg, (size_t)1 << lg, out_be);
+  return BPGPU_OK;
+}
+
+void bph_r1cs_transcript_state(const char* label, uint8_t* out203) {
+  Transcript t{std::string(label)};
+  t.r1cs_domain_sep();
+  t.export_state(out203);
 }
 
 }  // extern "C"

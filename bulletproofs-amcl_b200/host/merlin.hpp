@@ -79,6 +79,12 @@ class Strobe128 {
   void meta_ad(const uint8_t* d, size_t n, bool more) { begin_op(FLAG_M | FLAG_A, more); absorb(d, n); }
   void ad(const uint8_t* d, size_t n, bool more) { begin_op(FLAG_A, more); absorb(d, n); }
   void prf(uint8_t* out, size_t n, bool more) { begin_op(FLAG_I | FLAG_A | FLAG_C, more); squeeze(out, n); }
+  // 200 state bytes | pos | pos_begin | cur_flags: where the device-side replay of a slab's transcripts starts
+  // (csrc/merlin.cuh StrobeHD::load)
+  void export_state(uint8_t out[203]) const {
+    memcpy(out, st_, 200);
+    out[200] = pos_; out[201] = pos_begin_; out[202] = cur_flags_;
+  }
 
  private:
   static constexpr uint8_t R = 166;
@@ -139,6 +145,7 @@ class Transcript {
   void r1cs_domain_sep() { append_message("dom-sep", std::string("r1cs v1")); }
   void r1cs_1phase_domain_sep() { append_message("dom-sep", std::string("r1cs-1phase")); }
   void r1cs_2phase_domain_sep() { append_message("dom-sep", std::string("r1cs-2phase")); }
+  void export_state(uint8_t out[203]) const { strobe_.export_state(out); }
 
  private:
   Strobe128 strobe_;

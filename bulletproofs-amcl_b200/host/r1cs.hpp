@@ -614,6 +614,50 @@ class Verifier : public ConstraintSystem<C> {
   }
 
   struct Challenges { FE y, z, u, x, w; size_t n1, n, padded_n; };
+
+ public:
+  // flattened_constraints (verifier.rs:149-193) as a sparse matrix, for circuits shared by a whole batch of proofs
+  // (bpgpu_circuit_create): rows = variables [wL 0..n) | wR | wO | wV 0..m) | wc], an entry = (constraint index q, coefficient)
+  // meaning coefficient * z^(q+1), with the signs of :166-190 applied (committed and constant terms negated).
+  // ent_q flags coefficients +1 (bit 31) and -1 (bit 30).  One-phase circuits only (no deferred constraints): E_ARG otherwise.
+  struct CircuitCSR { size_t n = 0, m = 0, q = 0; std::vector<uint32_t> row_start, ent_q; std::vector<uint8_t> ent_c_be; };
+  int export_csr(CircuitCSR* out) const {
+    if (!deferred_.empty() || constraints_.size() >= (1u << 30)) return E_ARG;
+    const size_t n = num_vars_, m = V_.size(), rows = 3 * n + m + 1;
+    auto row_of = [&](const Variable& v) -> size_t {
+      switch (v.kind) {
+        case Variable::MultiplierLeft: return v.index;
+        case Variable::MultiplierRight: return n + v.index;
+        case Variable::MultiplierOutput: return 2 * n + v.index;
+        case Variable::Committed: return 3 * n + v.index;
+        default: return 3 * n + m;
+      }
+    };
+    out->n = n; out->m = m; out->q = constraints_.size();
+    out->row_start.assign(rows + 1, 0);
+    for (const LC& lc : constraints_)
+      for (const auto& t : lc.terms) out->row_start[row_of(t.first) + 1]++;
+    for (size_t r = 0; r < rows; r++) out->row_start[r + 1] += out->row_start[r];
+    const size_t nnz = out->row_start[rows];
+    out->ent_q.assign(nnz, 0);
+    out->ent_c_be.assign(nnz * C::MODBYTES + 1, 0);
+    std::vector<uint32_t> fill(out->row_start.begin(), out->row_start.end() - 1);
+    const FE one = FE::one(), minus_one = FE::minus_one();
+    uint32_t q = 0;
+    for (const LC& lc : constraints_) {
+      for (const auto& t : lc.terms) {
+        const bool neg = t.first.kind == Variable::Committed || t.first.kind == Variable::One;
+        const FE c = neg ? t.second.negation() : t.second;
+        const uint32_t e = fill[row_of(t.first)]++;
+        out->ent_q[e] = q | (c == one ? 0x80000000u : 0u) | (c == minus_one ? 0x40000000u : 0u);
+        c.to_bytes(out->ent_c_be.data() + (size_t)e * C::MODBYTES);
+      }
+      q++;
+    }
+    return OK;
+  }
+
+ private:
   // verifier.rs:279-323: absorb the proof, derive y, z, u, x, w (and run the deferred constraints in between)
   int replay_transcript(const R1CSProof<C>& proof, size_t gens_len, Challenges* c) {
     transcript_.append_u64("m", V_.size());                            // :279

@@ -138,6 +138,45 @@ int bpgpu_msm_parts_batch(bpgpu_ctx* ctx, const bpgpu_msm_part* parts, const siz
 typedef struct bpgpu_fixed_run { const bpgpu_points* points; size_t off; size_t n; const uint8_t* host_base_xy; } bpgpu_fixed_run;
 int bpgpu_msm_batch_is_identity(bpgpu_ctx* ctx, const bpgpu_fixed_run* runs, size_t nruns, size_t batch, const uint8_t* fixed_scalars_be,
                                 const uint8_t* var_points_xy, const uint8_t* var_scalars_be, size_t vn, uint8_t* is_identity);
+/* ---- batched R1CS verification, per-proof scalars built on the device (csrc/verifybatch.cu) -----------------------------
+ * A bpgpu_circuit is the constraint system of a ONE-PHASE circuit in the form Verifier::flattened_constraints
+ * (verifier.rs:149-193; Prover: prover.rs:142-184) consumes it, as a sparse matrix shared by every proof of a batch:
+ * rows = variables [wL 0..n) | wR 0..n) | wO 0..n) | wV 0..m) | wc] (row_start: 3n + m + 2 offsets), entry e of a row =
+ * (ent_q[e] & 0x3fffffff = constraint index k, ent_coeff_be[e]) meaning coefficient * z^(k+1), with the signs of
+ * verifier.rs:166-190 applied by the caller (committed and constant terms negated).  Bits 31 / 30 of ent_q flag the
+ * coefficients +1 / -1 (the product is skipped).  q = number of constraints.  host/r1cs.hpp Verifier::export_csr builds it.
+ * bpgpu_circuit_flatten: [wL | wR | wO | wV | wc] for one challenge z (3n + m + 1 device scalars). */
+typedef struct bpgpu_circuit bpgpu_circuit;
+int bpgpu_circuit_create(bpgpu_ctx* ctx, size_t n, size_t m, size_t q, const uint32_t* row_start, const uint32_t* ent_q,
+                         const uint8_t* ent_coeff_be, bpgpu_circuit** out);
+void bpgpu_circuit_free(bpgpu_circuit* c);
+size_t bpgpu_circuit_multipliers(const bpgpu_circuit* c);
+size_t bpgpu_circuit_commitments(const bpgpu_circuit* c);
+int bpgpu_circuit_flatten(bpgpu_ctx* ctx, const bpgpu_circuit* c, const uint8_t* z_be, bpgpu_scalars** out);
+/* Verifier::verify (verifier.rs:267-457) for `count` independent proofs of `circuit`: verdicts[i] = BPGPU_OK,
+ * BPGPU_E_VERIFY (VerificationError) or BPGPU_E_FORMAT (missing 0x04 tag, scalar >= r, coordinate >= p, point off the
+ * curve).  proofs = count records of proof_stride bytes in the flat form A_I1 A_O1 S1 A_I2 A_O2 S2 T_1 T_3 T_4 T_5 T_6
+ * (0x04||X||Y each) | t_x t_x_blinding e_blinding | L_1..L_lg | R_1..R_lg | a | b; comms_xy = count x m commitments X||Y.
+ * Challenges come from EXACTLY ONE of
+ *   transcript_state: the 203-byte exported Merlin state (200 STROBE state bytes | pos | pos_begin | 0) after
+ *                     Transcript::new(label) and r1cs_domain_sep(); the device replays every proof's transcript from there
+ *                     (verifier.rs:124-132,279-323; ipp.rs:278-288), one thread per proof;
+ *   challenges_be:    count x (5 + lg) scalars y, z, u, x, w, u_1..u_lg from the caller's own transcripts.
+ * Everything else -- the circuit's weights from z, the s vector (ipp.rs:295-312), y^-i, delta, g/h scalars
+ * (verifier.rs:341-390), the 13 + m head scalars (:392-429) -- is built on the device, one block per proof, straight into
+ * the scalar slab of the batched MSM check.  The verifier's random scalar of proof i (verifier.rs:392) is draw i of the
+ * counter-mode stream SHAKE256(rnd_key || le64(i)) mod r (host layer: Rng); pass fresh entropy as rnd_key.
+ * G and H get window tables on first use.  Nothing is merged across proofs. */
+int bpgpu_r1cs_verify_batch(bpgpu_ctx* ctx, const bpgpu_circuit* circuit, bpgpu_points* G, bpgpu_points* H, const uint8_t* g_xy,
+                            const uint8_t* h_xy, size_t count, const uint8_t* proofs, size_t proof_stride, const uint8_t* comms_xy,
+                            const uint8_t* transcript_state, const uint8_t* challenges_be, const uint8_t* rnd_key, size_t rnd_key_len,
+                            int32_t* verdicts);
+/* test hook: the same call (count <= 4096) that also returns the scalars the device built: count x (2N + 2) for
+ * [G | H | g | h] and count x (6 + m + 5 + 2 lg) for [A_I1 A_O1 S1 A_I2 A_O2 S2 | V | T_1 T_3 T_4 T_5 T_6 | L | R] */
+int bpgpu_r1cs_verify_batch_terms(bpgpu_ctx* ctx, const bpgpu_circuit* circuit, bpgpu_points* G, bpgpu_points* H, const uint8_t* g_xy,
+                                  const uint8_t* h_xy, size_t count, const uint8_t* proofs, size_t proof_stride, const uint8_t* comms_xy,
+                                  const uint8_t* transcript_state, const uint8_t* challenges_be, const uint8_t* rnd_key,
+                                  size_t rnd_key_len, int32_t* verdicts, uint8_t* fixed_scalars_be, uint8_t* var_scalars_be);
 /* window width the MSM would use for n terms (reporting only) */
 int bpgpu_msm_window_bits(size_t n);
 

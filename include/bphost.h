@@ -85,15 +85,42 @@ int bph_range_verify_many(bpgpu_ctx* const* ctxs, size_t nctx, const char* trans
                           const bpgpu_points* G, const bpgpu_points* H, size_t count, size_t m, size_t bits, const uint8_t* proofs,
                           size_t proof_stride, const uint8_t* comms_xy, int32_t* verdicts);
 
-/* The same verdicts as bph_range_verify_many from batched device calls (bpgpu_msm_batch_is_identity): `nthreads` host
- * threads (0 = all cores) replay the transcripts and build every proof's verification scalars on the host (O(n) field
- * operations per proof) in slabs of 512 or 1024 proofs; every completed slab is evaluated by one group of launches (all of
- * its verification MSMs at once, one verdict byte per proof) while the threads build the next slab.  G and H get
- * window tables on first use (bpgpu_points_precompute).  Meant for small circuits verified in bulk (config 5: 64-bit
- * range proofs, n = 64). */
+/* The same verdicts as bph_range_verify_many from ONE batched device call per slab of <= 4096 proofs
+ * (bpgpu_r1cs_verify_batch, csrc/verifybatch.cu): the circuit (m x positive_no_gadget) is recorded once as a sparse matrix
+ * (Verifier::export_csr -> bpgpu_circuit), the host uploads proof and commitment bytes, and the device replays every proof's
+ * transcript (one thread per proof), builds its O(N) verification scalars (one block per proof: flattened constraints from
+ * z, the s vector, y^-i, delta, g/h scalars, head scalars) and evaluates its verification MSM -- one verdict per proof,
+ * nothing merged.  G and H get window tables on first use (bpgpu_points_precompute).
+ * bph_range_verify_batch_mode selects where the transcripts run:
+ *   mode 0  on the device (default; what bph_range_verify_batch does; `nthreads` unused);
+ *   mode 1  on `nthreads` host threads (0 = all cores) as the reference's design has it; only the 5 + lg challenges per
+ *           proof are uploaded, everything else as mode 0;
+ *   mode 2  round 1's path: transcripts AND all scalars on host threads (bpgpu_msm_batch_is_identity) -- kept for A/B runs. */
 int bph_range_verify_batch(bpgpu_ctx* ctx, const char* transcript_label, const uint8_t* g_xy, const uint8_t* h_xy, bpgpu_points* G,
                            bpgpu_points* H, size_t count, size_t m, size_t bits, const uint8_t* proofs, size_t proof_stride,
                            const uint8_t* comms_xy, size_t nthreads, int32_t* verdicts);
+int bph_range_verify_batch_mode(bpgpu_ctx* ctx, const char* transcript_label, const uint8_t* g_xy, const uint8_t* h_xy, bpgpu_points* G,
+                                bpgpu_points* H, size_t count, size_t m, size_t bits, const uint8_t* proofs, size_t proof_stride,
+                                const uint8_t* comms_xy, int mode, size_t nthreads, int32_t* verdicts);
+/* verify_proof_of_bounded_num (gadgets/bound_check.rs:163-178) for `count` proofs over the same [lower, upper] and
+ * max_bits_in_val: 3 commitments per proof (v, v - lower, upper - v), n = 2 * bits multipliers; modes 0 and 1 as above.
+ * Proof records as bph_range_proof_len(curve, 2, bits). */
+int bph_bound_check_verify_batch(bpgpu_ctx* ctx, const char* transcript_label, const uint8_t* g_xy, const uint8_t* h_xy, bpgpu_points* G,
+                                 bpgpu_points* H, size_t count, uint64_t lower, uint64_t upper, size_t max_bits_in_val,
+                                 const uint8_t* proofs, size_t proof_stride, const uint8_t* comms_xy, int mode, size_t nthreads,
+                                 int32_t* verdicts);
+/* The recorded circuits as CSR arrays (host only, no device needed; see bpgpu_circuit_create for the layout).  Call once
+ * with the array pointers NULL to get n, m, q, nnz, then with buffers of 3n + m + 2, nnz and nnz * MODBYTES entries. */
+int bph_range_circuit_csr(int curve, size_t m, size_t bits, size_t* n, size_t* m_out, size_t* q, size_t* nnz, uint32_t* row_start,
+                          uint32_t* ent_q, uint8_t* ent_coeff_be);
+int bph_bound_check_circuit_csr(int curve, uint64_t lower, uint64_t upper, size_t bits, size_t* n, size_t* m_out, size_t* q, size_t* nnz,
+                                uint32_t* row_start, uint32_t* ent_q, uint8_t* ent_coeff_be);
+/* exported Merlin state (203 bytes) after Transcript::new(label) + r1cs_domain_sep(): bpgpu_r1cs_verify_batch's transcript_state */
+void bph_r1cs_transcript_state(const char* transcript_label, uint8_t* out203);
+/* the challenges y, z, u, x, w, u_1..u_lg ((5 + lg) x MODBYTES, big endian) of one proof of a one-phase circuit with m
+ * commitments from a HOST transcript (verifier.rs:279-323, ipp.rs:278-288): bpgpu_r1cs_verify_batch's challenges_be */
+int bph_r1cs_replay_challenges(int curve, const char* transcript_label, const uint8_t* proof, const uint8_t* comms_xy, size_t m, size_t lg,
+                               uint8_t* out_be);
 
 /* `count` independent range proofs (m x `bits`-bit values each) proved in LOCK-STEP on one context (bpgpu_pbatch_*): one
  * device call per prover stage and per IPP round for a whole slab of proofs, the transcripts on `nthreads` host threads

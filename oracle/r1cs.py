@@ -76,6 +76,27 @@ class R1CSProof:
         return out + C.fr_to_bytes(ip.a) + C.fr_to_bytes(ip.b)
 
 
+    @classmethod
+    def from_bytes(cls, C, buf):
+        """inverse of to_bytes (fixture format of this repo)"""
+        PB, SB = 1 + 2 * C.MODBYTES, C.MODBYTES
+        lg = (len(buf) - 11 * PB - 5 * SB) // (2 * PB)
+        assert len(buf) == 11 * PB + 5 * SB + 2 * lg * PB
+        kw, off = {}, 0
+        for k in cls.POINTS:
+            kw[k] = C.g1_from_bytes(buf[off:off + PB])
+            off += PB
+        for k in cls.SCALARS:
+            kw[k] = int.from_bytes(buf[off:off + SB], "big")
+            off += SB
+        L = [C.g1_from_bytes(buf[off + k * PB:off + (k + 1) * PB]) for k in range(lg)]
+        off += lg * PB
+        R = [C.g1_from_bytes(buf[off + k * PB:off + (k + 1) * PB]) for k in range(lg)]
+        off += lg * PB
+        a, b = int.from_bytes(buf[off:off + SB], "big"), int.from_bytes(buf[off + SB:off + 2 * SB], "big")
+        return cls(ipp_proof=ipp_mod.IPPProof(L, R, a, b), **kw)
+
+
 class Prover:
     def __init__(self, C, g, h, transcript):               # prover.rs:84-101
         transcript.r1cs_domain_sep()
