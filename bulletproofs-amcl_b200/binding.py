@@ -3,6 +3,7 @@ FieldElement::to_bytes() (MODBYTES big endian), points are G1::to_bytes()[1:] (X
 import ctypes
 import os
 import subprocess
+import weakref
 
 BLS12_381 = 0
 BN254 = 1
@@ -280,6 +281,7 @@ class Circuit:
         ctx._check(lib().bpgpu_circuit_create(ctx.handle, csr["n"], csr["m"], csr["q"], ctypes.cast(rows, ctypes.c_void_p),
                                               ctypes.cast(eq, ctypes.c_void_p), _buf(csr["ent_c_be"]), ctypes.byref(h)), "circuit_create")
         self.handle = h
+        ctx._track(self)
 
     def flatten(self, z_be):
         """[wL | wR | wO | wV | wc] for the challenge z, as a DeviceScalars of 3n + m + 1 entries"""
@@ -365,6 +367,7 @@ def _buf(b):
 class DevicePoints:
     def __init__(self, ctx, handle):
         self.ctx, self.handle = ctx, handle
+        ctx._track(self)
 
     def __len__(self):
         return lib().bpgpu_points_len(self.handle)
@@ -393,6 +396,7 @@ class DevicePoints:
 class DeviceScalars:
     def __init__(self, ctx, handle):
         self.ctx, self.handle = ctx, handle
+        ctx._track(self)
 
     def __len__(self):
         return lib().bpgpu_scalars_len(self.handle)
@@ -425,15 +429,30 @@ class Context:
             raise BpgpuError(rc, "bpgpu_ctx_create")
         self.handle, self.curve, self.device = h, curve, device
         self.modbytes = lib().bpgpu_modbytes(curve)
+        self._live = weakref.WeakSet()          # device handles created on this context: released before the context is
+
+    def _track(self, obj):
+        self._live.add(obj)
 
     def _check(self, rc, what):
         if rc:
             raise BpgpuError(rc, what)
 
     def close(self):
+        """destroy the context; handles still alive on it are freed first (freeing one after its context would be a
+        use-after-free on the C side)"""
         if self.handle:
+            for obj in list(self._live):
+                obj.free()
             lib().bpgpu_ctx_destroy(self.handle)
             self.handle = None
+
+    def __enter__(self):
+        return self
+
+    def __exit__(self, *exc):
+        self.close()
+        return False
 
     @property
     def stream(self):

@@ -22,22 +22,19 @@ int launch_check(bpgpu_ctx* ctx, const char* what) {
 }
 
 // ------------------------------------------------------------------ conversion kernels
+// X || Y -> affine Montgomery form.  Validity is decided as AMCL's ECP::frombytes / new_bigs do (coordinates < p, on the curve,
+// (0, 1) = identity); an invalid point becomes the identity on the device and raises the ctx's bad-input word, which fails
+// the entry point that consumed it with BPGPU_E_FORMAT.
 template <class Curve>
-__global__ void k_points_from_be(const uint8_t* __restrict__ xy, size_t n, Affine<typename Curve::Fq>* __restrict__ out) {
+__global__ void k_points_from_be(const uint8_t* __restrict__ xy, size_t n, Affine<typename Curve::Fq>* __restrict__ out, uint32_t* bad) {
   using Fq = typename Curve::Fq;
   size_t i = (size_t)blockIdx.x * blockDim.x + threadIdx.x;
   if (i >= n) return;
-  const uint8_t* p = xy + i * 2 * Curve::MODBYTES;
   Affine<Fq> a;
-  be_to_limbs<Fq::N>(p, Curve::MODBYTES, a.x.v);
-  be_to_limbs<Fq::N>(p + Curve::MODBYTES, Curve::MODBYTES, a.y.v);
-  bool y_one = a.y.v[0] == 1;
-  for (int k = 1; k < Fq::N; k++) y_one = y_one && a.y.v[k] == 0;
-  if (a.x.is_zero() && y_one) {
-    a = Affine<Fq>::inf();                 // AMCL's identity (0, 1)
-  } else {
-    canonicalise(a.x); canonicalise(a.y);
-    a.x = a.x.to_mont(); a.y = a.y.to_mont();
+  if (!g1_from_be_checked<Curve>(xy + i * 2 * Curve::MODBYTES, &a)) {
+    a = Affine<Fq>::inf();
+    *(volatile uint32_t*)bad = 1;
+    __threadfence_system();
   }
   store_vec(out + i, a);
 }
@@ -62,16 +59,25 @@ __global__ void k_points_to_be(const Affine<typename Curve::Fq>* __restrict__ in
   affine_to_be2(a, Curve::MODBYTES, xy + i * 2 * Curve::MODBYTES);
 }
 
-// big-endian MODBYTES -> Fr; mont = 0 leaves the canonical integer (MSM digit source)
+// big-endian MODBYTES -> Fr, reduced mod r as FieldElement::from(&[u8; MODBYTES]) does (all 48 bytes count on BLS12-381);
+// mont = 0 leaves the canonical integer (MSM digit source)
 template <class Curve>
 __global__ void k_scalars_from_be(const uint8_t* __restrict__ be, size_t n, int mont, typename Curve::Fr* __restrict__ out) {
   using Fr = typename Curve::Fr;
   size_t i = (size_t)blockIdx.x * blockDim.x + threadIdx.x;
   if (i >= n) return;
+  const uint8_t* src = be + i * Curve::MODBYTES;
+  bool wide = false;
+  for (int k = 0; k < Curve::MODBYTES - 32; k++) wide = wide || src[k] != 0;
   Fr s;
-  be_to_limbs<8>(be + i * Curve::MODBYTES, Curve::MODBYTES, s.v);
-  canonicalise(s);
-  if (mont) s = s.to_mont();
+  if (wide) {
+    s = fr_from_be_wide<Curve>(src);
+    if (!mont) s = s.from_mont();
+  } else {
+    be_to_limbs<8>(src, Curve::MODBYTES, s.v);
+    canonicalise(s);
+    if (mont) s = s.to_mont();
+  }
   store_vec(out + i, s);
 }
 
@@ -200,7 +206,7 @@ static int points_from_host_on(bpgpu_ctx* ctx, cudaStream_t st, const uint8_t* x
   int rc = ctx->io_dev.reserve(bytes);
   if (rc) return rc;
   BP_CUDA_OK(cudaMemcpyAsync(ctx->io_dev.p, xy, bytes, cudaMemcpyHostToDevice, st));
-  k_points_from_be<Curve><<<(unsigned)((n + 127) / 128), 128, 0, st>>>((const uint8_t*)ctx->io_dev.p, n, (Affine<typename Curve::Fq>*)dst);
+  k_points_from_be<Curve><<<(unsigned)((n + 127) / 128), 128, 0, st>>>((const uint8_t*)ctx->io_dev.p, n, (Affine<typename Curve::Fq>*)dst, ctx->bad_input);
   ctx->launches++;
   return launch_check(ctx, "k_points_from_be");
 }
@@ -293,6 +299,7 @@ int msm_mixed_to_host(bpgpu_ctx* ctx, const TableSeg* segs, int nsegs, const voi
     else BP_CUDA_OK(cudaMemcpyAsync(tsum, ctx->tbl_part.p, psz, cudaMemcpyDeviceToHost, ctx->stream));
   }
   if (res.W || tn) BP_CUDA_OK(stream_sync(ctx));
+  if ((rc = inputs_ok(ctx))) return rc;
   if (hp) { if (bls) host_sum_partials<BlsFq>(tsum, 1, hp); else host_sum_partials<BnFq>(tsum, 1, hp); }
   if (bls) msm_finish_mixed<BlsFq>(ctx->pinned, res.W, res.c, res.qshift, tn ? tsum : nullptr, mb, out_xy);
   else msm_finish_mixed<BnFq>(ctx->pinned, res.W, res.c, res.qshift, tn ? tsum : nullptr, mb, out_xy);
@@ -313,6 +320,7 @@ int msm_pair_to_host(bpgpu_ctx* ctx, const void* d_pts, const void* d_scal_a, co
     BP_CUDA_OK(cudaMemcpyAsync(ctx->pinned, res.d_winsum, (size_t)4 * res.W * psz, cudaMemcpyDeviceToHost, ctx->stream));
     BP_CUDA_OK(stream_sync(ctx));
   }
+  if ((rc = inputs_ok(ctx))) return rc;
   uint8_t* outs[2] = {out_a_xy, out_b_xy};
   for (int s = 0; s < 2; s++) {
     if (bls) msm_finish_mixed<BlsFq>(ctx->pinned, res.W, res.c, res.qshift, nullptr, mb, outs[s], s, 2);
@@ -369,21 +377,42 @@ int bpgpu_ctx_create(int curve, int device, bpgpu_ctx** out) {
   if (!c) return BPGPU_E_CUDA;
   c->curve = curve;
   c->device = device;
+  // any failure below releases what was created so far (bpgpu_ctx_destroy copes with a partially built ctx)
+#define CTX_OK(expr)                                                                           \
+  do {                                                                                         \
+    cudaError_t _e = (expr);                                                                   \
+    if (_e != cudaSuccess) {                                                                   \
+      fprintf(stderr, "bpgpu: CUDA error %s at %s:%d\n", cudaGetErrorString(_e), __FILE__, __LINE__); \
+      bpgpu_ctx_destroy(c);                                                                    \
+      return BPGPU_E_CUDA;                                                                     \
+    }                                                                                          \
+  } while (0)
   cudaDeviceProp prop;
-  BP_CUDA_OK(cudaGetDeviceProperties(&prop, device));
+  CTX_OK(cudaGetDeviceProperties(&prop, device));
   c->sm_count = prop.multiProcessorCount;
-  BP_CUDA_OK(cudaStreamCreateWithFlags(&c->stream, cudaStreamNonBlocking));
-  BP_CUDA_OK(cudaStreamCreateWithFlags(&c->copy_stream, cudaStreamNonBlocking));
-  BP_CUDA_OK(cudaEventCreateWithFlags(&c->points_ready, cudaEventDisableTiming));
-  BP_CUDA_OK(cudaEventCreateWithFlags(&c->sync_event, cudaEventDisableTiming | cudaEventBlockingSync));
+  CTX_OK(cudaStreamCreateWithFlags(&c->stream, cudaStreamNonBlocking));
+  CTX_OK(cudaStreamCreateWithFlags(&c->copy_stream, cudaStreamNonBlocking));
+  CTX_OK(cudaEventCreateWithFlags(&c->points_ready, cudaEventDisableTiming));
+  CTX_OK(cudaEventCreateWithFlags(&c->sync_event, cudaEventDisableTiming | cudaEventBlockingSync));
   { const char* e = getenv("BPGPU_BLOCKING_SYNC"); c->blocking_sync = e && atoi(e) != 0; }
   {
-    cudaMemPool_t pool;
-    uint64_t keep = ~0ull;                      // keep freed blocks in the pool: the next proof reuses them
-    if (cudaDeviceGetDefaultMemPool(&pool, device) == cudaSuccess) cudaMemPoolSetAttribute(pool, cudaMemPoolAttrReleaseThreshold, &keep);
+    // a memory pool of the ctx's own for handle storage: freed blocks stay in it for the next proof (release threshold
+    // raised), without touching the device's default pool that other cudaMallocAsync users of the process share
+    cudaMemPoolProps pp;
+    memset(&pp, 0, sizeof pp);
+    pp.allocType = cudaMemAllocationTypePinned;
+    pp.handleTypes = cudaMemHandleTypeNone;
+    pp.location.type = cudaMemLocationTypeDevice;
+    pp.location.id = device;
+    CTX_OK(cudaMemPoolCreate(&c->pool, &pp));
+    uint64_t keep = ~0ull;
+    CTX_OK(cudaMemPoolSetAttribute(c->pool, cudaMemPoolAttrReleaseThreshold, &keep));
   }
   c->pinned_cap = 1 << 18;
-  BP_CUDA_OK(cudaHostAlloc((void**)&c->pinned, c->pinned_cap, cudaHostAllocDefault));
+  CTX_OK(cudaHostAlloc((void**)&c->pinned, c->pinned_cap, cudaHostAllocDefault));
+  CTX_OK(cudaHostAlloc((void**)&c->bad_input, 64, cudaHostAllocMapped));
+  *c->bad_input = 0;
+#undef CTX_OK
   *out = c;
   return BPGPU_OK;
 }
@@ -391,7 +420,7 @@ int bpgpu_ctx_create(int curve, int device, bpgpu_ctx** out) {
 void bpgpu_ctx_destroy(bpgpu_ctx* c) {
   if (!c) return;
   cudaSetDevice(c->device);
-  cudaStreamSynchronize(c->stream);
+  if (c->stream) cudaStreamSynchronize(c->stream);
   for (bpgpu_fixed_bases* fb : c->fb_cache) bpgpu_fixed_bases_free(fb);
   c->fb_cache.clear();
   c->msm_a.release(); c->msm_b.release(); c->msm_c.release(); c->msm_d.release(); c->msm_e.release();
@@ -400,8 +429,10 @@ void bpgpu_ctx_destroy(bpgpu_ctx* c) {
   c->fr_tmp.release(); c->fr_out.release(); c->fr_args.release(); c->fr_pow.release(); c->fr_pow2.release();
   c->vb.release();
   if (c->pinned) cudaFreeHost(c->pinned);
-  cudaStreamDestroy(c->stream);
+  if (c->bad_input) cudaFreeHost(c->bad_input);
+  if (c->stream) cudaStreamDestroy(c->stream);
   if (c->copy_stream) cudaStreamDestroy(c->copy_stream);
+  if (c->pool) cudaMemPoolDestroy(c->pool);
   if (c->points_ready) cudaEventDestroy(c->points_ready);
   if (c->sync_event) cudaEventDestroy(c->sync_event);
   delete c;
@@ -451,6 +482,7 @@ int bpgpu_points_upload(bpgpu_ctx* ctx, const uint8_t* xy, size_t n, bpgpu_point
   int rc = DISPATCH(ctx, CALL);
 #undef CALL
   if (rc == BPGPU_OK && stream_sync(ctx) != cudaSuccess) rc = BPGPU_E_CUDA;
+  if (rc == BPGPU_OK) rc = inputs_ok(ctx);
   if (rc) { dev_free(ctx, p->d); delete p; return rc; }
   *out = p;
   return BPGPU_OK;

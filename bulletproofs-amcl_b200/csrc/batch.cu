@@ -167,6 +167,7 @@ static int batch_identity_t(bpgpu_ctx* ctx, const FixedRuns& runs, uint32_t F, s
       return rc;
     BP_CUDA_OK(cudaMemcpyAsync(is_identity + lo, base + L.v, cnt, cudaMemcpyDeviceToHost, ctx->stream));
     BP_CUDA_OK(stream_sync(ctx));
+    if ((rc = inputs_ok(ctx))) return rc;                 // a var point that is not a point (callers validate per proof first)
   }
   return BPGPU_OK;
 }

@@ -49,6 +49,7 @@ struct bpgpu_ctx {
   int device = 0;
   int sm_count = 148;
   cudaStream_t stream = nullptr;
+  cudaMemPool_t pool = nullptr;   // stream-ordered pool of this ctx (handle storage: G1Vector / FieldElementVector / IPP state)
   // second queue for the host->device copy of the points of a large bpgpu_msm_refs: the copy and the byte->limb
   // conversion overlap the scalar pipeline (digits, scan, scatter) on `stream`; k_chunk_acc waits on `points_ready`
   cudaStream_t copy_stream = nullptr;
@@ -64,6 +65,9 @@ struct bpgpu_ctx {
   bp::Scratch fr_tmp, fr_out, fr_args, fr_pow, fr_pow2, ipp_pts, ipp_scl, parts_pts, parts_scl, tbl_part;
   bp::Scratch vb;                 // batched verifier / prover: proof bytes, per-proof headers, transcript states
   uint8_t* pinned = nullptr;      // small pinned staging (results, challenges)
+  // host-mapped word the decoding kernels raise when a host-supplied point is not a point (coordinate >= p, off the curve);
+  // read after the next synchronisation by the entry point that consumed the input (inputs_ok)
+  uint32_t* bad_input = nullptr;
   size_t pinned_cap = 0;
   // per-stage CUDA-event timing of the MSM pipeline (bpgpu_ctx_set_profile)
   int profile = 0;
@@ -91,13 +95,18 @@ namespace bp {
 
 // Handle storage (G1Vector / FieldElementVector / IPP state) comes from the device's stream-ordered pool on the ctx
 // stream: allocation and release are queue operations (microseconds), not driver calls that synchronise the device.
-// The pool's release threshold is raised at ctx creation so freed blocks are reused by the next proof.
+// The pool is the ctx's own (created with the ctx, release threshold raised so freed blocks are reused by the next proof).
 inline cudaError_t stream_sync(bpgpu_ctx* ctx) {
   if (!ctx->blocking_sync) return cudaStreamSynchronize(ctx->stream);
   cudaError_t e = cudaEventRecord(ctx->sync_event, ctx->stream);
   return e != cudaSuccess ? e : cudaEventSynchronize(ctx->sync_event);
 }
-inline cudaError_t dev_alloc(bpgpu_ctx* ctx, void** p, size_t bytes) { return cudaMallocAsync(p, bytes ? bytes : 16, ctx->stream); }
+// BPGPU_E_FORMAT if a point decoded since the last check was invalid (call after a stream synchronisation)
+inline int inputs_ok(bpgpu_ctx* ctx) {
+  if (ctx->bad_input && *(volatile uint32_t*)ctx->bad_input) { *(volatile uint32_t*)ctx->bad_input = 0; return BPGPU_E_FORMAT; }
+  return BPGPU_OK;
+}
+inline cudaError_t dev_alloc(bpgpu_ctx* ctx, void** p, size_t bytes) { return cudaMallocFromPoolAsync(p, bytes ? bytes : 16, ctx->pool, ctx->stream); }
 inline void dev_free(bpgpu_ctx* ctx, void* p) { if (p) cudaFreeAsync(p, ctx->stream); }
 
 // ------------------------------------------------------------------ 128-bit vector I/O

@@ -305,8 +305,9 @@ static int fb_build(bpgpu_fixed_bases* fb, const uint8_t* bases_xy) {
   void* d_bases = nullptr;
   BP_CUDA_OK(cudaMalloc(&d_bases, fb->k * sizeof(Affine<Fq>)));
   int rc = points_from_host<Curve>(ctx, bases_xy, fb->k, d_bases);
-  if (!rc) rc = build_tables<Curve>(ctx, d_bases, fb->k, &fb->table);
+  if (!rc) rc = build_tables<Curve>(ctx, d_bases, fb->k, &fb->table);      // synchronises
   cudaFree(d_bases);
+  if (!rc && (rc = inputs_ok(ctx))) { cudaFree(fb->table); fb->table = nullptr; }   // a base that is not a point: BPGPU_E_FORMAT
   return rc;
 }
 
@@ -388,6 +389,7 @@ int msm_tables_to_host(bpgpu_ctx* ctx, const TableSeg* segs, int nsegs, int ngro
     BP_CUDA_OK(cudaMemcpyAsync(ctx->pinned, ctx->tbl_part.p, ngroups * psz, cudaMemcpyDeviceToHost, ctx->stream));
     BP_CUDA_OK(stream_sync(ctx));
   }
+  if ((rc = inputs_ok(ctx))) return rc;
   uint8_t tmp[TBL_MAX_GROUPS * 2 * 48];
   if (bls) normalise_batch_host<BlsFq>(ctx->pinned, ngroups, mb, tmp);
   else normalise_batch_host<BnFq>(ctx->pinned, ngroups, mb, tmp);

@@ -154,6 +154,31 @@ struct HFp {
   }
 };
 
+// Is X || Y (big endian, `modbytes` each) a point as AMCL's ECP::frombytes / ECP::new_bigs decide it: both coordinates
+// < p and y^2 = x^3 + b, or the identity's encoding (0, 1)?  Host twin of csrc/curves.cuh g1_from_be_checked: the host
+// layer validates every untrusted point (proof points, commitments, bases) before its bytes are hashed or shipped.
+template <class P>
+inline bool g1_xy_is_valid(const uint8_t* xy, int modbytes, unsigned curve_b) {
+  using F = HFp<P>;
+  uint64_t raw[2][F::NL];
+  for (int c = 0; c < 2; c++) {
+    const uint8_t* be = xy + c * modbytes;
+    for (int i = 0; i < F::NL; i++) {
+      uint64_t w = 0; const uint8_t* p = be + modbytes - 8 * (i + 1);
+      for (int k = 0; k < 8; k++) w = (w << 8) | p[k];
+      raw[c][i] = w;
+    }
+    if (F::geq_p(raw[c])) return false;
+  }
+  uint64_t xz = 0, y1 = raw[1][0] ^ 1;
+  for (int i = 0; i < F::NL; i++) { xz |= raw[0][i]; if (i) y1 |= raw[1][i]; }
+  if (xz == 0 && y1 == 0) return true;
+  F x, y;
+  for (int i = 0; i < F::NL; i++) { x.v[i] = raw[0][i]; y.v[i] = raw[1][i]; }
+  x = x.to_mont(); y = y.to_mont();
+  return y.sqr() == x.sqr() * x + F::from_u64(curve_b);
+}
+
 // XYZZ point on the host; layout-compatible with the device's XYZZ<Fp<P>> (little-endian limbs)
 template <class P>
 struct HXYZZ {

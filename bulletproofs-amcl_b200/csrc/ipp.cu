@@ -289,6 +289,7 @@ static int ipp_begin_t(bpgpu_ipp* st, const bpgpu_points* Gp, size_t goff, const
     }
     if ((rc = points_from_host<Curve>(ctx, Q_xy, 1, (Affine<Fq>*)st->P + 2 * N))) return rc;
     BP_CUDA_OK(cudaStreamSynchronize(s));        // qtmp is a stack buffer
+    if ((rc = inputs_ok(ctx))) return rc;
   }
   BP_CUDA_OK(cudaMemcpyAsync(st->a, a, N * sizeof(Fr), cudaMemcpyDeviceToDevice, s));
   BP_CUDA_OK(cudaMemcpyAsync(st->b, b, N * sizeof(Fr), cudaMemcpyDeviceToDevice, s));

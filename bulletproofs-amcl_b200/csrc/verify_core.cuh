@@ -170,10 +170,14 @@ BP_HD int vb_from_challenges(const uint8_t* chal_be, const uint8_t* proof, uint3
     const uint32_t off = k < 11 ? PL::point(k) : PL::L(k - 11);
     if (proof[off] != 4) return BPGPU_E_FORMAT;
   }
-  Fr c[VB_CH_FIXED], uk[32];
-  for (int k = 0; k < VB_CH_FIXED; k++) c[k] = fr_from_be_wide<Curve>(chal_be + (size_t)k * MB);
+  const Fr y = fr_from_be_wide<Curve>(chal_be + (size_t)VB_CH_Y * MB);
+  const Fr z = fr_from_be_wide<Curve>(chal_be + (size_t)VB_CH_Z * MB);
+  const Fr u = fr_from_be_wide<Curve>(chal_be + (size_t)VB_CH_U * MB);
+  const Fr x = fr_from_be_wide<Curve>(chal_be + (size_t)VB_CH_X * MB);
+  const Fr w = fr_from_be_wide<Curve>(chal_be + (size_t)VB_CH_W * MB);
+  Fr uk[32];
   for (uint32_t k = 0; k < lg; k++) uk[k] = fr_from_be_wide<Curve>(chal_be + (size_t)(VB_CH_FIXED + k) * MB);
-  return vb_header_finish<Curve>(proof, lg, c[VB_CH_Y], c[VB_CH_Z], c[VB_CH_U], c[VB_CH_X], c[VB_CH_W], r, uk, hdr);
+  return vb_header_finish<Curve>(proof, lg, y, z, u, x, w, r, uk, hdr);
 }
 
 // one row of the flattened constraint matrices times the powers of z: sum_e coeff_e * z^(q_e + 1)

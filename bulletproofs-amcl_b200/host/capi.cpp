@@ -47,21 +47,44 @@ int ipp_from_bytes(const uint8_t* buf, size_t len, InnerProductArgumentProof<C>*
   p->L.resize(lg);
   p->R.resize(lg);
   size_t off = 0;
-  for (size_t k = 0; k < lg; k++, off += PB) { if (buf[off] != 4) return BPGPU_E_FORMAT; p->L[k] = G1<C>::from_xy(buf + off + 1); }
-  for (size_t k = 0; k < lg; k++, off += PB) { if (buf[off] != 4) return BPGPU_E_FORMAT; p->R[k] = G1<C>::from_xy(buf + off + 1); }
-  p->a = FieldElement<C>::from_bytes(buf + off);
-  p->b = FieldElement<C>::from_bytes(buf + off + SB);
+  auto point = [&](G1<C>* q) {
+    if (buf[off] != 4 || !G1<C>::xy_valid(buf + off + 1)) return false;
+    *q = G1<C>::from_xy(buf + off + 1);
+    off += PB;
+    return true;
+  };
+  auto scalar = [&](FieldElement<C>* s) {              // canonical (< r), as R1CSProof::from_bytes requires
+    *s = FieldElement<C>::from_bytes(buf + off);
+    uint8_t chk[C::MODBYTES];
+    s->to_bytes(chk);
+    const bool ok = memcmp(chk, buf + off, SB) == 0;
+    off += SB;
+    return ok;
+  };
+  for (size_t k = 0; k < lg; k++) if (!point(&p->L[k])) return BPGPU_E_FORMAT;
+  for (size_t k = 0; k < lg; k++) if (!point(&p->R[k])) return BPGPU_E_FORMAT;
+  if (!scalar(&p->a) || !scalar(&p->b)) return BPGPU_E_FORMAT;
+  return BPGPU_OK;
+}
+
+// every point of a caller-supplied list is a point (ECP::frombytes): else BPGPU_E_FORMAT
+template <class C>
+int points_valid(const uint8_t* xy, size_t n) {
+  for (size_t k = 0; k < n; k++) if (!G1<C>::xy_valid(xy + k * 2 * C::MODBYTES)) return BPGPU_E_FORMAT;
   return BPGPU_OK;
 }
 
 template <class C>
 Rng<C> make_rng(int mode, uint64_t seed) { return mode == 1 ? Rng<C>(seed, "blind") : Rng<C>(); }
 
+// the verifier's FieldElement::random() (verifier.rs:392): explicit, or one draw of an OS-entropy stream
 template <class C>
-FieldElement<C> verifier_scalar(const uint8_t* r_be) {
-  if (r_be) return FieldElement<C>::from_bytes(r_be);
+int verifier_scalar(const uint8_t* r_be, FieldElement<C>* out) {
+  if (r_be) { *out = FieldElement<C>::from_bytes(r_be); return BPGPU_OK; }
   Rng<C> os;
-  return os.next();
+  if (!os.ok()) return BPH_E_ENTROPY;
+  *out = os.next();
+  return BPGPU_OK;
 }
 
 template <class C>
@@ -85,6 +108,7 @@ int ipp_verify_t(bpgpu_ctx* ctx, const char* label, size_t n, const uint8_t* Gf,
   InnerProductArgumentProof<C> p;
   int rc = ipp_from_bytes<C>(proof, len, &p);
   if (rc) return rc;
+  if ((rc = points_valid<C>(P_xy, 1)) || (rc = points_valid<C>(Q_xy, 1))) return rc;
   FieldElementVector<C> dGf, dHf;
   if ((rc = FieldElementVector<C>::from_bytes(ctx, Gf, n, &dGf)) || (rc = FieldElementVector<C>::from_bytes(ctx, Hf, n, &dHf))) return rc;
   G1Vector<C> vG = G1Vector<C>::borrow(ctx, G), vH = G1Vector<C>::borrow(ctx, H);
@@ -99,6 +123,7 @@ int bound_prove_t(bpgpu_ctx* ctx, const char* label, const uint8_t* g_xy, const 
                   uint8_t* proof, size_t cap, size_t* len, uint8_t* comms_xy) {
   if (val < lower || val > upper) return BPH_E_GADGET;
   Rng<C> rng = make_rng<C>(rng_mode, seed);
+  if (!rng.ok()) return BPH_E_ENTROPY;
   FieldElement<C> rnd;
   if (randomness_be) rnd = FieldElement<C>::from_bytes(randomness_be);
   G1Vector<C> vG = G1Vector<C>::borrow(ctx, G), vH = G1Vector<C>::borrow(ctx, H);
@@ -117,11 +142,13 @@ int bound_verify_t(bpgpu_ctx* ctx, const char* label, const uint8_t* g_xy, const
   R1CSProof<C> p;
   int rc = R1CSProof<C>::from_bytes(proof, len, &p);
   if (rc) return rc;
+  if ((rc = points_valid<C>(comms_xy, 3)) || (rc = points_valid<C>(g_xy, 1)) || (rc = points_valid<C>(h_xy, 1))) return rc;
   std::vector<G1<C>> comms(3);
   for (int k = 0; k < 3; k++) comms[k] = G1<C>::from_xy(comms_xy + k * 2 * C::MODBYTES);
   G1Vector<C> vG = G1Vector<C>::borrow(ctx, G), vH = G1Vector<C>::borrow(ctx, H);
-  return verify_proof_of_bounded_num<C>(ctx, lower, upper, bits, p, comms, label, G1<C>::from_xy(g_xy), G1<C>::from_xy(h_xy), vG, vH,
-                                        verifier_scalar<C>(r_be));
+  FieldElement<C> vr;
+  if ((rc = verifier_scalar<C>(r_be, &vr))) return rc;
+  return verify_proof_of_bounded_num<C>(ctx, lower, upper, bits, p, comms, label, G1<C>::from_xy(g_xy), G1<C>::from_xy(h_xy), vG, vH, vr);
 }
 
 template <class C>
@@ -129,6 +156,7 @@ int range_prove_t(bpgpu_ctx* ctx, const char* label, const uint8_t* g_xy, const 
                   const uint64_t* values, size_t m, size_t bits, int rng_mode, uint64_t seed, uint8_t* proof, size_t cap, size_t* len,
                   uint8_t* comms_xy) {
   Rng<C> rng = make_rng<C>(rng_mode, seed);
+  if (!rng.ok()) return BPH_E_ENTROPY;
   G1Vector<C> vG = G1Vector<C>::borrow(ctx, G), vH = G1Vector<C>::borrow(ctx, H);
   R1CSProof<C> p;
   std::vector<G1<C>> comms;
@@ -145,10 +173,13 @@ int range_verify_t(bpgpu_ctx* ctx, const char* label, const uint8_t* g_xy, const
   R1CSProof<C> p;
   int rc = R1CSProof<C>::from_bytes(proof, len, &p);
   if (rc) return rc;
+  if ((rc = points_valid<C>(comms_xy, m)) || (rc = points_valid<C>(g_xy, 1)) || (rc = points_valid<C>(h_xy, 1))) return rc;
   std::vector<G1<C>> comms(m);
   for (size_t k = 0; k < m; k++) comms[k] = G1<C>::from_xy(comms_xy + k * 2 * C::MODBYTES);
   G1Vector<C> vG = G1Vector<C>::borrow(ctx, G), vH = G1Vector<C>::borrow(ctx, H);
-  return verify_proof_of_positive_nums<C>(ctx, bits, p, comms, label, G1<C>::from_xy(g_xy), G1<C>::from_xy(h_xy), vG, vH, verifier_scalar<C>(r_be));
+  FieldElement<C> vr;
+  if ((rc = verifier_scalar<C>(r_be, &vr))) return rc;
+  return verify_proof_of_positive_nums<C>(ctx, bits, p, comms, label, G1<C>::from_xy(g_xy), G1<C>::from_xy(h_xy), vG, vH, vr);
 }
 
 template <class C>
@@ -156,6 +187,7 @@ int shuffle_prove_t(bpgpu_ctx* ctx, const char* label, const uint8_t* g_xy, cons
                     const uint64_t* x, const uint64_t* y, size_t k, size_t bits, int rng_mode, uint64_t seed, uint8_t* proof, size_t cap,
                     size_t* len, uint8_t* comms_xy) {
   Rng<C> rng = make_rng<C>(rng_mode, seed);
+  if (!rng.ok()) return BPH_E_ENTROPY;
   G1Vector<C> vG = G1Vector<C>::borrow(ctx, G), vH = G1Vector<C>::borrow(ctx, H);
   R1CSProof<C> p;
   std::vector<G1<C>> comms;
@@ -172,10 +204,13 @@ int shuffle_verify_t(bpgpu_ctx* ctx, const char* label, const uint8_t* g_xy, con
   R1CSProof<C> p;
   int rc = R1CSProof<C>::from_bytes(proof, len, &p);
   if (rc) return rc;
+  if ((rc = points_valid<C>(comms_xy, 2 * k)) || (rc = points_valid<C>(g_xy, 1)) || (rc = points_valid<C>(h_xy, 1))) return rc;
   std::vector<G1<C>> comms(2 * k);
   for (size_t j = 0; j < 2 * k; j++) comms[j] = G1<C>::from_xy(comms_xy + j * 2 * C::MODBYTES);
   G1Vector<C> vG = G1Vector<C>::borrow(ctx, G), vH = G1Vector<C>::borrow(ctx, H);
-  return verify_proof_of_shuffle<C>(ctx, k, bits, p, comms, label, G1<C>::from_xy(g_xy), G1<C>::from_xy(h_xy), vG, vH, verifier_scalar<C>(r_be));
+  FieldElement<C> vr;
+  if ((rc = verifier_scalar<C>(r_be, &vr))) return rc;
+  return verify_proof_of_shuffle<C>(ctx, k, bits, p, comms, label, G1<C>::from_xy(g_xy), G1<C>::from_xy(h_xy), vG, vH, vr);
 }
 
 // hash_msg: SHAKE256(msg) squeezed to MODBYTES (G1::from_msg_hash / FieldElement::from_msg_hash)
@@ -230,14 +265,17 @@ int range_verify_batch_hostscalars_t(bpgpu_ctx* ctx, const char* label, const ui
   for (auto& d : done) d.store(0);
   std::atomic<size_t> next{0};
   auto worker = [&]() {
+    Rng<C> os;                                      // one entropy stream per worker thread (verifier.rs:392 draws per proof)
     for (;;) {
       const size_t i = next.fetch_add(1);
       if (i >= count) break;
+      if (!os.ok()) { verdicts[i] = BPH_E_ENTROPY; done[i / SLAB].fetch_add(1, std::memory_order_release); continue; }
       uint8_t* fo = fixed.data() + i * F * mb;
       uint8_t* po = vpts.data() + i * vn * pb;
       uint8_t* so = vscal.data() + i * vn * mb;
       R1CSProof<C> p;
       int st = R1CSProof<C>::from_bytes(proofs + i * stride, plen, &p);
+      if (!st) st = points_valid<C>(comms_xy + i * m * pb, m);
       typename Verifier<C>::VerificationTerms t;
       if (!st) {
         Transcript tr{std::string(label)};
@@ -246,7 +284,6 @@ int range_verify_batch_hostscalars_t(bpgpu_ctx* ctx, const char* label, const ui
           Variable var = verifier.commit(G1<C>::from_xy(comms_xy + (i * m + k) * pb));
           st = positive_no_gadget<C>(verifier, AllocatedQuantity<C>{var, false, FieldElement<C>::zero()}, bits);
         }
-        Rng<C> os;
         if (!st) st = verifier.verification_terms_host(p, N, os.next(), &t);
         if (!st && (t.fixed.size() != F || t.var_points.size() != vn)) st = BPGPU_E_FORMAT;
       }
@@ -359,6 +396,7 @@ int verify_batch_device_t(bpgpu_ctx* ctx, const char* label, const uint8_t* g_xy
   Transcript t0{std::string(label)};
   t0.r1cs_domain_sep();                                   // Verifier::new (verifier.rs:97-108)
   Rng<C> os;                                              // one key per call; proof i takes draw i (verifier.rs:392)
+  if (!os.ok()) { bpgpu_circuit_free(circ); return BPH_E_ENTROPY; }
   if (mode == 0) {
     uint8_t state0[203];
     t0.export_state(state0);

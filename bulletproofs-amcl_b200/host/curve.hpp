@@ -11,8 +11,9 @@
 #include <stdio.h>
 #include <stdlib.h>
 
+#include <sys/random.h>
+
 #include <chrono>
-#include <random>
 #include <string>
 #include <vector>
 
@@ -24,11 +25,15 @@ namespace bph {
 
 struct Bls381 {
   using FrP = bp::BlsFr;
+  using FqP = bp::BlsFq;
+  static constexpr unsigned CURVE_B = 4;
   static constexpr int ID = BPGPU_BLS12_381;
   static constexpr int MODBYTES = 48;
 };
 struct Bn254 {
   using FrP = bp::BnFr;
+  using FqP = bp::BnFq;
+  static constexpr unsigned CURVE_B = 2;
   static constexpr int ID = BPGPU_BN254;
   static constexpr int MODBYTES = 32;
 };
@@ -62,6 +67,7 @@ enum : int {
   E_ARG = BPGPU_E_ARG,
   E_MISSING_ASSIGNMENT = -8,
   E_GADGET = -9,
+  E_ENTROPY = -11,
 };
 
 template <class C>
@@ -113,6 +119,10 @@ struct G1 {
   static G1 identity() { G1 p; memset(p.xy, 0, sizeof p.xy); p.xy[2 * MB - 1] = 1; return p; }
   static G1 from_xy(const uint8_t* b) { G1 p; memcpy(p.xy, b, sizeof p.xy); return p; }
   bool is_identity() const { return *this == identity(); }
+  // a point as AMCL's ECP::frombytes accepts it (coordinates < p, on the curve, or (0, 1)): checked for every point that
+  // arrives from outside before it is hashed into a transcript or used in an MSM
+  bool is_valid() const { return bp::host::g1_xy_is_valid<typename C::FqP>(xy, MB, C::CURVE_B); }
+  static bool xy_valid(const uint8_t* b) { return bp::host::g1_xy_is_valid<typename C::FqP>(b, MB, C::CURVE_B); }
   bool operator==(const G1& o) const { return memcmp(xy, o.xy, sizeof xy) == 0; }
   bool operator!=(const G1& o) const { return !(*this == o); }
   // G1::to_bytes(): 0x04 || X || Y
@@ -138,12 +148,24 @@ struct TranscriptProtocol {
 //   mode 0: key = 32 bytes of OS entropy || "os".
 // Counter mode lets the long draws (the blinding VECTORS s_L, s_R) be generated on the device, element i by thread i
 // (fill_device -> bpgpu_fr_random), at the place in the stream where the same number of next() calls would have been.
+// best-effort wipe of secret host memory (keys, blindings, witness) that the optimiser may not drop
+inline void secure_zero(void* p, size_t n) {
+  volatile uint8_t* v = static_cast<volatile uint8_t*>(p);
+  for (size_t i = 0; i < n; i++) v[i] = 0;
+}
+
 template <class C>
 class Rng {
  public:
+  // OS entropy through getrandom(2); ok() is false if the kernel could not supply it (callers return BPH_E_ENTROPY:
+  // no blinding is ever derived from a partially filled key)
   Rng() {
-    std::random_device rd;
-    for (int i = 0; i < 8; i++) { uint32_t w = rd(); memcpy(key_ + 4 * i, &w, 4); }
+    size_t got = 0;
+    while (got < 32) {
+      ssize_t r = getrandom(key_ + got, 32 - got, 0);
+      if (r <= 0) { ok_ = false; break; }
+      got += (size_t)r;
+    }
     key_[32] = 'o'; key_[33] = 's';
     key_len_ = 34;
   }
@@ -151,6 +173,8 @@ class Rng {
     for (int i = 0; i < 8; i++) key_[key_len_++] = (uint8_t)(seed >> (8 * i));
     for (char ch : tag) if (key_len_ < 48) key_[key_len_++] = (uint8_t)ch;
   }
+  ~Rng() { secure_zero(key_, sizeof key_); }
+  bool ok() const { return ok_; }
   FieldElement<C> next() {
     uint8_t m[64], out[C::MODBYTES];
     memcpy(m, key_, key_len_);
@@ -175,6 +199,7 @@ class Rng {
   uint8_t key_[56] = {0};
   size_t key_len_ = 0;
   uint64_t ctr_ = 0;
+  bool ok_ = true;
 };
 
 }  // namespace bph

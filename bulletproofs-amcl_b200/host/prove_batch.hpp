@@ -92,6 +92,7 @@ struct BatchProverAccess {
     std::vector<std::unique_ptr<State>> st(B);
     for (size_t i = 0; i < B; i++)
       st[i].reset(new State(ctx, g, h, label, rng_mode == 1 ? Rng<C>(seed0 + i, "blind") : Rng<C>()));
+    for (size_t i = 0; i < B; i++) if (!st[i]->rng.ok()) return E_ENTROPY;
     int rc;
     Trace tr_("prove_slab");
     std::atomic<int> err{0};

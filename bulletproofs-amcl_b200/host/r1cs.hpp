@@ -127,7 +127,7 @@ struct R1CSProof {
     append_fe(out, ipp_proof.a); append_fe(out, ipp_proof.b);
     return out;
   }
-  // malformed length / tag / non-canonical scalar -> E_FORMAT (R1CSError::FormatError)
+  // malformed length / tag / non-canonical scalar / coordinate >= p / point off the curve -> E_FORMAT (R1CSError::FormatError)
   static int from_bytes(const uint8_t* buf, size_t len, R1CSProof* out) {
     const size_t PB = 1 + 2 * C::MODBYTES, SB = C::MODBYTES;
     const size_t fixed = 11 * PB + 3 * SB + 2 * SB;
@@ -135,7 +135,10 @@ struct R1CSProof {
     const size_t lg = (len - fixed) / (2 * PB);
     if (lg >= 32) return E_FORMAT;
     size_t off = 0;
-    auto point = [&](G1<C>* p) { if (buf[off] != 4) return false; *p = G1<C>::from_xy(buf + off + 1); off += PB; return true; };
+    auto point = [&](G1<C>* p) {                  // 0x04 || X || Y with X, Y < p on the curve (or AMCL's identity): ECP::frombytes
+      if (buf[off] != 4 || !G1<C>::xy_valid(buf + off + 1)) return false;
+      *p = G1<C>::from_xy(buf + off + 1); off += PB; return true;
+    };
     auto scalar = [&](FieldElement<C>* s) {
       *s = FieldElement<C>::from_bytes(buf + off);
       uint8_t chk[C::MODBYTES];

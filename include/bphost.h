@@ -29,6 +29,7 @@ extern "C" {
 #define BPH_E_MISSING_ASSIGNMENT (-8) /* R1CSError::MissingAssignment */
 #define BPH_E_GADGET (-9)             /* R1CSError::GadgetError */
 #define BPH_E_BUFFER (-10)            /* output buffer too small; *len holds the required size */
+#define BPH_E_ENTROPY (-11)           /* the OS could not supply entropy for blindings (getrandom failed): nothing was proved */
 
 /* merlin::Transcript known-answer hook: new(label); append_message(msg_label, msg); challenge_bytes(ch_label, out_len) */
 int bph_merlin_kat(const char* label, const char* msg_label, const uint8_t* msg, size_t msg_len, const char* ch_label,

@@ -56,13 +56,14 @@ def test_device_built_verification_scalars_match_oracle(bp, ctx_bls, ctx_bn, nam
     for kw in ({"state": state}, {"challenges": chal}):
         verdicts, fixed, var = circ.verify_batch(dG, dH, gx, hx, count, proof_b * count, len(proof_b), comms_b * count, key=key_b,
                                                  terms=True, **kw)
-        assert verdicts == [0] * count
         F, vn = 2 * N + 2, 6 + m + 5 + 2 * lg
         gf, gv = dec_scalars(C, fixed), dec_scalars(C, var)
         for i in range(count):
             exp_fixed, exp_var, _ = _oracle_arg1(C, label, proof_b, comms_b, build, C.synth_scalar(777, i, b"blind"))
-            assert gv[i * vn:(i + 1) * vn] == exp_var, (i, kw.keys())
-            assert gf[i * F:(i + 1) * F] == exp_fixed, (i, kw.keys())
+            bad_v = [k for k in range(vn) if gv[i * vn + k] != exp_var[k]]
+            bad_f = [k for k in range(F) if gf[i * F + k] != exp_fixed[k]]
+            assert not bad_v and not bad_f, (i, list(kw.keys()), bad_v, bad_f)
+        assert verdicts == [0] * count
     circ.free()
 
 
