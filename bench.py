@@ -54,7 +54,34 @@ def synth_scalars_be(n, seed, modbytes=48):
     return out
 
 
-def gen_points(ctx, n, seed):
+BLS_R = 0x73eda753299d7d483339d80809a1d80553bda402fffe5bfeffffffff00000001
+
+
+def make_config(lg, world):
+    """the workload description both arms print (the driver compares it between the arms)"""
+    import bulletproofs_amcl_b200 as bp
+    n = 1 << lg
+    c = bp.lib().bpgpu_msm_window_bits(n)
+    W = (256 + c - 1) // c
+    return {"workload": f"G1 MSM, BLS12-381, 2^{lg} random points x 255-bit scalars per GPU, general bases "
+                        f"(no precomputation), signed {c}-bit windows x {W}",
+            "l2": f"2 input sets alternated (2x{(n * (2 * 48 + 32)) >> 20} MiB > 126 MB L2), no explicit flush",
+            "parallelism": f"points sharded over {world} GPU(s); partial sums all-gathered over NCCL" if world > 1 else "1 GPU"}
+
+
+def be_ints(block, n, mb):
+    """n big-endian MODBYTES scalars (bytes or numpy block) -> Python ints"""
+    b = block if isinstance(block, (bytes, bytearray)) else block.tobytes()
+    return [int.from_bytes(b[i * mb:(i + 1) * mb], "big") for i in range(n)]
+
+
+def expected_point(total_scalar):
+    """(sum s_i * k_i mod r) * G by the ORACLE (checker only): what an MSM over the bench's points k_i * G must equal"""
+    from oracle.curves import BLS12_381 as C
+    return C.g1_xy_bytes(C.mul(C.from_affine(C.g), total_scalar % C.r))
+
+
+def gen_points(ctx, n, seed, with_multipliers=False):
     """n synthetic G1 points k_i*G, computed on the device (selftest_group op 2)."""
     from bulletproofs_amcl_b200 import lib
     mb = ctx.modbytes
@@ -62,7 +89,8 @@ def gen_points(ctx, n, seed):
     gy = 0x08B3F481E3AAA0F1A09E30ED741D8AE4FCF5E095D5D00AF600DB18CB2C04B3EDD03CC744A2888AE40CAA232946C5E7E1
     g = gx.to_bytes(mb, "big") + gy.to_bytes(mb, "big")
     ks = synth_scalars_be(n, seed, mb).tobytes()
-    return ctx.selftest_group(2, g * n, g * n, ks)
+    xy = ctx.selftest_group(2, g * n, g * n, ks)
+    return (xy, ks) if with_multipliers else xy
 
 
 class ClockSampler:
@@ -112,11 +140,14 @@ class ClockSampler:
                 "reasons": reasons, "samples": len(sm)}
 
 
+TRAFFIC_CAPTURES = ["k_chunk_acc_r02_raw.csv", "k_chunk_acc_r01_raw.csv"]
+
+
 def ncu_traffic_bytes():
-    """dram__bytes_read.sum + dram__bytes_write.sum of k_chunk_acc per launch, from the committed `ncu --set full` capture
-    of this same command (profiles/k_chunk_acc_r01_raw.csv); None if the capture is missing."""
+    """dram__bytes_read.sum + dram__bytes_write.sum of k_chunk_acc per launch, READ FROM A STORED `ncu --set full` capture of
+    this same command (profiles/, newest round first) -- not measured in this run; (None, None) if no capture is there."""
     import csv
-    path = os.path.join(ROOT, "profiles", "k_chunk_acc_r01_raw.csv")
+    path = next((os.path.join(ROOT, "profiles", f) for f in TRAFFIC_CAPTURES if os.path.exists(os.path.join(ROOT, "profiles", f))), "")
     try:
         rows = list(csv.reader(open(path)))
         hdr, units, vals = rows[0], rows[1], rows[2]
@@ -125,9 +156,9 @@ def ncu_traffic_bytes():
         for name in ("dram__bytes_read.sum", "dram__bytes_write.sum"):
             i = hdr.index(name)
             tot += float(vals[i]) * scale[units[i]]
-        return tot
+        return tot, "profiles/" + os.path.basename(path)
     except Exception:
-        return None
+        return None, None
 
 
 def proof_section(bp, ctx, local, rank, world, dist, torch, no_cpu=False):
@@ -164,7 +195,7 @@ def proof_section(bp, ctx, local, rank, world, dist, torch, no_cpu=False):
             v = bp.range_verify_many(ctxs, b"bench", gx, hx, G, H, count, m, bits, proofs, stride, comms)
             ok = ok and v == [0] * count
         tv = time.perf_counter() - t0
-        tb = tpb = None
+        tb = tpb = tb1 = None
         if batch_call:
             # the same statement proved in lock-step on ONE context (bph_range_prove_batch): every prover stage and IPP round
             # is one device call for the whole batch, the transcripts run on the host threads in between
@@ -191,17 +222,25 @@ def proof_section(bp, ctx, local, rank, world, dist, torch, no_cpu=False):
             v = bp.range_verify_batch(c0, b"bench", gx, hx, G, H, count * reps, m, bits, big_p, stride, big_c, nthreads=hthreads)
             tb = time.perf_counter() - t0
             ok = ok and v == [0] * (count * reps)
+            # the same call with the transcripts replayed on this rank's host threads (mode 1) instead of on the device
+            if dist is not None:
+                dist.barrier()
+            t0 = time.perf_counter()
+            v = bp.range_verify_batch(c0, b"bench", gx, hx, G, H, count * reps, m, bits, big_p, stride, big_c, nthreads=hthreads, mode=1)
+            tb1 = time.perf_counter() - t0
+            ok = ok and v == [0] * (count * reps)
         if dist is not None:
             # the exchange step of the sharded batch verification: verdict bytes of every rank, all-gathered
             t = torch.tensor([1 if ok else 0] * count, dtype=torch.uint8, device="cuda")
             allv = torch.empty(world * count, dtype=torch.uint8, device="cuda")
             dist.all_gather_into_tensor(allv, t)
             ok = bool(allv.min().item() == 1)
-            tt = torch.tensor([tp, tv, tb or 0.0, tpb or 0.0], device="cuda", dtype=torch.float64)
+            tt = torch.tensor([tp, tv, tb or 0.0, tpb or 0.0, tb1 or 0.0], device="cuda", dtype=torch.float64)
             dist.all_reduce(tt, op=dist.ReduceOp.MAX)
             tp, tv = float(tt[0].item()), float(tt[1].item())
             tb = float(tt[2].item()) if tb is not None else None
             tpb = float(tt[3].item()) if tpb is not None else None
+            tb1 = float(tt[4].item()) if tb1 is not None else None
         for c in ctxs:
             c.close()
         out[tag] = {"multipliers": n, "committed_values": m, "proofs": count * world, "prove_per_s": count * world / tp,
@@ -209,6 +248,9 @@ def proof_section(bp, ctx, local, rank, world, dist, torch, no_cpu=False):
                     "prove_verify_per_s": count * world / (tp + tv / verify_reps), "all_verified": ok, "proof_bytes": stride}
         if tb is not None:
             out[tag]["verify_batch_call_per_s"] = count * world * verify_reps / tb
+            out[tag]["verify_batch_call"] = "bph_range_verify_batch: transcripts, per-proof scalars and MSMs on the device; host uploads bytes"
+        if tb1 is not None:
+            out[tag]["verify_batch_host_transcripts_per_s"] = count * world * verify_reps / tb1
         if tpb is not None:
             out[tag]["prove_batch_call_per_s"] = count * world * verify_reps / tpb
         if cpu_base and rank == 0 and world == 1:
@@ -269,7 +311,7 @@ def run_reference(args):
         "impl": "reference", "metric": METRIC, "value": value, "unit": UNIT, "n_gpus": args.gpus, "steps": args.steps,
         "warmup": args.warmup, "ms_per_step": 1e3 * sum(dt for _, dt in vals) / len(vals), "higher_is_better": True,
         "scaling": "weak", "vs_baseline": None, "dtype": "u32 limbs (host: u64)", "data": "synthetic",
-        "config": {"workload": f"G1 MSM, BLS12-381, 2^{args.lg} points (bounded sample 2^{lg_s} per step)"},
+        "config": make_config(args.lg, args.gpus),
         "cpu_baseline": {"value": value, "unit": UNIT, "cores": cores, "kind": "port", "sample": sample},
         "e2e": {"value": value, "unit": UNIT, "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
     }))
@@ -285,6 +327,7 @@ def main():
     ap.add_argument("--ref-lg", type=int, default=18)
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--no-proofs", action="store_true", help="skip the IPP / R1CS proofs-per-second section")
+    ap.add_argument("--no-sweep", action="store_true", help="skip BASELINE config 4 (size sweep at N = 1, fixed-size strong scaling)")
     args = ap.parse_args()
     if args.impl == "reference":
         return run_reference(args)
@@ -315,13 +358,20 @@ def main():
     # ---- synthetic inputs: two independent input sets (2 x (96+32) MB at 2^20 > 126 MB L2), alternated
     # between steps so no step finds its inputs in L2
     NSETS = 2
-    pts_xy = [gen_points(ctx, n, 1000 + 17 * rank + s) for s in range(NSETS)]
+    gen = [gen_points(ctx, n, 1000 + 17 * rank + s, with_multipliers=True) for s in range(NSETS)]
+    pts_xy = [g[0] for g in gen]
+    ks_be = [g[1] for g in gen]
+    del gen
     sc_np = [synth_scalars_be(n, 2000 + 17 * rank + s, mb) for s in range(NSETS)]
     dpts = [ctx.upload_points(x) for x in pts_xy]
     dsc = [ctx.upload_scalars(s.tobytes()) for s in sc_np]
-    # pinned host copies for the end-to-end leg
-    hp, hs = [], []
+    # pinned host copies for the end-to-end legs (hs: 48-byte big-endian scalars; hs_le: 32-byte little-endian)
+    hp, hs, hs_le = [], [], []
     for s in range(NSETS):
+        le = sc_np[s][:, mb - 32:][:, ::-1].copy()
+        q = ctx.host_alloc(le.nbytes)
+        ctypes.memmove(q, le.ctypes.data, le.nbytes)
+        hs_le.append(q)
         p = ctx.host_alloc(len(pts_xy[s]))
         ctypes.memmove(p, pts_xy[s], len(pts_xy[s]))
         hp.append(p)
@@ -342,6 +392,12 @@ def main():
 
     def step_e2e(i):
         return combine(ctx.msm_refs(hp[i % NSETS], hs[i % NSETS], n=n))
+
+    def step_e2e_resident(i):            # bases cached on the device (fixed generators), scalars from the host every step
+        return combine(ctx.msm(dpts[i % NSETS], hs[i % NSETS], n=n))
+
+    def step_e2e_resident_le32(i):
+        return combine(ctx.msm_le32(dpts[i % NSETS], hs_le[i % NSETS], n=n))
 
     stream = torch.cuda.ExternalStream(ctx.stream)
 
@@ -382,11 +438,102 @@ def main():
     ms, launches, (runs, stages) = timed(step_resident, args.steps, args.warmup, profile=True)
     clocks = sampler.stop()
     ms_e2e, _, _ = timed(step_e2e, args.steps, args.warmup)
+    ms_e2e_res, _, _ = timed(step_e2e_resident, args.steps, args.warmup)
+    ms_e2e_le, _, _ = timed(step_e2e_resident_le32, args.steps, args.warmup)
 
-    # parity guard inside the bench: both paths agree with each other on the same inputs
-    a = ctx.msm_device(dpts[0], dsc[0], n=n)
-    b = ctx.msm_refs(hp[0], hs[0], n=n)
-    assert a == b, "resident and host-buffer MSM disagree"
+    # ---- parity guard against the ORACLE, on every rank and on the combined result at every N: the bench points are
+    # k_i * G with known k_i, so the MSM must equal (sum s_i * k_i mod r) * G -- one oracle scalar multiplication.
+    # A mismatch aborts the run: no bench line is printed.
+    def shard_total(set_idx):
+        ks = be_ints(ks_be[set_idx], n, mb)
+        ss = be_ints(sc_np[set_idx], n, mb)
+        return sum(a * b for a, b in zip(ks, ss)) % BLS_R
+
+    def all_totals(local_total):
+        if world == 1:
+            return [local_total]
+        t = torch.tensor(list(local_total.to_bytes(32, "big")), dtype=torch.uint8, device="cuda")
+        allt = torch.empty(world * 32, dtype=torch.uint8, device="cuda")
+        dist.all_gather_into_tensor(allt, t)
+        raw = bytes(allt.cpu().tolist())
+        return [int.from_bytes(raw[i * 32:(i + 1) * 32], "big") for i in range(world)]
+
+    parity = {}
+    for set_idx in range(NSETS):
+        tot = shard_total(set_idx)
+        exp_local = expected_point(tot)
+        for name, got in (("msm_device", ctx.msm_device(dpts[set_idx], dsc[set_idx], n=n)),
+                          ("msm_refs", ctx.msm_refs(hp[set_idx], hs[set_idx], n=n)),
+                          ("msm", ctx.msm(dpts[set_idx], hs[set_idx], n=n)),
+                          ("msm_le32", ctx.msm_le32(dpts[set_idx], hs_le[set_idx], n=n))):
+            if got != exp_local:
+                sys.stderr.write(f"PARITY FAILURE rank {rank}: {name} on input set {set_idx} differs from the oracle\n")
+                sys.exit(3)
+        exp_all = expected_point(sum(all_totals(tot)))
+        if step_resident(set_idx) != exp_all or step_e2e(set_idx) != exp_all:
+            sys.stderr.write(f"PARITY FAILURE rank {rank}: combined {world}-GPU result of input set {set_idx} differs from the oracle\n")
+            sys.exit(3)
+    parity = {"checked_against": "oracle: (sum s_i*k_i mod r)*G, one scalar multiplication (oracle/curves.py)",
+              "entries": ["bpgpu_msm_device", "bpgpu_msm_refs", "bpgpu_msm", "bpgpu_msm_le32"], "input_sets": NSETS,
+              "per_rank": True, "combined_over_ranks": world, "ok": True}
+
+    # ---- config 4: size sweep on one GPU, and a FIXED-size MSM split by points over the ranks (strong scaling)
+    def time_msm(dp, ds, nn, reps, comb):
+        for _ in range(2):
+            r0 = ctx.msm_device(dp, ds, n=nn)
+            if comb:
+                combine(r0)
+        if world > 1:
+            dist.barrier()
+        torch.cuda.synchronize()
+        t0 = time.perf_counter()
+        for _ in range(reps):
+            r0 = ctx.msm_device(dp, ds, n=nn)
+            if comb:
+                r0 = combine(r0)
+        dt = (time.perf_counter() - t0) * 1e3 / reps
+        if world > 1:
+            t = torch.tensor([dt], device="cuda", dtype=torch.float64)
+            dist.all_reduce(t, op=dist.ReduceOp.MAX)
+            dt = float(t.item())
+        return dt, r0
+
+    sweep, strong = None, None
+    if not args.no_sweep:
+        # release the headline inputs first: the 2^22 case needs 0.4 GB of points + scratch
+        if world == 1:
+            sweep = []
+            for lg in range(10, 23, 2):
+                nn = 1 << lg
+                xy, kb = gen_points(ctx, nn, 7000 + lg, with_multipliers=True)
+                sb = synth_scalars_be(nn, 8000 + lg, mb)
+                dp, ds = ctx.upload_points(xy), ctx.upload_scalars(sb.tobytes())
+                reps = 50 if lg <= 14 else (20 if lg <= 18 else 8)
+                dt, res = time_msm(dp, ds, nn, reps, False)
+                tot = sum(a * b for a, b in zip(be_ints(kb, nn, mb), be_ints(sb, nn, mb))) % BLS_R
+                if res != expected_point(tot):
+                    sys.stderr.write(f"PARITY FAILURE: sweep 2^{lg} differs from the oracle\n")
+                    sys.exit(3)
+                sweep.append({"lg_n": lg, "ms": dt, "points_per_s": nn / (dt * 1e-3), "window_bits": bp.lib().bpgpu_msm_window_bits(nn),
+                              "oracle_checked": True})
+                dp.free()
+                ds.free()
+        strong = {}
+        for lg_tot in (20, 22):
+            nn = (1 << lg_tot) // world
+            xy, kb = gen_points(ctx, nn, 9000 + lg_tot + 31 * rank, with_multipliers=True)
+            sb = synth_scalars_be(nn, 9500 + lg_tot + 31 * rank, mb)
+            dp, ds = ctx.upload_points(xy), ctx.upload_scalars(sb.tobytes())
+            dt, res = time_msm(dp, ds, nn, 8, True)
+            tot = sum(a * b for a, b in zip(be_ints(kb, nn, mb), be_ints(sb, nn, mb))) % BLS_R
+            if res != expected_point(sum(all_totals(tot))):
+                sys.stderr.write(f"PARITY FAILURE rank {rank}: strong-scaling 2^{lg_tot} over {world} ranks differs from the oracle\n")
+                sys.exit(3)
+            strong[f"total_2^{lg_tot}"] = {"points_total": 1 << lg_tot, "points_per_gpu": nn, "gpus": world, "ms": dt,
+                                            "points_per_s": (1 << lg_tot) / (dt * 1e-3), "oracle_checked": True,
+                                            "includes": "per-rank MSM + NCCL all-gather of the partial sums + host add on every rank"}
+            dp.free()
+            ds.free()
 
     proofs = None if args.no_proofs else proof_section(bp, ctx, local, rank, world, dist, torch, no_cpu=args.no_cpu_baseline)
 
@@ -404,12 +551,17 @@ def main():
             "metric": METRIC, "value": value, "unit": UNIT, "n_gpus": world, "steps": args.steps, "warmup": args.warmup,
             "ms_per_step": ms / args.steps, "higher_is_better": True, "scaling": "weak", "vs_baseline": None,
             "dtype": "u32 limbs (Montgomery Fq 12x32, Fr 8x32)", "data": "synthetic",
-            "config": {"workload": f"G1 MSM, BLS12-381, 2^{args.lg} random points x 255-bit scalars per GPU, general bases "
-                                   f"(no precomputation), signed {c}-bit windows x {W}",
-                       "l2": f"{NSETS} input sets alternated ({NSETS}x{(n * (2 * mb + 32)) >> 20} MiB > 126 MB L2), no explicit flush",
-                       "parallelism": f"points sharded over {world} GPU(s); partial sums all-gathered over NCCL" if world > 1 else "1 GPU"},
+            "config": make_config(args.lg, world),
             "e2e": {"value": e2e_value, "unit": UNIT, "h2d_bytes_per_step": n * 3 * mb, "d2h_bytes_per_step": 2 * W * 4 * mb,
                     "ms_per_step": ms_e2e / args.steps, "api": "bpgpu_msm_refs (host points + host scalars, pinned)"},
+            # the reference's call sites multiply FIXED generators (ipp.rs:91-104, prover.rs:347-362, verifier.rs:451): bases stay
+            # resident, only the scalars travel
+            "e2e_resident_bases": {"value": total_points / (ms_e2e_res * 1e-3), "unit": UNIT, "h2d_bytes_per_step": n * mb,
+                                   "ms_per_step": ms_e2e_res / args.steps, "api": "bpgpu_msm (cached bases, 48-byte big-endian host scalars)",
+                                   "le32": {"value": total_points / (ms_e2e_le * 1e-3), "h2d_bytes_per_step": n * 32,
+                                            "ms_per_step": ms_e2e_le / args.steps,
+                                            "api": "bpgpu_msm_le32 (cached bases, 32-byte little-endian host scalars, no conversion pass)"}},
+            "parity": parity,
             "gpu_launches": int(launches),
             "clocks": clocks,
             "roofline": {"bound": "int32-imad", "kernel": "k_chunk_acc", "achieved": achieved, "peak": imad_peak,
@@ -422,7 +574,13 @@ def main():
         }
         if proofs is not None:
             out["proofs"] = proofs
-        out["roofline"]["traffic"] = ncu_traffic_bytes()
+        if sweep is not None:
+            out["sweep"] = sweep
+        if strong is not None:
+            out["strong_scaling"] = strong
+        out["roofline"]["traffic"], out["roofline"]["traffic_source"] = ncu_traffic_bytes()
+        if out["roofline"]["traffic_source"]:
+            out["roofline"]["traffic_source"] += " (stored ncu --set full capture, not measured in this run)"
         if world == 1 and not args.no_cpu_baseline:
             cores = os.cpu_count() or 1
             v1, dt1 = cpu_reference(16, 1)

@@ -41,6 +41,7 @@ SYMBOLS = [
     ("bpgpu_scalars_len", _SZ, [_VP]),
     ("bpgpu_scalars_free", None, [_VP]),
     ("bpgpu_msm", _INT, [_VP, _VP, _SZ, _SZ, _VP, _VP]),
+    ("bpgpu_msm_le32", _INT, [_VP, _VP, _SZ, _SZ, _VP, _VP]),
     ("bpgpu_msm_device", _INT, [_VP, _VP, _SZ, _SZ, _VP, _SZ, _VP]),
     ("bpgpu_msm_refs", _INT, [_VP, _VP, _VP, _SZ, _VP]),
     ("bpgpu_msm_parts_batch", _INT, [_VP, _VP, _VP, _SZ, _VP]),
@@ -599,6 +600,13 @@ class Context:
         n = len(scalars_be) // self.modbytes if n is None else n
         out = ctypes.create_string_buffer(2 * self.modbytes)
         self._check(lib().bpgpu_msm(self.handle, points.handle, off, n, _buf(scalars_be), out), "msm")
+        return out.raw
+
+    def msm_le32(self, points, scalars_le32, off=0, n=None):
+        """resident bases, scalars as 32-byte little-endian canonical integers"""
+        n = len(scalars_le32) // 32 if n is None else n
+        out = ctypes.create_string_buffer(2 * self.modbytes)
+        self._check(lib().bpgpu_msm_le32(self.handle, points.handle, off, n, _buf(scalars_le32), out), "msm_le32")
         return out.raw
 
     def msm_device(self, points, scalars, poff=0, soff=0, n=None):

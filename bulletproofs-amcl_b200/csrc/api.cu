@@ -610,6 +610,24 @@ int bpgpu_msm(bpgpu_ctx* ctx, const bpgpu_points* p, size_t off, size_t n, const
   return msm_to_host(ctx, (const uint8_t*)p->d + off * psz, ctx->msm_c.p, false, n, out_xy);
 }
 
+// resident bases, scalars as 32-byte LITTLE-endian canonical integers (< r): exactly the device's limb layout, so the
+// upload is one copy of 32 bytes per term and no conversion launch (48-byte big-endian scalars cost 50 % more PCIe
+// traffic on BLS12-381 plus a pass over them)
+int bpgpu_msm_le32(bpgpu_ctx* ctx, const bpgpu_points* p, size_t off, size_t n, const uint8_t* scalars_le32, uint8_t* out_xy) {
+  if (!ctx || !p || !out_xy || (!scalars_le32 && n)) return BPGPU_E_ARG;
+  if (off > p->n || n > p->n - off) return BPGPU_E_LEN;
+  BP_CUDA_OK(cudaSetDevice(ctx->device));
+  int rc = ctx->msm_c.reserve(n * 32 + 32);
+  if (rc) return rc;
+  if (n) BP_CUDA_OK(cudaMemcpyAsync(ctx->msm_c.p, scalars_le32, n * 32, cudaMemcpyHostToDevice, ctx->stream));
+  size_t psz = (ctx->curve == BPGPU_BLS12_381) ? sizeof(Affine<Bls::Fq>) : sizeof(Affine<Bn::Fq>);
+  if (p->table && n) {
+    TableSeg seg{(const uint8_t*)p->table + off * TBL_ENTRIES * psz, ctx->msm_c.p, (uint32_t)n, 0};
+    return msm_mixed_to_host(ctx, &seg, 1, nullptr, nullptr, false, 0, out_xy);
+  }
+  return msm_to_host(ctx, (const uint8_t*)p->d + off * psz, ctx->msm_c.p, false, n, out_xy);
+}
+
 int bpgpu_msm_device(bpgpu_ctx* ctx, const bpgpu_points* p, size_t poff, size_t n, const bpgpu_scalars* s, size_t soff,
                      uint8_t* out_xy) {
   if (!ctx || !p || !s || !out_xy) return BPGPU_E_ARG;

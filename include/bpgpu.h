@@ -107,6 +107,10 @@ void bpgpu_scalars_free(bpgpu_scalars* s);
 /* cached bases P[off .. off+n), host scalars */
 int bpgpu_msm(bpgpu_ctx* ctx, const bpgpu_points* p, size_t off, size_t n, const uint8_t* scalars_be,
               uint8_t* out_xy);
+/* cached bases, host scalars as 32-byte LITTLE-endian canonical integers (value < r, the caller's responsibility): the
+ * wire format of callers that keep scalars as 4 x u64 limbs -- one 32-byte copy per term, no conversion pass */
+int bpgpu_msm_le32(bpgpu_ctx* ctx, const bpgpu_points* p, size_t off, size_t n, const uint8_t* scalars_le32,
+                   uint8_t* out_xy);
 /* cached bases and device-resident scalars */
 int bpgpu_msm_device(bpgpu_ctx* ctx, const bpgpu_points* p, size_t poff, size_t n, const bpgpu_scalars* s,
                      size_t soff, uint8_t* out_xy);

@@ -218,3 +218,45 @@ def test_msm_sharded_over_contexts(which, bp, ctx_bls, ctx_bn):
         sh.free()
     for c in ctxs[1:]:
         c.close()
+
+
+def _np_scalars(n, seed, mb, bits=253):
+    """n uniform `bits`-bit scalars as (big-endian MODBYTES byte block, list of ints) -- numpy, for the 2^21 / 2^22 cases"""
+    import numpy as np
+    rng = np.random.default_rng(seed)
+    raw = rng.integers(0, 256, size=(n, 32), dtype=np.uint8)
+    keep = bits - 248
+    raw[:, 0] &= (1 << keep) - 1 if keep > 0 else 0
+    out = np.zeros((n, mb), dtype=np.uint8)
+    out[:, mb - 32:] = raw
+    b = out.tobytes()
+    return b, [int.from_bytes(b[i * mb + mb - 32:(i + 1) * mb], "big") for i in range(n)]
+
+
+@pytest.mark.parametrize("which,lg", [("bls", 21), ("bls", 22), ("bn", 22)])
+def test_msm_config4_top_sizes(which, lg, ctx_bls, ctx_bn):
+    """BASELINE.json config 4 ("standalone G1 MSM sweep 2^10-2^22") at its two largest sizes, which nothing exercised in
+    round 1: sum s_i*(k_i*G) == (sum s_i*k_i mod r)*G for uniform scalars and for a 0/1-heavy mix (giant buckets), through
+    the resident-bases entry point and through the host-buffer one (copy queue + event path)."""
+    ctx = ctx_bls if which == "bls" else ctx_bn
+    C = curve_of(ctx)
+    n, mb = 1 << lg, C.MODBYTES
+    kb, ks = _np_scalars(n, 100 + lg, mb)
+    g = C.g1_xy_bytes(C.from_affine(C.g))
+    xy = ctx.selftest_group(2, g * n, g * n, kb)
+    dp = ctx.upload_points(xy)
+    G = C.from_affine(C.g)
+    sb, s = _np_scalars(n, 200 + lg, mb)
+    tot = sum(a * b for a, b in zip(s, ks)) % C.r
+    exp = C.g1_xy_bytes(C.mul(G, tot))
+    assert ctx.msm(dp, sb) == exp
+    assert ctx.msm_le32(dp, b"".join(x.to_bytes(32, "little") for x in s)) == exp
+    if lg == 22:
+        assert ctx.msm_refs(xy, sb) == exp
+    import numpy as np
+    bits = np.random.default_rng(5).integers(0, 2, size=n, dtype=np.uint8)
+    blk = np.zeros((n, mb), dtype=np.uint8)
+    blk[:, mb - 1] = bits
+    tot = sum(k for k, b in zip(ks, bits.tolist()) if b) % C.r
+    assert ctx.msm(dp, blk.tobytes()) == C.g1_xy_bytes(C.mul(G, tot))
+    dp.free()
