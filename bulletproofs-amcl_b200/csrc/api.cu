@@ -2,6 +2,7 @@
 // the MSM entry points, and the self-test / microbenchmark hooks.
 #include <string.h>
 
+#include <mutex>
 #include <new>
 
 #include "common.cuh"
@@ -339,6 +340,29 @@ using namespace bp;
 #define DISPATCH(ctx, CALL)                          \
   ((ctx)->curve == BPGPU_BLS12_381 ? CALL(Bls) : CALL(Bn))
 
+// one stream-ordered pool per device, created on first use and never destroyed (contexts come and go, e.g. the second
+// driver of a batch call: a fresh pool per context would pay the physical allocation of its scratch again every call)
+static cudaMemPool_t library_pool(int device) {
+  static std::mutex mu;
+  static cudaMemPool_t pools[64] = {nullptr};
+  if (device < 0 || device >= 64) return nullptr;
+  std::lock_guard<std::mutex> lock(mu);
+  if (!pools[device]) {
+    cudaMemPoolProps pp;
+    memset(&pp, 0, sizeof pp);
+    pp.allocType = cudaMemAllocationTypePinned;
+    pp.handleTypes = cudaMemHandleTypeNone;
+    pp.location.type = cudaMemLocationTypeDevice;
+    pp.location.id = device;
+    cudaMemPool_t p = nullptr;
+    if (cudaMemPoolCreate(&p, &pp) != cudaSuccess) return nullptr;
+    uint64_t keep = ~0ull;
+    cudaMemPoolSetAttribute(p, cudaMemPoolAttrReleaseThreshold, &keep);
+    pools[device] = p;
+  }
+  return pools[device];
+}
+
 extern "C" {
 
 const char* bpgpu_strerror(int code) {
@@ -395,19 +419,11 @@ int bpgpu_ctx_create(int curve, int device, bpgpu_ctx** out) {
   CTX_OK(cudaEventCreateWithFlags(&c->points_ready, cudaEventDisableTiming));
   CTX_OK(cudaEventCreateWithFlags(&c->sync_event, cudaEventDisableTiming | cudaEventBlockingSync));
   { const char* e = getenv("BPGPU_BLOCKING_SYNC"); c->blocking_sync = e && atoi(e) != 0; }
-  {
-    // a memory pool of the ctx's own for handle storage: freed blocks stay in it for the next proof (release threshold
-    // raised), without touching the device's default pool that other cudaMallocAsync users of the process share
-    cudaMemPoolProps pp;
-    memset(&pp, 0, sizeof pp);
-    pp.allocType = cudaMemAllocationTypePinned;
-    pp.handleTypes = cudaMemHandleTypeNone;
-    pp.location.type = cudaMemLocationTypeDevice;
-    pp.location.id = device;
-    CTX_OK(cudaMemPoolCreate(&c->pool, &pp));
-    uint64_t keep = ~0ull;
-    CTX_OK(cudaMemPoolSetAttribute(c->pool, cudaMemPoolAttrReleaseThreshold, &keep));
-  }
+  // handle storage comes from a memory pool the LIBRARY owns (one per device, shared by its contexts, kept for the life of
+  // the process): freed blocks stay in it for the next proof and the next context (release threshold raised), and the
+  // device's default pool -- which other cudaMallocAsync users of the process share -- is left alone
+  c->pool = library_pool(device);
+  if (!c->pool) { bpgpu_ctx_destroy(c); return BPGPU_E_CUDA; }
   c->pinned_cap = 1 << 18;
   CTX_OK(cudaHostAlloc((void**)&c->pinned, c->pinned_cap, cudaHostAllocDefault));
   CTX_OK(cudaHostAlloc((void**)&c->bad_input, 64, cudaHostAllocMapped));
@@ -432,7 +448,6 @@ void bpgpu_ctx_destroy(bpgpu_ctx* c) {
   if (c->bad_input) cudaFreeHost(c->bad_input);
   if (c->stream) cudaStreamDestroy(c->stream);
   if (c->copy_stream) cudaStreamDestroy(c->copy_stream);
-  if (c->pool) cudaMemPoolDestroy(c->pool);
   if (c->points_ready) cudaEventDestroy(c->points_ready);
   if (c->sync_event) cudaEventDestroy(c->sync_event);
   delete c;

@@ -49,7 +49,7 @@ struct bpgpu_ctx {
   int device = 0;
   int sm_count = 148;
   cudaStream_t stream = nullptr;
-  cudaMemPool_t pool = nullptr;   // stream-ordered pool of this ctx (handle storage: G1Vector / FieldElementVector / IPP state)
+  cudaMemPool_t pool = nullptr;   // the library's stream-ordered pool on this device (handle storage: G1Vector / FieldElementVector / IPP state)
   // second queue for the host->device copy of the points of a large bpgpu_msm_refs: the copy and the byte->limb
   // conversion overlap the scalar pipeline (digits, scan, scatter) on `stream`; k_chunk_acc waits on `points_ready`
   cudaStream_t copy_stream = nullptr;
@@ -95,7 +95,7 @@ namespace bp {
 
 // Handle storage (G1Vector / FieldElementVector / IPP state) comes from the device's stream-ordered pool on the ctx
 // stream: allocation and release are queue operations (microseconds), not driver calls that synchronise the device.
-// The pool is the ctx's own (created with the ctx, release threshold raised so freed blocks are reused by the next proof).
+// The pool is the library's own, one per device (api.cu library_pool; release threshold raised so freed blocks are reused).
 inline cudaError_t stream_sync(bpgpu_ctx* ctx) {
   if (!ctx->blocking_sync) return cudaStreamSynchronize(ctx->stream);
   cudaError_t e = cudaEventRecord(ctx->sync_event, ctx->stream);

@@ -7,6 +7,7 @@
 // 9 us per dependent XYZZ doubling, tools/latency_probe.py), so for fixed bases the doublings are done ONCE:
 // the table T[j][w][d-1] = d * 2^(8w) * B_j (w < 32, d = 1..255, affine) turns every later commitment into a sum of
 // <= 32k table entries, reduced by a block-wide tree: no doublings, one launch for a whole batch.
+#include <stdlib.h>
 #include <string.h>
 #include <thread>
 
@@ -107,32 +108,43 @@ struct TableSegs {
   uint32_t gfirst[TBL_MAX_GROUPS + 1];         // first segment of each group
   uint32_t gtotal[TBL_MAX_GROUPS];             // terms per group
 };
+// Grid-stride over (term, limb) items with SMALL blocks (6 tree levels instead of the 8 of a 256-thread block: every level
+// is a dependent full addition on a shrinking number of lanes): a thread adds the 4 byte-window entries of each of its
+// items, then the block tree leaves one XYZZ per block.  The next table entry is requested before the current one is
+// added: entries of a multi-GB table set are DRAM misses.
+static const int TS_THREADS = 64;
 template <class Curve>
-__global__ void __launch_bounds__(256) k_table_sum(TableSegs segs, XYZZ<typename Curve::Fq>* __restrict__ partial) {
+__global__ void __launch_bounds__(TS_THREADS) k_table_sum(TableSegs segs, XYZZ<typename Curve::Fq>* __restrict__ partial) {
   using Fq = typename Curve::Fq;
   using Fr = typename Curve::Fr;
-  __shared__ __align__(16) unsigned char smraw[256 * sizeof(XYZZ<Fq>)];
+  __shared__ __align__(16) unsigned char smraw[TS_THREADS * sizeof(XYZZ<Fq>)];
   XYZZ<Fq>* sm = reinterpret_cast<XYZZ<Fq>*>(smraw);
   const uint32_t grp = blockIdx.y;
-  const uint32_t gid = blockIdx.x * blockDim.x + threadIdx.x;
-  const uint32_t p = gid >> 3, j = gid & 7;
+  const uint32_t items = segs.gtotal[grp] * 8;
+  const uint32_t last = segs.gfirst[grp + 1] - 1;
   XYZZ<Fq> acc = XYZZ<Fq>::inf();
-  if (p < segs.gtotal[grp]) {
+  for (uint32_t it = blockIdx.x * TS_THREADS + threadIdx.x; it < items; it += gridDim.x * TS_THREADS) {
+    const uint32_t p = it >> 3, j = it & 7;
     uint32_t sg = segs.gfirst[grp];
-    const uint32_t last = segs.gfirst[grp + 1] - 1;
     while (sg < last && p >= segs.start[sg + 1]) sg++;
     const uint32_t idx = p - segs.start[sg];
-    Fr sc = load_vec((const Fr*)segs.scal[sg] + idx);
-    if (segs.mont[sg]) sc = sc.from_mont();
-    const uint32_t limb = sc.v[j];
-    if (limb) {
-      const uint32_t row = segs.rows[sg] ? segs.rows[sg][idx] : idx;
-      const Affine<Fq>* tb = (const Affine<Fq>*)segs.table[sg] + ((size_t)row * TBL_WINDOWS + TBL_PER_LIMB * j) * TBL_DIGITS;
+    uint32_t limb;
+    if (segs.mont[sg]) { Fr sc = load_vec((const Fr*)segs.scal[sg] + idx); limb = sc.is_zero() ? 0u : sc.from_mont().v[j]; }
+    else limb = ((const Fr*)segs.scal[sg])[idx].v[j];
+    if (!limb) continue;
+    const uint32_t row = segs.rows[sg] ? segs.rows[sg][idx] : idx;
+    const Affine<Fq>* tb = (const Affine<Fq>*)segs.table[sg] + ((size_t)row * TBL_WINDOWS + TBL_PER_LIMB * j) * TBL_DIGITS;
+    uint32_t d = limb & (uint32_t)TBL_DIGITS;
+    Affine<Fq> cur = d ? load_vec_ro(tb + (d - 1)) : Affine<Fq>::inf();
 #pragma unroll 1
-      for (int k = 0; k < TBL_PER_LIMB; k++) {
-        const uint32_t d = (limb >> (TBL_BITS * k)) & (uint32_t)TBL_DIGITS;
-        if (d) acc.madd(load_vec_ro(tb + k * TBL_DIGITS + (d - 1)));
+    for (int k = 0; k < TBL_PER_LIMB; k++) {
+      Affine<Fq> nxt = Affine<Fq>::inf();
+      if (k + 1 < TBL_PER_LIMB) {
+        const uint32_t dn = (limb >> (TBL_BITS * (k + 1))) & (uint32_t)TBL_DIGITS;
+        if (dn) nxt = load_vec_ro(tb + (k + 1) * TBL_DIGITS + (dn - 1));
       }
+      acc.madd(cur);                                   // madd of the identity (0, 0) is a no-op
+      cur = nxt;
     }
   }
   XYZZ<Fq> tot = block_tree_sum_256(acc, sm);
@@ -269,18 +281,34 @@ int table_sum_run(bpgpu_ctx* ctx, const TableSeg* segs, int nsegs, int ngroups, 
   ts.gfirst[ngroups] = q;
   ts.start[q] = 0;
   if (q > TBL_MAX_SEGS) return BPGPU_E_ARG;
-  // Every level of a block tree is one dependent XYZZ addition (~15 us): these sums are latency bound, so when the
-  // caller finishes on the host anyway (host_partials) small sums use 64-thread blocks (6 tree levels instead of 8) and
-  // the block results go to the host as they are -- it adds a few dozen points in less time than a second launch takes.
-  const uint32_t threads = maxtotal * 8;
-  uint32_t bs = 256;
-  if (host_partials && (threads + 63) / 64 * ngroups <= (uint32_t)TBL_HOST_PARTIALS) bs = 64;
-  uint32_t blocks = (threads + bs - 1) / bs;
+  // Every level of a block tree is one dependent XYZZ addition: these sums are latency bound, so blocks are small (6 tree
+  // levels) and, when the caller finishes on the host anyway (host_partials) and there are few of them, the block results go
+  // to the host as they are -- it adds a few dozen points in less time than a second launch takes.
+  // one (term, limb) item per thread while that fits the machine (these sums are bound by the LATENCY of a thread's chain:
+  // ~5 us per dependent mixed addition on BN254, ~10 us on BLS12-381); beyond sm_count * 8 blocks the grid strides
+  const uint32_t items = maxtotal * 8;
+  const uint32_t bs = TS_THREADS;
+  uint32_t blocks = (items + bs - 1) / bs;
+  const uint32_t cap = (uint32_t)ctx->sm_count * 8;
+  if (blocks > cap) blocks = cap;
   if (blocks == 0) blocks = 1;
   int rc = ctx->tbl_part.reserve(((size_t)blocks * ngroups + TBL_MAX_GROUPS) * sizeof(XYZZ<Fq>));
   if (rc) return rc;
   XYZZ<Fq>* out = (XYZZ<Fq>*)ctx->tbl_part.p;           // [0, ngroups) = results, then per-block sums
   if (host_partials) *host_partials = 0;
+  static const bool prof = getenv("BPGPU_PROFILE") != nullptr;
+  cudaEvent_t ev[2];
+  if (prof) { for (auto& e : ev) cudaEventCreate(&e); cudaEventRecord(ev[0], ctx->stream); }
+  struct ProfEnd {
+    bool on; cudaEvent_t* ev; cudaStream_t st; uint32_t terms, blocks; int groups;
+    ~ProfEnd() {
+      if (!on) return;
+      cudaEventRecord(ev[1], st); cudaEventSynchronize(ev[1]);
+      float ms; cudaEventElapsedTime(&ms, ev[0], ev[1]);
+      fprintf(stderr, "[bpgpu table_sum terms=%u groups=%d blocks=%u] %.3f ms\n", terms, groups, blocks, ms);
+      cudaEventDestroy(ev[0]); cudaEventDestroy(ev[1]);
+    }
+  } prof_end{prof, ev, ctx->stream, maxtotal, blocks, ngroups};
   if (blocks == 1) {
     k_table_sum<Curve><<<dim3(1, ngroups), bs, 0, ctx->stream>>>(ts, out);
     ctx->launches += 1;

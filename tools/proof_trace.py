@@ -5,7 +5,8 @@ m = int(sys.argv[1]); curve = bp.BLS12_381 if sys.argv[2] == "bls" else bp.BN254
 ctx = bp.Context(curve, 0)
 gx, hx = ctx.g1_from_msg_hash(b"g"), ctx.g1_from_msg_hash(b"h")
 n = m * 64
-G, H = ctx.get_generators("G", n, precompute=True), ctx.get_generators("H", n, precompute=True)
+pre = len(sys.argv) <= 3 or sys.argv[3] != "0"
+G, H = ctx.get_generators("G", n, precompute=pre), ctx.get_generators("H", n, precompute=pre)
 vals = [(12345678901234567 * (i + 1)) & ((1 << 64) - 1) for i in range(m)]
 proof, comms = ctx.range_prove(b"bench", gx, hx, G, H, vals, 64, seed=1)
 print("=== PROVE", file=sys.stderr, flush=True)
