@@ -20,6 +20,7 @@ SYMBOLS = [
     ("bpgpu_device_count", _INT, []),
     ("bpgpu_ctx_create", _INT, [_INT, _INT, _c.POINTER(_VP)]),
     ("bpgpu_ctx_destroy", None, [_VP]),
+    ("bpgpu_ctx_aux", _INT, [_VP, _c.POINTER(_VP)]),
     ("bpgpu_ctx_stream", _VP, [_VP]),
     ("bpgpu_ctx_sync", _INT, [_VP]),
     ("bpgpu_ctx_curve", _INT, [_VP]),
@@ -56,6 +57,7 @@ SYMBOLS = [
     ("bpgpu_r1cs_verify_batch_terms", _INT, [_VP, _VP, _VP, _VP, _VP, _VP, _SZ, _VP, _SZ, _VP, _VP, _VP, _VP, _SZ, _VP, _VP, _VP]),
     ("bpgpu_pbatch_create", _INT, [_VP, _VP, _VP, _VP, _VP, _SZ, _SZ, _c.POINTER(_VP)]),
     ("bpgpu_pbatch_free", None, [_VP]),
+    ("bpgpu_pbatch_prove_range", _INT, [_VP, _VP, _VP, _SZ, _SZ, _VP, _VP, _SZ, _VP, _SZ, _VP]),
     ("bpgpu_pbatch_commit3", _INT, [_VP, _VP, _VP, _SZ, _VP, _VP, _VP]),
     ("bpgpu_pbatch_polys", _INT, [_VP, _VP, _VP, _VP]),
     ("bpgpu_pbatch_eval", _INT, [_VP, _VP]),
@@ -113,6 +115,7 @@ SYMBOLS_HOST = [
     ("bph_range_proof_len", _SZ, [_INT, _SZ, _SZ]),
     ("bph_range_prove_many", _INT, [_VP, _SZ, _CS, _VP, _VP, _VP, _VP, _VP, _SZ, _SZ, _SZ, _INT, _U64, _VP, _SZ, _VP]),
     ("bph_range_prove_batch", _INT, [_VP, _CS, _VP, _VP, _VP, _VP, _VP, _SZ, _SZ, _SZ, _INT, _U64, _SZ, _VP, _SZ, _VP]),
+    ("bph_range_prove_batch_mode", _INT, [_VP, _CS, _VP, _VP, _VP, _VP, _VP, _SZ, _SZ, _SZ, _INT, _U64, _INT, _SZ, _VP, _SZ, _VP]),
     ("bph_range_verify_batch", _INT, [_VP, _CS, _VP, _VP, _VP, _VP, _SZ, _SZ, _SZ, _VP, _SZ, _VP, _SZ, _VP]),
     ("bph_range_verify_batch_mode", _INT, [_VP, _CS, _VP, _VP, _VP, _VP, _SZ, _SZ, _SZ, _VP, _SZ, _VP, _INT, _SZ, _VP]),
     ("bph_bound_check_verify_batch", _INT, [_VP, _CS, _VP, _VP, _VP, _VP, _SZ, _U64, _U64, _SZ, _VP, _SZ, _VP, _INT, _SZ, _VP]),
@@ -158,16 +161,17 @@ def range_prove_many(ctxs, label, g_xy, h_xy, G, H, values, m, bits, seed=None):
     return proofs.raw[:count * stride], stride, comms.raw[:count * m * 2 * c0.modbytes]
 
 
-def range_prove_batch(ctx, label, g_xy, h_xy, G, H, values, m, bits, seed=None, nthreads=0):
+def range_prove_batch(ctx, label, g_xy, h_xy, G, H, values, m, bits, seed=None, nthreads=0, mode=0):
     """the same proofs as range_prove_many, proved in lock-step on ONE context (one device call per prover stage and IPP
-    round for the whole batch).  Returns (proofs bytes, stride, commitments bytes)."""
+    round for the whole batch; mode 0: transcripts on the device too, mode 1: on host threads).
+    Returns (proofs bytes, stride, commitments bytes)."""
     count = len(values) // m
     stride = lib().bph_range_proof_len(ctx.curve, m, bits)
     proofs = ctypes.create_string_buffer(max(1, count * stride))
     comms = ctypes.create_string_buffer(max(1, count * m * 2 * ctx.modbytes))
     arr = (ctypes.c_uint64 * max(1, len(values)))(*values)
-    rc = lib().bph_range_prove_batch(ctx.handle, label, _buf(g_xy), _buf(h_xy), G.handle, H.handle, ctypes.cast(arr, ctypes.c_void_p), count, m,
-                                     bits, 0 if seed is None else 1, seed or 0, nthreads, proofs, stride, comms)
+    rc = lib().bph_range_prove_batch_mode(ctx.handle, label, _buf(g_xy), _buf(h_xy), G.handle, H.handle, ctypes.cast(arr, ctypes.c_void_p),
+                                          count, m, bits, 0 if seed is None else 1, seed or 0, mode, nthreads, proofs, stride, comms)
     if rc:
         raise BpgpuError(rc, "range_prove_batch")
     return proofs.raw[:count * stride], stride, comms.raw[:count * m * 2 * ctx.modbytes]

@@ -433,8 +433,19 @@ int bpgpu_ctx_create(int curve, int device, bpgpu_ctx** out) {
   return BPGPU_OK;
 }
 
+int bpgpu_ctx_aux(bpgpu_ctx* c, bpgpu_ctx** out) {
+  if (!c || !out) return BPGPU_E_ARG;
+  if (!c->aux) {
+    int rc = bpgpu_ctx_create(c->curve, c->device, &c->aux);
+    if (rc) return rc;
+  }
+  *out = c->aux;
+  return BPGPU_OK;
+}
+
 void bpgpu_ctx_destroy(bpgpu_ctx* c) {
   if (!c) return;
+  if (c->aux) { bpgpu_ctx_destroy(c->aux); c->aux = nullptr; }
   cudaSetDevice(c->device);
   if (c->stream) cudaStreamSynchronize(c->stream);
   for (bpgpu_fixed_bases* fb : c->fb_cache) bpgpu_fixed_bases_free(fb);

@@ -74,6 +74,7 @@ struct bpgpu_ctx {
   double stage_ms_sum[8] = {0, 0, 0, 0, 0, 0, 0, 0};
   uint64_t stage_runs = 0;
   std::vector<bpgpu_fixed_bases*> fb_cache;   // ctx-owned fixed-base tables (fixedbase.cu)
+  bpgpu_ctx* aux = nullptr;       // a second context on the same device, owned by this one (bpgpu_ctx_aux): the other driver of a batch call
 };
 
 struct bpgpu_points {

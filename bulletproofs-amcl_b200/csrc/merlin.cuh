@@ -15,7 +15,7 @@ namespace bp {
 BP_HD uint64_t mrl_rotl64(uint64_t x, int n) { return (x << n) | (x >> (64 - n)); }
 
 // Keccak-f[1600], 24 rounds; one round unrolled, the round loop kept rolled (code size: this runs next to field code)
-BP_HD_COLD void keccak_f1600_hd(uint64_t* a) {
+static BP_HD_COLD void keccak_f1600_hd(uint64_t* a) {
   const uint64_t RC[24] = {0x0000000000000001ULL, 0x0000000000008082ULL, 0x800000000000808aULL, 0x8000000080008000ULL,
                            0x000000000000808bULL, 0x0000000080000001ULL, 0x8000000080008081ULL, 0x8000000000008009ULL,
                            0x000000000000008aULL, 0x0000000000000088ULL, 0x0000000080008009ULL, 0x000000008000000aULL,

@@ -104,22 +104,21 @@ BP_HD int vb_header_finish(const uint8_t* proof, uint32_t lg, const typename Cur
   return BPGPU_OK;
 }
 
-// The verifier's transcript for one proof of a one-phase circuit (verifier.rs:124-132, 279-323; ipp.rs:278-288), starting
-// from the exported state after Transcript::new(label) and r1cs_domain_sep().  Writes the header; returns BPGPU_OK or
-// BPGPU_E_FORMAT (a point without the 0x04 tag, a non-canonical scalar).
+// The transcript of one proof of a one-phase circuit in the four stages at which a PROVER can advance it (the verifier
+// replays them back to back): identical on both sides (prover.rs:119-129,327,364-366,432-439,502-509,543-549; verifier.rs:
+// 124-132,279-323; ipp.rs:62,106-113,172-179,278-288).  Points are read from the flat proof record / the commitment list.
 template <class Curve>
-BP_HD int vb_replay(const uint8_t* state0, const uint8_t* proof, const uint8_t* comms_xy, uint32_t m, uint32_t lg, uint64_t N,
-                    const typename Curve::Fr& r, typename Curve::Fr* hdr) {
-  using Fr = typename Curve::Fr;
+BP_HD typename Curve::Fr tr_challenge(StrobeHD& t, const char* label, uint32_t label_len) {
+  uint8_t buf[Curve::MODBYTES];
+  t.challenge_bytes(label, label_len, buf, Curve::MODBYTES);
+  return fr_from_be_wide<Curve>(buf);
+}
+// V_1..V_m, "m", A_I1 A_O1 S1, 1-phase separator, A_I2 A_O2 S2 -> y, z
+template <class Curve>
+BP_HD void tr_stage_commitments(StrobeHD& t, const uint8_t* proof, const uint8_t* comms_xy, uint32_t m, typename Curve::Fr* y,
+                                typename Curve::Fr* z) {
   using PL = ProofLayout<Curve>;
   constexpr uint32_t MB = Curve::MODBYTES;
-  for (uint32_t k = 0; k < 11 + 2 * lg; k++) {
-    const uint32_t off = k < 11 ? PL::point(k) : PL::L(k - 11);
-    if (proof[off] != 4) return BPGPU_E_FORMAT;
-  }
-  StrobeHD t;
-  t.load(state0);
-  uint8_t buf[MB];
   for (uint32_t j = 0; j < m; j++) t.append_message(MRL_LIT("V"), comms_xy + (size_t)j * 2 * MB, 2 * MB, 4);
   t.append_u64(MRL_LIT("m"), m);
   t.append_message(MRL_LIT("A_I1"), proof + PL::point(0) + 1, 2 * MB, 4);
@@ -129,33 +128,64 @@ BP_HD int vb_replay(const uint8_t* state0, const uint8_t* proof, const uint8_t* 
   t.append_message(MRL_LIT("A_I2"), proof + PL::point(3) + 1, 2 * MB, 4);
   t.append_message(MRL_LIT("A_O2"), proof + PL::point(4) + 1, 2 * MB, 4);
   t.append_message(MRL_LIT("S2"), proof + PL::point(5) + 1, 2 * MB, 4);
-  t.challenge_bytes(MRL_LIT("y"), buf, MB);
-  const Fr y = fr_from_be_wide<Curve>(buf);
-  t.challenge_bytes(MRL_LIT("z"), buf, MB);
-  const Fr z = fr_from_be_wide<Curve>(buf);
+  *y = tr_challenge<Curve>(t, MRL_LIT("y"));
+  *z = tr_challenge<Curve>(t, MRL_LIT("z"));
+}
+// T_1 T_3 T_4 T_5 T_6 -> u, x
+template <class Curve>
+BP_HD void tr_stage_t(StrobeHD& t, const uint8_t* proof, typename Curve::Fr* u, typename Curve::Fr* x) {
+  using PL = ProofLayout<Curve>;
+  constexpr uint32_t MB = Curve::MODBYTES;
   t.append_message(MRL_LIT("T_1"), proof + PL::point(6) + 1, 2 * MB, 4);
   t.append_message(MRL_LIT("T_3"), proof + PL::point(7) + 1, 2 * MB, 4);
   t.append_message(MRL_LIT("T_4"), proof + PL::point(8) + 1, 2 * MB, 4);
   t.append_message(MRL_LIT("T_5"), proof + PL::point(9) + 1, 2 * MB, 4);
   t.append_message(MRL_LIT("T_6"), proof + PL::point(10) + 1, 2 * MB, 4);
-  t.challenge_bytes(MRL_LIT("u"), buf, MB);
-  const Fr u = fr_from_be_wide<Curve>(buf);
-  t.challenge_bytes(MRL_LIT("x"), buf, MB);
-  const Fr x = fr_from_be_wide<Curve>(buf);
+  *u = tr_challenge<Curve>(t, MRL_LIT("u"));
+  *x = tr_challenge<Curve>(t, MRL_LIT("x"));
+}
+// t_x, t_x_blinding, e_blinding -> w; then the inner-product argument's separator
+template <class Curve>
+BP_HD void tr_stage_scalars(StrobeHD& t, const uint8_t* proof, uint64_t N, typename Curve::Fr* w) {
+  using PL = ProofLayout<Curve>;
+  constexpr uint32_t MB = Curve::MODBYTES;
   t.append_message(MRL_LIT("t_x"), proof + PL::scalar(0), MB);
   t.append_message(MRL_LIT("t_x_blinding"), proof + PL::scalar(1), MB);
   t.append_message(MRL_LIT("e_blinding"), proof + PL::scalar(2), MB);
-  t.challenge_bytes(MRL_LIT("w"), buf, MB);
-  const Fr w = fr_from_be_wide<Curve>(buf);
+  *w = tr_challenge<Curve>(t, MRL_LIT("w"));
   t.append_message(MRL_LIT("dom-sep"), (const uint8_t*)"ipp v1", 6);
   t.append_u64(MRL_LIT("n"), N);
-  Fr uk[32];
-  for (uint32_t k = 0; k < lg; k++) {
-    t.append_message(MRL_LIT("L"), proof + PL::L(k) + 1, 2 * MB, 4);
-    t.append_message(MRL_LIT("R"), proof + PL::R(lg, k) + 1, 2 * MB, 4);
-    t.challenge_bytes(MRL_LIT("u"), buf, MB);
-    uk[k] = fr_from_be_wide<Curve>(buf);
+}
+// L_k, R_k -> u_k
+template <class Curve>
+BP_HD typename Curve::Fr tr_round(StrobeHD& t, const uint8_t* proof, uint32_t lg, uint32_t k) {
+  using PL = ProofLayout<Curve>;
+  constexpr uint32_t MB = Curve::MODBYTES;
+  t.append_message(MRL_LIT("L"), proof + PL::L(k) + 1, 2 * MB, 4);
+  t.append_message(MRL_LIT("R"), proof + PL::R(lg, k) + 1, 2 * MB, 4);
+  return tr_challenge<Curve>(t, MRL_LIT("u"));
+}
+
+// The verifier's replay for one proof, starting from the exported state after Transcript::new(label) and
+// r1cs_domain_sep().  Writes the header; returns BPGPU_OK or BPGPU_E_FORMAT (a point without the 0x04 tag, a non-canonical
+// scalar).
+template <class Curve>
+BP_HD int vb_replay(const uint8_t* state0, const uint8_t* proof, const uint8_t* comms_xy, uint32_t m, uint32_t lg, uint64_t N,
+                    const typename Curve::Fr& r, typename Curve::Fr* hdr) {
+  using Fr = typename Curve::Fr;
+  using PL = ProofLayout<Curve>;
+  for (uint32_t k = 0; k < 11 + 2 * lg; k++) {
+    const uint32_t off = k < 11 ? PL::point(k) : PL::L(k - 11);
+    if (proof[off] != 4) return BPGPU_E_FORMAT;
   }
+  StrobeHD t;
+  t.load(state0);
+  Fr y, z, u, x, w;
+  tr_stage_commitments<Curve>(t, proof, comms_xy, m, &y, &z);
+  tr_stage_t<Curve>(t, proof, &u, &x);
+  tr_stage_scalars<Curve>(t, proof, N, &w);
+  Fr uk[32];
+  for (uint32_t k = 0; k < lg; k++) uk[k] = tr_round<Curve>(t, proof, lg, k);
   return vb_header_finish<Curve>(proof, lg, y, z, u, x, w, r, uk, hdr);
 }
 
@@ -264,3 +294,11 @@ BP_HD const uint8_t* vb_var_point_bytes(const uint8_t* proof, const uint8_t* com
 }
 
 }  // namespace bp
+
+// bpgpu_circuit (include/bpgpu.h): a one-phase constraint system resident on one device
+struct bpgpu_ctx;
+struct bpgpu_circuit {
+  bpgpu_ctx* ctx;
+  bp::CircuitDev dev;
+  void* mem;
+};

@@ -18,12 +18,6 @@
 #include "host_fp.h"
 #include "verify_core.cuh"
 
-struct bpgpu_circuit {
-  bpgpu_ctx* ctx;
-  bp::CircuitDev dev;
-  void* mem;
-};
-
 namespace bp {
 
 struct VbKey { uint8_t b[64]; uint32_t len; };

@@ -460,10 +460,84 @@ int circuit_csr_export(const typename Verifier<C>::CircuitCSR& csr, size_t* n, s
   return BPGPU_OK;
 }
 
+// mode 0: the whole slab on the device (bpgpu_pbatch_prove_range: transcripts, draws, flattening and normalisation there too);
+// mode 1: lock-step with the transcripts on `nthreads` host threads (prove_batch.hpp)
+template <class C>
+int range_prove_batch_device_t(bpgpu_ctx* ctx, const char* label, const uint8_t* g_xy, const uint8_t* h_xy, bpgpu_points* G, bpgpu_points* H,
+                               const uint64_t* values, size_t count, size_t m, size_t bits, int rng_mode, uint64_t seed, uint8_t* proofs,
+                               size_t stride, uint8_t* comms_xy) {
+  const size_t mb = C::MODBYTES, n = m * bits;
+  typename Verifier<C>::CircuitCSR csr;
+  int rc = range_circuit_csr<C>(m, bits, &csr);
+  if (rc) return rc;
+  if ((rc = points_valid<C>(g_xy, 1)) || (rc = points_valid<C>(h_xy, 1))) return rc;
+  if ((rc = bpgpu_points_precompute(ctx, G)) || (rc = bpgpu_points_precompute(ctx, H))) return rc;
+  uint8_t state0[203];
+  {
+    Transcript t0{std::string(label)};
+    t0.r1cs_domain_sep();                                  // Prover::new (prover.rs:84-101)
+    t0.export_state(state0);
+  }
+  // one blinding stream per proof (host/curve.hpp Rng): seed + i || "blind", or 32 bytes of OS entropy || "os"
+  const size_t klen = rng_mode == 1 ? 13 : 34;
+  std::vector<uint8_t> keys(count * klen);
+  for (size_t i = 0; i < count; i++) {
+    Rng<C> r = rng_mode == 1 ? Rng<C>(seed + i, "blind") : Rng<C>();
+    if (!r.ok() || r.key_len() != klen) return BPH_E_ENTROPY;
+    memcpy(keys.data() + i * klen, r.key(), klen);
+  }
+  // Slabs in flight: the per-proof kernels of a slab (transcripts, inversions: a few warps, latency bound) run in the gaps of
+  // the table sums of the others.  BPH_PB_SLAB / BPH_PB_DRIVERS override the defaults (tuning runs).
+  size_t SLAB = n <= 128 ? 2048 : (n <= 1024 ? 1024 : 256);
+  size_t maxdrv = 2;
+  if (const char* e = getenv("BPH_PB_SLAB")) SLAB = (size_t)atol(e) ? (size_t)atol(e) : SLAB;
+  if (const char* e = getenv("BPH_PB_DRIVERS")) maxdrv = (size_t)atol(e) >= 1 && (size_t)atol(e) <= 4 ? (size_t)atol(e) : maxdrv;
+  size_t ndrv = (count + SLAB - 1) / SLAB;
+  if (ndrv > maxdrv) ndrv = maxdrv;
+  if (ndrv == 0) ndrv = 1;
+  size_t B = (count + ndrv - 1) / ndrv;
+  if (B > SLAB) B = SLAB;
+  const size_t nslab = (count + B - 1) / B;
+  bpgpu_ctx* dctxs[4] = {ctx, nullptr, nullptr, nullptr};
+  for (size_t k = 1; k < ndrv; k++)
+    if ((rc = bpgpu_ctx_aux(dctxs[k - 1], &dctxs[k]))) return rc;      // a chain of cached contexts: ctx -> aux -> aux of aux
+  std::atomic<int> err{0};
+  auto driver = [&](size_t k, bpgpu_ctx* dctx) {
+    bpgpu_pbatch* pb = nullptr;
+    bpgpu_circuit* circ = nullptr;
+    size_t pb_size = 0;
+    int r = bpgpu_circuit_create(dctx, csr.n, csr.m, csr.q, csr.row_start.data(), csr.ent_q.data(), csr.ent_c_be.data(), &circ);
+    for (size_t sl = k; !r && sl < nslab && !err.load(); sl += ndrv) {
+      const size_t lo = sl * B, cnt = count - lo < B ? count - lo : B;
+      if (cnt != pb_size) {
+        bpgpu_pbatch_free(pb);
+        pb = nullptr;
+        r = bpgpu_pbatch_create(dctx, G, H, g_xy, h_xy, cnt, n, &pb);
+        pb_size = cnt;
+      }
+      if (!r)
+        r = bpgpu_pbatch_prove_range(pb, circ, values + lo * m, m, bits, state0, keys.data() + lo * klen, klen, proofs + lo * stride, stride,
+                                     comms_xy + lo * m * 2 * mb);
+    }
+    if (r) { int z = 0; err.compare_exchange_strong(z, r); }
+    bpgpu_pbatch_free(pb);
+    bpgpu_circuit_free(circ);
+  };
+  {
+    std::vector<std::thread> others;
+    for (size_t k = 1; k < ndrv; k++) others.emplace_back(driver, k, dctxs[k]);
+    driver(0, ctx);
+    for (auto& t : others) t.join();
+  }
+  secure_zero(keys.data(), keys.size());
+  return err.load();
+}
+
 template <class C>
 int range_prove_batch_t(bpgpu_ctx* ctx, const char* label, const uint8_t* g_xy, const uint8_t* h_xy, bpgpu_points* G, bpgpu_points* H,
-                        const uint64_t* values, size_t count, size_t m, size_t bits, int rng_mode, uint64_t seed, size_t nthreads,
+                        const uint64_t* values, size_t count, size_t m, size_t bits, int rng_mode, uint64_t seed, int mode, size_t nthreads,
                         uint8_t* proofs, size_t stride, uint8_t* comms_xy) {
+  if (mode == 0) return range_prove_batch_device_t<C>(ctx, label, g_xy, h_xy, G, H, values, count, m, bits, rng_mode, seed, proofs, stride, comms_xy);
   if (nthreads == 0) nthreads = std::thread::hardware_concurrency();
   if (nthreads == 0) nthreads = 1;
   // Two drivers (this thread on `ctx`, a second thread on a context of its own on the same device) take alternate slabs:
@@ -476,8 +550,8 @@ int range_prove_batch_t(bpgpu_ctx* ctx, const char* label, const uint8_t* g_xy, 
   const G1<C> g = G1<C>::from_xy(g_xy), h = G1<C>::from_xy(h_xy);
   bpgpu_ctx* ctx2 = nullptr;
   int rc = BPGPU_OK;
-  if (ndrv == 2 && (rc = bpgpu_ctx_create(bpgpu_ctx_curve(ctx), bpgpu_ctx_device(ctx), &ctx2))) return rc;
-  if ((rc = bpgpu_points_precompute(ctx, G)) || (rc = bpgpu_points_precompute(ctx, H))) { if (ctx2) bpgpu_ctx_destroy(ctx2); return rc; }
+  if (ndrv == 2 && (rc = bpgpu_ctx_aux(ctx, &ctx2))) return rc;
+  if ((rc = bpgpu_points_precompute(ctx, G)) || (rc = bpgpu_points_precompute(ctx, H))) return rc;
   std::atomic<int> err{0};
   auto driver = [&](size_t k, bpgpu_ctx* dctx) {
     typename BatchProverAccess<C>::Pool pool(std::max<size_t>(1, nthreads / ndrv));
@@ -503,7 +577,6 @@ int range_prove_batch_t(bpgpu_ctx* ctx, const char* label, const uint8_t* g_xy, 
     std::thread other(driver, 1, ctx2);
     driver(0, ctx);
     other.join();
-    bpgpu_ctx_destroy(ctx2);
   } else {
     driver(0, ctx);
   }
@@ -695,15 +768,22 @@ int bph_range_verify_many(bpgpu_ctx* const* ctxs, size_t nctx, const char* label
   return BPGPU_OK;
 }
 
+int bph_range_prove_batch_mode(bpgpu_ctx* ctx, const char* label, const uint8_t* g_xy, const uint8_t* h_xy, bpgpu_points* G, bpgpu_points* H,
+                               const uint64_t* values, size_t count, size_t m, size_t bits, int rng_mode, uint64_t seed, int mode, size_t nthreads,
+                               uint8_t* proofs, size_t proof_stride, uint8_t* comms_xy) {
+  if (!ctx || !label || !g_xy || !h_xy || !G || !H || (count && (!values || !proofs || !comms_xy)) || !m || !bits || bits > 64 || mode < 0 || mode > 1)
+    return BPGPU_E_ARG;
+  if (proof_stride < bph_range_proof_len(bpgpu_ctx_curve(ctx), m, bits)) return BPH_E_BUFFER;
+  if (count == 0) return BPGPU_OK;
+#define CALL(C) range_prove_batch_t<C>(ctx, label, g_xy, h_xy, G, H, values, count, m, bits, rng_mode, seed, mode, nthreads, proofs, proof_stride, comms_xy)
+  return BY_CURVE(ctx, CALL);
+#undef CALL
+}
+
 int bph_range_prove_batch(bpgpu_ctx* ctx, const char* label, const uint8_t* g_xy, const uint8_t* h_xy, bpgpu_points* G, bpgpu_points* H,
                           const uint64_t* values, size_t count, size_t m, size_t bits, int rng_mode, uint64_t seed, size_t nthreads,
                           uint8_t* proofs, size_t proof_stride, uint8_t* comms_xy) {
-  if (!ctx || !label || !g_xy || !h_xy || !G || !H || (count && (!values || !proofs || !comms_xy)) || !m || !bits || bits > 64) return BPGPU_E_ARG;
-  if (proof_stride < bph_range_proof_len(bpgpu_ctx_curve(ctx), m, bits)) return BPH_E_BUFFER;
-  if (count == 0) return BPGPU_OK;
-#define CALL(C) range_prove_batch_t<C>(ctx, label, g_xy, h_xy, G, H, values, count, m, bits, rng_mode, seed, nthreads, proofs, proof_stride, comms_xy)
-  return BY_CURVE(ctx, CALL);
-#undef CALL
+  return bph_range_prove_batch_mode(ctx, label, g_xy, h_xy, G, H, values, count, m, bits, rng_mode, seed, 0, nthreads, proofs, proof_stride, comms_xy);
 }
 
 int bph_g1_sum(int curve, const uint8_t* points_xy, size_t count, uint8_t* out_xy) {

@@ -47,6 +47,7 @@ typedef struct bpgpu_points bpgpu_points;   /* device-resident G1Vector (affine,
 typedef struct bpgpu_scalars bpgpu_scalars; /* device-resident FieldElementVector (Montgomery form) */
 typedef struct bpgpu_ipp bpgpu_ipp;         /* device-resident state of one create_ipp run */
 typedef struct bpgpu_fixed_bases bpgpu_fixed_bases; /* window tables of a few fixed bases, e.g. the Pedersen pair (g, h) */
+typedef struct bpgpu_circuit bpgpu_circuit;         /* a one-phase constraint system as a device-resident sparse matrix */
 
 const char* bpgpu_strerror(int code);
 int bpgpu_modbytes(int curve);              /* amcl_wrapper::constants::MODBYTES */
@@ -54,6 +55,9 @@ int bpgpu_device_count(void);
 
 int bpgpu_ctx_create(int curve, int device, bpgpu_ctx** out);
 void bpgpu_ctx_destroy(bpgpu_ctx* ctx);
+/* a second context (stream + scratch) on the same device, created on first use, owned by and destroyed with `ctx`: the other
+ * driver thread of the batch calls, which keep two slabs in flight (a context costs ~20 ms to set up: not per call) */
+int bpgpu_ctx_aux(bpgpu_ctx* ctx, bpgpu_ctx** out);
 void* bpgpu_ctx_stream(bpgpu_ctx* ctx);     /* the cudaStream_t all work of this ctx is issued on */
 int bpgpu_ctx_sync(bpgpu_ctx* ctx);
 int bpgpu_ctx_curve(const bpgpu_ctx* ctx);
@@ -150,7 +154,6 @@ int bpgpu_msm_batch_is_identity(bpgpu_ctx* ctx, const bpgpu_fixed_run* runs, siz
  * verifier.rs:166-190 applied by the caller (committed and constant terms negated).  Bits 31 / 30 of ent_q flag the
  * coefficients +1 / -1 (the product is skipped).  q = number of constraints.  host/r1cs.hpp Verifier::export_csr builds it.
  * bpgpu_circuit_flatten: [wL | wR | wO | wV | wc] for one challenge z (3n + m + 1 device scalars). */
-typedef struct bpgpu_circuit bpgpu_circuit;
 int bpgpu_circuit_create(bpgpu_ctx* ctx, size_t n, size_t m, size_t q, const uint32_t* row_start, const uint32_t* ent_q,
                          const uint8_t* ent_coeff_be, bpgpu_circuit** out);
 void bpgpu_circuit_free(bpgpu_circuit* c);
@@ -247,6 +250,18 @@ int bpgpu_pbatch_polys(bpgpu_pbatch* pb, const uint8_t* weights_be, const uint8_
 int bpgpu_pbatch_eval(bpgpu_pbatch* pb, const uint8_t* xuw_be);
 int bpgpu_pbatch_ipp_round(bpgpu_pbatch* pb, const uint8_t* uv_be, uint8_t* out_xy);
 int bpgpu_pbatch_ipp_finish(bpgpu_pbatch* pb, const uint8_t* uv_be, uint8_t* ab_be);
+
+/* The whole slab in ONE call, transcripts on the device (SURVEY.md section 8 f3 for slabs): `batch` range proofs of m values x
+ * `bits` bits each (m * bits = the pbatch's n; `circuit` = the same statement's constraint matrix, bph_range_circuit_csr).
+ * values = batch x m u64; transcript_state = the exported Merlin state after Transcript::new(label) + r1cs_domain_sep()
+ * (203 bytes); keys = batch x key_len bytes, proof i's blinding stream SHAKE256(key_i || le64(counter)) consumed in the
+ * reference's draw order.  The device derives the witness bits (positive_no.rs:18-24), draws every
+ * blinding, replays the transcripts (one thread per proof), flattens the constraints from each proof's z, normalises every
+ * commitment (one inversion per 4 points) and assembles the flat proof records: proofs = batch x proof_stride bytes,
+ * comms_xy = batch x m commitments.  Proof i is byte-identical to gen_proof_of_positive_nums with the same stream. */
+int bpgpu_pbatch_prove_range(bpgpu_pbatch* pb, const bpgpu_circuit* circuit, const uint64_t* values, size_t m, size_t bits,
+                             const uint8_t* transcript_state, const uint8_t* keys, size_t key_len, uint8_t* proofs,
+                             size_t proof_stride, uint8_t* comms_xy);
 
 /* ---- inner-product argument, device-resident across rounds (IPP::create_ipp, ipp.rs:35-202) ----
  * begin: clones G[goff..goff+n), H[hoff..), a, b and the factor vectors (ipp.rs:57-60); n must be a power

@@ -123,13 +123,19 @@ void bph_r1cs_transcript_state(const char* transcript_label, uint8_t* out203);
 int bph_r1cs_replay_challenges(int curve, const char* transcript_label, const uint8_t* proof, const uint8_t* comms_xy, size_t m, size_t lg,
                                uint8_t* out_be);
 
-/* `count` independent range proofs (m x `bits`-bit values each) proved in LOCK-STEP on one context (bpgpu_pbatch_*): one
- * device call per prover stage and per IPP round for a whole slab of proofs, the transcripts on `nthreads` host threads
- * (0 = all cores) in between.  Same arguments and same bytes as bph_range_prove_many (proof i uses seed + i); G and H get
- * window tables on first use.  For small circuits proved in bulk, where a proof of its own is bound by launch latency. */
+/* `count` independent range proofs (m x `bits`-bit values each) proved in LOCK-STEP on one context (bpgpu_pbatch_*): every
+ * prover stage and every IPP round is one device call for a whole slab of proofs.  Same arguments and same bytes as
+ * bph_range_prove_many (proof i uses seed + i); G and H get window tables on first use.  bph_range_prove_batch_mode selects
+ * where the transcripts run:
+ *   mode 0  on the device (default; what bph_range_prove_batch does; `nthreads` unused): bpgpu_pbatch_prove_range -- values
+ *           and blinding keys go up, finished proof records come down, nothing in between;
+ *   mode 1  on `nthreads` host threads (0 = all cores) between the device stages, as the reference's design has it. */
 int bph_range_prove_batch(bpgpu_ctx* ctx, const char* transcript_label, const uint8_t* g_xy, const uint8_t* h_xy, bpgpu_points* G,
                           bpgpu_points* H, const uint64_t* values, size_t count, size_t m, size_t bits, int rng_mode, uint64_t seed,
                           size_t nthreads, uint8_t* proofs, size_t proof_stride, uint8_t* comms_xy);
+int bph_range_prove_batch_mode(bpgpu_ctx* ctx, const char* transcript_label, const uint8_t* g_xy, const uint8_t* h_xy, bpgpu_points* G,
+                               bpgpu_points* H, const uint64_t* values, size_t count, size_t m, size_t bits, int rng_mode, uint64_t seed,
+                               int mode, size_t nthreads, uint8_t* proofs, size_t proof_stride, uint8_t* comms_xy);
 
 /* ---- a TWO-PHASE circuit: k-shuffle ({y} is a permutation of {x}) over 2k committed values, x[0] range-checked to `bits`
  * bits in the first phase (0 = none).  The gadget is the example of the reference's ConstraintSystem documentation

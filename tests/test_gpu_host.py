@@ -277,11 +277,12 @@ def test_lock_step_batch_prover_equals_single_proofs(which, m, bits, count, bp, 
     gx, hx = ctx.g1_from_msg_hash(b"g"), ctx.g1_from_msg_hash(b"h")
     values = [(0x9E3779B97F4A7C15 * (i + 1)) % (1 << bits) for i in range(count * m)]
     ref_p, stride, ref_c = bp.range_prove_many([ctx], b"Batch", gx, hx, dG, dH, values, m, bits, seed=300)
-    got_p, stride2, got_c = bp.range_prove_batch(ctx, b"Batch", gx, hx, dG, dH, values, m, bits, seed=300, nthreads=3)
-    assert stride2 == stride
-    assert got_c == ref_c
-    for i in range(count):
-        assert got_p[i * stride:(i + 1) * stride] == ref_p[i * stride:(i + 1) * stride], i
+    for mode in (0, 1):                       # transcripts on the device / on host threads
+        got_p, stride2, got_c = bp.range_prove_batch(ctx, b"Batch", gx, hx, dG, dH, values, m, bits, seed=300, nthreads=3, mode=mode)
+        assert stride2 == stride
+        assert got_c == ref_c, mode
+        for i in range(count):
+            assert got_p[i * stride:(i + 1) * stride] == ref_p[i * stride:(i + 1) * stride], (mode, i)
     assert bp.range_verify_batch(ctx, b"Batch", gx, hx, dG, dH, count, m, bits, got_p, stride, got_c) == [0] * count
     # OS-entropy blindings: proofs differ from run to run and verify
     p1, _, c1 = bp.range_prove_batch(ctx, b"Batch", gx, hx, dG, dH, values, m, bits)
@@ -299,8 +300,30 @@ def test_lock_step_batch_prover_two_drivers(bp, ctx_bls):
     values = [(37 * i + 11) % 256 for i in range(count)]
     ctxs = [ctx] + [bp.Context(bp.BLS12_381, 0) for _ in range(3)]
     ref_p, stride, ref_c = bp.range_prove_many(ctxs, b"Batch2", gx, hx, dG, dH, values, m, bits, seed=9000)
-    got_p, _, got_c = bp.range_prove_batch(ctx, b"Batch2", gx, hx, dG, dH, values, m, bits, seed=9000)
-    assert got_c == ref_c and got_p == ref_p
+    for mode in (0, 1):
+        got_p, _, got_c = bp.range_prove_batch(ctx, b"Batch2", gx, hx, dG, dH, values, m, bits, seed=9000, mode=mode)
+        assert got_c == ref_c and got_p == ref_p, mode
     assert bp.range_verify_batch(ctx, b"Batch2", gx, hx, dG, dH, count, m, bits, got_p, stride, got_c) == [0] * count
+    for c in ctxs[1:]:
+        c.close()
+
+
+@pytest.mark.parametrize("which", ["bls", "bn"])
+def test_device_transcript_batch_prover_warp_rows(which, bp, ctx_bls, ctx_bn):
+    """1100 proofs of 32 multipliers: the slab is large enough for the one-warp-per-row table sums (>= 2048 rows of >= 32
+    terms) in the A_I / A_O / S stage and in every IPP round; records byte-identical to single proofs, in both modes"""
+    ctx = ctx_bls if which == "bls" else ctx_bn
+    m, bits, count = 1, 32, 1100
+    dG, dH = ctx.get_generators("G", 32), ctx.get_generators("H", 32)
+    gx, hx = ctx.g1_from_msg_hash(b"g"), ctx.g1_from_msg_hash(b"h")
+    values = [(0x9E3779B97F4A7C15 * (i + 3)) % (1 << bits) for i in range(count)]
+    ctxs = [ctx] + [bp.Context(ctx.curve, 0) for _ in range(3)]
+    ref_p, stride, ref_c = bp.range_prove_many(ctxs, b"Warp", gx, hx, dG, dH, values, m, bits, seed=77000)
+    for mode in (0, 1):
+        got_p, _, got_c = bp.range_prove_batch(ctx, b"Warp", gx, hx, dG, dH, values, m, bits, seed=77000, mode=mode)
+        assert got_c == ref_c, mode
+        bad = [i for i in range(count) if got_p[i * stride:(i + 1) * stride] != ref_p[i * stride:(i + 1) * stride]]
+        assert not bad, (mode, bad[:5])
+    assert bp.range_verify_batch(ctx, b"Warp", gx, hx, dG, dH, count, m, bits, got_p, stride, got_c) == [0] * count
     for c in ctxs[1:]:
         c.close()

@@ -11,6 +11,7 @@ m = int(sys.argv[2]) if len(sys.argv) > 2 else 1
 bits = int(sys.argv[3]) if len(sys.argv) > 3 else 64
 curve = bp.BN254 if len(sys.argv) > 4 and sys.argv[4] == "bn" else bp.BLS12_381
 reps = int(sys.argv[5]) if len(sys.argv) > 5 else 3
+mode = int(sys.argv[6]) if len(sys.argv) > 6 else 0
 ctx = bp.Context(curve, 0)
 n = m * bits
 G, H = ctx.get_generators("G", n, precompute=True), ctx.get_generators("H", n, precompute=True)
@@ -18,8 +19,8 @@ gx, hx = ctx.g1_from_msg_hash(b"g"), ctx.g1_from_msg_hash(b"h")
 vals = [(0x9E3779B97F4A7C15 * (i + 1)) % (1 << min(bits, 63)) for i in range(count * m)]
 for rep in range(reps):
     t0 = time.perf_counter()
-    proofs, stride, comms = bp.range_prove_batch(ctx, b"bench", gx, hx, G, H, vals, m, bits)
+    proofs, stride, comms = bp.range_prove_batch(ctx, b"bench", gx, hx, G, H, vals, m, bits, mode=mode)
     dt = time.perf_counter() - t0
-    print(f"prove_batch rep {rep}: {count / dt:.0f} proofs/s ({dt * 1e3:.1f} ms)", flush=True)
+    print(f"prove_batch mode {mode} rep {rep}: {count / dt:.0f} proofs/s ({dt * 1e3:.1f} ms)", flush=True)
 v = bp.range_verify_batch(ctx, b"bench", gx, hx, G, H, count, m, bits, proofs, stride, comms)
 assert v == [0] * count
