@@ -99,7 +99,10 @@ int batch_identity_launch(bpgpu_ctx* ctx, const FixedRuns& runs, uint32_t F, siz
   static const bool prof = getenv("BPGPU_PROFILE") != nullptr;
   cudaEvent_t ev[3];
   if (prof) { for (auto& e : ev) cudaEventCreate(&e); cudaEventRecord(ev[0], ctx->stream); }
-  k_batch_fixed<Curve><<<(unsigned)cnt, BATCH_FIXED_THREADS, 0, ctx->stream>>>(runs, F, (const Fr*)d_fs, 0, d_sum);
+  if (cnt >= 2048 && F * 8 >= 256)          // thousands of rows: one warp per row (batchsum.cuh)
+    k_batch_fixed_warp<Curve><<<(unsigned)((cnt + 3) / 4), 128, 0, ctx->stream>>>(runs, F, (uint32_t)cnt, (const Fr*)d_fs, 0, d_sum);
+  else
+    k_batch_fixed<Curve><<<(unsigned)cnt, BATCH_FIXED_THREADS, 0, ctx->stream>>>(runs, F, (const Fr*)d_fs, 0, d_sum);
   if (prof) cudaEventRecord(ev[1], ctx->stream);
   if (vn) {
     const size_t np = cnt * vn, nw = cnt * VAR_WINDOWS;

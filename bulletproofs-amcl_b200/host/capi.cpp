@@ -397,13 +397,25 @@ int verify_batch_device_t(bpgpu_ctx* ctx, const char* label, const uint8_t* g_xy
   t0.r1cs_domain_sep();                                   // Verifier::new (verifier.rs:97-108)
   Rng<C> os;                                              // one key per call; proof i takes draw i (verifier.rs:392)
   if (!os.ok()) { bpgpu_circuit_free(circ); return BPH_E_ENTROPY; }
-  if (mode == 0) {
-    uint8_t state0[203];
-    t0.export_state(state0);
-    rc = bpgpu_r1cs_verify_batch(ctx, circ, G, H, g_xy, h_xy, count, proofs, stride, comms_xy, state0, nullptr, os.key(), os.key_len(), verdicts);
-  } else {
-    const size_t nch = 5 + lg;
-    std::vector<uint8_t> chal(count * nch * mb);
+  if (bpgpu_points_len(G) >= N && bpgpu_points_len(H) >= N &&          // tables built once, before the drivers share them
+      ((rc = bpgpu_points_precompute(ctx, G)) || (rc = bpgpu_points_precompute(ctx, H)))) { bpgpu_circuit_free(circ); return rc; }
+  // Two slabs in flight on two contexts (the second one cached in the first, bpgpu_ctx_aux): the latency-bound kernels of a
+  // slab (per-proof transcripts, the 252-doubling Horner chains) run under the table sums of the other.  Every slab call
+  // gets its own key for the verifiers' random scalars (key || slab index).
+  const size_t SLABV = 4096;
+  const size_t nslab = (count + SLABV - 1) / SLABV;
+  size_t maxdrv = nslab >= 8 ? 4 : 2;
+  if (const char* e = getenv("BPH_VB_DRIVERS")) maxdrv = (size_t)atol(e) >= 1 && (size_t)atol(e) <= 4 ? (size_t)atol(e) : maxdrv;   // tuning runs
+  const size_t ndrv = nslab < maxdrv ? nslab : maxdrv;
+  bpgpu_ctx* dctxs[4] = {ctx, nullptr, nullptr, nullptr};
+  for (size_t k = 1; k < ndrv; k++)
+    if ((rc = bpgpu_ctx_aux(dctxs[k - 1], &dctxs[k]))) { bpgpu_circuit_free(circ); return rc; }
+  uint8_t state0[203];
+  t0.export_state(state0);
+  std::vector<uint8_t> chal;
+  const size_t nch = 5 + lg;
+  if (mode != 0) {
+    chal.resize(count * nch * mb);
     if (nthreads == 0) nthreads = std::thread::hardware_concurrency();
     if (nthreads == 0) nthreads = 1;
     if (nthreads > count) nthreads = count;
@@ -422,8 +434,29 @@ int verify_batch_device_t(bpgpu_ctx* ctx, const char* label, const uint8_t* g_xy
     worker();
     for (auto& x : th) x.join();
     tr.mark("host transcripts");
-    rc = bpgpu_r1cs_verify_batch(ctx, circ, G, H, g_xy, h_xy, count, proofs, stride, comms_xy, nullptr, chal.data(), os.key(), os.key_len(), verdicts);
   }
+  std::atomic<int> err{0};
+  auto driver = [&](size_t k) {
+    for (size_t sl = k; sl < nslab && !err.load(); sl += ndrv) {
+      const size_t lo = sl * SLABV, cnt = count - lo < SLABV ? count - lo : SLABV;
+      uint8_t key[56];
+      memcpy(key, os.key(), os.key_len());
+      key[os.key_len()] = (uint8_t)sl;
+      key[os.key_len() + 1] = (uint8_t)(sl >> 8);
+      const int r = bpgpu_r1cs_verify_batch(dctxs[k], circ, G, H, g_xy, h_xy, cnt, proofs + lo * stride, stride, comms_xy + lo * m * 2 * mb,
+                                            mode == 0 ? state0 : nullptr, mode == 0 ? nullptr : chal.data() + lo * nch * mb, key,
+                                            os.key_len() + 2, verdicts + lo);
+      secure_zero(key, sizeof key);
+      if (r) { int z = 0; err.compare_exchange_strong(z, r); }
+    }
+  };
+  {
+    std::vector<std::thread> others;
+    for (size_t k = 1; k < ndrv; k++) others.emplace_back(driver, k);
+    driver(0);
+    for (auto& t : others) t.join();
+  }
+  rc = err.load();
   tr.mark("device");
   bpgpu_circuit_free(circ);
   return rc;

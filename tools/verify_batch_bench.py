@@ -19,7 +19,8 @@ vals = [(0x9E3779B97F4A7C15 * (i + 1)) % (1 << min(bits, 63)) for i in range(cou
 t0 = time.perf_counter()
 proofs, stride, comms = bp.range_prove_batch(ctx, b"bench", gx, hx, G, H, vals, m, bits)
 print(f"prove_batch: {count / (time.perf_counter() - t0):.0f} proofs/s", flush=True)
-for mode in (0, 1, 2):
+modes = [int(x) for x in os.environ.get('VB_MODES', '0,1,2').split(',')]
+for mode in modes:
     for rep in range(3):
         t0 = time.perf_counter()
         v = bp.range_verify_batch(ctx, b"bench", gx, hx, G, H, count, m, bits, proofs, stride, comms, mode=mode)
