@@ -171,7 +171,7 @@ def proof_section(bp, ctx, local, rank, world, dist, torch, no_cpu=False):
     hthreads = max(1, ncpu // max(1, world))          # host threads of the batch calls: this rank's share of the cores
     out = {"contexts_per_gpu": nctx, "host_cpus": ncpu, "host_threads_per_rank": hthreads}
 
-    def run(curve, m, bits, count, tag, verify_reps=1, batch_call=False, cpu_base=0):
+    def run(curve, m, bits, count, tag, verify_reps=1, batch_call=False, cpu_base=0, weak=4096):
         ctxs = [bp.Context(curve, local) for _ in range(nctx)]
         c0 = ctxs[0]
         gx, hx = c0.g1_from_msg_hash(b"g"), c0.g1_from_msg_hash(b"h")
@@ -196,7 +196,8 @@ def proof_section(bp, ctx, local, rank, world, dist, torch, no_cpu=False):
             v = bp.range_verify_many(ctxs, b"bench", gx, hx, G, H, count, m, bits, proofs, stride, comms)
             ok = ok and v == [0] * count
         tv = time.perf_counter() - t0
-        tb = tpb = tb1 = None
+        tb = tpb = tb1 = twv = twp = None
+        weak_n = 0
         if batch_call:
             # the same statement proved in lock-step on ONE context (bph_range_prove_batch): every prover stage and IPP round
             # is one device call for the whole batch, the transcripts run on the host threads in between
@@ -208,6 +209,7 @@ def proof_section(bp, ctx, local, rank, world, dist, torch, no_cpu=False):
             t0 = time.perf_counter()
             bproofs, bstride, bcomms = bp.range_prove_batch(c0, b"bench", gx, hx, G, H, bvals, m, bits, nthreads=hthreads)
             tpb = time.perf_counter() - t0
+            vals_per_call = range(nb)
             v = bp.range_verify_batch(c0, b"bench", gx, hx, G, H, nb, m, bits, bproofs, bstride, bcomms, nthreads=hthreads)
             ok = ok and v == [0] * nb
         if batch_call:
@@ -224,20 +226,43 @@ def proof_section(bp, ctx, local, rank, world, dist, torch, no_cpu=False):
             tb = time.perf_counter() - t0
             ok = ok and v == [0] * (count * reps)
             # the same call with the transcripts replayed on this rank's host threads (mode 1) instead of on the device
+            bp.range_verify_batch(c0, b"bench", gx, hx, G, H, count * reps, m, bits, big_p, stride, big_c, nthreads=hthreads, mode=1)   # warm-up
             if dist is not None:
                 dist.barrier()
             t0 = time.perf_counter()
             v = bp.range_verify_batch(c0, b"bench", gx, hx, G, H, count * reps, m, bits, big_p, stride, big_c, nthreads=hthreads, mode=1)
             tb1 = time.perf_counter() - t0
             ok = ok and v == [0] * (count * reps)
+            # WEAK scaling of the batch calls: `weak` proofs on EVERY GPU (config 5's literal 4096 proofs split 8 ways leave 512
+            # per GPU, where the per-slab latency -- transcript threads, the 252-doubling Horner chains -- is all there is)
+            wreps = max(1, weak // len(vals_per_call))
+            wp, wc = bproofs[:len(vals_per_call) * bstride] * wreps, bcomms[:len(vals_per_call) * m * 2 * c0.modbytes] * wreps
+            wn = len(vals_per_call) * wreps
+            bp.range_verify_batch(c0, b"bench", gx, hx, G, H, wn, m, bits, wp, bstride, wc)
+            if dist is not None:
+                dist.barrier()
+            t0 = time.perf_counter()
+            v = bp.range_verify_batch(c0, b"bench", gx, hx, G, H, wn, m, bits, wp, bstride, wc)
+            twv = time.perf_counter() - t0
+            ok = ok and v == [0] * wn
+            wvals = [int(x) for x in rng.integers(0, 1 << 63, size=wn * m, dtype=np.uint64)]
+            bp.range_prove_batch(c0, b"bench", gx, hx, G, H, wvals, m, bits)
+            if dist is not None:
+                dist.barrier()
+            t0 = time.perf_counter()
+            bp.range_prove_batch(c0, b"bench", gx, hx, G, H, wvals, m, bits)
+            twp = time.perf_counter() - t0
+            weak_n = wn
         if dist is not None:
             # the exchange step of the sharded batch verification: verdict bytes of every rank, all-gathered
             t = torch.tensor([1 if ok else 0] * count, dtype=torch.uint8, device="cuda")
             allv = torch.empty(world * count, dtype=torch.uint8, device="cuda")
             dist.all_gather_into_tensor(allv, t)
             ok = bool(allv.min().item() == 1)
-            tt = torch.tensor([tp, tv, tb or 0.0, tpb or 0.0, tb1 or 0.0], device="cuda", dtype=torch.float64)
+            tt = torch.tensor([tp, tv, tb or 0.0, tpb or 0.0, tb1 or 0.0, twv or 0.0, twp or 0.0], device="cuda", dtype=torch.float64)
             dist.all_reduce(tt, op=dist.ReduceOp.MAX)
+            twv = float(tt[5].item()) if twv is not None else None
+            twp = float(tt[6].item()) if twp is not None else None
             tp, tv = float(tt[0].item()), float(tt[1].item())
             tb = float(tt[2].item()) if tb is not None else None
             tpb = float(tt[3].item()) if tpb is not None else None
@@ -252,6 +277,9 @@ def proof_section(bp, ctx, local, rank, world, dist, torch, no_cpu=False):
             out[tag]["verify_batch_call"] = "bph_range_verify_batch: transcripts, per-proof scalars and MSMs on the device; host uploads bytes"
         if tb1 is not None:
             out[tag]["verify_batch_host_transcripts_per_s"] = count * world * verify_reps / tb1
+        if twv is not None:
+            out[tag]["weak_scaling_batch"] = {"proofs_per_gpu": weak_n, "verify_batch_per_s": weak_n * world / twv,
+                                              "prove_batch_per_s": weak_n * world / twp}
         if tpb is not None:
             out[tag]["prove_batch_call_per_s"] = count * world * verify_reps / tpb
         if cpu_base and rank == 0 and world == 1:
@@ -276,7 +304,7 @@ def proof_section(bp, ctx, local, rank, world, dist, torch, no_cpu=False):
         batch_call=True, cpu_base=0 if no_cpu else 4)
     # config 2: 16 x 64-bit values in one constraint system, 1024 generators
     run(bp.BLS12_381, 16, 64, max(nctx, 64 // world), "range64x16_bls12_381_n1024", verify_reps=4, batch_call=True,
-        cpu_base=0 if no_cpu else 1)
+        cpu_base=0 if no_cpu else 1, weak=1024)
     # config 3: 2^14 multipliers on BN254 (256 x 64-bit values)
     run(bp.BN254, 256, 64, max(nctx, 16 // world), "range64x256_bn254_n16384", cpu_base=0 if no_cpu else 1)
     return out

@@ -7,7 +7,7 @@ configs = [{}] + [json.loads(a) for a in sys.argv[2:]]
 for cfg in configs:
     env = dict(os.environ)
     env.update({k: str(v) for k, v in cfg.items()})
-    r = subprocess.run([sys.executable, os.path.join(ROOT, "bench.py"), "--steps", "4", "--warmup", "2", "--no-proofs", "--no-cpu-baseline", "--lg", lg],
+    r = subprocess.run([sys.executable, os.path.join(ROOT, "bench.py"), "--steps", "4", "--warmup", "2", "--no-proofs", "--no-cpu-baseline", "--no-sweep", "--lg", lg],
                        capture_output=True, text=True, env=env)
     try:
         d = json.loads(r.stdout.strip().splitlines()[-1])
