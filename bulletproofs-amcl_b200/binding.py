@@ -27,6 +27,7 @@ SYMBOLS = [
     ("bpgpu_ctx_device", _INT, [_VP]),
     ("bpgpu_ctx_launches", _c.c_uint64, [_VP]),
     ("bpgpu_ctx_set_profile", _INT, [_VP, _INT]),
+    ("bpgpu_ctx_set_fixed_schedule", _INT, [_VP, _INT]),
     ("bpgpu_msm_stage_ms", _INT, [_VP, _c.POINTER(_c.c_double), _INT]),
     ("bpgpu_host_alloc", _VP, [_SZ]),
     ("bpgpu_host_free", None, [_VP]),
@@ -91,6 +92,7 @@ SYMBOLS = [
     ("bpgpu_r1cs_prover_polys", _INT, [_VP, _SZ, _VP, _VP, _VP, _VP, _VP, _VP, _VP] + [_c.POINTER(_VP)] * 4),
     ("bpgpu_r1cs_prover_eval", _INT, [_VP, _SZ, _SZ, _SZ] + [_VP] * 6 + [_VP, _VP, _VP] + [_c.POINTER(_VP)] * 4),
     ("bpgpu_r1cs_verifier_scalars", _INT, [_VP, _SZ, _SZ, _SZ] + [_VP] * 4 + [_VP] * 5 + [_c.POINTER(_VP), _VP]),
+    ("bpgpu_mimc_witness", _INT, [_VP, _VP, _VP, _SZ, _VP, _SZ] + [_c.POINTER(_VP)] * 4),
     ("bpgpu_selftest_field", _INT, [_VP, _INT, _INT, _VP, _VP, _SZ, _VP]),
     ("bpgpu_selftest_group", _INT, [_VP, _INT, _VP, _VP, _VP, _SZ, _VP]),
     ("bpgpu_int_pipe_bench", _INT, [_VP, _INT, _INT, _c.POINTER(_c.c_double), _c.POINTER(_c.c_double)]),
@@ -121,6 +123,7 @@ SYMBOLS_HOST = [
     ("bph_bound_check_verify_batch", _INT, [_VP, _CS, _VP, _VP, _VP, _VP, _SZ, _U64, _U64, _SZ, _VP, _SZ, _VP, _INT, _SZ, _VP]),
     ("bph_range_circuit_csr", _INT, [_INT, _SZ, _SZ] + [_c.POINTER(_SZ)] * 4 + [_VP, _VP, _VP]),
     ("bph_bound_check_circuit_csr", _INT, [_INT, _U64, _U64, _SZ] + [_c.POINTER(_SZ)] * 4 + [_VP, _VP, _VP]),
+    ("bph_set_secret_fixed_schedule", None, [_INT]),
     ("bph_r1cs_transcript_state", None, [_CS, _VP]),
     ("bph_r1cs_replay_challenges", _INT, [_INT, _CS, _VP, _VP, _SZ, _SZ, _VP]),
     ("bph_msm_sharded", _INT, [_VP, _SZ, _VP, _VP, _VP, _VP]),
@@ -469,6 +472,10 @@ class Context:
 
     STAGES = ["digits", "scan", "scatter", "chunk_acc", "giant", "merge", "reduce_l1", "reduce_l2"]
 
+    def set_fixed_schedule(self, on):
+        """table-path MSMs of this context with a fixed trip count per term (secret scalars)"""
+        self._check(lib().bpgpu_ctx_set_fixed_schedule(self.handle, 1 if on else 0), "set_fixed_schedule")
+
     def set_profile(self, min_n):
         """record per-stage times of every MSM with at least min_n terms (0 / False = off)"""
         self._check(lib().bpgpu_ctx_set_profile(self.handle, int(min_n)), "set_profile")
@@ -696,6 +703,18 @@ class Context:
                                                       _buf(x_be), _buf(a_be), _buf(b_be), _buf(u_be), ctypes.byref(h), delta),
                     "r1cs_verifier_scalars")
         return DeviceScalars(self, h), delta.raw
+
+    def mimc_witness(self, xl, xr, constants, rounds, count=None, with_multipliers=True):
+        """batched mimc(xl, xr, constants, rounds) -> (image, a_L, a_R, a_O) device vectors (a_* None without multipliers)"""
+        count = len(xl) if count is None else count
+        hs = [ctypes.c_void_p() for _ in range(4)]
+        refs = [ctypes.byref(h) for h in hs]
+        if not with_multipliers:
+            refs[1:] = [None, None, None]
+        self._check(lib().bpgpu_mimc_witness(self.handle, xl.handle, xr.handle, count, constants.handle, rounds, *refs), "mimc_witness")
+        out = [DeviceScalars(self, hs[0])]
+        out += [DeviceScalars(self, h) for h in hs[1:]] if with_multipliers else [None, None, None]
+        return out
 
     # ---- host layer (include/bphost.h): the reference's API end to end
     def get_generators(self, prefix, n, precompute=False):

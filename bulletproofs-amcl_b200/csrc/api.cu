@@ -474,6 +474,12 @@ int bpgpu_ctx_curve(const bpgpu_ctx* c) { return c ? c->curve : BPGPU_E_ARG; }
 int bpgpu_ctx_device(const bpgpu_ctx* c) { return c ? c->device : -1; }
 uint64_t bpgpu_ctx_launches(const bpgpu_ctx* c) { return c ? c->launches : 0; }
 
+int bpgpu_ctx_set_fixed_schedule(bpgpu_ctx* c, int on) {
+  if (!c) return BPGPU_E_ARG;
+  c->fixed_schedule = on != 0;
+  return BPGPU_OK;
+}
+
 int bpgpu_ctx_set_profile(bpgpu_ctx* c, int on) {
   if (!c) return BPGPU_E_ARG;
   c->profile = on;

@@ -60,6 +60,7 @@ struct bpgpu_ctx {
   bool blocking_sync = false;
   cudaEvent_t sync_event = nullptr;
   uint64_t launches = 0;
+  bool fixed_schedule = false;    // table sums with a fixed trip count per term (secret scalars): bpgpu_ctx_set_fixed_schedule
   // MSM scratch
   bp::Scratch msm_a, msm_b, msm_c, msm_d, msm_e, io_dev, io_dev2;
   bp::Scratch fr_tmp, fr_out, fr_args, fr_pow, fr_pow2, ipp_pts, ipp_scl, parts_pts, parts_scl, tbl_part;

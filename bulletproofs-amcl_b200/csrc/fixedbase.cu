@@ -113,7 +113,13 @@ struct TableSegs {
 // items, then the block tree leaves one XYZZ per block.  The next table entry is requested before the current one is
 // added: entries of a multi-GB table set are DRAM misses.
 static const int TS_THREADS = 64;
-template <class Curve>
+// FIXED = the fixed-schedule variant for SECRET scalars (bpgpu_ctx_set_fixed_schedule; the reference commits to the witness
+// with inner_product_const_time, prover.rs:347-362): every (term, limb) item performs exactly 4 table loads and 4 mixed
+// additions whatever the digits are -- a zero digit loads entry 1 and discards the sum by a lane-wise select; zero limbs and
+// zero scalars are not skipped.  What still depends on the scalars: the table ADDRESSES (one entry is fetched per digit, as
+// AMCL's windowed multiplication selects one -- but a GPU fetch is not a masked scan) and the first addition into an empty
+// accumulator.  See DESIGN.md "secret scalars".
+template <class Curve, bool FIXED>
 __global__ void __launch_bounds__(TS_THREADS) k_table_sum(TableSegs segs, XYZZ<typename Curve::Fq>* __restrict__ partial) {
   using Fq = typename Curve::Fq;
   using Fr = typename Curve::Fr;
@@ -129,11 +135,22 @@ __global__ void __launch_bounds__(TS_THREADS) k_table_sum(TableSegs segs, XYZZ<t
     while (sg < last && p >= segs.start[sg + 1]) sg++;
     const uint32_t idx = p - segs.start[sg];
     uint32_t limb;
-    if (segs.mont[sg]) { Fr sc = load_vec((const Fr*)segs.scal[sg] + idx); limb = sc.is_zero() ? 0u : sc.from_mont().v[j]; }
+    if (segs.mont[sg]) { Fr sc = load_vec((const Fr*)segs.scal[sg] + idx); limb = (!FIXED && sc.is_zero()) ? 0u : sc.from_mont().v[j]; }
     else limb = ((const Fr*)segs.scal[sg])[idx].v[j];
-    if (!limb) continue;
+    if (!FIXED && !limb) continue;
     const uint32_t row = segs.rows[sg] ? segs.rows[sg][idx] : idx;
     const Affine<Fq>* tb = (const Affine<Fq>*)segs.table[sg] + ((size_t)row * TBL_WINDOWS + TBL_PER_LIMB * j) * TBL_DIGITS;
+    if (FIXED) {
+#pragma unroll 1
+      for (int k = 0; k < TBL_PER_LIMB; k++) {
+        const uint32_t dk = (limb >> (TBL_BITS * k)) & (uint32_t)TBL_DIGITS;
+        const Affine<Fq> e = load_vec_ro(tb + k * TBL_DIGITS + (dk ? dk - 1 : 0));
+        XYZZ<Fq> t = acc;
+        t.madd(e);
+        acc = select(dk != 0, t, acc);
+      }
+      continue;
+    }
     uint32_t d = limb & (uint32_t)TBL_DIGITS;
     Affine<Fq> cur = d ? load_vec_ro(tb + (d - 1)) : Affine<Fq>::inf();
 #pragma unroll 1
@@ -309,15 +326,19 @@ int table_sum_run(bpgpu_ctx* ctx, const TableSeg* segs, int nsegs, int ngroups, 
       cudaEventDestroy(ev[0]); cudaEventDestroy(ev[1]);
     }
   } prof_end{prof, ev, ctx->stream, maxtotal, blocks, ngroups};
+  auto launch = [&](dim3 grid, XYZZ<Fq>* dst) {
+    if (ctx->fixed_schedule) k_table_sum<Curve, true><<<grid, bs, 0, ctx->stream>>>(ts, dst);
+    else k_table_sum<Curve, false><<<grid, bs, 0, ctx->stream>>>(ts, dst);
+  };
   if (blocks == 1) {
-    k_table_sum<Curve><<<dim3(1, ngroups), bs, 0, ctx->stream>>>(ts, out);
+    launch(dim3(1, ngroups), out);
     ctx->launches += 1;
   } else if (host_partials && blocks * ngroups <= (uint32_t)TBL_HOST_PARTIALS) {
-    k_table_sum<Curve><<<dim3(blocks, ngroups), bs, 0, ctx->stream>>>(ts, out + TBL_MAX_GROUPS);
+    launch(dim3(blocks, ngroups), out + TBL_MAX_GROUPS);
     ctx->launches += 1;
     *host_partials = (int)blocks;                       // group g: out[TBL_MAX_GROUPS + g * blocks + b], b < blocks
   } else {
-    k_table_sum<Curve><<<dim3(blocks, ngroups), bs, 0, ctx->stream>>>(ts, out + TBL_MAX_GROUPS);
+    launch(dim3(blocks, ngroups), out + TBL_MAX_GROUPS);
     k_table_sum_final<Fq><<<ngroups, 256, 0, ctx->stream>>>(out + TBL_MAX_GROUPS, blocks, out);
     ctx->launches += 2;
   }

@@ -10,6 +10,7 @@
 //   k_vb_scalars    : one block per proof: the circuit's CSR times the powers of z, s, y^-i, g/h scalars, delta, head
 //   batch.cu        : the 2N+2 fixed terms from window tables, the proof's own points by Straus, verdict byte
 // and one verdict per proof returns.  Nothing is merged across proofs (the reference has no batch API).
+#include <stdlib.h>
 #include <string.h>
 
 #include <vector>
@@ -114,6 +115,12 @@ __global__ void __launch_bounds__(128) k_circuit_flatten(const __grid_constant__
   store_vec(out + row, csr_row_eval(c, row, ztab.t));
 }
 
+// proofs per group of launches (bounds the scratch: 15 XYZZ multiples per proof point); BPGPU_VB_SLAB overrides (tuning runs)
+static size_t verify_slab() {
+  static const size_t v = getenv("BPGPU_VB_SLAB") && atol(getenv("BPGPU_VB_SLAB")) > 0 ? (size_t)atol(getenv("BPGPU_VB_SLAB")) : 4096;
+  return v;
+}
+
 template <class Curve>
 static int verify_batch_t(bpgpu_ctx* ctx, const bpgpu_circuit* circ, const FixedRuns& runs, size_t count, const uint8_t* proofs, size_t stride,
                           const uint8_t* comms_xy, const uint8_t* state0, const uint8_t* chal_be, const uint8_t* key, size_t klen,
@@ -127,7 +134,7 @@ static int verify_batch_t(bpgpu_ctx* ctx, const bpgpu_circuit* circ, const Fixed
   while (N < c.n) { N <<= 1; lg++; }
   const uint32_t F = 2 * N + 2, vn = 6 + c.m + 5 + 2 * lg, hl = vb_hdr_len(lg);
   const uint32_t plen = PL::len(lg), nch = VB_CH_FIXED + lg;
-  const size_t SLAB = 4096;
+  const size_t SLAB = verify_slab();
   const size_t slab = count < SLAB ? count : SLAB;
   int rc;
   const BatchScratch L = batch_scratch_layout<Curve>(slab, F, vn);
@@ -299,7 +306,7 @@ int bpgpu_r1cs_verify_batch_terms(bpgpu_ctx* ctx, const bpgpu_circuit* circuit, 
                                   const uint8_t* h_xy, size_t count, const uint8_t* proofs, size_t proof_stride, const uint8_t* comms_xy,
                                   const uint8_t* transcript_state, const uint8_t* challenges_be, const uint8_t* rnd_key, size_t rnd_key_len,
                                   int32_t* verdicts, uint8_t* fixed_scalars_be, uint8_t* var_scalars_be) {
-  if (!fixed_scalars_be || !var_scalars_be || count > 4096) return BPGPU_E_ARG;
+  if (!fixed_scalars_be || !var_scalars_be || count > 4096 || verify_slab() < count) return BPGPU_E_ARG;
   return verify_batch_entry(ctx, circuit, G, H, g_xy, h_xy, count, proofs, proof_stride, comms_xy, transcript_state, challenges_be, rnd_key,
                             rnd_key_len, verdicts, fixed_scalars_be, var_scalars_be);
 }

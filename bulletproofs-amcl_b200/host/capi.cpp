@@ -402,7 +402,7 @@ int verify_batch_device_t(bpgpu_ctx* ctx, const char* label, const uint8_t* g_xy
   // Two slabs in flight on two contexts (the second one cached in the first, bpgpu_ctx_aux): the latency-bound kernels of a
   // slab (per-proof transcripts, the 252-doubling Horner chains) run under the table sums of the other.  Every slab call
   // gets its own key for the verifiers' random scalars (key || slab index).
-  const size_t SLABV = 4096;
+  const size_t SLABV = getenv("BPGPU_VB_SLAB") && atol(getenv("BPGPU_VB_SLAB")) > 0 ? (size_t)atol(getenv("BPGPU_VB_SLAB")) : 4096;
   const size_t nslab = (count + SLABV - 1) / SLABV;
   size_t maxdrv = nslab >= 8 ? 4 : 2;
   if (const char* e = getenv("BPH_VB_DRIVERS")) maxdrv = (size_t)atol(e) >= 1 && (size_t)atol(e) <= 4 ? (size_t)atol(e) : maxdrv;   // tuning runs
@@ -918,6 +918,8 @@ int bph_r1cs_replay_challenges(int curve, const char* label, const uint8_t* proo
   else replay_challenges_host<Bn254>(t, proof, comms_xy, m, lg, (size_t)1 << lg, out_be);
   return BPGPU_OK;
 }
+
+void bph_set_secret_fixed_schedule(int on) { secret_fixed_schedule_flag().store(on ? 1 : 0); }
 
 void bph_r1cs_transcript_state(const char* label, uint8_t* out203) {
   Transcript t{std::string(label)};

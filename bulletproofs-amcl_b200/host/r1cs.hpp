@@ -4,6 +4,7 @@
 // include/bpgpu.h (commitment MSMs, l/r polynomial kernels, the nine inner products, IPP rounds, the single
 // verification MSM).
 #pragma once
+#include <atomic>
 #include <functional>
 #include <memory>
 #include <utility>
@@ -158,6 +159,14 @@ struct R1CSProof {
     return OK;
   }
 };
+
+// process-wide switch (bph_set_secret_fixed_schedule, or BPH_FIXED_SCHEDULE=1 in the environment): the prover's witness
+// commitments A_I, A_O, S run with bpgpu_ctx_set_fixed_schedule on
+inline std::atomic<int>& secret_fixed_schedule_flag() {
+  static std::atomic<int> f{getenv("BPH_FIXED_SCHEDULE") && atoi(getenv("BPH_FIXED_SCHEDULE")) ? 1 : 0};
+  return f;
+}
+inline bool secret_fixed_schedule() { return secret_fixed_schedule_flag().load(std::memory_order_relaxed) != 0; }
 
 inline size_t next_power_of_two(size_t n) { size_t p = 1; while (p < n) p <<= 1; return p; }   // usize::next_power_of_two (0 -> 1)
 
@@ -473,7 +482,11 @@ class Prover : public ConstraintSystem<C> {
                                part_dev(G, sL), part_dev(H, sR), part_h(sb)};    // S    (:361-362)
     const size_t counts[3] = {3, 2, 3};
     uint8_t out[3 * 2 * C::MODBYTES];
+    // the witness and its blindings are the prover's secrets: fixed-schedule table sums when the caller asked for them
+    // (secret_fixed_schedule(); the reference uses inner_product_const_time here, prover.rs:347-362)
+    if (secret_fixed_schedule()) bpgpu_ctx_set_fixed_schedule(ctx_, 1);
     int rc = bpgpu_msm_parts_batch(ctx_, parts, counts, 3, out);
+    if (secret_fixed_schedule()) bpgpu_ctx_set_fixed_schedule(ctx_, 0);
     if (rc) return rc;
     *A_I = G1<C>::from_xy(out);
     *A_O = G1<C>::from_xy(out + 2 * C::MODBYTES);

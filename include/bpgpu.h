@@ -65,6 +65,13 @@ int bpgpu_ctx_device(const bpgpu_ctx* ctx);
 /* number of kernels this ctx has launched so far (bench.py's gpu_launches) */
 uint64_t bpgpu_ctx_launches(const bpgpu_ctx* ctx);
 
+/* Secret scalars (the reference commits to the witness and its blindings with inner_product_const_time /
+ * commit_to_field_element_vectors, prover.rs:347-362): while this switch is on, every MSM of the ctx that runs on window
+ * tables (bpgpu_points_precompute) uses a FIXED schedule -- 32 table loads and 32 mixed additions per term whatever the
+ * scalar's digits are, zero digits and zero scalars included (their sums are discarded by a lane-wise select).  It does
+ * NOT make the fetched table addresses independent of the scalars (one entry per digit is read, not a masked scan of the
+ * row), and MSMs that take the bucket path (no tables) are variable time regardless: see DESIGN.md "secret scalars". */
+int bpgpu_ctx_set_fixed_schedule(bpgpu_ctx* ctx, int on);
 /* per-stage CUDA-event timing of the MSM pipeline on the ctx stream (roofline evidence for bench.py).
  * stages: 0 digits, 1 scan, 2 scatter, 3 chunk_acc, 4 giant, 5 merge, 6 reduce_l1, 7 reduce_l2.
  * set_profile(min_n > 0) records every MSM of at least min_n terms (0 = off); bpgpu_msm_stage_ms writes the average ms
@@ -314,6 +321,14 @@ int bpgpu_r1cs_verifier_scalars(bpgpu_ctx* ctx, size_t n, size_t n1, size_t padd
                                 const bpgpu_scalars* wR, const bpgpu_scalars* wO, const bpgpu_scalars* s,
                                 const uint8_t* y_be, const uint8_t* x_be, const uint8_t* a_be, const uint8_t* b_be,
                                 const uint8_t* u_be, bpgpu_scalars** gh_scalars, uint8_t* delta_be);
+
+/* ---- witness generation for the MiMC hash gadget (gadgets/helper_constraints/mimc.rs:10-29,53-77) ----
+ * `count` independent instances of mimc(xl, xr, constants, rounds): per round xl, xr := xr + (xl + c_i)^3, xl.
+ * image[i] = the hash of instance i; a_L / a_R / a_O (optional, all three or none) receive the multiplier assignments of
+ * enforce_mimc_2_inputs, instance-major, 2 * rounds multipliers each: (l, l, l^2) and (l^2, l, l^3) with l = xl + c_i --
+ * device-resident, ready for the commitment MSMs.  constants must hold at least `rounds` scalars (mimc.rs:18). */
+int bpgpu_mimc_witness(bpgpu_ctx* ctx, const bpgpu_scalars* xl, const bpgpu_scalars* xr, size_t count, const bpgpu_scalars* constants,
+                       size_t rounds, bpgpu_scalars** image, bpgpu_scalars** a_L, bpgpu_scalars** a_R, bpgpu_scalars** a_O);
 
 /* ---- self-test / measurement hooks (used by tests/ and bench.py; not part of the drop-in) ---- */
 /* field: 0 Fq, 1 Fr of the ctx curve; op: 0 mul 1 add 2 sub 3 inv 4 sqr; operands are canonical

@@ -116,6 +116,10 @@ int bph_range_circuit_csr(int curve, size_t m, size_t bits, size_t* n, size_t* m
                           uint32_t* ent_q, uint8_t* ent_coeff_be);
 int bph_bound_check_circuit_csr(int curve, uint64_t lower, uint64_t upper, size_t bits, size_t* n, size_t* m_out, size_t* q, size_t* nnz,
                                 uint32_t* row_start, uint32_t* ent_q, uint8_t* ent_coeff_be);
+/* process-wide: the prover's witness commitments A_I, A_O, S (prover.rs:347-362: inner_product_const_time in the
+ * reference) use fixed-schedule table sums (bpgpu_ctx_set_fixed_schedule) when the generators carry window tables.  Off by
+ * default (BPH_FIXED_SCHEDULE=1 in the environment turns it on); the proof bytes do not change. */
+void bph_set_secret_fixed_schedule(int on);
 /* exported Merlin state (203 bytes) after Transcript::new(label) + r1cs_domain_sep(): bpgpu_r1cs_verify_batch's transcript_state */
 void bph_r1cs_transcript_state(const char* transcript_label, uint8_t* out203);
 /* the challenges y, z, u, x, w, u_1..u_lg ((5 + lg) x MODBYTES, big endian) of one proof of a one-phase circuit with m

@@ -274,6 +274,10 @@ class Prover:
         Q = C.mul(self.g, w)
         G_factors = [1] * n1 + [u] * (n2 + pad)            # :552-556
         H_factors = [yi * g % r for yi, g in zip(exp_y_inv, G_factors)]   # :557-563
+        if getattr(self, "trace", None) is not None:       # test hook: the intermediate vectors of steps 8, 12, 15 (row a11)
+            self.trace.update(y=y, z=z, u=u, x=x, w=w, n=n, n1=n1, padded_n=padded_n, wL=wL, wR=wR, wO=wO, wV=wV, s_L=s_L1, s_R=s_R1,
+                              l1=l1, l2=l2, l3=l3, r0=r0, r1=r1, r3=r3, t=[t1, t2, t3, t4, t5, t6], l_vec=l_vec, r_vec=r_vec,
+                              G_factors=G_factors, H_factors=H_factors)
         ipp_proof = ipp_mod.create_ipp(C, T, Q, G_factors, H_factors, G[:padded_n], H[:padded_n], l_vec, r_vec)
         return R1CSProof(A_I1=A_I1, A_O1=A_O1, S1=S1, A_I2=A_I2, A_O2=A_O2, S2=S2, T_1=T_1, T_3=T_3, T_4=T_4,
                          T_5=T_5, T_6=T_6, t_x=t_x, t_x_blinding=t_x_blinding, e_blinding=e_blinding,
@@ -399,6 +403,9 @@ class Verifier:
         rx4 = rx3 * x % r
         rx5 = rx4 * x % r
         rx6 = rx5 * x % r
+        if getattr(self, "trace", None) is not None:       # test hook: steps 3, 5 (row a12)
+            self.trace.update(y=y, z=z, u=u, x=x, w=w, n=n, n1=n1, padded_n=padded_n, wL=wL, wR=wR, wO=wO, wV=wV, wc=wc, s=s, a=a, b=b,
+                              delta=delta, g_scalars=g_scalars, h_scalars=h_scalars)
         arg1 = [x, x2, x3, u * x % r, u * x2 % r, u * x3 % r]
         arg1 += [v * r_x2 % r for v in wV]                 # :416-418
         arg1 += [rx, rx3, rx4, rx5, rx6]
@@ -489,6 +496,30 @@ def shuffle_gadget(cs, xs, ys):
         ox, oy = chain(xs), chain(ys)
         cs.constrain(LC([(ox, 1), (oy, C.r - 1)]))
     cs.specify_randomized_constraints(cb)
+
+
+def mimc(C, xl, xr, constants, rounds):
+    """gadgets/helper_constraints/mimc.rs:10-29."""
+    assert len(constants) == rounds
+    r = C.r
+    for i in range(rounds):
+        tmp1 = (xl + constants[i]) % r
+        tmp2 = (tmp1 * tmp1 % r * tmp1 + xr) % r
+        xr, xl = xl, tmp2
+    return xl
+
+
+def enforce_mimc_2_inputs(cs, left, right, rounds, constants):
+    """gadgets/helper_constraints/mimc.rs:53-77 (left, right: LC); returns the LC of the image."""
+    C = cs.C
+    left_v, right_v = left, right
+    for j in range(rounds):
+        lpc = left_v.add(LC([(VAR_ONE, constants[j] % C.r)]), C)
+        l, _, l_sqr = cs.multiply(lpc, LC(list(lpc.terms)))
+        _, _, l_cube = cs.multiply(LC.of(l_sqr, C), LC.of(l, C))
+        tmp = LC.of(l_cube, C).add(right_v, C)
+        right_v, left_v = left_v, tmp
+    return left_v
 
 
 def make_rng(C, seed, tag=b"blind"):

@@ -260,3 +260,37 @@ def test_msm_config4_top_sizes(which, lg, ctx_bls, ctx_bn):
     tot = sum(k for k, b in zip(ks, bits.tolist()) if b) % C.r
     assert ctx.msm(dp, blk.tobytes()) == C.g1_xy_bytes(C.mul(G, tot))
     dp.free()
+
+
+@pytest.mark.parametrize("which", ["bls", "bn"])
+def test_fixed_schedule_table_sums_give_the_same_bytes(which, bp, ctx_bls, ctx_bn):
+    """bpgpu_ctx_set_fixed_schedule (secret scalars; the reference's inner_product_const_time, prover.rs:347-362): no digit or
+    scalar is skipped, results are the same group elements -- zero scalars, 0/1 witnesses, short and full scalars, and a
+    whole range proof with BPH's switch on."""
+    ctx = ctx_bls if which == "bls" else ctx_bn
+    C = curve_of(ctx)
+    n = 70
+    pts = rand_points(C, n, 5)
+    tab = ctx.upload_points(enc_points(C, pts)).precompute()
+    rnd = random.Random(4)
+    cases = [[0] * n, [rnd.randrange(2) for _ in range(n)], [rnd.randrange(256) for _ in range(n)], C.synth_scalars(6, n),
+             [0, 1, C.r - 1, 1 << 200] + [0] * (n - 4)]
+    ctx.set_fixed_schedule(True)
+    try:
+        for s in cases:
+            assert ctx.msm(tab, enc_scalars(C, s)) == C.g1_xy_bytes(C.msm(pts, s))
+            ds = ctx.upload_scalars(enc_scalars(C, s))
+            assert ctx.msm_device(tab, ds) == C.g1_xy_bytes(C.msm(pts, s))
+            ds.free()
+    finally:
+        ctx.set_fixed_schedule(False)
+    tab.free()
+    dG, dH = ctx.get_generators("G", 16, precompute=True), ctx.get_generators("H", 16, precompute=True)
+    gx, hx = ctx.g1_from_msg_hash(b"g"), ctx.g1_from_msg_hash(b"h")
+    ref, comms = ctx.range_prove(b"FS", gx, hx, dG, dH, [200, 7], 8, seed=3)
+    bp.lib().bph_set_secret_fixed_schedule(1)
+    try:
+        got, comms2 = ctx.range_prove(b"FS", gx, hx, dG, dH, [200, 7], 8, seed=3)
+    finally:
+        bp.lib().bph_set_secret_fixed_schedule(0)
+    assert got == ref and comms2 == comms
