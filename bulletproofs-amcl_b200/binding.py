@@ -93,6 +93,7 @@ SYMBOLS = [
     ("bpgpu_r1cs_prover_eval", _INT, [_VP, _SZ, _SZ, _SZ] + [_VP] * 6 + [_VP, _VP, _VP] + [_c.POINTER(_VP)] * 4),
     ("bpgpu_r1cs_verifier_scalars", _INT, [_VP, _SZ, _SZ, _SZ] + [_VP] * 4 + [_VP] * 5 + [_c.POINTER(_VP), _VP]),
     ("bpgpu_mimc_witness", _INT, [_VP, _VP, _VP, _SZ, _VP, _SZ] + [_c.POINTER(_VP)] * 4),
+    ("bpgpu_poseidon_permutation", _INT, [_VP, _VP, _SZ, _SZ, _SZ, _SZ, _SZ, _INT, _VP, _VP, _c.POINTER(_VP)]),
     ("bpgpu_selftest_field", _INT, [_VP, _INT, _INT, _VP, _VP, _SZ, _VP]),
     ("bpgpu_selftest_group", _INT, [_VP, _INT, _VP, _VP, _VP, _SZ, _VP]),
     ("bpgpu_int_pipe_bench", _INT, [_VP, _INT, _INT, _c.POINTER(_c.c_double), _c.POINTER(_c.c_double)]),
@@ -715,6 +716,12 @@ class Context:
         out = [DeviceScalars(self, hs[0])]
         out += [DeviceScalars(self, h) for h in hs[1:]] if with_multipliers else [None, None, None]
         return out
+
+    def poseidon_permutation(self, inputs, count, width, frb, pr, fre, sbox, round_keys, mds):
+        h = ctypes.c_void_p()
+        self._check(lib().bpgpu_poseidon_permutation(self.handle, inputs.handle, count, width, frb, pr, fre, sbox, round_keys.handle, mds.handle,
+                                                     ctypes.byref(h)), "poseidon_permutation")
+        return DeviceScalars(self, h)
 
     # ---- host layer (include/bphost.h): the reference's API end to end
     def get_generators(self, prefix, n, precompute=False):

@@ -1,4 +1,5 @@
-// Witness generation for the MiMC hash gadget, batched (the caller's step BEFORE the proving path).
+// Witness generation for the hash gadgets, batched (the caller's step BEFORE the proving path):
+// MiMC with its multiplier assignments, and the Poseidon permutation.
 //
 // /root/reference/src/r1cs/gadgets/helper_constraints/mimc.rs:10-29 `mimc(xl, xr, constants, rounds)`:
 //     per round  xl, xr := xr + (xl + c_i)^3, xl ;  the image is xl after the last round
@@ -36,9 +37,76 @@ __global__ void __launch_bounds__(128) k_mimc_witness(uint32_t count, uint32_t r
   store_vec(image + b, xl);
 }
 
+// /root/reference/src/r1cs/gadgets/helper_constraints/poseidon.rs:202-293 `Poseidon_permutation`: full rounds (round key +
+// S-box on every element), partial rounds (round keys on every element, S-box on the LAST one), full rounds; after each
+// S-box layer the linear layer new[i] = sum_j state[j] * MDS[j][i].  S-box (poseidon.rs:122-138): 0 cube, 1 inverse
+// (0 -> 0 as FieldElement::inverse), 2 quint.  Round keys and the MDS matrix are the caller's (the reference's tables are
+// parameters, not code); one thread per instance, the state (width <= 9) in registers / local memory.
+static const int POSEIDON_MAX_WIDTH = 9;
+template <class Fr>
+__device__ __forceinline__ Fr poseidon_sbox(const Fr& e, int sbox) {
+  if (sbox == 1) return e.inv();
+  const Fr sq = e.sqr();
+  if (sbox == 0) return sq * e;
+  return sq.sqr() * e;
+}
+template <class Curve>
+__global__ void __launch_bounds__(128) k_poseidon(uint32_t count, uint32_t width, uint32_t full_begin, uint32_t partial, uint32_t full_end, int sbox,
+                                                  const typename Curve::Fr* __restrict__ input, const typename Curve::Fr* __restrict__ keys,
+                                                  const typename Curve::Fr* __restrict__ mds, typename Curve::Fr* __restrict__ out) {
+  using Fr = typename Curve::Fr;
+  const uint32_t b = blockIdx.x * blockDim.x + threadIdx.x;
+  if (b >= count) return;
+  Fr st[POSEIDON_MAX_WIDTH], tmp[POSEIDON_MAX_WIDTH];
+  for (uint32_t i = 0; i < width; i++) st[i] = load_vec(input + (size_t)b * width + i);
+  uint32_t off = 0;
+  const uint32_t total = full_begin + partial + full_end;
+  for (uint32_t r = 0; r < total; r++) {
+    const bool full = r < full_begin || r >= full_begin + partial;
+    for (uint32_t i = 0; i < width; i++) {
+      st[i] = st[i] + load_vec(keys + off + i);
+      if (full || i == width - 1) st[i] = poseidon_sbox(st[i], sbox);
+    }
+    off += width;
+    for (uint32_t i = 0; i < width; i++) {
+      Fr acc = Fr::zero();
+      for (uint32_t j = 0; j < width; j++) acc = acc + st[j] * load_vec(mds + j * width + i);
+      tmp[i] = acc;
+    }
+    for (uint32_t i = 0; i < width; i++) st[i] = tmp[i];
+  }
+  for (uint32_t i = 0; i < width; i++) store_vec(out + (size_t)b * width + i, st[i]);
+}
+
 }  // namespace bp
 
 using namespace bp;
+
+extern "C" int bpgpu_poseidon_permutation(bpgpu_ctx* ctx, const bpgpu_scalars* input, size_t count, size_t width, size_t full_rounds_beginning,
+                                          size_t partial_rounds, size_t full_rounds_end, int sbox, const bpgpu_scalars* round_keys,
+                                          const bpgpu_scalars* mds, bpgpu_scalars** out) {
+  if (!ctx || !input || !round_keys || !mds || !out || sbox < 0 || sbox > 2 || count >= (1ull << 28)) return BPGPU_E_ARG;
+  if (width != 3 && width != 5 && width != 9) return BPGPU_E_ARG;                        // poseidon.rs:32-34
+  const size_t total = full_rounds_beginning + partial_rounds + full_rounds_end;
+  if (total >= (1u << 16)) return BPGPU_E_ARG;
+  if (input->n < count * width || round_keys->n < total * width || mds->n < width * width) return BPGPU_E_LEN;   // poseidon.rs:58-64,92-96
+  BP_CUDA_OK(cudaSetDevice(ctx->device));
+  int rc = bpgpu_scalars_alloc(ctx, count * width, out);
+  if (rc || count == 0) return rc;
+  const unsigned blocks = (unsigned)((count + 127) / 128);
+  if (ctx->curve == BPGPU_BLS12_381)
+    k_poseidon<Bls><<<blocks, 128, 0, ctx->stream>>>((uint32_t)count, (uint32_t)width, (uint32_t)full_rounds_beginning, (uint32_t)partial_rounds,
+                                                      (uint32_t)full_rounds_end, sbox, (const Bls::Fr*)input->d, (const Bls::Fr*)round_keys->d,
+                                                      (const Bls::Fr*)mds->d, (Bls::Fr*)(*out)->d);
+  else
+    k_poseidon<Bn><<<blocks, 128, 0, ctx->stream>>>((uint32_t)count, (uint32_t)width, (uint32_t)full_rounds_beginning, (uint32_t)partial_rounds,
+                                                     (uint32_t)full_rounds_end, sbox, (const Bn::Fr*)input->d, (const Bn::Fr*)round_keys->d,
+                                                     (const Bn::Fr*)mds->d, (Bn::Fr*)(*out)->d);
+  ctx->launches++;
+  rc = launch_check(ctx, "k_poseidon");
+  if (rc) { bpgpu_scalars_free(*out); *out = nullptr; }
+  return rc;
+}
 
 extern "C" int bpgpu_mimc_witness(bpgpu_ctx* ctx, const bpgpu_scalars* xl, const bpgpu_scalars* xr, size_t count, const bpgpu_scalars* constants,
                                   size_t rounds, bpgpu_scalars** image, bpgpu_scalars** a_L, bpgpu_scalars** a_R, bpgpu_scalars** a_O) {

@@ -330,6 +330,15 @@ int bpgpu_r1cs_verifier_scalars(bpgpu_ctx* ctx, size_t n, size_t n1, size_t padd
 int bpgpu_mimc_witness(bpgpu_ctx* ctx, const bpgpu_scalars* xl, const bpgpu_scalars* xr, size_t count, const bpgpu_scalars* constants,
                        size_t rounds, bpgpu_scalars** image, bpgpu_scalars** a_L, bpgpu_scalars** a_R, bpgpu_scalars** a_O);
 
+/* Poseidon_permutation (gadgets/helper_constraints/poseidon.rs:202-293) for `count` independent states of `width` (3, 5
+ * or 9) scalars: full_rounds_beginning full rounds, partial_rounds partial rounds (S-box on the last element only),
+ * full_rounds_end full rounds; round_keys = (total rounds) x width scalars consumed in order, mds = width x width row-major
+ * (new[i] = sum_j state[j] * mds[j][i]); sbox: 0 cube, 1 inverse, 2 quint (poseidon.rs:122-138).  The round keys and the
+ * matrix are the caller's parameters (the reference's tables: gadgets/poseidon_constants.rs).  out = count x width. */
+int bpgpu_poseidon_permutation(bpgpu_ctx* ctx, const bpgpu_scalars* input, size_t count, size_t width, size_t full_rounds_beginning,
+                               size_t partial_rounds, size_t full_rounds_end, int sbox, const bpgpu_scalars* round_keys,
+                               const bpgpu_scalars* mds, bpgpu_scalars** out);
+
 /* ---- self-test / measurement hooks (used by tests/ and bench.py; not part of the drop-in) ---- */
 /* field: 0 Fq, 1 Fr of the ctx curve; op: 0 mul 1 add 2 sub 3 inv 4 sqr; operands are canonical
  * big-endian MODBYTES values (converted to/from Montgomery form on the device). */

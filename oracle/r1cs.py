@@ -522,6 +522,28 @@ def enforce_mimc_2_inputs(cs, left, right, rounds, constants):
     return left_v
 
 
+def poseidon_permutation(C, inp, width, frb, pr, fre, round_keys, mds, sbox):
+    """gadgets/helper_constraints/poseidon.rs:202-293; sbox: "cube" | "inverse" | "quint" (:122-138); mds[j][i] as there."""
+    r = C.r
+    assert len(inp) == width
+
+    def sb(e):
+        if sbox == "inverse":
+            return C.fr_inv(e)
+        return pow(e, 3 if sbox == "cube" else 5, r)
+    st = [x % r for x in inp]
+    off = 0
+    for rd in range(frb + pr + fre):
+        full = rd < frb or rd >= frb + pr
+        for i in range(width):
+            st[i] = (st[i] + round_keys[off]) % r
+            off += 1
+            if full or i == width - 1:
+                st[i] = sb(st[i])
+        st = [sum(st[j] * mds[j][i] for j in range(width)) % r for i in range(width)]
+    return st
+
+
 def make_rng(C, seed, tag=b"blind"):
     """Deterministic blinding stream: SHAKE256(seed_le64 || tag || i_le64) mod r."""
     ctr = [0]

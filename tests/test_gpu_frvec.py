@@ -179,3 +179,27 @@ def test_mimc_witness_generation(which, ctx_bls, ctx_bn):
     assert img2.download() == img.download()
     with pytest.raises(Exception):
         ctx.mimc_witness(up(xl), up(xr), up(consts[:3]), rounds)
+
+
+@pytest.mark.parametrize("which", ["bls", "bn"])
+@pytest.mark.parametrize("width,sbox", [(3, 0), (5, 1), (9, 2), (3, 1)])
+def test_poseidon_permutation(which, width, sbox, ctx_bls, ctx_bn):
+    """Poseidon_permutation (poseidon.rs:202-293) batched on the device against the oracle's restatement: all three S-boxes,
+    the three widths, full and partial rounds, a zero state element under the inverse S-box (0 -> 0)"""
+    from oracle import r1cs as or1cs
+    ctx = ctx_bls if which == "bls" else ctx_bn
+    C = curve_of(ctx)
+    frb, pr, fre, count = 2, 5, 2, 9
+    keys = C.synth_scalars(21, (frb + pr + fre) * width, b"rk")
+    mds = [[C.synth_scalar(22, j * width + i, b"mds") for i in range(width)] for j in range(width)]
+    states = [[C.synth_scalar(23, b * width + i, b"in") for i in range(width)] for b in range(count)]
+    states[0] = [0] * width
+    states[1][width - 1] = (C.r - keys[width - 1]) % C.r            # the S-box input of the last element is 0 in round 1
+    up = lambda v: ctx.upload_scalars(enc_scalars(C, v))
+    out = ctx.poseidon_permutation(up([x for s in states for x in s]), count, width, frb, pr, fre, sbox, up(keys),
+                                   up([mds[j][i] for j in range(width) for i in range(width)]))
+    name = ["cube", "inverse", "quint"][sbox]
+    exp = [x for s in states for x in or1cs.poseidon_permutation(C, s, width, frb, pr, fre, keys, mds, name)]
+    assert dec_scalars(C, out.download()) == exp
+    with pytest.raises(Exception):
+        ctx.poseidon_permutation(up(states[0]), 1, 4, frb, pr, fre, sbox, up(keys), up([1] * 16))     # width 4: not supported
