@@ -44,11 +44,23 @@ __global__ void __launch_bounds__(64) k_batch_multiples(size_t total, const Affi
   }
 }
 
-// wsum[w * batch + b] = sum_i M[b][i][digit_w(s[b][i]) - 1]
+// BLS12-381 only: the scalars of the proofs' own points are split k = k1 + k2 * lambda (curves.cuh), k1 in limbs 0..3 and k2
+// in limbs 4..7 of the same slot, so that windows 0..31 are the 4-bit windows of k1 on P and windows 32..63 those of k2 on
+// phi(P) = (beta x, y): same number of window sums, HALF the doubling chain in k_batch_horner.
+template <class Curve>
+__global__ void __launch_bounds__(256) k_glv_split(size_t total, typename Curve::Fr* __restrict__ scal) {
+  const size_t t = (size_t)blockIdx.x * blockDim.x + threadIdx.x;
+  if (t >= total) return;
+  typename Curve::Fr k = load_vec(scal + t), o;
+  glv_bls_split(k.v, o.v);
+  store_vec(scal + t, o);
+}
+
+// wsum[w * batch + b] = sum_i M[b][i][digit_w(s[b][i]) - 1]   (glv: windows >= 32 read k2's digits and add phi of the multiple)
 template <class Curve>
 __global__ void __launch_bounds__(128) k_batch_windows(size_t batch, uint32_t vn, const typename Curve::Fr* __restrict__ scal,
                                                        const XYZZ<typename Curve::Fq>* __restrict__ mult,
-                                                       XYZZ<typename Curve::Fq>* __restrict__ wsum) {
+                                                       XYZZ<typename Curve::Fq>* __restrict__ wsum, int glv) {
   using Fq = typename Curve::Fq;
   using Fr = typename Curve::Fr;
   const size_t t = (size_t)blockIdx.x * blockDim.x + threadIdx.x;
@@ -57,11 +69,18 @@ __global__ void __launch_bounds__(128) k_batch_windows(size_t batch, uint32_t vn
   const uint32_t w = (uint32_t)(t - b * VAR_WINDOWS);
   const Fr* sc = scal + b * vn;
   const XYZZ<Fq>* M = mult + b * (size_t)vn * VAR_DIGITS;
+  const bool phi = glv && w >= VAR_WINDOWS / 2;
+  Fq beta = Fq::zero();
+  if (phi) beta = glv_beta<Curve>();
   XYZZ<Fq> acc = XYZZ<Fq>::inf();
 #pragma unroll 1
   for (uint32_t i = 0; i < vn; i++) {
     const uint32_t d = (sc[i].v[w >> 3] >> ((w & 7) * 4)) & 15u;
-    if (d) { XYZZ<Fq> q = load_vec(M + (size_t)i * VAR_DIGITS + (d - 1)); acc.add(q); }
+    if (d) {
+      XYZZ<Fq> q = load_vec(M + (size_t)i * VAR_DIGITS + (d - 1));
+      if (phi) q.x = Fq::mulc(q.x, beta);
+      acc.add(q);
+    }
   }
   store_vec(wsum + (size_t)w * batch + b, acc);
 }
@@ -69,18 +88,20 @@ __global__ void __launch_bounds__(128) k_batch_windows(size_t batch, uint32_t vn
 template <class Curve>
 __global__ void __launch_bounds__(32) k_batch_horner(size_t batch, uint32_t vn, const XYZZ<typename Curve::Fq>* __restrict__ wsum,
                                                      const XYZZ<typename Curve::Fq>* __restrict__ fixed_sum,
-                                                     uint8_t* __restrict__ is_identity) {
+                                                     uint8_t* __restrict__ is_identity, int glv) {
   using Fq = typename Curve::Fq;
   const size_t b = (size_t)blockIdx.x * blockDim.x + threadIdx.x;
   if (b >= batch) return;
   XYZZ<Fq> acc = XYZZ<Fq>::inf();
   if (vn) {
-    acc = load_vec(wsum + (size_t)(VAR_WINDOWS - 1) * batch + b);
+    // glv: windows w and w + 32 carry the same weight 16^w -> 31 steps of 4 doublings instead of 63
+    const int top = glv ? VAR_WINDOWS / 2 : VAR_WINDOWS;
 #pragma unroll 1
-    for (int w = VAR_WINDOWS - 2; w >= 0; w--) {
-      acc.dbl(); acc.dbl(); acc.dbl(); acc.dbl();
+    for (int w = top - 1; w >= 0; w--) {
+      if (w != top - 1) { acc.dbl(); acc.dbl(); acc.dbl(); acc.dbl(); }
       XYZZ<Fq> q = load_vec(wsum + (size_t)w * batch + b);
       acc.add(q);
+      if (glv) { XYZZ<Fq> q2 = load_vec(wsum + (size_t)(w + top) * batch + b); acc.add(q2); }
     }
   }
   XYZZ<Fq> f = load_vec(fixed_sum + b);
@@ -104,13 +125,18 @@ int batch_identity_launch(bpgpu_ctx* ctx, const FixedRuns& runs, uint32_t F, siz
   else
     k_batch_fixed<Curve><<<(unsigned)cnt, BATCH_FIXED_THREADS, 0, ctx->stream>>>(runs, F, (const Fr*)d_fs, 0, d_sum);
   if (prof) cudaEventRecord(ev[1], ctx->stream);
+  const int glv = Curve::ID == BPGPU_BLS12_381 ? 1 : 0;
   if (vn) {
     const size_t np = cnt * vn, nw = cnt * VAR_WINDOWS;
+    if (glv) {                                  // d_vs is this call's scratch: split in place
+      k_glv_split<Curve><<<(unsigned)((np + 255) / 256), 256, 0, ctx->stream>>>(np, (Fr*)const_cast<void*>(d_vs));
+      ctx->launches++;
+    }
     k_batch_multiples<Curve><<<(unsigned)((np + 63) / 64), 64, 0, ctx->stream>>>(np, (const Affine<Fq>*)d_vp, d_m);
-    k_batch_windows<Curve><<<(unsigned)((nw + 127) / 128), 128, 0, ctx->stream>>>(cnt, vn, (const Fr*)d_vs, d_m, d_w);
+    k_batch_windows<Curve><<<(unsigned)((nw + 127) / 128), 128, 0, ctx->stream>>>(cnt, vn, (const Fr*)d_vs, d_m, d_w, glv);
     ctx->launches += 2;
   }
-  k_batch_horner<Curve><<<(unsigned)((cnt + 31) / 32), 32, 0, ctx->stream>>>(cnt, vn, d_w, d_sum, d_v);
+  k_batch_horner<Curve><<<(unsigned)((cnt + 31) / 32), 32, 0, ctx->stream>>>(cnt, vn, d_w, d_sum, d_v, glv);
   if (prof) {
     cudaEventRecord(ev[2], ctx->stream);
     cudaEventSynchronize(ev[2]);

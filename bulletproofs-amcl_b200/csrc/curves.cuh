@@ -126,4 +126,78 @@ BP_HD bool g1_from_be_checked(const uint8_t* xy, Affine<typename Curve::Fq>* out
   return true;
 }
 
+// ---- GLV on BLS12-381 G1: phi(x, y) = (beta * x, y) = lambda * (x, y) with lambda = z^2 - 1 (z the curve parameter),
+// lambda^2 + lambda + 1 = 0 mod r.  Since r = z^4 - z^2 + 1 ~ lambda^2, plain division k = k2 * lambda + k1 already gives
+// 0 <= k1 < lambda < 2^128 and k2 <= r / lambda < 2^128: k * P = k1 * P + k2 * phi(P) with two 128-bit scalars, which halves
+// the doubling chain of a Straus / Horner evaluation (batch.cu).  Constants checked against the oracle in
+// tests/test_host_core.py (phi(G) == lambda * G; k1 + k2 * lambda == k).
+BP_HD uint32_t glv_bls_lambda(int i) { const uint32_t v[4] = {0xffffffffu, 0x00000000u, 0x0001a402u, 0xac45a401u}; return v[i]; }
+BP_HD uint32_t glv_bls_mu(int i) { const uint32_t v[5] = {0xf6cfee30u, 0x63f6e522u, 0xe01faaddu, 0x7c6becf1u, 0x00000001u}; return v[i]; }   // floor(2^256 / lambda)
+// beta (canonical limbs); Montgomery form by to_mont()
+BP_HD Fp<BlsFq> glv_bls_beta() {
+  const uint32_t v[12] = {0x0000aaacu, 0x8bfd0000u, 0x4f49fffdu, 0x409427ebu, 0x0fb85f9bu, 0x897d2965u,
+                          0x89759ad4u, 0xaa0d857du, 0x63d4de85u, 0xec024086u, 0x397fe699u, 0x1a0111eau};
+  Fp<BlsFq> b;
+  for (int i = 0; i < 12; i++) b.v[i] = v[i];
+  return b.to_mont();
+}
+// k (canonical, < r, 8 limbs) -> out[0..4) = k1, out[4..8) = k2
+BP_HD void glv_bls_split(const uint32_t* k, uint32_t* out) {
+  // q = floor(k * mu / 2^256): 8 x 5 limb product, limbs 8..12
+  uint32_t prod[13];
+  for (int i = 0; i < 13; i++) prod[i] = 0;
+  for (int i = 0; i < 8; i++) {
+    uint64_t carry = 0;
+    for (int j = 0; j < 5; j++) {
+      const uint64_t t = (uint64_t)k[i] * glv_bls_mu(j) + prod[i + j] + carry;
+      prod[i + j] = (uint32_t)t;
+      carry = t >> 32;
+    }
+    prod[i + 5] = (uint32_t)carry;
+  }
+  uint32_t q[4] = {prod[8], prod[9], prod[10], prod[11]};          // < 2^128 (prod[12] = 0 for k < r)
+  // rem = k - q * lambda  (< 3 * lambda: 5 limbs are enough, computed modulo 2^160)
+  uint32_t ql[5] = {0, 0, 0, 0, 0};
+  for (int i = 0; i < 4; i++) {
+    uint64_t carry = 0;
+    for (int j = 0; j < 4 && i + j < 5; j++) {
+      const uint64_t t = (uint64_t)q[i] * glv_bls_lambda(j) + ql[i + j] + carry;
+      ql[i + j] = (uint32_t)t;
+      carry = t >> 32;
+    }
+    if (i + 4 < 5) ql[i + 4] = (uint32_t)carry;
+  }
+  uint32_t rem[5];
+  uint64_t borrow = 0;
+  for (int i = 0; i < 5; i++) {
+    const uint64_t t = (uint64_t)k[i] - ql[i] - borrow;
+    rem[i] = (uint32_t)t;
+    borrow = (t >> 32) & 1;
+  }
+  for (int it = 0; it < 3; it++) {                                  // at most 2 corrections (measured: 1)
+    bool ge = rem[4] != 0;
+    if (!ge) {
+      ge = true;
+      for (int i = 3; i >= 0; i--) {
+        if (rem[i] > glv_bls_lambda(i)) break;
+        if (rem[i] < glv_bls_lambda(i)) { ge = false; break; }
+      }
+    }
+    if (!ge) break;
+    borrow = 0;
+    for (int i = 0; i < 5; i++) {
+      const uint64_t t = (uint64_t)rem[i] - (i < 4 ? glv_bls_lambda(i) : 0u) - borrow;
+      rem[i] = (uint32_t)t;
+      borrow = (t >> 32) & 1;
+    }
+    for (int i = 0; i < 4; i++) { if (++q[i] != 0) break; }
+  }
+  for (int i = 0; i < 4; i++) { out[i] = rem[i]; out[4 + i] = q[i]; }
+}
+
+// beta of the curve's GLV endomorphism in Montgomery form (only BLS12-381 uses it; BN254's balanced split needs a lattice)
+template <class Curve> BP_HD typename Curve::Fq glv_beta();
+template <> BP_HD Bls::Fq glv_beta<Bls>() { return glv_bls_beta(); }
+template <> BP_HD Bn::Fq glv_beta<Bn>() { return Bn::Fq::zero(); }
+
 }  // namespace bp

@@ -170,19 +170,20 @@ static int verify_batch_t(bpgpu_ctx* ctx, const bpgpu_circuit* circ, const Fixed
     k_vb_scalars<Curve><<<(unsigned)cnt, 128, 0, ctx->stream>>>(c, N, lg, F, vn, d_hdr, (Fr*)(base + L.fs), (Fr*)(base + L.vs));
     ctx->launches += 3;
     if ((rc = launch_check(ctx, "verify_batch"))) return rc;
+    std::vector<uint32_t> dbg;
+    if (dbg_fixed_be && lo == 0) {                 // test hook: the scalars of the first slab as the device built them (canonical integers),
+      dbg.resize(cnt * (size_t)(F + vn) * 8);      // read before the MSM stage splits the variable ones in place (GLV)
+      BP_CUDA_OK(cudaMemcpyAsync(dbg.data(), base + L.fs, cnt * (size_t)F * 32, cudaMemcpyDeviceToHost, ctx->stream));
+      BP_CUDA_OK(cudaMemcpyAsync(dbg.data() + cnt * (size_t)F * 8, base + L.vs, cnt * (size_t)vn * 32, cudaMemcpyDeviceToHost, ctx->stream));
+      BP_CUDA_OK(stream_sync(ctx));
+      for (size_t i = 0; i < cnt * (size_t)F; i++) hd_limbs_to_be<8>(dbg.data() + i * 8, (int)MB, dbg_fixed_be + i * MB);
+      for (size_t i = 0; i < cnt * (size_t)vn; i++) hd_limbs_to_be<8>(dbg.data() + (cnt * (size_t)F + i) * 8, (int)MB, dbg_var_be + i * MB);
+    }
     if ((rc = batch_identity_launch<Curve>(ctx, runs, F, cnt, base + L.fs, base + L.vp, base + L.vs, vn, base + L.sum, base + L.m, base + L.w,
                                            base + L.v)))
       return rc;
     BP_CUDA_OK(cudaMemcpyAsync(ident.data(), base + L.v, cnt, cudaMemcpyDeviceToHost, ctx->stream));
     BP_CUDA_OK(cudaMemcpyAsync(status.data(), d_status, cnt * 4, cudaMemcpyDeviceToHost, ctx->stream));
-    if (dbg_fixed_be && lo == 0) {                 // test hook: the scalars of the first slab as the device built them (canonical integers)
-      std::vector<uint32_t> tmp(cnt * (size_t)(F + vn) * 8);
-      BP_CUDA_OK(cudaMemcpyAsync(tmp.data(), base + L.fs, cnt * (size_t)F * 32, cudaMemcpyDeviceToHost, ctx->stream));
-      BP_CUDA_OK(cudaMemcpyAsync(tmp.data() + cnt * (size_t)F * 8, base + L.vs, cnt * (size_t)vn * 32, cudaMemcpyDeviceToHost, ctx->stream));
-      BP_CUDA_OK(stream_sync(ctx));
-      for (size_t i = 0; i < cnt * (size_t)F; i++) hd_limbs_to_be<8>(tmp.data() + i * 8, (int)MB, dbg_fixed_be + i * MB);
-      for (size_t i = 0; i < cnt * (size_t)vn; i++) hd_limbs_to_be<8>(tmp.data() + (cnt * (size_t)F + i) * 8, (int)MB, dbg_var_be + i * MB);
-    }
     BP_CUDA_OK(stream_sync(ctx));
     for (size_t i = 0; i < cnt; i++) verdicts[lo + i] = status[i] ? status[i] : (ident[i] ? BPGPU_OK : BPGPU_E_VERIFY);
   }

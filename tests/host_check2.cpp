@@ -93,3 +93,18 @@ extern "C" void hc2_fr_from_be_wide(int curve, const uint8_t* be, uint8_t* out) 
   if (curve == 0) { Bls::Fr v = fr_from_be_wide<Bls>(be).from_mont(); hd_limbs_to_be<8>(v.v, 48, out); }
   else { Bn::Fr v = fr_from_be_wide<Bn>(be).from_mont(); hd_limbs_to_be<8>(v.v, 32, out); }
 }
+
+// GLV split on BLS12-381: k (32-byte big endian, < r) -> k1 | k2 (16 bytes big endian each); and phi(P) = (beta * x, y)
+extern "C" void hc2_glv_split(const uint8_t* k_be, uint8_t* k1_be, uint8_t* k2_be) {
+  uint32_t k[8], out[8];
+  hd_be_to_limbs<8>(k_be, 32, k);
+  glv_bls_split(k, out);
+  hd_limbs_to_be<4>(out, 16, k1_be);
+  hd_limbs_to_be<4>(out + 4, 16, k2_be);
+}
+extern "C" void hc2_glv_phi_x(const uint8_t* x_be, uint8_t* out_be) {
+  Bls::Fq x;
+  hd_be_to_limbs<12>(x_be, 48, x.v);
+  Bls::Fq y = (x.to_mont() * glv_bls_beta()).from_mont();
+  hd_limbs_to_be<12>(y.v, 48, out_be);
+}

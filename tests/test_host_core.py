@@ -186,3 +186,26 @@ def test_wide_scalar_reduction(hc2):
             out = ctypes.create_string_buffer(mb)
             hc2.hc2_fr_from_be_wide(cid, v.to_bytes(mb, "big"), out)
             assert int.from_bytes(out.raw, "big") == v % C.r
+
+
+def test_glv_constants_and_split(hc2):
+    """GLV on BLS12-381 G1 (csrc/curves.cuh): phi(P) = (beta x, y) = lambda P checked with the oracle's group law, and the
+    device's split k = k1 + k2 lambda with both halves below 2^128, on edge cases and random scalars"""
+    import random
+    C = CURVES["BLS12_381"]
+    lam = 0xac45a4010001a40200000000ffffffff
+    assert (lam * lam + lam + 1) % C.r == 0
+    G = C.from_affine(C.g)
+    for P in (G, C.mul(G, 7777)):
+        x, y = C.to_affine(P)
+        out = ctypes.create_string_buffer(48)
+        hc2.hc2_glv_phi_x(x.to_bytes(48, "big"), out)
+        assert (int.from_bytes(out.raw, "big"), y) == C.to_affine(C.mul(P, lam))
+    rnd = random.Random(5)
+    ks = [0, 1, lam - 1, lam, lam + 1, C.r - 1, C.r - 2, lam * ((C.r - 1) // lam), lam * lam % C.r, (1 << 254) + 3]
+    ks += [rnd.randrange(C.r) for _ in range(3000)]
+    for k in ks:
+        a, b = ctypes.create_string_buffer(16), ctypes.create_string_buffer(16)
+        hc2.hc2_glv_split(k.to_bytes(32, "big"), a, b)
+        k1, k2 = int.from_bytes(a.raw, "big"), int.from_bytes(b.raw, "big")
+        assert k1 + k2 * lam == k and k1 < lam, hex(k)
