@@ -77,7 +77,7 @@ __global__ void __launch_bounds__(128) k_vb_scalars(const __grid_constant__ Circ
   for (uint32_t k = threadIdx.x; k < hl; k += blockDim.x) store_vec(sh + k, load_vec(hdr + (size_t)b * hl + k));
   __syncthreads();
   if (threadIdx.x == 0) hd_square_table(sh[VB_YINV], yitab);
-  if (threadIdx.x == 32) hd_square_table(sh[VB_Z], ztab);
+  if (threadIdx.x == blockDim.x - 1) hd_square_table(sh[VB_Z], ztab);
   __syncthreads();
   Fr* f = fs + (size_t)b * F;
   Fr* v = vs + (size_t)b * vn;
@@ -167,7 +167,8 @@ static int verify_batch_t(bpgpu_ctx* ctx, const bpgpu_circuit* circ, const Fixed
     const size_t np = cnt * vn;
     k_vb_points<Curve><<<(unsigned)((np + 127) / 128), 128, 0, ctx->stream>>>((uint32_t)cnt, vn, c.m, lg, d_proofs, plen, d_comms,
                                                                               (Affine<Fq>*)(base + L.vp), d_status);
-    k_vb_scalars<Curve><<<(unsigned)cnt, 128, 0, ctx->stream>>>(c, N, lg, F, vn, d_hdr, (Fr*)(base + L.fs), (Fr*)(base + L.vs));
+    const unsigned sbs = N >= 128 ? 128u : (N >= 32 ? N : 32u);      // a power of two; no idle half-block for the 64-multiplier circuits
+    k_vb_scalars<Curve><<<(unsigned)cnt, sbs, 0, ctx->stream>>>(c, N, lg, F, vn, d_hdr, (Fr*)(base + L.fs), (Fr*)(base + L.vs));
     ctx->launches += 3;
     if ((rc = launch_check(ctx, "verify_batch"))) return rc;
     std::vector<uint32_t> dbg;
