@@ -298,6 +298,69 @@ def proof_section(bp, ctx, local, rank, world, dist, torch, no_cpu=False):
             except Exception:
                 out[tag]["cpu_baseline"] = {"error": (r.stderr or r.stdout)[-300:]}
 
+    def run_ipp(n, count, tag, cpu_base=0):
+        """BASELINE config 1: the standalone inner-product argument (IPP::create_ipp / verify_ipp, ipp.rs:35-260, the shape of
+        the reference's own ipp tests at length n) through bph_ipp_create / bph_ipp_verify, one proof per context in flight"""
+        from concurrent.futures import ThreadPoolExecutor
+        ctxs = [bp.Context(bp.BLS12_381, local) for _ in range(nctx)]
+        c0 = ctxs[0]
+        mb = c0.modbytes
+        G, H = c0.get_generators("g", n, precompute=True), c0.get_generators("h", n, precompute=True)
+        Q = c0.g1_from_msg_hash(b"Q")
+        ones = b"".join([(1).to_bytes(mb, "big")] * n)
+        jobs = []
+        for i in range(count):
+            ab = synth_scalars_be(n, 7000 + 131 * rank + 2 * i, mb).tobytes()
+            bb = synth_scalars_be(n, 7001 + 131 * rank + 2 * i, mb).tobytes()
+            cb = (sum(x * y for x, y in zip(be_ints(ab, n, mb), be_ints(bb, n, mb))) % BLS_R).to_bytes(mb, "big")
+            P = c0.msm_parts([(G, ab, n), (H, bb, n), (Q, cb, 1)])
+            jobs.append((ab, bb, P))
+
+        def prove(k):
+            ctx = ctxs[k % nctx]
+            return [ctx.ipp_create(b"ipp", G, H, Q, ones, ones, jobs[i][0], jobs[i][1], n) for i in range(k, count, nctx)]
+
+        def verify(k):
+            ctx = ctxs[k % nctx]
+            return all(ctx.ipp_verify(b"ipp", n, ones, ones, jobs[i][2], Q, G, H, proofs[i]) for i in range(k, count, nctx))
+        with ThreadPoolExecutor(nctx) as ex:
+            list(ex.map(prove, range(nctx)))                                         # warm-up
+            if dist is not None:
+                dist.barrier()
+            t0 = time.perf_counter()
+            res = list(ex.map(prove, range(nctx)))
+            tp = time.perf_counter() - t0
+            proofs = [None] * count
+            for k, lst in enumerate(res):
+                for j, pr in enumerate(lst):
+                    proofs[k + j * nctx] = pr
+            list(ex.map(verify, range(nctx)))
+            if dist is not None:
+                dist.barrier()
+            t0 = time.perf_counter()
+            ok = all(ex.map(verify, range(nctx)))
+            tv = time.perf_counter() - t0
+        if dist is not None:
+            tt = torch.tensor([tp, tv, 0.0 if ok else 1.0], device="cuda", dtype=torch.float64)
+            dist.all_reduce(tt, op=dist.ReduceOp.MAX)
+            tp, tv, ok = float(tt[0].item()), float(tt[1].item()), tt[2].item() == 0.0
+        for c in ctxs:
+            c.close()
+        out[tag] = {"n": n, "proofs": count * world, "prove_per_s": count * world / tp, "verify_per_s": count * world / tv,
+                    "prove_verify_per_s": count * world / (tp + tv), "all_verified": ok, "proof_bytes": len(proofs[0])}
+        if cpu_base and rank == 0 and world == 1:
+            r = subprocess.run([sys.executable, "-m", "oracle.fast", "ipp", "BLS12_381", str(n), str(cpu_base), str(ncpu)],
+                               capture_output=True, text=True, cwd=ROOT)
+            try:
+                d = json.loads(r.stdout.strip().splitlines()[-1])
+                out[tag]["cpu_baseline"] = {"prove_per_s": d["prove_per_s"], "verify_per_s": d["verify_per_s"],
+                                            "prove_verify_per_s": d["prove_verify_per_s"], "unit": "proofs/s", "cores": ncpu, "kind": "port",
+                                            "sample": f"{d['proofs']} proofs, {ncpu} processes x {cpu_base}, {d['wall_s']:.1f} s wall"}
+            except Exception:
+                out[tag]["cpu_baseline"] = {"error": (r.stderr or r.stdout)[-300:]}
+
+    # config 1: IPP prove + verify at n = 64
+    run_ipp(64, max(nctx, 512 // world), "ipp_bls12_381_n64", cpu_base=0 if no_cpu else 8)
     # config 5 unit / config 1 size: one 64-bit range proof = 64 multipliers, IPP of length 64; 4096 verifications in total
     per_rank = max(nctx, 512 // world)
     run(bp.BLS12_381, 1, 64, per_rank, "range64_bls12_381_n64", verify_reps=max(1, 4096 // (per_rank * world)),

@@ -37,6 +37,13 @@ struct IPP {
       q_scalar->to_bytes(qs);
       rc = bpgpu_ipp_begin_fixed_q(ctx, G_vec.handle(), goff, H_vec.handle(), hoff, q_base->xy, qs, G_factors.handle(), H_factors.handle(),
                                    a_vec.handle(), b_vec.handle(), n, &st);
+    } else if (bpgpu_points_has_tables(G_vec.handle()) && bpgpu_points_has_tables(H_vec.handle())) {
+      // generators with window tables: Q = 1 * Q takes a table of its own (cached in the ctx; the reference's callers reuse one
+      // Q for many arguments, ipp.rs:342), so that every round stays on the table path
+      uint8_t one[C::MODBYTES];
+      FE::one().to_bytes(one);
+      rc = bpgpu_ipp_begin_fixed_q(ctx, G_vec.handle(), goff, H_vec.handle(), hoff, Q.xy, one, G_factors.handle(), H_factors.handle(),
+                                   a_vec.handle(), b_vec.handle(), n, &st);
     } else {
       rc = bpgpu_ipp_begin(ctx, G_vec.handle(), goff, H_vec.handle(), hoff, Q.xy, G_factors.handle(), H_factors.handle(), a_vec.handle(),
                            b_vec.handle(), n, &st);

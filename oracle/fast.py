@@ -88,6 +88,41 @@ def range_prove_verify(C, vals, bits, seed, gens=None, label=b"bench"):
     return t1 - t0, t2 - t1, proof.to_bytes(F), gens
 
 
+def ipp_prove_verify(C, n, seed, gens=None, label=b"ipp"):
+    """IPP::create_ipp + IPP::verify_ipp (ipp.rs:35-260, the shape of its own tests ipp.rs:325-390 at length n) with the
+    C-accelerated oracle.  Returns (prove_seconds, verify_seconds, gens)."""
+    import time
+    from . import ipp as oipp
+    from .merlin import Transcript
+    F = C if isinstance(C, FastCurve) else FastCurve(C)
+    if gens is None:
+        gens = (F.get_generators("g", n), F.get_generators("h", n), F.g1_from_msg_hash(b"Q"))
+    G, H, Q = gens
+    a, b = F.synth_scalars(seed, n, b"a"), F.synth_scalars(seed, n, b"b")
+    ones = [1] * n
+    P = F.msm(G + H + [Q], a + b + [F.inner_product(a, b)])
+    with c_keccak():
+        t0 = time.perf_counter()
+        proof = oipp.create_ipp(F, Transcript(label, F), Q, ones, ones, G, H, a, b)
+        t1 = time.perf_counter()
+        oipp.verify_ipp(F, n, Transcript(label, F), ones, ones, P, Q, G, H, proof.a, proof.b, proof.L, proof.R)
+        t2 = time.perf_counter()
+    return t1 - t0, t2 - t1, gens
+
+
+def _ipp_worker(args):
+    cname, n, count, seed = args
+    from .curves import CURVES
+    F = FastCurve(CURVES[cname])
+    gens = None
+    tp = tv = 0.0
+    for k in range(count):
+        a, b, gens = ipp_prove_verify(F, n, seed + k, gens)
+        tp += a
+        tv += b
+    return tp, tv
+
+
 def _worker(args):
     cname, m, bits, count, seed = args
     import time
@@ -109,14 +144,22 @@ def main(argv):
     import json
     import multiprocessing as mp
     import time
-    cname, m, bits, count, procs = argv[0], int(argv[1]), int(argv[2]), int(argv[3]), int(argv[4])
-    jobs = [(cname, m, bits, count, 1000 * (i + 1)) for i in range(procs)]
+    ipp = argv[0] == "ipp"                      # python -m oracle.fast ipp CURVE n proofs_per_process processes
+    if ipp:
+        argv = argv[1:]
+        cname, m, bits, count, procs = argv[0], int(argv[1]), 1, int(argv[2]), int(argv[3])
+        jobs = [(cname, m, count, 1000 * (i + 1)) for i in range(procs)]
+        fn = _ipp_worker
+    else:
+        cname, m, bits, count, procs = argv[0], int(argv[1]), int(argv[2]), int(argv[3]), int(argv[4])
+        jobs = [(cname, m, bits, count, 1000 * (i + 1)) for i in range(procs)]
+        fn = _worker
     t0 = time.perf_counter()
     if procs == 1:
-        res = [_worker(jobs[0])]
+        res = [fn(jobs[0])]
     else:
         with mp.get_context("fork").Pool(procs) as pool:
-            res = pool.map(_worker, jobs)
+            res = pool.map(fn, jobs)
     wall = time.perf_counter() - t0
     tp, tv = sum(r[0] for r in res), sum(r[1] for r in res)
     total = count * procs

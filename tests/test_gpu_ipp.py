@@ -93,3 +93,25 @@ def test_ipp_argument_errors(ctx_bls):
         ctx.ipp_begin(dG, dG, Q, v3, v3, v3, v3, 3)
     with pytest.raises(Exception):        # assert_eq!(a_vec.len(), n)     ipp.rs:52
         ctx.ipp_begin(dG, dG, Q, v4, v4, v3, v4, 4)
+
+
+@pytest.mark.parametrize("which", ["bls", "bn"])
+@pytest.mark.parametrize("n", [1, 2, 16, 64])
+def test_ipp_with_tables_and_arbitrary_q(which, n, ctx_bls, ctx_bn):
+    """bph_ipp_create / bph_ipp_verify (the reference's own test shape, ipp.rs:325-390) with generators that carry window
+    tables and a Q that is NOT a multiple of a cached base: Q gets a table of its own and every round runs on the table
+    path; the proof bytes equal the oracle's, also for Q = identity"""
+    ctx = ctx_bls if which == "bls" else ctx_bn
+    C = curve_of(ctx)
+    G, H = C.get_generators("g", n), C.get_generators("h", n)
+    dG, dH = ctx.get_generators("g", n, precompute=True), ctx.get_generators("h", n, precompute=True)
+    a, b = C.synth_scalars(8, n, b"a"), C.synth_scalars(8, n, b"b")
+    ones = [1] * n
+    for Q in (C.g1_from_msg_hash(b"Q"), C.INF):
+        exp = oipp.create_ipp(C, Transcript(b"tab", C), Q, ones, ones, G, H, a, b)
+        want = b"".join(C.g1_to_bytes(p) for p in exp.L) + b"".join(C.g1_to_bytes(p) for p in exp.R) + C.fr_to_bytes(exp.a) + C.fr_to_bytes(exp.b)
+        got = ctx.ipp_create(b"tab", dG, dH, C.g1_xy_bytes(Q), enc_scalars(C, ones), enc_scalars(C, ones), enc_scalars(C, a), enc_scalars(C, b), n)
+        assert got == want
+        P = C.msm(G + H + [Q], a + b + [C.inner_product(a, b)])
+        assert ctx.ipp_verify(b"tab", n, enc_scalars(C, ones), enc_scalars(C, ones), C.g1_xy_bytes(P), C.g1_xy_bytes(Q), dG, dH, got)
+        assert not ctx.ipp_verify(b"tab", n, enc_scalars(C, ones), enc_scalars(C, ones), C.g1_xy_bytes(C.dbl(P)), C.g1_xy_bytes(Q), dG, dH, got)
