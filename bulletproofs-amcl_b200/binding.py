@@ -44,6 +44,11 @@ SYMBOLS = [
     ("bpgpu_scalars_free", None, [_VP]),
     ("bpgpu_msm", _INT, [_VP, _VP, _SZ, _SZ, _VP, _VP]),
     ("bpgpu_msm_le32", _INT, [_VP, _VP, _SZ, _SZ, _VP, _VP]),
+    ("bpgpu_msm_begin", _INT, [_VP, _VP, _SZ, _SZ, _VP]),
+    ("bpgpu_msm_le32_begin", _INT, [_VP, _VP, _SZ, _SZ, _VP]),
+    ("bpgpu_msm_device_begin", _INT, [_VP, _VP, _SZ, _SZ, _VP, _SZ]),
+    ("bpgpu_msm_refs_begin", _INT, [_VP, _VP, _VP, _SZ]),
+    ("bpgpu_msm_finish", _INT, [_VP, _VP]),
     ("bpgpu_msm_device", _INT, [_VP, _VP, _SZ, _SZ, _VP, _SZ, _VP]),
     ("bpgpu_msm_refs", _INT, [_VP, _VP, _VP, _SZ, _VP]),
     ("bpgpu_msm_parts_batch", _INT, [_VP, _VP, _VP, _SZ, _VP]),
@@ -619,6 +624,28 @@ class Context:
         n = len(scalars_le32) // 32 if n is None else n
         out = ctypes.create_string_buffer(2 * self.modbytes)
         self._check(lib().bpgpu_msm_le32(self.handle, points.handle, off, n, _buf(scalars_le32), out), "msm_le32")
+        return out.raw
+
+    # two-halves form: begin enqueues, finish returns the point (one MSM in flight per context)
+    def msm_device_begin(self, points, scalars, poff=0, soff=0, n=None):
+        n = len(scalars) - soff if n is None else n
+        self._check(lib().bpgpu_msm_device_begin(self.handle, points.handle, poff, n, scalars.handle, soff), "msm_device_begin")
+
+    def msm_begin(self, points, scalars_be, off=0, n=None):
+        n = len(scalars_be) // self.modbytes if n is None else n
+        self._check(lib().bpgpu_msm_begin(self.handle, points.handle, off, n, _buf(scalars_be)), "msm_begin")
+
+    def msm_le32_begin(self, points, scalars_le32, off=0, n=None):
+        n = len(scalars_le32) // 32 if n is None else n
+        self._check(lib().bpgpu_msm_le32_begin(self.handle, points.handle, off, n, _buf(scalars_le32)), "msm_le32_begin")
+
+    def msm_refs_begin(self, points_xy, scalars_be, n=None):
+        n = len(scalars_be) // self.modbytes if n is None else n
+        self._check(lib().bpgpu_msm_refs_begin(self.handle, _buf(points_xy), _buf(scalars_be), n), "msm_refs_begin")
+
+    def msm_finish(self):
+        out = ctypes.create_string_buffer(2 * self.modbytes)
+        self._check(lib().bpgpu_msm_finish(self.handle, out), "msm_finish")
         return out.raw
 
     def msm_device(self, points, scalars, poff=0, soff=0, n=None):

@@ -273,11 +273,14 @@ static void msm_finish_mixed(const uint8_t* winsum_bytes, int W, int c, int qshi
   acc.to_xy_be(modbytes, out_xy);
 }
 
-int msm_mixed_to_host(bpgpu_ctx* ctx, const TableSeg* segs, int nsegs, const void* d_pts, const void* d_scal, bool mont, size_t n,
-                      uint8_t* out_xy) {
-  const int mb = bpgpu_modbytes(ctx->curve);
+// The MSM in two halves: `begin` enqueues the device pipeline and the copy of its per-window sums on the ctx stream and
+// returns; `finish` waits for the stream, checks the inputs and does the host part (Horner + one inversion).  Between the
+// two the host thread is free -- to finish the previous MSM of ANOTHER context, whose sort stages (HBM / latency bound)
+// then run under this one's bucket accumulation (integer pipe bound): bpgpu_msm_*_begin / bpgpu_msm_finish.
+int msm_mixed_begin(bpgpu_ctx* ctx, const TableSeg* segs, int nsegs, const void* d_pts, const void* d_scal, bool mont, size_t n) {
   const bool bls = ctx->curve == BPGPU_BLS12_381;
   const size_t psz = bls ? sizeof(XYZZ<Bls::Fq>) : sizeof(XYZZ<Bn::Fq>);
+  if (ctx->pending.active) return BPGPU_E_ARG;                    // one MSM in flight per ctx
   MsmResult res;
   res.W = 0; res.c = 0; res.qshift = 0; res.d_winsum = nullptr;
   int rc;
@@ -299,12 +302,39 @@ int msm_mixed_to_host(bpgpu_ctx* ctx, const TableSeg* segs, int nsegs, const voi
                                        ctx->stream));
     else BP_CUDA_OK(cudaMemcpyAsync(tsum, ctx->tbl_part.p, psz, cudaMemcpyDeviceToHost, ctx->stream));
   }
-  if (res.W || tn) BP_CUDA_OK(stream_sync(ctx));
+  ctx->pending.active = true;
+  ctx->pending.W = res.W; ctx->pending.c = res.c; ctx->pending.qshift = res.qshift;
+  ctx->pending.tn = tn; ctx->pending.hp = hp;
+  return BPGPU_OK;
+}
+
+int msm_mixed_finish(bpgpu_ctx* ctx, uint8_t* out_xy) {
+  if (!ctx->pending.active) return BPGPU_E_ARG;
+  const int mb = bpgpu_modbytes(ctx->curve);
+  const bool bls = ctx->curve == BPGPU_BLS12_381;
+  const size_t psz = bls ? sizeof(XYZZ<Bls::Fq>) : sizeof(XYZZ<Bn::Fq>);
+  const int W = ctx->pending.W, c = ctx->pending.c, qshift = ctx->pending.qshift, hp = ctx->pending.hp;
+  const size_t tn = ctx->pending.tn;
+  ctx->pending.active = false;
+  uint8_t* tsum = ctx->pinned + 2 * 128 * psz;
+  if (W || tn) BP_CUDA_OK(stream_sync(ctx));
+  if (ctx->wait_points) {                  // the pipeline did not get as far as the wait (error path): drain the copy queue
+    ctx->wait_points = false;
+    cudaStreamSynchronize(ctx->copy_stream);
+  }
+  int rc;
   if ((rc = inputs_ok(ctx))) return rc;
   if (hp) { if (bls) host_sum_partials<BlsFq>(tsum, 1, hp); else host_sum_partials<BnFq>(tsum, 1, hp); }
-  if (bls) msm_finish_mixed<BlsFq>(ctx->pinned, res.W, res.c, res.qshift, tn ? tsum : nullptr, mb, out_xy);
-  else msm_finish_mixed<BnFq>(ctx->pinned, res.W, res.c, res.qshift, tn ? tsum : nullptr, mb, out_xy);
+  if (bls) msm_finish_mixed<BlsFq>(ctx->pinned, W, c, qshift, tn ? tsum : nullptr, mb, out_xy);
+  else msm_finish_mixed<BnFq>(ctx->pinned, W, c, qshift, tn ? tsum : nullptr, mb, out_xy);
   return BPGPU_OK;
+}
+
+int msm_mixed_to_host(bpgpu_ctx* ctx, const TableSeg* segs, int nsegs, const void* d_pts, const void* d_scal, bool mont, size_t n,
+                      uint8_t* out_xy) {
+  int rc = msm_mixed_begin(ctx, segs, nsegs, d_pts, d_scal, mont, n);
+  if (rc) return rc;
+  return msm_mixed_finish(ctx, out_xy);
 }
 
 int msm_pair_to_host(bpgpu_ctx* ctx, const void* d_pts, const void* d_scal_a, const void* d_scal_b, bool mont, size_t n, uint8_t* out_a_xy,
@@ -624,8 +654,9 @@ int bpgpu_scalars_view(bpgpu_scalars* s, size_t off, size_t n, bpgpu_scalars** o
 int bpgpu_msm_window_bits(size_t n) { return msm_window_bits(n); }
 
 
-int bpgpu_msm(bpgpu_ctx* ctx, const bpgpu_points* p, size_t off, size_t n, const uint8_t* scalars_be, uint8_t* out_xy) {
-  if (!ctx || !p || !out_xy || (!scalars_be && n)) return BPGPU_E_ARG;
+// ---- begin halves (see msm_mixed_begin): host buffers passed here must stay valid until bpgpu_msm_finish
+int bpgpu_msm_begin(bpgpu_ctx* ctx, const bpgpu_points* p, size_t off, size_t n, const uint8_t* scalars_be) {
+  if (!ctx || !p || (!scalars_be && n)) return BPGPU_E_ARG;
   if (off > p->n || n > p->n - off) return BPGPU_E_LEN;
   BP_CUDA_OK(cudaSetDevice(ctx->device));
   int rc = ctx->msm_c.reserve(n * 32 + 32);
@@ -637,16 +668,16 @@ int bpgpu_msm(bpgpu_ctx* ctx, const bpgpu_points* p, size_t off, size_t n, const
   size_t psz = (ctx->curve == BPGPU_BLS12_381) ? sizeof(Affine<Bls::Fq>) : sizeof(Affine<Bn::Fq>);
   if (p->table && n) {
     TableSeg seg{(const uint8_t*)p->table + off * TBL_ENTRIES * psz, ctx->msm_c.p, (uint32_t)n, 0};
-    return msm_mixed_to_host(ctx, &seg, 1, nullptr, nullptr, false, 0, out_xy);
+    return msm_mixed_begin(ctx, &seg, 1, nullptr, nullptr, false, 0);
   }
-  return msm_to_host(ctx, (const uint8_t*)p->d + off * psz, ctx->msm_c.p, false, n, out_xy);
+  return msm_mixed_begin(ctx, nullptr, 0, (const uint8_t*)p->d + off * psz, ctx->msm_c.p, false, n);
 }
 
 // resident bases, scalars as 32-byte LITTLE-endian canonical integers (< r): exactly the device's limb layout, so the
 // upload is one copy of 32 bytes per term and no conversion launch (48-byte big-endian scalars cost 50 % more PCIe
 // traffic on BLS12-381 plus a pass over them)
-int bpgpu_msm_le32(bpgpu_ctx* ctx, const bpgpu_points* p, size_t off, size_t n, const uint8_t* scalars_le32, uint8_t* out_xy) {
-  if (!ctx || !p || !out_xy || (!scalars_le32 && n)) return BPGPU_E_ARG;
+int bpgpu_msm_le32_begin(bpgpu_ctx* ctx, const bpgpu_points* p, size_t off, size_t n, const uint8_t* scalars_le32) {
+  if (!ctx || !p || (!scalars_le32 && n)) return BPGPU_E_ARG;
   if (off > p->n || n > p->n - off) return BPGPU_E_LEN;
   BP_CUDA_OK(cudaSetDevice(ctx->device));
   int rc = ctx->msm_c.reserve(n * 32 + 32);
@@ -655,26 +686,25 @@ int bpgpu_msm_le32(bpgpu_ctx* ctx, const bpgpu_points* p, size_t off, size_t n, 
   size_t psz = (ctx->curve == BPGPU_BLS12_381) ? sizeof(Affine<Bls::Fq>) : sizeof(Affine<Bn::Fq>);
   if (p->table && n) {
     TableSeg seg{(const uint8_t*)p->table + off * TBL_ENTRIES * psz, ctx->msm_c.p, (uint32_t)n, 0};
-    return msm_mixed_to_host(ctx, &seg, 1, nullptr, nullptr, false, 0, out_xy);
+    return msm_mixed_begin(ctx, &seg, 1, nullptr, nullptr, false, 0);
   }
-  return msm_to_host(ctx, (const uint8_t*)p->d + off * psz, ctx->msm_c.p, false, n, out_xy);
+  return msm_mixed_begin(ctx, nullptr, 0, (const uint8_t*)p->d + off * psz, ctx->msm_c.p, false, n);
 }
 
-int bpgpu_msm_device(bpgpu_ctx* ctx, const bpgpu_points* p, size_t poff, size_t n, const bpgpu_scalars* s, size_t soff,
-                     uint8_t* out_xy) {
-  if (!ctx || !p || !s || !out_xy) return BPGPU_E_ARG;
+int bpgpu_msm_device_begin(bpgpu_ctx* ctx, const bpgpu_points* p, size_t poff, size_t n, const bpgpu_scalars* s, size_t soff) {
+  if (!ctx || !p || !s) return BPGPU_E_ARG;
   if (poff > p->n || n > p->n - poff || soff > s->n || n > s->n - soff) return BPGPU_E_LEN;
   BP_CUDA_OK(cudaSetDevice(ctx->device));
   size_t psz = (ctx->curve == BPGPU_BLS12_381) ? sizeof(Affine<Bls::Fq>) : sizeof(Affine<Bn::Fq>);
   if (p->table && n) {
     TableSeg seg{(const uint8_t*)p->table + poff * TBL_ENTRIES * psz, (const uint8_t*)s->d + soff * 32, (uint32_t)n, 1};
-    return msm_mixed_to_host(ctx, &seg, 1, nullptr, nullptr, false, 0, out_xy);
+    return msm_mixed_begin(ctx, &seg, 1, nullptr, nullptr, false, 0);
   }
-  return msm_to_host(ctx, (const uint8_t*)p->d + poff * psz, (const uint8_t*)s->d + soff * 32, true, n, out_xy);
+  return msm_mixed_begin(ctx, nullptr, 0, (const uint8_t*)p->d + poff * psz, (const uint8_t*)s->d + soff * 32, true, n);
 }
 
-int bpgpu_msm_refs(bpgpu_ctx* ctx, const uint8_t* points_xy, const uint8_t* scalars_be, size_t n, uint8_t* out_xy) {
-  if (!ctx || !out_xy || ((!points_xy || !scalars_be) && n)) return BPGPU_E_ARG;
+int bpgpu_msm_refs_begin(bpgpu_ctx* ctx, const uint8_t* points_xy, const uint8_t* scalars_be, size_t n) {
+  if (!ctx || ((!points_xy || !scalars_be) && n)) return BPGPU_E_ARG;
   BP_CUDA_OK(cudaSetDevice(ctx->device));
   size_t psz = (ctx->curve == BPGPU_BLS12_381) ? sizeof(Affine<Bls::Fq>) : sizeof(Affine<Bn::Fq>);
   int rc = ctx->msm_d.reserve(n * psz + 32);
@@ -682,7 +712,8 @@ int bpgpu_msm_refs(bpgpu_ctx* ctx, const uint8_t* points_xy, const uint8_t* scal
   if ((rc = ctx->msm_c.reserve(n * 32 + 32))) return rc;
   // Scalars first: the digit / sort stages need only them.  For large n the points follow on the copy queue, so their
   // transfer and conversion run under k_digits / k_scan / k_scatter; k_chunk_acc waits for `points_ready`.
-  // (Every entry point returns with the ctx idle, so the staging buffers are free when we get here.)
+  // (Every entry point returns with the ctx idle or with ONE pending MSM whose finish precedes the next begin, so the
+  // staging buffers are free when we get here.)
   const bool overlap = n >= ((size_t)1 << 14);
 #define CALL(C) scalars_upload_t<C>(ctx, scalars_be, n, 0, ctx->msm_c.p, ctx->io_dev2)
   rc = DISPATCH(ctx, CALL);
@@ -696,12 +727,43 @@ int bpgpu_msm_refs(bpgpu_ctx* ctx, const uint8_t* points_xy, const uint8_t* scal
     BP_CUDA_OK(cudaEventRecord(ctx->points_ready, ctx->copy_stream));
     ctx->wait_points = true;
   }
-  rc = msm_to_host(ctx, ctx->msm_d.p, ctx->msm_c.p, false, n, out_xy);
-  if (ctx->wait_points) {                  // msm_run did not get as far as the wait (error path): drain the copy queue
+  rc = msm_mixed_begin(ctx, nullptr, 0, ctx->msm_d.p, ctx->msm_c.p, false, n);
+  if (rc && ctx->wait_points) {            // msm_run did not get as far as the wait (error path): drain the copy queue
     ctx->wait_points = false;
     cudaStreamSynchronize(ctx->copy_stream);
   }
   return rc;
+}
+
+int bpgpu_msm_finish(bpgpu_ctx* ctx, uint8_t* out_xy) {
+  if (!ctx || !out_xy) return BPGPU_E_ARG;
+  BP_CUDA_OK(cudaSetDevice(ctx->device));
+  return msm_mixed_finish(ctx, out_xy);
+}
+
+int bpgpu_msm(bpgpu_ctx* ctx, const bpgpu_points* p, size_t off, size_t n, const uint8_t* scalars_be, uint8_t* out_xy) {
+  if (!out_xy) return BPGPU_E_ARG;
+  int rc = bpgpu_msm_begin(ctx, p, off, n, scalars_be);
+  return rc ? rc : bpgpu_msm_finish(ctx, out_xy);
+}
+
+int bpgpu_msm_le32(bpgpu_ctx* ctx, const bpgpu_points* p, size_t off, size_t n, const uint8_t* scalars_le32, uint8_t* out_xy) {
+  if (!out_xy) return BPGPU_E_ARG;
+  int rc = bpgpu_msm_le32_begin(ctx, p, off, n, scalars_le32);
+  return rc ? rc : bpgpu_msm_finish(ctx, out_xy);
+}
+
+int bpgpu_msm_device(bpgpu_ctx* ctx, const bpgpu_points* p, size_t poff, size_t n, const bpgpu_scalars* s, size_t soff,
+                     uint8_t* out_xy) {
+  if (!out_xy) return BPGPU_E_ARG;
+  int rc = bpgpu_msm_device_begin(ctx, p, poff, n, s, soff);
+  return rc ? rc : bpgpu_msm_finish(ctx, out_xy);
+}
+
+int bpgpu_msm_refs(bpgpu_ctx* ctx, const uint8_t* points_xy, const uint8_t* scalars_be, size_t n, uint8_t* out_xy) {
+  if (!out_xy) return BPGPU_E_ARG;
+  int rc = bpgpu_msm_refs_begin(ctx, points_xy, scalars_be, n);
+  return rc ? rc : bpgpu_msm_finish(ctx, out_xy);
 }
 
 // ------------------------------------------------------------------ self tests

@@ -60,6 +60,7 @@ struct bpgpu_ctx {
   bool blocking_sync = false;
   cudaEvent_t sync_event = nullptr;
   uint64_t launches = 0;
+  struct { bool active = false; int W = 0, c = 0, qshift = 0, hp = 0; size_t tn = 0; } pending;   // an MSM begun, not finished (api.cu)
   bool fixed_schedule = false;    // table sums with a fixed trip count per term (secret scalars): bpgpu_ctx_set_fixed_schedule
   // MSM scratch
   bp::Scratch msm_a, msm_b, msm_c, msm_d, msm_e, io_dev, io_dev2;

@@ -294,3 +294,48 @@ def test_fixed_schedule_table_sums_give_the_same_bytes(which, bp, ctx_bls, ctx_b
     finally:
         bp.lib().bph_set_secret_fixed_schedule(0)
     assert got == ref and comms2 == comms
+
+
+@pytest.mark.parametrize("which", ["bls", "bn"])
+def test_msm_begin_finish_pipelined_over_two_contexts(which, bp, ctx_bls, ctx_bn):
+    """bpgpu_msm_*_begin / bpgpu_msm_finish: two MSMs in flight on two contexts of one device, all four input forms, with
+    and without window tables; one MSM in flight per context (a second begin is an argument error)"""
+    ctx = ctx_bls if which == "bls" else ctx_bn
+    C = curve_of(ctx)
+    other = bp.Context(ctx.curve, 0)
+    n = 3000
+    P = rand_points(C, n, 12)
+    xy = enc_points(C, P)
+    dp = ctx.upload_points(xy)
+    tab = ctx.upload_points(xy[:200 * 2 * C.MODBYTES]).precompute()
+    sets = [C.synth_scalars(50 + k, n) for k in range(4)]
+    exp = [C.g1_xy_bytes(C.msm(P, s)) for s in sets]
+    ds = [ctx.upload_scalars(enc_scalars(C, s)) for s in sets[:2]]
+    ctx.msm_device_begin(dp, ds[0])
+    other.msm_device_begin(dp, ds[1])                      # the points live on ctx; any context of the device may read them
+    with pytest.raises(Exception):
+        ctx.msm_device_begin(dp, ds[1])
+    assert ctx.msm_finish() == exp[0]
+    assert other.msm_finish() == exp[1]
+    with pytest.raises(Exception):
+        ctx.msm_finish()                                   # nothing pending
+    sb2, sb3 = enc_scalars(C, sets[2]), enc_scalars(C, sets[3])
+    ctx.msm_begin(dp, sb2)
+    other.msm_refs_begin(xy, sb3)
+    assert other.msm_finish() == exp[3]
+    assert ctx.msm_finish() == exp[2]
+    le = b"".join(x.to_bytes(32, "little") for x in sets[0])
+    ctx.msm_le32_begin(dp, le)
+    other.msm_begin(tab, sb2[:200 * C.MODBYTES])           # table path
+    assert ctx.msm_finish() == exp[0]
+    assert other.msm_finish() == C.g1_xy_bytes(C.msm(P[:200], sets[2][:200]))
+    # an invalid point surfaces at finish
+    bad = bytearray(xy)
+    bad[5] ^= 1
+    other.msm_refs_begin(bytes(bad), sb3)
+    with pytest.raises(bp.BpgpuError) as e:
+        other.msm_finish()
+    assert e.value.code == -5
+    other.close()
+    dp.free()
+    tab.free()
