@@ -236,6 +236,115 @@ __global__ void __launch_bounds__(128) k_ipp_verify_scalars(uint32_t N, int lg, 
   }
 }
 
+// ---- hybrid for large N in table mode: the folded generators ARE materialised, once ----
+// While G and H are the original generators every round costs N + 1 table terms per side whatever n_cur is.  After k rounds
+//     G'[j] = sum_{t < 2^k} sG[t * n_cur + j] * G[t * n_cur + j]      (H' likewise, Q = q_scalar * base)
+// is 2 n_cur + 1 table sums of 2^k terms (32 N additions in all: one more round), and from then on L and R are MSMs over
+// the 2 n_cur + 1 materialised points (bucket pipeline, coefficient vectors = 1).  Same group elements, same proof bytes.
+template <class Fr>
+__global__ void __launch_bounds__(128) k_ipp_mat_scalars(uint32_t N, uint32_t n_cur, Fr* __restrict__ sG, Fr* __restrict__ sH,
+                                                         const Fr* __restrict__ wq, Fr* __restrict__ canon) {
+  const uint32_t i = blockIdx.x * blockDim.x + threadIdx.x;
+  if (i == 0) store_vec(canon + 2 * (size_t)N, load_vec(wq).from_mont());
+  if (i >= N) return;
+  store_vec(canon + i, load_vec(sG + i).from_mont());
+  store_vec(canon + N + i, load_vec(sH + i).from_mont());
+  if (i < n_cur) { store_vec(sG + i, Fr::one()); store_vec(sH + i, Fr::one()); }
+}
+
+// one warp per materialised point: lane w adds the entries of byte-window w of the point's 2^k terms, five tree levels
+template <class Curve>
+__global__ void __launch_bounds__(128) k_ipp_materialise(uint32_t N, uint32_t n_cur, const void* __restrict__ tG, const void* __restrict__ tH,
+                                                         const void* __restrict__ tQ, const typename Curve::Fr* __restrict__ canon,
+                                                         XYZZ<typename Curve::Fq>* __restrict__ out) {
+  using Fq = typename Curve::Fq;
+  __shared__ __align__(16) unsigned char smraw[128 * sizeof(XYZZ<Fq>)];
+  XYZZ<Fq>* sm = reinterpret_cast<XYZZ<Fq>*>(smraw);
+  const uint32_t rows = 2 * n_cur + 1;
+  const uint32_t r = blockIdx.x * 4 + (threadIdx.x >> 5), w = threadIdx.x & 31;
+  XYZZ<Fq> acc = XYZZ<Fq>::inf();
+  if (r < rows) {
+    const bool isq = r == 2 * n_cur, ish = r >= n_cur;
+    const Affine<Fq>* tb = (const Affine<Fq>*)(isq ? tQ : ish ? tH : tG);
+    const uint32_t j = isq ? 0 : ish ? r - n_cur : r;
+    const typename Curve::Fr* sc = canon + (isq ? 2 * (size_t)N : ish ? (size_t)N : 0);
+    const uint32_t step = isq ? 1 : n_cur, terms = isq ? 1 : N / n_cur;
+#pragma unroll 1
+    for (uint32_t t = 0; t < terms; t++) {
+      const uint32_t i = t * step + j;
+      const uint32_t d = (sc[i].v[w / TBL_PER_LIMB] >> ((w % TBL_PER_LIMB) * TBL_BITS)) & (uint32_t)TBL_DIGITS;
+      if (d) acc.madd(load_vec_ro(tb + ((size_t)i * TBL_WINDOWS + w) * TBL_DIGITS + (d - 1)));
+    }
+  }
+  store_vec(sm + threadIdx.x, acc);
+  __syncthreads();
+  for (int o = 16; o > 0; o >>= 1) {
+    if ((int)w < o) {
+      XYZZ<Fq> a = load_vec(sm + threadIdx.x), c = load_vec(sm + threadIdx.x + o);
+      a.add(c);
+      store_vec(sm + threadIdx.x, a);
+    }
+    __syncthreads();
+  }
+  if (w == 0 && r < rows) store_vec(out + r, load_vec(sm + threadIdx.x));
+}
+
+// XYZZ -> affine (Montgomery form, the identity as (0, 0)); MAT_NORM points per thread share one inversion
+static const int MAT_NORM = 4;
+template <class Fq>
+__global__ void __launch_bounds__(64) k_ipp_mat_affine(uint32_t rows, const XYZZ<Fq>* __restrict__ src, Affine<Fq>* __restrict__ dst) {
+  const uint32_t r0 = (blockIdx.x * blockDim.x + threadIdx.x) * MAT_NORM;
+  if (r0 >= rows) return;
+  const uint32_t cnt = min((uint32_t)MAT_NORM, rows - r0);
+  Fq pre[MAT_NORM + 1];
+  pre[0] = Fq::one();
+  for (uint32_t i = 0; i < cnt; i++) {
+    const Fq zzz = load_vec(&src[r0 + i].zzz);
+    pre[i + 1] = zzz.is_zero() ? pre[i] : Fq::mulc(pre[i], zzz);
+  }
+  Fq inv = pre[cnt].inv();
+  for (uint32_t i = cnt; i-- > 0;) {
+    const XYZZ<Fq> p = load_vec(src + r0 + i);
+    if (p.is_inf()) { store_vec(dst + r0 + i, Affine<Fq>::inf()); continue; }
+    const Fq i3 = Fq::mulc(inv, pre[i]);                // 1 / zzz
+    inv = Fq::mulc(inv, p.zzz);
+    const Fq i1 = Fq::mulc(i3, p.zz);                   // 1 / z
+    Affine<Fq> a;
+    a.x = Fq::mulc(p.x, Fq::mulc(i1, i1));
+    a.y = Fq::mulc(p.y, i3);
+    store_vec(dst + r0 + i, a);
+  }
+}
+
+// after how many table rounds the generators are materialised (0 = never); BPGPU_IPP_HYBRID / BPGPU_IPP_HYBRID_MIN override
+static int hybrid_rounds(size_t N) {
+  const char *ek = getenv("BPGPU_IPP_HYBRID"), *em = getenv("BPGPU_IPP_HYBRID_MIN");
+  const int k = ek ? atoi(ek) : 3;
+  const size_t nmin = em ? (size_t)atoll(em) : (size_t)8192;
+  return N >= nmin && k > 0 && ((size_t)2 << k) <= N ? k : 0;      // at least one round is left after materialising
+}
+
+template <class Curve>
+static int ipp_materialise_t(bpgpu_ipp* st) {
+  using Fq = typename Curve::Fq;
+  using Fr = typename Curve::Fr;
+  bpgpu_ctx* ctx = st->ctx;
+  const uint32_t N = (uint32_t)st->N, n = (uint32_t)st->n_cur, rows = 2 * n + 1;
+  cudaStream_t s = ctx->stream;
+  const size_t pbytes = ((size_t)rows * sizeof(Affine<Fq>) + 255) & ~(size_t)255;
+  BP_CUDA_OK(dev_alloc(ctx, &st->P, pbytes + (size_t)rows * sizeof(XYZZ<Fq>)));
+  XYZZ<Fq>* sums = (XYZZ<Fq>*)((uint8_t*)st->P + pbytes);
+  Fr* canon = (Fr*)st->sclL;                            // 2N + 1 slots, free between rounds
+  k_ipp_mat_scalars<Fr><<<(N + 127) / 128, 128, 0, s>>>(N, n, (Fr*)st->sG, (Fr*)st->sH, (const Fr*)st->wq, canon);
+  k_ipp_materialise<Curve><<<(rows + 3) / 4, 128, 0, s>>>(N, n, st->tG, st->tH, st->tQ, canon, sums);
+  k_ipp_mat_affine<Fq><<<((rows + MAT_NORM - 1) / MAT_NORM + 63) / 64, 64, 0, s>>>(rows, sums, (Affine<Fq>*)st->P);
+  ctx->launches += 3;
+  st->N = n;                                            // general mode over [G' | H' | Q] from here on
+  st->wq = nullptr;
+  st->tG = st->tH = st->tQ = nullptr;
+  return launch_check(ctx, "ipp_materialise");
+}
+
 template <class Curve>
 static int ipp_begin_t(bpgpu_ipp* st, const bpgpu_points* Gp, size_t goff, const bpgpu_points* Hp, size_t hoff, const uint8_t* Q_xy,
                        const uint8_t* q_base_xy, const uint8_t* q_scalar_be, const void* Gf, const void* Hf, const void* a, const void* b) {
@@ -302,11 +411,24 @@ template <class Curve>
 static int ipp_round_t(bpgpu_ipp* st, uint8_t* L_xy, uint8_t* R_xy) {
   using Fr = typename Curve::Fr;
   bpgpu_ctx* ctx = st->ctx;
-  const uint32_t N = (uint32_t)st->N, n = (uint32_t)st->n_cur;
+  uint32_t N = (uint32_t)st->N;
+  const uint32_t n = (uint32_t)st->n_cur;
   int rc;
   FrArg uc, uic;
   memcpy(uc.v, st->pu, sizeof uc.v);
   memcpy(uic.v, st->pui, sizeof uic.v);
+  const int hk = st->wq ? hybrid_rounds(N) : 0;
+  if (hk > 0 && n <= (N >> hk)) {                       // table rounds are over: materialise, then general mode (below)
+    if (st->pending) {
+      k_ipp_fold<Fr><<<(N + 127) / 128, 128, 0, ctx->stream>>>(N, (uint32_t)st->n_dev, uc, uic, (Fr*)st->a, (Fr*)st->b, (Fr*)st->sG, (Fr*)st->sH,
+                                                               (Fr*)nullptr);
+      ctx->launches++;
+      st->pending = false;
+      st->n_dev = n;
+    }
+    if ((rc = ipp_materialise_t<Curve>(st))) return rc;
+    N = (uint32_t)st->N;
+  }
   if (st->wq && N <= 4096) {
     // small table mode: [fold] + scalar lists + cross products in one launch, both sums in one more (two groups)
     const uint32_t Nh = N >> 1;

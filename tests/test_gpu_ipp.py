@@ -115,3 +115,29 @@ def test_ipp_with_tables_and_arbitrary_q(which, n, ctx_bls, ctx_bn):
         P = C.msm(G + H + [Q], a + b + [C.inner_product(a, b)])
         assert ctx.ipp_verify(b"tab", n, enc_scalars(C, ones), enc_scalars(C, ones), C.g1_xy_bytes(P), C.g1_xy_bytes(Q), dG, dH, got)
         assert not ctx.ipp_verify(b"tab", n, enc_scalars(C, ones), enc_scalars(C, ones), C.g1_xy_bytes(C.dbl(P)), C.g1_xy_bytes(Q), dG, dH, got)
+
+
+@pytest.mark.parametrize("which", ["bls", "bn"])
+@pytest.mark.parametrize("n,k", [(64, 1), (64, 3), (64, 5), (16, 3), (256, 2)])
+def test_ipp_hybrid_materialised_generators(which, n, k, ctx_bls, ctx_bn, monkeypatch):
+    """Large-N table mode materialises the folded generators after k rounds (csrc/ipp.cu "hybrid") and continues on the
+    bucket pipeline over 2 n_k + 1 points.  Forced on at small n here: same L, R, a, b bytes as the oracle, with factor
+    vectors that are not 1 (they are folded into the materialised points) and for Q = identity."""
+    ctx = ctx_bls if which == "bls" else ctx_bn
+    C = curve_of(ctx)
+    monkeypatch.setenv("BPGPU_IPP_HYBRID", str(k))
+    monkeypatch.setenv("BPGPU_IPP_HYBRID_MIN", "2")
+    G, H = C.get_generators("g", n), C.get_generators("h", n)
+    dG, dH = ctx.get_generators("g", n, precompute=True), ctx.get_generators("h", n, precompute=True)
+    a, b = C.synth_scalars(18, n, b"a"), C.synth_scalars(18, n, b"b")
+    gf, hf = C.synth_scalars(18, n, b"gf"), C.synth_scalars(18, n, b"hf")
+    for Q in (C.g1_from_msg_hash(b"Q"), C.INF):
+        exp = oipp.create_ipp(C, Transcript(b"hyb", C), Q, gf, hf, G, H, a, b)
+        want = b"".join(C.g1_to_bytes(p) for p in exp.L) + b"".join(C.g1_to_bytes(p) for p in exp.R) + C.fr_to_bytes(exp.a) + C.fr_to_bytes(exp.b)
+        launches0 = ctx.launches
+        got = ctx.ipp_create(b"hyb", dG, dH, C.g1_xy_bytes(Q), enc_scalars(C, gf), enc_scalars(C, hf), enc_scalars(C, a), enc_scalars(C, b), n)
+        assert got == want
+        assert ctx.launches > launches0
+    # and the switch is what changed the path: with it off the same bytes come from table sums alone
+    monkeypatch.setenv("BPGPU_IPP_HYBRID", "0")
+    assert ctx.ipp_create(b"hyb", dG, dH, C.g1_xy_bytes(Q), enc_scalars(C, gf), enc_scalars(C, hf), enc_scalars(C, a), enc_scalars(C, b), n) == want
