@@ -306,7 +306,9 @@ int table_sum_run(bpgpu_ctx* ctx, const TableSeg* segs, int nsegs, int ngroups, 
   const uint32_t items = maxtotal * 8;
   const uint32_t bs = TS_THREADS;
   uint32_t blocks = (items + bs - 1) / bs;
-  const uint32_t cap = (uint32_t)ctx->sm_count * 8;
+  static const uint32_t per_sm = [] { const char* e = getenv("BPGPU_TS_BLOCKS_PER_SM"); return e ? (uint32_t)atoi(e) : 4u; }();
+  uint32_t cap = (uint32_t)ctx->sm_count * per_sm / (uint32_t)ngroups;      // all groups together: one resident wave
+  if (cap == 0) cap = 1;
   if (blocks > cap) blocks = cap;
   if (blocks == 0) blocks = 1;
   int rc = ctx->tbl_part.reserve(((size_t)blocks * ngroups + TBL_MAX_GROUPS) * sizeof(XYZZ<Fq>));

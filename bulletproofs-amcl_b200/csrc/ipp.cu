@@ -252,7 +252,10 @@ __global__ void __launch_bounds__(128) k_ipp_mat_scalars(uint32_t N, uint32_t n_
   if (i < n_cur) { store_vec(sG + i, Fr::one()); store_vec(sH + i, Fr::one()); }
 }
 
-// one warp per materialised point: lane w adds the entries of byte-window w of the point's 2^k terms, five tree levels
+// MAT_LANES lanes per materialised point: lane q adds the entries of byte-windows q, q + MAT_LANES, ... of the point's 2^k
+// terms (a chain of 32 / MAT_LANES * 2^k mixed additions), then log2(MAT_LANES) tree levels.  Few lanes per point keep the
+// tree (dependent FULL additions on half, a quarter, ... of the lanes) a small share of the work.
+static const int MAT_LANES = 8;
 template <class Curve>
 __global__ void __launch_bounds__(128) k_ipp_materialise(uint32_t N, uint32_t n_cur, const void* __restrict__ tG, const void* __restrict__ tH,
                                                          const void* __restrict__ tQ, const typename Curve::Fr* __restrict__ canon,
@@ -261,7 +264,7 @@ __global__ void __launch_bounds__(128) k_ipp_materialise(uint32_t N, uint32_t n_
   __shared__ __align__(16) unsigned char smraw[128 * sizeof(XYZZ<Fq>)];
   XYZZ<Fq>* sm = reinterpret_cast<XYZZ<Fq>*>(smraw);
   const uint32_t rows = 2 * n_cur + 1;
-  const uint32_t r = blockIdx.x * 4 + (threadIdx.x >> 5), w = threadIdx.x & 31;
+  const uint32_t r = blockIdx.x * (128 / MAT_LANES) + threadIdx.x / MAT_LANES, q = threadIdx.x % MAT_LANES;
   XYZZ<Fq> acc = XYZZ<Fq>::inf();
   if (r < rows) {
     const bool isq = r == 2 * n_cur, ish = r >= n_cur;
@@ -272,21 +275,24 @@ __global__ void __launch_bounds__(128) k_ipp_materialise(uint32_t N, uint32_t n_
 #pragma unroll 1
     for (uint32_t t = 0; t < terms; t++) {
       const uint32_t i = t * step + j;
-      const uint32_t d = (sc[i].v[w / TBL_PER_LIMB] >> ((w % TBL_PER_LIMB) * TBL_BITS)) & (uint32_t)TBL_DIGITS;
-      if (d) acc.madd(load_vec_ro(tb + ((size_t)i * TBL_WINDOWS + w) * TBL_DIGITS + (d - 1)));
+#pragma unroll 1
+      for (uint32_t w = q; w < (uint32_t)TBL_WINDOWS; w += MAT_LANES) {
+        const uint32_t d = (sc[i].v[w / TBL_PER_LIMB] >> ((w % TBL_PER_LIMB) * TBL_BITS)) & (uint32_t)TBL_DIGITS;
+        if (d) acc.madd(load_vec_ro(tb + ((size_t)i * TBL_WINDOWS + w) * TBL_DIGITS + (d - 1)));
+      }
     }
   }
   store_vec(sm + threadIdx.x, acc);
   __syncthreads();
-  for (int o = 16; o > 0; o >>= 1) {
-    if ((int)w < o) {
+  for (int o = MAT_LANES / 2; o > 0; o >>= 1) {
+    if ((int)q < o) {
       XYZZ<Fq> a = load_vec(sm + threadIdx.x), c = load_vec(sm + threadIdx.x + o);
       a.add(c);
       store_vec(sm + threadIdx.x, a);
     }
     __syncthreads();
   }
-  if (w == 0 && r < rows) store_vec(out + r, load_vec(sm + threadIdx.x));
+  if (q == 0 && r < rows) store_vec(out + r, load_vec(sm + threadIdx.x));
 }
 
 // XYZZ -> affine (Montgomery form, the identity as (0, 0)); MAT_NORM points per thread share one inversion
@@ -319,7 +325,7 @@ __global__ void __launch_bounds__(64) k_ipp_mat_affine(uint32_t rows, const XYZZ
 // after how many table rounds the generators are materialised (0 = never); BPGPU_IPP_HYBRID / BPGPU_IPP_HYBRID_MIN override
 static int hybrid_rounds(size_t N) {
   const char *ek = getenv("BPGPU_IPP_HYBRID"), *em = getenv("BPGPU_IPP_HYBRID_MIN");
-  const int k = ek ? atoi(ek) : 3;
+  const int k = ek ? atoi(ek) : 4;
   const size_t nmin = em ? (size_t)atoll(em) : (size_t)8192;
   return N >= nmin && k > 0 && ((size_t)2 << k) <= N ? k : 0;      // at least one round is left after materialising
 }
@@ -336,7 +342,7 @@ static int ipp_materialise_t(bpgpu_ipp* st) {
   XYZZ<Fq>* sums = (XYZZ<Fq>*)((uint8_t*)st->P + pbytes);
   Fr* canon = (Fr*)st->sclL;                            // 2N + 1 slots, free between rounds
   k_ipp_mat_scalars<Fr><<<(N + 127) / 128, 128, 0, s>>>(N, n, (Fr*)st->sG, (Fr*)st->sH, (const Fr*)st->wq, canon);
-  k_ipp_materialise<Curve><<<(rows + 3) / 4, 128, 0, s>>>(N, n, st->tG, st->tH, st->tQ, canon, sums);
+  k_ipp_materialise<Curve><<<(rows * MAT_LANES + 127) / 128, 128, 0, s>>>(N, n, st->tG, st->tH, st->tQ, canon, sums);
   k_ipp_mat_affine<Fq><<<((rows + MAT_NORM - 1) / MAT_NORM + 63) / 64, 64, 0, s>>>(rows, sums, (Affine<Fq>*)st->P);
   ctx->launches += 3;
   st->N = n;                                            // general mode over [G' | H' | Q] from here on
