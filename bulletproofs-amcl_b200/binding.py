@@ -59,6 +59,9 @@ SYMBOLS = [
     ("bpgpu_circuit_multipliers", _SZ, [_VP]),
     ("bpgpu_circuit_commitments", _SZ, [_VP]),
     ("bpgpu_circuit_flatten", _INT, [_VP, _VP, _VP, _c.POINTER(_VP)]),
+    ("bpgpu_ctx_circuit_put", _INT, [_VP, _c.c_uint64, _VP]),
+    ("bpgpu_ctx_circuit_get", _VP, [_VP, _c.c_uint64]),
+    ("bpgpu_range_witness", _INT, [_VP, _c.POINTER(_c.c_uint64), _SZ, _SZ, _c.POINTER(_VP)]),
     ("bpgpu_r1cs_verify_batch", _INT, [_VP, _VP, _VP, _VP, _VP, _VP, _SZ, _VP, _SZ, _VP, _VP, _VP, _VP, _SZ, _VP]),
     ("bpgpu_r1cs_verify_batch_terms", _INT, [_VP, _VP, _VP, _VP, _VP, _VP, _SZ, _VP, _SZ, _VP, _VP, _VP, _VP, _SZ, _VP, _VP, _VP]),
     ("bpgpu_pbatch_create", _INT, [_VP, _VP, _VP, _VP, _VP, _SZ, _SZ, _c.POINTER(_VP)]),
@@ -477,6 +480,14 @@ class Context:
         return lib().bpgpu_ctx_launches(self.handle)
 
     STAGES = ["digits", "scan", "scatter", "chunk_acc", "giant", "merge", "reduce_l1", "reduce_l2"]
+
+    def range_witness(self, values, bits):
+        """[a_L | a_R | a_O] of len(values) positive_no gadgets, built on the device (DeviceScalars of 3 * m * bits entries)"""
+        m = len(values)
+        arr = (ctypes.c_uint64 * m)(*values)
+        h = ctypes.c_void_p()
+        self._check(lib().bpgpu_range_witness(self.handle, arr, m, bits, ctypes.byref(h)), "range_witness")
+        return DeviceScalars(self, h)
 
     def set_fixed_schedule(self, on):
         """table-path MSMs of this context with a fixed trip count per term (secret scalars)"""

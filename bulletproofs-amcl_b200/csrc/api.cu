@@ -480,6 +480,8 @@ void bpgpu_ctx_destroy(bpgpu_ctx* c) {
   if (c->stream) cudaStreamSynchronize(c->stream);
   for (bpgpu_fixed_bases* fb : c->fb_cache) bpgpu_fixed_bases_free(fb);
   c->fb_cache.clear();
+  for (auto& kv : c->circuit_cache) bpgpu_circuit_free(kv.second);
+  c->circuit_cache.clear();
   c->msm_a.release(); c->msm_b.release(); c->msm_c.release(); c->msm_d.release(); c->msm_e.release();
   c->io_dev.release(); c->io_dev2.release();
   c->ipp_pts.release(); c->ipp_scl.release(); c->parts_pts.release(); c->parts_scl.release(); c->tbl_part.release();

@@ -77,6 +77,7 @@ struct bpgpu_ctx {
   uint64_t stage_runs = 0;
   std::vector<bpgpu_fixed_bases*> fb_cache;   // ctx-owned fixed-base tables (fixedbase.cu)
   bpgpu_ctx* aux = nullptr;       // a second context on the same device, owned by this one (bpgpu_ctx_aux): the other driver of a batch call
+  std::vector<std::pair<uint64_t, bpgpu_circuit*>> circuit_cache;   // recorded circuits kept with the ctx (bpgpu_ctx_circuit_put)
 };
 
 struct bpgpu_points {

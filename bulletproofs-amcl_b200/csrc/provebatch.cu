@@ -775,6 +775,31 @@ int bpgpu_pbatch_prove_range(bpgpu_pbatch* pb, const bpgpu_circuit* circuit, con
 #undef CALL
 }
 
+// the multiplier assignments of m positive_no gadgets (positive_no.rs:18-24) for ONE proof, built on the device from the values
+int bpgpu_range_witness(bpgpu_ctx* ctx, const uint64_t* values, size_t m, size_t bits, bpgpu_scalars** out) {
+  if (!ctx || !values || !out || !m || !bits || bits > 64 || m > ((size_t)1 << 22)) return BPGPU_E_ARG;
+  *out = nullptr;
+  BP_CUDA_OK(cudaSetDevice(ctx->device));
+  const size_t n = m * bits;
+  int rc = bpgpu_scalars_alloc(ctx, 3 * n, out);
+  if (rc) return rc;
+  void* dv = nullptr;
+  if (dev_alloc(ctx, &dv, m * sizeof(uint64_t)) != cudaSuccess ||
+      cudaMemcpyAsync(dv, values, m * sizeof(uint64_t), cudaMemcpyHostToDevice, ctx->stream) != cudaSuccess) {
+    dev_free(ctx, dv); bpgpu_scalars_free(*out); *out = nullptr;
+    return BPGPU_E_CUDA;
+  }
+  if (ctx->curve == BPGPU_BLS12_381)
+    k_pd_witness<Bls::Fr><<<(unsigned)((n + 127) / 128), 128, 0, ctx->stream>>>(1, (uint32_t)m, (uint32_t)bits, (const uint64_t*)dv, (Bls::Fr*)(*out)->d);
+  else
+    k_pd_witness<Bn::Fr><<<(unsigned)((n + 127) / 128), 128, 0, ctx->stream>>>(1, (uint32_t)m, (uint32_t)bits, (const uint64_t*)dv, (Bn::Fr*)(*out)->d);
+  ctx->launches++;
+  dev_free(ctx, dv);
+  rc = launch_check(ctx, "k_pd_witness");
+  if (rc) { bpgpu_scalars_free(*out); *out = nullptr; }
+  return rc;
+}
+
 int bpgpu_pbatch_commit3(bpgpu_pbatch* pb, const uint8_t* witness_be, const uint8_t* keys, size_t key_len, const uint64_t* ctr0,
                          const uint8_t* blind_be, uint8_t* out_xy) {
   if (!pb || !witness_be || !keys || !ctr0 || !blind_be || !out_xy || key_len > 64) return BPGPU_E_ARG;

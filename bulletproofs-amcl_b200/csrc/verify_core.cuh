@@ -210,12 +210,12 @@ BP_HD int vb_from_challenges(const uint8_t* chal_be, const uint8_t* proof, uint3
   return vb_header_finish<Curve>(proof, lg, y, z, u, x, w, r, uk, hdr);
 }
 
-// one row of the flattened constraint matrices times the powers of z: sum_e coeff_e * z^(q_e + 1)
+// entries [lo, hi) of the flattened constraint matrices times the powers of z, every `step`-th one: sum_e coeff_e * z^(q_e + 1)
 template <class Fr>
-BP_HD Fr csr_row_eval(const CircuitDev& c, uint32_t row, const Fr* ztab) {
+BP_HD Fr csr_span_eval(const CircuitDev& c, uint32_t lo, uint32_t hi, uint32_t step, const Fr* ztab) {
   Fr acc = Fr::zero();
   const Fr* ec = (const Fr*)c.ent_c;
-  for (uint32_t e = c.row_start[row]; e < c.row_start[row + 1]; e++) {
+  for (uint32_t e = lo; e < hi; e += step) {
     const uint32_t q = c.ent_q[e];
     const Fr zp = hd_pow_tab(ztab, (q & CSR_QMASK) + 1);
     if (q & CSR_PLUS) acc = acc + zp;
@@ -223,6 +223,12 @@ BP_HD Fr csr_row_eval(const CircuitDev& c, uint32_t row, const Fr* ztab) {
     else acc = acc + ec[e] * zp;
   }
   return acc;
+}
+// one row (a variable's weight; the LAST row, the constants, has one entry per constraint with a constant: kernels split it
+// over a block with csr_span_eval)
+template <class Fr>
+BP_HD Fr csr_row_eval(const CircuitDev& c, uint32_t row, const Fr* ztab) {
+  return csr_span_eval(c, c.row_start[row], c.row_start[row + 1], 1u, ztab);
 }
 
 // x^(2^k), k < 32

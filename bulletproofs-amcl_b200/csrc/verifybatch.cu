@@ -89,17 +89,25 @@ __global__ void __launch_bounds__(128) k_vb_scalars(const __grid_constant__ Circ
     store_vec(f + N + i, h.from_mont());
     dsum = dsum + d;
   }
-  store_vec(red + threadIdx.x, dsum);
-  __syncthreads();
-  for (int o = blockDim.x / 2; o > 0; o >>= 1) {
-    if ((int)threadIdx.x < o) store_vec(red + threadIdx.x, load_vec(red + threadIdx.x) + load_vec(red + threadIdx.x + o));
+  // the constants row has an entry per constraint with a constant term (n of them for range gadgets): split over the block
+  const uint32_t wrow = 3 * c.n + c.m;
+  const Fr wpart = csr_span_eval(c, c.row_start[wrow] + threadIdx.x, c.row_start[wrow + 1], blockDim.x, ztab);
+  auto block_sum = [&](const Fr& mine) {
     __syncthreads();
-  }
+    store_vec(red + threadIdx.x, mine);
+    __syncthreads();
+    for (int o = blockDim.x / 2; o > 0; o >>= 1) {
+      if ((int)threadIdx.x < o) store_vec(red + threadIdx.x, load_vec(red + threadIdx.x) + load_vec(red + threadIdx.x + o));
+      __syncthreads();
+    }
+    return load_vec(red);
+  };
+  const Fr delta = block_sum(dsum);
+  const Fr wc = block_sum(wpart);
   for (uint32_t j = threadIdx.x; j < c.m; j += blockDim.x) store_vec(v + 6 + j, vb_var_wv(c, j, sh, ztab));
   if (threadIdx.x == blockDim.x - 1) {
-    const Fr wc = csr_row_eval(c, 3 * c.n + c.m, ztab);
     Fr fg, fh;
-    vb_head(c.m, lg, sh, load_vec(red), wc, &fg, &fh, v);
+    vb_head(c.m, lg, sh, delta, wc, &fg, &fh, v);
     store_vec(f + 2 * N, fg);
     store_vec(f + 2 * N + 1, fh);
   }
@@ -111,8 +119,21 @@ template <class Fr>
 __global__ void __launch_bounds__(128) k_circuit_flatten(const __grid_constant__ CircuitDev c, const __grid_constant__ ZTab<Fr> ztab,
                                                          Fr* __restrict__ out) {
   const uint32_t row = blockIdx.x * blockDim.x + threadIdx.x;
-  if (row >= 3 * c.n + c.m + 1) return;
+  if (row >= 3 * c.n + c.m) return;                      // the constants row: k_circuit_wc
   store_vec(out + row, csr_row_eval(c, row, ztab.t));
+}
+template <class Fr>
+__global__ void __launch_bounds__(256) k_circuit_wc(const __grid_constant__ CircuitDev c, const __grid_constant__ ZTab<Fr> ztab, Fr* __restrict__ out) {
+  __shared__ __align__(16) unsigned char red_raw[256 * sizeof(Fr)];
+  Fr* red = reinterpret_cast<Fr*>(red_raw);
+  const uint32_t wrow = 3 * c.n + c.m;
+  store_vec(red + threadIdx.x, csr_span_eval(c, c.row_start[wrow] + threadIdx.x, c.row_start[wrow + 1], blockDim.x, ztab.t));
+  __syncthreads();
+  for (int o = blockDim.x / 2; o > 0; o >>= 1) {
+    if ((int)threadIdx.x < o) store_vec(red + threadIdx.x, load_vec(red + threadIdx.x) + load_vec(red + threadIdx.x + o));
+    __syncthreads();
+  }
+  if (threadIdx.x == 0) store_vec(out + wrow, load_vec(red));
 }
 
 // proofs per group of launches (bounds the scratch: 15 XYZZ multiples per proof point); BPGPU_VB_SLAB overrides (tuning runs)
@@ -202,7 +223,8 @@ static int circuit_flatten_t(bpgpu_ctx* ctx, const bpgpu_circuit* circ, const ui
   for (int k = 0; k < 32; k++) { t[k] = cur; cur = cur.sqr(); }
   const uint32_t rows = 3 * circ->dev.n + circ->dev.m + 1;
   k_circuit_flatten<Fr><<<(rows + 127) / 128, 128, 0, ctx->stream>>>(circ->dev, tab, (Fr*)d_out);
-  ctx->launches++;
+  k_circuit_wc<Fr><<<1, 256, 0, ctx->stream>>>(circ->dev, tab, (Fr*)d_out);
+  ctx->launches += 2;
   return launch_check(ctx, "k_circuit_flatten");
 }
 
@@ -252,6 +274,18 @@ void bpgpu_circuit_free(bpgpu_circuit* c) {
   cudaSetDevice(c->ctx->device);
   dev_free(c->ctx, c->mem);
   delete c;
+}
+
+int bpgpu_ctx_circuit_put(bpgpu_ctx* ctx, uint64_t key, bpgpu_circuit* c) {
+  if (!ctx || !c || c->ctx != ctx) return BPGPU_E_ARG;
+  for (auto& kv : ctx->circuit_cache) if (kv.first == key) return BPGPU_E_ARG;
+  ctx->circuit_cache.emplace_back(key, c);
+  return BPGPU_OK;
+}
+const bpgpu_circuit* bpgpu_ctx_circuit_get(const bpgpu_ctx* ctx, uint64_t key) {
+  if (!ctx) return nullptr;
+  for (auto& kv : ctx->circuit_cache) if (kv.first == key) return kv.second;
+  return nullptr;
 }
 
 size_t bpgpu_circuit_multipliers(const bpgpu_circuit* c) { return c ? c->dev.n : 0; }

@@ -152,6 +152,9 @@ int bound_verify_t(bpgpu_ctx* ctx, const char* label, const uint8_t* g_xy, const
 }
 
 template <class C>
+int range_circuit_csr(size_t m, size_t bits, typename Verifier<C>::CircuitCSR* csr);
+
+template <class C>
 int range_prove_t(bpgpu_ctx* ctx, const char* label, const uint8_t* g_xy, const uint8_t* h_xy, const bpgpu_points* G, const bpgpu_points* H,
                   const uint64_t* values, size_t m, size_t bits, int rng_mode, uint64_t seed, uint8_t* proof, size_t cap, size_t* len,
                   uint8_t* comms_xy) {
@@ -161,7 +164,28 @@ int range_prove_t(bpgpu_ctx* ctx, const char* label, const uint8_t* g_xy, const 
   R1CSProof<C> p;
   std::vector<G1<C>> comms;
   std::vector<uint64_t> vals(values, values + m);
-  int rc = gen_proof_of_positive_nums<C>(ctx, vals, bits, rng, label, G1<C>::from_xy(g_xy), G1<C>::from_xy(h_xy), vG, vH, &p, &comms);
+  int rc;
+  // Large statements: the circuit of (m, bits) is recorded once per context and kept on the device; each proof then builds
+  // its witness and its weights there.  Small ones run the gadget as the reference does: recording
+  // costs more than it saves.  BPH_RANGE_RECORDED=0 / 1 forces one path (the tests compare the two).
+  const char* env = getenv("BPH_RANGE_RECORDED");
+  const int forced = env ? atoi(env) : -1;
+  const bool recorded = forced >= 0 ? forced != 0 : m * bits >= 1024;
+  if (recorded) {
+    const uint64_t key = ((uint64_t)0x5241 << 48) | ((uint64_t)bits << 32) | (uint64_t)m;     // "RA" | bits | m
+    const bpgpu_circuit* circ = bpgpu_ctx_circuit_get(ctx, key);
+    if (!circ) {
+      typename Verifier<C>::CircuitCSR csr;
+      if ((rc = range_circuit_csr<C>(m, bits, &csr))) return rc;
+      bpgpu_circuit* made = nullptr;
+      if ((rc = bpgpu_circuit_create(ctx, csr.n, csr.m, csr.q, csr.row_start.data(), csr.ent_q.data(), csr.ent_c_be.data(), &made))) return rc;
+      if ((rc = bpgpu_ctx_circuit_put(ctx, key, made))) { bpgpu_circuit_free(made); return rc; }
+      circ = made;
+    }
+    rc = gen_proof_of_positive_nums_recorded<C>(ctx, circ, vals, bits, rng, label, G1<C>::from_xy(g_xy), G1<C>::from_xy(h_xy), vG, vH, &p, &comms);
+  } else {
+    rc = gen_proof_of_positive_nums<C>(ctx, vals, bits, rng, label, G1<C>::from_xy(g_xy), G1<C>::from_xy(h_xy), vG, vH, &p, &comms);
+  }
   if (rc) return rc;
   for (size_t k = 0; k < comms.size(); k++) memcpy(comms_xy + k * 2 * C::MODBYTES, comms[k].xy, 2 * C::MODBYTES);
   return emit(p.to_bytes(), proof, cap, len);

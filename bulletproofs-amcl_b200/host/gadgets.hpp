@@ -141,6 +141,31 @@ int gen_proof_of_positive_nums(bpgpu_ctx* ctx, const std::vector<uint64_t>& vals
   return prover.prove(G, H, proof);
 }
 
+// The same proof from a circuit recorded earlier (bpgpu_circuit of m positive_no gadgets) and a witness built on the
+// device: what a caller proving the same statement shape over and over does instead of re-running the gadget per proof.
+// The draws (one blinding per value, then prove()'s) and the transcript are those of gen_proof_of_positive_nums.
+template <class C>
+int gen_proof_of_positive_nums_recorded(bpgpu_ctx* ctx, const bpgpu_circuit* circuit, const std::vector<uint64_t>& vals, size_t bits, Rng<C>& rng,
+                                        const std::string& transcript_label, const G1<C>& g, const G1<C>& h, const G1Vector<C>& G,
+                                        const G1Vector<C>& H, R1CSProof<C>* proof, std::vector<G1<C>>* comms) {
+  using FE = FieldElement<C>;
+  Trace tr("range_prove");
+  Transcript prover_transcript(transcript_label);
+  Prover<C> prover(ctx, g, h, prover_transcript, rng);
+  std::vector<FE> fv, blind;
+  for (uint64_t v : vals) { fv.push_back(FE::from_u64(v)); blind.push_back(rng.next()); }
+  std::vector<Variable> vars;
+  int rc = prover.commit_vec(fv, blind, comms, &vars);
+  if (rc) return rc;
+  bpgpu_scalars* wit = nullptr;
+  if ((rc = bpgpu_range_witness(ctx, vals.data(), vals.size(), bits, &wit))) return rc;
+  tr.mark("commit + device witness");
+  typename Prover<C>::DeviceCircuit dc{circuit, wit, vals.size() * bits};
+  rc = prover.prove(G, H, proof, &dc);
+  bpgpu_scalars_free(wit);
+  return rc;
+}
+
 template <class C>
 int verify_proof_of_positive_nums(bpgpu_ctx* ctx, size_t bits, const R1CSProof<C>& proof, const std::vector<G1<C>>& commitments,
                                   const std::string& transcript_label, const G1<C>& g, const G1<C>& h, const G1Vector<C>& G,

@@ -277,11 +277,23 @@ class Prover : public ConstraintSystem<C> {
     return OK;
   }
 
+  // A one-phase statement whose circuit is already on the device (a bpgpu_circuit recorded once per statement shape) and
+  // whose multiplier assignments [a_L | a_R | a_O] were built there: prove() then never touches LinearCombinations --
+  // no gadget run, no host flattening, no witness upload.  Same transcript, same draws, same proof bytes.
+  struct DeviceCircuit {
+    const bpgpu_circuit* circuit;
+    const bpgpu_scalars* witness;    // 3 * n scalars
+    size_t n;
+  };
+
   // prover.rs:322-593.  G, H are device-resident generator tables of length >= padded_n.
-  int prove(const G1Vector<C>& G, const G1Vector<C>& H, R1CSProof<C>* proof) {
+  int prove(const G1Vector<C>& G, const G1Vector<C>& H, R1CSProof<C>* proof, const DeviceCircuit* dc = nullptr) {
     Trace tr("prove");
+    if (dc && (!a_L_.empty() || !constraints_.empty() || !deferred_.empty() || bpgpu_circuit_multipliers(dc->circuit) != dc->n ||
+               bpgpu_circuit_commitments(dc->circuit) != v_.size()))
+      return E_ARG;
     transcript_.append_u64("m", v_.size());                            // :327
-    const size_t n1 = a_L_.size();
+    const size_t n1 = dc ? dc->n : a_L_.size();
     if (G.len() < n1 || H.len() < n1) return E_INVALID_GENERATORS_LENGTH;   // :332-334
     const FE i_blinding1 = rng_.next(), o_blinding1 = rng_.next(), s_blinding1 = rng_.next();   // :336-338
     int rc;
@@ -289,7 +301,12 @@ class Prover : public ConstraintSystem<C> {
     // polynomial kernels later.  s_L, s_R (:340-341) are DRAWN on the device (FieldElementVector::random as
     // bpgpu_fr_random: the same stream positions n1 + n1 host draws would use), so they never exist on the host.
     FieldElementVector<C> d_aL, d_aR, d_aO, d_sL, d_sR;
-    if ((rc = FieldElementVector<C>::from_host_many(ctx_, {&a_L_, &a_R_, &a_O_}, {&d_aL, &d_aR, &d_aO}))) return rc;
+    if (dc) {
+      FieldElementVector<C> w = FieldElementVector<C>::borrow(ctx_, dc->witness);
+      if ((rc = w.view(0, n1, &d_aL)) || (rc = w.view(n1, n1, &d_aR)) || (rc = w.view(2 * n1, n1, &d_aO))) return rc;
+    } else if ((rc = FieldElementVector<C>::from_host_many(ctx_, {&a_L_, &a_R_, &a_O_}, {&d_aL, &d_aR, &d_aO}))) {
+      return rc;
+    }
     {
       bpgpu_scalars* hs = nullptr;                                     // s_L (:340) then s_R (:341): 2*n1 consecutive draws
       if ((rc = rng_.fill_device(ctx_, 2 * n1, &hs))) return rc;
@@ -307,7 +324,7 @@ class Prover : public ConstraintSystem<C> {
 
     if ((rc = create_randomized_constraints())) return rc;             // :369
 
-    const size_t n = a_L_.size();
+    const size_t n = dc ? n1 : a_L_.size();
     const size_t n2 = n - n1;
     const size_t padded_n = next_power_of_two(n);
     if (G.len() < padded_n || H.len() < padded_n) return E_INVALID_GENERATORS_LENGTH;   // :379-381
@@ -337,12 +354,22 @@ class Prover : public ConstraintSystem<C> {
     const FE y = TP::challenge_scalar(transcript_, "y");               // :438-439
     const FE z = TP::challenge_scalar(transcript_, "z");
     std::vector<FE> wL, wR, wO, wV;
-    flattened_constraints(z, &wL, &wR, &wO, &wV);                      // :441
+    FieldElementVector<C> d_wL, d_wR, d_wO;                            // l(x), r(x) coefficient vectors on the device (:458-486)
+    if (dc) {
+      // the recorded matrix times the powers of z, on the device; only wV (m scalars, for t_2_blinding) comes back
+      uint8_t zb[C::MODBYTES];
+      z.to_bytes(zb);
+      bpgpu_scalars* hw = nullptr;
+      if ((rc = bpgpu_circuit_flatten(ctx_, dc->circuit, zb, &hw))) return rc;
+      FieldElementVector<C> all = FieldElementVector<C>::adopt(ctx_, hw), d_wV;
+      if ((rc = all.view(0, n, &d_wL)) || (rc = all.view(n, n, &d_wR)) || (rc = all.view(2 * n, n, &d_wO)) ||
+          (rc = all.view(3 * n, v_.size(), &d_wV)) || (rc = d_wV.to_host(&wV)))
+        return rc;
+    } else {
+      flattened_constraints(z, &wL, &wR, &wO, &wV);                    // :441
+      if ((rc = FieldElementVector<C>::from_host_many(ctx_, {&wL, &wR, &wO}, {&d_wL, &d_wR, &d_wO}))) return rc;
+    }
     tr.mark("flattened_constraints");
-
-    // l(x), r(x) coefficient vectors on the device (:458-486)
-    FieldElementVector<C> d_wL, d_wR, d_wO;
-    if ((rc = FieldElementVector<C>::from_host_many(ctx_, {&wL, &wR, &wO}, {&d_wL, &d_wR, &d_wO}))) return rc;
     uint8_t yb[C::MODBYTES];
     y.to_bytes(yb);
     bpgpu_scalars *h_l1 = nullptr, *h_r0 = nullptr, *h_r1 = nullptr, *h_r3 = nullptr;

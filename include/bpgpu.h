@@ -178,6 +178,16 @@ void bpgpu_circuit_free(bpgpu_circuit* c);
 size_t bpgpu_circuit_multipliers(const bpgpu_circuit* c);
 size_t bpgpu_circuit_commitments(const bpgpu_circuit* c);
 int bpgpu_circuit_flatten(bpgpu_ctx* ctx, const bpgpu_circuit* c, const uint8_t* z_be, bpgpu_scalars** out);
+/* A recorded circuit kept WITH a context under a caller-chosen key (the host layer keys range statements by (m, bits)):
+ * put hands ownership to the ctx (freed by bpgpu_ctx_destroy; BPGPU_E_ARG if the key is taken or the circuit belongs to
+ * another ctx), get returns NULL when absent.  With it a single proof of a known statement never rebuilds
+ * LinearCombinations on the host: weights come from bpgpu_circuit_flatten (prover.rs:142-184), the witness of a range
+ * statement from bpgpu_range_witness. */
+int bpgpu_ctx_circuit_put(bpgpu_ctx* ctx, uint64_t key, bpgpu_circuit* c);
+const bpgpu_circuit* bpgpu_ctx_circuit_get(const bpgpu_ctx* ctx, uint64_t key);
+/* [a_L | a_R | a_O] (3 * m * bits device scalars) of m positive_no gadgets over `values` (gadgets/positive_no.rs:18-24:
+ * per bit a_L = 1 - bit, a_R = bit, a_O = 0), in the allocation order of the gadget: value-major, least significant bit first */
+int bpgpu_range_witness(bpgpu_ctx* ctx, const uint64_t* values, size_t m, size_t bits, bpgpu_scalars** out);
 /* Verifier::verify (verifier.rs:267-457) for `count` independent proofs of `circuit`: verdicts[i] = BPGPU_OK,
  * BPGPU_E_VERIFY (VerificationError) or BPGPU_E_FORMAT (missing 0x04 tag, scalar >= r, coordinate >= p, point off the
  * curve).  proofs = count records of proof_stride bytes in the flat form A_I1 A_O1 S1 A_I2 A_O2 S2 T_1 T_3 T_4 T_5 T_6

@@ -172,3 +172,51 @@ def test_gpu_two_phase_shuffle_golden(ctx_bls, ctx_bn):
         assert ctx.shuffle_verify(d["label"].encode(), gx, hx, G, H, k, bits, proof, comms) is True
         G.free()
         H.free()
+
+
+@pytest.mark.gpu
+@pytest.mark.parametrize("recorded", ["0", "1"])
+@pytest.mark.parametrize("name,pre", [("range_small.json", False), ("range_config2.json", True), ("range_config3.json", False),
+                                      ("range_config3.json", True)])
+def test_gpu_range_proof_golden_both_prover_paths(name, pre, recorded, ctx_bls, ctx_bn, monkeypatch):
+    """The committed proofs from BOTH single-proof paths of the host layer: the gadget run per proof (as the reference) and the
+    circuit recorded once per context with witness and weights built on the device (BPH_RANGE_RECORDED); with window tables
+    config 3 also goes through the hybrid IPP (generators materialised after 4 table rounds)."""
+    monkeypatch.setenv("BPH_RANGE_RECORDED", recorded)
+    fx = load(name)
+    for _, d in fx.items():
+        ctx = _ctx(d["curve"], ctx_bls, ctx_bn)
+        m, bits = d["m"], d["bits"]
+        n = m * bits
+        N = 1 << max(0, (n - 1).bit_length())
+        dG, dH = ctx.get_generators("G", N, precompute=pre), ctx.get_generators("H", N, precompute=pre)
+        gx, hx = ctx.g1_from_msg_hash(b"g"), ctx.g1_from_msg_hash(b"h")
+        vals = [int(v) for v in d["values"]]
+        for _rep in range(2):                                # the second proof finds the circuit in the context's cache
+            proof, comms = ctx.range_prove(d["label"].encode(), gx, hx, dG, dH, vals, bits, seed=d["seed"])
+            assert comms.hex() == d["commitments"]
+            assert proof.hex() == d["proof"]
+        dG.free()
+        dH.free()
+
+
+@pytest.mark.gpu
+def test_gpu_range_witness_elementwise(ctx_bls, ctx_bn):
+    """bpgpu_range_witness against positive_no.rs:18-24: a_L = 1 - bit, a_R = bit, a_O = 0, value-major, LSB first"""
+    for ctx in (ctx_bls, ctx_bn):
+        mb = 48 if ctx is ctx_bls else 32
+        vals, bits = [0, 1, 0xdeadbeefcafef00d, (1 << 64) - 1, 5], 64
+        w = ctx.range_witness(vals, bits)
+        got = w.download()
+        n = len(vals) * bits
+        assert len(got) == 3 * n * mb
+        for j, v in enumerate(vals):
+            for k in range(bits):
+                bit = (v >> k) & 1
+                i = j * bits + k
+                assert int.from_bytes(got[i * mb:(i + 1) * mb], "big") == 1 - bit
+                assert int.from_bytes(got[(n + i) * mb:(n + i + 1) * mb], "big") == bit
+                assert int.from_bytes(got[(2 * n + i) * mb:(2 * n + i + 1) * mb], "big") == 0
+        w.free()
+        w7 = ctx.range_witness([0x55, 0x7f], 7).download()     # bits < 64: higher bits of the value are ignored, as shift_right(i) for i < n
+        assert [int.from_bytes(w7[(14 + i) * mb:(15 + i) * mb], "big") for i in range(14)] == [1, 0, 1, 0, 1, 0, 1] + [1] * 7
