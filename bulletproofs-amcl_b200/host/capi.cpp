@@ -154,6 +154,27 @@ int bound_verify_t(bpgpu_ctx* ctx, const char* label, const uint8_t* g_xy, const
 template <class C>
 int range_circuit_csr(size_t m, size_t bits, typename Verifier<C>::CircuitCSR* csr);
 
+// Large range statements: the circuit of (m, bits) is recorded once per context and kept on the device; each proof / check then
+// builds its witness and its weights there.  Small ones run the gadget as the reference does: recording
+// costs more than it saves.  BPH_RANGE_RECORDED=0 / 1 forces one path (the tests compare the two).
+static bool range_use_recorded(size_t m, size_t bits) {
+  const char* env = getenv("BPH_RANGE_RECORDED");
+  return env ? atoi(env) != 0 : m * bits >= 1024;
+}
+template <class C>
+int range_circuit_cached(bpgpu_ctx* ctx, size_t m, size_t bits, const bpgpu_circuit** out) {
+  const uint64_t key = ((uint64_t)0x5241 << 48) | ((uint64_t)bits << 32) | (uint64_t)m;     // "RA" | bits | m
+  if ((*out = bpgpu_ctx_circuit_get(ctx, key))) return BPGPU_OK;
+  typename Verifier<C>::CircuitCSR csr;
+  int rc = range_circuit_csr<C>(m, bits, &csr);
+  if (rc) return rc;
+  bpgpu_circuit* made = nullptr;
+  if ((rc = bpgpu_circuit_create(ctx, csr.n, csr.m, csr.q, csr.row_start.data(), csr.ent_q.data(), csr.ent_c_be.data(), &made))) return rc;
+  if ((rc = bpgpu_ctx_circuit_put(ctx, key, made))) { bpgpu_circuit_free(made); return rc; }
+  *out = made;
+  return BPGPU_OK;
+}
+
 template <class C>
 int range_prove_t(bpgpu_ctx* ctx, const char* label, const uint8_t* g_xy, const uint8_t* h_xy, const bpgpu_points* G, const bpgpu_points* H,
                   const uint64_t* values, size_t m, size_t bits, int rng_mode, uint64_t seed, uint8_t* proof, size_t cap, size_t* len,
@@ -165,23 +186,9 @@ int range_prove_t(bpgpu_ctx* ctx, const char* label, const uint8_t* g_xy, const 
   std::vector<G1<C>> comms;
   std::vector<uint64_t> vals(values, values + m);
   int rc;
-  // Large statements: the circuit of (m, bits) is recorded once per context and kept on the device; each proof then builds
-  // its witness and its weights there.  Small ones run the gadget as the reference does: recording
-  // costs more than it saves.  BPH_RANGE_RECORDED=0 / 1 forces one path (the tests compare the two).
-  const char* env = getenv("BPH_RANGE_RECORDED");
-  const int forced = env ? atoi(env) : -1;
-  const bool recorded = forced >= 0 ? forced != 0 : m * bits >= 1024;
-  if (recorded) {
-    const uint64_t key = ((uint64_t)0x5241 << 48) | ((uint64_t)bits << 32) | (uint64_t)m;     // "RA" | bits | m
-    const bpgpu_circuit* circ = bpgpu_ctx_circuit_get(ctx, key);
-    if (!circ) {
-      typename Verifier<C>::CircuitCSR csr;
-      if ((rc = range_circuit_csr<C>(m, bits, &csr))) return rc;
-      bpgpu_circuit* made = nullptr;
-      if ((rc = bpgpu_circuit_create(ctx, csr.n, csr.m, csr.q, csr.row_start.data(), csr.ent_q.data(), csr.ent_c_be.data(), &made))) return rc;
-      if ((rc = bpgpu_ctx_circuit_put(ctx, key, made))) { bpgpu_circuit_free(made); return rc; }
-      circ = made;
-    }
+  if (range_use_recorded(m, bits)) {
+    const bpgpu_circuit* circ = nullptr;
+    if ((rc = range_circuit_cached<C>(ctx, m, bits, &circ))) return rc;
     rc = gen_proof_of_positive_nums_recorded<C>(ctx, circ, vals, bits, rng, label, G1<C>::from_xy(g_xy), G1<C>::from_xy(h_xy), vG, vH, &p, &comms);
   } else {
     rc = gen_proof_of_positive_nums<C>(ctx, vals, bits, rng, label, G1<C>::from_xy(g_xy), G1<C>::from_xy(h_xy), vG, vH, &p, &comms);
@@ -203,6 +210,12 @@ int range_verify_t(bpgpu_ctx* ctx, const char* label, const uint8_t* g_xy, const
   G1Vector<C> vG = G1Vector<C>::borrow(ctx, G), vH = G1Vector<C>::borrow(ctx, H);
   FieldElement<C> vr;
   if ((rc = verifier_scalar<C>(r_be, &vr))) return rc;
+  if (m > ((size_t)1 << 24) || bits > 64) return BPGPU_E_ARG;
+  if (range_use_recorded(m, bits)) {
+    const bpgpu_circuit* circ = nullptr;
+    if ((rc = range_circuit_cached<C>(ctx, m, bits, &circ))) return rc;
+    return verify_proof_of_positive_nums_recorded<C>(ctx, circ, p, comms, label, G1<C>::from_xy(g_xy), G1<C>::from_xy(h_xy), vG, vH, vr);
+  }
   return verify_proof_of_positive_nums<C>(ctx, bits, p, comms, label, G1<C>::from_xy(g_xy), G1<C>::from_xy(h_xy), vG, vH, vr);
 }
 

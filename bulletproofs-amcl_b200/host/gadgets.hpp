@@ -182,6 +182,19 @@ int verify_proof_of_positive_nums(bpgpu_ctx* ctx, size_t bits, const R1CSProof<C
   return verifier.verify(proof, g, h, G, H, verifier_r);
 }
 
+// the verifier's side of gen_proof_of_positive_nums_recorded: commitments into the transcript, weights from the recorded circuit
+template <class C>
+int verify_proof_of_positive_nums_recorded(bpgpu_ctx* ctx, const bpgpu_circuit* circuit, const R1CSProof<C>& proof,
+                                           const std::vector<G1<C>>& commitments, const std::string& transcript_label, const G1<C>& g,
+                                           const G1<C>& h, const G1Vector<C>& G, const G1Vector<C>& H, const FieldElement<C>& verifier_r) {
+  Trace tr("range_verify");
+  Transcript verifier_transcript(transcript_label);
+  Verifier<C> verifier(ctx, verifier_transcript);
+  for (const auto& com : commitments) verifier.commit(com);
+  tr.mark("commit");
+  return verifier.verify(proof, g, h, G, H, verifier_r, circuit);
+}
+
 // k-shuffle: {y} is a permutation of {x}.  The TWO-PHASE gadget of the reference's ConstraintSystem documentation
 // (constraint_system.rs:86-135): the challenge z exists only after the first-phase commitments A_I1, A_O1, S1, and
 // prod (x_i - z) = prod (y_i - z) costs 2(k-1) second-phase multipliers -- the path through

@@ -603,9 +603,16 @@ class Verifier : public ConstraintSystem<C> {
 
   // verifier.rs:267-457.  `r` is the verifier's random batching scalar (FieldElement::random(), :392).
   // Returns OK, E_VERIFICATION or E_INVALID_GENERATORS_LENGTH.
-  int verify(const R1CSProof<C>& proof, const G1<C>& g, const G1<C>& h, const G1Vector<C>& G, const G1Vector<C>& H, const FE& r) {
+  // `recorded`: the statement's circuit already on the device (a one-phase bpgpu_circuit with as many commitments as this
+  // verifier holds); no gadget has been run against this verifier, the weights come from bpgpu_circuit_flatten.
+  int verify(const R1CSProof<C>& proof, const G1<C>& g, const G1<C>& h, const G1Vector<C>& G, const G1Vector<C>& H, const FE& r,
+             const bpgpu_circuit* recorded = nullptr) {
     bool is_identity = false;
-    int rc = verification_msm(proof, g, h, G, H, r, &is_identity);
+    if (recorded) {
+      if (num_vars_ || !constraints_.empty() || !deferred_.empty() || bpgpu_circuit_commitments(recorded) != V_.size()) return E_ARG;
+      num_vars_ = bpgpu_circuit_multipliers(recorded);
+    }
+    int rc = verification_msm(proof, g, h, G, H, r, &is_identity, recorded);
     if (rc) return rc;
     return is_identity ? OK : E_VERIFICATION;                          // :453-456
   }
@@ -812,7 +819,7 @@ class Verifier : public ConstraintSystem<C> {
 
  private:
   int verification_msm(const R1CSProof<C>& proof, const G1<C>& g, const G1<C>& h, const G1Vector<C>& G, const G1Vector<C>& H, const FE& rnd,
-                       bool* is_identity) {
+                       bool* is_identity, const bpgpu_circuit* recorded = nullptr) {
     const size_t mb = C::MODBYTES;
     Trace tr("verify");
     Challenges ch;
@@ -823,7 +830,21 @@ class Verifier : public ConstraintSystem<C> {
     std::vector<FE> wL, wR, wO, wV;
     FE wc;
     tr.mark("transcript");
-    flattened_constraints(z, &wL, &wR, &wO, &wV, &wc);                 // :325
+    FieldElementVector<C> d_wL, d_wR, d_wO;
+    if (recorded) {                                                    // :325 on the device; wV and wc (m + 1 scalars) come back
+      uint8_t zb[C::MODBYTES];
+      z.to_bytes(zb);
+      bpgpu_scalars* hw = nullptr;
+      if ((rc = bpgpu_circuit_flatten(ctx_, recorded, zb, &hw))) return rc;
+      FieldElementVector<C> all = FieldElementVector<C>::adopt(ctx_, hw), d_tail;
+      if ((rc = all.view(0, n, &d_wL)) || (rc = all.view(n, n, &d_wR)) || (rc = all.view(2 * n, n, &d_wO)) ||
+          (rc = all.view(3 * n, V_.size() + 1, &d_tail)) || (rc = d_tail.to_host(&wV)))
+        return rc;
+      wc = wV.back();
+      wV.pop_back();
+    } else {
+      flattened_constraints(z, &wL, &wR, &wO, &wV, &wc);               // :325
+    }
     tr.mark("flattened_constraints");
     const FE a = proof.ipp_proof.a, b = proof.ipp_proof.b;
 
@@ -834,8 +855,7 @@ class Verifier : public ConstraintSystem<C> {
 
     tr.mark("ipp scalars");
     // g_scalars | h_scalars and delta on the device (:341-390)
-    FieldElementVector<C> d_wL, d_wR, d_wO;
-    if ((rc = FieldElementVector<C>::from_host_many(ctx_, {&wL, &wR, &wO}, {&d_wL, &d_wR, &d_wO}))) return rc;
+    if (!recorded && (rc = FieldElementVector<C>::from_host_many(ctx_, {&wL, &wR, &wO}, {&d_wL, &d_wR, &d_wO}))) return rc;
     uint8_t yb[C::MODBYTES], xb[C::MODBYTES], ab[C::MODBYTES], bb[C::MODBYTES], ub[C::MODBYTES], deltab[C::MODBYTES];
     y.to_bytes(yb); x.to_bytes(xb); a.to_bytes(ab); b.to_bytes(bb); u.to_bytes(ub);
     bpgpu_scalars* h_gh = nullptr;

@@ -196,6 +196,15 @@ def test_gpu_range_proof_golden_both_prover_paths(name, pre, recorded, ctx_bls, 
             proof, comms = ctx.range_prove(d["label"].encode(), gx, hx, dG, dH, vals, bits, seed=d["seed"])
             assert comms.hex() == d["commitments"]
             assert proof.hex() == d["proof"]
+        label = d["label"].encode()
+        assert ctx.range_verify(label, gx, hx, dG, dH, m, bits, proof, comms) is True
+        bad = bytearray(proof)
+        bad[-1] ^= 1                                         # the IPP's b
+        assert ctx.range_verify(label, gx, hx, dG, dH, m, bits, bytes(bad), comms) is False
+        if m > 1:                                            # commitments swapped: another statement
+            mb2 = len(comms) // m
+            swapped = comms[mb2:2 * mb2] + comms[:mb2] + comms[2 * mb2:]
+            assert ctx.range_verify(label, gx, hx, dG, dH, m, bits, proof, swapped) is False
         dG.free()
         dH.free()
 
