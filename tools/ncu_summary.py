@@ -16,6 +16,8 @@ COMMANDS = {
     "launches_verify_batch_%s.csv" % R: "VB_MODES=0 BPH_VB_DRIVERS=1 python tools/verify_batch_bench.py 4096 (one range_prove_batch call to make the proofs, "
                                         "then bph_range_verify_batch x 3)",
     "launches_prove_batch_%s.csv" % R: "python tools/prove_batch_bench.py 2048 1 64 bls 2 0 (bph_range_prove_batch x 2, device transcripts, one verify)",
+    "launches_config3_%s.csv" % R: "python tools/proof_trace.py 256 bn 1 (config 3: two bph_range_prove + one bph_range_verify at n = 2^14 on BN254, "
+                                   "window tables (k_fb_*: one-off set-up), recorded circuit, hybrid IPP)",
 }
 MSM = ("k_digits", "k_scan", "k_scatter", "k_chunk", "k_giant", "k_merge", "k_reduce")
 
