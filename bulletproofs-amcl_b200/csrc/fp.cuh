@@ -32,6 +32,9 @@
 #ifndef BP_FQ_SPLIT
 #define BP_FQ_SPLIT 0
 #endif
+#ifndef BP_SQR_DEDICATED
+#define BP_SQR_DEDICATED 1
+#endif
 
 namespace bp {
 
@@ -175,7 +178,109 @@ struct Fp {
     return r;
   }
 
+#if BP_SQR_DEDICATED
+  BP_HD Fp sqr() const { return sqr_t(*this); }
+#else
   BP_HD Fp sqr() const { return (*this) * (*this); }
+#endif
+
+  // Dedicated squaring: the N(N-1)/2 products above the diagonal once, doubled, plus the N squares (N(N+1)/2 wide
+  // multiply-adds instead of N^2), as a 2N-limb integer T; then N reduction rows on T's low half (the row of mul_t without
+  // the a*b_i part: the one-limb shift rides the accumulate of m*p) and ONE addition of T's high half:
+  // REDC(T_lo + 2^(32N) T_hi) = REDC(T_lo) + T_hi < 2p.  222 + 12 multiply-adds instead of 288 + 12 for the 12-limb field.
+  BP_HD static Fp sqr_t(const Fp& a) {
+    static_assert(N % 2 == 0, "even limb count");
+    uint32_t EV[2 * N], OD[2 * N];          // EV[k]: limb position k ; OD[k]: position k + 1
+#pragma unroll
+    for (int k = 0; k < 2 * N; k++) { EV[k] = 0; OD[k] = 0; }
+#pragma unroll
+    for (int i = 0; i < N - 1; i++) {
+      {                                      // j = i+1, i+3, ...: i + j odd -> OD[i+j-1], OD[i+j]
+        CarryChain c;
+        int p = i + (i + 1) - 1;
+        OD[p] = c.mad_lo_cc(a.v[i], a.v[i + 1], OD[p]);
+        OD[p + 1] = c.madc_hi_cc(a.v[i], a.v[i + 1], OD[p + 1]);
+#pragma unroll
+        for (int j = i + 3; j < N; j += 2) {
+          p = i + j - 1;
+          OD[p] = c.madc_lo_cc(a.v[i], a.v[j], OD[p]);
+          OD[p + 1] = c.madc_hi_cc(a.v[i], a.v[j], OD[p + 1]);
+        }
+        OD[p + 2] = c.addc(OD[p + 2], 0);    // lands on a limb that holds only earlier rows' carries so far
+      }
+      if (i + 2 < N) {                       // j = i+2, i+4, ...: i + j even -> EV[i+j], EV[i+j+1]
+        CarryChain c;
+        int p = i + (i + 2);
+        EV[p] = c.mad_lo_cc(a.v[i], a.v[i + 2], EV[p]);
+        EV[p + 1] = c.madc_hi_cc(a.v[i], a.v[i + 2], EV[p + 1]);
+#pragma unroll
+        for (int j = i + 4; j < N; j += 2) {
+          p = i + j;
+          EV[p] = c.madc_lo_cc(a.v[i], a.v[j], EV[p]);
+          EV[p + 1] = c.madc_hi_cc(a.v[i], a.v[j], EV[p + 1]);
+        }
+        EV[p + 2] = c.addc(EV[p + 2], 0);
+      }
+    }
+    {                                        // double both halves of the triangle (the total is < 2^(64N-1))
+      CarryChain c, d;
+      EV[0] = c.add_cc(EV[0], EV[0]);
+#pragma unroll
+      for (int k = 1; k < 2 * N - 1; k++) EV[k] = c.addc_cc(EV[k], EV[k]);
+      EV[2 * N - 1] = c.addc(EV[2 * N - 1], EV[2 * N - 1]);
+      OD[0] = d.add_cc(OD[0], OD[0]);
+#pragma unroll
+      for (int k = 1; k < 2 * N - 1; k++) OD[k] = d.addc_cc(OD[k], OD[k]);
+      OD[2 * N - 1] = d.addc(OD[2 * N - 1], OD[2 * N - 1]);
+    }
+    {                                        // the diagonal: a_i^2 at position 2i
+      CarryChain c;
+      EV[0] = c.mad_lo_cc(a.v[0], a.v[0], EV[0]);
+      EV[1] = c.madc_hi_cc(a.v[0], a.v[0], EV[1]);
+#pragma unroll
+      for (int i = 1; i < N - 1; i++) {
+        EV[2 * i] = c.madc_lo_cc(a.v[i], a.v[i], EV[2 * i]);
+        EV[2 * i + 1] = c.madc_hi_cc(a.v[i], a.v[i], EV[2 * i + 1]);
+      }
+      EV[2 * N - 2] = c.madc_lo_cc(a.v[N - 1], a.v[N - 1], EV[2 * N - 2]);
+      EV[2 * N - 1] = c.madc_hi(a.v[N - 1], a.v[N - 1], EV[2 * N - 1]);      // a^2 < 2^(64N): no carry out
+    }
+    uint32_t hi[N], ev[N], od[N];
+    {                                        // T = EV + 2^32 OD as ONE integer: low half -> the window, high half kept
+      CarryChain c;
+      ev[0] = EV[0];
+      ev[1] = c.add_cc(EV[1], OD[0]);
+#pragma unroll
+      for (int k = 2; k < N; k++) ev[k] = c.addc_cc(EV[k], OD[k - 1]);
+#pragma unroll
+      for (int k = 0; k < N - 1; k++) hi[k] = c.addc_cc(EV[N + k], OD[N + k - 1]);
+      hi[N - 1] = c.addc(EV[2 * N - 1], OD[2 * N - 2]);
+#pragma unroll
+      for (int k = 0; k < N; k++) od[k] = 0;
+    }
+    reduce_row<0>(ev, od);
+#pragma unroll
+    for (int i = 1; i < N; i++) {
+      if (i & 1) redc_row(od, ev); else redc_row(ev, od);
+    }
+    Fp r;
+    {
+      uint32_t* e = ((N - 1) & 1) ? od : ev;   // accumulator with limb 0 == 0
+      uint32_t* o = ((N - 1) & 1) ? ev : od;
+      CarryChain c;
+      r.v[0] = c.add_cc(o[0], e[1]);
+#pragma unroll
+      for (int k = 1; k < N - 1; k++) r.v[k] = c.addc_cc(o[k], e[k + 1]);
+      r.v[N - 1] = c.addc(o[N - 1], 0);
+      CarryChain d;
+      r.v[0] = d.add_cc(r.v[0], hi[0]);
+#pragma unroll
+      for (int k = 1; k < N - 1; k++) r.v[k] = d.addc_cc(r.v[k], hi[k]);
+      r.v[N - 1] = d.addc(r.v[N - 1], hi[N - 1]);
+    }
+    reduce_once(r.v);
+    return r;
+  }
 
   // The same products as REAL CALLS on the device.  An inlined product is ~400 straight-line instructions (6 KB); a
   // group addition built from inlined products is ~90 KB of code that a latency-bound kernel (tree levels, the bucket
@@ -308,7 +413,30 @@ struct Fp {
     odd[N - 1] = e.addc(odd[N - 1], 0);
   }
 
-  // m = even[0] * (-p^-1); even += p_even*m (clears even[0]); odd += p_odd*m
+  // a reduction row WITH the one-limb shift (roles as in mul_row): even := previous odd accumulator, odd := previous even
+  // accumulator (limb 0 cleared) two limbs down; m from the new limb 0; even += p_even*m, odd = shifted odd + p_odd*m
+  BP_HD static void redc_row(uint32_t* even, uint32_t* odd) {
+    CarryChain c;
+    even[0] = c.add_cc(even[0], odd[1]);                 // carry -> position 1 = first limb of the odd chain
+    const uint32_t m = even[0] * P::INV;
+#pragma unroll
+    for (int j = 0; j < N - 2; j += 2) {
+      odd[j] = c.madc_lo_cc(P::PC(j + 1), m, odd[j + 2]);
+      odd[j + 1] = c.madc_hi_cc(P::PC(j + 1), m, odd[j + 3]);
+    }
+    odd[N - 2] = c.madc_lo_cc(P::PC(N - 1), m, 0);
+    odd[N - 1] = c.madc_hi(P::PC(N - 1), m, 0);
+    CarryChain d;
+    even[0] = d.mad_lo_cc(P::PC(0), m, even[0]);
+    even[1] = d.madc_hi_cc(P::PC(0), m, even[1]);
+#pragma unroll
+    for (int j = 2; j < N; j += 2) {
+      even[j] = d.madc_lo_cc(P::PC(j), m, even[j]);
+      even[j + 1] = d.madc_hi_cc(P::PC(j), m, even[j + 1]);
+    }
+    odd[N - 1] = d.addc(odd[N - 1], 0);                  // position N lives in odd[N-1]
+  }
+
   template <int SP>
   BP_HD static void reduce_row(uint32_t* even, uint32_t* odd) {
     const uint32_t m = even[0] * P::INV;

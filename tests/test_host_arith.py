@@ -37,7 +37,11 @@ def test_montgomery_schedule(hc, fid, p, n):
         hc.hc_fp_op(fid, o, _L(a, n), _L(b, n), out)
         return _I(out)
     edge = [0, 1, p - 1, R % p, p - 2, (1 << (32 * n - 1)) % p]
-    vals = edge + [rnd.randrange(p) for _ in range(120)]
+    # carry-heavy operands for the dedicated squaring (fp.cuh sqr_t): runs of 0xffffffff limbs, single high limbs, p/2
+    carry = [(R - 1) % p, (1 << (32 * (n - 1))) - 1, ((1 << (32 * (n - 1))) - 1) ^ 0xffffffff, p >> 1, (p >> 1) + 1,
+             ((1 << 32) - 1) << (32 * (n - 2)), sum(0xffffffff << (64 * k) for k in range(n // 2)) % p,
+             sum(0xffffffff << (64 * k + 32) for k in range(n // 2)) % p]
+    vals = edge + carry + [rnd.randrange(p) for _ in range(400)]
     Rinv = pow(R, -1, p)
     for a in vals:
         for b in rnd.sample(vals, 4) + edge:
