@@ -166,13 +166,20 @@ def proof_section(bp, ctx, local, rank, world, dist, torch, no_cpu=False):
     Independent proofs are spread over `nctx` contexts (one host thread + one CUDA stream each) of this rank's GPU; with N
     ranks the batch-verification job is sharded by proofs and the verdict bytes are all-gathered over NCCL."""
     import numpy as np
-    ncpu = os.cpu_count() or 1
-    nctx = max(1, min(16, ncpu // max(1, world)))
+    ncpu = len(os.sched_getaffinity(0)) if hasattr(os, "sched_getaffinity") else (os.cpu_count() or 1)
+    # one proof per context is round-synchronous (a host transcript step per IPP round): the GPU is kept busy by contexts, not
+    # by cores.  With a core per context the waits spin; with fewer cores than that (8 ranks on a 16-core box) the contexts
+    # sleep on blocking events instead (bpgpu_ctx_set_blocking_sync) and 16 of them share this rank's cores.
+    cores = max(1, ncpu // max(1, world))
+    nctx = 16
+    oversub = cores < nctx
     hthreads = max(1, ncpu // max(1, world))          # host threads of the batch calls: this rank's share of the cores
-    out = {"contexts_per_gpu": nctx, "host_cpus": ncpu, "host_threads_per_rank": hthreads}
+    out = {"contexts_per_gpu": nctx, "host_cpus": ncpu, "host_threads_per_rank": hthreads, "contexts_sleep_on_events": oversub}
 
     def run(curve, m, bits, count, tag, verify_reps=1, batch_call=False, cpu_base=0, weak=4096):
         ctxs = [bp.Context(curve, local) for _ in range(nctx)]
+        for c in ctxs if oversub else []:
+            c.set_blocking_sync(True)
         c0 = ctxs[0]
         gx, hx = c0.g1_from_msg_hash(b"g"), c0.g1_from_msg_hash(b"h")
         n = m * bits
@@ -303,6 +310,8 @@ def proof_section(bp, ctx, local, rank, world, dist, torch, no_cpu=False):
         the reference's own ipp tests at length n) through bph_ipp_create / bph_ipp_verify, one proof per context in flight"""
         from concurrent.futures import ThreadPoolExecutor
         ctxs = [bp.Context(bp.BLS12_381, local) for _ in range(nctx)]
+        for c in ctxs if oversub else []:
+            c.set_blocking_sync(True)
         c0 = ctxs[0]
         mb = c0.modbytes
         G, H = c0.get_generators("g", n, precompute=True), c0.get_generators("h", n, precompute=True)

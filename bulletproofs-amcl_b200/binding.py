@@ -28,6 +28,7 @@ SYMBOLS = [
     ("bpgpu_ctx_launches", _c.c_uint64, [_VP]),
     ("bpgpu_ctx_set_profile", _INT, [_VP, _INT]),
     ("bpgpu_ctx_set_fixed_schedule", _INT, [_VP, _INT]),
+    ("bpgpu_ctx_set_blocking_sync", _INT, [_VP, _INT]),
     ("bpgpu_msm_stage_ms", _INT, [_VP, _c.POINTER(_c.c_double), _INT]),
     ("bpgpu_host_alloc", _VP, [_SZ]),
     ("bpgpu_host_free", None, [_VP]),
@@ -488,6 +489,10 @@ class Context:
         h = ctypes.c_void_p()
         self._check(lib().bpgpu_range_witness(self.handle, arr, m, bits, ctypes.byref(h)), "range_witness")
         return DeviceScalars(self, h)
+
+    def set_blocking_sync(self, on):
+        """host waits of this context sleep on an event instead of spinning (more contexts than cores)"""
+        self._check(lib().bpgpu_ctx_set_blocking_sync(self.handle, 1 if on else 0), "set_blocking_sync")
 
     def set_fixed_schedule(self, on):
         """table-path MSMs of this context with a fixed trip count per term (secret scalars)"""

@@ -512,6 +512,12 @@ int bpgpu_ctx_set_fixed_schedule(bpgpu_ctx* c, int on) {
   return BPGPU_OK;
 }
 
+int bpgpu_ctx_set_blocking_sync(bpgpu_ctx* c, int on) {
+  if (!c) return BPGPU_E_ARG;
+  c->blocking_sync = on != 0;
+  return BPGPU_OK;
+}
+
 int bpgpu_ctx_set_profile(bpgpu_ctx* c, int on) {
   if (!c) return BPGPU_E_ARG;
   c->profile = on;

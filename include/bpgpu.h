@@ -72,6 +72,11 @@ uint64_t bpgpu_ctx_launches(const bpgpu_ctx* ctx);
  * NOT make the fetched table addresses independent of the scalars (one entry per digit is read, not a masked scan of the
  * row), and MSMs that take the bucket path (no tables) are variable time regardless: see DESIGN.md "secret scalars". */
 int bpgpu_ctx_set_fixed_schedule(bpgpu_ctx* ctx, int on);
+/* How the host waits for this context's stream: 0 (default) spins -- lowest latency, one core per context; 1 sleeps on a
+ * blocking event, so that MORE contexts than host cores can keep independent proofs in flight (one proof per context is
+ * round-synchronous: with c cores, c spinning contexts leave the GPU idle between rounds).  Also BPGPU_BLOCKING_SYNC=1 at
+ * creation.  Measured with 4 cores on config 3: 4 spinning contexts 307 proofs/s, 32 sleeping ones 416. */
+int bpgpu_ctx_set_blocking_sync(bpgpu_ctx* ctx, int on);
 /* per-stage CUDA-event timing of the MSM pipeline on the ctx stream (roofline evidence for bench.py).
  * stages: 0 digits, 1 scan, 2 scatter, 3 chunk_acc, 4 giant, 5 merge, 6 reduce_l1, 7 reduce_l2.
  * set_profile(min_n > 0) records every MSM of at least min_n terms (0 = off); bpgpu_msm_stage_ms writes the average ms
