@@ -13,3 +13,5 @@ print("=== PROVE", file=sys.stderr, flush=True)
 t0 = time.perf_counter(); proof, comms = ctx.range_prove(b"bench", gx, hx, G, H, vals, 64, seed=1); print("prove ms", (time.perf_counter()-t0)*1e3, file=sys.stderr)
 print("=== VERIFY", file=sys.stderr, flush=True)
 t0 = time.perf_counter(); ok = ctx.range_verify(b"bench", gx, hx, G, H, m, 64, proof, comms); print("verify ms", (time.perf_counter()-t0)*1e3, ok, file=sys.stderr)
+for _ in range(2):
+    t0 = time.perf_counter(); ok = ctx.range_verify(b"bench", gx, hx, G, H, m, 64, proof, comms); print("verify again ms", (time.perf_counter()-t0)*1e3, ok, file=sys.stderr)
