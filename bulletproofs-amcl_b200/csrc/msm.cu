@@ -15,8 +15,8 @@
 //                   each, whatever the bucket sizes are -> no divergence between lanes and no
 //                   serialisation on a hot bucket (0/1 witness scalars put half of all points
 //                   in one bucket: helper_constraints/positive_no.rs:18-24)
-//   k_giant         buckets spanning > T chunks: block-wide tree reduction, collapsed in place
-//   k_merge         one thread per chunk boundary a bucket straddles: its partial sums folded into one
+//   k_merge         one thread per chunk boundary a bucket straddles: its partial sums folded into one; the extra blocks of
+//                   the same launch collapse buckets spanning > T chunks with a block-wide tree (giant_blocks)
 //   k_reduce_l1     one WARP per 32*L1 buckets: lanes run top-down running sums over their buckets
 //                   (two additions per bucket), then a warp suffix-scan turns them into sum (b-base)*B_b
 //   k_reduce_l2     per window: combine the segment results (two warps)
@@ -42,7 +42,7 @@ struct MsmGeom {
   int lgL2;         // log2(segments per lane) in k_reduce_l2
 };
 
-static const int GIANT_T = 16;         // buckets with more partials than this are collapsed by k_giant (a block tree: ~9 dependent additions)
+static const int GIANT_T = 16;         // buckets with more partials than this are collapsed by giant_blocks (a block tree: ~9 dependent additions)
 static const int GIANT_BLOCK = 128;
 
 int msm_window_bits(size_t n) {
@@ -239,13 +239,13 @@ __device__ __forceinline__ XYZZ<Fq> block_tree_sum(XYZZ<Fq> v, XYZZ<Fq>* sm) {
 // scalars) are collapsed by a whole block: the total goes to the bucket's first partial slot and
 // the bucket's partial count becomes 1, so k_reduce_l1 reads at most GIANT_T partials per bucket.
 template <class Fq>
-__global__ void __launch_bounds__(GIANT_BLOCK) k_giant(MsmGeom g, const uint32_t* __restrict__ pstart, uint32_t* __restrict__ pcount,
-                                                       XYZZ<Fq>* __restrict__ partials,
-                                                       const uint32_t* __restrict__ giant_count, const uint32_t* __restrict__ giant_list) {
+__device__ __forceinline__ void giant_blocks(uint32_t first, uint32_t stride, MsmGeom g, const uint32_t* __restrict__ pstart,
+                                             uint32_t* __restrict__ pcount, XYZZ<Fq>* __restrict__ partials,
+                                             const uint32_t* __restrict__ giant_count, const uint32_t* __restrict__ giant_list) {
   __shared__ __align__(16) unsigned char smraw[GIANT_BLOCK * sizeof(XYZZ<Fq>)];
   XYZZ<Fq>* sm = reinterpret_cast<XYZZ<Fq>*>(smraw);
   const uint32_t ng = *giant_count;
-  for (uint32_t gi = blockIdx.x; gi < ng; gi += gridDim.x) {
+  for (uint32_t gi = first; gi < ng; gi += stride) {
     const uint32_t gid = giant_list[gi];
     const uint32_t w = gid / g.nbp, b = gid - w * g.nbp;
     const uint32_t* ps = pstart + (size_t)w * (g.nbp + 1);
@@ -263,12 +263,21 @@ __global__ void __launch_bounds__(GIANT_BLOCK) k_giant(MsmGeom g, const uint32_t
 // reduction folds them into ONE sum per bucket, in place at the bucket's first partial slot, with full parallelism: the
 // thread of the chunk in which the bucket STARTS does it, and only if the bucket continues into the next chunk (so a
 // thread has at most one bucket to fold, and -- the chunk length being about two buckets -- almost always exactly one
-// addition: no divergence, W * n / S independent threads).  k_giant has already collapsed the > GIANT_T cases.
+// addition: no divergence, W * n / S independent threads).  The > GIANT_T cases belong to the giant blocks.
 // Afterwards pcount[b] is 0 or 1 for every bucket and k_reduce_l1 is two additions per bucket with no inner loop.
+// ONE launch does both: blocks [0, merge_blocks) fold the straddling buckets, the blocks after them collapse the giant
+// buckets (the two sets of buckets are disjoint: a merging thread leaves a bucket with more than GIANT_T partials alone
+// whether or not its giant block has already finished), so a small MSM does not wait for a block tree before it merges.
 template <class Fq>
-__global__ void __launch_bounds__(128) k_merge(MsmGeom g, const uint32_t* __restrict__ bstart,
+__global__ void __launch_bounds__(128) k_merge(MsmGeom g, uint32_t merge_blocks, const uint32_t* __restrict__ bstart,
                                                const uint32_t* __restrict__ pstart, uint32_t* __restrict__ pcount,
-                                               XYZZ<Fq>* __restrict__ partials) {
+                                               XYZZ<Fq>* __restrict__ partials, const uint32_t* __restrict__ giant_count,
+                                               const uint32_t* __restrict__ giant_list) {
+  static_assert(GIANT_BLOCK == 128, "one block shape for both roles");
+  if (blockIdx.x >= merge_blocks) {
+    giant_blocks<Fq>(blockIdx.x - merge_blocks, gridDim.x - merge_blocks, g, pstart, pcount, partials, giant_count, giant_list);
+    return;
+  }
   const uint32_t gid = blockIdx.x * blockDim.x + threadIdx.x;
   if (gid >= (uint32_t)g.W * g.nchunk) return;
   const uint32_t w = gid / g.nchunk, t = gid - w * g.nchunk;
@@ -280,7 +289,7 @@ __global__ void __launch_bounds__(128) k_merge(MsmGeom g, const uint32_t* __rest
   if (bs[b + 1] <= e1 || bs[b] / g.S != t) return;          // no straddle, or the bucket began in an earlier chunk
   uint32_t* pc = pcount + (size_t)w * g.nbp;
   const uint32_t np = pc[b];
-  if (np <= 1) return;                                      // collapsed by k_giant
+  if (np <= 1 || np > (uint32_t)GIANT_T) return;            // nothing to fold, or a giant block's bucket (collapsed there, maybe already)
   XYZZ<Fq>* in = partials + (size_t)w * g.pcap + pstart[(size_t)w * (g.nbp + 1) + b];
   XYZZ<Fq> acc = load_vec(in);
   for (uint32_t k = 1; k < np; k++) { XYZZ<Fq> q = load_vec(in + k); acc.add(q); }   // one addition per thread: compact code, see Fp::mulc
@@ -512,11 +521,11 @@ int msm_run(bpgpu_ctx* ctx, const Affine<typename Curve::Fq>* d_points, const vo
     k_chunk_acc<Fq><<<(threads + 127) / 128, 128, 0, st>>>(g, d_points, sidx, bstart, pstart, partials);
     tm.mark("chunk_acc");
   }
-  k_giant<Fq><<<ctx->sm_count * 2, GIANT_BLOCK, 0, st>>>(g, pstart, hist, partials, giant, giant + 1);
-  tm.mark("giant");
+  tm.mark("giant");                          // (kept as a stage name: its work now rides the merge launch)
   {
     uint32_t threads = (uint32_t)g.W * g.nchunk;
-    k_merge<Fq><<<(threads + 127) / 128, 128, 0, st>>>(g, bstart, pstart, hist, partials);
+    const uint32_t mb = (threads + 127) / 128;
+    k_merge<Fq><<<mb + (uint32_t)ctx->sm_count * 2, 128, 0, st>>>(g, mb, bstart, pstart, hist, partials, giant, giant + 1);
   }
   tm.mark("merge");
   const int qshift = 5 + g.lgL1;
@@ -527,7 +536,7 @@ int msm_run(bpgpu_ctx* ctx, const Affine<typename Curve::Fq>* d_points, const vo
     k_reduce_l2<Fq><<<g.W, 64, 0, st>>>(g, segA, segS, winsum, winsum + g.W);
     tm.mark("reduce_l2");
   }
-  ctx->launches += 8;
+  ctx->launches += 7;
   res->W = g.W0; res->c = g.c; res->qshift = qshift; res->d_winsum = winsum;    // P at [0, nsets*W), Q at [nsets*W, 2*nsets*W)
   int lrc = launch_check(ctx, "msm");
   tm.report(g, ctx);
