@@ -357,7 +357,8 @@ __global__ void __launch_bounds__(128) k_reduce_l1(MsmGeom g, const uint32_t* __
     }
   }
   warp_weighted_sum(acc, run, g.lgL1);
-  if (lane == 0) { store_vec(segA + warp, acc); store_vec(segS + warp, run); }
+  // callers with ONE segment per window pass segA = the window sums P_w and segS = Q_w (weight 0: the identity): no level 2
+  if (lane == 0) { store_vec(segA + warp, acc); store_vec(segS + warp, g.nseg == 1 ? XYZZ<Fq>::inf() : run); }
 }
 
 
@@ -531,12 +532,19 @@ int msm_run(bpgpu_ctx* ctx, const Affine<typename Curve::Fq>* d_points, const vo
   const int qshift = 5 + g.lgL1;
   {
     uint32_t warps = (uint32_t)g.W * g.nseg;
-    k_reduce_l1<Fq><<<(warps * 32 + 127) / 128, 128, 0, st>>>(g, pstart, hist, partials, segA, segS);
-    tm.mark("reduce_l1");
-    k_reduce_l2<Fq><<<g.W, 64, 0, st>>>(g, segA, segS, winsum, winsum + g.W);
-    tm.mark("reduce_l2");
+    if (g.nseg == 1) {                         // small windows: level 1 writes the window sums itself
+      k_reduce_l1<Fq><<<(warps * 32 + 127) / 128, 128, 0, st>>>(g, pstart, hist, partials, winsum, winsum + g.W);
+      tm.mark("reduce_l1");
+      tm.mark("reduce_l2");
+    } else {
+      k_reduce_l1<Fq><<<(warps * 32 + 127) / 128, 128, 0, st>>>(g, pstart, hist, partials, segA, segS);
+      tm.mark("reduce_l1");
+      k_reduce_l2<Fq><<<g.W, 64, 0, st>>>(g, segA, segS, winsum, winsum + g.W);
+      tm.mark("reduce_l2");
+      ctx->launches += 1;
+    }
   }
-  ctx->launches += 7;
+  ctx->launches += 6;
   res->W = g.W0; res->c = g.c; res->qshift = qshift; res->d_winsum = winsum;    // P at [0, nsets*W), Q at [nsets*W, 2*nsets*W)
   int lrc = launch_check(ctx, "msm");
   tm.report(g, ctx);
