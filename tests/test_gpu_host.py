@@ -327,3 +327,32 @@ def test_device_transcript_batch_prover_warp_rows(which, bp, ctx_bls, ctx_bn):
     assert bp.range_verify_batch(ctx, b"Warp", gx, hx, dG, dH, count, m, bits, got_p, stride, got_c) == [0] * count
     for c in ctxs[1:]:
         c.close()
+
+
+@pytest.mark.gpu
+def test_padded_large_circuit_same_bytes_on_every_prover_path(ctx_bn, monkeypatch):
+    """m = 100 values x 64 bits = 6400 multipliers, padded to N = 8192 (prover.rs:527-535) on BN254 with window tables: the
+    proof bytes do not depend on the path -- gadget per proof or recorded circuit (BPH_RANGE_RECORDED), every IPP round on
+    table sums or generators materialised after 4 rounds (BPGPU_IPP_HYBRID) -- and the verifier (its own MSM path) accepts
+    them on both of its paths; a tampered value commitment is rejected."""
+    ctx = ctx_bn
+    m, bits = 100, 64
+    N = 8192
+    gx, hx = ctx.g1_from_msg_hash(b"g"), ctx.g1_from_msg_hash(b"h")
+    dG, dH = ctx.get_generators("G", N, precompute=True), ctx.get_generators("H", N, precompute=True)
+    vals = [(0x9E3779B97F4A7C15 * (i + 1)) & ((1 << 64) - 1) for i in range(m)]
+    seen = set()
+    for rec in ("0", "1"):
+        for hyb in ("0", "4", "2"):
+            monkeypatch.setenv("BPH_RANGE_RECORDED", rec)
+            monkeypatch.setenv("BPGPU_IPP_HYBRID", hyb)
+            proof, comms = ctx.range_prove(b"padded", gx, hx, dG, dH, vals, bits, seed=77)
+            seen.add((proof, comms))
+            assert ctx.range_verify(b"padded", gx, hx, dG, dH, m, bits, proof, comms) is True
+    assert len(seen) == 1
+    proof, comms = next(iter(seen))
+    mb2 = len(comms) // m
+    swapped = comms[mb2:2 * mb2] + comms[:mb2] + comms[2 * mb2:]
+    assert ctx.range_verify(b"padded", gx, hx, dG, dH, m, bits, proof, swapped) is False
+    dG.free()
+    dH.free()
