@@ -66,7 +66,7 @@ __global__ void __launch_bounds__(256) k_digits(const Fr* __restrict__ scal0, co
   const int set = blockIdx.y;                   // scalar set: its digits are windows [set * W0, (set + 1) * W0)
   const Fr* scal = set ? scal1 : scal0;
   digits += (size_t)set * g.W0 * g.n;
-  hist += (size_t)set * g.W0 * g.nbp;
+  if (hist) hist += (size_t)set * g.W0 * g.nbp;
   Fr s = load_vec(scal + i);
   if (mont) s = s.from_mont();
   uint32_t limbs[9];
@@ -89,7 +89,7 @@ __global__ void __launch_bounds__(256) k_digits(const Fr* __restrict__ scal0, co
     if (d > half) { mag = (mask + 1) - d; sign = 0x80000000u; carry = 1; }
     else { mag = d; sign = 0; carry = 0; }
     digits[(size_t)w * g.n + i] = mag ? (mag | sign) : 0u;
-    if (mag) atomicAdd(&hist[(size_t)w * g.nbp + mag], 1u);
+    if (mag && hist) atomicAdd(&hist[(size_t)w * g.nbp + mag], 1u);
   }
 }
 
@@ -397,6 +397,145 @@ __global__ void __launch_bounds__(64) k_reduce_l2(MsmGeom g, const XYZZ<Fq>* __r
 }
 
 // ------------------------------------------------------------------------------------------
+// SMALL MSMs (n <= SMALL_MAX_N): one block per window does everything after the digits -- counting sort in shared memory,
+// balanced accumulation, folding of the buckets that straddle threads, bucket reduction -- in ONE launch.  The general
+// pipeline above is six launches of latency-bound kernels for such an input (0.27 ms whatever n is); the verification MSM
+// of a proof, the IPP rounds after the generators were materialised and every MSM below a few thousand terms are this shape.
+//   phase 1  histogram of the window's digits, exclusive scan (one warp), scatter of (index | sign) into shared memory
+//   phase 2  thread t accumulates sorted entries [t S, (t+1) S), S = ceil(entries / 256): a run that covers its whole
+//            bucket goes to bsum[b]; a run of a bucket that began in an earlier thread goes to head[t], one that continues
+//            in the next thread to tail[t] (at most one of each per thread)
+//   phase 3  thread b folds bucket b = tail[t0] + head[t0+1 .. t1] when it spans few threads; wider ones (skewed digits,
+//            the short top window) are summed by a warp each
+//   phase 4  warp 0: lanes run top-down sums over their buckets, warp suffix scan (as k_reduce_l1 with one segment)
+static const uint32_t SMALL_MAX_N = 4096;
+static const int SMALL_T = 256;
+static const uint32_t SMALL_SPAN = 6;
+
+template <class Fq>
+__global__ void __launch_bounds__(SMALL_T) k_msm_small(MsmGeom g, const Affine<Fq>* __restrict__ pts, const uint32_t* __restrict__ digits,
+                                                       XYZZ<Fq>* __restrict__ scratch, XYZZ<Fq>* __restrict__ winP, XYZZ<Fq>* __restrict__ winQ) {
+  extern __shared__ uint32_t sm32[];
+  const uint32_t nb = g.nbp - 1, n = g.n, w = blockIdx.x, tid = threadIdx.x;
+  const int lane = tid & 31, wid = tid >> 5;
+  uint32_t* cnt = sm32;                 // [nb + 2]  histogram, then the scatter cursors
+  uint32_t* bs = cnt + nb + 2;          // [nb + 2]  bs[b] = first sorted entry of bucket b (1..nb); bs[nb + 1] = entries
+  uint32_t* wide = bs + nb + 2;         // [nb + 1]  [0] = count, then the buckets left to the warps
+  uint32_t* ent = wide + nb + 1;        // [n]       (index | sign) sorted by bucket
+  const uint32_t* dg = digits + (size_t)w * n;
+  for (uint32_t b = tid; b < nb + 2; b += SMALL_T) cnt[b] = 0;
+  if (tid == 0) wide[0] = 0;
+  __syncthreads();
+  for (uint32_t i = tid; i < n; i += SMALL_T) {
+    const uint32_t d = dg[i];
+    if (d) atomicAdd(&cnt[d & 0x7fffffffu], 1u);
+  }
+  __syncthreads();
+  if (tid < 32) {
+    const uint32_t K = (nb + 31) / 32, lo = 1 + tid * K;
+    uint32_t sum = 0;
+    for (uint32_t k = 0; k < K; k++) if (lo + k <= nb) sum += cnt[lo + k];
+    uint32_t inc = sum;
+#pragma unroll
+    for (int o = 1; o < 32; o <<= 1) {
+      const uint32_t t = __shfl_up_sync(0xffffffffu, inc, o);
+      if (lane >= o) inc += t;
+    }
+    uint32_t run = inc - sum;
+    for (uint32_t k = 0; k < K; k++) if (lo + k <= nb) { bs[lo + k] = run; run += cnt[lo + k]; }
+    if (tid == 31) bs[nb + 1] = inc;
+  }
+  __syncthreads();
+  for (uint32_t b = 1 + tid; b <= nb; b += SMALL_T) cnt[b] = bs[b];
+  __syncthreads();
+  for (uint32_t i = tid; i < n; i += SMALL_T) {
+    const uint32_t d = dg[i];
+    if (d) ent[atomicAdd(&cnt[d & 0x7fffffffu], 1u)] = i | (d & 0x80000000u);
+  }
+  __syncthreads();
+  const uint32_t total = bs[nb + 1];
+  XYZZ<Fq>* head = scratch + (size_t)w * (2 * SMALL_T + g.nbp);
+  XYZZ<Fq>* tail = head + SMALL_T;
+  XYZZ<Fq>* bsum = tail + SMALL_T;      // [nbp], indexed by bucket
+  // chunk length: a thread's chain is S mixed additions, then the bucket's thread folds ~avg / S partial sums (full additions,
+  // 1.4 x the cost): S ~ sqrt(1.4 avg) minimises the sum; never fewer entries per thread than 256 threads need to cover them
+  uint32_t S = (total + SMALL_T - 1) / SMALL_T;
+  {
+    const uint32_t avg14 = (total * 14u) / (10u * (nb ? nb : 1u));          // 1.4 * entries per bucket
+    uint32_t r = 1;
+    while ((r + 1) * (r + 1) <= avg14) r++;
+    if (S < r) S = r;
+    if (S == 0) S = 1;
+  }
+  {
+    const uint32_t e0 = tid * S, e1 = min(e0 + S, total);
+    if (e0 < e1) {
+      uint32_t lo = 1, hi = nb + 1;                   // bs[lo] <= e0 < bs[hi]: the largest such lo is the bucket of e0
+      while (hi - lo > 1) { const uint32_t mid = (lo + hi) >> 1; if (bs[mid] <= e0) lo = mid; else hi = mid; }
+      uint32_t cur = lo, end = bs[cur + 1];
+      XYZZ<Fq> acc = XYZZ<Fq>::inf();
+      for (uint32_t e = e0; e <= e1; e++) {
+        if (e == e1 || e >= end) {                    // the run of bucket `cur` is over: where does it go?
+          if (bs[cur] < e0) store_vec(head + tid, acc);
+          else if (end > e1) store_vec(tail + tid, acc);
+          else store_vec(bsum + cur, acc);
+          if (e == e1) break;
+          acc = XYZZ<Fq>::inf();
+          do { cur++; end = bs[cur + 1]; } while (e >= end);
+        }
+        const uint32_t id = ent[e];
+        Affine<Fq> P = load_vec_ro(pts + (id & 0x7fffffffu));
+        if (id >> 31) P.y = P.y.neg();
+        acc.madd(P);
+      }
+    }
+  }
+  __syncthreads();
+  if (tid >= 1 && tid <= nb) {
+    const uint32_t b = tid, s0 = bs[b], s1 = bs[b + 1];
+    if (s1 > s0) {
+      const uint32_t t0 = s0 / S, t1 = (s1 - 1) / S;
+      if (t1 - t0 > SMALL_SPAN) wide[1 + atomicAdd(&wide[0], 1u)] = b;
+      else if (t1 > t0) {
+        XYZZ<Fq> acc = load_vec(tail + t0);
+        for (uint32_t t = t0 + 1; t <= t1; t++) { XYZZ<Fq> q = load_vec(head + t); acc.add(q); }
+        store_vec(bsum + b, acc);
+      }
+    }
+  }
+  __syncthreads();
+  for (uint32_t gi = wid; gi < wide[0]; gi += SMALL_T / 32) {
+    const uint32_t b = wide[1 + gi], s0 = bs[b], s1 = bs[b + 1];
+    const uint32_t t0 = s0 / S, t1 = (s1 - 1) / S;
+    XYZZ<Fq> acc = XYZZ<Fq>::inf();
+    if (lane == 0) acc = load_vec(tail + t0);
+    for (uint32_t t = t0 + 1 + lane; t <= t1; t += 32) { XYZZ<Fq> q = load_vec(head + t); acc.add(q); }
+#pragma unroll 1
+    for (int o = 16; o > 0; o >>= 1) {
+      XYZZ<Fq> t = shfl_down_xyzz(acc, o);
+      if (lane < o) acc.add(t);
+    }
+    if (lane == 0) store_vec(bsum + b, acc);
+  }
+  __syncthreads();
+  if (wid == 0) {
+    int lgL = 0;
+    while ((32u << lgL) < nb) lgL++;
+    const uint32_t L1 = 1u << lgL, lo = (uint32_t)lane * L1 + 1;
+    XYZZ<Fq> run = XYZZ<Fq>::inf(), acc = XYZZ<Fq>::inf();
+    if (lo <= nb) {
+      const uint32_t hi = min(lo + L1 - 1, nb);
+      for (uint32_t b = hi; b >= lo; b--) {
+        if (bs[b + 1] > bs[b]) { XYZZ<Fq> q = load_vec(bsum + b); run.add(q); }
+        acc.add(run);
+      }
+    }
+    warp_weighted_sum(acc, run, lgL);
+    if (lane == 0) { store_vec(winP + w, acc); store_vec(winQ + w, XYZZ<Fq>::inf()); }
+  }
+}
+
+// ------------------------------------------------------------------------------------------
 static inline size_t align256(size_t x) { return (x + 255) & ~(size_t)255; }
 
 struct StageTimer {
@@ -470,6 +609,36 @@ int msm_run(bpgpu_ctx* ctx, const Affine<typename Curve::Fq>* d_points, const vo
     int lg2 = 0;
     while ((32u << lg2) < g.nseg) lg2++;
     g.lgL2 = lg2;
+  }
+
+  static const bool small_on = !(getenv("BPGPU_SMALL") && atoi(getenv("BPGPU_SMALL")) == 0);
+  if (small_on && n <= SMALL_MAX_N && g.c <= 8) {
+    // ---- small input: digits, then ONE block per window (k_msm_small)
+    const size_t szd = align256((size_t)g.W * n * 4);
+    const size_t szs = align256((size_t)g.W * (2 * SMALL_T + g.nbp) * sizeof(XYZZ<Fq>));
+    const size_t szw = align256((size_t)2 * g.W * sizeof(XYZZ<Fq>));
+    int rc;
+    if ((rc = ctx->msm_a.reserve(szd)) || (rc = ctx->msm_b.reserve(szs + szw))) return rc;
+    uint32_t* digits = (uint32_t*)ctx->msm_a.p;
+    XYZZ<Fq>* scratch = (XYZZ<Fq>*)ctx->msm_b.p;
+    XYZZ<Fq>* winsum = (XYZZ<Fq>*)((uint8_t*)ctx->msm_b.p + szs);
+    StageTimer tm(st, ctx->profile != 0 && n >= (size_t)ctx->profile);
+    k_digits<Fr><<<dim3((g.n + 255) / 256, d_scalars2 ? 2 : 1), 256, 0, st>>>((const Fr*)d_scalars, (const Fr*)d_scalars2, scalars_mont ? 1 : 0, g, digits,
+                                                                               (uint32_t*)nullptr);
+    tm.mark("digits");
+    if (ctx->wait_points) {
+      ctx->wait_points = false;
+      BP_CUDA_OK(cudaStreamWaitEvent(st, ctx->points_ready, 0));
+    }
+    const size_t smem = ((size_t)3 * (g.nbp + 2) + n) * sizeof(uint32_t);
+    k_msm_small<Fq><<<g.W, SMALL_T, smem, st>>>(g, d_points, digits, scratch, winsum, winsum + g.W);
+    tm.mark("small");
+    ctx->launches += 2;
+    g.S = 0; g.lgL1 = 0; g.nseg = 1;
+    res->W = g.W0; res->c = g.c; res->qshift = 5; res->d_winsum = winsum;
+    int lrc = launch_check(ctx, "msm_small");
+    tm.report(g, ctx);
+    return lrc;
   }
 
   // ---- scratch layout

@@ -339,3 +339,20 @@ def test_msm_begin_finish_pipelined_over_two_contexts(which, bp, ctx_bls, ctx_bn
     other.close()
     dp.free()
     tab.free()
+
+
+@pytest.mark.parametrize("which", ["bls", "bn"])
+@pytest.mark.parametrize("n", [300, 2049, 4096])
+def test_small_msm_kernel_skewed_digits(which, n, ctx_bls, ctx_bn):
+    """The one-launch small-MSM kernel (csrc/msm.cu k_msm_small, n <= 4096): equal scalars (ONE bucket per window, summed by
+    a warp), 0/1 witnesses, small scalars (most windows empty), r - 1 (all digits negative), a few distinct values (wide and
+    narrow buckets mixed), repeated points and identities among the inputs -- against the oracle's sum."""
+    ctx = ctx_bls if which == "bls" else ctx_bn
+    C = curve_of(ctx)
+    base = rand_points(C, 37, 900 + n)
+    P = [base[i % 37] if i % 53 else C.INF for i in range(n)]
+    rnd = random.Random(n)
+    few = [rnd.randrange(C.r) for _ in range(5)]
+    for s in ([few[0]] * n, [rnd.randrange(2) for _ in range(n)], [rnd.randrange(1 << 20) for _ in range(n)], [C.r - 1] * n,
+              [few[rnd.randrange(5)] for _ in range(n)], [rnd.randrange(C.r) if i % 3 else 0 for i in range(n)]):
+        _check(ctx, C, P, s)
