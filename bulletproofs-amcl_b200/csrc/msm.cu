@@ -402,7 +402,7 @@ __global__ void __launch_bounds__(64) k_reduce_l2(MsmGeom g, const XYZZ<Fq>* __r
 // pipeline above is six launches of latency-bound kernels for such an input (0.27 ms whatever n is); the verification MSM
 // of a proof, the IPP rounds after the generators were materialised and every MSM below a few thousand terms are this shape.
 //   phase 1  histogram of the window's digits, exclusive scan (one warp), scatter of (index | sign) into shared memory
-//   phase 2  thread t accumulates sorted entries [t S, (t+1) S), S = ceil(entries / 256): a run that covers its whole
+//   phase 2  thread t accumulates sorted entries [t S, (t+1) S), S >= ceil(entries / threads): a run that covers its whole
 //            bucket goes to bsum[b]; a run of a bucket that began in an earlier thread goes to head[t], one that continues
 //            in the next thread to tail[t] (at most one of each per thread)
 //   phase 3  thread b folds bucket b = tail[t0] + head[t0+1 .. t1] when it spans few threads; wider ones (skewed digits,
@@ -416,17 +416,17 @@ template <class Fq>
 __global__ void __launch_bounds__(SMALL_T) k_msm_small(MsmGeom g, const Affine<Fq>* __restrict__ pts, const uint32_t* __restrict__ digits,
                                                        XYZZ<Fq>* __restrict__ scratch, XYZZ<Fq>* __restrict__ winP, XYZZ<Fq>* __restrict__ winQ) {
   extern __shared__ uint32_t sm32[];
-  const uint32_t nb = g.nbp - 1, n = g.n, w = blockIdx.x, tid = threadIdx.x;
+  const uint32_t nb = g.nbp - 1, n = g.n, w = blockIdx.x, tid = threadIdx.x, T = blockDim.x;      // T = 64, 128 or 256 >= nb
   const int lane = tid & 31, wid = tid >> 5;
   uint32_t* cnt = sm32;                 // [nb + 2]  histogram, then the scatter cursors
   uint32_t* bs = cnt + nb + 2;          // [nb + 2]  bs[b] = first sorted entry of bucket b (1..nb); bs[nb + 1] = entries
   uint32_t* wide = bs + nb + 2;         // [nb + 1]  [0] = count, then the buckets left to the warps
   uint32_t* ent = wide + nb + 1;        // [n]       (index | sign) sorted by bucket
   const uint32_t* dg = digits + (size_t)w * n;
-  for (uint32_t b = tid; b < nb + 2; b += SMALL_T) cnt[b] = 0;
+  for (uint32_t b = tid; b < nb + 2; b += T) cnt[b] = 0;
   if (tid == 0) wide[0] = 0;
   __syncthreads();
-  for (uint32_t i = tid; i < n; i += SMALL_T) {
+  for (uint32_t i = tid; i < n; i += T) {
     const uint32_t d = dg[i];
     if (d) atomicAdd(&cnt[d & 0x7fffffffu], 1u);
   }
@@ -446,9 +446,9 @@ __global__ void __launch_bounds__(SMALL_T) k_msm_small(MsmGeom g, const Affine<F
     if (tid == 31) bs[nb + 1] = inc;
   }
   __syncthreads();
-  for (uint32_t b = 1 + tid; b <= nb; b += SMALL_T) cnt[b] = bs[b];
+  for (uint32_t b = 1 + tid; b <= nb; b += T) cnt[b] = bs[b];
   __syncthreads();
-  for (uint32_t i = tid; i < n; i += SMALL_T) {
+  for (uint32_t i = tid; i < n; i += T) {
     const uint32_t d = dg[i];
     if (d) ent[atomicAdd(&cnt[d & 0x7fffffffu], 1u)] = i | (d & 0x80000000u);
   }
@@ -459,7 +459,7 @@ __global__ void __launch_bounds__(SMALL_T) k_msm_small(MsmGeom g, const Affine<F
   XYZZ<Fq>* bsum = tail + SMALL_T;      // [nbp], indexed by bucket
   // chunk length: a thread's chain is S mixed additions, then the bucket's thread folds ~avg / S partial sums (full additions,
   // 1.4 x the cost): S ~ sqrt(1.4 avg) minimises the sum; never fewer entries per thread than 256 threads need to cover them
-  uint32_t S = (total + SMALL_T - 1) / SMALL_T;
+  uint32_t S = (total + T - 1) / T;
   {
     const uint32_t avg14 = (total * 14u) / (10u * (nb ? nb : 1u));          // 1.4 * entries per bucket
     uint32_t r = 1;
@@ -504,7 +504,7 @@ __global__ void __launch_bounds__(SMALL_T) k_msm_small(MsmGeom g, const Affine<F
     }
   }
   __syncthreads();
-  for (uint32_t gi = wid; gi < wide[0]; gi += SMALL_T / 32) {
+  for (uint32_t gi = wid; gi < wide[0]; gi += T / 32) {
     const uint32_t b = wide[1 + gi], s0 = bs[b], s1 = bs[b + 1];
     const uint32_t t0 = s0 / S, t1 = (s1 - 1) / S;
     XYZZ<Fq> acc = XYZZ<Fq>::inf();
@@ -612,7 +612,11 @@ int msm_run(bpgpu_ctx* ctx, const Affine<typename Curve::Fq>* d_points, const vo
   }
 
   static const bool small_on = !(getenv("BPGPU_SMALL") && atoi(getenv("BPGPU_SMALL")) == 0);
-  if (small_on && n <= SMALL_MAX_N && g.c <= 8) {
+  // measured (tools/small_msm_ab.py, tools/proof_rate.py): the one-launch kernel wins from a few hundred terms up on both curves
+  // and at every small size on BN254; on BLS12-381 (175 registers x the block's threads held to the end) the 154-term
+  // verification MSM of a 64-bit range proof is no faster alone (0.69 against 0.66 ms) and 10 % slower with 16 contexts
+  const bool small_fits = n <= SMALL_MAX_N && g.c <= 8 && (Fq::N == 8 || n > 256);
+  if (small_on && small_fits) {
     // ---- small input: digits, then ONE block per window (k_msm_small)
     const size_t szd = align256((size_t)g.W * n * 4);
     const size_t szs = align256((size_t)g.W * (2 * SMALL_T + g.nbp) * sizeof(XYZZ<Fq>));
@@ -631,7 +635,11 @@ int msm_run(bpgpu_ctx* ctx, const Affine<typename Curve::Fq>* d_points, const vo
       BP_CUDA_OK(cudaStreamWaitEvent(st, ctx->points_ready, 0));
     }
     const size_t smem = ((size_t)3 * (g.nbp + 2) + n) * sizeof(uint32_t);
-    k_msm_small<Fq><<<g.W, SMALL_T, smem, st>>>(g, d_points, digits, scratch, winsum, winsum + g.W);
+    // block size by input size: the block's registers are held until its warp 0 has finished the bucket reduction, so a
+    // small input (the 154-term verification MSM of a 64-bit range proof) gets 128 threads and two or more blocks share an SM
+    int T = n <= 1024 ? 128 : SMALL_T;
+    if ((uint32_t)T < g.nbp) T = SMALL_T;              // one thread per bucket in the folding phase (nbp <= 129)
+    k_msm_small<Fq><<<g.W, T, smem, st>>>(g, d_points, digits, scratch, winsum, winsum + g.W);
     tm.mark("small");
     ctx->launches += 2;
     g.S = 0; g.lgL1 = 0; g.nseg = 1;
