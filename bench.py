@@ -177,12 +177,15 @@ def proof_section(bp, ctx, local, rank, world, dist, torch, no_cpu=False):
     out = {"contexts_per_gpu": nctx, "host_cpus": ncpu, "host_threads_per_rank": hthreads, "contexts_sleep_on_events": oversub}
 
     def run(curve, m, bits, count, tag, verify_reps=1, batch_call=False, cpu_base=0, weak=4096):
-        ctxs = [bp.Context(curve, local) for _ in range(nctx)]
-        for c in ctxs if oversub else []:
+        n = m * bits
+        # sleeping contexts pay ~30 us per wake-up: worth it for proofs of milliseconds (n >= 1024), not for the 1.8 ms of a
+        # 64-bit proof with its ~30 waits -- those keep one spinning context per core
+        sleepers = oversub and n >= 1024
+        ctxs = [bp.Context(curve, local) for _ in range(nctx if (sleepers or not oversub) else cores)]
+        for c in ctxs if sleepers else []:
             c.set_blocking_sync(True)
         c0 = ctxs[0]
         gx, hx = c0.g1_from_msg_hash(b"g"), c0.g1_from_msg_hash(b"h")
-        n = m * bits
         pre = True                 # window tables in HBM (2 x 8.4 GB on BN254 at n = 2^14): table sums for the commitments and the first
                                    # IPP rounds, then the folded generators are materialised (csrc/ipp.cu hybrid): 223 -> 440 proofs/s
         G, H = c0.get_generators("G", n, precompute=pre), c0.get_generators("H", n, precompute=pre)
@@ -309,9 +312,8 @@ def proof_section(bp, ctx, local, rank, world, dist, torch, no_cpu=False):
         """BASELINE config 1: the standalone inner-product argument (IPP::create_ipp / verify_ipp, ipp.rs:35-260, the shape of
         the reference's own ipp tests at length n) through bph_ipp_create / bph_ipp_verify, one proof per context in flight"""
         from concurrent.futures import ThreadPoolExecutor
-        ctxs = [bp.Context(bp.BLS12_381, local) for _ in range(nctx)]
-        for c in ctxs if oversub else []:
-            c.set_blocking_sync(True)
+        ctxs = [bp.Context(bp.BLS12_381, local) for _ in range(min(nctx, cores))]     # n = 64: one spinning context per core
+        nc = len(ctxs)
         c0 = ctxs[0]
         mb = c0.modbytes
         G, H = c0.get_generators("g", n, precompute=True), c0.get_generators("h", n, precompute=True)
@@ -326,28 +328,28 @@ def proof_section(bp, ctx, local, rank, world, dist, torch, no_cpu=False):
             jobs.append((ab, bb, P))
 
         def prove(k):
-            ctx = ctxs[k % nctx]
-            return [ctx.ipp_create(b"ipp", G, H, Q, ones, ones, jobs[i][0], jobs[i][1], n) for i in range(k, count, nctx)]
+            ctx = ctxs[k % nc]
+            return [ctx.ipp_create(b"ipp", G, H, Q, ones, ones, jobs[i][0], jobs[i][1], n) for i in range(k, count, nc)]
 
         def verify(k):
-            ctx = ctxs[k % nctx]
-            return all(ctx.ipp_verify(b"ipp", n, ones, ones, jobs[i][2], Q, G, H, proofs[i]) for i in range(k, count, nctx))
-        with ThreadPoolExecutor(nctx) as ex:
-            list(ex.map(prove, range(nctx)))                                         # warm-up
+            ctx = ctxs[k % nc]
+            return all(ctx.ipp_verify(b"ipp", n, ones, ones, jobs[i][2], Q, G, H, proofs[i]) for i in range(k, count, nc))
+        with ThreadPoolExecutor(nc) as ex:
+            list(ex.map(prove, range(nc)))                                         # warm-up
             if dist is not None:
                 dist.barrier()
             t0 = time.perf_counter()
-            res = list(ex.map(prove, range(nctx)))
+            res = list(ex.map(prove, range(nc)))
             tp = time.perf_counter() - t0
             proofs = [None] * count
             for k, lst in enumerate(res):
                 for j, pr in enumerate(lst):
-                    proofs[k + j * nctx] = pr
-            list(ex.map(verify, range(nctx)))
+                    proofs[k + j * nc] = pr
+            list(ex.map(verify, range(nc)))
             if dist is not None:
                 dist.barrier()
             t0 = time.perf_counter()
-            ok = all(ex.map(verify, range(nctx)))
+            ok = all(ex.map(verify, range(nc)))
             tv = time.perf_counter() - t0
         if dist is not None:
             tt = torch.tensor([tp, tv, 0.0 if ok else 1.0], device="cuda", dtype=torch.float64)
