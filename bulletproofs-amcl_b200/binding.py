@@ -36,6 +36,7 @@ SYMBOLS = [
     ("bpgpu_points_download", _INT, [_VP, _VP, _SZ, _SZ, _VP]),
     ("bpgpu_points_from_hashes", _INT, [_VP, _VP, _SZ, _c.POINTER(_VP)]),
     ("bpgpu_points_precompute", _INT, [_VP, _VP]),
+    ("bpgpu_points_precompute_wide", _INT, [_VP, _VP]),
     ("bpgpu_points_has_tables", _INT, [_VP]),
     ("bpgpu_points_len", _SZ, [_VP]),
     ("bpgpu_points_free", None, [_VP]),
@@ -395,9 +396,19 @@ class DevicePoints:
         self.ctx._check(lib().bpgpu_points_precompute(self.ctx.handle, self.handle), "points_precompute")
         return self
 
+    def precompute_wide(self):
+        """16-bit window tables on top (bpgpu_points_precompute_wide): the batch calls add half as many entries per term"""
+        self.ctx._check(lib().bpgpu_points_precompute_wide(self.ctx.handle, self.handle), "points_precompute_wide")
+        return self
+
     @property
     def has_tables(self):
         return bool(lib().bpgpu_points_has_tables(self.handle))
+
+    @property
+    def table_level(self):
+        """0: no tables, 1: 8-bit window tables, 2: also the wide (16-bit window) tables"""
+        return int(lib().bpgpu_points_has_tables(self.handle))
 
     def download(self, off=0, n=None):
         n = len(self) - off if n is None else n

@@ -585,12 +585,20 @@ int bpgpu_points_precompute(bpgpu_ctx* ctx, bpgpu_points* p) {
   BP_CUDA_OK(cudaSetDevice(ctx->device));
   return ctx->curve == BPGPU_BLS12_381 ? build_tables<Bls>(ctx, p->d, p->n, &p->table) : build_tables<Bn>(ctx, p->d, p->n, &p->table);
 }
-int bpgpu_points_has_tables(const bpgpu_points* p) { return p && p->table ? 1 : 0; }
+int bpgpu_points_precompute_wide(bpgpu_ctx* ctx, bpgpu_points* p) {
+  if (!ctx || !p) return BPGPU_E_ARG;
+  if (p->table16 || p->n == 0) return BPGPU_OK;
+  int rc = bpgpu_points_precompute(ctx, p);
+  if (rc) return rc;
+  return ctx->curve == BPGPU_BLS12_381 ? build_tables16<Bls>(ctx, p->table, p->n, &p->table16) : build_tables16<Bn>(ctx, p->table, p->n, &p->table16);
+}
+int bpgpu_points_has_tables(const bpgpu_points* p) { return p && p->table ? (p->table16 ? 2 : 1) : 0; }
 void bpgpu_points_free(bpgpu_points* p) {
   if (!p) return;
   cudaSetDevice(p->ctx->device);
   dev_free(p->ctx, p->d);
   if (p->table) cudaFree(p->table);
+  if (p->table16) cudaFree(p->table16);
   delete p;
 }
 

@@ -212,10 +212,12 @@ int resolve_fixed_runs(bpgpu_ctx* ctx, const bpgpu_fixed_run* runs, size_t nruns
     const bpgpu_fixed_run& r = runs[k];
     if (r.n == 0) continue;
     const void* tbl = nullptr;
+    const void* tbl16 = nullptr;
     if (r.points) {
       if (!(r.off <= r.points->n && r.n <= r.points->n - r.off)) return BPGPU_E_LEN;
       if (!r.points->table) return BPGPU_E_ARG;                       // bpgpu_points_precompute first
       tbl = (const uint8_t*)r.points->table + r.off * TBL_ENTRIES * asz;
+      if (r.points->table16) tbl16 = (const uint8_t*)r.points->table16 + r.off * TBL16_ENTRIES * asz;
     } else {
       if (!r.host_base_xy || r.n != 1) return BPGPU_E_ARG;
       tbl = fixed_table_lookup(ctx, r.host_base_xy);
@@ -227,12 +229,13 @@ int resolve_fixed_runs(bpgpu_ctx* ctx, const bpgpu_fixed_run* runs, size_t nruns
       }
     }
     fr.table[fr.nruns] = tbl;
+    fr.table16[fr.nruns] = tbl16;
     fr.start[fr.nruns] = F;
     fr.nruns++;
     F += (uint32_t)r.n;
   }
   fr.start[fr.nruns] = F;
-  if (fr.nruns == 0) { fr.nruns = 1; fr.table[0] = nullptr; fr.start[0] = 0; fr.start[1] = 0; }
+  if (fr.nruns == 0) { fr.nruns = 1; fr.table[0] = nullptr; fr.table16[0] = nullptr; fr.start[0] = 0; fr.start[1] = 0; }
   *F_out = F;
   return BPGPU_OK;
 }

@@ -12,6 +12,7 @@ static const int BATCH_FIXED_THREADS = 128;
 
 struct FixedRuns {
   const void* table[TBL_MAX_SEGS];
+  const void* table16[TBL_MAX_SEGS];      // wide (16-bit window) tables of the run, or null
   uint32_t start[TBL_MAX_SEGS + 1];
   int nruns;
 };
@@ -112,6 +113,13 @@ __global__ void __launch_bounds__(128, 3) k_batch_fixed_warp(FixedRuns runs, uin
       int rg = 0;
       while (rg + 1 < runs.nruns && base >= runs.start[rg + 1]) rg++;
       const uint32_t row = base - runs.start[rg];
+      if (runs.table16[rg]) {                            // wide tables: two 16-bit windows per limb, half the additions
+        const Affine<Fq>* tw = (const Affine<Fq>*)runs.table16[rg] + ((size_t)row * TBL16_WINDOWS + 2 * j) * TBL16_DIGITS;
+        const uint32_t d0 = limb & 0xffffu, d1 = limb >> 16;
+        if (d0) acc.madd(load_vec_ro(tw + (d0 - 1)));
+        if (d1) acc.madd(load_vec_ro(tw + TBL16_DIGITS + (d1 - 1)));
+        continue;
+      }
       const Affine<Fq>* tb = (const Affine<Fq>*)runs.table[rg] + ((size_t)row * TBL_WINDOWS + TBL_PER_LIMB * j) * TBL_DIGITS;
 #pragma unroll 1
       for (int k = 0; k < TBL_PER_LIMB; k++) {

@@ -85,6 +85,7 @@ struct bpgpu_points {
   void* d;        // Affine<Fq>[n]
   size_t n;
   void* table = nullptr;   // optional window tables Affine<Fq>[n][64][15] (bpgpu_points_precompute, fixedbase.cu)
+  void* table16 = nullptr; // optional wide tables Affine<Fq>[n][16][65535] (bpgpu_points_precompute_wide)
 };
 // a device allocation shared by several bpgpu_scalars handles (bpgpu_scalars_view): released with the last of them
 struct bpgpu_shared_block { void* base; int refs; };
@@ -186,6 +187,12 @@ static const int TBL_WINDOWS = 256 / TBL_BITS;                // 32
 static const int TBL_DIGITS = (1 << TBL_BITS) - 1;            // 255
 static const int TBL_PER_LIMB = 32 / TBL_BITS;                // windows per 32-bit scalar limb
 static const int TBL_ENTRIES = TBL_WINDOWS * TBL_DIGITS;      // per point
+// WIDE tables (bpgpu_points_precompute_wide): 16-bit windows, T16[i][W][d-1] = d * 2^(16 W) * P_i, 16 x 65535 affine entries per
+// point (100 MB on BLS12-381, 67 MB on BN254): HALF the additions per term, for generator sets of a few dozen points that are
+// summed millions of times (the 64-multiplier statements of the batch verifier / prover)
+static const int TBL16_WINDOWS = 16;
+static const int TBL16_DIGITS = 65535;
+static const size_t TBL16_ENTRIES = (size_t)TBL16_WINDOWS * TBL16_DIGITS;
 static const int TBL_MAX_SEGS = 12;
 static const int TBL_MAX_GROUPS = 4;
 // one run of terms whose points have tables: table already offset to the first point, scalars = Fr[n];
@@ -204,6 +211,7 @@ template <class FqParams> void host_sum_partials(uint8_t* xyzz_bytes, int ngroup
 // table-only MSMs, one per group: device sums, one D2H, one shared inversion for the affine results
 int msm_tables_to_host(bpgpu_ctx* ctx, const TableSeg* segs, int nsegs, int ngroups, uint8_t* const* outs_xy);
 // (fixed-base cache lookup) table of a point that is one of the bases of a cached bpgpu_fixed_bases, or nullptr
+template <class Curve> int build_tables16(bpgpu_ctx* ctx, const void* table8, size_t n, void** table16_out);
 const void* fixed_table_lookup(bpgpu_ctx* ctx, const uint8_t* xy);
 // full MSM over table segments plus (optionally) a general run of device points/scalars; host finish
 int msm_mixed_to_host(bpgpu_ctx* ctx, const TableSeg* segs, int nsegs, const void* d_pts, const void* d_scal, bool mont, size_t n,

@@ -271,6 +271,68 @@ int build_tables(bpgpu_ctx* ctx, const void* d_affine, size_t n, void** table_ou
 template int build_tables<Bls>(bpgpu_ctx*, const void*, size_t, void**);
 template int build_tables<Bn>(bpgpu_ctx*, const void*, size_t, void**);
 
+// wide[pW][d-1] = d * 2^(16 W) * B_p for d = 1..65535 = the sum of the two byte-window entries T8[p][2W+1][d >> 8] and
+// T8[p][2W][d & 255]: ONE mixed addition per entry, no doublings.  One thread per (p, W, 15 consecutive d) -- 65535 = 15 * 4369 --
+// and one shared inversion per thread (Montgomery's trick), as k_fb_multiples.
+static const int WIDE_GROUP = 15;
+static const uint32_t WIDE_GROUPS = TBL16_DIGITS / WIDE_GROUP;     // 4369
+template <class Fq>
+__global__ void __launch_bounds__(64) k_fb_wide(const Affine<Fq>* __restrict__ table8, size_t npw, Affine<Fq>* __restrict__ table16) {
+  const size_t t = (size_t)blockIdx.x * blockDim.x + threadIdx.x;      // pW * WIDE_GROUPS + g
+  if (t >= npw * WIDE_GROUPS) return;
+  const size_t pw = t / WIDE_GROUPS;
+  const uint32_t g = (uint32_t)(t - pw * WIDE_GROUPS);
+  const size_t pt = pw / TBL16_WINDOWS, W = pw - pt * TBL16_WINDOWS;
+  const Affine<Fq>* lo8 = table8 + (pt * TBL_WINDOWS + 2 * W) * TBL_DIGITS;
+  const Affine<Fq>* hi8 = lo8 + TBL_DIGITS;
+  Affine<Fq>* out = table16 + pw * TBL16_DIGITS + (size_t)g * WIDE_GROUP;
+  XYZZ<Fq> m[WIDE_GROUP];
+  Fq pre[WIDE_GROUP];
+  Fq run = Fq::one();
+#pragma unroll 1
+  for (int k = 0; k < WIDE_GROUP; k++) {
+    const uint32_t d = g * WIDE_GROUP + 1 + (uint32_t)k, dl = d & 255u, dh = d >> 8;
+    XYZZ<Fq> acc = dh ? XYZZ<Fq>::from_affine(load_vec_ro(hi8 + (dh - 1))) : XYZZ<Fq>::inf();
+    if (dl) acc.madd(load_vec_ro(lo8 + (dl - 1)));
+    m[k] = acc;
+    if (!acc.is_inf()) run = run * acc.zzz;
+    pre[k] = run;
+  }
+  Fq inv = run.inv();
+#pragma unroll 1
+  for (int k = WIDE_GROUP - 1; k >= 0; k--) {
+    if (m[k].is_inf()) { store_vec(out + k, Affine<Fq>::inf()); continue; }     // the identity among the bases
+    Fq i3 = k ? inv * pre[k - 1] : inv;     // 1 / zzz_k
+    inv = inv * m[k].zzz;
+    Fq i1 = i3 * m[k].zz;                   // 1 / z
+    Affine<Fq> a;
+    a.x = m[k].x * i1.sqr();
+    a.y = m[k].y * i3;
+    store_vec(out + k, a);
+  }
+}
+
+template <class Curve>
+int build_tables16(bpgpu_ctx* ctx, const void* table8, size_t n, void** table16_out) {
+  using Fq = typename Curve::Fq;
+  *table16_out = nullptr;
+  if (n == 0 || !table8) return BPGPU_E_ARG;
+  const size_t bytes = n * TBL16_ENTRIES * sizeof(Affine<Fq>);
+  if (bytes > ((size_t)48 << 30)) return BPGPU_E_ARG;                        // a few dozen generators, not a circuit of thousands
+  void* t16 = nullptr;
+  if (cudaMalloc(&t16, bytes) != cudaSuccess) { cudaGetLastError(); return BPGPU_E_CUDA; }
+  const size_t npw = n * TBL16_WINDOWS, threads = npw * WIDE_GROUPS;
+  k_fb_wide<Fq><<<(unsigned)((threads + 63) / 64), 64, 0, ctx->stream>>>((const Affine<Fq>*)table8, npw, (Affine<Fq>*)t16);
+  ctx->launches++;
+  int rc = launch_check(ctx, "k_fb_wide");
+  if (!rc && stream_sync(ctx) != cudaSuccess) rc = BPGPU_E_CUDA;
+  if (rc) { cudaFree(t16); return rc; }
+  *table16_out = t16;
+  return BPGPU_OK;
+}
+template int build_tables16<Bls>(bpgpu_ctx*, const void*, size_t, void**);
+template int build_tables16<Bn>(bpgpu_ctx*, const void*, size_t, void**);
+
 template <class Curve>
 int table_sum_run(bpgpu_ctx* ctx, const TableSeg* segs, int nsegs, int ngroups, int* host_partials) {
   using Fq = typename Curve::Fq;

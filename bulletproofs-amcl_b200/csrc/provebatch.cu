@@ -730,8 +730,10 @@ int bpgpu_pbatch_create(bpgpu_ctx* ctx, bpgpu_points* G, bpgpu_points* H, const 
   memset(pb, 0, sizeof *pb);
   pb->ctx = ctx; pb->B = batch; pb->n = n; pb->N = N;
   pb->runs1.nruns = 3; pb->runs1.table[0] = G->table; pb->runs1.table[1] = H->table; pb->runs1.table[2] = th;
+  pb->runs1.table16[0] = G->table16; pb->runs1.table16[1] = H->table16; pb->runs1.table16[2] = nullptr;      // wide tables when the caller built them
   pb->runs1.start[0] = 0; pb->runs1.start[1] = (uint32_t)n; pb->runs1.start[2] = (uint32_t)(2 * n); pb->runs1.start[3] = (uint32_t)(2 * n + 1);
   pb->runs2.nruns = 3; pb->runs2.table[0] = G->table; pb->runs2.table[1] = H->table; pb->runs2.table[2] = tg;
+  pb->runs2.table16[0] = G->table16; pb->runs2.table16[1] = H->table16; pb->runs2.table16[2] = nullptr;
   pb->runs2.start[0] = 0; pb->runs2.start[1] = (uint32_t)N; pb->runs2.start[2] = (uint32_t)(2 * N); pb->runs2.start[3] = (uint32_t)(2 * N + 1);
   const size_t fr = 32, xz = ctx->curve == BPGPU_BLS12_381 ? sizeof(XYZZ<Bls::Fq>) : sizeof(XYZZ<Bn::Fq>);
   const size_t B = batch;

@@ -417,6 +417,18 @@ void replay_challenges_host(Transcript t, const uint8_t* proof, const uint8_t* c
   }
 }
 
+// Small statements proved / verified in bulk get WIDE generator tables (16-bit windows, bpgpu_points_precompute_wide: 100 MB
+// per BLS12-381 generator): N <= 64 by default (2 x 6.4 GB), BPH_WIDE_TABLES=<max N> moves the limit, 0 turns it off.
+static size_t wide_tables_max_n() {
+  const char* e = getenv("BPH_WIDE_TABLES");
+  return e ? (size_t)atol(e) : 64;
+}
+static int maybe_wide_tables(bpgpu_ctx* ctx, bpgpu_points* G, bpgpu_points* H, size_t N, size_t count) {
+  if (N > wide_tables_max_n() || count < 256 || bpgpu_points_len(G) > 2 * N || bpgpu_points_len(H) > 2 * N) return BPGPU_OK;
+  int rc = bpgpu_points_precompute_wide(ctx, G);
+  return rc ? rc : bpgpu_points_precompute_wide(ctx, H);
+}
+
 // mode 0: transcripts replayed on the device; mode 1: transcripts on `nthreads` host threads, challenges uploaded
 template <class C>
 int verify_batch_device_t(bpgpu_ctx* ctx, const char* label, const uint8_t* g_xy, const uint8_t* h_xy, bpgpu_points* G, bpgpu_points* H,
@@ -435,7 +447,10 @@ int verify_batch_device_t(bpgpu_ctx* ctx, const char* label, const uint8_t* g_xy
   Rng<C> os;                                              // one key per call; proof i takes draw i (verifier.rs:392)
   if (!os.ok()) { bpgpu_circuit_free(circ); return BPH_E_ENTROPY; }
   if (bpgpu_points_len(G) >= N && bpgpu_points_len(H) >= N &&          // tables built once, before the drivers share them
-      ((rc = bpgpu_points_precompute(ctx, G)) || (rc = bpgpu_points_precompute(ctx, H)))) { bpgpu_circuit_free(circ); return rc; }
+      ((rc = bpgpu_points_precompute(ctx, G)) || (rc = bpgpu_points_precompute(ctx, H)) || (rc = maybe_wide_tables(ctx, G, H, N, count)))) {
+    bpgpu_circuit_free(circ);
+    return rc;
+  }
   // Two slabs in flight on two contexts (the second one cached in the first, bpgpu_ctx_aux): the latency-bound kernels of a
   // slab (per-proof transcripts, the 252-doubling Horner chains) run under the table sums of the other.  Every slab call
   // gets its own key for the verifiers' random scalars (key || slab index).
@@ -541,7 +556,9 @@ int range_prove_batch_device_t(bpgpu_ctx* ctx, const char* label, const uint8_t*
   int rc = range_circuit_csr<C>(m, bits, &csr);
   if (rc) return rc;
   if ((rc = points_valid<C>(g_xy, 1)) || (rc = points_valid<C>(h_xy, 1))) return rc;
-  if ((rc = bpgpu_points_precompute(ctx, G)) || (rc = bpgpu_points_precompute(ctx, H))) return rc;
+  if ((rc = bpgpu_points_precompute(ctx, G)) || (rc = bpgpu_points_precompute(ctx, H)) ||
+      (rc = maybe_wide_tables(ctx, G, H, next_power_of_two(n), count)))
+    return rc;
   uint8_t state0[203];
   {
     Transcript t0{std::string(label)};

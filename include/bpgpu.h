@@ -102,6 +102,12 @@ int bpgpu_points_from_hashes(bpgpu_ctx* ctx, const uint8_t* hashes, size_t n, bp
  * generators of a 1024-multiplier circuit) for latency: a clear win up to a few thousand generators (prove n = 64:
  * 10.4 -> 2.4 ms, n = 1024: 29.6 -> 5.3 ms), a loss in throughput mode at 2^14 -- callers precompute accordingly. */
 int bpgpu_points_precompute(bpgpu_ctx* ctx, bpgpu_points* p);
+/* WIDE tables on top of those: T16[i][W][d] = d * 2^(16 W) * P_i, 16 windows x 65535 multiples = 100 MB (BLS12-381) / 67 MB
+ * (BN254) per generator, each entry ONE addition of two entries of the 8-bit tables.  The batch calls (bpgpu_r1cs_verify_batch,
+ * bpgpu_msm_batch_is_identity, bpgpu_pbatch_*) then add 16 instead of 32 entries per fixed term.  For the few dozen generators
+ * of a small statement proved / verified in bulk (G, H of a 64-bit range proof: 2 x 6.4 GB of the 180 GB); refused above
+ * 48 GB per handle.  Single MSMs keep using the 8-bit tables.  has_tables: 0 none, 1 8-bit, 2 both. */
+int bpgpu_points_precompute_wide(bpgpu_ctx* ctx, bpgpu_points* p);
 int bpgpu_points_has_tables(const bpgpu_points* p);
 size_t bpgpu_points_len(const bpgpu_points* p);
 void bpgpu_points_free(bpgpu_points* p);

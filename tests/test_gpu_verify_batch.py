@@ -155,3 +155,34 @@ def test_bound_check_batch(bp, ctx_bls, ctx_bn, which):
     swapped = comms[:3 * 2 * mbytes] + comms[6 * 2 * mbytes:9 * 2 * mbytes] + comms[3 * 2 * mbytes:6 * 2 * mbytes] + comms[9 * 2 * mbytes:]
     assert bp.bound_check_verify_batch(ctx, b"Bounds", gx, hx, dG, dH, len(vals), lower, upper, bits, proofs, stride, swapped) == \
         [0, -4, -4, 0, 0, 0]
+
+
+@pytest.mark.gpu
+@pytest.mark.parametrize("which,m,bits", [("bls", 1, 64), ("bn", 2, 16)])
+def test_wide_generator_tables_change_no_byte(which, m, bits, bp, ctx_bls, ctx_bn, monkeypatch):
+    """16-bit-window tables (bpgpu_points_precompute_wide) halve the additions of the batch calls' fixed terms; the batch
+    prover's proofs and the batch verifier's verdicts (incl. tampered proofs) are the same with and without them, and equal
+    the single-proof prover's bytes."""
+    ctx = ctx_bls if which == "bls" else ctx_bn
+    n = m * bits
+    count = 300
+    gx, hx = ctx.g1_from_msg_hash(b"g"), ctx.g1_from_msg_hash(b"h")
+    vals = [(0x9E3779B97F4A7C15 * (i + 1)) % (1 << min(bits, 63)) for i in range(count * m)]
+    out = {}
+    for wide in ("0", "64"):
+        monkeypatch.setenv("BPH_WIDE_TABLES", wide)
+        G, H = ctx.get_generators("G", n, precompute=True), ctx.get_generators("H", n, precompute=True)
+        proofs, stride, comms = bp.range_prove_batch(ctx, b"wide", gx, hx, G, H, vals, m, bits, seed=5)
+        assert (G.table_level == 2) == (wide != "0")
+        bad = bytearray(proofs)
+        for i in (3, 150, 299):
+            bad[i * stride + stride - 1] ^= 1
+        v = bp.range_verify_batch(ctx, b"wide", gx, hx, G, H, count, m, bits, bytes(bad), stride, comms)
+        assert [i for i, x in enumerate(v) if x != 0] == [3, 150, 299]
+        out[wide] = (proofs, comms)
+        if wide != "0":
+            single, scomms = ctx.range_prove(b"wide", gx, hx, G, H, vals[7 * m:8 * m], bits, seed=5 + 7)
+            assert proofs[7 * stride:7 * stride + len(single)] == single
+        G.free()
+        H.free()
+    assert out["0"] == out["64"]
