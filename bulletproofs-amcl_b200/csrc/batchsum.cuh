@@ -113,18 +113,18 @@ __global__ void __launch_bounds__(128, 3) k_batch_fixed_warp(FixedRuns runs, uin
       int rg = 0;
       while (rg + 1 < runs.nruns && base >= runs.start[rg + 1]) rg++;
       const uint32_t row = base - runs.start[rg];
-      if (runs.table16[rg]) {                            // wide tables: two 16-bit windows per limb, half the additions
-        const Affine<Fq>* tw = (const Affine<Fq>*)runs.table16[rg] + ((size_t)row * TBL16_WINDOWS + 2 * j) * TBL16_DIGITS;
-        const uint32_t d0 = limb & 0xffffu, d1 = limb >> 16;
-        if (d0) acc.madd(load_vec_ro(tw + (d0 - 1)));
-        if (d1) acc.madd(load_vec_ro(tw + TBL16_DIGITS + (d1 - 1)));
-        continue;
-      }
-      const Affine<Fq>* tb = (const Affine<Fq>*)runs.table[rg] + ((size_t)row * TBL_WINDOWS + TBL_PER_LIMB * j) * TBL_DIGITS;
+      // wide tables (two 16-bit windows per limb: half the additions) or the 8-bit ones (four): ONE loop and ONE inlined
+      // mixed addition for both -- a second copy of its ~60 KB body makes the kernel miss the instruction cache
+      const bool wide = runs.table16[rg] != nullptr;
+      const Affine<Fq>* tb = wide ? (const Affine<Fq>*)runs.table16[rg] + ((size_t)row * TBL16_WINDOWS + 2 * j) * TBL16_DIGITS
+                                  : (const Affine<Fq>*)runs.table[rg] + ((size_t)row * TBL_WINDOWS + TBL_PER_LIMB * j) * TBL_DIGITS;
+      const uint32_t wbits = wide ? 16u : (uint32_t)TBL_BITS, wmask = wide ? 0xffffu : (uint32_t)TBL_DIGITS;
+      const uint32_t wstride = wide ? (uint32_t)TBL16_DIGITS : (uint32_t)TBL_DIGITS;
+      const int nwin = wide ? 2 : TBL_PER_LIMB;
 #pragma unroll 1
-      for (int k = 0; k < TBL_PER_LIMB; k++) {
-        const uint32_t d = (limb >> (TBL_BITS * k)) & (uint32_t)TBL_DIGITS;
-        if (d) acc.madd(load_vec_ro(tb + k * TBL_DIGITS + (d - 1)));
+      for (int k = 0; k < nwin; k++) {
+        const uint32_t d = (limb >> (wbits * k)) & wmask;
+        if (d) acc.madd(load_vec_ro(tb + (size_t)k * wstride + (d - 1)));
       }
     }
   }
