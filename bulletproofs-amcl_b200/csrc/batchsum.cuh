@@ -9,6 +9,9 @@ namespace bp {
 // 128 threads per row: 8 table lookups per (term, limb) item and a 7-level tree -- two to three blocks fit an SM, and a
 // thread spends more of its time adding table entries than waiting in the tree (256 threads: one block per SM, 8 levels)
 static const int BATCH_FIXED_THREADS = 128;
+#ifndef BP_WARP_MADD
+#define BP_WARP_MADD madd_c
+#endif
 
 struct FixedRuns {
   const void* table[TBL_MAX_SEGS];
@@ -124,7 +127,7 @@ __global__ void __launch_bounds__(128, 3) k_batch_fixed_warp(FixedRuns runs, uin
 #pragma unroll 1
       for (int k = 0; k < nwin; k++) {
         const uint32_t d = (limb >> (wbits * k)) & wmask;
-        if (d) acc.madd(load_vec_ro(tb + (size_t)k * wstride + (d - 1)));
+        if (d) acc.BP_WARP_MADD(load_vec_ro(tb + (size_t)k * wstride + (d - 1)));
       }
     }
   }

@@ -91,6 +91,29 @@ struct XYZZ {
     x = X3; y = Y3;
   }
 
+  // the same mixed addition with its products as real calls (Fp::mulc / sqrc / mul2c): ~1 KB of code at the call site
+  // instead of ~60 KB, for kernels whose loop would otherwise not stay in the instruction cache
+  BP_HD_COLD void madd_c(const Affine<F>& a) {
+    if (a.is_inf()) return;
+    if (is_inf()) { *this = from_affine(a); return; }
+    F U2 = F::mulc(a.x, zz);
+    F S2 = F::mulc(a.y, zzz);
+    F Pd = U2 - x;
+    F R = S2 - y;
+    if (Pd.is_zero()) {
+      if (R.is_zero()) *this = dbl_affine(a); else *this = inf();
+      return;
+    }
+    F PP = F::sqrc(Pd);
+    F PPP = F::mulc(Pd, PP);
+    F Q = F::mulc(x, PP);
+    F X3 = F::sqrc(R) - PPP - Q.dbl();
+    F Y3 = F::mul2c(R, Q - X3, y.neg(), PPP);
+    zz = F::mulc(zz, PP);
+    zzz = F::mulc(zzz, PPP);
+    x = X3; y = Y3;
+  }
+
   // add-2008-s: this += q
   // compact form: a real call whose products are real calls too (see Fp::mulc) -- for latency-bound code
   BP_HD_COLD void add(const XYZZ& q) { add_t<true>(q); }

@@ -288,6 +288,7 @@ struct Fp {
   // the multiplier.  The cold-path group operations (XYZZ::add / dbl) are built from these instead: one 6 KB body
   // that stays in the instruction cache.  Throughput kernels keep the inlined forms.
   BP_HD_COLD static Fp mulc(Fp a, Fp b) { return mul_t<0>(a, b); }
+  BP_HD_COLD static Fp sqrc(Fp a) { return a.sqr(); }
   BP_HD_COLD static Fp mul2c(Fp a, Fp b, Fp c, Fp d) { return mul2(a, b, c, d); }
 
   // (a*b + c*d) / 2^(32N) mod p with ONE Montgomery reduction: every row adds a*b_i AND c*d_i to the accumulators

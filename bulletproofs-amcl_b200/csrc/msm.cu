@@ -42,6 +42,9 @@ struct MsmGeom {
   int lgL2;         // log2(segments per lane) in k_reduce_l2
 };
 
+#ifndef BP_CHUNK_MADD
+#define BP_CHUNK_MADD madd_c
+#endif
 static const int GIANT_T = 16;         // buckets with more partials than this are collapsed by giant_blocks (a block tree: ~9 dependent additions)
 static const int GIANT_BLOCK = 128;
 
@@ -213,7 +216,7 @@ __global__ void __launch_bounds__(128, 2) k_chunk_acc(MsmGeom g, const Affine<Fq
     uint32_t id = idx[e];
     Affine<Fq> P = load_vec_ro(pts + (id & 0x7fffffffu));
     if (id >> 31) P.y = P.y.neg();
-    acc.madd(P);
+    acc.BP_CHUNK_MADD(P);
   }
   store_vec(out + ps[cur] + (t - bs[cur] / g.S), acc);
 }
