@@ -42,9 +42,6 @@ struct MsmGeom {
   int lgL2;         // log2(segments per lane) in k_reduce_l2
 };
 
-#ifndef BP_CHUNK_MADD
-#define BP_CHUNK_MADD madd_c
-#endif
 static const int GIANT_T = 16;         // buckets with more partials than this are collapsed by giant_blocks (a block tree: ~9 dependent additions)
 static const int GIANT_BLOCK = 128;
 
@@ -184,10 +181,13 @@ __device__ __forceinline__ uint32_t bucket_of(const uint32_t* __restrict__ bs, u
   return lo;
 }
 
-// 2 blocks of 128 threads per SM (186 registers); forcing 3 blocks (168 registers) measures the same: the kernel is bound by
-// the multiplier pipe, not by occupancy
-template <class Fq>
-__global__ void __launch_bounds__(128, 2) k_chunk_acc(MsmGeom g, const Affine<Fq>* __restrict__ pts,
+// The inlined form needs 194 registers (2 blocks of 128 threads per SM; forcing it into 168 measured the same in round 1).
+// COMPACT: the mixed addition as real calls (XYZZ::madd_c, 138 registers, the loop stays in the instruction cache): what a
+// machine-filling launch wants (2^20 terms: 6.43 -> 5.98 ms, 0.93 of the multiplier pipe).  A launch that does not fill the
+// machine is bound by the latency of one thread's chain, where the inlined form (independent products overlap) is faster
+// (2^16 terms: 1.44 against 1.73 ms), so the host picks per launch.
+template <class Fq, bool COMPACT>
+__global__ void __launch_bounds__(128, COMPACT ? 3 : 2) k_chunk_acc(MsmGeom g, const Affine<Fq>* __restrict__ pts,
                                                    const uint32_t* __restrict__ sidx,
                                                    const uint32_t* __restrict__ bstart, const uint32_t* __restrict__ pstart,
                                                    XYZZ<Fq>* __restrict__ partials) {
@@ -216,7 +216,7 @@ __global__ void __launch_bounds__(128, 2) k_chunk_acc(MsmGeom g, const Affine<Fq
     uint32_t id = idx[e];
     Affine<Fq> P = load_vec_ro(pts + (id & 0x7fffffffu));
     if (id >> 31) P.y = P.y.neg();
-    acc.BP_CHUNK_MADD(P);
+    if (COMPACT) acc.madd_c(P); else acc.madd(P);
   }
   store_vec(out + ps[cur] + (t - bs[cur] / g.S), acc);
 }
@@ -355,8 +355,8 @@ __global__ void __launch_bounds__(128) k_reduce_l1(MsmGeom g, const uint32_t* __
   if (lo <= g.nbp - 1) {
     const uint32_t hi = min(lo + L1 - 1, g.nbp - 1);
     for (uint32_t b = hi; b >= lo; b--) {
-      if (pc[b]) { XYZZ<Fq> q = load_vec(in + ps[b]); run.add_inl(q); }      // k_merge left ONE sum per bucket
-      acc.add_inl(run);
+      if (pc[b]) { XYZZ<Fq> q = load_vec(in + ps[b]); run.add(q); }      // k_merge left ONE sum per bucket
+      acc.add(run);
     }
   }
   warp_weighted_sum(acc, run, g.lgL1);
@@ -699,7 +699,10 @@ int msm_run(bpgpu_ctx* ctx, const Affine<typename Curve::Fq>* d_points, const vo
   }
   {
     uint32_t threads = (uint32_t)g.W * g.nchunk;
-    k_chunk_acc<Fq><<<(threads + 127) / 128, 128, 0, st>>>(g, d_points, sidx, bstart, pstart, partials);
+    if (threads >= (uint32_t)ctx->sm_count * 3 * 128)           // at least one resident wave of the compact form: throughput bound
+      k_chunk_acc<Fq, true><<<(threads + 127) / 128, 128, 0, st>>>(g, d_points, sidx, bstart, pstart, partials);
+    else
+      k_chunk_acc<Fq, false><<<(threads + 127) / 128, 128, 0, st>>>(g, d_points, sidx, bstart, pstart, partials);
     tm.mark("chunk_acc");
   }
   tm.mark("giant");                          // (kept as a stage name: its work now rides the merge launch)
