@@ -187,7 +187,7 @@ __device__ __forceinline__ uint32_t bucket_of(const uint32_t* __restrict__ bs, u
 // machine is bound by the latency of one thread's chain, where the inlined form (independent products overlap) is faster
 // (2^16 terms: 1.44 against 1.73 ms), so the host picks per launch.
 template <class Fq, bool COMPACT>
-__global__ void __launch_bounds__(128, COMPACT ? 3 : 2) k_chunk_acc(MsmGeom g, const Affine<Fq>* __restrict__ pts,
+__global__ void __launch_bounds__(128, COMPACT ? 4 : 2) k_chunk_acc(MsmGeom g, const Affine<Fq>* __restrict__ pts,
                                                    const uint32_t* __restrict__ sidx,
                                                    const uint32_t* __restrict__ bstart, const uint32_t* __restrict__ pstart,
                                                    XYZZ<Fq>* __restrict__ partials) {
