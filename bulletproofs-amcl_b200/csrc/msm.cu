@@ -182,8 +182,8 @@ __device__ __forceinline__ uint32_t bucket_of(const uint32_t* __restrict__ bs, u
 }
 
 // The inlined form needs 194 registers (2 blocks of 128 threads per SM; forcing it into 168 measured the same in round 1).
-// COMPACT: the mixed addition as real calls (XYZZ::madd_c, 138 registers, the loop stays in the instruction cache): what a
-// machine-filling launch wants (2^20 terms: 6.43 -> 5.98 ms, 0.93 of the multiplier pipe).  A launch that does not fill the
+// COMPACT: the mixed addition as real calls (XYZZ::madd_c, 128 registers = 4 blocks per SM, the loop stays in the instruction
+// cache): what a machine-filling launch wants (2^20 terms: 6.43 -> 5.80 ms, 0.955 of the multiplier pipe).  A launch that does not fill the
 // machine is bound by the latency of one thread's chain, where the inlined form (independent products overlap) is faster
 // (2^16 terms: 1.44 against 1.73 ms), so the host picks per launch.
 template <class Fq, bool COMPACT>
